@@ -1,0 +1,239 @@
+/* sde4b200.h -- C-ABI of libsde4b200.so, the B200 (sm_100a) implementation of the
+ * sde4mbrl hot path: batched Euler-Maruyama particle rollouts of the controlled
+ * neural SDE and the fused cost + reverse-mode pass the APG-MPC solver needs.
+ *
+ * The reference (wuwushrek/sde4mbrl) is pure Python/JAX and has no FFI of its own;
+ * each entry point below names the reference interface it replaces (paths relative
+ * to the reference root).  This is the set of symbols an XLA custom-call /
+ * jax.ffi shim (or ctypes, as in sde4mbrl_b200/_lib.py) binds -- see INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C, POD structs, device pointers unless stated, caller owns every
+ *     buffer; the library allocates nothing persistent and keeps no global
+ *     mutable state except a thread-local error string;
+ *   - all launchers are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return 0 on success, a negative sde4_status otherwise; the message is
+ *     available from sde4_last_error();
+ *   - "samples" g = p*N + n enumerate (problem p, particle n); every per-sample
+ *     array is SAMPLE-MINOR (g is the fastest index) so that a warp's accesses
+ *     coalesce: xevol[H+1][x_rows][G], noise[H][n_x][G].
+ *     The reference's logical [P, N, H+1, n_x] array is the strided view
+ *     (stride_p=N, stride_n=1, stride_t=x_rows*G, stride_i=G) of that buffer.
+ */
+#ifndef SDE4B200_H_
+#define SDE4B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDE4_ABI_VERSION 1
+#define SDE4_MAX_NX 16
+#define SDE4_MAX_NU 8
+#define SDE4_MAX_NOPT 24
+
+typedef enum sde4_status {
+  SDE4_OK = 0,
+  SDE4_ERR_INVALID = -1,      /* bad argument (null pointer, negative size ...)      */
+  SDE4_ERR_UNSUPPORTED = -2,  /* model / architecture / option has no compiled kernel */
+  SDE4_ERR_CUDA = -3,         /* CUDA runtime error (message has the cudaError)       */
+  SDE4_ERR_WORKSPACE = -4     /* workspace too small                                   */
+} sde4_status;
+
+/* Which ControlledSDE subclass (sde4mbrl/nsde.py:134) the descriptor describes. */
+typedef enum sde4_model_id {
+  SDE4_MODEL_MSD = 1,       /* sde4mbrlExamples/mass_spring_damper/mass_spring_model.py:21-123 */
+  SDE4_MODEL_CARTPOLE = 2,  /* sde4mbrlExamples/cartpole/cartpole_sde.py:20-106               */
+  SDE4_MODEL_ROTOR = 3      /* sde4mbrlExamples/rotor_uav/sde_rotor_model.py:121-458          */
+} sde4_model_id;
+
+typedef enum sde4_act { SDE4_ACT_NONE = 0, SDE4_ACT_TANH = 1, SDE4_ACT_SWISH = 2 } sde4_act;
+
+/* jax.random stream layout (jax_threefry_partitionable False / True). */
+typedef enum sde4_rng_mode { SDE4_RNG_ORIGINAL = 0, SDE4_RNG_PARTITIONABLE = 1 } sde4_rng_mode;
+
+/* Where the Brownian increments dw[H][n_x] of each sample come from. */
+typedef enum sde4_noise_mode {
+  SDE4_NOISE_NONE = 0,      /* ODE: diffusion term skipped                                    */
+  SDE4_NOISE_THREEFRY = 1,  /* in-kernel threefry2x32, bit-exact with jax.random (see rng_*)  */
+  SDE4_NOISE_GIVEN = 2      /* caller-supplied standard normals, noise[H][n_x][G]             */
+} sde4_noise_mode;
+
+/* model flags */
+#define SDE4_MSD_CONTROL       (1 << 0)  /* params['control']            mass_spring_model.py:54 */
+#define SDE4_MSD_GROUND_TRUTH  (1 << 1)  /* params['ground_truth']       :58                     */
+#define SDE4_MSD_SIDE_INFO     (1 << 2)  /* params['include_side_info']  :80                     */
+#define SDE4_CART_SIDE_INFO    (1 << 0)  /* params['side_info']          cartpole_sde.py:70      */
+#define SDE4_ROTOR_AERO_DRAG   (1 << 0)  /* params['aero_drag_effect']   sde_rotor_model.py:322  */
+
+/* hk.nets.MLP with exactly two hidden layers (every shipped config):
+ * n_in -> h1 -> h2 -> n_out, activation after the two hidden layers only.
+ * n_in == 0 means "network absent". */
+typedef struct sde4_net_desc {
+  int32_t n_in, h1, h2, n_out, act;
+} sde4_net_desc;
+
+/* Static + numeric description of one nSDE model.  Everything that is NOT a
+ * learnable parameter lives here (it comes from the reference's `params_model`
+ * dict); learnable parameters come in the packed `params` block, laid out by
+ * sde4_param_layout(). */
+typedef struct sde4_model_desc {
+  int32_t model_id;        /* sde4_model_id                                         */
+  int32_t n_x, n_u;        /* solver state dim and control dim                      */
+  int32_t flags;           /* SDE4_<MODEL>_* bits                                   */
+  sde4_net_desc density;   /* diffusion_density_nn.density_nn   nsde.py:384-390     */
+  sde4_net_desc net_a;     /* MSD: Fres; cartpole/rotor: res_forces                 */
+  sde4_net_desc net_b;     /* cartpole: control_nn; rotor: res_moments              */
+  uint32_t noise_in_mask;  /* bit i: reduced_state[i] feeds the density net :353,361*/
+  uint32_t noise_out_mask; /* bit i: state i is scaled by eta (others by 1)  :356,363*/
+  uint32_t net_a_in_mask;  /* rotor: residual_forces.active_indx over (v_b, w) :317 */
+  uint32_t net_b_in_mask;  /* rotor: residual_moments.active_indx             :348 */
+  int32_t n_scaler;        /* 0: no scaler_nn; else 2*popcount(noise_out_mask) :372 */
+  float aggr;              /* density_nn.aggressiveness                      :398   */
+  float noise_prior[SDE4_MAX_NX];       /* noise_prior_params                        */
+  float inv_state_scaling[SDE4_MAX_NX]; /* 1/state_scaling (1 if absent)             */
+  float inv_red_scale;     /* rotor: 1/max(state_scaling) sde_rotor_model.py:139-144;
+                              cartpole: 1/state_scaling[-1] cartpole_sde.py:41      */
+  float cfloat[8];         /* MSD: mass,k,b ; cartpole: nn_out_scale[2]; rotor: gravity */
+} sde4_model_desc;
+
+/* Stage / terminal cost evaluated inside the cost+gradient kernel. */
+typedef enum sde4_cost_kind {
+  SDE4_COST_NONE = 0,
+  SDE4_COST_ROTOR_TRACK = 1, /* one_step_cost_f, rotor_uav/sde_mpc_design.py:73-132   */
+  SDE4_COST_QUADRATIC = 2    /* sum w_i (phi(x)-phi(xref))_i^2 + sum r_j (u-uref)_j^2 */
+} sde4_cost_kind;
+
+typedef enum sde4_constr_mode {
+  SDE4_CONSTR_NONE = 0,
+  SDE4_CONSTR_NOPROX = 1,   /* constr_cost_noprox   nsde.py:1400-1410 */
+  SDE4_CONSTR_WITHPROX = 2  /* constr_cost_withprox nsde.py:1413-1419 */
+} sde4_constr_mode;
+
+typedef struct sde4_cost_desc {
+  int32_t kind;              /* sde4_cost_kind                                         */
+  int32_t feat;              /* QUADRATIC: 0 identity, 1 cartpole [x,xd,sin,cos,thd]   */
+  uint32_t sig_mask;         /* ROTOR: bit g (0 p,1 v,2 q,3 w,4 u): '<g>err_sig' given */
+  int32_t use_res_sig;       /* ROTOR: 'res_sig' = (lo, mult) given                    */
+  float res_mult;            /* 'res_mult' (default 1)                                 */
+  float res_sig_lo, res_sig_mult;
+  float w_x[SDE4_MAX_NX];    /* ROTOR: perr(0-2) verr(3-5) qerr(7-9) werr(10-12); QUADRATIC: feature weights */
+  float w_x_sig[SDE4_MAX_NX];
+  float w_u[SDE4_MAX_NU];    /* 'uerr' broadcast to n_u                                */
+  float w_u_sig[SDE4_MAX_NU];
+  float uref[SDE4_MAX_NU];
+  /* state constraints (nsde.py:75-130, 1392-1470) */
+  int32_t constr_mode;       /* sde4_constr_mode                                       */
+  int32_t n_slack;           /* extra opt columns (WITHPROX), else 0                   */
+  int32_t slack_col[SDE4_MAX_NX]; /* state i -> slack column k, or -1 if unconstrained */
+  float pen[SDE4_MAX_NX], lb[SDE4_MAX_NX], ub[SDE4_MAX_NX], slack_scale[SDE4_MAX_NX];
+  float constr_weight;
+  /* particle-independent control slew term of augmented_cost (sde_mpc_design.py:141-148) */
+  int32_t has_slew;
+  float u_slew_coeff[SDE4_MAX_NU];
+} sde4_cost_desc;
+
+/* ---- rollout: create_sampling_fn(...).multi_sampling, sde4mbrl/nsde.py:1024-1028
+ *      -> sample_sde (:544-556) -> euler_maruyama, sde4mbrl/sde_solver.py:243-317.
+ *      One call = P problems x N particles x H steps. */
+typedef struct sde4_rollout_args {
+  int32_t struct_size;          /* sizeof(sde4_rollout_args), ABI check               */
+  int32_t P, N, H;
+  const float* params;          /* packed learnable block (sde4_param_layout), 16B aligned */
+  const float* y0;              /* [P][n_x] initial observation (= state, identity encoder) */
+  const float* u;               /* controls; element (p,t,j) at u[p*u_stride_p + t*u_stride_t + j*u_stride_j] */
+  int64_t u_stride_p, u_stride_t, u_stride_j;
+  const float* dt;              /* [H] time steps (compute_timesteps, nsde.py:15-40)  */
+  const uint32_t* key;          /* jax-layout keys uint32[2]; problem p uses key + p*key_stride_p */
+  int64_t key_stride_p;         /* 0: one key shared by all problems, 2: one per problem */
+  int32_t rng_mode;             /* sde4_rng_mode                                      */
+  int32_t noise_mode;           /* sde4_noise_mode                                    */
+  const float* noise;           /* NOISE_GIVEN: [H][n_x][G]                           */
+  float* xevol;                 /* out [H+1][x_rows][G]                               */
+  int32_t x_rows;               /* >= n_x (rows beyond n_x are left untouched)        */
+  int32_t block_threads;        /* 0 = library heuristic                              */
+} sde4_rollout_args;
+
+int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, void* stream);
+
+/* ---- cost + gradient: create_online_cost_sampling_fn(...).multi_sampling,
+ *      sde4mbrl/nsde.py:1485-1527,1576-1586 and jax.value_and_grad of it as used by
+ *      sde4mbrl/apg.py:82,224; stage cost = one_step_cost_f, control slew =
+ *      augmented_cost (rotor_uav/sde_mpc_design.py:73-167).
+ *      cost[p] = mean_n sum_t 0.5*dt_t*(c_t + c_{t+1}) (+ terminal) (+ slew(opt_p));
+ *      grad[p] = d cost[p] / d opt[p]   (same strides as opt). */
+typedef struct sde4_cost_args {
+  int32_t struct_size;
+  int32_t P, N, H;
+  const float* params;
+  const float* y0;              /* [P][n_x]                                           */
+  const float* opt;             /* optimisation variables, n_opt = n_u + n_slack columns */
+  int64_t opt_stride_p, opt_stride_t, opt_stride_j;
+  const float* dt;              /* [H]                                                */
+  const float* xref;            /* reference (p,t,i) at xref[p*xref_stride_p + t*n_x + i], t in [0,H] */
+  int64_t xref_stride_p;        /* 0: shared by all problems                          */
+  const uint32_t* key;
+  int64_t key_stride_p;
+  int32_t rng_mode, noise_mode;
+  const float* noise;           /* NOISE_GIVEN: [H][n_x][G]                           */
+  const sde4_cost_desc* stage;  /* HOST pointer, copied at launch                     */
+  const sde4_cost_desc* terminal; /* HOST pointer or NULL                             */
+  float* cost;                  /* out [P]                                            */
+  float* grad;                  /* out, same indexing as opt; NULL = value only       */
+  float* xtraj;                 /* out [H+1][n_x+1][G] (row n_x = stage cost) or NULL */
+  void* workspace;              /* >= sde4_cost_workspace_bytes(...)                   */
+  size_t workspace_bytes;
+  int32_t block_threads;
+} sde4_cost_args;
+
+size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_t N, int32_t H,
+                                 int32_t n_slack, int32_t want_grad, int32_t have_xtraj);
+int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* args, void* stream);
+
+/* ---- RNG self-test: jax.random.{split, bits, normal} (call sites
+ *      sde4mbrl/sde_solver.py:276,277,283; sde4mbrl/nsde.py:1026,1581).
+ *      out[i] = element (offset+i) of random_bits(key, (total,)), uint32, bit-exact. */
+int sde4_rng_bits(const uint32_t* key_host, uint64_t total, uint64_t offset, uint64_t count,
+                  int32_t rng_mode, uint32_t* out, void* stream);
+/* out[i] = element (offset+i) of jax.random.normal(key, (total,)), float32 */
+int sde4_rng_normal(const uint32_t* key_host, uint64_t total, uint64_t offset, uint64_t count,
+                    int32_t rng_mode, float* out, void* stream);
+/* out[num][2] = jax.random.split(key, num); key_dev is a DEVICE uint32[2] */
+int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint32_t* out, void* stream);
+
+/* ---- layout of the packed parameter block -------------------------------------
+ * Returns the number of floats of the block for `model` (<0 on error).  The
+ * order is: model scalars, scaler vector, density net, net_a, net_b; every
+ * tensor starts on a 4-float boundary; a layer is w[in][out4] (row-major, as
+ * haiku stores it, with `out` padded up to a multiple of 4 with zeros) followed by
+ * b[out4].  If `offsets` is non-NULL it receives, in floats:
+ *   [0] scalars  [1] scaler  [2] density  [3] net_a  [4] net_b  [5] total.
+ * Rotor scalars (16): mass,Ixx,Iyy,Izz,Lmx,Lmy,CoeffDrag, c3,c2,c1,c0 (motor
+ * polynomial, highest power first), aero_kdx,kdy,kdz,kh, pad. */
+int sde4_param_layout(const sde4_model_desc* model, int32_t* offsets /*[6] or NULL*/);
+
+/* 1 if a compiled specialisation exists for this architecture, else 0. */
+int sde4_model_supported(const sde4_model_desc* model);
+/* Human-readable list of compiled architectures (static string). */
+const char* sde4_supported_archs(void);
+
+const char* sde4_last_error(void);
+int sde4_version(void);
+/* sizeof() of the four POD structs, in the order model_desc, cost_desc, rollout_args, cost_args
+ * (lets a foreign-language binding verify its struct layout at load time). */
+void sde4_struct_sizes(int32_t out[4]);
+
+/* ---- FP32 FMA micro-benchmark (roofline denominator) ---------------
+ * Runs `iters` dependent-chain-free FFMA (variant 0) / packed fma.rn.f32x2
+ * (variant 1) per thread on `blocks` x `threads`; writes nothing but a checksum.
+ * Returns the flop count through *flops; time it with events on `stream`. */
+int sde4_fma_peak(int32_t variant, int32_t blocks, int32_t threads, int32_t iters, float* sink,
+                  double* flops, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDE4B200_H_ */

@@ -1,0 +1,141 @@
+"""ctypes binding of ``libsde4b200.so`` (the C-ABI declared in ``include/sde4b200.h``).
+
+This is the binding used in this image (no jax / XLA FFI headers available); the
+XLA-FFI stub a reference maintainer would add is shown in ``INTEGRATION.md``.
+The product path FAILS LOUDLY when the CUDA library is missing -- there is no
+CPU fallback anywhere in this package.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsde4b200.so")
+
+MAX_NX, MAX_NU, MAX_NOPT = 16, 8, 24
+
+MODEL_MSD, MODEL_CARTPOLE, MODEL_ROTOR = 1, 2, 3
+ACT_NONE, ACT_TANH, ACT_SWISH = 0, 1, 2
+RNG_ORIGINAL, RNG_PARTITIONABLE = 0, 1
+NOISE_NONE, NOISE_THREEFRY, NOISE_GIVEN = 0, 1, 2
+MSD_CONTROL, MSD_GROUND_TRUTH, MSD_SIDE_INFO = 1, 2, 4
+CART_SIDE_INFO = 1
+ROTOR_AERO_DRAG = 1
+COST_NONE, COST_ROTOR_TRACK, COST_QUADRATIC = 0, 1, 2
+CONSTR_NONE, CONSTR_NOPROX, CONSTR_WITHPROX = 0, 1, 2
+
+
+class NetDesc(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("h1", C.c_int32), ("h2", C.c_int32), ("n_out", C.c_int32), ("act", C.c_int32)]
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [("model_id", C.c_int32), ("n_x", C.c_int32), ("n_u", C.c_int32), ("flags", C.c_int32),
+                ("density", NetDesc), ("net_a", NetDesc), ("net_b", NetDesc),
+                ("noise_in_mask", C.c_uint32), ("noise_out_mask", C.c_uint32),
+                ("net_a_in_mask", C.c_uint32), ("net_b_in_mask", C.c_uint32),
+                ("n_scaler", C.c_int32), ("aggr", C.c_float),
+                ("noise_prior", C.c_float * MAX_NX), ("inv_state_scaling", C.c_float * MAX_NX),
+                ("inv_red_scale", C.c_float), ("cfloat", C.c_float * 8)]
+
+
+class CostDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("feat", C.c_int32), ("sig_mask", C.c_uint32), ("use_res_sig", C.c_int32),
+                ("res_mult", C.c_float), ("res_sig_lo", C.c_float), ("res_sig_mult", C.c_float),
+                ("w_x", C.c_float * MAX_NX), ("w_x_sig", C.c_float * MAX_NX),
+                ("w_u", C.c_float * MAX_NU), ("w_u_sig", C.c_float * MAX_NU), ("uref", C.c_float * MAX_NU),
+                ("constr_mode", C.c_int32), ("n_slack", C.c_int32), ("slack_col", C.c_int32 * MAX_NX),
+                ("pen", C.c_float * MAX_NX), ("lb", C.c_float * MAX_NX), ("ub", C.c_float * MAX_NX),
+                ("slack_scale", C.c_float * MAX_NX), ("constr_weight", C.c_float),
+                ("has_slew", C.c_int32), ("u_slew_coeff", C.c_float * MAX_NU)]
+
+    def __init__(self, *a, **k):
+        super().__init__(*a, **k)
+        for i in range(MAX_NX):
+            self.slack_col[i] = -1
+        self.res_mult = 1.0
+        self.constr_weight = 1.0
+
+
+class RolloutArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("P", C.c_int32), ("N", C.c_int32), ("H", C.c_int32),
+                ("params", C.c_void_p), ("y0", C.c_void_p), ("u", C.c_void_p),
+                ("u_stride_p", C.c_int64), ("u_stride_t", C.c_int64), ("u_stride_j", C.c_int64),
+                ("dt", C.c_void_p), ("key", C.c_void_p), ("key_stride_p", C.c_int64),
+                ("rng_mode", C.c_int32), ("noise_mode", C.c_int32), ("noise", C.c_void_p),
+                ("xevol", C.c_void_p), ("x_rows", C.c_int32), ("block_threads", C.c_int32)]
+
+
+class CostArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("P", C.c_int32), ("N", C.c_int32), ("H", C.c_int32),
+                ("params", C.c_void_p), ("y0", C.c_void_p), ("opt", C.c_void_p),
+                ("opt_stride_p", C.c_int64), ("opt_stride_t", C.c_int64), ("opt_stride_j", C.c_int64),
+                ("dt", C.c_void_p), ("xref", C.c_void_p), ("xref_stride_p", C.c_int64),
+                ("key", C.c_void_p), ("key_stride_p", C.c_int64),
+                ("rng_mode", C.c_int32), ("noise_mode", C.c_int32), ("noise", C.c_void_p),
+                ("stage", C.POINTER(CostDesc)), ("terminal", C.POINTER(CostDesc)),
+                ("cost", C.c_void_p), ("grad", C.c_void_p), ("xtraj", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("block_threads", C.c_int32)]
+
+
+EXPORTED_SYMBOLS = (
+    "sde4_rollout", "sde4_cost_workspace_bytes", "sde4_cost_grad", "sde4_rng_bits", "sde4_rng_normal",
+    "sde4_rng_split", "sde4_param_layout", "sde4_model_supported", "sde4_supported_archs",
+    "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_fma_peak",
+)
+
+_lib = None
+
+
+class Sde4Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Sde4Error(
+            "libsde4b200.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C sde4mbrl_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.sde4_rollout.argtypes = [C.POINTER(ModelDesc), C.POINTER(RolloutArgs), C.c_void_p]
+    lib.sde4_rollout.restype = C.c_int
+    lib.sde4_cost_workspace_bytes.argtypes = [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                              C.c_int32, C.c_int32]
+    lib.sde4_cost_workspace_bytes.restype = C.c_size_t
+    lib.sde4_cost_grad.argtypes = [C.POINTER(ModelDesc), C.POINTER(CostArgs), C.c_void_p]
+    lib.sde4_cost_grad.restype = C.c_int
+    for name in ("sde4_rng_bits", "sde4_rng_normal"):
+        fn = getattr(lib, name)
+        fn.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int
+    lib.sde4_rng_split.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.sde4_rng_split.restype = C.c_int
+    lib.sde4_param_layout.argtypes = [C.POINTER(ModelDesc), C.POINTER(C.c_int32)]
+    lib.sde4_param_layout.restype = C.c_int
+    lib.sde4_model_supported.argtypes = [C.POINTER(ModelDesc)]
+    lib.sde4_model_supported.restype = C.c_int
+    lib.sde4_supported_archs.restype = C.c_char_p
+    lib.sde4_last_error.restype = C.c_char_p
+    lib.sde4_version.restype = C.c_int
+    lib.sde4_fma_peak.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_double),
+                                  C.c_void_p]
+    lib.sde4_fma_peak.restype = C.c_int
+    sizes = (C.c_int32 * 4)()
+    lib.sde4_struct_sizes(sizes)
+    mine = [C.sizeof(ModelDesc), C.sizeof(CostDesc), C.sizeof(RolloutArgs), C.sizeof(CostArgs)]
+    if list(sizes) != mine:
+        raise Sde4Error("ABI mismatch between _lib.py and libsde4b200.so: %s vs %s" % (mine, list(sizes)))
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise Sde4Error("libsde4b200: error %d: %s" % (rc, load().sde4_last_error().decode()))
+
+
+def last_error():
+    return load().sde4_last_error().decode()

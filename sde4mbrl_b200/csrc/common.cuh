@@ -1,0 +1,226 @@
+// common.cuh -- device math, threefry2x32 and staging helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/sde4b200.h"
+
+#define SDE4_DEV __device__ __forceinline__
+#define SDE4_HD __host__ __device__ __forceinline__
+
+namespace sde4 {
+
+// ----------------------------------------------------------------------------
+// compile-time helpers
+// ----------------------------------------------------------------------------
+SDE4_HD constexpr int popc(uint32_t m) {
+  int c = 0;
+  for (int i = 0; i < 32; ++i) c += (m >> i) & 1u;
+  return c;
+}
+// index of the k-th set bit of m (k < popc(m))
+SDE4_HD constexpr int nth_bit(uint32_t m, int k) {
+  int c = 0;
+  for (int i = 0; i < 32; ++i) {
+    if ((m >> i) & 1u) {
+      if (c == k) return i;
+      ++c;
+    }
+  }
+  return -1;
+}
+SDE4_HD constexpr int up4(int n) { return (n + 3) & ~3; }
+
+// ----------------------------------------------------------------------------
+// activations.  value h = act(a), derivative d = act'(a)
+// ----------------------------------------------------------------------------
+SDE4_DEV float fast_rcp(float x) { return __fdividef(1.0f, x); }
+
+SDE4_DEV float sigmoidf_(float a) { return fast_rcp(1.0f + __expf(-a)); }
+
+// Rational tanh on [-7.99, 7.99] (the float approximation Eigen / XLA:CPU evaluate:
+// odd degree-13 numerator over even degree-6 denominator), ~2 ulp, branch free.
+SDE4_DEV float tanhf_(float a) {
+  const float c = 7.99881172180175781f;
+  float x = fminf(fmaxf(a, -c), c);
+  float x2 = x * x;
+  float p = -2.76076847742355e-16f;
+  p = fmaf(p, x2, 2.00018790482477e-13f);
+  p = fmaf(p, x2, -8.60467152213735e-11f);
+  p = fmaf(p, x2, 5.12229709037114e-08f);
+  p = fmaf(p, x2, 1.48572235717979e-05f);
+  p = fmaf(p, x2, 6.37261928875436e-04f);
+  p = fmaf(p, x2, 4.89352455891786e-03f);
+  p = p * x;
+  float q = 1.19825839466702e-06f;
+  q = fmaf(q, x2, 1.18534705686654e-04f);
+  q = fmaf(q, x2, 2.26843463243900e-03f);
+  q = fmaf(q, x2, 4.89352518554385e-03f);
+  return __fdividef(p, q);
+}
+
+template <int ACT>
+SDE4_DEV float act_fwd(float a) {
+  if (ACT == SDE4_ACT_TANH) return tanhf_(a);
+  if (ACT == SDE4_ACT_SWISH) return a * sigmoidf_(a);
+  return a;
+}
+// value and derivative together (shares the transcendental)
+template <int ACT>
+SDE4_DEV void act_fwd_d(float a, float& h, float& d) {
+  if (ACT == SDE4_ACT_TANH) {
+    h = tanhf_(a);
+    d = fmaf(-h, h, 1.0f);
+  } else if (ACT == SDE4_ACT_SWISH) {
+    float s = sigmoidf_(a);
+    h = a * s;
+    d = fmaf(h, 1.0f - s, s);  // s + a*s*(1-s)
+  } else {
+    h = a;
+    d = 1.0f;
+  }
+}
+
+// ----------------------------------------------------------------------------
+// threefry2x32 (20 rounds) and the jax.random layouts
+// ----------------------------------------------------------------------------
+SDE4_HD uint32_t rotl32(uint32_t x, int r) {
+#ifdef __CUDA_ARCH__
+  return __funnelshift_l(x, x, r);
+#else
+  return (x << r) | (x >> (32 - r));
+#endif
+}
+
+SDE4_HD void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t& o0,
+                          uint32_t& o1) {
+  const uint32_t k2 = k0 ^ k1 ^ 0x1BD11BDAu;
+  uint32_t x0 = c0 + k0, x1 = c1 + k1;
+#define SDE4_TF_R(r)   \
+  x0 += x1;            \
+  x1 = rotl32(x1, r);  \
+  x1 ^= x0;
+  SDE4_TF_R(13) SDE4_TF_R(15) SDE4_TF_R(26) SDE4_TF_R(6)
+  x0 += k1; x1 += k2 + 1u;
+  SDE4_TF_R(17) SDE4_TF_R(29) SDE4_TF_R(16) SDE4_TF_R(24)
+  x0 += k2; x1 += k0 + 2u;
+  SDE4_TF_R(13) SDE4_TF_R(15) SDE4_TF_R(26) SDE4_TF_R(6)
+  x0 += k0; x1 += k1 + 3u;
+  SDE4_TF_R(17) SDE4_TF_R(29) SDE4_TF_R(16) SDE4_TF_R(24)
+  x0 += k1; x1 += k2 + 4u;
+  SDE4_TF_R(13) SDE4_TF_R(15) SDE4_TF_R(26) SDE4_TF_R(6)
+  x0 += k2; x1 += k0 + 5u;
+#undef SDE4_TF_R
+  o0 = x0;
+  o1 = x1;
+}
+
+// element j of random_bits(key, (total,)) -- 32-bit, both jax layouts
+SDE4_HD uint32_t jax_bits(uint32_t k0, uint32_t k1, uint64_t j, uint64_t total, int mode) {
+  uint32_t o0, o1;
+  if (mode == SDE4_RNG_PARTITIONABLE) {
+    threefry2x32(k0, k1, (uint32_t)(j >> 32), (uint32_t)j, o0, o1);
+    return o0 ^ o1;
+  }
+  // original: counts iota(total) (padded with one 0 if odd) hashed by halves
+  const uint64_t half = (total + 1) >> 1;
+  if (j < half) {
+    const uint64_t hi = j + half;
+    threefry2x32(k0, k1, (uint32_t)j, hi < total ? (uint32_t)hi : 0u, o0, o1);
+    return o0;
+  }
+  threefry2x32(k0, k1, (uint32_t)(j - half), (uint32_t)j, o0, o1);
+  return o1;
+}
+
+// child `i` of jax.random.split(key, num)
+SDE4_HD void jax_split(uint32_t k0, uint32_t k1, uint32_t i, uint32_t num, int mode, uint32_t& c0,
+                       uint32_t& c1) {
+  if (mode == SDE4_RNG_PARTITIONABLE) {
+    threefry2x32(k0, k1, 0u, i, c0, c1);
+    return;
+  }
+  c0 = jax_bits(k0, k1, 2ull * i, 2ull * num, SDE4_RNG_ORIGINAL);
+  c1 = jax_bits(k0, k1, 2ull * i + 1, 2ull * num, SDE4_RNG_ORIGINAL);
+}
+
+// XLA float32 erf_inv (Giles) -- see SURVEY appendix F
+SDE4_DEV float erfinv_f32(float x) {
+  float w = -__logf(fmaf(-x, x, 1.0f));
+  float p;
+  if (w < 5.0f) {
+    w = w - 2.5f;
+    p = 2.81022636e-08f;
+    p = fmaf(p, w, 3.43273939e-07f);
+    p = fmaf(p, w, -3.5233877e-06f);
+    p = fmaf(p, w, -4.39150654e-06f);
+    p = fmaf(p, w, 0.00021858087f);
+    p = fmaf(p, w, -0.00125372503f);
+    p = fmaf(p, w, -0.00417768164f);
+    p = fmaf(p, w, 0.246640727f);
+    p = fmaf(p, w, 1.50140941f);
+  } else {
+    w = sqrtf(w) - 3.0f;
+    p = -0.000200214257f;
+    p = fmaf(p, w, 0.000100950558f);
+    p = fmaf(p, w, 0.00134934322f);
+    p = fmaf(p, w, -0.00367342844f);
+    p = fmaf(p, w, 0.00573950773f);
+    p = fmaf(p, w, -0.0076224613f);
+    p = fmaf(p, w, 0.00943887047f);
+    p = fmaf(p, w, 1.00167406f);
+    p = fmaf(p, w, 2.83297682f);
+  }
+  return p * x;
+}
+
+// jax.random.normal transform of one 32-bit word
+SDE4_DEV float bits_to_normal(uint32_t bits) {
+  const float lo = -0.99999994f;  // nextafter(-1, 0)
+  float u = __uint_as_float((bits >> 9) | 0x3F800000u) - 1.0f;
+  float v = fmaxf(lo, fmaf(u, 2.0f, lo));  // (hi - lo) rounds to exactly 2.0f in float32
+  return 1.41421356237309505f * erfinv_f32(v);
+}
+
+// Per-sample Brownian key: k_p = split(rng, N)[n] (nsde.py:1026,1581), then
+// rng_brownian = split(k_p, 2)[0] (sde_solver.py:276).
+SDE4_DEV void brownian_key(uint32_t r0, uint32_t r1, uint32_t n, uint32_t N, int mode, uint32_t& b0,
+                           uint32_t& b1) {
+  uint32_t p0, p1;
+  jax_split(r0, r1, n, N, mode, p0, p1);
+  jax_split(p0, p1, 0u, 2u, mode, b0, b1);
+}
+
+// ----------------------------------------------------------------------------
+// parameter staging: one 1-D bulk async copy (TMA engine, UBLKCP) global -> shared,
+// completion on an mbarrier.  nbytes must be a multiple of 16, both pointers 16B aligned.
+// ----------------------------------------------------------------------------
+SDE4_DEV void stage_params_bulk(float* smem_dst, const float* gsrc, uint32_t nbytes, uint64_t* mbar) {
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nbytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(gsrc), "r"(nbytes), "r"(bar)
+        : "memory");
+  }
+  // all threads wait for phase 0
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar)
+      : "memory");
+}
+
+}  // namespace sde4

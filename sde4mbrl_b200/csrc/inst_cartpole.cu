@@ -1,0 +1,21 @@
+// inst_cartpole.cu -- cartpole architectures (sde4mbrlExamples/cartpole/cartpole_sde.yaml:12-75
+// and the shipped my_models/cartpole_bb_*.pkl).
+#include "registry.cuh"
+namespace sde4 {
+using CartD32 = Net<3, 32, 32, 1, SWISH>;
+using CartD8 = Net<3, 8, 8, 1, SWISH>;
+using CartResSi = Net<3, 8, 24, 2, TANH>;
+using CartResBb = Net<4, 8, 24, 2, TANH>;
+using CartCtrl = Net<2, 6, 8, 2, TANH>;
+// noise inputs reduced_state[1,2,3], noise outputs states [1,3]
+using CartSiD32 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, SDE4_CART_SIDE_INFO, CartD32, 0xE, 0xA, true, CartResSi, 0, CartCtrl, 0>;
+using CartBbD32 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, CartD32, 0xE, 0xA, true, CartResBb, 0, NoNet, 0>;
+using CartBbD8 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, CartD8, 0xE, 0xA, true, CartResBb, 0, NoNet, 0>;
+using CartSiOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, SDE4_CART_SIDE_INFO, NoNet, 0, 0, false, CartResSi, 0, CartCtrl, 0>;
+using CartBbOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, NoNet, 0, 0, false, CartResBb, 0, NoNet, 0>;
+SDE4_REGISTER(cartpole_si_d32, CartpoleModel<CartSiD32>)
+SDE4_REGISTER(cartpole_bb_d32, CartpoleModel<CartBbD32>)
+SDE4_REGISTER(cartpole_bb_d8, CartpoleModel<CartBbD8>)
+SDE4_REGISTER(cartpole_si_ode, CartpoleModel<CartSiOde>)
+SDE4_REGISTER(cartpole_bb_ode, CartpoleModel<CartBbOde>)
+}  // namespace sde4

@@ -1,0 +1,120 @@
+// misc_kernels.cuh -- non-template kernels (K3 reduction, K0 RNG self-test, FMA peak);
+// included by sde4b200.cu only.
+#pragma once
+#include "kernels.cuh"
+
+namespace sde4 {
+
+// ----------------------------------------------------------------------------
+// K3: fixed-order reduction of the partials of each problem, 1/N, + control-slew term.
+// thread <-> (row = t*n_opt + j, p), p fastest.  Row index H*n_opt is the cost.
+// ----------------------------------------------------------------------------
+__global__ void k_reduce(const __grid_constant__ ReduceK a) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int rows = a.H * a.n_opt + 1;
+  if (idx >= (long long)rows * a.P) return;
+  const int p = (int)(idx % a.P);
+  const int row = (int)(idx / a.P);
+  const float invN = 1.0f / (float)a.N;
+  const float* op = a.opt + (size_t)p * a.o_sp;
+  if (row == a.H * a.n_opt) {
+    const float* src = a.cpart + (size_t)p * a.NP;
+    float s = 0.0f;
+    for (int k = 0; k < a.NP; ++k) s += src[k];
+    s *= invN;
+    if (a.has_slew) {  // sum_t sum_j coeff_j ((u_{t+1,j}-u_{t,j})/dt_t)^2 * res_mult
+      float sl = 0.0f;
+      for (int t = 0; t + 1 < a.H; ++t) {
+        const float idt = 1.0f / a.dt[t];
+        for (int j = 0; j < a.n_u; ++j) {
+          const float dv = (op[(size_t)(t + 1) * a.o_st + (size_t)j * a.o_sj] - op[(size_t)t * a.o_st + (size_t)j * a.o_sj]) * idt;
+          sl = fmaf(a.slew[j] * dv, dv, sl);
+        }
+      }
+      s = fmaf(sl, a.res_mult, s);
+    }
+    a.cost[p] = s;
+    return;
+  }
+  if (a.grad == nullptr) return;
+  const int t = row / a.n_opt, j = row - t * a.n_opt;
+  const float* src = a.gpart + (size_t)row * a.PW + (size_t)p * a.NP;
+  float s = 0.0f;
+  for (int k = 0; k < a.NP; ++k) s += src[k];
+  s *= invN;
+  if (a.has_slew && j < a.n_u) {
+    const float uj = op[(size_t)t * a.o_st + (size_t)j * a.o_sj];
+    float gsl = 0.0f;
+    if (t > 0) {
+      const float idt = 1.0f / a.dt[t - 1];
+      gsl += 2.0f * a.slew[j] * (uj - op[(size_t)(t - 1) * a.o_st + (size_t)j * a.o_sj]) * idt * idt;
+    }
+    if (t + 1 < a.H) {
+      const float idt = 1.0f / a.dt[t];
+      gsl -= 2.0f * a.slew[j] * (op[(size_t)(t + 1) * a.o_st + (size_t)j * a.o_sj] - uj) * idt * idt;
+    }
+    s = fmaf(gsl, a.res_mult, s);
+  }
+  a.grad[(size_t)p * a.o_sp + (size_t)t * a.o_st + (size_t)j * a.o_sj] = s;
+}
+
+// ----------------------------------------------------------------------------
+// K0: RNG self-test kernels
+// ----------------------------------------------------------------------------
+__global__ void k_rng_bits(uint32_t k0, uint32_t k1, unsigned long long total, unsigned long long offset,
+                           unsigned long long count, int mode, uint32_t* out, float* outf) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t b = jax_bits(k0, k1, offset + i, total, mode);
+  if (out) out[i] = b;
+  if (outf) outf[i] = bits_to_normal(b);
+}
+
+__global__ void k_rng_split(const uint32_t* key, int num, int mode, uint32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= num) return;
+  uint32_t c0, c1;
+  jax_split(key[0], key[1], (uint32_t)i, (uint32_t)num, mode, c0, c1);
+  out[2 * i] = c0;
+  out[2 * i + 1] = c1;
+}
+
+// ----------------------------------------------------------------------------
+// FP32 FMA peak micro-benchmark (roofline denominator)
+// ----------------------------------------------------------------------------
+template <int VARIANT>
+__global__ void __launch_bounds__(1024) k_fma_peak(int iters, float* sink) {
+  float acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (float)(threadIdx.x + i) * 1e-3f;
+  const float a = 1.000001f, b = 1e-7f;
+  if (VARIANT == 0) {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) acc[i] = fmaf(acc[i], a, b);
+    }
+  } else {
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 2) {
+        asm volatile(
+            "{\n"
+            ".reg .b64 ra, rb, rc;\n"
+            "mov.b64 ra, {%0, %1};\n"
+            "mov.b64 rb, {%2, %2};\n"
+            "mov.b64 rc, {%3, %3};\n"
+            "fma.rn.f32x2 ra, ra, rb, rc;\n"
+            "mov.b64 {%0, %1}, ra;\n"
+            "}\n"
+            : "+f"(acc[i]), "+f"(acc[i + 1])
+            : "f"(a), "f"(b));
+      }
+    }
+  }
+  float s = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456f) sink[0] = s;
+}
+
+}  // namespace sde4

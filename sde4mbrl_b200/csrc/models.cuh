@@ -1,0 +1,614 @@
+// models.cuh -- the three ControlledSDE subclasses of the reference as per-thread device
+// code: drift, distance-aware diffusion, projection, and their hand-derived
+// vector-Jacobian products (the reverse-mode pass APG differentiates through).
+//
+//   MassSpringDamper  sde4mbrlExamples/mass_spring_damper/mass_spring_model.py:21-123
+//   CartPoleSDE       sde4mbrlExamples/cartpole/cartpole_sde.py:20-106
+//   SDERotorModel     sde4mbrlExamples/rotor_uav/sde_rotor_model.py:121-458,
+//                     motor_models.py:21-95, rotor_uav/utils.py:13-63
+//   diffusion         sde4mbrl/nsde.py:298-449
+#pragma once
+#include "nets.cuh"
+
+namespace sde4 {
+
+// ----------------------------------------------------------------------------
+// Static architecture: everything that changes the *code* (sizes, activations,
+// index sets, structural flags).  Numeric constants come from sde4_model_desc.
+// ----------------------------------------------------------------------------
+template <int MODEL_, int NX_, int NU_, uint32_t FLAGS_, class DNet_, uint32_t NIN_MASK_, uint32_t NOUT_MASK_,
+          bool HAS_SCALER_, class NetA_, uint32_t A_MASK_, class NetB_, uint32_t B_MASK_>
+struct Arch {
+  static constexpr int MODEL = MODEL_, NX = NX_, NU = NU_;
+  static constexpr uint32_t FLAGS = FLAGS_, NIN_MASK = NIN_MASK_, NOUT_MASK = NOUT_MASK_, A_MASK = A_MASK_,
+                            B_MASK = B_MASK_;
+  using DNet = DNet_;
+  using NetA = NetA_;
+  using NetB = NetB_;
+  static constexpr bool HAS_DENSITY = DNet::PRESENT;
+  static constexpr bool HAS_SCALER = HAS_SCALER_ && HAS_DENSITY;
+  static constexpr int NO = popc(NOUT_MASK_);  // number of eta-scaled states
+  static constexpr int N_SCALER = HAS_SCALER ? 2 * NO : 0;
+  static constexpr int N_SCALARS = MODEL_ == SDE4_MODEL_ROTOR ? 16 : 0;
+  // packed parameter block
+  static constexpr int OFF_SCALARS = 0;
+  static constexpr int OFF_SCALER = OFF_SCALARS + N_SCALARS;
+  static constexpr int OFF_DENSITY = OFF_SCALER + up4(N_SCALER);
+  static constexpr int OFF_NET_A = OFF_DENSITY + DNet::SIZE;
+  static constexpr int OFF_NET_B = OFF_NET_A + NetA::SIZE;
+  static constexpr int PARAM_TOTAL = up4(OFF_NET_B + NetB::SIZE);
+  // derived per-block constants appended after the parameter image in shared memory
+  static constexpr int OFF_DERIVED = PARAM_TOTAL;
+  static constexpr int N_DERIVED = up4(2 * NO);
+  static constexpr int SMEM_FLOATS = PARAM_TOTAL + N_DERIVED;
+  static constexpr int MACS = DNet::MACS + NetA::MACS + NetB::MACS;
+
+  static bool matches(const sde4_model_desc& d) {
+    return d.model_id == MODEL && d.n_x == NX && d.n_u == NU && (uint32_t)d.flags == FLAGS &&
+           DNet::matches(d.density) && NetA::matches(d.net_a) && NetB::matches(d.net_b) &&
+           (!HAS_DENSITY || (d.noise_in_mask == NIN_MASK && d.noise_out_mask == NOUT_MASK)) &&
+           d.n_scaler == N_SCALER && (!NetA::PRESENT || d.net_a_in_mask == A_MASK) &&
+           (!NetB::PRESENT || d.net_b_in_mask == B_MASK);
+  }
+};
+
+// ----------------------------------------------------------------------------
+// quaternion algebra, [w, x, y, z]  (rotor_uav/utils.py:13-63)
+// ----------------------------------------------------------------------------
+struct Quat {
+  float w, x, y, z;
+};
+SDE4_DEV Quat qmul(const Quat& a, const Quat& b) {
+  Quat r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x;
+  r.z = a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w;
+  return r;
+}
+SDE4_DEV Quat qconj(const Quat& a) { return Quat{a.w, -a.x, -a.y, -a.z}; }
+SDE4_DEV Quat qvec(float x, float y, float z) { return Quat{0.0f, x, y, z}; }
+SDE4_DEV void qacc(Quat& a, const Quat& b) {
+  a.w += b.w;
+  a.x += b.x;
+  a.y += b.y;
+  a.z += b.z;
+}
+// For r = a (x) b (bilinear):  abar = rbar (x) conj(b),  bbar = conj(a) (x) rbar.
+
+// ----------------------------------------------------------------------------
+// Diffusion (nsde.py:298-449), shared by all models through Model::reduced_state.
+// Derived constants D[0..NO) = exp(scaler[k])*1e-7 (coeff), D[NO..2NO) = offset.
+// ----------------------------------------------------------------------------
+template <class M>
+struct Diffusion {
+  using A = typename M::A;
+  using DNet = typename A::DNet;
+  static constexpr int NX = A::NX, NO = A::NO;
+
+  SDE4_DEV static void gather_in(const float (&x)[NX], const sde4_model_desc& d, float (&z)[DNet::IN > 0 ? DNet::IN : 1]) {
+    float red[M::NR];
+    M::reduced_state(x, d, red);
+#pragma unroll
+    for (int k = 0; k < DNet::IN; ++k) z[k] = red[nth_bit(A::NIN_MASK, k)];
+  }
+
+  SDE4_DEV static float eta_of(const float* __restrict__ W, const sde4_model_desc& d, float dens, int k) {
+    float coeff = 0.0f, offs = 0.0f;
+    if constexpr (A::HAS_SCALER) {
+      coeff = W[A::OFF_DERIVED + k];
+      offs = W[A::OFF_DERIVED + NO + k];
+    }
+    return sigmoidf_((d.aggr + coeff) * dens - 7.0f + offs);  // nsde.py:426
+  }
+
+  // sig[i] = eta_full[i] * prior[i]
+  SDE4_DEV static void fwd(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                           float (&sig)[NX]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) sig[i] = d.noise_prior[i];  // non-noise outputs: eta = 1 (nsde.py:363)
+    if constexpr (A::HAS_DENSITY) {
+      float z[DNet::IN > 0 ? DNet::IN : 1];
+      gather_in(x, d, z);
+      float dens[1];
+      mlp_fwd<DNet>(W + A::OFF_DENSITY, z, dens);
+#pragma unroll
+      for (int k = 0; k < NO; ++k) sig[nth_bit(A::NOUT_MASK, k)] *= eta_of(W, d, dens[0], k);
+    }
+  }
+
+  // gx += (d sig / d x)^T vs      (sigma does not depend on u: control_dependent_noise unsupported)
+  SDE4_DEV static void vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                           const float (&vs)[NX], float (&gx)[NX]) {
+    if constexpr (!A::HAS_DENSITY) {
+      return;
+    } else {
+    float z[DNet::IN > 0 ? DNet::IN : 1];
+    gather_in(x, d, z);
+    float dens[1], d1[DNet::H1 > 0 ? DNet::H1 : 1], d2[DNet::H2 > 0 ? DNet::H2 : 1];
+    mlp_fwd_keep<DNet>(W + A::OFF_DENSITY, z, dens, d1, d2);
+    float gd[1] = {0.0f};
+#pragma unroll
+    for (int k = 0; k < NO; ++k) {
+      const int i = nth_bit(A::NOUT_MASK, k);
+      float coeff = 0.0f;
+      if constexpr (A::HAS_SCALER) coeff = W[A::OFF_DERIVED + k];
+      float e = eta_of(W, d, dens[0], k);
+      gd[0] = fmaf(vs[i] * d.noise_prior[i], e * (1.0f - e) * (d.aggr + coeff), gd[0]);
+    }
+    float gz[DNet::IN > 0 ? DNet::IN : 1];
+    mlp_bwd<DNet>(W + A::OFF_DENSITY, d1, d2, gd, gz);
+    float gred[M::NR];
+#pragma unroll
+    for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = gz[k];
+    M::reduced_state_vjp(x, d, gred, gx);
+    }
+  }
+
+  // prologue: threads compute exp(scaler)*1e-7 once per block (nsde.py:413)
+  SDE4_DEV static void derive(float* __restrict__ W) {
+    if constexpr (A::HAS_SCALER) {
+      for (int k = threadIdx.x; k < 2 * NO; k += blockDim.x) W[A::OFF_DERIVED + k] = expf(W[A::OFF_SCALER + k]) * 1e-7f;
+    }
+  }
+};
+
+// ----------------------------------------------------------------------------
+// Mass-spring-damper  (mass_spring_model.py:36-86)
+// ----------------------------------------------------------------------------
+template <class A_>
+struct MsdModel {
+  using A = A_;
+  static constexpr int NX = 2, NU = 1, NR = 2, NAUX = 0;
+  static constexpr bool GT = (A::FLAGS & SDE4_MSD_GROUND_TRUTH) != 0;
+  static constexpr bool SI = (A::FLAGS & SDE4_MSD_SIDE_INFO) != 0;
+  static constexpr bool CTRL = (A::FLAGS & SDE4_MSD_CONTROL) != 0;
+  using NetA = typename A::NetA;
+
+  SDE4_DEV static void reduced_state(const float (&x)[NX], const sde4_model_desc&, float (&r)[NR]) {
+    r[0] = x[0];
+    r[1] = x[1];
+  }
+  SDE4_DEV static void reduced_state_vjp(const float (&)[NX], const sde4_model_desc&, const float (&g)[NR],
+                                         float (&gx)[NX]) {
+    gx[0] += g[0];
+    gx[1] += g[1];
+  }
+
+  SDE4_DEV static void drift(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                             const float (&u)[NU], float (&f)[NX]) {
+    const float m = d.cfloat[0], k = d.cfloat[1], b = d.cfloat[2];
+    const float u0 = CTRL ? u[0] : 0.0f;
+    f[0] = x[1];
+    if constexpr (GT) {
+      f[1] = (u0 - k * x[0] - b * x[1]) / m;
+    } else if constexpr (SI) {
+      float in[1] = {x[1]}, out[1];
+      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      f[1] = (u0 - k * x[0] + out[0]) / m;
+    } else {
+      float in[2] = {x[0], x[1]}, out[1];
+      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      f[1] = out[0];
+    }
+  }
+
+  SDE4_DEV static void drift_vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                                 const float (&u)[NU], const float (&vf)[NX], float (&gx)[NX], float (&gu)[NU]) {
+    const float m = d.cfloat[0], k = d.cfloat[1], b = d.cfloat[2];
+    gx[1] += vf[0];
+    if constexpr (GT) {
+      const float s = vf[1] / m;
+      gx[0] -= k * s;
+      gx[1] -= b * s;
+      if constexpr (CTRL) gu[0] += s;
+    } else if constexpr (SI) {
+      const float s = vf[1] / m;
+      gx[0] -= k * s;
+      if constexpr (CTRL) gu[0] += s;
+      float in[1] = {x[1]}, go[1] = {s}, gi[1];
+      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+      gx[1] += gi[0];
+    } else {
+      float in[2] = {x[0], x[1]}, go[1] = {vf[1]}, gi[2];
+      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+      gx[0] += gi[0];
+      gx[1] += gi[1];
+    }
+  }
+
+  SDE4_DEV static void project(float (&)[NX], float&) {}
+  SDE4_DEV static void project_vjp(const float (&)[NX], float, float (&)[NX]) {}
+};
+
+// ----------------------------------------------------------------------------
+// Cartpole  (cartpole_sde.py:56-83); state [x, xdot, theta, thetadot]
+// ----------------------------------------------------------------------------
+template <class A_>
+struct CartpoleModel {
+  using A = A_;
+  static constexpr int NX = 4, NU = 1, NR = 4, NAUX = 0;
+  static constexpr bool SI = (A::FLAGS & SDE4_CART_SIDE_INFO) != 0;
+  using NetA = typename A::NetA;
+  using NetB = typename A::NetB;
+
+  // [xdot, sin th, cos th, thdot] / state_scaling[-1]   (cartpole_sde.py:41)
+  SDE4_DEV static void reduced_state(const float (&x)[NX], const sde4_model_desc& d, float (&r)[NR]) {
+    float s, c;
+    sincosf(x[2], &s, &c);
+    r[0] = x[1] * d.inv_red_scale;
+    r[1] = s * d.inv_red_scale;
+    r[2] = c * d.inv_red_scale;
+    r[3] = x[3] * d.inv_red_scale;
+  }
+  SDE4_DEV static void reduced_state_vjp(const float (&x)[NX], const sde4_model_desc& d, const float (&g)[NR],
+                                         float (&gx)[NX]) {
+    float s, c;
+    sincosf(x[2], &s, &c);
+    gx[1] += g[0] * d.inv_red_scale;
+    gx[2] += (g[1] * c - g[2] * s) * d.inv_red_scale;
+    gx[3] += g[3] * d.inv_red_scale;
+  }
+
+  SDE4_DEV static void drift(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                             const float (&u)[NU], float (&f)[NX]) {
+    float s, c;
+    sincosf(x[2], &s, &c);
+    const float thd_sc = x[3] * d.inv_state_scaling[3];
+    const float sc0 = d.cfloat[0], sc1 = d.cfloat[1];
+    f[0] = x[1];
+    f[2] = x[3];
+    if constexpr (!SI) {
+      float in[4] = {s, c, thd_sc, u[0]}, out[2];
+      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      f[1] = sc0 * out[0];
+      f[3] = sc1 * out[1];
+    } else {
+      float in[3] = {s, c, thd_sc}, out[2];
+      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      float cin[2] = {c, c * c}, ce[2];
+      mlp_fwd<NetB>(W + A::OFF_NET_B, cin, ce);
+      f[1] = sc0 * (out[0] + ce[0] * u[0]);
+      f[3] = sc1 * (out[1] + ce[1] * u[0]);
+    }
+  }
+
+  SDE4_DEV static void drift_vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                                 const float (&u)[NU], const float (&vf)[NX], float (&gx)[NX], float (&gu)[NU]) {
+    float s, c;
+    sincosf(x[2], &s, &c);
+    const float thd_sc = x[3] * d.inv_state_scaling[3];
+    const float sc0 = d.cfloat[0], sc1 = d.cfloat[1];
+    gx[1] += vf[0];
+    gx[3] += vf[2];
+    float gs = 0.0f, gc = 0.0f;  // cotangents of sin(theta), cos(theta)
+    if constexpr (!SI) {
+      float in[4] = {s, c, thd_sc, u[0]}, go[2] = {sc0 * vf[1], sc1 * vf[3]}, gi[4];
+      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+      gs = gi[0];
+      gc = gi[1];
+      gx[3] += gi[2] * d.inv_state_scaling[3];
+      gu[0] += gi[3];
+    } else {
+      const float go0 = sc0 * vf[1], go1 = sc1 * vf[3];
+      {
+        float in[3] = {s, c, thd_sc}, go[2] = {go0, go1}, gi[3];
+        mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+        gs = gi[0];
+        gc = gi[1];
+        gx[3] += gi[2] * d.inv_state_scaling[3];
+      }
+      {
+        float cin[2] = {c, c * c}, ce[2], d1[NetB::H1 > 0 ? NetB::H1 : 1], d2[NetB::H2 > 0 ? NetB::H2 : 1];
+        mlp_fwd_keep<NetB>(W + A::OFF_NET_B, cin, ce, d1, d2);
+        gu[0] += go0 * ce[0] + go1 * ce[1];
+        float gce[2] = {go0 * u[0], go1 * u[0]}, gcin[2];
+        mlp_bwd<NetB>(W + A::OFF_NET_B, d1, d2, gce, gcin);
+        gc += gcin[0] + 2.0f * c * gcin[1];
+      }
+    }
+    gx[2] += gs * c - gc * s;
+  }
+
+  SDE4_DEV static void project(float (&)[NX], float&) {}
+  SDE4_DEV static void project_vjp(const float (&)[NX], float, float (&)[NX]) {}
+};
+
+// ----------------------------------------------------------------------------
+// Multirotor  (sde_rotor_model.py:121-458); state [p(3), v(3), q(wxyz), w(3)]
+// Scalars in the packed block (A::OFF_SCALARS + k):
+//   0 mass 1 Ixx 2 Iyy 3 Izz 4 Lmx 5 Lmy 6 CoeffDrag 7..10 motor poly c3,c2,c1,c0
+//   11 aero_kdx 12 aero_kdy 13 aero_kdz 14 aero_kh
+// ----------------------------------------------------------------------------
+template <int NU>
+struct Mixer;
+template <>
+struct Mixer<4> {  // motor_models.py:9-16
+  SDE4_DEV static float m(int r, int i) {
+    constexpr float v[4][4] = {{-0.707f, 0.707f, 0.707f, -0.707f},
+                               {-0.707f, 0.707f, -0.707f, 0.707f},
+                               {-1.0f, -1.0f, 1.0f, 1.0f},
+                               {1.0f, 1.0f, 1.0f, 1.0f}};
+    return v[r][i];
+  }
+};
+template <>
+struct Mixer<6> {  // motor_models.py:21-28
+  SDE4_DEV static float m(int r, int i) {
+    constexpr float v[4][6] = {{-1.0f, 1.0f, 0.5f, -0.5f, -0.5f, 0.5f},
+                               {0.0f, 0.0f, -0.866f, 0.866f, -0.866f, 0.866f},
+                               {1.0f, -1.0f, 1.0f, -1.0f, -1.0f, 1.0f},
+                               {1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 1.0f}};
+    return v[r][i];
+  }
+};
+
+template <class A_>
+struct RotorModel {
+  using A = A_;
+  static constexpr int NX = 13, NU = A::NU, NR = 13, NAUX = 1;
+  static constexpr bool DRAG = (A::FLAGS & SDE4_ROTOR_AERO_DRAG) != 0;
+  using NetA = typename A::NetA;  // res_forces
+  using NetB = typename A::NetB;  // res_moments
+  static constexpr bool HAS_F = NetA::PRESENT, HAS_M = NetB::PRESENT;
+
+  SDE4_DEV static void reduced_state(const float (&x)[NX], const sde4_model_desc& d, float (&r)[NR]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) r[i] = x[i] * d.inv_red_scale;  // sde_rotor_model.py:139-144
+  }
+  SDE4_DEV static void reduced_state_vjp(const float (&)[NX], const sde4_model_desc& d, const float (&g)[NR],
+                                         float (&gx)[NX]) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) gx[i] = fmaf(g[i], d.inv_red_scale, gx[i]);
+  }
+
+  // (v_b, w) / state_scaling[[3,4,5,10,11,12]]   (sde_rotor_model.py:311-315)
+  SDE4_DEV static void nn_features(const float (&x)[NX], const sde4_model_desc& d, const float (&vb)[3],
+                                   float (&in6)[6]) {
+    in6[0] = vb[0] * d.inv_state_scaling[3];
+    in6[1] = vb[1] * d.inv_state_scaling[4];
+    in6[2] = vb[2] * d.inv_state_scaling[5];
+    in6[3] = x[10] * d.inv_state_scaling[10];
+    in6[4] = x[11] * d.inv_state_scaling[11];
+    in6[5] = x[12] * d.inv_state_scaling[12];
+  }
+
+  SDE4_DEV static float motor_thrust(const float* __restrict__ S, float u) {
+    return fmaf(fmaf(fmaf(S[7], u, S[8]), u, S[9]), u, S[10]);  // motor_models.py:47-60
+  }
+  SDE4_DEV static float motor_thrust_du(const float* __restrict__ S, float u) {
+    return fmaf(fmaf(3.0f * S[7], u, 2.0f * S[8]), u, S[9]);
+  }
+
+  SDE4_DEV static void drift(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                             const float (&u)[NU], float (&f)[NX]) {
+    const float* __restrict__ S = W + A::OFF_SCALARS;
+    const Quat q{x[6], x[7], x[8], x[9]};
+    // v_b = q^-1 (x) (v (x) q)   (rotor_uav/utils.py:53-63, :439)
+    const Quat t1 = qmul(qvec(x[3], x[4], x[5]), q);
+    const Quat r1 = qmul(qconj(q), t1);
+    const float vb[3] = {r1.x, r1.y, r1.z};
+    float in6[6];
+    nn_features(x, d, vb, in6);
+    float Fb[3] = {0.0f, 0.0f, 0.0f}, Mt[3] = {0.0f, 0.0f, 0.0f};
+    if constexpr (HAS_F) {
+      float in[NetA::IN > 0 ? NetA::IN : 1], out[3];
+#pragma unroll
+      for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
+      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      Fb[0] = out[0];
+      Fb[1] = out[1];
+      Fb[2] = out[2];
+    }
+    if constexpr (DRAG) {  // :264-277
+      Fb[0] += -S[11] * vb[0];
+      Fb[1] += -S[12] * vb[1];
+      Fb[2] += -S[13] * vb[2] + S[14] * (vb[0] * vb[0] + vb[1] * vb[1]);
+    }
+    if constexpr (HAS_M) {
+      float in[NetB::IN > 0 ? NetB::IN : 1], out[3];
+#pragma unroll
+      for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
+      mlp_fwd<NetB>(W + A::OFF_NET_B, in, out);
+      Mt[0] = out[0];
+      Mt[1] = out[1];
+      Mt[2] = out[2];
+    }
+    // motors -> thrust and moments (motor_models.py:74-95)
+    float T = 0.0f, Mm[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {
+      const float th = motor_thrust(S, u[i]);
+      Mm[0] = fmaf(Mixer<NU>::m(0, i) * S[4], th, Mm[0]);
+      Mm[1] = fmaf(Mixer<NU>::m(1, i) * S[5], th, Mm[1]);
+      Mm[2] = fmaf(Mixer<NU>::m(2, i) * S[6], th, Mm[2]);
+      T = fmaf(Mixer<NU>::m(3, i), th, T);
+    }
+    // translational dynamics (:173-210): a = rot(q, [0,0,T] + Fres)/m + [0,0,-g]
+    Fb[2] += T;
+    const Quat t2 = qmul(q, qvec(Fb[0], Fb[1], Fb[2]));
+    const Quat r2 = qmul(t2, qconj(q));
+    const float m = S[0], g = d.cfloat[0];
+    f[0] = x[3];
+    f[1] = x[4];
+    f[2] = x[5];
+    f[3] = r2.x / m;
+    f[4] = r2.y / m;
+    f[5] = r2.z / m - g;
+    // rotational dynamics (:212-250)
+    const float I0 = S[1], I1 = S[2], I2 = S[3];
+    const float w0 = x[10], w1 = x[11], w2 = x[12];
+    const float Iw0 = I0 * w0, Iw1 = I1 * w1, Iw2 = I2 * w2;
+    f[10] = (Mm[0] + Mt[0] - (w1 * Iw2 - w2 * Iw1)) / I0;
+    f[11] = (Mm[1] + Mt[1] - (w2 * Iw0 - w0 * Iw2)) / I1;
+    f[12] = (Mm[2] + Mt[2] - (w0 * Iw1 - w1 * Iw0)) / I2;
+    const Quat qd = qmul(q, qvec(w0, w1, w2));
+    f[6] = 0.5f * qd.w;
+    f[7] = 0.5f * qd.x;
+    f[8] = 0.5f * qd.y;
+    f[9] = 0.5f * qd.z;
+  }
+
+  SDE4_DEV static void drift_vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+                                 const float (&u)[NU], const float (&vf)[NX], float (&gx)[NX], float (&gu)[NU]) {
+    const float* __restrict__ S = W + A::OFF_SCALARS;
+    const Quat q{x[6], x[7], x[8], x[9]};
+    const Quat qc = qconj(q);
+    const Quat V = qvec(x[3], x[4], x[5]);
+    const Quat t1 = qmul(V, q);
+    const Quat r1 = qmul(qc, t1);
+    const float vb[3] = {r1.x, r1.y, r1.z};
+    float in6[6];
+    nn_features(x, d, vb, in6);
+    const float m = S[0];
+    const float I0 = S[1], I1 = S[2], I2 = S[3];
+    const float w0 = x[10], w1 = x[11], w2 = x[12];
+    Quat gq{0.0f, 0.0f, 0.0f, 0.0f};
+    float gw[3] = {0.0f, 0.0f, 0.0f};
+    // pdot = v
+    gx[3] += vf[0];
+    gx[4] += vf[1];
+    gx[5] += vf[2];
+    // ---- rotational part: alpha = (Mm + Mres - w x (I w)) / I
+    const float gM[3] = {vf[10] / I0, vf[11] / I1, vf[12] / I2};
+    {
+      // c = w x b, b = I*w ; Mtot -= c  => cbar = -gM ; wbar += b x cbar ; bbar = cbar x w ; wbar += I*bbar
+      const float b0 = I0 * w0, b1 = I1 * w1, b2 = I2 * w2;
+      const float c0 = -gM[0], c1 = -gM[1], c2 = -gM[2];
+      gw[0] += b1 * c2 - b2 * c1;
+      gw[1] += b2 * c0 - b0 * c2;
+      gw[2] += b0 * c1 - b1 * c0;
+      const float bb0 = c1 * w2 - c2 * w1, bb1 = c2 * w0 - c0 * w2, bb2 = c0 * w1 - c1 * w0;
+      gw[0] = fmaf(I0, bb0, gw[0]);
+      gw[1] = fmaf(I1, bb1, gw[1]);
+      gw[2] = fmaf(I2, bb2, gw[2]);
+    }
+    // ---- qdot = 0.5 q (x) [0,w]
+    {
+      const Quat gqd{0.5f * vf[6], 0.5f * vf[7], 0.5f * vf[8], 0.5f * vf[9]};
+      const Quat Om = qvec(w0, w1, w2);
+      qacc(gq, qmul(gqd, qconj(Om)));
+      const Quat gOm = qmul(qc, gqd);
+      gw[0] += gOm.x;
+      gw[1] += gOm.y;
+      gw[2] += gOm.z;
+    }
+    // ---- translational part: a = vec(q (x) Fq (x) conj(q))/m + [0,0,-g], Fq = [0, Fb].
+    // The cotangent of Fb does not depend on Fb itself, so it is formed first and the
+    // residual-force net is evaluated once (forward keeping act', then backward).
+    const Quat R2 = qvec(vf[3] / m, vf[4] / m, vf[5] / m);
+    const Quat t2bar = qmul(R2, q);  // r2 = t2 (x) qc  =>  t2bar = R2 (x) conj(qc)
+    float gFb[3];
+    {
+      const Quat gFq = qmul(qc, t2bar);  // t2 = q (x) Fq  =>  Fqbar = conj(q) (x) t2bar
+      gFb[0] = gFq.x;
+      gFb[1] = gFq.y;
+      gFb[2] = gFq.z;
+    }
+    float gvb[3] = {0.0f, 0.0f, 0.0f};
+    float gin6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    float Fb[3] = {0.0f, 0.0f, 0.0f};
+    if constexpr (HAS_F) {
+      float in[NetA::IN > 0 ? NetA::IN : 1], gi[NetA::IN > 0 ? NetA::IN : 1], out[3];
+      float d1[NetA::H1 > 0 ? NetA::H1 : 1], d2[NetA::H2 > 0 ? NetA::H2 : 1];
+#pragma unroll
+      for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
+      mlp_fwd_keep<NetA>(W + A::OFF_NET_A, in, out, d1, d2);
+      Fb[0] = out[0];
+      Fb[1] = out[1];
+      Fb[2] = out[2];
+      mlp_bwd<NetA>(W + A::OFF_NET_A, d1, d2, gFb, gi);
+#pragma unroll
+      for (int k = 0; k < NetA::IN; ++k) gin6[nth_bit(A::A_MASK, k)] += gi[k];
+    }
+    if constexpr (DRAG) {
+      Fb[0] += -S[11] * vb[0];
+      Fb[1] += -S[12] * vb[1];
+      Fb[2] += -S[13] * vb[2] + S[14] * (vb[0] * vb[0] + vb[1] * vb[1]);
+      gvb[0] += -S[11] * gFb[0] + 2.0f * S[14] * vb[0] * gFb[2];
+      gvb[1] += -S[12] * gFb[1] + 2.0f * S[14] * vb[1] * gFb[2];
+      gvb[2] += -S[13] * gFb[2];
+    }
+    {
+      float T = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) T = fmaf(Mixer<NU>::m(3, i), motor_thrust(S, u[i]), T);
+      Fb[2] += T;
+      const Quat Fq = qvec(Fb[0], Fb[1], Fb[2]);
+      const Quat t2 = qmul(q, Fq);
+      qacc(gq, qconj(qmul(qconj(t2), R2)));  // qcbar = conj(t2) (x) R2
+      qacc(gq, qmul(t2bar, qconj(Fq)));      // qbar += t2bar (x) conj(Fq)
+    }
+    // ---- motors
+    {
+      const float gT = gFb[2];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        float gth = Mixer<NU>::m(3, i) * gT;
+        gth = fmaf(Mixer<NU>::m(0, i) * S[4], gM[0], gth);
+        gth = fmaf(Mixer<NU>::m(1, i) * S[5], gM[1], gth);
+        gth = fmaf(Mixer<NU>::m(2, i) * S[6], gM[2], gth);
+        gu[i] = fmaf(gth, motor_thrust_du(S, u[i]), gu[i]);
+      }
+    }
+    if constexpr (HAS_M) {
+      float in[NetB::IN > 0 ? NetB::IN : 1], gi[NetB::IN > 0 ? NetB::IN : 1];
+#pragma unroll
+      for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
+      mlp_fwd_vjp<NetB>(W + A::OFF_NET_B, in, gM, gi);
+#pragma unroll
+      for (int k = 0; k < NetB::IN; ++k) gin6[nth_bit(A::B_MASK, k)] += gi[k];
+    }
+    gvb[0] = fmaf(gin6[0], d.inv_state_scaling[3], gvb[0]);
+    gvb[1] = fmaf(gin6[1], d.inv_state_scaling[4], gvb[1]);
+    gvb[2] = fmaf(gin6[2], d.inv_state_scaling[5], gvb[2]);
+    gw[0] = fmaf(gin6[3], d.inv_state_scaling[10], gw[0]);
+    gw[1] = fmaf(gin6[4], d.inv_state_scaling[11], gw[1]);
+    gw[2] = fmaf(gin6[5], d.inv_state_scaling[12], gw[2]);
+    // ---- v_b = vec(qc (x) t1), t1 = V (x) q
+    {
+      const Quat R1 = qvec(gvb[0], gvb[1], gvb[2]);
+      // r1 = qc (x) t1 : qcbar = R1 (x) conj(t1) ; t1bar = conj(qc) (x) R1 = q (x) R1
+      qacc(gq, qconj(qmul(R1, qconj(t1))));
+      const Quat t1bar = qmul(q, R1);
+      // t1 = V (x) q : Vbar = t1bar (x) conj(q) ; qbar += conj(V) (x) t1bar
+      const Quat gV = qmul(t1bar, qc);
+      gx[3] += gV.x;
+      gx[4] += gV.y;
+      gx[5] += gV.z;
+      qacc(gq, qmul(qconj(V), t1bar));
+    }
+    gx[6] += gq.w;
+    gx[7] += gq.x;
+    gx[8] += gq.y;
+    gx[9] += gq.z;
+    gx[10] += gw[0];
+    gx[11] += gw[1];
+    gx[12] += gw[2];
+  }
+
+  // q <- q/|q| (sde_rotor_model.py:160-171); aux = 1/|q_z| for the VJP
+  SDE4_DEV static void project(float (&z)[NX], float& aux) {
+    const float s = z[6] * z[6] + z[7] * z[7] + z[8] * z[8] + z[9] * z[9];
+    float r = rsqrtf(s);
+    r = r * fmaf(-0.5f * s * r, r, 1.5f);  // one Newton step -> ~0.5 ulp
+    z[6] *= r;
+    z[7] *= r;
+    z[8] *= r;
+    z[9] *= r;
+    aux = r;
+  }
+  // lam (wrt projected state) -> lam (wrt z), given the projected state xn and aux = 1/|q_z|
+  SDE4_DEV static void project_vjp(const float (&xn)[NX], float aux, float (&lam)[NX]) {
+    const float dot = xn[6] * lam[6] + xn[7] * lam[7] + xn[8] * lam[8] + xn[9] * lam[9];
+#pragma unroll
+    for (int i = 6; i < 10; ++i) lam[i] = (lam[i] - xn[i] * dot) * aux;
+  }
+};
+
+template <class A>
+struct ModelOf;
+
+}  // namespace sde4

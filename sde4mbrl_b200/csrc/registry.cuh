@@ -1,0 +1,83 @@
+// registry.cuh -- table of compiled architecture specialisations.  Each inst_*.cu translation
+// unit instantiates the kernels of a few architectures and registers them at load time.
+#pragma once
+#include <vector>
+#include "kernels.cuh"
+
+namespace sde4 {
+
+struct ArchEntry {
+  const char* name;
+  bool (*matches)(const sde4_model_desc&);
+  int nx, nu, naux;
+  int param_total;
+  int offsets[6];
+  int smem_bytes;
+  int macs;
+  cudaError_t (*launch_rollout)(const sde4_model_desc&, const RolloutK&, int blocks, int threads, cudaStream_t);
+  cudaError_t (*launch_cost)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
+                             bool grad, bool constr, int blocks, int threads, cudaStream_t);
+};
+
+std::vector<ArchEntry>& arch_table();
+
+template <class M>
+cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int blocks, int threads, cudaStream_t s) {
+  using A = typename M::A;
+  k_rollout<M><<<blocks, threads, A::SMEM_FLOATS * sizeof(float), s>>>(d, a);
+  return cudaGetLastError();
+}
+
+template <class M>
+cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td,
+                          const CostK& a, bool grad, bool constr, int blocks, int threads, cudaStream_t s) {
+  using A = typename M::A;
+  const size_t sm = A::SMEM_FLOATS * sizeof(float);
+  if (grad) {
+    if (constr)
+      k_cost<M, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+    else
+      k_cost<M, true, false><<<blocks, threads, sm, s>>>(d, cd, td, a);
+  } else {
+    if (constr)
+      k_cost<M, false, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+    else
+      k_cost<M, false, false><<<blocks, threads, sm, s>>>(d, cd, td, a);
+  }
+  return cudaGetLastError();
+}
+
+template <class M>
+ArchEntry make_entry(const char* name) {
+  using A = typename M::A;
+  ArchEntry e;
+  e.name = name;
+  e.matches = &A::matches;
+  e.nx = M::NX;
+  e.nu = M::NU;
+  e.naux = M::NAUX;
+  e.param_total = A::PARAM_TOTAL;
+  e.offsets[0] = A::OFF_SCALARS;
+  e.offsets[1] = A::OFF_SCALER;
+  e.offsets[2] = A::OFF_DENSITY;
+  e.offsets[3] = A::OFF_NET_A;
+  e.offsets[4] = A::OFF_NET_B;
+  e.offsets[5] = A::PARAM_TOTAL;
+  e.smem_bytes = A::SMEM_FLOATS * (int)sizeof(float);
+  e.macs = A::MACS;
+  e.launch_rollout = &launch_rollout_t<M>;
+  e.launch_cost = &launch_cost_t<M>;
+  return e;
+}
+
+struct ArchRegistrar {
+  explicit ArchRegistrar(const ArchEntry& e) { arch_table().push_back(e); }
+};
+
+#define SDE4_REGISTER(NAME, MODEL) static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL>(#NAME));
+
+// shorthand for the architecture zoo
+constexpr int TANH = SDE4_ACT_TANH, SWISH = SDE4_ACT_SWISH;
+constexpr uint32_t ROTOR_NOISE_MASK = (7u << 3) | (7u << 10);  // states 3,4,5,10,11,12
+
+}  // namespace sde4

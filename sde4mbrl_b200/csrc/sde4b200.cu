@@ -1,0 +1,310 @@
+// sde4b200.cu -- C-ABI of libsde4b200.so (see include/sde4b200.h for the contract).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include "registry.cuh"
+#include "misc_kernels.cuh"
+
+namespace sde4 {
+
+std::vector<ArchEntry>& arch_table() {
+  static std::vector<ArchEntry> table;
+  return table;
+}
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a, b);
+  return code;
+}
+
+static const ArchEntry* find_arch(const sde4_model_desc& d) {
+  for (const ArchEntry& e : arch_table())
+    if (e.matches(d)) return &e;
+  return nullptr;
+}
+
+static std::string describe(const sde4_model_desc& d) {
+  char buf[384];
+  snprintf(buf, sizeof(buf),
+           "model_id=%d n_x=%d n_u=%d flags=0x%x density=[%d,%d,%d,%d act %d] net_a=[%d,%d,%d,%d act %d] "
+           "net_b=[%d,%d,%d,%d act %d] in_mask=0x%x out_mask=0x%x n_scaler=%d a_mask=0x%x b_mask=0x%x",
+           d.model_id, d.n_x, d.n_u, d.flags, d.density.n_in, d.density.h1, d.density.h2, d.density.n_out,
+           d.density.act, d.net_a.n_in, d.net_a.h1, d.net_a.h2, d.net_a.n_out, d.net_a.act, d.net_b.n_in, d.net_b.h1,
+           d.net_b.h2, d.net_b.n_out, d.net_b.act, d.noise_in_mask, d.noise_out_mask, d.n_scaler, d.net_a_in_mask,
+           d.net_b_in_mask);
+  return buf;
+}
+
+static int pick_threads(int requested, long long G) {
+  if (requested > 0) return requested;
+  // few samples: one warp per CTA so the warps spread over all 148 SMs; many samples: fatter CTAs
+  if (G <= 148LL * 32 * 4) return 32;
+  if (G <= 148LL * 64 * 8) return 64;
+  return 128;
+}
+
+static sde4_cost_desc empty_cost() {
+  sde4_cost_desc c;
+  memset(&c, 0, sizeof(c));
+  for (int i = 0; i < SDE4_MAX_NX; ++i) c.slack_col[i] = -1;
+  return c;
+}
+
+struct CostLayout {
+  size_t xbuf, dwbuf, auxbuf, gpart, cpart, total;
+  int PW, NP, warp_reduce;
+};
+
+static CostLayout cost_layout(const ArchEntry& e, int P, int N, int H, int n_slack, bool grad, bool have_xtraj,
+                              int noise_mode) {
+  CostLayout L;
+  const size_t G = (size_t)P * N;
+  L.warp_reduce = (N % 32 == 0) ? 1 : 0;
+  L.NP = L.warp_reduce ? N / 32 : N;
+  L.PW = P * L.NP;
+  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  size_t off = 0;
+  L.xbuf = off;
+  if (grad && !have_xtraj) off += al((size_t)(H + 1) * e.nx * G * 4);
+  L.dwbuf = off;
+  if (grad && noise_mode == SDE4_NOISE_THREEFRY) off += al((size_t)H * e.nx * G * 4);
+  L.auxbuf = off;
+  if (grad && e.naux) off += al((size_t)H * G * 4);
+  L.gpart = off;
+  if (grad) off += al((size_t)H * (e.nu + n_slack) * L.PW * 4);
+  L.cpart = off;
+  off += al((size_t)L.PW * 4);
+  L.total = off;
+  return L;
+}
+
+}  // namespace sde4
+
+using namespace sde4;
+
+extern "C" {
+
+int sde4_version(void) { return SDE4_ABI_VERSION; }
+void sde4_struct_sizes(int32_t out[4]) {
+  out[0] = (int32_t)sizeof(sde4_model_desc);
+  out[1] = (int32_t)sizeof(sde4_cost_desc);
+  out[2] = (int32_t)sizeof(sde4_rollout_args);
+  out[3] = (int32_t)sizeof(sde4_cost_args);
+}
+const char* sde4_last_error(void) { return g_err; }
+
+const char* sde4_supported_archs(void) {
+  static std::string s;
+  s.clear();
+  for (const ArchEntry& e : arch_table()) {
+    s += e.name;
+    s += " ";
+  }
+  return s.c_str();
+}
+
+int sde4_model_supported(const sde4_model_desc* model) { return model && find_arch(*model) ? 1 : 0; }
+
+int sde4_param_layout(const sde4_model_desc* model, int32_t* offsets) {
+  if (!model) return fail(SDE4_ERR_INVALID, "null model");
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return fail(SDE4_ERR_UNSUPPORTED, "no compiled specialisation for %s; compiled: %s", describe(*model).c_str(), sde4_supported_archs());
+  if (offsets) memcpy(offsets, e->offsets, sizeof(e->offsets));
+  return e->param_total;
+}
+
+int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void* stream) {
+  if (!model || !a) return fail(SDE4_ERR_INVALID, "null argument");
+  if (a->struct_size != (int)sizeof(sde4_rollout_args)) return fail(SDE4_ERR_INVALID, "sde4_rollout_args size mismatch (ABI)");
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return fail(SDE4_ERR_UNSUPPORTED, "no compiled specialisation for %s; compiled: %s", describe(*model).c_str(), sde4_supported_archs());
+  if (a->P <= 0 || a->N <= 0 || a->H <= 0) return fail(SDE4_ERR_INVALID, "P, N, H must be positive");
+  if (!a->params || !a->y0 || !a->u || !a->dt || !a->xevol) return fail(SDE4_ERR_INVALID, "null buffer");
+  if (((uintptr_t)a->params & 15) != 0) return fail(SDE4_ERR_INVALID, "params must be 16-byte aligned");
+  if (a->x_rows < e->nx) return fail(SDE4_ERR_INVALID, "x_rows < n_x");
+  if (a->noise_mode == SDE4_NOISE_THREEFRY && !a->key) return fail(SDE4_ERR_INVALID, "threefry noise needs a key");
+  if (a->noise_mode == SDE4_NOISE_GIVEN && !a->noise) return fail(SDE4_ERR_INVALID, "given noise needs a buffer");
+  if (a->noise_mode < 0 || a->noise_mode > 2 || a->rng_mode < 0 || a->rng_mode > 1) return fail(SDE4_ERR_INVALID, "bad noise/rng mode");
+  const long long G = (long long)a->P * a->N;
+  if (G > 0x7fffffffLL) return fail(SDE4_ERR_INVALID, "P*N exceeds 2^31-1");
+  RolloutK k;
+  k.params = a->params;
+  k.y0 = a->y0;
+  k.u = a->u;
+  k.u_sp = a->u_stride_p;
+  k.u_st = a->u_stride_t;
+  k.u_sj = a->u_stride_j;
+  k.dt = a->dt;
+  k.key = a->key;
+  k.key_sp = a->key_stride_p;
+  k.noise = a->noise;
+  k.xevol = a->xevol;
+  k.P = a->P;
+  k.N = a->N;
+  k.H = a->H;
+  k.G = (int)G;
+  k.x_rows = a->x_rows;
+  k.rng_mode = a->rng_mode;
+  k.noise_mode = a->noise_mode;
+  const int threads = pick_threads(a->block_threads, G);
+  const int blocks = (int)((G + threads - 1) / threads);
+  cudaError_t err = e->launch_rollout(*model, k, blocks, threads, (cudaStream_t)stream);
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rollout launch (%s): %s", e->name, cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_t N, int32_t H, int32_t n_slack,
+                                 int32_t want_grad, int32_t have_xtraj) {
+  if (!model) return 0;
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return 0;
+  // worst case over noise modes (threefry keeps a dw buffer)
+  return cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY).total;
+}
+
+int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* stream) {
+  if (!model || !a) return fail(SDE4_ERR_INVALID, "null argument");
+  if (a->struct_size != (int)sizeof(sde4_cost_args)) return fail(SDE4_ERR_INVALID, "sde4_cost_args size mismatch (ABI)");
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return fail(SDE4_ERR_UNSUPPORTED, "no compiled specialisation for %s; compiled: %s", describe(*model).c_str(), sde4_supported_archs());
+  if (a->P <= 0 || a->N <= 0 || a->H <= 0) return fail(SDE4_ERR_INVALID, "P, N, H must be positive");
+  if (!a->params || !a->y0 || !a->opt || !a->dt || !a->xref || !a->stage || !a->cost || !a->workspace)
+    return fail(SDE4_ERR_INVALID, "null buffer");
+  if (((uintptr_t)a->params & 15) != 0) return fail(SDE4_ERR_INVALID, "params must be 16-byte aligned");
+  if (a->noise_mode == SDE4_NOISE_THREEFRY && !a->key) return fail(SDE4_ERR_INVALID, "threefry noise needs a key");
+  if (a->noise_mode == SDE4_NOISE_GIVEN && !a->noise) return fail(SDE4_ERR_INVALID, "given noise needs a buffer");
+  if (a->noise_mode < 0 || a->noise_mode > 2 || a->rng_mode < 0 || a->rng_mode > 1) return fail(SDE4_ERR_INVALID, "bad noise/rng mode");
+  const sde4_cost_desc& cd = *a->stage;
+  if (cd.kind == SDE4_COST_ROTOR_TRACK && e->nx != 13) return fail(SDE4_ERR_UNSUPPORTED, "rotor tracking cost needs a 13-state model");
+  if (cd.n_slack < 0 || e->nu + cd.n_slack > SDE4_MAX_NOPT) return fail(SDE4_ERR_INVALID, "bad n_slack");
+  if (cd.constr_mode != SDE4_CONSTR_WITHPROX && cd.n_slack != 0) return fail(SDE4_ERR_INVALID, "n_slack without WITHPROX constraints");
+  const long long G = (long long)a->P * a->N;
+  if (G > 0x7fffffffLL) return fail(SDE4_ERR_INVALID, "P*N exceeds 2^31-1");
+  const bool grad = a->grad != nullptr;
+  const bool constr = cd.constr_mode != SDE4_CONSTR_NONE;
+  const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode);
+  if (a->workspace_bytes < L.total) return fail(SDE4_ERR_WORKSPACE, "workspace too small");
+  if (((uintptr_t)a->workspace & 255) != 0) return fail(SDE4_ERR_INVALID, "workspace must be 256-byte aligned");
+  char* ws = (char*)a->workspace;
+  CostK k;
+  k.params = a->params;
+  k.y0 = a->y0;
+  k.opt = a->opt;
+  k.o_sp = a->opt_stride_p;
+  k.o_st = a->opt_stride_t;
+  k.o_sj = a->opt_stride_j;
+  k.dt = a->dt;
+  k.xref = a->xref;
+  k.xref_sp = a->xref_stride_p;
+  k.key = a->key;
+  k.key_sp = a->key_stride_p;
+  k.noise = a->noise;
+  if (a->xtraj) {
+    k.xbuf = a->xtraj;
+    k.x_rows = e->nx + 1;
+    k.write_stage_cost = 1;
+  } else if (grad) {
+    k.xbuf = (float*)(ws + L.xbuf);
+    k.x_rows = e->nx;
+    k.write_stage_cost = 0;
+  } else {
+    k.xbuf = nullptr;
+    k.x_rows = e->nx;
+    k.write_stage_cost = 0;
+  }
+  k.dwbuf = (grad && a->noise_mode == SDE4_NOISE_THREEFRY) ? (float*)(ws + L.dwbuf) : nullptr;
+  k.auxbuf = (grad && e->naux) ? (float*)(ws + L.auxbuf) : nullptr;
+  k.gpart = grad ? (float*)(ws + L.gpart) : nullptr;
+  k.cpart = (float*)(ws + L.cpart);
+  k.P = a->P;
+  k.N = a->N;
+  k.H = a->H;
+  k.G = (int)G;
+  k.rng_mode = a->rng_mode;
+  k.noise_mode = a->noise_mode;
+  k.n_slack = cd.n_slack;
+  k.warp_reduce = L.warp_reduce;
+  k.PW = L.PW;
+  k.has_terminal = (a->terminal && a->terminal->kind != SDE4_COST_NONE) ? 1 : 0;
+  const sde4_cost_desc td = k.has_terminal ? *a->terminal : empty_cost();
+  int threads = pick_threads(a->block_threads, G);
+  const int blocks = (int)((G + threads - 1) / threads);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t err = e->launch_cost(*model, cd, td, k, grad, constr, blocks, threads, s);
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "cost launch (%s): %s", e->name, cudaGetErrorString(err));
+  ReduceK r;
+  r.gpart = k.gpart;
+  r.cpart = k.cpart;
+  r.opt = a->opt;
+  r.o_sp = a->opt_stride_p;
+  r.o_st = a->opt_stride_t;
+  r.o_sj = a->opt_stride_j;
+  r.dt = a->dt;
+  r.cost = a->cost;
+  r.grad = a->grad;
+  r.P = a->P;
+  r.N = a->N;
+  r.H = a->H;
+  r.n_u = e->nu;
+  r.n_opt = e->nu + cd.n_slack;
+  r.PW = L.PW;
+  r.NP = L.NP;
+  r.has_slew = cd.has_slew;
+  r.res_mult = cd.res_mult;
+  for (int j = 0; j < SDE4_MAX_NU; ++j) r.slew[j] = cd.u_slew_coeff[j];
+  const long long items = (long long)(a->H * r.n_opt + 1) * a->P;
+  const int rthreads = 128;
+  k_reduce<<<(int)((items + rthreads - 1) / rthreads), rthreads, 0, s>>>(r);
+  err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+int sde4_rng_bits(const uint32_t* key_host, uint64_t total, uint64_t offset, uint64_t count, int32_t rng_mode,
+                  uint32_t* out, void* stream) {
+  if (!key_host || !out) return fail(SDE4_ERR_INVALID, "null argument");
+  if (count == 0) return SDE4_OK;
+  if (rng_mode == SDE4_RNG_ORIGINAL && total > 0xffffffffull) return fail(SDE4_ERR_UNSUPPORTED, "original layout beyond 2^32 elements");
+  k_rng_bits<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key_host[0], key_host[1], total, offset,
+                                                                              count, rng_mode, out, nullptr);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+int sde4_rng_normal(const uint32_t* key_host, uint64_t total, uint64_t offset, uint64_t count, int32_t rng_mode,
+                    float* out, void* stream) {
+  if (!key_host || !out) return fail(SDE4_ERR_INVALID, "null argument");
+  if (count == 0) return SDE4_OK;
+  if (rng_mode == SDE4_RNG_ORIGINAL && total > 0xffffffffull) return fail(SDE4_ERR_UNSUPPORTED, "original layout beyond 2^32 elements");
+  k_rng_bits<<<(unsigned)((count + 255) / 256), 256, 0, (cudaStream_t)stream>>>(key_host[0], key_host[1], total, offset,
+                                                                              count, rng_mode, nullptr, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint32_t* out, void* stream) {
+  if (!key_dev || !out || num <= 0) return fail(SDE4_ERR_INVALID, "bad argument");
+  k_rng_split<<<(num + 127) / 128, 128, 0, (cudaStream_t)stream>>>(key_dev, num, rng_mode, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+int sde4_fma_peak(int32_t variant, int32_t blocks, int32_t threads, int32_t iters, float* sink, double* flops,
+                  void* stream) {
+  if (!sink || blocks <= 0 || threads <= 0 || threads > 1024) return fail(SDE4_ERR_INVALID, "bad argument");
+  if (variant == 0)
+    k_fma_peak<0><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+  else
+    k_fma_peak<1><<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, sink);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "fma_peak launch: %s", cudaGetErrorString(err));
+  if (flops) *flops = 2.0 * 16.0 * (double)iters * (double)blocks * (double)threads;
+  return SDE4_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+"""Thin launcher over the C-ABI: owns the device copies of the packed parameters, the time
+steps and a grow-only workspace, and turns torch CUDA tensors into the pointer/stride structs of
+``include/sde4b200.h``.  torch is plumbing only (device memory + streams); all arithmetic of the
+hot path happens inside ``libsde4b200.so``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from ._lib import Sde4Error
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise Sde4Error("sde4mbrl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def as_f32(x, device=None):
+    """numpy / list / torch -> float32 CUDA tensor (no copy if already there)."""
+    device = _dev() if device is None else device
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=torch.float32)
+    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=device)
+
+
+def as_key(k, device=None):
+    """jax-layout key(s) uint32[...,2] -> int32 CUDA tensor holding the same bits."""
+    device = _dev() if device is None else device
+    if isinstance(k, torch.Tensor):
+        if k.dtype == torch.uint32:
+            k = k.view(torch.int32)
+        elif k.dtype == torch.int64:
+            k = (k & 0xFFFFFFFF).to(torch.int32) if False else k.to(torch.int32)
+        if k.dtype != torch.int32:
+            raise Sde4Error("keys must be uint32/int32 tensors")
+        return k.to(device).contiguous()
+    arr = np.asarray(k)
+    if arr.dtype != np.uint32:
+        arr = arr.astype(np.uint32)
+    return torch.as_tensor(arr.view(np.int32), device=device).contiguous()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class PackedParams:
+    """Device-resident packed parameter block (see ``sde4_param_layout``)."""
+
+    def __init__(self, model, nn_params, desc):
+        self.host = model.pack(nn_params, desc)
+        self.dev = torch.as_tensor(self.host, device=_dev())
+        self.source = nn_params
+
+
+class Engine:
+    """One model (descriptor) bound to the current CUDA device."""
+
+    def __init__(self, model, rng_mode=L.RNG_ORIGINAL):
+        self.model = model
+        self.desc = model.describe()
+        L.load()
+        self.offsets, self.param_total = model.layout(self.desc)
+        self.n_x, self.n_u = model.n_x, model.n_u
+        self.rng_mode = rng_mode
+        self.noisy = model.is_noisy()
+        self._packed = None
+        self._ws = None
+        self._dt_cache = {}
+
+    # ---- parameters -----------------------------------------------------
+    def packed(self, nn_params):
+        if isinstance(nn_params, PackedParams):
+            return nn_params
+        if self._packed is None or self._packed.source is not nn_params:
+            self._packed = PackedParams(self.model, nn_params, self.desc)
+        return self._packed
+
+    def dt_tensor(self, dt):
+        key = tuple(float(v) for v in np.asarray(dt).ravel())
+        t = self._dt_cache.get(key)
+        if t is None:
+            t = torch.as_tensor(np.asarray(dt, np.float32), device=_dev())
+            self._dt_cache[key] = t
+        return t
+
+    def workspace(self, nbytes):
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=_dev())
+        return self._ws
+
+    # ---- K1 --------------------------------------------------------------
+    def rollout(self, nn_params, y0, u, dt, key=None, N=1, noise=None, noise_mode=None, x_rows=None,
+                block_threads=0, out=None):
+        """y0[P,n_x], u[P,H,n_u] (or [H,n_u], shared), key [2] or [P,2].  Returns the native
+        buffer ``xevol[H+1, x_rows, P*N]`` (sample-minor)."""
+        pk = self.packed(nn_params)
+        y0 = as_f32(y0).reshape(-1, self.n_x).contiguous()
+        P = y0.shape[0]
+        dt_t = self.dt_tensor(dt)
+        H = dt_t.numel()
+        u = as_f32(u)
+        if u.dim() == 2:
+            sp, (st, sj) = 0, u.stride()
+        else:
+            sp, st, sj = u.stride()
+            if u.shape[0] == 1:
+                sp = 0
+            elif u.shape[0] != P:
+                raise Sde4Error("u batch size does not match y0")
+        if u.shape[-2] != H or u.shape[-1] != self.n_u:
+            raise AssertionError("Dimension mismatch on the input of the sde solver")
+        G = P * N
+        x_rows = self.n_x if x_rows is None else x_rows
+        if out is None:
+            out = torch.empty((H + 1, x_rows, G), dtype=torch.float32, device=y0.device)
+        if noise_mode is None:
+            noise_mode = L.NOISE_GIVEN if noise is not None else (L.NOISE_THREEFRY if self.noisy else L.NOISE_NONE)
+        a = L.RolloutArgs()
+        a.struct_size = C.sizeof(L.RolloutArgs)
+        a.P, a.N, a.H = P, N, H
+        a.params, a.y0, a.u = _ptr(pk.dev), _ptr(y0), _ptr(u)
+        a.u_stride_p, a.u_stride_t, a.u_stride_j = sp, st, sj
+        a.dt = _ptr(dt_t)
+        keyt = None
+        if noise_mode == L.NOISE_THREEFRY:
+            keyt = as_key(key).reshape(-1, 2)
+            a.key = _ptr(keyt)
+            a.key_stride_p = 0 if keyt.shape[0] == 1 else 2
+            if keyt.shape[0] not in (1, P):
+                raise Sde4Error("need one key or one key per problem")
+        if noise_mode == L.NOISE_GIVEN:
+            noise = as_f32(noise).contiguous()
+            if tuple(noise.shape) != (H, self.n_x, G):
+                raise Sde4Error("noise must be [H, n_x, P*N] (sample-minor), got %s" % (tuple(noise.shape),))
+            a.noise = _ptr(noise)
+        a.rng_mode, a.noise_mode = self.rng_mode, noise_mode
+        a.xevol, a.x_rows, a.block_threads = _ptr(out), x_rows, block_threads
+        L.check(L.load().sde4_rollout(C.byref(self.desc), C.byref(a), _stream()))
+        return out
+
+    # ---- K2 + K3 ----------------------------------------------------------
+    def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,
+                  noise_mode=None, want_grad=True, want_xtraj=False, block_threads=0, grad_out=None):
+        """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
+        Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
+        pk = self.packed(nn_params)
+        y0 = as_f32(y0).reshape(-1, self.n_x).contiguous()
+        P = y0.shape[0]
+        dt_t = self.dt_tensor(dt)
+        H = dt_t.numel()
+        opt = as_f32(opt)
+        n_opt = self.n_u + stage.n_slack
+        squeeze = opt.dim() == 2
+        if squeeze:
+            opt = opt.unsqueeze(0)
+        if opt.shape[0] != P or opt.shape[1] != H or opt.shape[2] != n_opt:
+            raise AssertionError("Shape of the opt params do not match: %s vs (%d,%d,%d)" % (tuple(opt.shape), P, H, n_opt))
+        xref = as_f32(xref)
+        if xref.dim() == 2:
+            xref = xref.contiguous()
+            xsp = 0
+        else:
+            xref = xref.contiguous()
+            xsp = xref.stride(0) if xref.shape[0] > 1 else 0
+        if xref.shape[-2] != H + 1 or xref.shape[-1] != self.n_x:
+            raise Sde4Error("xref must be [H+1, n_x]")
+        G = P * N
+        lib = L.load()
+        ws_bytes = lib.sde4_cost_workspace_bytes(C.byref(self.desc), P, N, H, stage.n_slack, int(want_grad),
+                                                 int(want_xtraj))
+        ws = self.workspace(ws_bytes)
+        cost = torch.empty(P, dtype=torch.float32, device=y0.device)
+        grad = None
+        if want_grad:
+            grad = torch.empty_strided(opt.shape, opt.stride(), dtype=torch.float32, device=y0.device) \
+                if grad_out is None else grad_out
+        xtraj = torch.empty((H + 1, self.n_x + 1, G), dtype=torch.float32, device=y0.device) if want_xtraj else None
+        if noise_mode is None:
+            noise_mode = L.NOISE_GIVEN if noise is not None else (L.NOISE_THREEFRY if self.noisy else L.NOISE_NONE)
+        a = L.CostArgs()
+        a.struct_size = C.sizeof(L.CostArgs)
+        a.P, a.N, a.H = P, N, H
+        a.params, a.y0, a.opt = _ptr(pk.dev), _ptr(y0), _ptr(opt)
+        a.opt_stride_p, a.opt_stride_t, a.opt_stride_j = opt.stride()
+        a.dt, a.xref, a.xref_stride_p = _ptr(dt_t), _ptr(xref), xsp
+        keyt = None
+        if noise_mode == L.NOISE_THREEFRY:
+            keyt = as_key(key).reshape(-1, 2)
+            if keyt.shape[0] not in (1, P):
+                raise Sde4Error("need one key or one key per problem")
+            a.key = _ptr(keyt)
+            a.key_stride_p = 0 if keyt.shape[0] == 1 else 2
+        if noise_mode == L.NOISE_GIVEN:
+            noise = as_f32(noise).contiguous()
+            if tuple(noise.shape) != (H, self.n_x, G):
+                raise Sde4Error("noise must be [H, n_x, P*N] (sample-minor), got %s" % (tuple(noise.shape),))
+            a.noise = _ptr(noise)
+        a.rng_mode, a.noise_mode = self.rng_mode, noise_mode
+        a.stage = C.pointer(stage)
+        a.terminal = C.pointer(terminal) if terminal is not None else None
+        a.cost, a.grad, a.xtraj = _ptr(cost), _ptr(grad), _ptr(xtraj)
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        a.block_threads = block_threads
+        L.check(lib.sde4_cost_grad(C.byref(self.desc), C.byref(a), _stream()))
+        if squeeze and grad is not None:
+            grad = grad.squeeze(0)
+        return cost, grad, xtraj

@@ -1,0 +1,337 @@
+"""Drop-in mirror of the sampling / cost factories of ``sde4mbrl/nsde.py``.
+
+Same function names, argument meaning and error behaviour as the reference; the closures they
+return launch the B200 kernels through the C-ABI (``libsde4b200.so``) instead of tracing JAX.
+Arrays in are numpy / torch; arrays out are torch CUDA tensors whose *logical* shapes equal the
+reference's (``[N, H+1, n_x]`` ...) and which are strided views of the kernels' sample-minor
+buffers.
+
+Differences that cannot be hidden (all raise instead of silently changing behaviour):
+  * ``sde_constr`` must be one of the descriptor classes in ``sde4mbrl_b200.sde_models``;
+  * controls must be arrays (a callable ``us(y)``, ``sde_solver.py:292``) is rejected;
+  * ``extra_args`` / ``extra_dyn_args`` must be ``None`` (no shipped model uses them);
+  * ``_cost_fn`` must be a ``costs.StageCost`` (the shipped cost families), not a Python callable.
+"""
+import copy
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from . import costs as _costs
+from . import random as _random
+from ._lib import Sde4Error
+from .engine import Engine, as_f32, as_key
+from .sde_models import ControlledSDE
+
+
+def compute_timesteps(params):
+    """``sde4mbrl/nsde.py:15-40``."""
+    horizon = params["horizon"]
+    stepsize = params["stepsize"]
+    num_short_dt = params.get("num_short_dt", horizon)
+    assert num_short_dt <= horizon, "The number of short dt is greater than horizon"
+    num_long_dt = horizon - num_short_dt
+    short_step_dt = params.get("short_step_dt", stepsize)
+    long_step_dt = params.get("long_step_dt", stepsize)
+    return np.array([short_step_dt] * num_short_dt + [long_step_dt] * num_long_dt, dtype=np.float32)
+
+
+def initialize_problem_constraints(n_x, n_u, params_model):
+    """``sde4mbrl/nsde.py:75-130`` (numpy instead of jnp)."""
+    has_ubound = "input_constr" in params_model
+    input_lb, input_ub = None, None
+    if has_ubound:
+        print("Found input bound constraints...\n")
+        input_lb = [-np.inf for _ in range(n_u)]
+        input_ub = [np.inf for _ in range(n_u)]
+        input_dict = params_model["input_constr"]
+        assert len(input_dict["input_id"]) <= n_u and \
+            len(input_dict["input_id"]) == len(input_dict["input_bound"]), \
+            "The number of constrained inputs identifier does not match the number of bounds"
+        for idx, (u_lb, u_ub) in zip(input_dict["input_id"], input_dict["input_bound"]):
+            input_lb[idx], input_ub[idx] = u_lb, u_ub
+        input_lb = np.array(input_lb, np.float32)
+        input_ub = np.array(input_ub, np.float32)
+    has_xbound = "state_constr" in params_model
+    weight_constr = 1
+    slack_scaling = 1
+    slack_proximal, state_idx, penalty_coeff, state_lb, state_ub = False, None, None, None, None
+    if has_xbound:
+        weight_constr = params_model["state_constr"].get("constr_pen", 1)
+        print("Found states bound constraints...\n")
+        slack_dict = params_model["state_constr"]
+        assert len(slack_dict["state_id"]) <= n_x and \
+            len(slack_dict["state_id"]) == len(slack_dict["state_bound"]), \
+            "The number of the constrained states identifier does not match the number of bounds"
+        for _idx in slack_dict["state_id"]:
+            assert _idx < n_x, "The state identifier is out of bound {}/{}".format(_idx, n_x)
+        state_idx = np.array(slack_dict["state_id"])
+        slack_proximal = slack_dict["slack_proximal"]
+        penalty_coeff = slack_dict["state_penalty"]
+        state_lb = np.array([x[0] for x in slack_dict["state_bound"]], np.float32)
+        state_ub = np.array([x[1] for x in slack_dict["state_bound"]], np.float32)
+        slack_scaling = np.array(params_model["state_constr"].get("slack_scaling", 1), np.float32) if slack_proximal else 1
+        state_lb = state_lb / slack_scaling
+        state_ub = state_ub / slack_scaling
+    return (has_ubound, input_lb, input_ub), \
+        (has_xbound, slack_proximal, state_idx, penalty_coeff, state_lb, state_ub, weight_constr, slack_scaling)
+
+
+def _check_constr(sde_constr):
+    if not (isinstance(sde_constr, type) and issubclass(sde_constr, ControlledSDE)) or sde_constr is ControlledSDE:
+        raise Sde4Error("sde_constr must be MassSpringDamper, CartPoleSDE or SDERotorModel from "
+                        "sde4mbrl_b200.sde_models (arbitrary Python drift/diffusion callables cannot run in a CUDA kernel)")
+
+
+def _controls(u, H, n_u):
+    if callable(u):
+        raise Sde4Error("controls given as a function of the observation are not supported by the CUDA path")
+    u = as_f32(u)
+    if u.dim() == 1:
+        u = u[None]  # sde_solver.py:264-265
+    assert u.shape[-2] == H, "Dimension mismatch on the input of the sde solver"
+    return u
+
+
+def _make_multi_sampling(engine, params_model, num_samples, squeeze_single):
+    n_x, n_u = engine.n_x, engine.n_u
+
+    def multi_sampling(_nn_params, y, u, rng, extra_args=None):
+        if extra_args is not None:
+            raise Sde4Error("extra_args must be None (no shipped model uses extra drift/diffusion arguments)")
+        time_steps = compute_timesteps(params_model)
+        H = time_steps.shape[0]
+        y = as_f32(y)
+        batched = y.dim() == 2  # extension: a leading batch of start states (vmap in nsde.py:1322-1323)
+        assert y.dim() in (1, 2), "Not the right dimension for the initial observation and the random key"
+        u = _controls(u, H, n_u)
+        key = as_key(rng)
+        assert key.dim() == (2 if (batched and key.dim() == 2) else 1), "RNG must be a single key for vmapping"
+        engine.rng_mode = _random.rng_mode()
+        xbuf = engine.rollout(_nn_params, y, u, time_steps, key=key, N=num_samples)
+        P = y.shape[0] if batched else 1
+        N = num_samples
+        x = xbuf.view(H + 1, n_x, P, N).permute(2, 3, 0, 1)  # [P, N, H+1, n_x] strided view
+        if u.dim() == 2:
+            uev = u.view(1, 1, H, n_u).expand(P, N, H, n_u)
+        else:
+            uev = u.view(u.shape[0], 1, H, n_u).expand(P, N, H, n_u)
+        if not batched:
+            x, uev = x[0], uev[0]
+        if squeeze_single and num_samples == 1:
+            x, uev = x.select(-3, 0), uev.select(-3, 0)
+        return x, x, uev  # identity observation map: yevol is xevol
+
+    multi_sampling.engine = engine
+    return multi_sampling
+
+
+def create_sampling_fn(params_model, sde_constr=ControlledSDE, seed=0, num_samples=None, **extra_args_sde_constr):
+    """``sde4mbrl/nsde.py:987-1030``: returns ``(nn_params, multi_sampling)`` with
+    ``multi_sampling(nn_params, y, u, rng, extra_args=None) -> (xevol, yevol, uevol)``,
+    shapes ``[N, H+1, n_x]``, ``[N, H+1, n_y]``, ``[N, H, n_u]``."""
+    _check_constr(sde_constr)
+    num_samples = params_model["num_particles"] if num_samples is None else num_samples
+    model = sde_constr(params_model, **extra_args_sde_constr)
+    nn_params = model.init_params(seed)
+    engine = Engine(model, _random.rng_mode())
+    return nn_params, _make_multi_sampling(engine, params_model, num_samples, squeeze_single=False)
+
+
+def create_one_step_sampling(params_model, sde_constr=ControlledSDE, seed=0, num_samples=None,
+                             **extra_args_sde_constr):
+    """``sde4mbrl/nsde.py:933-985``: horizon forced to 1, outputs squeezed when ``num_samples == 1``."""
+    _check_constr(sde_constr)
+    params_model = copy.deepcopy(params_model)
+    params_model["horizon"] = 1
+    params_model.pop("num_short_dt", None)
+    params_model.pop("short_step_dt", None)
+    params_model.pop("long_step_dt", None)
+    num_samples = params_model["num_particles"] if num_samples is None else num_samples
+    model = sde_constr(params_model, **extra_args_sde_constr)
+    engine = Engine(model, _random.rng_mode())
+    return _make_multi_sampling(engine, params_model, num_samples, squeeze_single=True)
+
+
+class _CostSampling(torch.autograd.Function):
+    """mean-over-particles MPC cost, differentiable in ``opt_params`` (the reference relies on
+    ``jax.value_and_grad`` of this function, ``sde4mbrl/apg.py:82,224``).  The forward launch
+    computes value AND gradient in one fused kernel when a gradient is required."""
+
+    @staticmethod
+    def forward(ctx, opt, fn):
+        need = bool(ctx.needs_input_grad[0])
+        cost, grad, xtraj = fn(opt.detach(), need)
+        ctx.grad = grad
+        ctx.mark_non_differentiable(xtraj)
+        return cost, xtraj
+
+    @staticmethod
+    def backward(ctx, gcost, _gx):
+        if ctx.grad is None:
+            return None, None
+        g = ctx.grad
+        if g.dim() == 3:
+            return g * gcost.view(-1, 1, 1), None
+        return g * gcost, None
+
+
+def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=ControlledSDE, seed=0,
+                                   **extra_args_sde_constr):
+    """``sde4mbrl/nsde.py:1341-1597``.  Returns
+    ``(nn_params, multi_sampling, vmapped_prox, constr_cost, construct_opt_params)``.
+
+    ``multi_sampling(nn_params, y, opt_params, rng, _cost_fn, _terminal_cost=None,
+    extra_dyn_args=None, extra_cost_args=None, extra_cost_terminal_args=None) -> (mean_cost, xtraj)``
+    where ``extra_cost_args`` is the reference trajectory ``xref[H+1, n_x]`` and ``xtraj`` is
+    ``[N, H+1, n_x+1]`` (last column = stage cost, nsde.py:1524-1525).  Like the reference this
+    MUTATES ``params_model`` (nsde.py:1372-1385)."""
+    _check_constr(sde_constr)
+    n_u = params_model["n_u"]
+    n_x = params_model["n_x"]
+    num_sample = params_mpc.get("num_particles", params_model.get("num_particles", 1))
+    params_model["num_particles"] = num_sample
+    print("Using [ N = {} ] particles for the loss".format(num_sample))
+    params_model["horizon"] = params_mpc.get("horizon", params_model.get("horizon", 1))
+    print("Using [ T = {} ] horizon for the loss".format(params_model["horizon"]))
+    params_model["num_short_dt"] = params_mpc["num_short_dt"]
+    params_model["short_step_dt"] = params_mpc["short_step_dt"]
+    params_model["long_step_dt"] = params_mpc["long_step_dt"]
+    time_steps = compute_timesteps(params_model)
+    H = time_steps.shape[0]
+
+    (has_ubound, input_lb, input_ub), \
+        (has_xbound, slack_proximal, state_idx, penalty_coeff, state_lb, state_ub, weight_constr, slack_scaling) = \
+        initialize_problem_constraints(n_x, n_u, params_mpc)
+    penalty_coeff = np.asarray(penalty_coeff, np.float32) if penalty_coeff is not None else None
+    has_slack = bool(has_xbound and slack_proximal)
+    n_slack = len(state_idx) if has_slack else 0
+    opt_params_size = n_u + n_slack
+
+    constr = None
+    if has_xbound:
+        ns = len(state_idx)
+        constr = dict(mode=L.CONSTR_WITHPROX if slack_proximal else L.CONSTR_NOPROX, n_slack=n_slack,
+                      weight=weight_constr, state_idx=[int(i) for i in state_idx], penalty=penalty_coeff,
+                      state_lb=state_lb, state_ub=state_ub,
+                      slack_scaling=np.broadcast_to(np.asarray(slack_scaling, np.float32), (ns,)))
+
+    def _t(a):
+        return as_f32(a)
+
+    def constr_vect(a, lb, ub):
+        return torch.minimum(torch.maximum(a, lb), ub)
+
+    # proximal operators (nsde.py:1435-1460); they act on [H, n_opt] (or [..., H, n_opt]) tensors
+    proximal_fn = None
+    constr_cost = None
+    if has_ubound and (not has_xbound):
+        lb, ub = _t(input_lb), _t(input_ub)
+        proximal_fn = lambda u_slack: constr_vect(as_f32(u_slack), lb, ub)
+    if (not has_ubound) and has_xbound and slack_proximal:
+        slb, sub = _t(state_lb), _t(state_ub)
+        proximal_fn = lambda u_slack: torch.cat((as_f32(u_slack)[..., :n_u], constr_vect(as_f32(u_slack)[..., n_u:], slb, sub)), dim=-1)
+    if has_ubound and has_xbound and (not slack_proximal):
+        lb, ub = _t(input_lb), _t(input_ub)
+        proximal_fn = lambda u_slack: constr_vect(as_f32(u_slack), lb, ub)
+    if has_ubound and has_xbound and slack_proximal:
+        lb = torch.cat((_t(input_lb), _t(state_lb)))
+        ub = torch.cat((_t(input_ub), _t(state_ub)))
+        proximal_fn = lambda u_slack: constr_vect(as_f32(u_slack), lb, ub)
+    if has_xbound:
+        constr_cost = "constr_cost_withprox" if slack_proximal else "constr_cost_noprox"  # evaluated in-kernel
+
+    model = sde_constr(params_model, **extra_args_sde_constr)
+    nn_params = model.init_params(seed)
+    engine = Engine(model, _random.rng_mode())
+
+    def multi_sampling(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost=None, extra_dyn_args=None,
+                       extra_cost_args=None, extra_cost_terminal_args=None):
+        if extra_dyn_args is not None:
+            raise Sde4Error("extra_dyn_args must be None (no shipped model uses them)")
+        if not isinstance(_cost_fn, _costs.StageCost):
+            raise Sde4Error("_cost_fn must be a sde4mbrl_b200.costs.StageCost (e.g. costs.one_step_cost_f(cost_params, n_u)); "
+                            "arbitrary Python cost callables cannot run inside the CUDA kernel")
+        if _terminal_cost is not None and not isinstance(_terminal_cost, _costs.StageCost):
+            raise Sde4Error("_terminal_cost must be a costs.StageCost or None")
+        if extra_cost_args is None:
+            raise Sde4Error("extra_cost_args (the reference trajectory xref[H+1, n_x]) is required")
+        opt = opt_params if isinstance(opt_params, torch.Tensor) else as_f32(opt_params)
+        opt = opt.to(dtype=torch.float32)
+        assert opt.dim() in (2, 3), "The parameters must be a two dimension array"
+        assert opt.shape[-1] == opt_params_size, "Shape of the opt params do not match"
+        key = as_key(rng)
+        assert key.dim() == 1 or opt.dim() == 3, "RNG must be a single key for vmapping"
+        stage = _cost_fn if constr is None else _costs.with_constraints(_cost_fn, constr, n_u)
+        term = _terminal_cost
+        engine.rng_mode = _random.rng_mode()
+        y_t = as_f32(y)
+        xref = as_f32(extra_cost_args)
+
+        def run(opt_d, need_grad):
+            cost, grad, xtraj = engine.cost_grad(_nn_params, y_t, opt_d, time_steps, xref, stage.desc,
+                                                 terminal=None if term is None else term.desc, key=key,
+                                                 N=num_sample, want_grad=need_grad, want_xtraj=True)
+            return (cost if opt_d.dim() == 3 else cost[0]), grad, xtraj
+
+        if opt.device.type != "cuda":
+            opt = opt.to(y_t.device)
+        cost, xbuf = _CostSampling.apply(opt, run)
+        P = opt.shape[0] if opt.dim() == 3 else 1
+        xtraj = xbuf.view(H + 1, n_x + 1, P, num_sample).permute(2, 3, 0, 1)
+        if opt.dim() == 2:
+            xtraj = xtraj[0]
+        return cost, xtraj
+
+    multi_sampling.engine = engine
+    multi_sampling.time_steps = time_steps
+
+    def _construct_opt_params(u=None, x=None):
+        """``nsde.py:1532-1573`` (including the doubled ``+1e-4`` of the 1-D ``u`` path)."""
+        num_var = H
+        dev = engine_device()
+        zero_u = torch.ones((num_var, n_u), device=dev) * 1e-4
+        zero_x = torch.ones((num_var, n_slack), device=dev) * 1e-4 if has_slack else None
+        ssv = None
+        if has_slack:
+            ss = np.asarray(slack_scaling, np.float32)
+            ssv = torch.ones((num_var, n_slack), device=dev) * (as_f32(ss) if ss.ndim >= 1 else float(ss))
+        if u is not None:
+            u = as_f32(u)
+            if u.dim() == 1:
+                u = u[None].repeat(num_var, 1) + 1e-4
+        if x is not None:
+            x = as_f32(x)
+            if x.dim() == 1:
+                x = x[None].repeat(num_var + 1, 1)
+            x = x.clone()
+            x[0, :] = x[-1, :]
+        sidx = [int(i) for i in state_idx] if has_slack else None
+        if u is None and not has_slack:
+            return zero_u
+        if u is None and x is None:
+            return torch.cat((zero_u, zero_x), dim=1)
+        if u is None and x is not None:
+            assert x.dim() == 2 and x.shape[0] == num_var + 1
+            return torch.cat((zero_u, x[:-1, sidx] / ssv), dim=1) + 1e-4
+        if u is not None and not has_slack:
+            assert u.dim() == 2 and u.shape[0] == num_var
+            return u + 1e-4
+        if u is not None and x is None:
+            assert u.dim() == 2 and u.shape[0] == num_var
+            return torch.cat((u, zero_x), dim=1) + 1e-4
+        assert u.dim() == 2 and x.dim() == 2 and u.shape[0] + 1 == x.shape[0]
+        return torch.cat((u, x[:-1, sidx] / ssv), dim=1) + 1e-4
+
+    vmapped_prox = proximal_fn  # the box clip broadcasts over the time axis
+    if vmapped_prox is not None:
+        construct_opt_params = lambda u=None, x=None: vmapped_prox(_construct_opt_params(u, x))
+    else:
+        construct_opt_params = _construct_opt_params
+    return nn_params, multi_sampling, vmapped_prox, constr_cost, construct_opt_params
+
+
+def engine_device():
+    from .engine import _dev
+    return _dev()

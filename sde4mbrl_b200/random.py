@@ -1,0 +1,66 @@
+"""``jax.random`` key plumbing on the device (threefry2x32, bit-exact with JAX).
+
+Keys are jax-layout ``uint32[2]`` values stored as int32 CUDA tensors (same bits).  Splitting
+runs in ``libsde4b200.so`` (``sde4_rng_split``) so no host round trip is needed; the rollout
+kernels derive their per-particle Brownian keys themselves (``nsde.py:1026`` ->
+``sde_solver.py:276``).  Reference call sites: ``sde4mbrl/sde_solver.py:276,277,283``,
+``sde4mbrl/nsde.py:1026,1187,1196,1581``, ``rotor_uav/sde_mpc_design.py:227``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .engine import as_key, _dev, _ptr, _stream
+
+_partitionable = False  # jax_threefry_partitionable (False was JAX's default when the reference was written)
+
+
+def set_threefry_partitionable(flag):
+    """Select the jax.random stream layout (``jax.config.jax_threefry_partitionable``)."""
+    global _partitionable
+    _partitionable = bool(flag)
+
+
+def rng_mode():
+    return L.RNG_PARTITIONABLE if _partitionable else L.RNG_ORIGINAL
+
+
+def PRNGKey(seed):
+    """``jax.random.PRNGKey(seed)`` -> int32 CUDA tensor [2] with bits [hi32(seed), lo32(seed)]."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return as_key(np.array([seed >> 32, seed & 0xFFFFFFFF], dtype=np.uint32))
+
+
+def split(key, num=2):
+    """``jax.random.split(key, num)`` -> int32 CUDA tensor [num, 2]."""
+    key = as_key(key).reshape(2)
+    out = torch.empty((num, 2), dtype=torch.int32, device=key.device)
+    L.check(L.load().sde4_rng_split(_ptr(key), int(num), rng_mode(), _ptr(out), _stream()))
+    return out
+
+
+def key_data(key):
+    """uint32 numpy view of a key tensor (host copy; for printing / tests)."""
+    return as_key(key).cpu().numpy().view(np.uint32)
+
+
+def bits(key, shape):
+    """``jax.random.bits(key, shape)`` uint32 (as int32 bits) -- RNG self-test entry."""
+    kd = key_data(key).reshape(2)
+    n = int(np.prod(shape)) if len(shape) else 1
+    out = torch.empty(n, dtype=torch.int32, device=_dev())
+    k = (C.c_uint32 * 2)(int(kd[0]), int(kd[1]))
+    L.check(L.load().sde4_rng_bits(k, n, 0, n, rng_mode(), _ptr(out), _stream()))
+    return out.reshape(shape)
+
+
+def normal(key, shape):
+    """``jax.random.normal(key, shape)`` float32."""
+    kd = key_data(key).reshape(2)
+    n = int(np.prod(shape)) if len(shape) else 1
+    out = torch.empty(n, dtype=torch.float32, device=_dev())
+    k = (C.c_uint32 * 2)(int(kd[0]), int(kd[1]))
+    L.check(L.load().sde4_rng_normal(k, n, 0, n, rng_mode(), _ptr(out), _stream()))
+    return out.reshape(shape)
