@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sde4mbrl hot path on B200.
+
+Workload (BASELINE.json configs[2], the one the >=100x target is quoted on): hexacopter nSDE,
+ONE problem, 4096 particles x 100 Euler-Maruyama steps with the distance-aware diffusion
+(in-kernel threefry noise) AND the reverse-mode gradient pass  ->  one "step" = one fused
+value+gradient evaluation of the MPC cost (sde4_cost_grad: K2 rollout+cost+adjoint, K3 reduce).
+Metric: particle-steps/s = particles x horizon / time per step (whole job, all GPUs).
+With N GPUs (weak scaling) every rank holds 4096 particles of the SAME problem (global
+N = 4096 x GPUs, keys = split(rng, N_global)) and the only collective is the NCCL all-reduce of
+the per-problem [cost, grad] sums (601 floats) -- the north star's single exchange step.
+
+Extra fields: forward-only rollout throughput, batched-MPC numbers, the measured FP32 FMA peak
+that the roofline fraction is taken against, the CPU baseline (oracle port on the host cores).
+
+`--impl reference` times the reference's CPU algorithm (the oracle port -- jax is not installed in
+this image) on the same workload / metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# algorithmic work, SURVEY.md 8(a)/(d): hexacopter F_fwd = 3790 flop per particle-step
+# (+90 stage cost); value+grad = 2 x F_fwd
+F_FWD_HEXA = 3790.0
+F_VALGRAD_HEXA = 2.0 * 3880.0
+N_PART, HORIZON = 4096, 100
+
+
+def build_workload(seed=0):
+    from sde4mbrl_b200 import configs, costs, sde_models
+    pm = configs.hexa_model(horizon=HORIZON, num_particles=N_PART, stepsize=0.01)
+    model = sde_models.SDERotorModel(pm)
+    nn = configs.random_params(model, seed=seed, scale="fan_in")
+    rng = np.random.default_rng(0)
+    y0 = configs.hover_state()
+    y0[3:6] += rng.normal(0, 0.01, 3).astype(np.float32)
+    y0[10:13] += rng.normal(0, 0.01, 3).astype(np.float32)
+    opt = rng.uniform(0.30, 0.36, (HORIZON, 6)).astype(np.float32)
+    xref = np.tile(configs.hover_state(), (HORIZON + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    cp = configs.hexa_mpc()["cost_params"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    return dict(pm=pm, model=model, nn=nn, y0=y0, opt=opt, xref=xref, cp=cp, stage=stage,
+                key=np.array([0, 2050], np.uint32))
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=6)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_reference_step(w, n_particles, threads):
+    """One value+gradient evaluation with the CPU restatement of the reference's algorithm:
+    oracle/c (plain C, AVX2/AVX-512 lanes over particles, OpenMP over particle chunks, in-line
+    threefry noise) -- the kind of code XLA:CPU would emit for the reference's vmapped scan."""
+    from oracle import c_oracle
+    if "c_packed" not in w:
+        w["c_desc"] = w["model"].describe()
+        w["c_packed"] = w["model"].pack(w["nn"], w["c_desc"])
+    ts = np.full(HORIZON, 0.01, np.float32)
+    t0 = time.perf_counter()
+    c, g, _ = c_oracle.rotor_cost_grad(w["c_desc"], w["stage"].desc, w["c_packed"], w["y0"], w["opt"], ts, w["xref"],
+                                       n_particles, key=w["key"], nthreads=threads)
+    return time.perf_counter() - t0, c, g
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; jax absent)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    w = build_workload()
+    from oracle import c_oracle
+    simd = c_oracle.load().sde4o_simd_width()
+    n_sample = N_PART  # the C port is fast enough to run the full 4096-particle workload per step
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_step(w, n_sample, threads)
+    times = [cpu_reference_step(w, n_sample, threads)[0] for _ in range(args.steps)]
+    t = float(np.mean(times))
+    val = n_sample * HORIZON / t
+    line = {"impl": "reference", "metric": "particle-steps/s (value+grad, hexacopter nSDE)", "value": val,
+            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "hexacopter nSDE, 1 problem, 4096 particles x 100 steps, diffusion + gradient pass "
+                                   "(BASELINE configs[2]); CPU arm runs the full workload per step"},
+            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                             "sample": "%d particles x %d steps value+grad per step; oracle/c (C, AVX-512/AVX2 + OpenMP, SIMD width %d)" % (n_sample, HORIZON, simd)},
+            "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-threads", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from sde4mbrl_b200 import _lib as L
+    from sde4mbrl_b200.engine import Engine, PackedParams
+
+    w = build_workload()
+    eng = Engine(w["model"])
+    pk = PackedParams(w["model"], w["nn"], eng.desc)
+    ts = np.full(HORIZON, 0.01, np.float32)
+    y0_d = torch.as_tensor(w["y0"], device=dev)[None]
+    opt_d = torch.as_tensor(w["opt"], device=dev)
+    xref_d = torch.as_tensor(w["xref"], device=dev)
+    key_d = torch.as_tensor(w["key"].view(np.int32), device=dev)
+    n_total = N_PART * world
+    red = torch.zeros(HORIZON * 6 + 1, device=dev)
+
+    def step_device():
+        cost, grad, _ = eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART,
+                                      want_grad=True, block_threads=args.block_threads,
+                                      particle_offset=rank * N_PART, particle_total=n_total)
+        if world > 1:
+            red[0:1].copy_(cost)
+            red[1:].copy_(grad.reshape(-1))
+            dist.all_reduce(red)
+            return red[0:1], red[1:].view(HORIZON, 6)
+        return cost, grad
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timing: K steps, each bracketed by CUDA events, L2 flushed in between
+    evs = []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step_device()
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    ms_per_step = float(np.mean(step_ms))
+    if world > 1:
+        t = torch.tensor([ms_per_step], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())
+
+    # ---- end-to-end through the public API with HOST buffers (pinned): H2D + kernels + D2H
+    from sde4mbrl_b200 import nsde, random as R
+    from sde4mbrl_b200 import configs, sde_models
+    mpc = configs.hexa_mpc(horizon=HORIZON, dt=0.01, num_particles=N_PART)
+    pm2 = configs.hexa_model(horizon=HORIZON, num_particles=N_PART, stepsize=0.01)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        _, multi_cost, _, _, _ = nsde.create_online_cost_sampling_fn(pm2, mpc, sde_constr=sde_models.SDERotorModel)
+    e2e_eng = multi_cost.engine
+    e2e_pk = PackedParams(e2e_eng.model, w["nn"], e2e_eng.desc)
+    y0_h = torch.as_tensor(w["y0"]).pin_memory()
+    opt_h = torch.as_tensor(w["opt"]).pin_memory()
+    xref_h = torch.as_tensor(w["xref"]).pin_memory()
+    key_h = torch.as_tensor(w["key"].view(np.int32)).pin_memory()
+    out_h = torch.empty(HORIZON * 6 + 1).pin_memory()
+    h2d = (y0_h.numel() + opt_h.numel() + xref_h.numel()) * 4 + 8
+    d2h = out_h.numel() * 4
+
+    def step_e2e():
+        y = y0_h.to(dev, non_blocking=True)
+        o = opt_h.to(dev, non_blocking=True).requires_grad_(True)
+        xr = xref_h.to(dev, non_blocking=True)
+        k = key_h.to(dev, non_blocking=True)
+        c, _ = multi_cost(e2e_pk, y, o, k, w["stage"], extra_cost_args=xr)
+        (g,) = torch.autograd.grad(c, o)
+        if world > 1:
+            red[0:1].copy_(c.reshape(1))
+            red[1:].copy_(g.reshape(-1))
+            dist.all_reduce(red)
+            out_h.copy_(red, non_blocking=True)
+        else:
+            out_h[0:1].copy_(c.reshape(1), non_blocking=True)
+            out_h[1:].copy_(g.reshape(-1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- extras (rank 0, N=1 only): forward rollout, FP32 peak, CPU baseline
+    extras = {}
+    roof = None
+    cpu_b = None
+    if rank == 0:
+        # measured FP32 FMA peak (roofline denominator; MEASURED_PEAKS.json has no FP32 number)
+        sink = torch.zeros(4, device=dev)
+        peaks = {}
+        for variant in (0, 1):
+            best = 0.0
+            for _ in range(3):
+                fl = L.C.c_double(0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                L.check(L.load().sde4_fma_peak(variant, 148 * 8, 256, 4000, L.C.c_void_p(sink.data_ptr()),
+                                               L.C.byref(fl), L.C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+                e1.record()
+                torch.cuda.synchronize()
+                best = max(best, fl.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+            peaks["ffma" if variant == 0 else "ffma2_f32x2"] = best
+        peak = max(peaks.values())
+        # the kernel alone (K2; K3 is ~2 us): same launch, events on the launch stream, no collective
+        kt = []
+        for _ in range(min(args.steps, 20)):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART, want_grad=True,
+                          block_threads=args.block_threads, particle_offset=rank * N_PART, particle_total=n_total)
+            e1.record()
+            torch.cuda.synchronize()
+            kt.append(e0.elapsed_time(e1))
+        k_ms = float(np.mean(kt))
+        flop = F_VALGRAD_HEXA * N_PART * HORIZON
+        achieved = flop / (k_ms * 1e-3) / 1e12
+        roof = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "measured in this run by sde4_fma_peak (FFMA / fma.rn.f32x2 loop)",
+                "peaks_tflops": peaks, "kernel_ms": k_ms,
+                "algorithmic_flop_per_launch": flop,
+                "note": "path is FP32-FMA bound (SURVEY 8d), not HBM/tensor; HBM write-out of this launch = %.1f MB"
+                        % (4.0 * N_PART * (HORIZON + 1) * 13 * 2 / 1e6)}
+        # forward-only rollout (K1) for context
+        ft = []
+        for _ in range(10):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            eng.rollout(pk, y0_d, opt_d, ts, key=key_d, N=N_PART)
+            e1.record()
+            torch.cuda.synchronize()
+            ft.append(e0.elapsed_time(e1))
+        extras["forward_rollout_ms"] = float(np.mean(ft))
+        extras["forward_particle_steps_per_s"] = N_PART * HORIZON / (float(np.mean(ft)) * 1e-3)
+        extras["forward_fp32_tflops"] = F_FWD_HEXA * N_PART * HORIZON / (float(np.mean(ft)) * 1e-3) / 1e12
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            n_sample = N_PART
+            cpu_reference_step(w, n_sample, threads)
+            tcpu = [cpu_reference_step(w, n_sample, threads)[0] for _ in range(20)]
+            v = n_sample * HORIZON / float(np.mean(tcpu))
+            cpu_b = {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "port",
+                     "sample": "all %d particles x %d steps, value+grad, 20 reps; oracle/c (C restatement, AVX-512/AVX2 lanes + OpenMP)" % (n_sample, HORIZON)}
+
+    if rank == 0:
+        total_ps = n_total * HORIZON
+        line = {
+            "metric": "particle-steps/s (value+grad, hexacopter nSDE)", "value": total_ps / (ms_per_step * 1e-3),
+            "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "hexacopter nSDE (13 states, 6 rotors), 1 problem, 4096 particles per GPU x 100 steps, "
+                                   "distance-aware diffusion with in-kernel threefry noise + gradient pass (BASELINE configs[2])",
+                       "particles_per_gpu": N_PART, "horizon": HORIZON, "parallelism": "particles sharded over %d GPU(s), "
+                       "NCCL all-reduce of [cost, grad] (601 floats)" % world,
+                       "l2": "flushed between timed steps (256 MB write)", "timing": "CUDA events per step, max over ranks"},
+            "clocks": clocks,
+            "e2e": {"value": total_ps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
+                    "api": "nsde.create_online_cost_sampling_fn(...).multi_sampling + torch.autograd.grad, pinned host buffers"},
+            "gpu_launches": 2 * args.steps,
+            "wall_s_timed_region": t_wall,
+        }
+        if roof:
+            line["roofline"] = roof
+        if cpu_b:
+            line["cpu_baseline"] = cpu_b
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

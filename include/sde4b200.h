@@ -155,6 +155,10 @@ typedef struct sde4_rollout_args {
   float* xevol;                 /* out [H+1][x_rows][G]                               */
   int32_t x_rows;               /* >= n_x (rows beyond n_x are left untouched)        */
   int32_t block_threads;        /* 0 = library heuristic                              */
+  /* particle sharding across GPUs: this call holds particles [particle_offset,
+   * particle_offset+N) of particle_total per problem (keys are split(rng, particle_total)).
+   * particle_total == 0 means (offset 0, total N). */
+  int32_t particle_offset, particle_total;
 } sde4_rollout_args;
 
 int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, void* stream);
@@ -187,6 +191,10 @@ typedef struct sde4_cost_args {
   void* workspace;              /* >= sde4_cost_workspace_bytes(...)                   */
   size_t workspace_bytes;
   int32_t block_threads;
+  /* particle sharding (see sde4_rollout_args): cost/grad are scaled by 1/particle_total so that a
+   * SUM all-reduce over the shards gives the mean over all particles.  The slew term is added by
+   * the shard with particle_offset == 0 only. */
+  int32_t particle_offset, particle_total;
 } sde4_cost_args;
 
 size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_t N, int32_t H,
@@ -207,9 +215,10 @@ int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint3
 /* ---- layout of the packed parameter block -------------------------------------
  * Returns the number of floats of the block for `model` (<0 on error).  The
  * order is: model scalars, scaler vector, density net, net_a, net_b; every
- * tensor starts on a 4-float boundary; a layer is w[in][out4] (row-major, as
- * haiku stores it, with `out` padded up to a multiple of 4 with zeros) followed by
- * b[out4].  If `offsets` is non-NULL it receives, in floats:
+ * tensor starts on a 4-float boundary; a network is
+ *   w0[in][h1_4] b0[h1_4] w1[h1][h2_4] b1[h2_4] w2T[out][h2_4] b2[out_4]
+ * (w0, w1 row-major [in][out] as haiku stores them, `out` padded up to a multiple of 4 with
+ * zeros; the last layer is stored transposed, one contiguous row per output).  If `offsets` is non-NULL it receives, in floats:
  *   [0] scalars  [1] scaler  [2] density  [3] net_a  [4] net_b  [5] total.
  * Rotor scalars (16): mass,Ixx,Iyy,Izz,Lmx,Lmy,CoeffDrag, c3,c2,c1,c0 (motor
  * polynomial, highest power first), aero_kdx,kdy,kdz,kh, pad. */

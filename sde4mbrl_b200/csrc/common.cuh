@@ -37,25 +37,11 @@ SDE4_DEV float fast_rcp(float x) { return __fdividef(1.0f, x); }
 
 SDE4_DEV float sigmoidf_(float a) { return fast_rcp(1.0f + __expf(-a)); }
 
-// Rational tanh on [-7.99, 7.99] (the float approximation Eigen / XLA:CPU evaluate:
-// odd degree-13 numerator over even degree-6 denominator), ~2 ulp, branch free.
+// tanh(a) = 1 - 2/(exp(2a) + 1): 2 MUFU + 3 FP32 ops, absolute error ~1.5e-7 (saturates correctly
+// to +-1; for |a| << 1 the error is absolute, not relative -- fine for float32 parity).
 SDE4_DEV float tanhf_(float a) {
-  const float c = 7.99881172180175781f;
-  float x = fminf(fmaxf(a, -c), c);
-  float x2 = x * x;
-  float p = -2.76076847742355e-16f;
-  p = fmaf(p, x2, 2.00018790482477e-13f);
-  p = fmaf(p, x2, -8.60467152213735e-11f);
-  p = fmaf(p, x2, 5.12229709037114e-08f);
-  p = fmaf(p, x2, 1.48572235717979e-05f);
-  p = fmaf(p, x2, 6.37261928875436e-04f);
-  p = fmaf(p, x2, 4.89352455891786e-03f);
-  p = p * x;
-  float q = 1.19825839466702e-06f;
-  q = fmaf(q, x2, 1.18534705686654e-04f);
-  q = fmaf(q, x2, 2.26843463243900e-03f);
-  q = fmaf(q, x2, 4.89352518554385e-03f);
-  return __fdividef(p, q);
+  const float t = exp2f(a * 2.88539008177792681f);  // exp(2a); MUFU.EX2
+  return 1.0f - __fdividef(2.0f, t + 1.0f);
 }
 
 template <int ACT>
@@ -145,7 +131,8 @@ SDE4_HD void jax_split(uint32_t k0, uint32_t k1, uint32_t i, uint32_t num, int m
 
 // XLA float32 erf_inv (Giles) -- see SURVEY appendix F
 SDE4_DEV float erfinv_f32(float x) {
-  float w = -__logf(fmaf(-x, x, 1.0f));
+  // XLA evaluates -log1p(-(x*x)) with the product rounded first; keep that (no FMA contraction)
+  float w = -__logf(1.0f - __fmul_rn(x, x));
   float p;
   if (w < 5.0f) {
     w = w - 2.5f;

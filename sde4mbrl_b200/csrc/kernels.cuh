@@ -29,6 +29,7 @@ struct RolloutK {
   float* xevol;
   int P, N, H, G;
   int x_rows, rng_mode, noise_mode;
+  int n_off, n_tot;
 };
 
 struct CostK {
@@ -50,6 +51,7 @@ struct CostK {
   int P, N, H, G;
   int x_rows, rng_mode, noise_mode;
   int n_slack, warp_reduce, PW, has_terminal, write_stage_cost;
+  int n_off, n_tot;
 };
 
 struct ReduceK {
@@ -60,40 +62,55 @@ struct ReduceK {
   const float* dt;
   float* cost;
   float* grad;
-  int P, N, H, n_u, n_opt, PW, NP;  // NP partials per problem
+  int P, N, H, n_u, n_opt, PW, NP;  // NP partials per problem; N = total particles (divisor)
   int has_slew;
   float res_mult;
   float slew[SDE4_MAX_NU];
 };
 
-// dw_t for one sample; components with zero prior diffusion are never generated.
+// dw_t for one sample, written to the per-thread scratch column `dwc` (element i at dwc[i*bs]);
+// components with zero prior diffusion are never generated.  ROLLED over the state index (the
+// threefry block is ~100 instructions; unrolling it 13x only bloats the instruction stream).
+// `keep` (optional) receives a copy for the backward sweep: keep[i*G] = dw_i.
 template <int NX>
 SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode, const float* __restrict__ noise,
-                         uint32_t b0, uint32_t b1, int t, int H, int G, int g, float (&dw)[NX]) {
+                         uint32_t b0, uint32_t b1, int t, int H, int G, int g, float* dwc, int bs, float* keep) {
+  // 4 elements per iteration: the threefry rounds are one serial dependency chain per element, so
+  // independent elements are interleaved for ILP (a single resident warp cannot hide it otherwise)
+#pragma unroll 1
+  for (int i0 = 0; i0 < NX; i0 += 4) {
+    float v[4];
 #pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    dw[i] = 0.0f;
-    if (d.noise_prior[i] != 0.0f) {
-      if (noise_mode == SDE4_NOISE_GIVEN) {
-        dw[i] = __ldg(noise + ((size_t)t * NX + i) * G + g);
-      } else {
-        dw[i] = bits_to_normal(jax_bits(b0, b1, (uint64_t)t * NX + i, (uint64_t)H * NX, rng_mode));
+    for (int q = 0; q < 4; ++q) {
+      const int i = i0 + q;
+      v[q] = 0.0f;
+      if (i < NX && d.noise_prior[i < NX ? i : 0] != 0.0f) {
+        if (noise_mode == SDE4_NOISE_GIVEN) {
+          v[q] = __ldg(noise + ((size_t)t * NX + i) * G + g);
+        } else {
+          v[q] = bits_to_normal(jax_bits(b0, b1, (uint64_t)t * NX + i, (uint64_t)H * NX, rng_mode));
+          if (keep) keep[(size_t)i * G] = v[q];
+        }
       }
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (i0 + q < NX) dwc[(size_t)(i0 + q) * bs] = v[q];
   }
 }
 
 // One Euler-Maruyama step in place: x <- proj(x + f dt + sigma dw)   (sde_solver.py:301-304)
 template <class M>
-SDE4_DEV void em_step(const float* __restrict__ W, const sde4_model_desc& d, float (&x)[M::NX],
-                      const float (&u)[M::NU], const float (&dw)[M::NX], float dt, bool noisy, float& aux) {
+SDE4_DEV void em_step(const float* W, const Scratch& sc, const sde4_model_desc& d, float (&x)[M::NX],
+                      const float (&u)[M::NU], float dt, bool noisy, float& aux) {
   float f[M::NX];
-  M::drift(W, d, x, u, f);
+  M::drift(W, sc, d, x, u, f);
   if (noisy) {
     float sig[M::NX];
-    Diffusion<M>::fwd(W, d, x, sig);
+    Diffusion<M>::fwd(W, sc, d, x, sig);
+    const float* dwc = sc.slot(Scratch::SLOT_X);
 #pragma unroll
-    for (int i = 0; i < M::NX; ++i) x[i] = fmaf(sig[i], dw[i], fmaf(f[i], dt, x[i]));
+    for (int i = 0; i < M::NX; ++i) x[i] = fmaf(sig[i], dwc[(size_t)i * sc.bs], fmaf(f[i], dt, x[i]));
   } else {
 #pragma unroll
     for (int i = 0; i < M::NX; ++i) x[i] = fmaf(f[i], dt, x[i]);
@@ -114,6 +131,7 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
   stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar);
   Diffusion<M>::derive(W);
   __syncthreads();
+  const Scratch sc{W + A::SMEM_FLOATS + threadIdx.x, (int)blockDim.x};
 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= a.G) return;
@@ -128,16 +146,18 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
   uint32_t b0 = 0, b1 = 0;
   if (a.noise_mode == SDE4_NOISE_THREEFRY) {
     const uint32_t* k = a.key + (size_t)p * a.key_sp;
-    brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)n, (uint32_t)a.N, a.rng_mode, b0, b1);
+    brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1);
   }
   const float* up = a.u + (size_t)p * a.u_sp;
   for (int t = 0; t < a.H; ++t) {
-    float u[NU], dw[NX];
+    float u[NU];
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = __ldg(up + (size_t)t * a.u_st + (size_t)j * a.u_sj);
-    if (noisy) draw_noise<NX>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, a.G, g, dw);
+    if (noisy)
+      draw_noise<NX>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, a.G, g, sc.slot(Scratch::SLOT_X), sc.bs,
+                     nullptr);
     float aux;
-    em_step<M>(W, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
+    em_step<M>(W, sc, d, x, u, __ldg(a.dt + t), noisy, aux);
     float* out = a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g;
 #pragma unroll
     for (int i = 0; i < NX; ++i) out[(size_t)i * a.G] = x[i];
@@ -165,6 +185,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar);
   Diffusion<M>::derive(W);
   __syncthreads();
+  const Scratch sc{W + A::SMEM_FLOATS + threadIdx.x, (int)blockDim.x};
 
   const int g0 = blockIdx.x * blockDim.x + threadIdx.x;
   const bool active = g0 < a.G;
@@ -185,7 +206,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   uint32_t b0 = 0, b1 = 0;
   if (a.noise_mode == SDE4_NOISE_THREEFRY) {
     const uint32_t* k = a.key + (size_t)p * a.key_sp;
-    brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)n, (uint32_t)a.N, a.rng_mode, b0, b1);
+    brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1);
   }
 
   // ---------------- forward sweep ----------------
@@ -206,17 +227,11 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   }
   for (int t = 0; t < H; ++t) {
     const float dt = __ldg(a.dt + t);
-    float dw[NX];
-    if (noisy) {
-      draw_noise<NX>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, dw);
-      if (GRAD && active && a.dwbuf) {
-#pragma unroll
-        for (int i = 0; i < NX; ++i)
-          if (d.noise_prior[i] != 0.0f) a.dwbuf[((size_t)t * NX + i) * G + g] = dw[i];
-      }
-    }
+    if (noisy)
+      draw_noise<NX>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, sc.slot(Scratch::SLOT_X), sc.bs,
+                     (GRAD && active && a.dwbuf) ? a.dwbuf + (size_t)t * NX * G + g : nullptr);
     float aux = 0.0f;
-    em_step<M>(W, d, x, u, dw, dt, noisy, aux);
+    em_step<M>(W, sc, d, x, u, dt, noisy, aux);
     if (GRAD && M::NAUX && active) a.auxbuf[(size_t)t * G + g] = aux;
     // control of the next stage: u_{t+1}, the last one repeated (nsde.py:1509)
     const int tn = t + 1 < H ? t + 1 : H - 1;
@@ -258,18 +273,19 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   if (!GRAD) return;
 
   // ---------------- backward sweep ----------------
-  // x holds x_H, u holds u_{H-1}
-  float lam[NX], gu_pend[NU], gs_pend[NX];
+  // x holds x_H, u holds u_{H-1}.  Live state is kept small on purpose (x, lam, gx, u, gu): the
+  // projected state and the noise are re-read from the checkpoint buffers where needed.
+  float lam[NX], gu[NU], gs_pend[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
     lam[i] = 0.0f;
     gs_pend[i] = 0.0f;
   }
 #pragma unroll
-  for (int j = 0; j < NU; ++j) gu_pend[j] = 0.0f;
+  for (int j = 0; j < NU; ++j) gu[j] = 0.0f;  // row H-1 also receives the u-gradient of stage H
   {
     const float wH = 0.5f * __ldg(a.dt + H - 1);
-    stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu_pend);
+    stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
     if (CONSTR) {
       float sl[NX];
 #pragma unroll
@@ -279,15 +295,22 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
                     : 0.0f;
       constr_cost<NX, true>(cd, x, sl, wH, lam, gs_pend);
     }
-    if (a.has_terminal) stage_cost<NX, NU, true>(td, x, u, xr + (size_t)H * NX, false, 1.0f, lam, gu_pend);
+    if (a.has_terminal) {
+      float gu_unused[NU];
+      stage_cost<NX, NU, true>(td, x, u, xr + (size_t)H * NX, false, 1.0f, lam, gu_unused);
+    }
   }
-  float xn[NX];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) xn[i] = x[i];
+  const float* nz = a.noise_mode == SDE4_NOISE_GIVEN ? a.noise : a.dwbuf;
 
   for (int t = H - 1; t >= 0; --t) {
     const float dt = __ldg(a.dt + t);
-    // checkpoint x_t, control u_t, noise dw_t
+    // through the projection (needs the projected x_{t+1}, still in the checkpoint buffer)
+    {
+      float aux = 0.0f;
+      if (M::NAUX) aux = a.auxbuf[(size_t)t * G + g];
+      M::project_vjp(a.xbuf + (size_t)(t + 1) * a.x_rows * G + g, (size_t)G, aux, lam);
+    }
+    // checkpoint x_t and control u_t
     {
       const float* in = a.xbuf + (size_t)t * a.x_rows * G + g;
 #pragma unroll
@@ -295,35 +318,21 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     }
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = __ldg(op + (size_t)t * a.o_st + (size_t)j * a.o_sj);
-    float gu[NU], gs[NX], gx[NX];
+    float gs[NX], gx[NX];
+    if (CONSTR) {
 #pragma unroll
-    for (int j = 0; j < NU; ++j) gu[j] = gu_pend[j];
-#pragma unroll
-    for (int j = 0; j < NU; ++j) gu_pend[j] = 0.0f;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) gs[i] = gs_pend[i];
-    // through the projection
-    float aux = 0.0f;
-    if (M::NAUX) aux = a.auxbuf[(size_t)t * G + g];
-    M::project_vjp(xn, aux, lam);
-    // through x + f dt + sigma dw
-    float vf[NX];
-#pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      gx[i] = lam[i];
-      vf[i] = dt * lam[i];
+      for (int i = 0; i < NX; ++i) gs[i] = gs_pend[i];
     }
-    M::drift_vjp(W, d, x, u, vf, gx, gu);
-    if (noisy) {
-      float vs[NX];
-      const float* nz = a.noise_mode == SDE4_NOISE_GIVEN ? a.noise : a.dwbuf;
+    // through x + f dt + sigma dw
 #pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        float dwi = 0.0f;
-        if (d.noise_prior[i] != 0.0f) dwi = nz[((size_t)t * NX + i) * G + g];
-        vs[i] = dwi * lam[i];
-      }
-      Diffusion<M>::vjp(W, d, x, vs, gx);
+    for (int i = 0; i < NX; ++i) gx[i] = lam[i];
+    {
+      const Scaled<NX> vf{lam, dt};
+      M::drift_vjp(W, sc, d, x, u, vf, gx, gu);
+    }
+    if (noisy) {
+      const float* nzt = nz + (size_t)t * NX * G + g;
+      Diffusion<M>::vjp(W, sc, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
     }
     // stage cost at t: trapezoid weight w_t
     const float wt = t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt;
@@ -348,6 +357,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
         float v = active ? gu[j] : 0.0f;
         if (a.warp_reduce) v = warp_sum(v);
         if (writer) gp[(size_t)j * a.PW + pw] = v;
+        gu[j] = 0.0f;
       }
       if (CONSTR) {
 #pragma unroll
@@ -361,10 +371,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       }
     }
 #pragma unroll
-    for (int i = 0; i < NX; ++i) {
-      lam[i] = gx[i];
-      xn[i] = x[i];
-    }
+    for (int i = 0; i < NX; ++i) lam[i] = gx[i];
   }
 }
 

@@ -52,6 +52,14 @@ struct Arch {
   }
 };
 
+// Lazily scaled cotangent: vf[i] = s * v[i] (avoids materialising dt*lambda in registers).
+template <int N>
+struct Scaled {
+  const float (&v)[N];
+  float s;
+  SDE4_DEV float operator[](int i) const { return s * v[i]; }
+};
+
 // ----------------------------------------------------------------------------
 // quaternion algebra, [w, x, y, z]  (rotor_uav/utils.py:13-63)
 // ----------------------------------------------------------------------------
@@ -93,7 +101,7 @@ struct Diffusion {
     for (int k = 0; k < DNet::IN; ++k) z[k] = red[nth_bit(A::NIN_MASK, k)];
   }
 
-  SDE4_DEV static float eta_of(const float* __restrict__ W, const sde4_model_desc& d, float dens, int k) {
+  SDE4_DEV static float eta_of(const float* W, const sde4_model_desc& d, float dens, int k) {
     float coeff = 0.0f, offs = 0.0f;
     if constexpr (A::HAS_SCALER) {
       coeff = W[A::OFF_DERIVED + k];
@@ -103,7 +111,7 @@ struct Diffusion {
   }
 
   // sig[i] = eta_full[i] * prior[i]
-  SDE4_DEV static void fwd(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void fwd(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
                            float (&sig)[NX]) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) sig[i] = d.noise_prior[i];  // non-noise outputs: eta = 1 (nsde.py:363)
@@ -111,39 +119,39 @@ struct Diffusion {
       float z[DNet::IN > 0 ? DNet::IN : 1];
       gather_in(x, d, z);
       float dens[1];
-      mlp_fwd<DNet>(W + A::OFF_DENSITY, z, dens);
+      mlp_fwd<DNet, false>(W + A::OFF_DENSITY, sc, z, dens);
 #pragma unroll
       for (int k = 0; k < NO; ++k) sig[nth_bit(A::NOUT_MASK, k)] *= eta_of(W, d, dens[0], k);
     }
   }
 
-  // gx += (d sig / d x)^T vs      (sigma does not depend on u: control_dependent_noise unsupported)
-  SDE4_DEV static void vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
-                           const float (&vs)[NX], float (&gx)[NX]) {
+  // Reverse mode of sig wrt x:  gx += (d sig / d x)^T (dw o lam), with the noise read on the fly.
+  // The density gradient J = d dens / d x does not depend on the cotangent, so it is formed
+  // first (fused value+gradient pass) and scaled afterwards.
+  template <class NoiseAt>
+  SDE4_DEV static void vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+                           const float (&lam)[NX], NoiseAt noise_at, float (&gx)[NX]) {
     if constexpr (!A::HAS_DENSITY) {
       return;
     } else {
-    float z[DNet::IN > 0 ? DNet::IN : 1];
-    gather_in(x, d, z);
-    float dens[1], d1[DNet::H1 > 0 ? DNet::H1 : 1], d2[DNet::H2 > 0 ? DNet::H2 : 1];
-    mlp_fwd_keep<DNet>(W + A::OFF_DENSITY, z, dens, d1, d2);
-    float gd[1] = {0.0f};
+      float z[DNet::IN], J[DNet::IN], dens;
+      gather_in(x, d, z);
+      mlp_scalar_value_grad<DNet>(W + A::OFF_DENSITY, sc, z, dens, J);
+      float gd = 0.0f;
 #pragma unroll
-    for (int k = 0; k < NO; ++k) {
-      const int i = nth_bit(A::NOUT_MASK, k);
-      float coeff = 0.0f;
-      if constexpr (A::HAS_SCALER) coeff = W[A::OFF_DERIVED + k];
-      float e = eta_of(W, d, dens[0], k);
-      gd[0] = fmaf(vs[i] * d.noise_prior[i], e * (1.0f - e) * (d.aggr + coeff), gd[0]);
-    }
-    float gz[DNet::IN > 0 ? DNet::IN : 1];
-    mlp_bwd<DNet>(W + A::OFF_DENSITY, d1, d2, gd, gz);
-    float gred[M::NR];
+      for (int k = 0; k < NO; ++k) {
+        const int i = nth_bit(A::NOUT_MASK, k);
+        float coeff = 0.0f;
+        if constexpr (A::HAS_SCALER) coeff = W[A::OFF_DERIVED + k];
+        const float e = eta_of(W, d, dens, k);
+        gd = fmaf(noise_at(i) * lam[i] * d.noise_prior[i], e * (1.0f - e) * (d.aggr + coeff), gd);
+      }
+      float gred[M::NR];
 #pragma unroll
-    for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
+      for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
 #pragma unroll
-    for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = gz[k];
-    M::reduced_state_vjp(x, d, gred, gx);
+      for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = gd * J[k];
+      M::reduced_state_vjp(x, d, gred, gx);
     }
   }
 
@@ -177,7 +185,7 @@ struct MsdModel {
     gx[1] += g[1];
   }
 
-  SDE4_DEV static void drift(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
                              const float (&u)[NU], float (&f)[NX]) {
     const float m = d.cfloat[0], k = d.cfloat[1], b = d.cfloat[2];
     const float u0 = CTRL ? u[0] : 0.0f;
@@ -186,17 +194,17 @@ struct MsdModel {
       f[1] = (u0 - k * x[0] - b * x[1]) / m;
     } else if constexpr (SI) {
       float in[1] = {x[1]}, out[1];
-      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
       f[1] = (u0 - k * x[0] + out[0]) / m;
     } else {
       float in[2] = {x[0], x[1]}, out[1];
-      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
       f[1] = out[0];
     }
   }
 
-  SDE4_DEV static void drift_vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
-                                 const float (&u)[NU], const float (&vf)[NX], float (&gx)[NX], float (&gu)[NU]) {
+  SDE4_DEV static void drift_vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+                                 const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
     const float m = d.cfloat[0], k = d.cfloat[1], b = d.cfloat[2];
     gx[1] += vf[0];
     if constexpr (GT) {
@@ -209,18 +217,18 @@ struct MsdModel {
       gx[0] -= k * s;
       if constexpr (CTRL) gu[0] += s;
       float in[1] = {x[1]}, go[1] = {s}, gi[1];
-      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
       gx[1] += gi[0];
     } else {
       float in[2] = {x[0], x[1]}, go[1] = {vf[1]}, gi[2];
-      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
       gx[0] += gi[0];
       gx[1] += gi[1];
     }
   }
 
   SDE4_DEV static void project(float (&)[NX], float&) {}
-  SDE4_DEV static void project_vjp(const float (&)[NX], float, float (&)[NX]) {}
+  SDE4_DEV static void project_vjp(const float*, size_t, float, float (&)[NX]) {}
 };
 
 // ----------------------------------------------------------------------------
@@ -252,7 +260,7 @@ struct CartpoleModel {
     gx[3] += g[3] * d.inv_red_scale;
   }
 
-  SDE4_DEV static void drift(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
                              const float (&u)[NU], float (&f)[NX]) {
     float s, c;
     sincosf(x[2], &s, &c);
@@ -262,21 +270,21 @@ struct CartpoleModel {
     f[2] = x[3];
     if constexpr (!SI) {
       float in[4] = {s, c, thd_sc, u[0]}, out[2];
-      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
       f[1] = sc0 * out[0];
       f[3] = sc1 * out[1];
     } else {
       float in[3] = {s, c, thd_sc}, out[2];
-      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
       float cin[2] = {c, c * c}, ce[2];
-      mlp_fwd<NetB>(W + A::OFF_NET_B, cin, ce);
+      mlp_fwd<NetB, false>(W + A::OFF_NET_B, sc, cin, ce);
       f[1] = sc0 * (out[0] + ce[0] * u[0]);
       f[3] = sc1 * (out[1] + ce[1] * u[0]);
     }
   }
 
-  SDE4_DEV static void drift_vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
-                                 const float (&u)[NU], const float (&vf)[NX], float (&gx)[NX], float (&gu)[NU]) {
+  SDE4_DEV static void drift_vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+                                 const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
     float s, c;
     sincosf(x[2], &s, &c);
     const float thd_sc = x[3] * d.inv_state_scaling[3];
@@ -286,7 +294,7 @@ struct CartpoleModel {
     float gs = 0.0f, gc = 0.0f;  // cotangents of sin(theta), cos(theta)
     if constexpr (!SI) {
       float in[4] = {s, c, thd_sc, u[0]}, go[2] = {sc0 * vf[1], sc1 * vf[3]}, gi[4];
-      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
       gs = gi[0];
       gc = gi[1];
       gx[3] += gi[2] * d.inv_state_scaling[3];
@@ -295,17 +303,17 @@ struct CartpoleModel {
       const float go0 = sc0 * vf[1], go1 = sc1 * vf[3];
       {
         float in[3] = {s, c, thd_sc}, go[2] = {go0, go1}, gi[3];
-        mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, in, go, gi);
+        mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
         gs = gi[0];
         gc = gi[1];
         gx[3] += gi[2] * d.inv_state_scaling[3];
       }
       {
-        float cin[2] = {c, c * c}, ce[2], d1[NetB::H1 > 0 ? NetB::H1 : 1], d2[NetB::H2 > 0 ? NetB::H2 : 1];
-        mlp_fwd_keep<NetB>(W + A::OFF_NET_B, cin, ce, d1, d2);
+        float cin[2] = {c, c * c}, ce[2];
+        mlp_fwd<NetB, true>(W + A::OFF_NET_B, sc, cin, ce);
         gu[0] += go0 * ce[0] + go1 * ce[1];
         float gce[2] = {go0 * u[0], go1 * u[0]}, gcin[2];
-        mlp_bwd<NetB>(W + A::OFF_NET_B, d1, d2, gce, gcin);
+        mlp_bwd<NetB>(W + A::OFF_NET_B, sc, gce, gcin);
         gc += gcin[0] + 2.0f * c * gcin[1];
       }
     }
@@ -313,7 +321,7 @@ struct CartpoleModel {
   }
 
   SDE4_DEV static void project(float (&)[NX], float&) {}
-  SDE4_DEV static void project_vjp(const float (&)[NX], float, float (&)[NX]) {}
+  SDE4_DEV static void project_vjp(const float*, size_t, float, float (&)[NX]) {}
 };
 
 // ----------------------------------------------------------------------------
@@ -382,7 +390,7 @@ struct RotorModel {
     return fmaf(fmaf(3.0f * S[7], u, 2.0f * S[8]), u, S[9]);
   }
 
-  SDE4_DEV static void drift(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
                              const float (&u)[NU], float (&f)[NX]) {
     const float* __restrict__ S = W + A::OFF_SCALARS;
     const Quat q{x[6], x[7], x[8], x[9]};
@@ -397,7 +405,7 @@ struct RotorModel {
       float in[NetA::IN > 0 ? NetA::IN : 1], out[3];
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      mlp_fwd<NetA>(W + A::OFF_NET_A, in, out);
+      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
       Fb[0] = out[0];
       Fb[1] = out[1];
       Fb[2] = out[2];
@@ -411,7 +419,7 @@ struct RotorModel {
       float in[NetB::IN > 0 ? NetB::IN : 1], out[3];
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      mlp_fwd<NetB>(W + A::OFF_NET_B, in, out);
+      mlp_fwd<NetB, false>(W + A::OFF_NET_B, sc, in, out);
       Mt[0] = out[0];
       Mt[1] = out[1];
       Mt[2] = out[2];
@@ -451,8 +459,8 @@ struct RotorModel {
     f[9] = 0.5f * qd.z;
   }
 
-  SDE4_DEV static void drift_vjp(const float* __restrict__ W, const sde4_model_desc& d, const float (&x)[NX],
-                                 const float (&u)[NU], const float (&vf)[NX], float (&gx)[NX], float (&gu)[NU]) {
+  SDE4_DEV static void drift_vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+                                 const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
     const float* __restrict__ S = W + A::OFF_SCALARS;
     const Quat q{x[6], x[7], x[8], x[9]};
     const Quat qc = qconj(q);
@@ -512,14 +520,13 @@ struct RotorModel {
     float Fb[3] = {0.0f, 0.0f, 0.0f};
     if constexpr (HAS_F) {
       float in[NetA::IN > 0 ? NetA::IN : 1], gi[NetA::IN > 0 ? NetA::IN : 1], out[3];
-      float d1[NetA::H1 > 0 ? NetA::H1 : 1], d2[NetA::H2 > 0 ? NetA::H2 : 1];
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      mlp_fwd_keep<NetA>(W + A::OFF_NET_A, in, out, d1, d2);
+      mlp_fwd<NetA, true>(W + A::OFF_NET_A, sc, in, out);
       Fb[0] = out[0];
       Fb[1] = out[1];
       Fb[2] = out[2];
-      mlp_bwd<NetA>(W + A::OFF_NET_A, d1, d2, gFb, gi);
+      mlp_bwd<NetA>(W + A::OFF_NET_A, sc, gFb, gi);
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) gin6[nth_bit(A::A_MASK, k)] += gi[k];
     }
@@ -557,7 +564,7 @@ struct RotorModel {
       float in[NetB::IN > 0 ? NetB::IN : 1], gi[NetB::IN > 0 ? NetB::IN : 1];
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      mlp_fwd_vjp<NetB>(W + A::OFF_NET_B, in, gM, gi);
+      mlp_fwd_vjp<NetB>(W + A::OFF_NET_B, sc, in, gM, gi);
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) gin6[nth_bit(A::B_MASK, k)] += gi[k];
     }
@@ -600,11 +607,15 @@ struct RotorModel {
     z[9] *= r;
     aux = r;
   }
-  // lam (wrt projected state) -> lam (wrt z), given the projected state xn and aux = 1/|q_z|
-  SDE4_DEV static void project_vjp(const float (&xn)[NX], float aux, float (&lam)[NX]) {
-    const float dot = xn[6] * lam[6] + xn[7] * lam[7] + xn[8] * lam[8] + xn[9] * lam[9];
-#pragma unroll
-    for (int i = 6; i < 10; ++i) lam[i] = (lam[i] - xn[i] * dot) * aux;
+  // lam (wrt projected state) -> lam (wrt z); the projected quaternion is re-read from the
+  // checkpoint buffer (xn[i*stride] = state i of x_{t+1}) and aux = 1/|q_z|
+  SDE4_DEV static void project_vjp(const float* __restrict__ xn, size_t stride, float aux, float (&lam)[NX]) {
+    const float q0 = xn[6 * stride], q1 = xn[7 * stride], q2 = xn[8 * stride], q3 = xn[9 * stride];
+    const float dot = q0 * lam[6] + q1 * lam[7] + q2 * lam[8] + q3 * lam[9];
+    lam[6] = (lam[6] - q0 * dot) * aux;
+    lam[7] = (lam[7] - q1 * dot) * aux;
+    lam[8] = (lam[8] - q2 * dot) * aux;
+    lam[9] = (lam[9] - q3 * dot) * aux;
   }
 };
 

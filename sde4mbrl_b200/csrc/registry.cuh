@@ -21,10 +21,22 @@ struct ArchEntry {
 
 std::vector<ArchEntry>& arch_table();
 
+// dynamic shared memory: parameter image + derived constants + per-thread scratch columns
+template <class A>
+constexpr size_t smem_bytes(int threads) {
+  return sizeof(float) * ((size_t)A::SMEM_FLOATS + (size_t)Scratch::NSLOTS * MAXW * threads);
+}
+
 template <class M>
 cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
-  k_rollout<M><<<blocks, threads, A::SMEM_FLOATS * sizeof(float), s>>>(d, a);
+  const size_t sm = smem_bytes<A>(threads);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<A>(256));
+    attr_set = true;
+  }
+  k_rollout<M><<<blocks, threads, sm, s>>>(d, a);
   return cudaGetLastError();
 }
 
@@ -32,7 +44,16 @@ template <class M>
 cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td,
                           const CostK& a, bool grad, bool constr, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
-  const size_t sm = A::SMEM_FLOATS * sizeof(float);
+  const size_t sm = smem_bytes<A>(threads);
+  static bool attr_set = false;
+  if (!attr_set) {
+    const int mx = (int)smem_bytes<A>(256);
+    cudaFuncSetAttribute(k_cost<M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_cost<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_cost<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    cudaFuncSetAttribute(k_cost<M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+    attr_set = true;
+  }
   if (grad) {
     if (constr)
       k_cost<M, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
@@ -63,7 +84,7 @@ ArchEntry make_entry(const char* name) {
   e.offsets[3] = A::OFF_NET_A;
   e.offsets[4] = A::OFF_NET_B;
   e.offsets[5] = A::PARAM_TOTAL;
-  e.smem_bytes = A::SMEM_FLOATS * (int)sizeof(float);
+  e.smem_bytes = (int)smem_bytes<A>(32);
   e.macs = A::MACS;
   e.launch_rollout = &launch_rollout_t<M>;
   e.launch_cost = &launch_cost_t<M>;

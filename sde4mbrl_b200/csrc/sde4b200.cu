@@ -148,6 +148,9 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void*
   k.x_rows = a->x_rows;
   k.rng_mode = a->rng_mode;
   k.noise_mode = a->noise_mode;
+  k.n_off = a->particle_total > 0 ? a->particle_offset : 0;
+  k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
+  if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   const int threads = pick_threads(a->block_threads, G);
   const int blocks = (int)((G + threads - 1) / threads);
   cudaError_t err = e->launch_rollout(*model, k, blocks, threads, (cudaStream_t)stream);
@@ -227,6 +230,9 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   k.n_slack = cd.n_slack;
   k.warp_reduce = L.warp_reduce;
   k.PW = L.PW;
+  k.n_off = a->particle_total > 0 ? a->particle_offset : 0;
+  k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
+  if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   k.has_terminal = (a->terminal && a->terminal->kind != SDE4_COST_NONE) ? 1 : 0;
   const sde4_cost_desc td = k.has_terminal ? *a->terminal : empty_cost();
   int threads = pick_threads(a->block_threads, G);
@@ -245,13 +251,13 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   r.cost = a->cost;
   r.grad = a->grad;
   r.P = a->P;
-  r.N = a->N;
+  r.N = k.n_tot;
   r.H = a->H;
   r.n_u = e->nu;
   r.n_opt = e->nu + cd.n_slack;
   r.PW = L.PW;
   r.NP = L.NP;
-  r.has_slew = cd.has_slew;
+  r.has_slew = (cd.has_slew && k.n_off == 0) ? 1 : 0;
   r.res_mult = cd.res_mult;
   for (int j = 0; j < SDE4_MAX_NU; ++j) r.slew[j] = cd.u_slew_coeff[j];
   const long long items = (long long)(a->H * r.n_opt + 1) * a->P;

@@ -125,6 +125,7 @@ class ControlledSDE:
 
     # ---- parameter trees ------------------------------------------------
     def _pack_net(self, out, base, tree, prefix, nd):
+        """w0[in][h1p] b0[h1p] w1[h1][h2p] b1[h2p] w2T[out][h2p] b2[outp]  (csrc/nets.cuh)."""
         o = base
         dims = [nd.n_in, nd.h1, nd.h2, nd.n_out]
         for k in range(3):
@@ -135,13 +136,17 @@ class ControlledSDE:
             b = np.asarray(tree[key]["b"], np.float32)
             if w.shape != (dims[k], dims[k + 1]) or b.shape != (dims[k + 1],):
                 raise Sde4Error("parameter shape mismatch at '%s': %s" % (key, w.shape))
-            outp = _up4(dims[k + 1])
-            wp = np.zeros((dims[k], outp), np.float32)
-            wp[:, :dims[k + 1]] = w
+            if k < 2:
+                outp = _up4(dims[k + 1])
+                wp = np.zeros((dims[k], outp), np.float32)
+                wp[:, :dims[k + 1]] = w
+            else:  # last layer stored transposed: [out][up4(in)]
+                wp = np.zeros((dims[k + 1], _up4(dims[k])), np.float32)
+                wp[:, :dims[k]] = w.T
             out[o:o + wp.size] = wp.ravel()
             o += wp.size
             out[o:o + dims[k + 1]] = b
-            o += outp
+            o += _up4(dims[k + 1])
         return o
 
     def pack(self, nn_params, desc=None):

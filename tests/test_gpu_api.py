@@ -1,0 +1,133 @@
+"""The reference-facing Python API (nsde.py factories, apg.py solver) on the GPU: shapes, views,
+differentiability through torch autograd, and APG iterate parity against the oracle APG driving
+the oracle cost."""
+import contextlib
+import io as _io
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as hp
+from oracle import apg_oracle
+from oracle import nsde_oracle as orc
+from oracle import threefry as tf
+from sde4mbrl_b200 import configs, costs, sde_models
+
+pytestmark = pytest.mark.gpu
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(_io.StringIO()):
+        return fn(*a, **k)
+
+
+def test_create_sampling_fn_shapes_and_values(cuda):
+    from sde4mbrl_b200 import nsde, random as R
+    pm = configs.hexa_model(horizon=15, num_particles=9)
+    nn0, multi_sampling = nsde.create_sampling_fn(pm, sde_constr=sde_models.SDERotorModel)
+    assert "sde_rotor_model" in nn0
+    nn = configs.random_params(sde_models.SDERotorModel(pm), seed=2)
+    rng = np.random.default_rng(0)
+    y0, u = hp.start_state("hexa", rng), hp.controls("hexa", 15, rng)
+    key = R.PRNGKey(5)
+    x, y, uev = multi_sampling(nn, y0, u, key)
+    assert tuple(x.shape) == (9, 16, 13) and tuple(y.shape) == (9, 16, 13) and tuple(uev.shape) == (9, 15, 6)
+    want, _ = orc.sample_rollouts(hp.oracle_model("hexa", pm, nn), y0, u, tf.PRNGKey(5), 9)
+    assert hp.rel_err(x.cpu().numpy(), want.numpy()) < 2e-5
+    np.testing.assert_array_equal(uev[3].cpu().numpy(), u)
+    with pytest.raises(Exception):
+        multi_sampling(nn, y0, u, key, extra_args=(1,))
+    with pytest.raises(AssertionError):
+        multi_sampling(nn, y0, u[:-1], key)
+
+
+def test_one_step_sampling_squeezes(cuda):
+    from sde4mbrl_b200 import nsde, random as R
+    pm = configs.cartpole_model(horizon=7, num_particles=1)
+    one = nsde.create_one_step_sampling(pm, sde_constr=sde_models.CartPoleSDE)
+    nn = configs.random_params(sde_models.CartPoleSDE(pm), seed=1)
+    x, _, uev = one(nn, np.array([0, 0, 3.0, 0], np.float32), np.array([0.3], np.float32), R.PRNGKey(1))
+    assert tuple(x.shape) == (2, 4) and tuple(uev.shape) == (1, 1)
+    many = nsde.create_one_step_sampling(pm, sde_constr=sde_models.CartPoleSDE, num_samples=10)
+    x, _, _ = many(nn, np.array([0, 0, 3.0, 0], np.float32), np.array([0.3], np.float32), R.PRNGKey(1))
+    assert tuple(x.shape) == (10, 2, 4)
+
+
+def _mpc_setup(N, H=20, max_iter=6):
+    from sde4mbrl_b200 import nsde
+    pm = configs.hexa_model(horizon=H, num_particles=N, stepsize=0.05)
+    mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=N, max_iter=max_iter)
+    out = _quiet(nsde.create_online_cost_sampling_fn, pm, mpc, sde_constr=sde_models.SDERotorModel)
+    nn = configs.random_params(sde_models.SDERotorModel(pm), seed=3)
+    return pm, mpc, nn, out
+
+
+def test_online_cost_sampling_value_grad_and_xtraj(cuda):
+    from sde4mbrl_b200 import random as R
+    N, H = 16, 20
+    pm, mpc, nn, (_, multi_cost, prox, constr_cost, construct_opt) = _mpc_setup(N, H)
+    assert constr_cost is None and prox is not None
+    cp = mpc["cost_params"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    rng = np.random.default_rng(1)
+    y0 = hp.start_state("hexa", rng)
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    opt = construct_opt(u=np.full(6, 0.33, np.float32))
+    assert tuple(opt.shape) == (H, 6) and abs(float(opt[0, 0]) - 0.3302) < 1e-6  # the doubled +1e-4 (nsde.py:1545,1563)
+    opt = opt.clone().requires_grad_(True)
+    c, xtraj = multi_cost(nn, y0, opt, R.PRNGKey(9), stage, extra_cost_args=xref)
+    (g,) = torch.autograd.grad(c, opt)
+    assert tuple(xtraj.shape) == (N, H + 1, 14)
+    dw = tf.rollout_noise(tf.PRNGKey(9), N, H, 13)
+    om = hp.oracle_model("hexa", pm, nn, torch.float64)
+    o = opt.detach().cpu().double().requires_grad_(True)
+    c64, xt = orc.compute_cost(om, torch.tensor(y0, dtype=torch.float64), o, torch.tensor(dw, dtype=torch.float64),
+                               hp.stage_cost_fn("hexa", cp), torch.tensor(xref, dtype=torch.float64))
+    c64 = c64 + orc.u_slew_cost(o, orc.compute_timesteps(pm), cp, 6)
+    (g64,) = torch.autograd.grad(c64, o)
+    assert abs(float(c) - float(c64)) < 2e-5 * abs(float(c64))
+    assert hp.rel_err(g.cpu().numpy(), g64.numpy()) < 1e-3
+    assert hp.rel_err(xtraj.cpu().numpy(), xt.detach().numpy()) < 1e-4
+    lo = float(prox(torch.full((H, 6), -3.0, device="cuda")).min())
+    assert abs(lo - 1e-4) < 1e-9  # box clip to [1e-4, 1] (mpc_test_cfg.yaml:10-13)
+
+
+def test_apg_mpc_trace_matches_oracle(cuda):
+    """One MPC solve: host APG (CUDA cost/grad) vs oracle APG (oracle cost/grad), same noise."""
+    from sde4mbrl_b200 import apg, random as R
+    N, H, iters = 8, 20, 6
+    pm, mpc, nn, (_, multi_cost, vprox, _, construct_opt) = _mpc_setup(N, H, iters)
+    cp, op = mpc["cost_params"], mpc["apg_mpc"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    rng = np.random.default_rng(2)
+    y0 = hp.start_state("hexa", rng)
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    key = R.PRNGKey(21)
+    cost_gpu = lambda o: multi_cost(nn, y0, o, key, stage, extra_cost_args=xref)[0]
+    prox_gpu = lambda x, stepsize=None: vprox(x)
+    x0 = construct_opt(u=np.full(6, 0.33, np.float32))
+    s = apg.apg(apg.init_apg(x0, cost_gpu, op), cost_gpu, op, proximal_fn=prox_gpu)
+    # oracle side
+    dw = torch.tensor(tf.rollout_noise(tf.PRNGKey(21), N, H, 13), dtype=torch.float64)
+    om = hp.oracle_model("hexa", pm, nn, torch.float64)
+    ts = orc.compute_timesteps(pm)
+    y64, xr64 = torch.tensor(y0, dtype=torch.float64), torch.tensor(xref, dtype=torch.float64)
+    cost_cpu = lambda o: orc.compute_cost(om, y64, o, dw, hp.stage_cost_fn("hexa", cp), xr64)[0] + orc.u_slew_cost(o, ts, cp, 6)
+    prox_cpu = lambda x, stepsize=None: torch.clamp(x, 1e-4, 1.0)
+    so = apg_oracle.apg(apg_oracle.init_apg(x0.cpu().double(), cost_cpu, op), cost_cpu, op, proximal_fn=prox_cpu)
+    assert s.num_steps == so.num_steps == iters + 1
+    assert float(s.opt_cost) < float(s.init_cost)
+    np.testing.assert_allclose(float(s.opt_cost), float(so.opt_cost), rtol=2e-4)
+    np.testing.assert_allclose(float(s.stepsize), float(so.stepsize), rtol=1e-5)
+    assert hp.rel_err(s.x_opt.cpu().numpy(), so.x_opt.numpy()) < 2e-3
+
+
+def test_rejects_python_cost_callables(cuda):
+    from sde4mbrl_b200 import random as R
+    from sde4mbrl_b200._lib import Sde4Error
+    pm, mpc, nn, (_, multi_cost, _, _, construct_opt) = _mpc_setup(4, 20)
+    with pytest.raises(Sde4Error):
+        multi_cost(nn, hp.start_state("hexa", np.random.default_rng(0)), construct_opt(), R.PRNGKey(0),
+                   lambda x, u, e: 0.0, extra_cost_args=np.zeros((21, 13), np.float32))

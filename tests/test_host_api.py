@@ -1,0 +1,80 @@
+"""Host-side mirror of the reference interface (no GPU needed): time steps, constraint set-up,
+cost descriptors, parameter packing, argument errors."""
+import numpy as np
+import pytest
+
+from sde4mbrl_b200 import _lib as L
+from sde4mbrl_b200 import configs, costs, nsde, sde_models
+
+
+def test_compute_timesteps():
+    p = {"horizon": 5, "stepsize": 0.1}
+    np.testing.assert_allclose(nsde.compute_timesteps(p), [0.1] * 5)
+    p = {"horizon": 5, "stepsize": 0.1, "num_short_dt": 2, "short_step_dt": 0.01, "long_step_dt": 0.2}
+    np.testing.assert_allclose(nsde.compute_timesteps(p), [0.01, 0.01, 0.2, 0.2, 0.2])
+    with pytest.raises(AssertionError):
+        nsde.compute_timesteps({"horizon": 2, "stepsize": 0.1, "num_short_dt": 3})
+
+
+def test_initialize_problem_constraints(capsys):
+    (hu, lb, ub), (hx, sp, idx, pen, slb, sub, w, ss) = nsde.initialize_problem_constraints(
+        4, 2, {"input_constr": {"input_id": [1], "input_bound": [[-1.0, 2.0]]},
+               "state_constr": {"state_id": [0, 3], "state_bound": [[-1, 1], [-4, 2]], "state_penalty": [1.0, 2.0],
+                                "slack_proximal": True, "slack_scaling": [1.0, 2.0], "constr_pen": 3.0}})
+    assert hu and hx and sp and w == 3.0
+    assert lb[0] == -np.inf and lb[1] == -1.0 and ub[1] == 2.0
+    np.testing.assert_allclose(slb, [-1.0, -2.0])
+    np.testing.assert_allclose(sub, [1.0, 1.0])
+    (hu, _, _), (hx, *_rest) = nsde.initialize_problem_constraints(4, 2, {})
+    assert not hu and not hx
+
+
+def test_rotor_cost_descriptor_follows_cost_params():
+    cp = configs.hexa_mpc()["cost_params"]
+    c = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6).desc
+    assert c.kind == L.COST_ROTOR_TRACK and abs(c.res_mult - 0.01) < 1e-9 and c.has_slew == 1
+    assert list(c.w_x)[:13] == [20, 20, 40, 3, 3, 3, 0] + [pytest.approx(0.1), pytest.approx(0.1), 20, 3, 3, 3]
+    assert all(abs(c.w_u[j] - 0.01) < 1e-9 and abs(c.uref[j] - 0.33) < 1e-7 for j in range(6))
+    with pytest.raises(L.Sde4Error):
+        costs.one_step_cost_f(dict(cp, urate_err=1.0), 6)
+    with pytest.raises(L.Sde4Error):
+        costs.one_step_cost_f(cp, 6)(None, None, None)  # not a Python callable
+
+
+def test_pack_layout_roundtrip():
+    m = sde_models.CartPoleSDE(configs.cartpole_model(horizon=3, num_particles=2))
+    nn = m.init_params(seed=1)
+    d = m.describe()
+    off, total = m.layout(d)
+    p = m.pack(nn, d)
+    sc = nn["cart_pole_sde"]["scaler"]
+    np.testing.assert_array_equal(p[off[1]:off[1] + 4], sc)
+    w0 = nn["cart_pole_sde/~init_residual_networks/res_forces/~/linear_0"]["w"]      # [3, 8]
+    np.testing.assert_array_equal(p[off[3]:off[3] + 24].reshape(3, 8), w0)
+    w2 = nn["cart_pole_sde/~init_residual_networks/res_forces/~/linear_2"]["w"]      # [24, 2], stored transposed
+    base = off[3] + 3 * 8 + 8 + 8 * 24 + 24
+    np.testing.assert_array_equal(p[base:base + 48].reshape(2, 24), w2.T)
+
+
+def test_motor_polynomial_and_fixed_params():
+    pm = configs.hexa_model(horizon=2, num_particles=1)
+    m = sde_models.SDERotorModel(pm)
+    nn = configs.random_params(m, seed=0)
+    p = m.pack(nn)
+    # order 1 with constant term: thrust = coeffMot0*u + coeffMot1 -> c3=c2=0, c1=coeffMot0, c0=coeffMot1
+    assert p[7] == 0 and p[8] == 0 and p[9] == np.float32(9.169) and p[10] == np.float32(0.786)
+    pm2 = dict(pm, fixed_init_params=True)
+    m2 = sde_models.SDERotorModel(pm2)
+    p2 = m2.pack(nn)
+    assert p2[0] == np.float32(2.295)  # get_param returns the YAML constant (sde_rotor_model.py:146-158)
+
+
+def test_errors_for_unsupported_requests():
+    with pytest.raises(L.Sde4Error):
+        nsde.create_sampling_fn(configs.hexa_model(2, 1), sde_constr=object)
+    with pytest.raises(L.Sde4Error):
+        sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), control_augmented_state=True)).describe()
+    with pytest.raises(L.Sde4Error):
+        sde_models.CartPoleSDE(dict(configs.cartpole_model(2, 1), control_dependent_noise=True))
+    with pytest.raises(L.Sde4Error):
+        sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), sde_solver="stratonovich_heun"))
