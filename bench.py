@@ -147,6 +147,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-threads", type=int, default=0)
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per sample (0 = library heuristic)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -177,7 +178,7 @@ def main():
 
     def step_device():
         cost, grad, _ = eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART,
-                                      want_grad=True, block_threads=args.block_threads,
+                                      want_grad=True, block_threads=args.block_threads, lanes=args.lanes,
                                       particle_offset=rank * N_PART, particle_total=n_total)
         if world > 1:
             red[0:1].copy_(cost)
@@ -298,7 +299,8 @@ def main():
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART, want_grad=True,
-                          block_threads=args.block_threads, particle_offset=rank * N_PART, particle_total=n_total)
+                          block_threads=args.block_threads, particle_offset=rank * N_PART, particle_total=n_total,
+                          lanes=args.lanes)
             e1.record()
             torch.cuda.synchronize()
             kt.append(e0.elapsed_time(e1))
@@ -317,7 +319,7 @@ def main():
             flush.fill_(1)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            eng.rollout(pk, y0_d, opt_d, ts, key=key_d, N=N_PART)
+            eng.rollout(pk, y0_d, opt_d, ts, key=key_d, N=N_PART, lanes=args.lanes)
             e1.record()
             torch.cuda.synchronize()
             ft.append(e0.elapsed_time(e1))

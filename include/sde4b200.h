@@ -159,6 +159,9 @@ typedef struct sde4_rollout_args {
    * particle_offset+N) of particle_total per problem (keys are split(rng, particle_total)).
    * particle_total == 0 means (offset 0, total N). */
   int32_t particle_offset, particle_total;
+  /* lanes per sample: 0 = library heuristic, 1 = one thread per sample, L > 1 = lane-split kernel
+   * (only if compiled for this architecture, else an error) */
+  int32_t lanes;
 } sde4_rollout_args;
 
 int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, void* stream);
@@ -195,8 +198,10 @@ typedef struct sde4_cost_args {
    * SUM all-reduce over the shards gives the mean over all particles.  The slew term is added by
    * the shard with particle_offset == 0 only. */
   int32_t particle_offset, particle_total;
+  int32_t lanes;                /* see sde4_rollout_args */
 } sde4_cost_args;
 
+/* Upper bound over the lane / noise modes the launcher may pick. */
 size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_t N, int32_t H,
                                  int32_t n_slack, int32_t want_grad, int32_t have_xtraj);
 int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* args, void* stream);

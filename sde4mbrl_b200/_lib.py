@@ -63,7 +63,7 @@ class RolloutArgs(C.Structure):
                 ("dt", C.c_void_p), ("key", C.c_void_p), ("key_stride_p", C.c_int64),
                 ("rng_mode", C.c_int32), ("noise_mode", C.c_int32), ("noise", C.c_void_p),
                 ("xevol", C.c_void_p), ("x_rows", C.c_int32), ("block_threads", C.c_int32),
-                ("particle_offset", C.c_int32), ("particle_total", C.c_int32)]
+                ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32)]
 
 
 class CostArgs(C.Structure):
@@ -76,7 +76,7 @@ class CostArgs(C.Structure):
                 ("stage", C.POINTER(CostDesc)), ("terminal", C.POINTER(CostDesc)),
                 ("cost", C.c_void_p), ("grad", C.c_void_p), ("xtraj", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("block_threads", C.c_int32),
-                ("particle_offset", C.c_int32), ("particle_total", C.c_int32)]
+                ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32)]
 
 
 EXPORTED_SYMBOLS = (

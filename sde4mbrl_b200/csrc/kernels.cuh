@@ -68,21 +68,95 @@ struct ReduceK {
   float slew[SDE4_MAX_NU];
 };
 
-// dw_t for one sample, written to the per-thread scratch column `dwc` (element i at dwc[i*bs]);
-// components with zero prior diffusion are never generated.  ROLLED over the state index (the
-// threefry block is ~100 instructions; unrolling it 13x only bloats the instruction stream).
+// ------------------------------------------------------------------------------------------------
+// Per-thread kernel context: which sample this thread works on, its lane within the sample's lane
+// group (EvL kernels) and the evaluator context.
+// ------------------------------------------------------------------------------------------------
+template <class M>
+struct Tctx {
+  static constexpr int L = M::Ev::L;
+  typename M::Ev::Ctx ev;
+  int l;  // lane within the sample (0 for one-thread-per-sample kernels)
+};
+
+// Prologue shared by K1/K2: stage the parameter image with one bulk async copy, derive the
+// state-independent constants, build the bank-spread w1 copies (lane-split kernels) and set up the
+// per-thread context.  Returns the thread's global sample slot (may be >= G: inactive).
+template <class M>
+SDE4_DEV int kernel_prologue(float* W, const float* params, uint64_t* mbar, Tctx<M>& tc) {
+  using A = typename M::A;
+  constexpr int L = M::Ev::L;
+  stage_params_bulk(W, params, A::PARAM_TOTAL * sizeof(float), mbar);
+  Diffusion<M>::derive(W);
+  if constexpr (L > 1) {
+    auto pad_copy = [&](auto net_tag, int off_net, int off_pad) {
+      using N = decltype(net_tag);
+      if constexpr (N::PRESENT) {
+        constexpr int B1 = N::H1 / L;
+        for (int e = threadIdx.x; e < N::H1 * N::H2P; e += blockDim.x) {
+          const int row = e / N::H2P, col = e - row * N::H2P;
+          W[off_pad + row * N::H2P + (row / B1) * 4 + col] = W[off_net + N::OFF_W1 + e];
+        }
+      }
+    };
+    pad_copy(typename A::DNet{}, A::OFF_DENSITY, A::off_w1p(0, L));
+    pad_copy(typename A::NetA{}, A::OFF_NET_A, A::off_w1p(1, L));
+    pad_copy(typename A::NetB{}, A::OFF_NET_B, A::off_w1p(2, L));
+  }
+  __syncthreads();
+  const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (L == 1) {
+    tc.ev = Scratch{W + A::smem_floats(1) + threadIdx.x, (int)blockDim.x};
+    tc.l = 0;
+    return gt;
+  } else {
+    tc.l = threadIdx.x & (L - 1);
+    tc.ev.l = tc.l;
+    return gt / L;
+  }
+}
+
+// dw_t for one sample.  Components with zero prior diffusion are never generated.
+//   one thread per sample: ROLLED over the state index in groups of 4 (ILP across the serial
+//     threefry chains), values parked in the thread's scratch column;
+//   lane-split: lane l generates elements l, l+L, ... and the group exchanges them by SHFL.
 // `keep` (optional) receives a copy for the backward sweep: keep[i*G] = dw_i.
-template <int NX>
+template <class M>
 SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode, const float* __restrict__ noise,
-                         uint32_t b0, uint32_t b1, int t, int H, int G, int g, float* dwc, int bs, float* keep) {
-  // 4 elements per iteration: the threefry rounds are one serial dependency chain per element, so
-  // independent elements are interleaved for ILP (a single resident warp cannot hide it otherwise)
+                         uint32_t b0, uint32_t b1, int t, int H, int G, int g, Tctx<M>& tc, float (&dw)[M::NX],
+                         float* keep) {
+  constexpr int NX = M::NX, L = M::Ev::L;
+  if constexpr (L == 1) {
+    float* dwc = tc.ev.slot(Scratch::SLOT_X);
+    const int bs = tc.ev.bs;
 #pragma unroll 1
-  for (int i0 = 0; i0 < NX; i0 += 4) {
-    float v[4];
+    for (int i0 = 0; i0 < NX; i0 += 4) {
+      float v[4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int i = i0 + q;
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + q;
+        v[q] = 0.0f;
+        if (i < NX && d.noise_prior[i < NX ? i : 0] != 0.0f) {
+          if (noise_mode == SDE4_NOISE_GIVEN) {
+            v[q] = __ldg(noise + ((size_t)t * NX + i) * G + g);
+          } else {
+            v[q] = bits_to_normal(jax_bits(b0, b1, (uint64_t)t * NX + i, (uint64_t)H * NX, rng_mode));
+            if (keep) keep[(size_t)i * G] = v[q];
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (i0 + q < NX) dwc[(size_t)(i0 + q) * bs] = v[q];
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dw[i] = dwc[(size_t)i * bs];
+  } else {
+    constexpr int PER = (NX + L - 1) / L;
+    float v[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tc.l + q * L;
       v[q] = 0.0f;
       if (i < NX && d.noise_prior[i < NX ? i : 0] != 0.0f) {
         if (noise_mode == SDE4_NOISE_GIVEN) {
@@ -93,29 +167,37 @@ SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode,
         }
       }
     }
+    const int base = (threadIdx.x & 31) & ~(L - 1);
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (i0 + q < NX) dwc[(size_t)(i0 + q) * bs] = v[q];
+    for (int i = 0; i < NX; ++i) dw[i] = __shfl_sync(0xffffffffu, v[i / L], base + (i % L));
   }
 }
 
 // One Euler-Maruyama step in place: x <- proj(x + f dt + sigma dw)   (sde_solver.py:301-304)
 template <class M>
-SDE4_DEV void em_step(const float* W, const Scratch& sc, const sde4_model_desc& d, float (&x)[M::NX],
-                      const float (&u)[M::NU], float dt, bool noisy, float& aux) {
+SDE4_DEV void em_step(const float* W, Tctx<M>& tc, const sde4_model_desc& d, float (&x)[M::NX],
+                      const float (&u)[M::NU], const float (&dw)[M::NX], float dt, bool noisy, float& aux) {
   float f[M::NX];
-  M::drift(W, sc, d, x, u, f);
+  M::drift(W, tc.ev, d, x, u, f);
   if (noisy) {
     float sig[M::NX];
-    Diffusion<M>::fwd(W, sc, d, x, sig);
-    const float* dwc = sc.slot(Scratch::SLOT_X);
+    Diffusion<M>::fwd(W, tc.ev, d, x, sig);
 #pragma unroll
-    for (int i = 0; i < M::NX; ++i) x[i] = fmaf(sig[i], dwc[(size_t)i * sc.bs], fmaf(f[i], dt, x[i]));
+    for (int i = 0; i < M::NX; ++i) x[i] = fmaf(sig[i], dw[i], fmaf(f[i], dt, x[i]));
   } else {
 #pragma unroll
     for (int i = 0; i < M::NX; ++i) x[i] = fmaf(f[i], dt, x[i]);
   }
   M::project(x, aux);
+}
+
+// state rows of one time slice: element i is written by lane (i mod L) of the sample's group
+template <class M>
+SDE4_DEV void store_state(float* out, int G, const float (&x)[M::NX], int l, bool active) {
+  constexpr int L = M::Ev::L;
+#pragma unroll
+  for (int i = 0; i < M::NX; ++i)
+    if (active && (L == 1 || (i % L) == l)) out[(size_t)i * G] = x[i];
 }
 
 // ----------------------------------------------------------------------------
@@ -124,24 +206,18 @@ SDE4_DEV void em_step(const float* W, const Scratch& sc, const sde4_model_desc& 
 template <class M>
 __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_model_desc d,
                                                   const __grid_constant__ RolloutK a) {
-  using A = typename M::A;
   constexpr int NX = M::NX, NU = M::NU;
   extern __shared__ __align__(16) float W[];
   __shared__ __align__(8) uint64_t mbar;
-  stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar);
-  Diffusion<M>::derive(W);
-  __syncthreads();
-  const Scratch sc{W + A::SMEM_FLOATS + threadIdx.x, (int)blockDim.x};
-
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.G) return;
+  Tctx<M> tc;
+  const int g0 = kernel_prologue<M>(W, a.params, &mbar, tc);
+  const bool active = g0 < a.G;
+  const int g = active ? g0 : a.G - 1;  // inactive lanes shadow a valid sample (warp collectives stay uniform)
   const int p = g / a.N, n = g - p * a.N;
   float x[NX];
 #pragma unroll
-  for (int i = 0; i < NX; ++i) {
-    x[i] = __ldg(a.y0 + (size_t)p * NX + i);
-    a.xevol[(size_t)i * a.G + g] = x[i];
-  }
+  for (int i = 0; i < NX; ++i) x[i] = __ldg(a.y0 + (size_t)p * NX + i);
+  store_state<M>(a.xevol + g, a.G, x, tc.l, active);
   const bool noisy = a.noise_mode != SDE4_NOISE_NONE;
   uint32_t b0 = 0, b1 = 0;
   if (a.noise_mode == SDE4_NOISE_THREEFRY) {
@@ -150,17 +226,13 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
   }
   const float* up = a.u + (size_t)p * a.u_sp;
   for (int t = 0; t < a.H; ++t) {
-    float u[NU];
+    float u[NU], dw[NX];
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = __ldg(up + (size_t)t * a.u_st + (size_t)j * a.u_sj);
-    if (noisy)
-      draw_noise<NX>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, a.G, g, sc.slot(Scratch::SLOT_X), sc.bs,
-                     nullptr);
+    if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, a.G, g, tc, dw, nullptr);
     float aux;
-    em_step<M>(W, sc, d, x, u, __ldg(a.dt + t), noisy, aux);
-    float* out = a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g;
-#pragma unroll
-    for (int i = 0; i < NX; ++i) out[(size_t)i * a.G] = x[i];
+    em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
+    store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
   }
 }
 
@@ -178,18 +250,14 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
                                                const __grid_constant__ sde4_cost_desc cd,
                                                const __grid_constant__ sde4_cost_desc td,
                                                const __grid_constant__ CostK a) {
-  using A = typename M::A;
-  constexpr int NX = M::NX, NU = M::NU;
+  constexpr int NX = M::NX, NU = M::NU, L = M::Ev::L, SPW = 32 / L;  // SPW: samples per warp
   extern __shared__ __align__(16) float W[];
   __shared__ __align__(8) uint64_t mbar;
-  stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar);
-  Diffusion<M>::derive(W);
-  __syncthreads();
-  const Scratch sc{W + A::SMEM_FLOATS + threadIdx.x, (int)blockDim.x};
-
-  const int g0 = blockIdx.x * blockDim.x + threadIdx.x;
+  Tctx<M> tc;
+  const int g0 = kernel_prologue<M>(W, a.params, &mbar, tc);
   const bool active = g0 < a.G;
   const int g = active ? g0 : a.G - 1;  // inactive lanes shadow a valid sample, contribute nothing
+  const bool contrib = active && tc.l == 0;  // one lane per sample feeds the particle reductions
   const int p = g / a.N, n = g - p * a.N;
   const int G = a.G, H = a.H;
   const float* op = a.opt + (size_t)p * a.o_sp;
@@ -219,20 +287,20 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   {
     c_prev = stage_cost<NX, NU, false>(cd, x, u, xr, true, 0.0f, dummy_gx, dummy_gu);
     if (CONSTR) c_prev += constr_cost<NX, false>(cd, x, x0s, 0.0f, dummy_gx, dummy_gs);  // slack_0 := x0 (nsde.py:1510)
-    if (keep && active && a.xbuf) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) a.xbuf[(size_t)i * G + g] = x[i];
-      if (a.write_stage_cost) a.xbuf[(size_t)NX * G + g] = c_prev;
+    if (keep && a.xbuf) {
+      store_state<M>(a.xbuf + g, G, x, tc.l, active);
+      if (a.write_stage_cost && contrib) a.xbuf[(size_t)NX * G + g] = c_prev;
     }
   }
   for (int t = 0; t < H; ++t) {
     const float dt = __ldg(a.dt + t);
+    float dw[NX];
     if (noisy)
-      draw_noise<NX>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, sc.slot(Scratch::SLOT_X), sc.bs,
-                     (GRAD && active && a.dwbuf) ? a.dwbuf + (size_t)t * NX * G + g : nullptr);
+      draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, tc, dw,
+                    (GRAD && active && a.dwbuf) ? a.dwbuf + (size_t)t * NX * G + g : nullptr);
     float aux = 0.0f;
-    em_step<M>(W, sc, d, x, u, dt, noisy, aux);
-    if (GRAD && M::NAUX && active) a.auxbuf[(size_t)t * G + g] = aux;
+    em_step<M>(W, tc, d, x, u, dw, dt, noisy, aux);
+    if (GRAD && M::NAUX && contrib) a.auxbuf[(size_t)t * G + g] = aux;
     // control of the next stage: u_{t+1}, the last one repeated (nsde.py:1509)
     const int tn = t + 1 < H ? t + 1 : H - 1;
 #pragma unroll
@@ -249,28 +317,26 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     }
     cost = fmaf(0.5f * dt, c_prev + c_next, cost);  // trapezoid (nsde.py:1515)
     c_prev = c_next;
-    if (keep && active && a.xbuf) {
+    if (keep && a.xbuf) {
       float* out = a.xbuf + (size_t)(t + 1) * a.x_rows * G + g;
-#pragma unroll
-      for (int i = 0; i < NX; ++i) out[(size_t)i * G] = x[i];
-      if (a.write_stage_cost) out[(size_t)NX * G] = c_next;
+      store_state<M>(out, G, x, tc.l, active);
+      if (a.write_stage_cost && contrib) out[(size_t)NX * G] = c_next;
     }
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = unext[j];
   }
   if (a.has_terminal) cost += stage_cost<NX, NU, false>(td, x, u, xr + (size_t)H * NX, false, 0.0f, dummy_gx, dummy_gu);
 
-  // cost partial
+  // partial index of this thread's sample: per warp (all its samples in one problem) or per sample
+  const int pw = a.warp_reduce ? (g / SPW) : g;
+  const bool writer = a.warp_reduce ? (active && (threadIdx.x & 31) == 0) : contrib;
   {
-    float cv = active ? cost : 0.0f;
-    if (a.warp_reduce) {
-      cv = warp_sum(cv);
-      if ((threadIdx.x & 31) == 0 && active) a.cpart[g >> 5] = cv;
-    } else if (active) {
-      a.cpart[g] = cv;
-    }
+    float cv = contrib ? cost : 0.0f;
+    if (a.warp_reduce) cv = warp_sum(cv);
+    if (writer) a.cpart[pw] = cv;
   }
   if (!GRAD) return;
+  if constexpr (L > 1) __syncwarp();  // checkpoints written by sibling lanes are read back below
 
   // ---------------- backward sweep ----------------
   // x holds x_H, u holds u_{H-1}.  Live state is kept small on purpose (x, lam, gx, u, gu): the
@@ -328,11 +394,11 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     for (int i = 0; i < NX; ++i) gx[i] = lam[i];
     {
       const Scaled<NX> vf{lam, dt};
-      M::drift_vjp(W, sc, d, x, u, vf, gx, gu);
+      M::drift_vjp(W, tc.ev, d, x, u, vf, gx, gu);
     }
     if (noisy) {
       const float* nzt = nz + (size_t)t * NX * G + g;
-      Diffusion<M>::vjp(W, sc, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
+      Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
     }
     // stage cost at t: trapezoid weight w_t
     const float wt = t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt;
@@ -350,11 +416,9 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     // emit row t of the per-sample gradient
     {
       float* gp = a.gpart + (size_t)t * (NU + a.n_slack) * a.PW;
-      const int pw = a.warp_reduce ? (g >> 5) : g;
-      const bool writer = active && (!a.warp_reduce || (threadIdx.x & 31) == 0);
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
-        float v = active ? gu[j] : 0.0f;
+        float v = contrib ? gu[j] : 0.0f;
         if (a.warp_reduce) v = warp_sum(v);
         if (writer) gp[(size_t)j * a.PW + pw] = v;
         gu[j] = 0.0f;
@@ -363,7 +427,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
           if (cd.slack_col[i] >= 0 && cd.constr_mode == SDE4_CONSTR_WITHPROX) {
-            float v = active ? gs[i] : 0.0f;
+            float v = contrib ? gs[i] : 0.0f;
             if (a.warp_reduce) v = warp_sum(v);
             if (writer) gp[(size_t)(NU + cd.slack_col[i]) * a.PW + pw] = v;
           }

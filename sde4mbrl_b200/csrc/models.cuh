@@ -42,6 +42,20 @@ struct Arch {
   static constexpr int N_DERIVED = up4(2 * NO);
   static constexpr int SMEM_FLOATS = PARAM_TOTAL + N_DERIVED;
   static constexpr int MACS = DNet::MACS + NetA::MACS + NetB::MACS;
+  // lane-split kernels keep a bank-spread copy of every w1 (see nets.cuh, EvL) after the image
+  template <class N>
+  static constexpr int w1p_floats(int L) {
+    return (L > 1 && N::PRESENT) ? up4(N::H1 * N::H2P + 4 * L) : 0;
+  }
+  static constexpr int off_w1p(int slot, int L) {
+    return SMEM_FLOATS + (slot > 0 ? w1p_floats<DNet>(L) : 0) + (slot > 1 ? w1p_floats<NetA>(L) : 0);
+  }
+  static constexpr int smem_floats(int L) { return off_w1p(2, L) + w1p_floats<NetB>(L); }
+  template <int SLOT, int L>
+  SDE4_DEV static NetRef ref(const float* W) {
+    constexpr int off = SLOT == 0 ? OFF_DENSITY : (SLOT == 1 ? OFF_NET_A : OFF_NET_B);
+    return NetRef{W + off, W + off_w1p(SLOT, L)};
+  }
 
   static bool matches(const sde4_model_desc& d) {
     return d.model_id == MODEL && d.n_x == NX && d.n_u == NU && (uint32_t)d.flags == FLAGS &&
@@ -92,6 +106,8 @@ template <class M>
 struct Diffusion {
   using A = typename M::A;
   using DNet = typename A::DNet;
+  using Ev = typename M::Ev;
+  using Ctx = typename Ev::Ctx;
   static constexpr int NX = A::NX, NO = A::NO;
 
   SDE4_DEV static void gather_in(const float (&x)[NX], const sde4_model_desc& d, float (&z)[DNet::IN > 0 ? DNet::IN : 1]) {
@@ -111,7 +127,7 @@ struct Diffusion {
   }
 
   // sig[i] = eta_full[i] * prior[i]
-  SDE4_DEV static void fwd(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void fwd(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                            float (&sig)[NX]) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) sig[i] = d.noise_prior[i];  // non-noise outputs: eta = 1 (nsde.py:363)
@@ -119,7 +135,7 @@ struct Diffusion {
       float z[DNet::IN > 0 ? DNet::IN : 1];
       gather_in(x, d, z);
       float dens[1];
-      mlp_fwd<DNet, false>(W + A::OFF_DENSITY, sc, z, dens);
+      Ev::template fwd<DNet, false>(A::template ref<0, Ev::L>(W), sc, z, dens);
 #pragma unroll
       for (int k = 0; k < NO; ++k) sig[nth_bit(A::NOUT_MASK, k)] *= eta_of(W, d, dens[0], k);
     }
@@ -129,14 +145,14 @@ struct Diffusion {
   // The density gradient J = d dens / d x does not depend on the cotangent, so it is formed
   // first (fused value+gradient pass) and scaled afterwards.
   template <class NoiseAt>
-  SDE4_DEV static void vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void vjp(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                            const float (&lam)[NX], NoiseAt noise_at, float (&gx)[NX]) {
     if constexpr (!A::HAS_DENSITY) {
       return;
     } else {
       float z[DNet::IN], J[DNet::IN], dens;
       gather_in(x, d, z);
-      mlp_scalar_value_grad<DNet>(W + A::OFF_DENSITY, sc, z, dens, J);
+      Ev::template scalar_value_grad<DNet>(A::template ref<0, Ev::L>(W), sc, z, dens, J);
       float gd = 0.0f;
 #pragma unroll
       for (int k = 0; k < NO; ++k) {
@@ -166,9 +182,11 @@ struct Diffusion {
 // ----------------------------------------------------------------------------
 // Mass-spring-damper  (mass_spring_model.py:36-86)
 // ----------------------------------------------------------------------------
-template <class A_>
+template <class A_, class Ev_ = Ev1>
 struct MsdModel {
   using A = A_;
+  using Ev = Ev_;
+  using Ctx = typename Ev_::Ctx;
   static constexpr int NX = 2, NU = 1, NR = 2, NAUX = 0;
   static constexpr bool GT = (A::FLAGS & SDE4_MSD_GROUND_TRUTH) != 0;
   static constexpr bool SI = (A::FLAGS & SDE4_MSD_SIDE_INFO) != 0;
@@ -185,7 +203,7 @@ struct MsdModel {
     gx[1] += g[1];
   }
 
-  SDE4_DEV static void drift(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                              const float (&u)[NU], float (&f)[NX]) {
     const float m = d.cfloat[0], k = d.cfloat[1], b = d.cfloat[2];
     const float u0 = CTRL ? u[0] : 0.0f;
@@ -194,16 +212,16 @@ struct MsdModel {
       f[1] = (u0 - k * x[0] - b * x[1]) / m;
     } else if constexpr (SI) {
       float in[1] = {x[1]}, out[1];
-      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
+      Ev::template fwd<NetA, false>(A::template ref<1, Ev::L>(W), sc, in, out);
       f[1] = (u0 - k * x[0] + out[0]) / m;
     } else {
       float in[2] = {x[0], x[1]}, out[1];
-      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
+      Ev::template fwd<NetA, false>(A::template ref<1, Ev::L>(W), sc, in, out);
       f[1] = out[0];
     }
   }
 
-  SDE4_DEV static void drift_vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift_vjp(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                                  const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
     const float m = d.cfloat[0], k = d.cfloat[1], b = d.cfloat[2];
     gx[1] += vf[0];
@@ -217,11 +235,11 @@ struct MsdModel {
       gx[0] -= k * s;
       if constexpr (CTRL) gu[0] += s;
       float in[1] = {x[1]}, go[1] = {s}, gi[1];
-      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
+      Ev::template fwd_vjp<NetA>(A::template ref<1, Ev::L>(W), sc, in, go, gi);
       gx[1] += gi[0];
     } else {
       float in[2] = {x[0], x[1]}, go[1] = {vf[1]}, gi[2];
-      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
+      Ev::template fwd_vjp<NetA>(A::template ref<1, Ev::L>(W), sc, in, go, gi);
       gx[0] += gi[0];
       gx[1] += gi[1];
     }
@@ -234,9 +252,11 @@ struct MsdModel {
 // ----------------------------------------------------------------------------
 // Cartpole  (cartpole_sde.py:56-83); state [x, xdot, theta, thetadot]
 // ----------------------------------------------------------------------------
-template <class A_>
+template <class A_, class Ev_ = Ev1>
 struct CartpoleModel {
   using A = A_;
+  using Ev = Ev_;
+  using Ctx = typename Ev_::Ctx;
   static constexpr int NX = 4, NU = 1, NR = 4, NAUX = 0;
   static constexpr bool SI = (A::FLAGS & SDE4_CART_SIDE_INFO) != 0;
   using NetA = typename A::NetA;
@@ -260,7 +280,7 @@ struct CartpoleModel {
     gx[3] += g[3] * d.inv_red_scale;
   }
 
-  SDE4_DEV static void drift(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                              const float (&u)[NU], float (&f)[NX]) {
     float s, c;
     sincosf(x[2], &s, &c);
@@ -270,20 +290,20 @@ struct CartpoleModel {
     f[2] = x[3];
     if constexpr (!SI) {
       float in[4] = {s, c, thd_sc, u[0]}, out[2];
-      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
+      Ev::template fwd<NetA, false>(A::template ref<1, Ev::L>(W), sc, in, out);
       f[1] = sc0 * out[0];
       f[3] = sc1 * out[1];
     } else {
       float in[3] = {s, c, thd_sc}, out[2];
-      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
+      Ev::template fwd<NetA, false>(A::template ref<1, Ev::L>(W), sc, in, out);
       float cin[2] = {c, c * c}, ce[2];
-      mlp_fwd<NetB, false>(W + A::OFF_NET_B, sc, cin, ce);
+      Ev::template fwd<NetB, false>(A::template ref<2, Ev::L>(W), sc, cin, ce);
       f[1] = sc0 * (out[0] + ce[0] * u[0]);
       f[3] = sc1 * (out[1] + ce[1] * u[0]);
     }
   }
 
-  SDE4_DEV static void drift_vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift_vjp(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                                  const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
     float s, c;
     sincosf(x[2], &s, &c);
@@ -294,7 +314,7 @@ struct CartpoleModel {
     float gs = 0.0f, gc = 0.0f;  // cotangents of sin(theta), cos(theta)
     if constexpr (!SI) {
       float in[4] = {s, c, thd_sc, u[0]}, go[2] = {sc0 * vf[1], sc1 * vf[3]}, gi[4];
-      mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
+      Ev::template fwd_vjp<NetA>(A::template ref<1, Ev::L>(W), sc, in, go, gi);
       gs = gi[0];
       gc = gi[1];
       gx[3] += gi[2] * d.inv_state_scaling[3];
@@ -303,17 +323,17 @@ struct CartpoleModel {
       const float go0 = sc0 * vf[1], go1 = sc1 * vf[3];
       {
         float in[3] = {s, c, thd_sc}, go[2] = {go0, go1}, gi[3];
-        mlp_fwd_vjp<NetA>(W + A::OFF_NET_A, sc, in, go, gi);
+        Ev::template fwd_vjp<NetA>(A::template ref<1, Ev::L>(W), sc, in, go, gi);
         gs = gi[0];
         gc = gi[1];
         gx[3] += gi[2] * d.inv_state_scaling[3];
       }
       {
         float cin[2] = {c, c * c}, ce[2];
-        mlp_fwd<NetB, true>(W + A::OFF_NET_B, sc, cin, ce);
+        Ev::template fwd<NetB, true>(A::template ref<2, Ev::L>(W), sc, cin, ce);
         gu[0] += go0 * ce[0] + go1 * ce[1];
         float gce[2] = {go0 * u[0], go1 * u[0]}, gcin[2];
-        mlp_bwd<NetB>(W + A::OFF_NET_B, sc, gce, gcin);
+        Ev::template bwd<NetB>(A::template ref<2, Ev::L>(W), sc, gce, gcin);
         gc += gcin[0] + 2.0f * c * gcin[1];
       }
     }
@@ -353,9 +373,11 @@ struct Mixer<6> {  // motor_models.py:21-28
   }
 };
 
-template <class A_>
+template <class A_, class Ev_ = Ev1>
 struct RotorModel {
   using A = A_;
+  using Ev = Ev_;
+  using Ctx = typename Ev_::Ctx;
   static constexpr int NX = 13, NU = A::NU, NR = 13, NAUX = 1;
   static constexpr bool DRAG = (A::FLAGS & SDE4_ROTOR_AERO_DRAG) != 0;
   using NetA = typename A::NetA;  // res_forces
@@ -390,7 +412,7 @@ struct RotorModel {
     return fmaf(fmaf(3.0f * S[7], u, 2.0f * S[8]), u, S[9]);
   }
 
-  SDE4_DEV static void drift(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                              const float (&u)[NU], float (&f)[NX]) {
     const float* __restrict__ S = W + A::OFF_SCALARS;
     const Quat q{x[6], x[7], x[8], x[9]};
@@ -405,7 +427,7 @@ struct RotorModel {
       float in[NetA::IN > 0 ? NetA::IN : 1], out[3];
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      mlp_fwd<NetA, false>(W + A::OFF_NET_A, sc, in, out);
+      Ev::template fwd<NetA, false>(A::template ref<1, Ev::L>(W), sc, in, out);
       Fb[0] = out[0];
       Fb[1] = out[1];
       Fb[2] = out[2];
@@ -419,7 +441,7 @@ struct RotorModel {
       float in[NetB::IN > 0 ? NetB::IN : 1], out[3];
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      mlp_fwd<NetB, false>(W + A::OFF_NET_B, sc, in, out);
+      Ev::template fwd<NetB, false>(A::template ref<2, Ev::L>(W), sc, in, out);
       Mt[0] = out[0];
       Mt[1] = out[1];
       Mt[2] = out[2];
@@ -459,7 +481,7 @@ struct RotorModel {
     f[9] = 0.5f * qd.z;
   }
 
-  SDE4_DEV static void drift_vjp(const float* W, const Scratch& sc, const sde4_model_desc& d, const float (&x)[NX],
+  SDE4_DEV static void drift_vjp(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                                  const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
     const float* __restrict__ S = W + A::OFF_SCALARS;
     const Quat q{x[6], x[7], x[8], x[9]};
@@ -522,11 +544,11 @@ struct RotorModel {
       float in[NetA::IN > 0 ? NetA::IN : 1], gi[NetA::IN > 0 ? NetA::IN : 1], out[3];
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      mlp_fwd<NetA, true>(W + A::OFF_NET_A, sc, in, out);
+      Ev::template fwd<NetA, true>(A::template ref<1, Ev::L>(W), sc, in, out);
       Fb[0] = out[0];
       Fb[1] = out[1];
       Fb[2] = out[2];
-      mlp_bwd<NetA>(W + A::OFF_NET_A, sc, gFb, gi);
+      Ev::template bwd<NetA>(A::template ref<1, Ev::L>(W), sc, gFb, gi);
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) gin6[nth_bit(A::A_MASK, k)] += gi[k];
     }
@@ -564,7 +586,7 @@ struct RotorModel {
       float in[NetB::IN > 0 ? NetB::IN : 1], gi[NetB::IN > 0 ? NetB::IN : 1];
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      mlp_fwd_vjp<NetB>(W + A::OFF_NET_B, sc, in, gM, gi);
+      Ev::template fwd_vjp<NetB>(A::template ref<2, Ev::L>(W), sc, in, gM, gi);
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) gin6[nth_bit(A::B_MASK, k)] += gi[k];
     }

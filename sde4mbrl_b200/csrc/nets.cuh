@@ -242,4 +242,237 @@ SDE4_DEV void mlp_scalar_value_grad(const float* W, const Scratch& sc, const flo
   mlp_bwd_tail<N>(W, sc, g2, J);
 }
 
+
+// ================================================================================================
+// Evaluator policies.  The model code (models.cuh) is written once against
+//   Ev::fwd<N,KEEP>, Ev::bwd<N>, Ev::fwd_vjp<N>, Ev::scalar_value_grad<N>
+// taking a NetRef (pointers into the shared-memory parameter image) and an evaluator context.
+//   Ev1      one thread per sample  (throughput configurations: many samples)
+//   EvL<L>   L adjacent lanes per sample (latency configurations: few samples, e.g. one MPC
+//            problem with 4096 particles = only 128 warps for 592 warp schedulers)
+// ================================================================================================
+struct NetRef {
+  const float* w;    // packed network image (layout above)
+  const float* w1p;  // EvL only: copy of w1 with a 4-float gap after every H1/L rows (bank spread)
+};
+
+struct Ev1 {
+  static constexpr int L = 1;
+  using Ctx = Scratch;
+  template <class N, bool KEEP>
+  SDE4_DEV static void fwd(const NetRef& r, Ctx& c, const float (&in)[N::IN], float (&out)[N::OUT]) {
+    mlp_fwd<N, KEEP>(r.w, c, in, out);
+  }
+  template <class N>
+  SDE4_DEV static void bwd(const NetRef& r, Ctx& c, const float (&gout)[N::OUT], float (&gin)[N::IN]) {
+    mlp_bwd<N>(r.w, c, gout, gin);
+  }
+  template <class N>
+  SDE4_DEV static void fwd_vjp(const NetRef& r, Ctx& c, const float (&in)[N::IN], const float (&gout)[N::OUT],
+                               float (&gin)[N::IN]) {
+    mlp_fwd_vjp<N>(r.w, c, in, gout, gin);
+  }
+  template <class N>
+  SDE4_DEV static void scalar_value_grad(const NetRef& r, Ctx& c, const float (&in)[N::IN], float& out,
+                                         float (&J)[N::IN]) {
+    mlp_scalar_value_grad<N>(r.w, c, in, out, J);
+  }
+};
+
+// ---- lane-split evaluator ------------------------------------------------------------------------
+// Lane l of a sample owns the hidden units [l*B, (l+1)*B) of each hidden layer (B = H/L).
+//   layer 1: every lane has the (replicated) inputs and computes its own block of outputs;
+//   layer 2: ROW split -- the lane multiplies its own h1 block with the matching rows of w1 and
+//            obtains partial sums of ALL outputs; a recursive-halving reduce-scatter over the L
+//            lanes (SHFL.BFLY) leaves each lane with the finished values of its own output block;
+//   layer 3: partial dot products over the own block + butterfly all-reduce.
+// The backward sweep mirrors this with the transposed products.
+constexpr int MAXB = 8;  // largest per-lane block (MAXW / smallest L >= 4)
+
+template <int L_>
+struct EvL {
+  static constexpr int L = L_;
+  static_assert(L_ == 2 || L_ == 4 || L_ == 8 || L_ == 16, "lanes per sample");
+  struct Ctx {
+    int l;             // lane within the sample's group
+    float d1[32 / L_ > 0 ? 32 / L_ : 1], d2[32 / L_ > 0 ? 32 / L_ : 1];  // act' of the own blocks (KEEP)
+  };
+  template <class N>
+  static constexpr bool ok() {
+    return N::H1 % L == 0 && N::H2 % L == 0;
+  }
+
+  // acc[0..LEN) summed over the L lanes; lane l ends with elements [l*LEN/L, (l+1)*LEN/L) in acc[0..LEN/L)
+  template <int LEN>
+  SDE4_DEV static void reduce_scatter(float (&acc)[LEN], int l) {
+#pragma unroll
+    for (int mask = L / 2, n = LEN; mask >= 1; mask >>= 1, n >>= 1) {
+      const bool up = (l & mask) != 0;
+#pragma unroll
+      for (int q = 0; q < n / 2; ++q) {
+        const float lo = acc[q], hi = acc[q + n / 2];
+        const float send = up ? lo : hi;
+        const float keep = up ? hi : lo;
+        acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    }
+  }
+  SDE4_DEV static float all_reduce(float v) {
+#pragma unroll
+    for (int mask = L / 2; mask >= 1; mask >>= 1) v += __shfl_xor_sync(0xffffffffu, v, mask);
+    return v;
+  }
+
+  // layer 1 own block: a1[m] = b0[l*B1+m] + sum_k in[k]*w0[k][l*B1+m]
+  template <class N>
+  SDE4_DEV static void layer1(const NetRef& r, int l, const float (&in)[N::IN], float (&a1)[N::H1 / L]) {
+    constexpr int B1 = N::H1 / L;
+    const float* w0 = r.w + N::OFF_W0 + l * B1;
+    const float* b0 = r.w + N::OFF_B0 + l * B1;
+#pragma unroll
+    for (int m = 0; m < B1; ++m) a1[m] = b0[m];
+#pragma unroll
+    for (int k = 0; k < N::IN; ++k) {
+#pragma unroll
+      for (int m = 0; m < B1; ++m) a1[m] = fmaf(in[k], w0[k * N::H1P + m], a1[m]);
+    }
+  }
+  // layer 2: own rows -> partial sums of all outputs -> reduce-scatter -> + bias: a2own[B2]
+  template <class N>
+  SDE4_DEV static void layer2(const NetRef& r, int l, const float (&h1)[N::H1 / L], float (&a2)[N::H2 / L]) {
+    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    const float* w1 = r.w1p + l * (B1 * N::H2P + 4);
+    float acc[N::H2];
+#pragma unroll
+    for (int j = 0; j < N::H2; ++j) acc[j] = 0.0f;
+#pragma unroll
+    for (int m = 0; m < B1; ++m) {
+#pragma unroll
+      for (int j = 0; j < N::H2; ++j) acc[j] = fmaf(h1[m], w1[m * N::H2P + j], acc[j]);
+    }
+    reduce_scatter<N::H2>(acc, l);
+    const float* b1 = r.w + N::OFF_B1 + l * B2;
+#pragma unroll
+    for (int m = 0; m < B2; ++m) a2[m] = acc[m] + b1[m];
+  }
+  // layer 3: out[o] = b2[o] + sum_j h2[j]*w2T[o][j]
+  template <class N>
+  SDE4_DEV static void layer3(const NetRef& r, int l, const float (&h2)[N::H2 / L], float (&out)[N::OUT]) {
+    constexpr int B2 = N::H2 / L;
+    const float* w2 = r.w + N::OFF_W2 + l * B2;
+#pragma unroll
+    for (int o = 0; o < N::OUT; ++o) {
+      float a = 0.0f;
+#pragma unroll
+      for (int m = 0; m < B2; ++m) a = fmaf(h2[m], w2[o * N::H2P + m], a);
+      out[o] = all_reduce(a) + r.w[N::OFF_B2 + o];
+    }
+  }
+  // backward tail: g2own (cotangent of own a2 block) -> gin (replicated)
+  template <class N>
+  SDE4_DEV static void bwd_tail(const NetRef& r, int l, const float (&g2)[N::H2 / L], const float (&d1)[N::H1 / L],
+                                float (&gin)[N::IN]) {
+    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    // partial c1[i] over the own column block of w1, for all rows i
+    float c1[N::H1];
+    const float* w1 = r.w + N::OFF_W1 + l * B2;
+#pragma unroll
+    for (int i = 0; i < N::H1; ++i) {
+      float a = 0.0f;
+#pragma unroll
+      for (int m = 0; m < B2; ++m) a = fmaf(w1[i * N::H2P + m], g2[m], a);
+      c1[i] = a;
+    }
+    reduce_scatter<N::H1>(c1, l);
+    const float* w0 = r.w + N::OFF_W0 + l * B1;
+#pragma unroll
+    for (int k = 0; k < N::IN; ++k) {
+      float a = 0.0f;
+#pragma unroll
+      for (int m = 0; m < B1; ++m) a = fmaf(w0[k * N::H1P + m], c1[m] * d1[m], a);
+      gin[k] = all_reduce(a);
+    }
+  }
+
+  template <class N, bool KEEP>
+  SDE4_DEV static void fwd(const NetRef& r, Ctx& c, const float (&in)[N::IN], float (&out)[N::OUT]) {
+    static_assert(ok<N>(), "hidden widths must be multiples of the lane count");
+    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    float a1[B1], a2[B2];
+    layer1<N>(r, c.l, in, a1);
+#pragma unroll
+    for (int m = 0; m < B1; ++m) {
+      if (KEEP) act_fwd_d<N::ACT>(a1[m], a1[m], c.d1[m]);
+      else a1[m] = act_fwd<N::ACT>(a1[m]);
+    }
+    layer2<N>(r, c.l, a1, a2);
+#pragma unroll
+    for (int m = 0; m < B2; ++m) {
+      if (KEEP) act_fwd_d<N::ACT>(a2[m], a2[m], c.d2[m]);
+      else a2[m] = act_fwd<N::ACT>(a2[m]);
+    }
+    layer3<N>(r, c.l, a2, out);
+  }
+  template <class N>
+  SDE4_DEV static void bwd(const NetRef& r, Ctx& c, const float (&gout)[N::OUT], float (&gin)[N::IN]) {
+    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    float g2[B2], d1[B1];
+    const float* w2 = r.w + N::OFF_W2 + c.l * B2;
+#pragma unroll
+    for (int m = 0; m < B2; ++m) {
+      float s = 0.0f;
+#pragma unroll
+      for (int o = 0; o < N::OUT; ++o) s = fmaf(w2[o * N::H2P + m], gout[o], s);
+      g2[m] = s * c.d2[m];
+    }
+#pragma unroll
+    for (int m = 0; m < B1; ++m) d1[m] = c.d1[m];
+    bwd_tail<N>(r, c.l, g2, d1, gin);
+  }
+  template <class N>
+  SDE4_DEV static void fwd_vjp(const NetRef& r, Ctx& c, const float (&in)[N::IN], const float (&gout)[N::OUT],
+                               float (&gin)[N::IN]) {
+    static_assert(ok<N>(), "hidden widths must be multiples of the lane count");
+    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    float a1[B1], d1[B1], a2[B2];
+    layer1<N>(r, c.l, in, a1);
+#pragma unroll
+    for (int m = 0; m < B1; ++m) act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
+    layer2<N>(r, c.l, a1, a2);
+    const float* w2 = r.w + N::OFF_W2 + c.l * B2;
+#pragma unroll
+    for (int m = 0; m < B2; ++m) {
+      float h, dd;
+      act_fwd_d<N::ACT>(a2[m], h, dd);
+      float s = 0.0f;
+#pragma unroll
+      for (int o = 0; o < N::OUT; ++o) s = fmaf(w2[o * N::H2P + m], gout[o], s);
+      a2[m] = s * dd;
+    }
+    bwd_tail<N>(r, c.l, a2, d1, gin);
+  }
+  template <class N>
+  SDE4_DEV static void scalar_value_grad(const NetRef& r, Ctx& c, const float (&in)[N::IN], float& out,
+                                         float (&J)[N::IN]) {
+    static_assert(N::OUT == 1 && ok<N>(), "scalar-output network with lane-divisible widths expected");
+    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    float a1[B1], d1[B1], a2[B2];
+    layer1<N>(r, c.l, in, a1);
+#pragma unroll
+    for (int m = 0; m < B1; ++m) act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
+    layer2<N>(r, c.l, a1, a2);
+    const float* w2 = r.w + N::OFF_W2 + c.l * B2;
+    float o = 0.0f;
+#pragma unroll
+    for (int m = 0; m < B2; ++m) {
+      float h, dd;
+      act_fwd_d<N::ACT>(a2[m], h, dd);
+      o = fmaf(w2[m], h, o);
+      a2[m] = w2[m] * dd;
+    }
+    out = all_reduce(o) + r.w[N::OFF_B2];
+    bwd_tail<N>(r, c.l, a2, d1, J);
+  }
+};
+
 }  // namespace sde4

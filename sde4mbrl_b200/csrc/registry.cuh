@@ -1,6 +1,7 @@
 // registry.cuh -- table of compiled architecture specialisations.  Each inst_*.cu translation
 // unit instantiates the kernels of a few architectures and registers them at load time.
 #pragma once
+#include <type_traits>
 #include <vector>
 #include "kernels.cuh"
 
@@ -14,26 +15,29 @@ struct ArchEntry {
   int offsets[6];
   int smem_bytes;
   int macs;
-  cudaError_t (*launch_rollout)(const sde4_model_desc&, const RolloutK&, int blocks, int threads, cudaStream_t);
-  cudaError_t (*launch_cost)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
-                             bool grad, bool constr, int blocks, int threads, cudaStream_t);
+  // index = log2(lanes per sample): [0] one thread per sample, [2] 4 lanes, [3] 8 lanes; null = not compiled
+  cudaError_t (*launch_rollout[5])(const sde4_model_desc&, const RolloutK&, int blocks, int threads, cudaStream_t);
+  cudaError_t (*launch_cost[5])(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
+                                bool grad, bool constr, int blocks, int threads, cudaStream_t);
 };
 
 std::vector<ArchEntry>& arch_table();
 
 // dynamic shared memory: parameter image + derived constants + per-thread scratch columns
-template <class A>
+template <class M>
 constexpr size_t smem_bytes(int threads) {
-  return sizeof(float) * ((size_t)A::SMEM_FLOATS + (size_t)Scratch::NSLOTS * MAXW * threads);
+  using A = typename M::A;
+  constexpr int L = M::Ev::L;
+  return sizeof(float) * ((size_t)A::smem_floats(L) + (L == 1 ? (size_t)Scratch::NSLOTS * MAXW * threads : 0));
 }
 
 template <class M>
 cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
-  const size_t sm = smem_bytes<A>(threads);
+  const size_t sm = smem_bytes<M>(threads);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<A>(256));
+    cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256));
     attr_set = true;
   }
   k_rollout<M><<<blocks, threads, sm, s>>>(d, a);
@@ -44,10 +48,10 @@ template <class M>
 cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td,
                           const CostK& a, bool grad, bool constr, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
-  const size_t sm = smem_bytes<A>(threads);
+  const size_t sm = smem_bytes<M>(threads);
   static bool attr_set = false;
   if (!attr_set) {
-    const int mx = (int)smem_bytes<A>(256);
+    const int mx = (int)smem_bytes<M>(256);
     cudaFuncSetAttribute(k_cost<M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_cost<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_cost<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
@@ -68,7 +72,19 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
   return cudaGetLastError();
 }
 
-template <class M>
+struct NoLaneSplit {};
+
+constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
+
+template <class MLS>
+void add_lane_variant(ArchEntry& e) {
+  if constexpr (!std::is_same<MLS, NoLaneSplit>::value) {
+    e.launch_rollout[ilog2(MLS::Ev::L)] = &launch_rollout_t<MLS>;
+    e.launch_cost[ilog2(MLS::Ev::L)] = &launch_cost_t<MLS>;
+  }
+}
+
+template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit>
 ArchEntry make_entry(const char* name) {
   using A = typename M::A;
   ArchEntry e;
@@ -84,10 +100,16 @@ ArchEntry make_entry(const char* name) {
   e.offsets[3] = A::OFF_NET_A;
   e.offsets[4] = A::OFF_NET_B;
   e.offsets[5] = A::PARAM_TOTAL;
-  e.smem_bytes = (int)smem_bytes<A>(32);
+  e.smem_bytes = (int)smem_bytes<M>(32);
   e.macs = A::MACS;
-  e.launch_rollout = &launch_rollout_t<M>;
-  e.launch_cost = &launch_cost_t<M>;
+  for (int i = 0; i < 5; ++i) {
+    e.launch_rollout[i] = nullptr;
+    e.launch_cost[i] = nullptr;
+  }
+  e.launch_rollout[0] = &launch_rollout_t<M>;
+  e.launch_cost[0] = &launch_cost_t<M>;
+  add_lane_variant<MLS>(e);
+  add_lane_variant<MLS2>(e);
   return e;
 }
 
@@ -96,6 +118,12 @@ struct ArchRegistrar {
 };
 
 #define SDE4_REGISTER(NAME, MODEL) static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL>(#NAME));
+// also instantiate the lane-split kernels (LANES adjacent lanes per sample) for latency-bound launches
+#define SDE4_REGISTER_LS(NAME, MODEL_T, ARCH, LANES) \
+  static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>>(#NAME));
+#define SDE4_REGISTER_LS2(NAME, MODEL_T, ARCH, LANES_A, LANES_B)                                          \
+  static ::sde4::ArchRegistrar reg_##NAME(                                                                \
+      ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES_A>>, MODEL_T<ARCH, ::sde4::EvL<LANES_B>>>(#NAME));
 
 // shorthand for the architecture zoo
 constexpr int TANH = SDE4_ACT_TANH, SWISH = SDE4_ACT_SWISH;

@@ -37,12 +37,32 @@ static std::string describe(const sde4_model_desc& d) {
   return buf;
 }
 
-static int pick_threads(int requested, long long G) {
+static int pick_threads(int requested, long long threads_total) {
   if (requested > 0) return requested;
-  // few samples: one warp per CTA so the warps spread over all 148 SMs; many samples: fatter CTAs
-  if (G <= 148LL * 32 * 4) return 32;
-  if (G <= 148LL * 64 * 8) return 64;
+  // few threads: one warp per CTA so the warps spread over all 148 SMs; many: fatter CTAs
+  if (threads_total <= 148LL * 32 * 8) return 32;
+  if (threads_total <= 148LL * 64 * 8) return 64;
   return 128;
+}
+
+// lanes per sample: with few samples one thread per sample leaves most of the 592 warp schedulers
+// idle and each resident warp latency-bound, so the lane-split kernel is used when it exists
+static int pick_lanes(const ArchEntry& e, int requested, long long G) {
+  if (requested == 1) return 1;
+  if (requested > 1) {
+    const int i = ilog2(requested);
+    return (i < 5 && (1 << i) == requested && e.launch_cost[i]) ? requested : -1;
+  }
+  // widest compiled variant that still leaves <= ~16 warps per SM
+  for (int i = 4; i >= 1; --i)
+    if (e.launch_cost[i] && G * (1LL << i) <= 148LL * 32 * 16) return 1 << i;
+  return 1;
+}
+
+static int max_lanes(const ArchEntry& e) {
+  for (int i = 4; i >= 1; --i)
+    if (e.launch_cost[i]) return 1 << i;
+  return 1;
 }
 
 static sde4_cost_desc empty_cost() {
@@ -58,11 +78,12 @@ struct CostLayout {
 };
 
 static CostLayout cost_layout(const ArchEntry& e, int P, int N, int H, int n_slack, bool grad, bool have_xtraj,
-                              int noise_mode) {
+                              int noise_mode, int lanes) {
   CostLayout L;
   const size_t G = (size_t)P * N;
-  L.warp_reduce = (N % 32 == 0) ? 1 : 0;
-  L.NP = L.warp_reduce ? N / 32 : N;
+  const int spw = 32 / lanes;  // samples per warp
+  L.warp_reduce = (N % spw == 0) ? 1 : 0;
+  L.NP = L.warp_reduce ? N / spw : N;
   L.PW = P * L.NP;
   auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
   size_t off = 0;
@@ -151,9 +172,12 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void*
   k.n_off = a->particle_total > 0 ? a->particle_offset : 0;
   k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
-  const int threads = pick_threads(a->block_threads, G);
-  const int blocks = (int)((G + threads - 1) / threads);
-  cudaError_t err = e->launch_rollout(*model, k, blocks, threads, (cudaStream_t)stream);
+  const int lanes = pick_lanes(*e, a->lanes, G);
+  if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
+  const long long nthr = G * lanes;
+  const int threads = pick_threads(a->block_threads, nthr);
+  const int blocks = (int)((nthr + threads - 1) / threads);
+  cudaError_t err = e->launch_rollout[ilog2(lanes)](*model, k, blocks, threads, (cudaStream_t)stream);
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rollout launch (%s): %s", e->name, cudaGetErrorString(err));
   return SDE4_OK;
 }
@@ -164,7 +188,12 @@ size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_
   const ArchEntry* e = find_arch(*model);
   if (!e) return 0;
   // worst case over noise modes (threefry keeps a dw buffer)
-  return cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY).total;
+  size_t a = cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY, 1).total;
+  for (int l = 2; l <= max_lanes(*e); l *= 2) {
+    size_t b = cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY, l).total;
+    if (b > a) a = b;
+  }
+  return a;
 }
 
 int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* stream) {
@@ -187,7 +216,9 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   if (G > 0x7fffffffLL) return fail(SDE4_ERR_INVALID, "P*N exceeds 2^31-1");
   const bool grad = a->grad != nullptr;
   const bool constr = cd.constr_mode != SDE4_CONSTR_NONE;
-  const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode);
+  const int lanes = pick_lanes(*e, a->lanes, G);
+  if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
+  const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
   if (a->workspace_bytes < L.total) return fail(SDE4_ERR_WORKSPACE, "workspace too small");
   if (((uintptr_t)a->workspace & 255) != 0) return fail(SDE4_ERR_INVALID, "workspace must be 256-byte aligned");
   char* ws = (char*)a->workspace;
@@ -235,10 +266,11 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   k.has_terminal = (a->terminal && a->terminal->kind != SDE4_COST_NONE) ? 1 : 0;
   const sde4_cost_desc td = k.has_terminal ? *a->terminal : empty_cost();
-  int threads = pick_threads(a->block_threads, G);
-  const int blocks = (int)((G + threads - 1) / threads);
+  const long long nthr = G * lanes;
+  int threads = pick_threads(a->block_threads, nthr);
+  const int blocks = (int)((nthr + threads - 1) / threads);
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t err = e->launch_cost(*model, cd, td, k, grad, constr, blocks, threads, s);
+  cudaError_t err = e->launch_cost[ilog2(lanes)](*model, cd, td, k, grad, constr, blocks, threads, s);
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "cost launch (%s): %s", e->name, cudaGetErrorString(err));
   ReduceK r;
   r.gpart = k.gpart;

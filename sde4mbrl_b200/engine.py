@@ -98,7 +98,7 @@ class Engine:
 
     # ---- K1 --------------------------------------------------------------
     def rollout(self, nn_params, y0, u, dt, key=None, N=1, noise=None, noise_mode=None, x_rows=None,
-                block_threads=0, out=None, particle_offset=0, particle_total=0):
+                block_threads=0, out=None, particle_offset=0, particle_total=0, lanes=0):
         """y0[P,n_x], u[P,H,n_u] (or [H,n_u], shared), key [2] or [P,2].  Returns the native
         buffer ``xevol[H+1, x_rows, P*N]`` (sample-minor)."""
         pk = self.packed(nn_params)
@@ -143,14 +143,14 @@ class Engine:
             a.noise = _ptr(noise)
         a.rng_mode, a.noise_mode = self.rng_mode, noise_mode
         a.xevol, a.x_rows, a.block_threads = _ptr(out), x_rows, block_threads
-        a.particle_offset, a.particle_total = particle_offset, particle_total
+        a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
         L.check(L.load().sde4_rollout(C.byref(self.desc), C.byref(a), _stream()))
         return out
 
     # ---- K2 + K3 ----------------------------------------------------------
     def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,
                   noise_mode=None, want_grad=True, want_xtraj=False, block_threads=0, grad_out=None,
-                  particle_offset=0, particle_total=0):
+                  particle_offset=0, particle_total=0, lanes=0):
         """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
         Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
         pk = self.packed(nn_params)
@@ -211,7 +211,7 @@ class Engine:
         a.cost, a.grad, a.xtraj = _ptr(cost), _ptr(grad), _ptr(xtraj)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
         a.block_threads = block_threads
-        a.particle_offset, a.particle_total = particle_offset, particle_total
+        a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
         L.check(lib.sde4_cost_grad(C.byref(self.desc), C.byref(a), _stream()))
         if squeeze and grad is not None:
             grad = grad.squeeze(0)
