@@ -416,12 +416,31 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     // emit row t of the per-sample gradient
     {
       float* gp = a.gpart + (size_t)t * (NU + a.n_slack) * a.PW;
+      if constexpr (L > 1 && NU <= L) {
+        // gu is replicated over the sample's lanes: lane j of every group carries gu[j], the
+        // groups of the warp are summed with log2(32/L) butterflies, lanes 0..NU-1 store
+        float v = 0.0f;
 #pragma unroll
-      for (int j = 0; j < NU; ++j) {
-        float v = contrib ? gu[j] : 0.0f;
-        if (a.warp_reduce) v = warp_sum(v);
-        if (writer) gp[(size_t)j * a.PW + pw] = v;
-        gu[j] = 0.0f;
+        for (int j = 0; j < NU; ++j) {
+          if (tc.l == j) v = gu[j];
+          gu[j] = 0.0f;
+        }
+        if (!active) v = 0.0f;
+        if (a.warp_reduce) {
+#pragma unroll
+          for (int o = 16; o >= L; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (active && (int)(threadIdx.x & 31) < NU) gp[(size_t)tc.l * a.PW + pw] = v;
+        } else if (active && tc.l < NU) {
+          gp[(size_t)tc.l * a.PW + pw] = v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          float v = contrib ? gu[j] : 0.0f;
+          if (a.warp_reduce) v = warp_sum(v);
+          if (writer) gp[(size_t)j * a.PW + pw] = v;
+          gu[j] = 0.0f;
+        }
       }
       if (CONSTR) {
 #pragma unroll

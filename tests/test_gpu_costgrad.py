@@ -145,3 +145,25 @@ def test_state_constraints_withprox_and_noprox(cuda):
         cost, grad, _ = eng.cost_grad(nn, y0[None], o, ts, xref, st.desc, N=N, noise=hp.to_native_noise(dw))
         assert abs(float(cost[0]) - float(c)) <= 3e-5 * abs(float(c))
         assert hp.rel_err(grad.cpu().numpy(), g64.numpy()) < 1e-3
+
+
+@pytest.mark.parametrize("lanes", [1, 8])
+def test_particle_sharding(cuda, lanes):
+    """One problem's particles split over two 'ranks' (particle_offset / particle_total): the SUM of
+    the shard results equals the unsharded mean, with in-kernel threefry keys split(rng, N_total)."""
+    from sde4mbrl_b200.engine import Engine
+    from oracle import threefry as tf
+    N, H = 64, 20
+    pm, model, nn, y0, opt, dw, cp, stage, xref = _setup("hexa", H, N, seed=21)
+    eng = Engine(model)
+    ts = orc.compute_timesteps(pm)
+    key = tf.PRNGKey(6)
+    c, g, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, key=key, N=N, lanes=lanes)
+    c, g = c.clone(), g.clone()
+    ca, ga, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, key=key, N=40, particle_offset=0,
+                              particle_total=N, lanes=lanes)
+    ca, ga = ca.clone(), ga.clone()
+    cb, gb, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, key=key, N=24, particle_offset=40,
+                              particle_total=N, lanes=lanes)
+    assert abs(float(ca[0] + cb[0]) - float(c[0])) <= 1e-6 * abs(float(c[0]))  # reduction order only
+    assert hp.rel_err((ga + gb).cpu().numpy(), g.cpu().numpy()) < 1e-5
