@@ -33,15 +33,26 @@ SDE4_HD constexpr int up4(int n) { return (n + 3) & ~3; }
 // ----------------------------------------------------------------------------
 // activations.  value h = act(a), derivative d = act'(a)
 // ----------------------------------------------------------------------------
-SDE4_DEV float fast_rcp(float x) { return __fdividef(1.0f, x); }
+// MUFU-based primitives (2 ulp): ex2.approx / rcp.approx without the denormal / range fix-up code
+// that exp2f() and 1.0f/x expand to.
+SDE4_DEV float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+SDE4_DEV float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
-SDE4_DEV float sigmoidf_(float a) { return fast_rcp(1.0f + __expf(-a)); }
+SDE4_DEV float sigmoidf_(float a) { return fast_rcp(1.0f + fast_ex2(a * -1.44269504088896341f)); }
 
 // tanh(a) = 1 - 2/(exp(2a) + 1): 2 MUFU + 3 FP32 ops, absolute error ~1.5e-7 (saturates correctly
 // to +-1; for |a| << 1 the error is absolute, not relative -- fine for float32 parity).
 SDE4_DEV float tanhf_(float a) {
-  const float t = exp2f(a * 2.88539008177792681f);  // exp(2a); MUFU.EX2
-  return 1.0f - __fdividef(2.0f, t + 1.0f);
+  const float t = fast_ex2(a * 2.88539008177792681f);  // exp(2a)
+  return fmaf(-2.0f, fast_rcp(t + 1.0f), 1.0f);
 }
 
 template <int ACT>

@@ -12,7 +12,7 @@ namespace sde4 {
 // value of the shaping  e -> sig ? sigmoid(e*w - 7)*wsig : e*w   and d/d(e)
 SDE4_DEV float shaped(float e, float w, float wsig, bool sig, float& dde) {
   const float v = e * w;
-  if (sig) {
+  if (__builtin_expect(sig, 0)) {  // warp-uniform (descriptor flag): a real branch, not a select
     const float s = sigmoidf_(v - 7.0f);
     dde = s * (1.0f - s) * wsig * w;
     return s * wsig;

@@ -97,6 +97,24 @@ SDE4_DEV void qacc(Quat& a, const Quat& b) {
   a.z += b.z;
 }
 // For r = a (x) b (bilinear):  abar = rbar (x) conj(b),  bbar = conj(a) (x) rbar.
+// Products with a pure-vector operand [0, v] (no multiplications by the literal zero, which the
+// compiler may not fold under IEEE semantics).
+SDE4_DEV Quat qmul_vq(float vx, float vy, float vz, const Quat& b) {  // [0,v] (x) b
+  Quat r;
+  r.w = -vx * b.x - vy * b.y - vz * b.z;
+  r.x = vx * b.w + vy * b.z - vz * b.y;
+  r.y = -vx * b.z + vy * b.w + vz * b.x;
+  r.z = vx * b.y - vy * b.x + vz * b.w;
+  return r;
+}
+SDE4_DEV Quat qmul_qv(const Quat& a, float vx, float vy, float vz) {  // a (x) [0,v]
+  Quat r;
+  r.w = -a.x * vx - a.y * vy - a.z * vz;
+  r.x = a.w * vx + a.y * vz - a.z * vy;
+  r.y = a.w * vy - a.x * vz + a.z * vx;
+  r.z = a.w * vz + a.x * vy - a.y * vx;
+  return r;
+}
 
 // ----------------------------------------------------------------------------
 // Diffusion (nsde.py:298-449), shared by all models through Model::reduced_state.
@@ -417,7 +435,7 @@ struct RotorModel {
     const float* __restrict__ S = W + A::OFF_SCALARS;
     const Quat q{x[6], x[7], x[8], x[9]};
     // v_b = q^-1 (x) (v (x) q)   (rotor_uav/utils.py:53-63, :439)
-    const Quat t1 = qmul(qvec(x[3], x[4], x[5]), q);
+    const Quat t1 = qmul_vq(x[3], x[4], x[5], q);
     const Quat r1 = qmul(qconj(q), t1);
     const float vb[3] = {r1.x, r1.y, r1.z};
     float in6[6];
@@ -458,23 +476,23 @@ struct RotorModel {
     }
     // translational dynamics (:173-210): a = rot(q, [0,0,T] + Fres)/m + [0,0,-g]
     Fb[2] += T;
-    const Quat t2 = qmul(q, qvec(Fb[0], Fb[1], Fb[2]));
+    const Quat t2 = qmul_qv(q, Fb[0], Fb[1], Fb[2]);
     const Quat r2 = qmul(t2, qconj(q));
-    const float m = S[0], g = d.cfloat[0];
+    const float inv_m = fast_rcp(S[0]), g = d.cfloat[0];  // F/m as F*(1/m): <= 2 ulp from the division
     f[0] = x[3];
     f[1] = x[4];
     f[2] = x[5];
-    f[3] = r2.x / m;
-    f[4] = r2.y / m;
-    f[5] = r2.z / m - g;
+    f[3] = r2.x * inv_m;
+    f[4] = r2.y * inv_m;
+    f[5] = fmaf(r2.z, inv_m, -g);
     // rotational dynamics (:212-250)
     const float I0 = S[1], I1 = S[2], I2 = S[3];
     const float w0 = x[10], w1 = x[11], w2 = x[12];
     const float Iw0 = I0 * w0, Iw1 = I1 * w1, Iw2 = I2 * w2;
-    f[10] = (Mm[0] + Mt[0] - (w1 * Iw2 - w2 * Iw1)) / I0;
-    f[11] = (Mm[1] + Mt[1] - (w2 * Iw0 - w0 * Iw2)) / I1;
-    f[12] = (Mm[2] + Mt[2] - (w0 * Iw1 - w1 * Iw0)) / I2;
-    const Quat qd = qmul(q, qvec(w0, w1, w2));
+    f[10] = (Mm[0] + Mt[0] - (w1 * Iw2 - w2 * Iw1)) * fast_rcp(I0);
+    f[11] = (Mm[1] + Mt[1] - (w2 * Iw0 - w0 * Iw2)) * fast_rcp(I1);
+    f[12] = (Mm[2] + Mt[2] - (w0 * Iw1 - w1 * Iw0)) * fast_rcp(I2);
+    const Quat qd = qmul_qv(q, w0, w1, w2);
     f[6] = 0.5f * qd.w;
     f[7] = 0.5f * qd.x;
     f[8] = 0.5f * qd.y;
@@ -487,7 +505,7 @@ struct RotorModel {
     const Quat q{x[6], x[7], x[8], x[9]};
     const Quat qc = qconj(q);
     const Quat V = qvec(x[3], x[4], x[5]);
-    const Quat t1 = qmul(V, q);
+    const Quat t1 = qmul_vq(x[3], x[4], x[5], q);
     const Quat r1 = qmul(qc, t1);
     const float vb[3] = {r1.x, r1.y, r1.z};
     float in6[6];
@@ -502,7 +520,7 @@ struct RotorModel {
     gx[4] += vf[1];
     gx[5] += vf[2];
     // ---- rotational part: alpha = (Mm + Mres - w x (I w)) / I
-    const float gM[3] = {vf[10] / I0, vf[11] / I1, vf[12] / I2};
+    const float gM[3] = {vf[10] * fast_rcp(I0), vf[11] * fast_rcp(I1), vf[12] * fast_rcp(I2)};
     {
       // c = w x b, b = I*w ; Mtot -= c  => cbar = -gM ; wbar += b x cbar ; bbar = cbar x w ; wbar += I*bbar
       const float b0 = I0 * w0, b1 = I1 * w1, b2 = I2 * w2;
@@ -518,8 +536,7 @@ struct RotorModel {
     // ---- qdot = 0.5 q (x) [0,w]
     {
       const Quat gqd{0.5f * vf[6], 0.5f * vf[7], 0.5f * vf[8], 0.5f * vf[9]};
-      const Quat Om = qvec(w0, w1, w2);
-      qacc(gq, qmul(gqd, qconj(Om)));
+      qacc(gq, qmul_qv(gqd, -w0, -w1, -w2));
       const Quat gOm = qmul(qc, gqd);
       gw[0] += gOm.x;
       gw[1] += gOm.y;
@@ -528,8 +545,9 @@ struct RotorModel {
     // ---- translational part: a = vec(q (x) Fq (x) conj(q))/m + [0,0,-g], Fq = [0, Fb].
     // The cotangent of Fb does not depend on Fb itself, so it is formed first and the
     // residual-force net is evaluated once (forward keeping act', then backward).
-    const Quat R2 = qvec(vf[3] / m, vf[4] / m, vf[5] / m);
-    const Quat t2bar = qmul(R2, q);  // r2 = t2 (x) qc  =>  t2bar = R2 (x) conj(qc)
+    const float inv_m = fast_rcp(m);
+    const Quat R2 = qvec(vf[3] * inv_m, vf[4] * inv_m, vf[5] * inv_m);
+    const Quat t2bar = qmul_vq(R2.x, R2.y, R2.z, q);  // r2 = t2 (x) qc  =>  t2bar = R2 (x) conj(qc)
     float gFb[3];
     {
       const Quat gFq = qmul(qc, t2bar);  // t2 = q (x) Fq  =>  Fqbar = conj(q) (x) t2bar
@@ -566,9 +584,9 @@ struct RotorModel {
       for (int i = 0; i < NU; ++i) T = fmaf(Mixer<NU>::m(3, i), motor_thrust(S, u[i]), T);
       Fb[2] += T;
       const Quat Fq = qvec(Fb[0], Fb[1], Fb[2]);
-      const Quat t2 = qmul(q, Fq);
-      qacc(gq, qconj(qmul(qconj(t2), R2)));  // qcbar = conj(t2) (x) R2
-      qacc(gq, qmul(t2bar, qconj(Fq)));      // qbar += t2bar (x) conj(Fq)
+      const Quat t2 = qmul_qv(q, Fb[0], Fb[1], Fb[2]);
+      qacc(gq, qconj(qmul_qv(qconj(t2), R2.x, R2.y, R2.z)));  // qcbar = conj(t2) (x) R2
+      qacc(gq, qmul_qv(t2bar, -Fb[0], -Fb[1], -Fb[2]));        // qbar += t2bar (x) conj(Fq)
     }
     // ---- motors
     {
@@ -600,14 +618,14 @@ struct RotorModel {
     {
       const Quat R1 = qvec(gvb[0], gvb[1], gvb[2]);
       // r1 = qc (x) t1 : qcbar = R1 (x) conj(t1) ; t1bar = conj(qc) (x) R1 = q (x) R1
-      qacc(gq, qconj(qmul(R1, qconj(t1))));
-      const Quat t1bar = qmul(q, R1);
+      qacc(gq, qconj(qmul_vq(gvb[0], gvb[1], gvb[2], qconj(t1))));
+      const Quat t1bar = qmul_qv(q, gvb[0], gvb[1], gvb[2]);
       // t1 = V (x) q : Vbar = t1bar (x) conj(q) ; qbar += conj(V) (x) t1bar
       const Quat gV = qmul(t1bar, qc);
       gx[3] += gV.x;
       gx[4] += gV.y;
       gx[5] += gV.z;
-      qacc(gq, qmul(qconj(V), t1bar));
+      qacc(gq, qmul_vq(-x[3], -x[4], -x[5], t1bar));
     }
     gx[6] += gq.w;
     gx[7] += gq.x;
