@@ -199,6 +199,9 @@ typedef struct sde4_cost_args {
    * the shard with particle_offset == 0 only. */
   int32_t particle_offset, particle_total;
   int32_t lanes;                /* see sde4_rollout_args */
+  /* stacked evaluations: problem p reads y0 / xref / key of problem (p mod data_mod) when data_mod > 0
+   * (several candidate control sequences of the same problem, e.g. the APG line search) */
+  int32_t data_mod;
 } sde4_cost_args;
 
 /* Upper bound over the lane / noise modes the launcher may pick. */
@@ -216,6 +219,52 @@ int sde4_rng_normal(const uint32_t* key_host, uint64_t total, uint64_t offset, u
                     int32_t rng_mode, float* out, void* stream);
 /* out[num][2] = jax.random.split(key, num); key_dev is a DEVICE uint32[2] */
 int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint32_t* out, void* stream);
+
+/* ---- batched APG-MPC: sde4mbrl/apg.py (init_apg :53-113, one_step_apg :164-274,
+ *      armijo_line_search :332-379, _while_loop :451-464) for P independent problems at once.
+ *      The control flow of the reference (lax.cond / bounded scans) becomes per-problem masks:
+ *      a problem whose `not_done` flag is 0 keeps its state, exactly like the no-op iterations
+ *      of the reference's scan.  All [H][n_opt][*] arrays are PROBLEM-MINOR (problem index fastest).
+ *      One iteration = sde4_apg_candidates -> sde4_cost_grad on (maxls+1)*P problems (value only)
+ *      -> sde4_apg_select -> sde4_cost_grad on 2P problems (value only) -> sde4_apg_pick ->
+ *      sde4_cost_grad on P problems (value + gradient) -> sde4_apg_update. */
+typedef struct sde4_apg_params {
+  int32_t P, H, n_opt;
+  int32_t maxls;               /* linesearch.maxls                                            */
+  int32_t reset_increase;      /* linesearch.reset_option == 'increase'                       */
+  int32_t has_prox;            /* box projection on [lb, ub] (nsde.py:1435-1460)              */
+  int32_t use_moment_scale;    /* optimizer_params['moment_scale'] is not None                */
+  int32_t max_no_improvement_iter;
+  float coef, decrease_factor, increase_factor, max_stepsize;
+  float moment_scale, atol, rtol;
+  float lb[SDE4_MAX_NOPT], ub[SDE4_MAX_NOPT];
+} sde4_apg_params;
+
+/* device pointers; scalars are [P]; vectors are [H][n_opt][P] */
+typedef struct sde4_apg_state {
+  int32_t *num_steps, *num_iter_no_improv, *not_done;
+  float *momentum, *avg_momentum, *avg_linesearch, *avg_stepsize, *stepsize;
+  float *opt_cost, *curr_cost, *init_cost, *grad_sqr;
+  float *x_opt, *xk, *yk, *grad_yk;
+} sde4_apg_state;
+
+/* init_apg after the value+gradient evaluation at x0: cost0[P], grad0 -> state (apg.py:82-112). */
+int sde4_apg_init(const sde4_apg_params* prm, const sde4_apg_state* st, const float* x0, const float* cost0,
+                  const float* grad0, const float* momentum_or_null, const float* stepsize_or_null,
+                  float init_stepsize, float beta_init, void* stream);
+/* candidates cand[H][n_opt][(maxls+1)*P] = yk - s_k*grad_yk, svals[(maxls+1)][P] (apg.py:179-184,312-321,358). */
+int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals, void* stream);
+/* Armijo selection (apg.py:324-329,362-379), prox, momentum point: xv[H][n_opt][2P] = [xcurr | vcurr];
+ * sel_step[P], sel_ls[P] (stepsize, number of line-search steps). */
+int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, const float* svals,
+                    const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, void* stream);
+/* ynext = where(cost_x <= cost_v, xcurr, vcurr) (apg.py:219-221): y[H][n_opt][P], pick[P] */
+int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
+                  int32_t* pick, void* stream);
+/* state update with grad(ynext) (apg.py:224-273); problems with not_done == 0 are left untouched */
+int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
+                    const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,
+                    const int32_t* sel_ls, void* stream);
 
 /* ---- layout of the packed parameter block -------------------------------------
  * Returns the number of floats of the block for `model` (<0 on error).  The
@@ -239,6 +288,7 @@ int sde4_version(void);
 /* sizeof() of the four POD structs, in the order model_desc, cost_desc, rollout_args, cost_args
  * (lets a foreign-language binding verify its struct layout at load time). */
 void sde4_struct_sizes(int32_t out[4]);
+void sde4_apg_struct_sizes(int32_t out[2]); /* sizeof sde4_apg_params, sde4_apg_state */
 
 /* ---- FP32 FMA micro-benchmark (roofline denominator) ---------------
  * Runs `iters` dependent-chain-free FFMA (variant 0) / packed fma.rn.f32x2

@@ -76,13 +76,34 @@ class CostArgs(C.Structure):
                 ("stage", C.POINTER(CostDesc)), ("terminal", C.POINTER(CostDesc)),
                 ("cost", C.c_void_p), ("grad", C.c_void_p), ("xtraj", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("block_threads", C.c_int32),
-                ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32)]
+                ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32),
+                ("data_mod", C.c_int32)]
+
+
+class ApgParams(C.Structure):
+    _fields_ = [("P", C.c_int32), ("H", C.c_int32), ("n_opt", C.c_int32), ("maxls", C.c_int32),
+                ("reset_increase", C.c_int32), ("has_prox", C.c_int32), ("use_moment_scale", C.c_int32),
+                ("max_no_improvement_iter", C.c_int32),
+                ("coef", C.c_float), ("decrease_factor", C.c_float), ("increase_factor", C.c_float),
+                ("max_stepsize", C.c_float), ("moment_scale", C.c_float), ("atol", C.c_float), ("rtol", C.c_float),
+                ("lb", C.c_float * MAX_NOPT), ("ub", C.c_float * MAX_NOPT)]
+
+
+APG_STATE_INT = ("num_steps", "num_iter_no_improv", "not_done")
+APG_STATE_F32 = ("momentum", "avg_momentum", "avg_linesearch", "avg_stepsize", "stepsize", "opt_cost", "curr_cost",
+                 "init_cost", "grad_sqr")
+APG_STATE_VEC = ("x_opt", "xk", "yk", "grad_yk")
+
+
+class ApgState(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in APG_STATE_INT + APG_STATE_F32 + APG_STATE_VEC]
 
 
 EXPORTED_SYMBOLS = (
     "sde4_rollout", "sde4_cost_workspace_bytes", "sde4_cost_grad", "sde4_rng_bits", "sde4_rng_normal",
     "sde4_rng_split", "sde4_param_layout", "sde4_model_supported", "sde4_supported_archs",
-    "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_fma_peak",
+    "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
+    "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
 )
 
 _lib = None
@@ -125,6 +146,18 @@ def load():
     lib.sde4_fma_peak.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_double),
                                   C.c_void_p]
     lib.sde4_fma_peak.restype = C.c_int
+    for name in ("sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update"):
+        getattr(lib, name).restype = C.c_int
+    lib.sde4_apg_init.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState), C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+    lib.sde4_apg_candidates.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState), C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.sde4_apg_select.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 7
+    lib.sde4_apg_pick.argtypes = [C.POINTER(ApgParams)] + [C.c_void_p] * 6
+    lib.sde4_apg_update.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 8
+    asz = (C.c_int32 * 2)()
+    lib.sde4_apg_struct_sizes(asz)
+    if list(asz) != [C.sizeof(ApgParams), C.sizeof(ApgState)]:
+        raise Sde4Error("ABI mismatch (apg structs): %s" % (list(asz),))
     sizes = (C.c_int32 * 4)()
     lib.sde4_struct_sizes(sizes)
     mine = [C.sizeof(ModelDesc), C.sizeof(CostDesc), C.sizeof(RolloutArgs), C.sizeof(CostArgs)]

@@ -1,0 +1,151 @@
+"""Batched APG-MPC: P independent ``sde4mbrl/apg.py`` solves advanced in lock step on the device.
+
+This is BASELINE config 4 (4096 independent hexacopter MPC solves) and SURVEY 8(f) rank 1.  The
+reference vmaps ``apg_mpc`` over problems, which turns every ``lax.cond`` into a select and
+evaluates all branches; here the same semantics are obtained with per-problem masks:
+
+    candidates (maxls+1 step sizes per problem)  -> ONE value-only launch over (maxls+1)*P problems
+    Armijo selection + box prox + momentum point -> ONE value-only launch over 2P problems (x and v)
+    ynext = where(cost_x <= cost_v, x, v)        -> ONE value+gradient launch over P problems
+    state update (masked by not_done)
+
+All arithmetic (cost evaluations and the APG bookkeeping) runs in ``libsde4b200.so``; torch only
+owns the buffers.  Arrays are problem-minor: ``[H, n_opt, P]``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .apg import APGState
+from .engine import as_f32, as_key, _ptr, _stream
+
+
+class BatchedAPG:
+    def __init__(self, engine, nn_params, stage, optimizer_params, time_steps, num_particles, lb=None, ub=None,
+                 terminal=None, lanes=0):
+        self.eng = engine
+        self.pk = engine.packed(nn_params)
+        self.stage = stage
+        self.terminal = terminal
+        self.op = optimizer_params
+        assert "linesearch" in optimizer_params, "the batched solver implements the line-search variant (apg.py:174-187)"
+        self.ts = np.asarray(time_steps, np.float32)
+        self.H = int(self.ts.shape[0])
+        self.N = int(num_particles)
+        self.n_opt = engine.n_u + stage.desc.n_slack
+        self.lanes = lanes
+        self.lb, self.ub = lb, ub
+        self.P = None
+
+    # ------------------------------------------------------------------
+    def _alloc(self, P, dev):
+        H, n, K = self.H, self.n_opt, self.op["linesearch"]["maxls"] + 1
+        self.P, self.K = P, K
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        i = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
+        self.t = {n_: i(P) for n_ in L.APG_STATE_INT}
+        self.t.update({n_: f(P) for n_ in L.APG_STATE_F32})
+        self.t.update({n_: f(H, n, P) for n_ in L.APG_STATE_VEC})
+        self.cand, self.svals, self.cand_cost = f(H, n, K * P), f(K, P), f(K * P)
+        self.xv, self.xv_cost = f(H, n, 2 * P), f(2 * P)
+        self.y, self.y_cost, self.y_grad = f(H, n, P), f(P), f(H, n, P)
+        self.cost_tmp = f(P)
+        self.sel_step, self.sel_ls, self.pick = f(P), i(P), i(P)
+        st = L.ApgState()
+        for name in L.APG_STATE_INT + L.APG_STATE_F32 + L.APG_STATE_VEC:
+            setattr(st, name, self.t[name].data_ptr())
+        self.st = st
+        ls = self.op["linesearch"]
+        prm = L.ApgParams()
+        prm.P, prm.H, prm.n_opt, prm.maxls = P, H, n, ls["maxls"]
+        prm.reset_increase = int(ls["reset_option"] == "increase")
+        prm.has_prox = int(self.lb is not None)
+        ms = self.op.get("moment_scale", None)
+        prm.use_moment_scale = int(ms is not None)
+        prm.moment_scale = float(ms) if ms is not None else 0.0
+        prm.max_no_improvement_iter = int(self.op["max_no_improvement_iter"])
+        prm.coef, prm.decrease_factor = float(ls["coef"]), float(ls["decrease_factor"])
+        prm.increase_factor, prm.max_stepsize = float(ls.get("increase_factor", 1.0)), float(ls["max_stepsize"])
+        prm.atol, prm.rtol = float(self.op["atol"]), float(self.op["rtol"])
+        if self.lb is not None:
+            lbv = np.broadcast_to(np.asarray(self.lb, np.float32), (n,))
+            ubv = np.broadcast_to(np.asarray(self.ub, np.float32), (n,))
+            for j in range(n):
+                prm.lb[j], prm.ub[j] = float(lbv[j]), float(ubv[j])
+        self.prm = prm
+
+    def _pm_view(self, buf):
+        """[H, n, Q] problem-minor buffer -> [Q, H, n] strided view the cost launcher accepts."""
+        return buf.permute(2, 0, 1)
+
+    def _cost(self, buf, cost_out, grad_buf=None, data_mod=0):
+        self.eng.cost_grad(self.pk, self.y0, self._pm_view(buf), self.ts, self.xref, self.stage.desc,
+                           terminal=None if self.terminal is None else self.terminal.desc, key=self.keys, N=self.N,
+                           want_grad=grad_buf is not None, grad_out=None if grad_buf is None else self._pm_view(grad_buf),
+                           lanes=self.lanes, data_mod=data_mod, cost_out=cost_out)
+
+    # ------------------------------------------------------------------
+    def init(self, x0, y0, xref, keys, momentum=None, stepsize=None):
+        """``init_apg`` for every problem (apg.py:53-113; like ``apg_mpc`` the warm start is NOT re-projected,
+        sde_mpc_design.py:236-239).  x0 [P,H,n_opt] (or [H,n_opt] shared), y0 [P,n_x], xref [P,H+1,n_x] or
+        [H+1,n_x], keys [P,2] or [2]."""
+        y0 = as_f32(y0).reshape(-1, self.eng.n_x).contiguous()
+        P, dev = y0.shape[0], y0.device
+        if self.P != P:
+            self._alloc(P, dev)
+        self.y0, self.xref, self.keys = y0, as_f32(xref).contiguous(), as_key(keys)
+        x0 = as_f32(x0)
+        if x0.dim() == 2:
+            x0 = x0.unsqueeze(0).expand(P, -1, -1)
+        self.y.copy_(x0.permute(1, 2, 0))
+        self._cost(self.y, self.y_cost, grad_buf=self.y_grad)
+        ls = self.op["linesearch"]
+        lib = L.load()
+        L.check(lib.sde4_apg_init(C.byref(self.prm), C.byref(self.st), _ptr(self.y), _ptr(self.y_cost), _ptr(self.y_grad),
+                                  _ptr(None if momentum is None else as_f32(momentum).contiguous()),
+                                  _ptr(None if stepsize is None else as_f32(stepsize).contiguous()),
+                                  C.c_float(ls["init_stepsize"]), C.c_float(self.op.get("beta_init", 0.25)), _stream()))
+        return self
+
+    def step(self):
+        """One masked ``one_step_apg`` for all problems (apg.py:164-274)."""
+        lib, prm, st, P = L.load(), self.prm, self.st, self.P
+        L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _stream()))
+        self._cost(self.cand, self.cand_cost, data_mod=P)
+        L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(self.cand_cost),
+                                    _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
+        self._cost(self.xv, self.xv_cost, data_mod=P)
+        L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
+                                  _ptr(self.pick), _stream()))
+        self._cost(self.y, self.cost_tmp, grad_buf=self.y_grad)
+        L.check(lib.sde4_apg_update(C.byref(prm), C.byref(st), _ptr(self.xv), _ptr(self.y), _ptr(self.y_cost),
+                                    _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
+
+    def run(self, max_iter=None, check_every=0):
+        """``apg`` (apg.py:115-161): at most ``max_iter`` masked iterations.  ``check_every`` > 0 polls the
+        not_done flags every that many iterations to exit early (one device->host sync each time)."""
+        max_iter = self.op["max_iter"] if max_iter is None else max_iter
+        for it in range(max_iter):
+            self.step()
+            if check_every and (it + 1) % check_every == 0 and not bool(self.t["not_done"].any()):
+                break
+        return self
+
+    # ------------------------------------------------------------------
+    def x_opt(self):
+        """[P, H, n_opt] view of the best iterates."""
+        return self.t["x_opt"].permute(2, 0, 1)
+
+    def state_of(self, p):
+        """``APGState`` of problem p (host scalars, device vectors) for parity checks / warm starts."""
+        g = lambda n_: self.t[n_][p].item()
+        v = lambda n_: self.t[n_][:, :, p]
+        return APGState(num_iter_no_improv=int(g("num_iter_no_improv")), num_steps=int(g("num_steps")),
+                        momentum=np.float32(g("momentum")), avg_momentum=np.float32(g("avg_momentum")),
+                        avg_linesearch=np.float32(g("avg_linesearch")), avg_stepsize=np.float32(g("avg_stepsize")),
+                        stepsize=np.float32(g("stepsize")), opt_cost=np.float32(g("opt_cost")), x_opt=v("x_opt"),
+                        curr_cost=np.float32(g("curr_cost")), init_cost=np.float32(g("init_cost")),
+                        grad_sqr=np.float32(g("grad_sqr")), not_done=bool(g("not_done")), xk=v("xk"), yk=v("yk"),
+                        grad_yk=v("grad_yk"))

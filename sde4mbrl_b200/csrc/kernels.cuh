@@ -52,6 +52,7 @@ struct CostK {
   int x_rows, rng_mode, noise_mode;
   int n_slack, warp_reduce, PW, has_terminal, write_stage_cost;
   int n_off, n_tot;
+  int data_mod;  // y0 / xref / key of problem p are those of (p mod data_mod)
 };
 
 struct ReduceK {
@@ -260,20 +261,21 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   const bool contrib = active && tc.l == 0;  // one lane per sample feeds the particle reductions
   const int p = g / a.N, n = g - p * a.N;
   const int G = a.G, H = a.H;
+  const int pd = p % a.data_mod;  // stacked candidate evaluations share the problem data
   const float* op = a.opt + (size_t)p * a.o_sp;
-  const float* xr = a.xref + (size_t)p * a.xref_sp;
+  const float* xr = a.xref + (size_t)pd * a.xref_sp;
   const bool noisy = a.noise_mode != SDE4_NOISE_NONE;
   const bool keep = GRAD || a.xbuf != nullptr;
 
   float x[NX], x0s[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) {
-    x[i] = __ldg(a.y0 + (size_t)p * NX + i);
+    x[i] = __ldg(a.y0 + (size_t)pd * NX + i);
     x0s[i] = x[i];
   }
   uint32_t b0 = 0, b1 = 0;
   if (a.noise_mode == SDE4_NOISE_THREEFRY) {
-    const uint32_t* k = a.key + (size_t)p * a.key_sp;
+    const uint32_t* k = a.key + (size_t)pd * a.key_sp;
     brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1);
   }
 

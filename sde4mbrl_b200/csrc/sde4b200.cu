@@ -4,6 +4,7 @@
 #include <string>
 #include "registry.cuh"
 #include "misc_kernels.cuh"
+#include "apg_kernels.cuh"
 
 namespace sde4 {
 
@@ -113,6 +114,10 @@ void sde4_struct_sizes(int32_t out[4]) {
   out[1] = (int32_t)sizeof(sde4_cost_desc);
   out[2] = (int32_t)sizeof(sde4_rollout_args);
   out[3] = (int32_t)sizeof(sde4_cost_args);
+}
+void sde4_apg_struct_sizes(int32_t out[2]) {
+  out[0] = (int32_t)sizeof(sde4_apg_params);
+  out[1] = (int32_t)sizeof(sde4_apg_state);
 }
 const char* sde4_last_error(void) { return g_err; }
 
@@ -264,6 +269,7 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   k.n_off = a->particle_total > 0 ? a->particle_offset : 0;
   k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
+  k.data_mod = a->data_mod > 0 ? a->data_mod : a->P;
   k.has_terminal = (a->terminal && a->terminal->kind != SDE4_COST_NONE) ? 1 : 0;
   const sde4_cost_desc td = k.has_terminal ? *a->terminal : empty_cost();
   const long long nthr = G * lanes;
@@ -330,6 +336,55 @@ int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint3
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
   return SDE4_OK;
+}
+
+static int apg_check(const sde4_apg_params* prm, const sde4_apg_state* st) {
+  if (!prm) return fail(SDE4_ERR_INVALID, "null apg params");
+  if (prm->P <= 0 || prm->H <= 0 || prm->n_opt <= 0 || prm->n_opt > SDE4_MAX_NOPT || prm->maxls < 0)
+    return fail(SDE4_ERR_INVALID, "bad apg sizes");
+  if (st && (!st->num_steps || !st->not_done || !st->xk || !st->yk || !st->grad_yk || !st->x_opt))
+    return fail(SDE4_ERR_INVALID, "null apg state buffer");
+  return SDE4_OK;
+}
+#define SDE4_APG_LAUNCH(KERNEL, ...)                                                          \
+  do {                                                                                        \
+    const int th = 128;                                                                       \
+    KERNEL<<<(prm->P + th - 1) / th, th, 0, (cudaStream_t)stream>>>(__VA_ARGS__);            \
+    cudaError_t err = cudaGetLastError();                                                     \
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, #KERNEL ": %s", cudaGetErrorString(err)); \
+    return SDE4_OK;                                                                           \
+  } while (0)
+
+int sde4_apg_init(const sde4_apg_params* prm, const sde4_apg_state* st, const float* x0, const float* cost0,
+                  const float* grad0, const float* momentum_or_null, const float* stepsize_or_null,
+                  float init_stepsize, float beta_init, void* stream) {
+  if (int rc = apg_check(prm, st)) return rc;
+  if (!st || !x0 || !cost0 || !grad0) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_init, *prm, *st, x0, cost0, grad0, momentum_or_null, stepsize_or_null, init_stepsize, beta_init);
+}
+int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals, void* stream) {
+  if (int rc = apg_check(prm, st)) return rc;
+  if (!st || !cand || !svals) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_candidates, *prm, *st, cand, svals);
+}
+int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, const float* svals,
+                    const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, void* stream) {
+  if (int rc = apg_check(prm, st)) return rc;
+  if (!st || !cand || !svals || !cand_cost || !xv || !sel_step || !sel_ls) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_select, *prm, *st, cand, svals, cand_cost, xv, sel_step, sel_ls);
+}
+int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
+                  int32_t* pick, void* stream) {
+  if (int rc = apg_check(prm, nullptr)) return rc;
+  if (!xv || !xv_cost || !y || !y_cost || !pick) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_pick, *prm, xv, xv_cost, y, y_cost, pick);
+}
+int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
+                    const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,
+                    const int32_t* sel_ls, void* stream) {
+  if (int rc = apg_check(prm, st)) return rc;
+  if (!st || !xv || !y || !y_cost || !y_grad || !pick || !sel_step || !sel_ls) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_update, *prm, *st, xv, y, y_cost, y_grad, pick, sel_step, sel_ls);
 }
 
 int sde4_fma_peak(int32_t variant, int32_t blocks, int32_t threads, int32_t iters, float* sink, double* flops,

@@ -150,7 +150,7 @@ class Engine:
     # ---- K2 + K3 ----------------------------------------------------------
     def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,
                   noise_mode=None, want_grad=True, want_xtraj=False, block_threads=0, grad_out=None,
-                  particle_offset=0, particle_total=0, lanes=0):
+                  particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None):
         """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
         Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
         pk = self.packed(nn_params)
@@ -159,6 +159,9 @@ class Engine:
         dt_t = self.dt_tensor(dt)
         H = dt_t.numel()
         opt = as_f32(opt)
+        if data_mod:
+            assert P == data_mod, "data_mod must equal the number of problem data rows"
+            P = opt.shape[0]  # stacked candidate evaluations: opt holds k*data_mod rows
         n_opt = self.n_u + stage.n_slack
         squeeze = opt.dim() == 2
         if squeeze:
@@ -179,7 +182,7 @@ class Engine:
         ws_bytes = lib.sde4_cost_workspace_bytes(C.byref(self.desc), P, N, H, stage.n_slack, int(want_grad),
                                                  int(want_xtraj))
         ws = self.workspace(ws_bytes)
-        cost = torch.empty(P, dtype=torch.float32, device=y0.device)
+        cost = torch.empty(P, dtype=torch.float32, device=y0.device) if cost_out is None else cost_out
         grad = None
         if want_grad:
             grad = torch.empty_strided(opt.shape, opt.stride(), dtype=torch.float32, device=y0.device) \
@@ -196,7 +199,7 @@ class Engine:
         keyt = None
         if noise_mode == L.NOISE_THREEFRY:
             keyt = as_key(key).reshape(-1, 2)
-            if keyt.shape[0] not in (1, P):
+            if keyt.shape[0] not in (1, P, data_mod):
                 raise Sde4Error("need one key or one key per problem")
             a.key = _ptr(keyt)
             a.key_stride_p = 0 if keyt.shape[0] == 1 else 2
@@ -212,6 +215,7 @@ class Engine:
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
         a.block_threads = block_threads
         a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
+        a.data_mod = data_mod
         L.check(lib.sde4_cost_grad(C.byref(self.desc), C.byref(a), _stream()))
         if squeeze and grad is not None:
             grad = grad.squeeze(0)

@@ -1,0 +1,58 @@
+"""Batched device-side APG (P problems in lock step, masks instead of lax.cond) vs the host APG
+(sde4mbrl_b200/apg.py, itself checked against the oracle APG) run problem by problem."""
+import contextlib
+import io as _io
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as hp
+from oracle import threefry as tf
+from sde4mbrl_b200 import configs, costs, sde_models
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("N,iters,rtol", [(1, 8, 0.0), (4, 6, 0.0), (1, 12, 0.05)])
+def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol):
+    from sde4mbrl_b200 import apg, nsde, random as R
+    from sde4mbrl_b200.apg_batched import BatchedAPG
+    P, H = 5, 20
+    pm = configs.hexa_model(horizon=H, num_particles=N, stepsize=0.05)
+    mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=N, max_iter=iters)
+    mpc["apg_mpc"]["rtol"] = rtol  # rtol > 0: some problems stop early -> exercises the not_done masks
+    with contextlib.redirect_stdout(_io.StringIO()):
+        _, multi_cost, vprox, _, construct_opt = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.SDERotorModel)
+    nn = configs.random_params(sde_models.SDERotorModel(pm), seed=3)
+    cp, op = mpc["cost_params"], mpc["apg_mpc"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    rng = np.random.default_rng(7)
+    y0 = np.stack([hp.start_state("hexa", rng) for _ in range(P)])
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    keys = tf.split(tf.PRNGKey(31), P)
+    x0 = construct_opt(u=np.full(6, 0.33, np.float32))
+    eng = multi_cost.engine
+    solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0)
+    solver.init(x0, y0, xref, keys).run()
+    xb = solver.x_opt().cpu().numpy()
+    n_done = 0
+    for p in range(P):
+        cost_p = lambda o, p=p: multi_cost(nn, y0[p], o, keys[p], stage, extra_cost_args=xref)[0]
+        prox = lambda x, stepsize=None: vprox(x)
+        s = apg.apg(apg.init_apg(x0, cost_p, op), cost_p, op, proximal_fn=prox)
+        sb = solver.state_of(p)
+        assert sb.num_steps == s.num_steps and sb.not_done == s.not_done
+        assert sb.num_iter_no_improv == s.num_iter_no_improv
+        # the kernels form y - s*g with one FMA, torch with two roundings: 1-ulp differences in the
+        # iterates grow over the iterations (most visibly in |grad|^2), hence the tolerances
+        for f in ("opt_cost", "curr_cost", "init_cost", "stepsize", "avg_stepsize", "momentum", "avg_linesearch"):
+            np.testing.assert_allclose(float(getattr(sb, f)), float(getattr(s, f)), rtol=1e-4, atol=1e-7, err_msg=f)
+        np.testing.assert_allclose(float(sb.grad_sqr), float(s.grad_sqr), rtol=5e-3)
+        assert hp.rel_err(xb[p], s.x_opt.cpu().numpy()) < 2e-4
+        assert hp.rel_err(sb.yk.cpu().numpy(), s.yk.cpu().numpy()) < 2e-4
+        n_done += int(not s.not_done)
+        assert float(s.opt_cost) < float(s.init_cost)
+    if rtol > 0:
+        assert n_done > 0  # the masked path was exercised
