@@ -270,6 +270,51 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    # ---- BASELINE configs[3]: batch of 4096 independent hexacopter MPC solves (H=20, dt=0.05, 20 APG
+    # iterations, mpc_test_cfg.yaml), PARTITIONED over the ranks with no collective (strong scaling)
+    mpc_extra = {}
+    try:
+        from sde4mbrl_b200.apg_batched import BatchedAPG
+        P_TOTAL, HM = 4096, 20
+        p_lo, p_cnt = rank * (P_TOTAL // world), P_TOTAL // world
+        rngm = np.random.default_rng(123)
+        y0m = np.tile(w["y0"], (P_TOTAL, 1))
+        y0m[:, 3:6] += rngm.normal(0, 0.05, (P_TOTAL, 3)).astype(np.float32)
+        y0m[:, 10:13] += rngm.normal(0, 0.05, (P_TOTAL, 3)).astype(np.float32)
+        keysm = np.stack([np.zeros(P_TOTAL, np.uint32), np.arange(P_TOTAL, dtype=np.uint32)], axis=1)
+        xrefm = np.tile(w["xref"][:1], (HM + 1, 1))
+        for n_part in (1, 32):
+            pmm = configs.hexa_model(horizon=HM, num_particles=n_part, stepsize=0.05)
+            mpcm = configs.hexa_mpc(horizon=HM, dt=0.05, num_particles=n_part, max_iter=20)
+            engm = Engine(sde_models.SDERotorModel(pmm))
+            solver = BatchedAPG(engm, w["nn"], w["stage"], mpcm["apg_mpc"], np.full(HM, 0.05, np.float32), n_part,
+                                lb=1e-4, ub=1.0)
+            x0m = torch.full((HM, 6), 0.33 + 2e-4, device=dev)
+            y0d = torch.as_tensor(y0m[p_lo:p_lo + p_cnt], device=dev)
+            kd = torch.as_tensor(keysm[p_lo:p_lo + p_cnt].view(np.int32), device=dev)
+            tms = []
+            for rep in range(4):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                solver.init(x0m, y0d, xrefm, kd).run(20)
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    tms.append(e0.elapsed_time(e1))
+            tm = float(np.mean(tms))
+            if world > 1:
+                t = torch.tensor([tm], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                tm = float(t.item())
+            init_c = float(solver.t["init_cost"].mean())
+            opt_c = float(solver.t["opt_cost"].mean())
+            mpc_extra["N%d" % n_part] = {"solves_per_s": P_TOTAL / (tm * 1e-3), "ms_per_batch": tm, "problems": P_TOTAL,
+                                         "particles": n_part, "horizon": HM, "apg_iterations": 20,
+                                         "mean_init_cost": init_c, "mean_opt_cost": opt_c,
+                                         "rollout_equiv_per_solve": 2 + 20 * 9}
+    except Exception as ex:  # never lose the headline line because of the extra
+        mpc_extra = {"error": repr(ex)}
 
     # ---- extras (rank 0, N=1 only): forward rollout, FP32 peak, CPU baseline
     extras = {}
@@ -359,6 +404,7 @@ def main():
         if cpu_b:
             line["cpu_baseline"] = cpu_b
         line.update(extras)
+        line["mpc_batch"] = mpc_extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
