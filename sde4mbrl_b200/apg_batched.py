@@ -38,6 +38,7 @@ class BatchedAPG:
         self.lanes = lanes
         self.lb, self.ub = lb, ub
         self.P = None
+        self._graph = None
 
     # ------------------------------------------------------------------
     def _alloc(self, P, dev):
@@ -95,7 +96,17 @@ class BatchedAPG:
         P, dev = y0.shape[0], y0.device
         if self.P != P:
             self._alloc(P, dev)
-        self.y0, self.xref, self.keys = y0, as_f32(xref).contiguous(), as_key(keys)
+            self._graph = None
+        # persistent input buffers: a captured CUDA graph keeps pointing at them across init() calls
+        xref_t, keys_t = as_f32(xref).contiguous(), as_key(keys).reshape(-1, 2)
+        if getattr(self, "y0", None) is None or self.y0.shape != y0.shape or self.xref.shape != xref_t.shape \
+                or self.keys.shape != keys_t.shape:
+            self.y0, self.xref, self.keys = y0.clone(), xref_t.clone(), keys_t.clone()
+            self._graph = None
+        else:
+            self.y0.copy_(y0)
+            self.xref.copy_(xref_t)
+            self.keys.copy_(keys_t)
         x0 = as_f32(x0)
         if x0.dim() == 2:
             x0 = x0.unsqueeze(0).expand(P, -1, -1)
@@ -123,12 +134,35 @@ class BatchedAPG:
         L.check(lib.sde4_apg_update(C.byref(prm), C.byref(st), _ptr(self.xv), _ptr(self.y), _ptr(self.y_cost),
                                     _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
 
-    def run(self, max_iter=None, check_every=0):
-        """``apg`` (apg.py:115-161): at most ``max_iter`` masked iterations.  ``check_every`` > 0 polls the
-        not_done flags every that many iterations to exit early (one device->host sync each time)."""
-        max_iter = self.op["max_iter"] if max_iter is None else max_iter
-        for it in range(max_iter):
+    def _capture(self):
+        """Capture one masked iteration (4 bookkeeping + 3 cost + 3 reduce launches) in a CUDA graph.
+        A throw-away eager iteration first makes every lazy set-up (workspace growth, func attributes)
+        happen outside the capture; the solver state is restored afterwards."""
+        names = L.APG_STATE_INT + L.APG_STATE_F32 + L.APG_STATE_VEC
+        snap = {n_: self.t[n_].clone() for n_ in names}
+        self.step()
+        torch.cuda.synchronize()
+        for n_ in names:
+            self.t[n_].copy_(snap[n_])
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
             self.step()
+        for n_ in names:  # the capture itself does not execute, but keep the state explicit
+            self.t[n_].copy_(snap[n_])
+        self._graph = g
+
+    def run(self, max_iter=None, check_every=0, use_graph=True):
+        """``apg`` (apg.py:115-161): at most ``max_iter`` masked iterations.  ``check_every`` > 0 polls the
+        not_done flags every that many iterations to exit early (one device->host sync each time).
+        ``use_graph`` replays a captured CUDA graph per iteration (launch-bound otherwise for small P*N)."""
+        max_iter = self.op["max_iter"] if max_iter is None else max_iter
+        if use_graph and getattr(self, "_graph", None) is None:
+            self._capture()
+        for it in range(max_iter):
+            if use_graph:
+                self._graph.replay()
+            else:
+                self.step()
             if check_every and (it + 1) % check_every == 0 and not bool(self.t["not_done"].any()):
                 break
         return self

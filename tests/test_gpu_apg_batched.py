@@ -35,7 +35,12 @@ def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol):
     x0 = construct_opt(u=np.full(6, 0.33, np.float32))
     eng = multi_cost.engine
     solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0)
-    solver.init(x0, y0, xref, keys).run()
+    solver.init(x0, y0, xref, keys).run(use_graph=False)
+    x_eager = solver.x_opt().clone()
+    solver.init(x0, y0, xref, keys).run(use_graph=True)  # CUDA-graph replay must give the same iterates
+    assert torch.equal(solver.x_opt(), x_eager)
+    solver.init(x0, y0 * 1.0, xref, keys).run(use_graph=True)  # re-init with new host buffers reuses the graph
+    assert torch.equal(solver.x_opt(), x_eager)
     xb = solver.x_opt().cpu().numpy()
     n_done = 0
     for p in range(P):
