@@ -270,6 +270,77 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    # ---- BASELINE configs[4] (second half): cartpole training loss forward/backward, B=512, N=1, H=30
+    train_extra = {}
+    if rank == 0:
+        try:
+            from sde4mbrl_b200 import costs as _c
+            BT, HT = 512, 30
+            pmt = configs.cartpole_model(horizon=HT, num_particles=1)
+            mt = sde_models.CartPoleSDE(pmt)
+            engt = Engine(mt)
+            pkt = PackedParams(mt, configs.random_params(mt, seed=0), engt.desc)
+            g = torch.Generator(device=dev).manual_seed(5)
+            ym = torch.randn((BT, HT + 1, 4), device=dev, generator=g) * 0.5
+            ut = torch.rand((BT, HT, 1), device=dev, generator=g) * 2 - 1
+            kt = torch.stack([torch.zeros(BT, dtype=torch.int32, device=dev), torch.arange(BT, dtype=torch.int32, device=dev)], dim=1).contiguous()
+            owt = np.array([9, 5, 1, 1.0, 10])
+            dc = _c.QuadraticCost(list(1.0 / owt ** 2), [0.0], [0.0], feat="cartpole")
+            tst = np.full(HT, 0.02, np.float32)
+            tms = []
+            for rep in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                engt.loss_grad(pkt, ym, ut, tst, dc.desc, kt, N=1)
+                e1.record()
+                torch.cuda.synchronize()
+                if rep > 1:
+                    tms.append(e0.elapsed_time(e1))
+            tm = float(np.mean(tms))
+            train_extra = {"batch": BT, "particles": 1, "horizon": HT, "ms_fwd_bwd": tm,
+                           "particle_steps_per_s": BT * HT / (tm * 1e-3),
+                           "fp32_tflops_algorithmic": 3.0 * 3135.0 * BT * HT / (tm * 1e-3) / 1e12}
+        except Exception as ex:
+            train_extra = {"error": repr(ex)}
+    # ---- BASELINE configs[4] (first half): cartpole nSDE as an MBRL simulator, 2^20 start states x
+    # horizon 30, one particle each; start states sharded over the ranks (no collective)
+    sim_extra = {}
+    try:
+        PS, HS = (1 << 20) // world, 30
+        pmc = configs.cartpole_model(horizon=HS, num_particles=1)
+        mc = sde_models.CartPoleSDE(pmc)
+        engc = Engine(mc)
+        nnc = configs.random_params(mc, seed=0)
+        pkc = PackedParams(mc, nnc, engc.desc)
+        g = torch.Generator(device=dev).manual_seed(rank)
+        obs = (torch.rand((PS, 4), device=dev, generator=g) * 2 - 1) * torch.tensor([2.0, 3.0, 3.14159, 6.0], device=dev)
+        actc = torch.rand((PS, HS, 1), device=dev, generator=g) * 2 - 1
+        keysc = torch.stack([torch.full((PS,), rank, dtype=torch.int32, device=dev),
+                             torch.arange(PS, dtype=torch.int32, device=dev)], dim=1).contiguous()
+        outc = torch.empty((HS + 1, 4, PS), device=dev)
+        tsc = np.full(HS, 0.02, np.float32)
+        tms = []
+        for rep in range(4):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engc.rollout(pkc, obs, actc, tsc, key=keysc, N=1, out=outc)
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                tms.append(e0.elapsed_time(e1))
+        tm = float(np.mean(tms))
+        if world > 1:
+            t = torch.tensor([tm], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tm = float(t.item())
+        tot = PS * world * HS
+        sim_extra = {"start_states": PS * world, "horizon": HS, "ms": tm, "particle_steps_per_s": tot / (tm * 1e-3),
+                     "fp32_tflops": 3135.0 * tot / (tm * 1e-3) / 1e12,
+                     "trajectory_writeout_gbs": 4.0 * PS * world * (HS + 1) * 4 / (tm * 1e-3) / 1e9}
+        del outc, obs, actc
+    except Exception as ex:
+        sim_extra = {"error": repr(ex)}
     # ---- BASELINE configs[3]: batch of 4096 independent hexacopter MPC solves (H=20, dt=0.05, 20 APG
     # iterations, mpc_test_cfg.yaml), PARTITIONED over the ranks with no collective (strong scaling)
     mpc_extra = {}
@@ -405,6 +476,8 @@ def main():
             line["cpu_baseline"] = cpu_b
         line.update(extras)
         line["mpc_batch"] = mpc_extra
+        line["simulator_rollouts"] = sim_extra
+        line["training_loss"] = train_extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

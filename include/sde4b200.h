@@ -220,6 +220,22 @@ int sde4_rng_normal(const uint32_t* key_host, uint64_t total, uint64_t offset, u
 /* out[num][2] = jax.random.split(key, num); key_dev is a DEVICE uint32[2] */
 int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint32_t* out, void* stream);
 
+/* ---- training loss: create_model_loss_fn(...).loss_fn data term and jax.grad of it w.r.t. the model
+ *      parameters, sde4mbrl/nsde.py:683-804 (sample_for_loss_computation), :1185-1203 (multi_sampling,
+ *      loss_fn), as used by sde4mbrl/train_sde.py:248-262.
+ *      Problems = minibatch elements b (P = B), each with N particles:
+ *        loss[b] = mean_n sum_{t=1..H} sum_i w_i (phi(ymeas[b,t]) - phi(x[b,n,t]))_i^2
+ *      with the QUADRATIC cost descriptor (w_x = 1/obs_weights^2, feat = state_transform_for_loss) in
+ *      args->stage, args->xref = ymeas[b][H+1][n_x] (rows = solver steps), args->opt = the controls
+ *      u[b][H][n_u], args->key = split(rng, B) (one key per element; the kernel derives
+ *      split(k_b, N)[n] -> split(., 3)[0] -> split(., 2)[0] as nsde.py:1187,709 / sde_solver.py:276).
+ *      grad_params (device, sde4_param_layout() floats, same layout as the parameter block) receives
+ *      d (mean_b loss[b]) / d params; args->grad (may be NULL) the gradient w.r.t. the controls.
+ *      Not covered: density_loss / mu_coeff terms and num_sample2consider, the
+ *      multirotor's physical scalars (kernel exists for the MSD and cartpole architectures). */
+size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t H);
+int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* args, float* grad_params, void* stream);
+
 /* ---- batched APG-MPC: sde4mbrl/apg.py (init_apg :53-113, one_step_apg :164-274,
  *      armijo_line_search :332-379, _while_loop :451-464) for P independent problems at once.
  *      The control flow of the reference (lax.cond / bounded scans) becomes per-problem masks:

@@ -33,7 +33,9 @@ from . import threefry as tf
 # helpers
 # ---------------------------------------------------------------------------
 def _t(v, like):
-    return torch.as_tensor(np.asarray(v, dtype=np.float64), dtype=like.dtype, device=like.device)
+    if isinstance(v, torch.Tensor):  # parameter trees of torch tensors keep their autograd history
+        return v.to(like.dtype)
+    return torch.as_tensor(np.array(v, dtype=np.float64), dtype=like.dtype, device=like.device)
 
 
 def activation(name):
@@ -536,3 +538,54 @@ def u_slew_cost(opt, time_steps, cp, n_u):
     slew = (opt[1:, :n_u] - opt[:-1, :n_u]) / ts
     coeff = _t(np.broadcast_to(np.asarray(cp["u_slew_coeff"], np.float64), (n_u,)), opt).reshape(1, -1)
     return (slew ** 2 * coeff).sum() * cp.get("res_mult", 1.0)
+
+
+# ---------------------------------------------------------------------------
+# Training loss, data term (nsde.py:683-804 sample_for_loss_computation, :1185-1203 loss_fn)
+# ---------------------------------------------------------------------------
+def loss_noise(rng, B, N, H, n_x, mode=tf.MODE_ORIGINAL):
+    """dw[B, N, H, n_x] with the training key chain: k_b = split(rng, B)[b] (nsde.py:1196),
+    k_bn = split(k_b, N)[n] (:1187), rng_brownian = split(k_bn, 3)[0] (:709), then the solver's own
+    split(rng_brownian)[0] (sde_solver.py:276) and normal(., (H, n_x)) (:283)."""
+    kb = tf.split(rng, B, mode)
+    out = np.zeros((B, N, H, n_x), np.float32)
+    for b in range(B):
+        kbn = tf.split(kb[b], N, mode)
+        for n in range(N):
+            r1 = tf.split(kbn[n], 3, mode)[0]
+            r2 = tf.split(r1, 2, mode)[0]
+            out[b, n] = tf.normal(r2, (H, n_x), mode)
+    return out
+
+
+def state_transform_for_loss(kind, x):
+    """cartpole_sde.py:49-53; identity for the other models (nsde.py:530-542)."""
+    if kind == "cart_pole_sde":
+        return torch.stack([x[..., 0], x[..., 1], torch.sin(x[..., 2]), torch.cos(x[..., 2]), x[..., 3]], dim=-1)
+    return x
+
+
+def data_loss(model, kind, ymeas, uval, dw, obs_weights=1.0, num_steps2data=1):
+    """mean over (batch, particles) of sum_t sum_i ((T(y_meas) - T(y_pred)) / w)^2 (nsde.py:766, :1203) with
+    u_sampling_strategy 'first' and no num_sample2consider.  ymeas[B, Hd+1, n_y], uval[B, Hd, n_u],
+    dw[B, N, H, n_x] (H = Hd / num_steps2data)."""
+    ts = compute_timesteps(model.params)
+    H = len(ts)
+    B = ymeas.shape[0]
+    y_values = ymeas[:, ::num_steps2data]
+    u_values = uval.reshape(B, H, num_steps2data, -1)[:, :, 0]
+    xs = euler_maruyama(model, ts, y_values[:, None, 0, :].expand(B, dw.shape[1], -1), u_values[:, None], dw)
+    pred = state_transform_for_loss(kind, xs[:, :, 1:])
+    meas = state_transform_for_loss(kind, y_values[:, None, 1:])
+    w = _t(np.broadcast_to(np.asarray(obs_weights, np.float64), (pred.shape[-1],)), pred)
+    err = (((meas - pred) / w) ** 2).sum(dim=(-1, -2))  # [B, N]
+    return err.mean(dim=1).mean(), err
+
+
+def weight_penalty(tree, nominal, coeffs):
+    """sum_leaves coeff * ||p - p_nominal||^2 (nsde.py:1216-1219)."""
+    tot = 0.0
+    for mod in tree:
+        for name in tree[mod]:
+            tot = tot + ((tree[mod][name] - nominal[mod][name]) ** 2).sum() * coeffs[mod][name]
+    return tot

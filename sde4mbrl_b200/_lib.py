@@ -100,7 +100,7 @@ class ApgState(C.Structure):
 
 
 EXPORTED_SYMBOLS = (
-    "sde4_rollout", "sde4_cost_workspace_bytes", "sde4_cost_grad", "sde4_rng_bits", "sde4_rng_normal",
+    "sde4_rollout", "sde4_cost_workspace_bytes", "sde4_cost_grad", "sde4_loss_workspace_bytes", "sde4_loss_grad", "sde4_rng_bits", "sde4_rng_normal",
     "sde4_rng_split", "sde4_param_layout", "sde4_model_supported", "sde4_supported_archs",
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
@@ -130,6 +130,10 @@ def load():
     lib.sde4_cost_workspace_bytes.restype = C.c_size_t
     lib.sde4_cost_grad.argtypes = [C.POINTER(ModelDesc), C.POINTER(CostArgs), C.c_void_p]
     lib.sde4_cost_grad.restype = C.c_int
+    lib.sde4_loss_workspace_bytes.argtypes = [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int32]
+    lib.sde4_loss_workspace_bytes.restype = C.c_size_t
+    lib.sde4_loss_grad.argtypes = [C.POINTER(ModelDesc), C.POINTER(CostArgs), C.c_void_p, C.c_void_p]
+    lib.sde4_loss_grad.restype = C.c_int
     for name in ("sde4_rng_bits", "sde4_rng_normal"):
         fn = getattr(lib, name)
         fn.argtypes = [C.POINTER(C.c_uint32), C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]

@@ -181,10 +181,18 @@ SDE4_DEV float bits_to_normal(uint32_t bits) {
 
 // Per-sample Brownian key: k_p = split(rng, N)[n] (nsde.py:1026,1581), then
 // rng_brownian = split(k_p, 2)[0] (sde_solver.py:276).
+// chain 1 (training loss, nsde.py:1187 -> :709 -> sde_solver.py:276): one more level,
+// rng_brownian = split(k_p, 3)[0], before the solver's own split.
 SDE4_DEV void brownian_key(uint32_t r0, uint32_t r1, uint32_t n, uint32_t N, int mode, uint32_t& b0,
-                           uint32_t& b1) {
+                           uint32_t& b1, int chain = 0) {
   uint32_t p0, p1;
   jax_split(r0, r1, n, N, mode, p0, p1);
+  if (chain == 1) {
+    uint32_t q0, q1;
+    jax_split(p0, p1, 0u, 3u, mode, q0, q1);
+    p0 = q0;
+    p1 = q1;
+  }
   jax_split(p0, p1, 0u, 2u, mode, b0, b1);
 }
 

@@ -53,6 +53,11 @@ struct CostK {
   int n_slack, warp_reduce, PW, has_terminal, write_stage_cost;
   int n_off, n_tot;
   int data_mod;  // y0 / xref / key of problem p are those of (p mod data_mod)
+  // training loss (sde4_loss_grad): plain sum over t >= 1 instead of the trapezoid, training key chain,
+  // parameter-gradient streams of the three networks ([rows][H*G], column = t*G + g)
+  int sum_mode, rng_chain;
+  float* pd_net[3];
+  unsigned long long pd_stride;
 };
 
 struct ReduceK {
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   uint32_t b0 = 0, b1 = 0;
   if (a.noise_mode == SDE4_NOISE_THREEFRY) {
     const uint32_t* k = a.key + (size_t)pd * a.key_sp;
-    brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1);
+    brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1, a.rng_chain);
   }
 
   // ---------------- forward sweep ----------------
@@ -317,7 +322,8 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
                     : 0.0f;
       c_next += constr_cost<NX, false>(cd, x, sl, 0.0f, dummy_gx, dummy_gs);
     }
-    cost = fmaf(0.5f * dt, c_prev + c_next, cost);  // trapezoid (nsde.py:1515)
+    if (a.sum_mode) cost += c_next;  // data term of the training loss: sum over t >= 1 (nsde.py:766)
+    else cost = fmaf(0.5f * dt, c_prev + c_next, cost);  // trapezoid (nsde.py:1515)
     c_prev = c_next;
     if (keep && a.xbuf) {
       float* out = a.xbuf + (size_t)(t + 1) * a.x_rows * G + g;
@@ -352,7 +358,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
 #pragma unroll
   for (int j = 0; j < NU; ++j) gu[j] = 0.0f;  // row H-1 also receives the u-gradient of stage H
   {
-    const float wH = 0.5f * __ldg(a.dt + H - 1);
+    const float wH = a.sum_mode ? 1.0f : 0.5f * __ldg(a.dt + H - 1);
     stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
     if (CONSTR) {
       float sl[NX];
@@ -370,8 +376,15 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   }
   const float* nz = a.noise_mode == SDE4_NOISE_GIVEN ? a.noise : a.dwbuf;
 
+  if constexpr (M::Ev::PGRAD) {
+    tc.ev.dnet[0] = a.pd_net[0];
+    tc.ev.dnet[1] = a.pd_net[1];
+    tc.ev.dnet[2] = a.pd_net[2];
+    tc.ev.dstride = a.pd_stride;
+  }
   for (int t = H - 1; t >= 0; --t) {
     const float dt = __ldg(a.dt + t);
+    if constexpr (M::Ev::PGRAD) tc.ev.dcol = (size_t)t * G + g;
     // through the projection (needs the projected x_{t+1}, still in the checkpoint buffer)
     {
       float aux = 0.0f;
@@ -403,7 +416,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
     }
     // stage cost at t: trapezoid weight w_t
-    const float wt = t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt;
+    const float wt = a.sum_mode ? (t > 0 ? 1.0f : 0.0f) : (t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt);
     stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)t * NX, true, wt, gx, gu);
     if (CONSTR) {
       float sl[NX];

@@ -117,4 +117,56 @@ __global__ void __launch_bounds__(1024) k_fma_peak(int iters, float* sink) {
   if (s == 123.456f) sink[0] = s;
 }
 
+
+// ----------------------------------------------------------------------------
+// K5: parameter gradients of the training loss from the streams written by the DUMP evaluators:
+//   out[a*ldo + b] = scale * sum_k A[a][k] * B[b][k]     (A == nullptr: A = 1, i.e. bias / scaler sums)
+// One CTA per output row a; threads stride over the K = H*G columns (coalesced), 32 register
+// accumulators per thread, fixed-order block reduction (deterministic, no atomics).
+// ----------------------------------------------------------------------------
+struct WgradTask {
+  const float* A;
+  const float* B;
+  float* out;
+  int n_a, n_b, ldo, row0;  // row0: first CTA of this task
+};
+struct WgradK {
+  WgradTask task[24];
+  int n_tasks;
+  unsigned long long K;  // columns; row stride of A and B
+  float scale;
+};
+
+__global__ void __launch_bounds__(256) k_wgrad(const __grid_constant__ WgradK a) {
+  int ti = 0;
+  while (ti + 1 < a.n_tasks && (int)blockIdx.x >= a.task[ti + 1].row0) ++ti;
+  const WgradTask& t = a.task[ti];
+  const int row = blockIdx.x - t.row0;
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
+  const float* Ar = t.A ? t.A + (size_t)row * a.K : nullptr;
+  for (unsigned long long k = threadIdx.x; k < a.K; k += blockDim.x) {
+    const float av = Ar ? Ar[k] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < t.n_b) acc[j] = fmaf(av, t.B[(size_t)j * a.K + k], acc[j]);
+  }
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < t.n_b) {
+    float s = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
+    t.out[(size_t)row * t.ldo + threadIdx.x] = s * a.scale;
+  }
+}
+
 }  // namespace sde4

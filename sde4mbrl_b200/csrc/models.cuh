@@ -54,7 +54,7 @@ struct Arch {
   template <int SLOT, int L>
   SDE4_DEV static NetRef ref(const float* W) {
     constexpr int off = SLOT == 0 ? OFF_DENSITY : (SLOT == 1 ? OFF_NET_A : OFF_NET_B);
-    return NetRef{W + off, W + off_w1p(SLOT, L)};
+    return NetRef{SLOT, W + off, W + off_w1p(SLOT, L)};
   }
 
   static bool matches(const sde4_model_desc& d) {
@@ -170,21 +170,32 @@ struct Diffusion {
     } else {
       float z[DNet::IN], J[DNet::IN], dens;
       gather_in(x, d, z);
-      Ev::template scalar_value_grad<DNet>(A::template ref<0, Ev::L>(W), sc, z, dens, J);
-      float gd = 0.0f;
+      // cotangent of the density output: gd = sum_k (dw_i lam_i prior_i) eta'(.) (aggr + coeff_k)
+      auto gd_of = [&](float dv) {
+        float gd = 0.0f;
 #pragma unroll
-      for (int k = 0; k < NO; ++k) {
-        const int i = nth_bit(A::NOUT_MASK, k);
-        float coeff = 0.0f;
-        if constexpr (A::HAS_SCALER) coeff = W[A::OFF_DERIVED + k];
-        const float e = eta_of(W, d, dens, k);
-        gd = fmaf(noise_at(i) * lam[i] * d.noise_prior[i], e * (1.0f - e) * (d.aggr + coeff), gd);
-      }
+        for (int k = 0; k < NO; ++k) {
+          const int i = nth_bit(A::NOUT_MASK, k);
+          float coeff = 0.0f;
+          if constexpr (A::HAS_SCALER) coeff = W[A::OFF_DERIVED + k];
+          const float e = eta_of(W, d, dv, k);
+          // states with zero prior have no noise sample (never generated / stored): guard the read
+          const float dwi = d.noise_prior[i] != 0.0f ? noise_at(i) : 0.0f;
+          const float t1 = dwi * lam[i] * d.noise_prior[i] * (e * (1.0f - e));  // d loss / d (sigmoid arg)
+          gd = fmaf(t1, d.aggr + coeff, gd);
+          if constexpr (Ev::PGRAD && A::HAS_SCALER) {  // scaler = [coeff | offset] = exp(.)*1e-7 (nsde.py:413-414)
+            sc.dnet[0][(size_t)(DNet::DUMP_ROWS + k) * sc.dstride + sc.dcol] = t1 * dv * coeff;
+            sc.dnet[0][(size_t)(DNet::DUMP_ROWS + NO + k) * sc.dstride + sc.dcol] = t1 * W[A::OFF_DERIVED + NO + k];
+          }
+        }
+        return gd;
+      };
+      Ev::template scalar_value_grad<DNet>(A::template ref<0, Ev::L>(W), sc, z, dens, J, gd_of);
       float gred[M::NR];
 #pragma unroll
       for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = gd * J[k];
+      for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = J[k];
       M::reduced_state_vjp(x, d, gred, gx);
     }
   }

@@ -35,6 +35,9 @@ struct Net {
   static constexpr int OFF_B2 = OFF_W2 + OUT_ * H2P;
   static constexpr int SIZE = PRESENT ? OFF_B2 + OUTP : 0;
   static constexpr int MACS = IN_ * H1_ + H1_ * H2_ + H2_ * OUT_;
+  // rows of the parameter-gradient stream of this network
+  static constexpr int R_IN = 0, R_H1 = IN_, R_H2 = IN_ + H1_, R_C1 = IN_ + H1_ + H2_, R_G2 = R_C1 + H1_,
+                       R_GOUT = R_G2 + H2_, DUMP_ROWS = PRESENT ? R_GOUT + OUT_ : 0;
   static_assert(H1_ <= MAXW && H2_ <= MAXW, "hidden width above MAXW");
 
   static bool matches(const sde4_net_desc& d) {
@@ -56,6 +59,11 @@ struct Scratch {
   static constexpr int SLOT_X = 3;   // noise dw[] / misc (NX <= 16 entries)
   static constexpr int NSLOTS = 4;
   SDE4_DEV float* slot(int s) const { return base + (size_t)s * MAXW * bs; }
+  // parameter-gradient streams (training-loss kernel only, DUMP evaluators): for network `slot` the
+  // rows [in | h1 | h2 | c1 | g2 | gout] of this thread's (step, sample) column, see wgrad in misc_kernels.cuh
+  float* dnet[3];
+  size_t dstride, dcol;
+  SDE4_DEV void dump(int slot_, int row, float v) const { dnet[slot_][(size_t)row * dstride + dcol] = v; }
 };
 
 // ---- layer 1: few inputs (registers), fully unrolled ----------------------------------------
@@ -100,9 +108,13 @@ SDE4_DEV void dense_out_t(const float* wT, const float* b, const float (&in)[IN]
 }
 
 // Forward.  KEEP: act' of both hidden layers is left in scratch slots D1 / D2 for mlp_bwd.
-template <class N, bool KEEP>
-SDE4_DEV void mlp_fwd(const float* W, const Scratch& sc, const float (&in)[N::IN], float (&out)[N::OUT]) {
+template <class N, bool KEEP, bool DUMP = false>
+SDE4_DEV void mlp_fwd(const float* W, const Scratch& sc, const float (&in)[N::IN], float (&out)[N::OUT], int slot = 0) {
   float* sh = sc.slot(Scratch::SLOT_H);
+  if (DUMP && KEEP) {
+#pragma unroll
+    for (int k = 0; k < N::IN; ++k) sc.dump(slot, N::R_IN + k, in[k]);
+  }
   {
     float a1[N::H1];
     dense_in_regs<N::IN, N::H1, N::H1P>(W + N::OFF_W0, W + N::OFF_B0, in, a1);
@@ -116,6 +128,7 @@ SDE4_DEV void mlp_fwd(const float* W, const Scratch& sc, const float (&in)[N::IN
         h = act_fwd<N::ACT>(a1[j]);
       }
       sh[(size_t)j * sc.bs] = h;
+      if (DUMP && KEEP) sc.dump(slot, N::R_H1 + j, h);
     }
   }
   float a2[N::H2];
@@ -126,6 +139,7 @@ SDE4_DEV void mlp_fwd(const float* W, const Scratch& sc, const float (&in)[N::IN
       float dd;
       act_fwd_d<N::ACT>(a2[j], a2[j], dd);
       sc.slot(Scratch::SLOT_D2)[(size_t)j * sc.bs] = dd;
+      if (DUMP) sc.dump(slot, N::R_H2 + j, a2[j]);
     } else {
       a2[j] = act_fwd<N::ACT>(a2[j]);
     }
@@ -135,8 +149,8 @@ SDE4_DEV void mlp_fwd(const float* W, const Scratch& sc, const float (&in)[N::IN
 
 // Shared tail of the backward sweeps: g2[] (cotangent of the pre-activation a2, registers) ->
 // cotangent of a1 (rolled over the H1 rows, through scratch) -> gin.
-template <class N>
-SDE4_DEV void mlp_bwd_tail(const float* W, const Scratch& sc, const float (&g2)[N::H2], float (&gin)[N::IN]) {
+template <class N, bool DUMP = false>
+SDE4_DEV void mlp_bwd_tail(const float* W, const Scratch& sc, const float (&g2)[N::H2], float (&gin)[N::IN], int slot = 0) {
   float* sh = sc.slot(Scratch::SLOT_H);
   const float* d1 = sc.slot(Scratch::SLOT_D1);
 #pragma unroll 4
@@ -145,7 +159,9 @@ SDE4_DEV void mlp_bwd_tail(const float* W, const Scratch& sc, const float (&g2)[
     float r[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // 4 independent chains per row (FMA latency)
 #pragma unroll
     for (int j = 0; j < N::H2; ++j) r[j & 3] = fmaf(row[j], g2[j], r[j & 3]);
-    sh[(size_t)i * sc.bs] = ((r[0] + r[1]) + (r[2] + r[3])) * d1[(size_t)i * sc.bs];
+    const float c1 = ((r[0] + r[1]) + (r[2] + r[3])) * d1[(size_t)i * sc.bs];
+    sh[(size_t)i * sc.bs] = c1;
+    if (DUMP) sc.dump(slot, N::R_C1 + i, c1);
   }
   float g1[N::H1];
 #pragma unroll
@@ -164,26 +180,37 @@ SDE4_DEV void mlp_bwd_tail(const float* W, const Scratch& sc, const float (&g2)[
 }
 
 // Input-VJP after mlp_fwd<N, true>:  gin = (d out / d in)^T gout.
-template <class N>
-SDE4_DEV void mlp_bwd(const float* W, const Scratch& sc, const float (&gout)[N::OUT], float (&gin)[N::IN]) {
+template <class N, bool DUMP = false>
+SDE4_DEV void mlp_bwd(const float* W, const Scratch& sc, const float (&gout)[N::OUT], float (&gin)[N::IN], int slot = 0) {
   float g2[N::H2];
   const float* d2 = sc.slot(Scratch::SLOT_D2);
+  if (DUMP) {
+#pragma unroll
+    for (int o = 0; o < N::OUT; ++o) sc.dump(slot, N::R_GOUT + o, gout[o]);
+  }
 #pragma unroll
   for (int j = 0; j < N::H2; ++j) {
     float s = 0.0f;
 #pragma unroll
     for (int o = 0; o < N::OUT; ++o) s = fmaf(W[N::OFF_W2 + o * N::H2P + j], gout[o], s);
     g2[j] = s * d2[(size_t)j * sc.bs];
+    if (DUMP) sc.dump(slot, N::R_G2 + j, g2[j]);
   }
-  mlp_bwd_tail<N>(W, sc, g2, gin);
+  mlp_bwd_tail<N, DUMP>(W, sc, g2, gin, slot);
 }
 
 // Recompute-forward + input-VJP when the output cotangent is known up front (nothing but act'(a1)
 // goes through scratch: the cotangent of a2 is formed in registers right after layer 2).
-template <class N>
+template <class N, bool DUMP = false>
 SDE4_DEV void mlp_fwd_vjp(const float* W, const Scratch& sc, const float (&in)[N::IN], const float (&gout)[N::OUT],
-                          float (&gin)[N::IN]) {
+                          float (&gin)[N::IN], int slot = 0) {
   float* sh = sc.slot(Scratch::SLOT_H);
+  if (DUMP) {
+#pragma unroll
+    for (int k = 0; k < N::IN; ++k) sc.dump(slot, N::R_IN + k, in[k]);
+#pragma unroll
+    for (int o = 0; o < N::OUT; ++o) sc.dump(slot, N::R_GOUT + o, gout[o]);
+  }
   {
     float a1[N::H1];
     dense_in_regs<N::IN, N::H1, N::H1P>(W + N::OFF_W0, W + N::OFF_B0, in, a1);
@@ -193,6 +220,7 @@ SDE4_DEV void mlp_fwd_vjp(const float* W, const Scratch& sc, const float (&in)[N
       act_fwd_d<N::ACT>(a1[j], h, dd);
       sc.slot(Scratch::SLOT_D1)[(size_t)j * sc.bs] = dd;
       sh[(size_t)j * sc.bs] = h;
+      if (DUMP) sc.dump(slot, N::R_H1 + j, h);
     }
   }
   float g2[N::H2];
@@ -205,17 +233,26 @@ SDE4_DEV void mlp_fwd_vjp(const float* W, const Scratch& sc, const float (&in)[N
 #pragma unroll
     for (int o = 0; o < N::OUT; ++o) s = fmaf(W[N::OFF_W2 + o * N::H2P + j], gout[o], s);
     g2[j] = s * dd;
+    if (DUMP) {
+      sc.dump(slot, N::R_H2 + j, h);
+      sc.dump(slot, N::R_G2 + j, g2[j]);
+    }
   }
-  mlp_bwd_tail<N>(W, sc, g2, gin);
+  mlp_bwd_tail<N, DUMP>(W, sc, g2, gin, slot);
 }
 
-// Scalar-output MLP (the diffusion density net, nsde.py:387-407): value and input-gradient in one
-// pass:  out = mlp(in),  J[k] = d out / d in[k].
-template <class N>
+// Scalar-output MLP (the diffusion density net, nsde.py:387-407): value and input-VJP in one pass:
+//   out = mlp(in),  gd = gd_of(out) (the output cotangent, which depends on the value),
+//   J[k] = gd * d out / d in[k].
+template <class N, bool DUMP = false, class GdFn>
 SDE4_DEV void mlp_scalar_value_grad(const float* W, const Scratch& sc, const float (&in)[N::IN], float& out,
-                                    float (&J)[N::IN]) {
+                                    float (&J)[N::IN], GdFn gd_of, int slot = 0) {
   static_assert(N::OUT == 1, "scalar-output network expected");
   float* sh = sc.slot(Scratch::SLOT_H);
+  if (DUMP) {
+#pragma unroll
+    for (int k = 0; k < N::IN; ++k) sc.dump(slot, N::R_IN + k, in[k]);
+  }
   {
     float a1[N::H1];
     dense_in_regs<N::IN, N::H1, N::H1P>(W + N::OFF_W0, W + N::OFF_B0, in, a1);
@@ -225,6 +262,7 @@ SDE4_DEV void mlp_scalar_value_grad(const float* W, const Scratch& sc, const flo
       act_fwd_d<N::ACT>(a1[j], h, dd);
       sc.slot(Scratch::SLOT_D1)[(size_t)j * sc.bs] = dd;
       sh[(size_t)j * sc.bs] = h;
+      if (DUMP) sc.dump(slot, N::R_H1 + j, h);
     }
   }
   float g2[N::H2];
@@ -237,9 +275,17 @@ SDE4_DEV void mlp_scalar_value_grad(const float* W, const Scratch& sc, const flo
     const float w2 = W[N::OFF_W2 + j];
     o = fmaf(w2, h, o);
     g2[j] = w2 * dd;
+    if (DUMP) sc.dump(slot, N::R_H2 + j, h);
   }
   out = o;
-  mlp_bwd_tail<N>(W, sc, g2, J);
+  const float gd = gd_of(o);
+#pragma unroll
+  for (int j = 0; j < N::H2; ++j) {
+    g2[j] *= gd;
+    if (DUMP) sc.dump(slot, N::R_G2 + j, g2[j]);
+  }
+  if (DUMP) sc.dump(slot, N::R_GOUT, gd);
+  mlp_bwd_tail<N, DUMP>(W, sc, g2, J, slot);
 }
 
 
@@ -252,32 +298,37 @@ SDE4_DEV void mlp_scalar_value_grad(const float* W, const Scratch& sc, const flo
 //            problem with 4096 particles = only 128 warps for 592 warp schedulers)
 // ================================================================================================
 struct NetRef {
+  int slot;          // 0 density, 1 net A, 2 net B
   const float* w;    // packed network image (layout above)
   const float* w1p;  // EvL only: copy of w1 with a 4-float gap after every H1/L rows (bank spread)
 };
 
-struct Ev1 {
+template <bool DUMP>
+struct Ev1T {
   static constexpr int L = 1;
+  static constexpr bool PGRAD = DUMP;  // also streams what the parameter gradients need (training loss)
   using Ctx = Scratch;
   template <class N, bool KEEP>
   SDE4_DEV static void fwd(const NetRef& r, Ctx& c, const float (&in)[N::IN], float (&out)[N::OUT]) {
-    mlp_fwd<N, KEEP>(r.w, c, in, out);
+    mlp_fwd<N, KEEP, DUMP>(r.w, c, in, out, r.slot);
   }
   template <class N>
   SDE4_DEV static void bwd(const NetRef& r, Ctx& c, const float (&gout)[N::OUT], float (&gin)[N::IN]) {
-    mlp_bwd<N>(r.w, c, gout, gin);
+    mlp_bwd<N, DUMP>(r.w, c, gout, gin, r.slot);
   }
   template <class N>
   SDE4_DEV static void fwd_vjp(const NetRef& r, Ctx& c, const float (&in)[N::IN], const float (&gout)[N::OUT],
                                float (&gin)[N::IN]) {
-    mlp_fwd_vjp<N>(r.w, c, in, gout, gin);
+    mlp_fwd_vjp<N, DUMP>(r.w, c, in, gout, gin, r.slot);
   }
-  template <class N>
+  template <class N, class GdFn>
   SDE4_DEV static void scalar_value_grad(const NetRef& r, Ctx& c, const float (&in)[N::IN], float& out,
-                                         float (&J)[N::IN]) {
-    mlp_scalar_value_grad<N>(r.w, c, in, out, J);
+                                         float (&J)[N::IN], GdFn gd_of) {
+    mlp_scalar_value_grad<N, DUMP>(r.w, c, in, out, J, gd_of, r.slot);
   }
 };
+using Ev1 = Ev1T<false>;
+using Ev1P = Ev1T<true>;
 
 // ---- lane-split evaluator ------------------------------------------------------------------------
 // Lane l of a sample owns the hidden units [l*B, (l+1)*B) of each hidden layer (B = H/L).
@@ -292,6 +343,7 @@ constexpr int MAXB = 8;  // largest per-lane block (MAXW / smallest L >= 4)
 template <int L_>
 struct EvL {
   static constexpr int L = L_;
+  static constexpr bool PGRAD = false;
   static_assert(L_ == 2 || L_ == 4 || L_ == 8 || L_ == 16, "lanes per sample");
   struct Ctx {
     int l;             // lane within the sample's group
@@ -451,9 +503,9 @@ struct EvL {
     }
     bwd_tail<N>(r, c.l, a2, d1, gin);
   }
-  template <class N>
+  template <class N, class GdFn>
   SDE4_DEV static void scalar_value_grad(const NetRef& r, Ctx& c, const float (&in)[N::IN], float& out,
-                                         float (&J)[N::IN]) {
+                                         float (&J)[N::IN], GdFn gd_of) {
     static_assert(N::OUT == 1 && ok<N>(), "scalar-output network with lane-divisible widths expected");
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
     float a1[B1], d1[B1], a2[B2];
@@ -471,6 +523,9 @@ struct EvL {
       a2[m] = w2[m] * dd;
     }
     out = all_reduce(o) + r.w[N::OFF_B2];
+    const float gd = gd_of(out);
+#pragma unroll
+    for (int m = 0; m < B2; ++m) a2[m] *= gd;
     bwd_tail<N>(r, c.l, a2, d1, J);
   }
 };

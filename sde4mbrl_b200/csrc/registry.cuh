@@ -19,6 +19,12 @@ struct ArchEntry {
   cudaError_t (*launch_rollout[5])(const sde4_model_desc&, const RolloutK&, int blocks, int threads, cudaStream_t);
   cudaError_t (*launch_cost[5])(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
                                 bool grad, bool constr, int blocks, int threads, cudaStream_t);
+  // training loss (value + input gradient + parameter-gradient streams); null = not compiled
+  cudaError_t (*launch_loss)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
+                             int blocks, int threads, cudaStream_t);
+  int net_dims[3][4];   // IN, H1, H2, OUT of density / net A / net B (0 = absent)
+  int net_off[3];       // offsets of the three networks in the packed block
+  int n_scaler, off_scaler;
 };
 
 std::vector<ArchEntry>& arch_table();
@@ -74,6 +80,19 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
 
 struct NoLaneSplit {};
 
+template <class M>
+cudaError_t launch_loss_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td, const CostK& a,
+                          int blocks, int threads, cudaStream_t s) {
+  const size_t sm = smem_bytes<M>(threads);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_cost<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256));
+    attr_set = true;
+  }
+  k_cost<M, true, false><<<blocks, threads, sm, s>>>(d, cd, td, a);
+  return cudaGetLastError();
+}
+
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
 
 template <class MLS>
@@ -84,7 +103,7 @@ void add_lane_variant(ArchEntry& e) {
   }
 }
 
-template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit>
+template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit, class MTRAIN = NoLaneSplit>
 ArchEntry make_entry(const char* name) {
   using A = typename M::A;
   ArchEntry e;
@@ -110,6 +129,19 @@ ArchEntry make_entry(const char* name) {
   e.launch_cost[0] = &launch_cost_t<M>;
   add_lane_variant<MLS>(e);
   add_lane_variant<MLS2>(e);
+  e.launch_loss = nullptr;
+  if constexpr (!std::is_same<MTRAIN, NoLaneSplit>::value) e.launch_loss = &launch_loss_t<MTRAIN>;
+  using D = typename A::DNet;
+  using NA = typename A::NetA;
+  using NB = typename A::NetB;
+  const int dims[3][4] = {{D::IN, D::H1, D::H2, D::OUT}, {NA::IN, NA::H1, NA::H2, NA::OUT}, {NB::IN, NB::H1, NB::H2, NB::OUT}};
+  for (int s = 0; s < 3; ++s)
+    for (int q = 0; q < 4; ++q) e.net_dims[s][q] = dims[s][q];
+  e.net_off[0] = A::OFF_DENSITY;
+  e.net_off[1] = A::OFF_NET_A;
+  e.net_off[2] = A::OFF_NET_B;
+  e.n_scaler = A::N_SCALER;
+  e.off_scaler = A::OFF_SCALER;
   return e;
 }
 
@@ -119,6 +151,10 @@ struct ArchRegistrar {
 
 #define SDE4_REGISTER(NAME, MODEL) static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL>(#NAME));
 // also instantiate the lane-split kernels (LANES adjacent lanes per sample) for latency-bound launches
+// one-thread-per-sample kernels + the training-loss kernel (parameter-gradient streams)
+#define SDE4_REGISTER_TRAIN(NAME, MODEL_T, ARCH)                                                     \
+  static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, ::sde4::NoLaneSplit, ::sde4::NoLaneSplit, \
+                                                              MODEL_T<ARCH, ::sde4::Ev1P>>(#NAME));
 #define SDE4_REGISTER_LS(NAME, MODEL_T, ARCH, LANES) \
   static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>>(#NAME));
 #define SDE4_REGISTER_LS2(NAME, MODEL_T, ARCH, LANES_A, LANES_B)                                          \

@@ -201,7 +201,45 @@ size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_
   return a;
 }
 
+struct LossOpts {
+  bool enabled = false;
+  float* grad_params = nullptr;
+};
+
+static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a, void* stream, const LossOpts& lo);
+
 int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* stream) {
+  return cost_grad_impl(model, a, stream, LossOpts());
+}
+
+static size_t loss_dump_floats(const ArchEntry& e, size_t K, size_t off[3]) {
+  size_t tot = 0;
+  for (int s = 0; s < 3; ++s) {
+    off[s] = tot;
+    const int* d = e.net_dims[s];
+    if (d[0] > 0) tot += (size_t)(d[0] + 2 * d[1] + 2 * d[2] + d[3] + (s == 0 ? e.n_scaler : 0)) * K;
+  }
+  return tot;
+}
+
+size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t H) {
+  if (!model) return 0;
+  const ArchEntry* e = find_arch(*model);
+  if (!e || !e->launch_loss) return 0;
+  size_t off[3];
+  const size_t dump = loss_dump_floats(*e, (size_t)B * N * H, off) * 4;
+  return cost_layout(*e, B, N, H, 0, true, false, SDE4_NOISE_THREEFRY, 1).total + ((dump + 255) & ~(size_t)255);
+}
+
+int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* a, float* grad_params, void* stream) {
+  if (!grad_params) return fail(SDE4_ERR_INVALID, "null grad_params");
+  LossOpts lo;
+  lo.enabled = true;
+  lo.grad_params = grad_params;
+  return cost_grad_impl(model, a, stream, lo);
+}
+
+static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a, void* stream, const LossOpts& lo) {
   if (!model || !a) return fail(SDE4_ERR_INVALID, "null argument");
   if (a->struct_size != (int)sizeof(sde4_cost_args)) return fail(SDE4_ERR_INVALID, "sde4_cost_args size mismatch (ABI)");
   const ArchEntry* e = find_arch(*model);
@@ -219,12 +257,19 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   if (cd.constr_mode != SDE4_CONSTR_WITHPROX && cd.n_slack != 0) return fail(SDE4_ERR_INVALID, "n_slack without WITHPROX constraints");
   const long long G = (long long)a->P * a->N;
   if (G > 0x7fffffffLL) return fail(SDE4_ERR_INVALID, "P*N exceeds 2^31-1");
-  const bool grad = a->grad != nullptr;
+  const bool grad = a->grad != nullptr || lo.enabled;
   const bool constr = cd.constr_mode != SDE4_CONSTR_NONE;
-  const int lanes = pick_lanes(*e, a->lanes, G);
+  if (lo.enabled) {
+    if (!e->launch_loss) return fail(SDE4_ERR_UNSUPPORTED, "no training-loss kernel compiled for %s", e->name);
+    if (constr || cd.kind != SDE4_COST_QUADRATIC || a->xtraj) return fail(SDE4_ERR_INVALID, "training loss: QUADRATIC data cost, no constraints, no xtraj");
+  }
+  const int lanes = lo.enabled ? 1 : pick_lanes(*e, a->lanes, G);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
-  if (a->workspace_bytes < L.total) return fail(SDE4_ERR_WORKSPACE, "workspace too small");
+  size_t dump_off[3] = {0, 0, 0};
+  const size_t Kcols = (size_t)G * a->H;
+  const size_t dump_bytes = lo.enabled ? loss_dump_floats(*e, Kcols, dump_off) * 4 : 0;
+  if (a->workspace_bytes < L.total + dump_bytes) return fail(SDE4_ERR_WORKSPACE, "workspace too small");
   if (((uintptr_t)a->workspace & 255) != 0) return fail(SDE4_ERR_INVALID, "workspace must be 256-byte aligned");
   char* ws = (char*)a->workspace;
   CostK k;
@@ -270,13 +315,24 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   k.data_mod = a->data_mod > 0 ? a->data_mod : a->P;
+  k.sum_mode = lo.enabled ? 1 : 0;
+  k.rng_chain = lo.enabled ? 1 : 0;
+  k.pd_stride = Kcols;
+  float* dump_base = (float*)(ws + L.total);
+  for (int s2 = 0; s2 < 3; ++s2) k.pd_net[s2] = lo.enabled ? dump_base + dump_off[s2] : nullptr;
   k.has_terminal = (a->terminal && a->terminal->kind != SDE4_COST_NONE) ? 1 : 0;
   const sde4_cost_desc td = k.has_terminal ? *a->terminal : empty_cost();
   const long long nthr = G * lanes;
   int threads = pick_threads(a->block_threads, nthr);
   const int blocks = (int)((nthr + threads - 1) / threads);
   cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t err = e->launch_cost[ilog2(lanes)](*model, cd, td, k, grad, constr, blocks, threads, s);
+  cudaError_t err;
+  if (lo.enabled) {
+    err = cudaMemsetAsync(dump_base, 0, dump_bytes, s);  // rows of networks that are not evaluated (ODE mode) stay 0
+    if (err == cudaSuccess) err = e->launch_loss(*model, cd, td, k, blocks, threads, s);
+  } else {
+    err = e->launch_cost[ilog2(lanes)](*model, cd, td, k, grad, constr, blocks, threads, s);
+  }
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "cost launch (%s): %s", e->name, cudaGetErrorString(err));
   ReduceK r;
   r.gpart = k.gpart;
@@ -303,6 +359,58 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   k_reduce<<<(int)((items + rthreads - 1) / rthreads), rthreads, 0, s>>>(r);
   err = cudaGetLastError();
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(err));
+  if (lo.enabled) {
+    // K5: parameter gradients from the streams; scale = 1/(B*N) (mean over minibatch and particles)
+    err = cudaMemsetAsync(lo.grad_params, 0, (size_t)e->param_total * 4, s);
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "memset: %s", cudaGetErrorString(err));
+    WgradK wk;
+    wk.n_tasks = 0;
+    wk.K = Kcols;
+    wk.scale = 1.0f / (float)((double)a->P * k.n_tot);
+    int row0 = 0;
+    auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo) {
+      WgradTask& t = wk.task[wk.n_tasks++];
+      t.A = A;
+      t.B = B;
+      t.out = out;
+      t.n_a = n_a;
+      t.n_b = n_b;
+      t.ldo = ldo;
+      t.row0 = row0;
+      row0 += n_a;
+    };
+    auto up4l = [](int n) { return (n + 3) & ~3; };
+    for (int s2 = 0; s2 < 3; ++s2) {
+      const int* dm = e->net_dims[s2];
+      if (dm[0] == 0) continue;
+      const int IN = dm[0], H1 = dm[1], H2 = dm[2], OUT = dm[3];
+      const float* base = k.pd_net[s2];
+      const float* r_in = base;
+      const float* r_h1 = base + (size_t)IN * Kcols;
+      const float* r_h2 = base + (size_t)(IN + H1) * Kcols;
+      const float* r_c1 = base + (size_t)(IN + H1 + H2) * Kcols;
+      const float* r_g2 = base + (size_t)(IN + 2 * H1 + H2) * Kcols;
+      const float* r_go = base + (size_t)(IN + 2 * H1 + 2 * H2) * Kcols;
+      float* gp = lo.grad_params + e->net_off[s2];
+      const int h1p = up4l(H1), h2p = up4l(H2);
+      float* w0 = gp;
+      float* b0 = w0 + IN * h1p;
+      float* w1 = b0 + h1p;
+      float* b1 = w1 + H1 * h2p;
+      float* w2 = b1 + h2p;  // transposed: [OUT][h2p]
+      float* b2 = w2 + OUT * h2p;
+      add(r_in, IN, r_c1, H1, w0, h1p);
+      add(nullptr, 1, r_c1, H1, b0, h1p);
+      add(r_h1, H1, r_g2, H2, w1, h2p);
+      add(nullptr, 1, r_g2, H2, b1, h2p);
+      add(r_go, OUT, r_h2, H2, w2, h2p);
+      add(nullptr, 1, r_go, OUT, b2, 4);
+      if (s2 == 0 && e->n_scaler) add(nullptr, 1, r_go + (size_t)OUT * Kcols, e->n_scaler, lo.grad_params + e->off_scaler, e->n_scaler);
+    }
+    k_wgrad<<<row0, 256, 0, s>>>(wk);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(err));
+  }
   return SDE4_OK;
 }
 

@@ -220,3 +220,49 @@ class Engine:
         if squeeze and grad is not None:
             grad = grad.squeeze(0)
         return cost, grad, xtraj
+
+    # ---- K2 (training variant) + K3 + K5 -----------------------------------
+    def loss_grad(self, nn_params, ymeas, u, dt, data_cost, key, N=1, noise=None, noise_mode=None, block_threads=0):
+        """Data term of the training loss and its gradient w.r.t. the PACKED parameter block.
+        ymeas[B, H+1, n_x] (rows = solver steps), u[B, H, n_u], key[B, 2] = split(rng, B).
+        Returns (loss[B], grad_packed[param_total]); d(mean_b loss)/d params = grad_packed."""
+        pk = self.packed(nn_params)
+        ymeas = as_f32(ymeas).contiguous()
+        B = ymeas.shape[0]
+        dt_t = self.dt_tensor(dt)
+        H = dt_t.numel()
+        u = as_f32(u).contiguous()
+        assert tuple(ymeas.shape) == (B, H + 1, self.n_x) and tuple(u.shape) == (B, H, self.n_u)
+        y0 = ymeas[:, 0, :].contiguous()
+        lib = L.load()
+        ws_bytes = lib.sde4_loss_workspace_bytes(C.byref(self.desc), B, N, H)
+        if ws_bytes == 0:
+            raise Sde4Error("no training-loss kernel compiled for this architecture")
+        ws = self.workspace(ws_bytes)
+        loss = torch.empty(B, dtype=torch.float32, device=y0.device)
+        gpar = torch.empty(self.param_total, dtype=torch.float32, device=y0.device)
+        if noise_mode is None:
+            noise_mode = L.NOISE_GIVEN if noise is not None else (L.NOISE_THREEFRY if self.noisy else L.NOISE_NONE)
+        a = L.CostArgs()
+        a.struct_size = C.sizeof(L.CostArgs)
+        a.P, a.N, a.H = B, N, H
+        a.params, a.y0, a.opt = _ptr(pk.dev), _ptr(y0), _ptr(u)
+        a.opt_stride_p, a.opt_stride_t, a.opt_stride_j = u.stride()
+        a.dt, a.xref, a.xref_stride_p = _ptr(dt_t), _ptr(ymeas), ymeas.stride(0)
+        if noise_mode == L.NOISE_THREEFRY:
+            keyt = as_key(key).reshape(-1, 2)
+            if keyt.shape[0] != B:
+                raise Sde4Error("need one key per minibatch element (split(rng, B))")
+            a.key, a.key_stride_p = _ptr(keyt), 2
+        if noise_mode == L.NOISE_GIVEN:
+            noise = as_f32(noise).contiguous()
+            if tuple(noise.shape) != (H, self.n_x, B * N):
+                raise Sde4Error("noise must be [H, n_x, B*N] (sample-minor)")
+            a.noise = _ptr(noise)
+        a.rng_mode, a.noise_mode = self.rng_mode, noise_mode
+        a.stage = C.pointer(data_cost)
+        a.cost = _ptr(loss)
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        a.block_threads = block_threads
+        L.check(lib.sde4_loss_grad(C.byref(self.desc), C.byref(a), _ptr(gpar), _stream()))
+        return loss, gpar

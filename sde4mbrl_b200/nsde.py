@@ -335,3 +335,179 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
 def engine_device():
     from .engine import _dev
     return _dev()
+
+
+def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, verbose=True, **extra_args_sde_constr):
+    """``sde4mbrl/nsde.py:1032-1338``: returns ``(nn_params, loss_fn, nonneg_projection, test_fn)``.
+
+    ``loss_fn(nn_params, y, u, rng) -> (total_loss, dict)`` evaluates the data term on the GPU and the
+    weight penalty on the host.  JAX users differentiate ``loss_fn`` with ``jax.grad``; here the
+    parameter gradient comes out of the same fused launch: ``loss_fn.value_and_grad(nn_params, y, u, rng)
+    -> (total_loss, dict, grads)`` with ``grads`` a tree shaped like ``nn_params`` (model scalars and
+    un-differentiated leaves get zeros).  Like the reference this MUTATES ``model_params`` /
+    ``loss_params`` (nsde.py:1064-1134).
+
+    Not covered (each raises): ``density_loss`` terms with a non-zero penalty, ``num_sample2consider``
+    below the horizon, ``u_sampling_strategy='random'`` (they need more of jax.random)."""
+    _check_constr(sde_constr)
+    vprint = print if verbose else (lambda *a, **k: None)
+    params_model = model_params
+    num_sample = loss_params.get("num_particles", params_model.get("num_particles", 1))
+    params_model["num_particles"] = num_sample
+    step_size = loss_params.get("stepsize", params_model["stepsize"])
+    params_model["stepsize"] = step_size
+    data_stepsize = loss_params.get("data_stepsize", step_size)
+    if abs(step_size - data_stepsize) <= 1e-6:
+        num_steps2data = 1
+    else:
+        num_steps2data = int((step_size / data_stepsize) + 0.5)  # nsde.py:1078
+    horizon = loss_params.get("horizon", params_model.get("horizon", 1))
+    data_horizon = horizon * num_steps2data
+    params_model["horizon"] = horizon
+    params_model["num_steps2data"] = num_steps2data
+    loss_params["data_horizon"] = data_horizon
+    vprint("Using [ N = {} ] particles for the loss".format(num_sample))
+    vprint("Using [ T = {} ] horizon for the loss".format(horizon))
+    vprint("Using [ dt = {} ] stepsize for the loss".format(step_size))
+    vprint("Using [ num_steps2data = {} ] steps between data points".format(num_steps2data))
+    for k in ("num_sample2consider", "obs_weights", "density_on_partial", "u_sampling_strategy"):
+        if k in loss_params:
+            params_model[k] = loss_params[k]
+    for k in ("num_short_dt", "short_step_dt", "long_step_dt"):
+        params_model.pop(k, None)
+    if "diffusion_density_nn" not in params_model or "density_nn" not in params_model["diffusion_density_nn"]:
+        loss_params.pop("density_loss", None)
+    if "density_loss" in loss_params and (loss_params.get("pen_grad_density", 0) > 0 or
+                                          loss_params.get("pen_density_scvex", 0) > 0 or
+                                          loss_params.get("pen_mu_coeff", 0) > 0):
+        raise Sde4Error("density_loss terms (pen_grad_density / pen_density_scvex / pen_mu_coeff > 0) have no compiled kernel yet")
+    if params_model.get("num_sample2consider", horizon) < horizon:
+        raise Sde4Error("num_sample2consider < horizon (jax.random.choice subsampling) has no compiled kernel yet")
+    strategy = params_model.get("u_sampling_strategy", "first")
+    if strategy not in ("first", "mean", "median"):
+        raise Sde4Error("u_sampling_strategy '%s' has no compiled kernel" % strategy)
+
+    model = sde_constr(params_model, **extra_args_sde_constr)
+    nn_params = model.init_params(loss_params.get("seed", 0))
+    engine = Engine(model, _random.rng_mode())
+    time_steps = compute_timesteps(params_model)
+    n_feat = 5 if model.module_name == "cart_pole_sde" else model.n_x  # state_transform_for_loss
+    ow = np.broadcast_to(np.asarray(params_model.get("obs_weights", 1.0), np.float64), (n_feat,))
+    data_cost = _costs.QuadraticCost(list(1.0 / ow ** 2), [0.0] * model.n_u, [0.0] * model.n_u,
+                                     feat="cartpole" if model.module_name == "cart_pole_sde" else "identity")
+    pen_w = loss_params.get("pen_weights", 0)
+    default_w = loss_params.get("default_weights", 1.0)
+    special = loss_params.get("special_parameters_pen", {})
+    default_val = loss_params.get("default_parameters_val", 0.0)
+
+    def _penalty(_nn_params, want_grad):
+        """pen_weights * sum_leaves coeff * ||p - nominal||^2 with the key-substring matching of
+        get_penalty_parameters (sde4mbrl/utils.py:119-146); nominal = default_parameters_val."""
+        tot, grads = 0.0, {}
+        for mod, leaves in _nn_params.items():
+            for name, arr in leaves.items():
+                coeff = default_w
+                for key, val in special.items():
+                    if key in mod or key in name:
+                        coeff = val
+                a = np.asarray(arr, np.float64)
+                tot += float(np.sum((a - default_val) ** 2) * coeff)
+                if want_grad:
+                    grads.setdefault(mod, {})[name] = (2.0 * coeff * pen_w * (a - default_val)).astype(np.float32)
+        return tot, grads
+
+    def _prepare(y, u):
+        y, u = as_f32(y), as_f32(u)
+        assert y.shape[1] == u.shape[1] + 1, "Trajectory horizon must match"
+        assert horizon * num_steps2data == u.shape[1], "Trajectory horizon and num_steps2data must match the number of control inputs"
+        B = y.shape[0]
+        y_values = y[:, ::num_steps2data]
+        uu = u.reshape(B, horizon, num_steps2data, model.n_u)
+        if strategy == "first":
+            u_values = uu[:, :, 0]
+        elif strategy == "mean":
+            u_values = uu.mean(dim=2)
+        else:
+            u_values = uu.median(dim=2).values
+        return y_values.contiguous(), u_values.contiguous()
+
+    def value_and_grad(_nn_params, y, u, rng, extra_args=None, want_grad=True):
+        if extra_args is not None:
+            raise Sde4Error("extra_args must be None")
+        key = as_key(rng)
+        assert key.dim() == 1, "THe rng key is splitted inside the loss function computation"
+        y_values, u_values = _prepare(y, u)
+        B = y_values.shape[0]
+        keys = _random.split(key, B)  # nsde.py:1196
+        engine.rng_mode = _random.rng_mode()
+        loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample)
+        loss_data = float(loss_b.mean())
+        total = 0.0
+        if loss_params.get("pen_data", 0) > 0:
+            total += loss_data * loss_params["pen_data"]
+        w_loss, wgrads = _penalty(_nn_params, want_grad) if pen_w > 0 else (0.0, {})
+        if pen_w > 0:
+            total += pen_w * w_loss
+        info = {"totalLoss": total, "gradDensity": 0.0, "lossMuCoeff": 0.0, "densitySCVEX": 0.0, "weights": w_loss,
+                "muCoeff": 0.0, "dataLoss": loss_data}
+        if not want_grad:
+            return total, info, None
+        gtree = model.unpack_grads(gpacked.cpu().numpy(), engine.desc)
+        pd = float(loss_params.get("pen_data", 0)) if loss_params.get("pen_data", 0) > 0 else 0.0
+        grads = {}
+        for mod, leaves in _nn_params.items():
+            for name, arr in leaves.items():
+                g = np.zeros_like(np.asarray(arr, np.float32))
+                if mod in gtree and name in gtree[mod]:
+                    g = g + pd * gtree[mod][name]
+                if mod in wgrads and name in wgrads[mod]:
+                    g = g + wgrads[mod][name]
+                grads.setdefault(mod, {})[name] = g
+        return total, info, grads
+
+    def loss_fn(_nn_params, y, u, rng, extra_args=None):
+        total, info, _ = value_and_grad(_nn_params, y, u, rng, extra_args, want_grad=False)
+        return total, info
+
+    loss_fn.value_and_grad = value_and_grad
+    loss_fn.engine = engine
+
+    nonneg = set(params_model.get("noneg_params", []))
+    nonzero = loss_params.get("nonneg_nonzero", {})
+
+    def nonneg_projection(_params):
+        """nsde.py:1181-1182: clamp the named parameters from below."""
+        out = {}
+        for mod, leaves in _params.items():
+            out[mod] = {}
+            for name, arr in leaves.items():
+                lo = None
+                if any(k in mod or k in name for k in nonneg):
+                    lo = 0.0
+                    for k, v in nonzero.items():
+                        if k in mod or k in name:
+                            lo = v
+                out[mod][name] = np.maximum(arr, lo) if lo is not None else arr
+        return out
+
+    _, multi_sampling_sde = create_sampling_fn(params_model, sde_constr, loss_params.get("seed", 0),
+                                               loss_params["num_particles_test"], **extra_args_sde_constr)
+
+    def test_fn(_nn_params, y, u, rng, extra_args=None):
+        """nsde.py:1268-1335: error of the particle-mean prediction and mean particle spread."""
+        key = as_key(rng)
+        y_values, u_values = _prepare(y, u)
+        B = y_values.shape[0]
+        keys = _random.split(key, B)
+        _, yevol, _ = multi_sampling_sde(_nn_params, y_values[:, 0], u_values, keys)  # [B, N, H+1, n_y]
+
+        def tf_loss(z):
+            if model.module_name == "cart_pole_sde":
+                return torch.stack([z[..., 0], z[..., 1], torch.sin(z[..., 2]), torch.cos(z[..., 2]), z[..., 3]], dim=-1)
+            return z
+        w = as_f32(np.broadcast_to(np.asarray(loss_params.get("obs_weights", 1.0), np.float32), (n_feat,)))
+        err = (((tf_loss(y_values) - tf_loss(yevol.mean(dim=1))) / w) ** 2).sum(dim=(-1, -2)).mean()
+        std_val = yevol.std(dim=1, unbiased=False).sum(dim=(-1, -2)).mean()
+        return float(err), {"TestErrorData": float(err), "TestStdData": float(std_val)}
+
+    return nn_params, loss_fn, nonneg_projection, test_fn

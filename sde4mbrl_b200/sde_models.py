@@ -169,6 +169,34 @@ class ControlledSDE:
     def _pack_scalars(self, out, base, top):
         pass
 
+    def unpack_grads(self, gpacked, desc=None):
+        """Inverse of ``pack`` for a gradient block: flat float32 -> haiku-style tree of numpy arrays
+        (network weights / biases and the scaler; model scalars are not differentiated)."""
+        desc = self.describe() if desc is None else desc
+        off, total = self.layout(desc)
+        g = np.asarray(gpacked, np.float32)
+        tree = {}
+        if desc.n_scaler:
+            tree.setdefault(self.module_name, {})["scaler"] = g[off[1]:off[1] + desc.n_scaler].copy()
+        for slot, prefix, nd in self._net_slots(desc):
+            if nd.n_in == 0:
+                continue
+            o = off[slot]
+            dims = [nd.n_in, nd.h1, nd.h2, nd.n_out]
+            for k in range(3):
+                if k < 2:
+                    outp = _up4(dims[k + 1])
+                    w = g[o:o + dims[k] * outp].reshape(dims[k], outp)[:, :dims[k + 1]].copy()
+                    o += dims[k] * outp
+                else:
+                    inp = _up4(dims[k])
+                    w = g[o:o + dims[k + 1] * inp].reshape(dims[k + 1], inp)[:, :dims[k]].T.copy()
+                    o += dims[k + 1] * inp
+                b = g[o:o + dims[k + 1]].copy()
+                o += _up4(dims[k + 1])
+                tree["%s/linear_%d" % (prefix, k)] = {"w": w, "b": b}
+        return tree
+
     def _net_slots(self, desc):
         m = self.module_name
         return [(2, "%s/~construct_diffusion_density_nn/density/~" % m, desc.density),

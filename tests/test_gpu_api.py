@@ -131,3 +131,32 @@ def test_rejects_python_cost_callables(cuda):
     with pytest.raises(Sde4Error):
         multi_cost(nn, hp.start_state("hexa", np.random.default_rng(0)), construct_opt(), R.PRNGKey(0),
                    lambda x, u, e: 0.0, extra_cost_args=np.zeros((21, 13), np.float32))
+
+
+def test_simulator_adapter(cuda):
+    """cartpole_sde_gym._my_pred_fn semantics (mean / population std over particles of the next state)
+    and the batched predict() over many start states, on the reference's shipped cartpole weights."""
+    import os
+    from sde4mbrl_b200 import io, random as R
+    from sde4mbrl_b200.simulator import SDESimulator
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nn, nominal = io.load_npz_fixture(os.path.join(gold, "ref_weights_cartpole_bb_learned_si.npz"))
+    sim = SDESimulator(sde_models.CartPoleSDE, nominal, nn, num_particles=10, tau=0.02, horizon=1)
+    x0, u0 = np.array([0.0, 0.0, np.pi, 0.0], np.float32), np.array([0.3], np.float32)
+    mean, std = sim.pred_fn(x0, u0, R.PRNGKey(10))
+    pm = dict(nominal, horizon=1, num_particles=10, stepsize=0.02)
+    om = orc.make_model("cart_pole_sde", pm, nn)
+    want, _ = orc.sample_rollouts(om, x0, u0[None], tf.PRNGKey(10), 10)
+    np.testing.assert_allclose(mean.cpu().numpy(), want[:, -1].mean(0).numpy(), rtol=2e-5, atol=1e-6)
+    np.testing.assert_allclose(std.cpu().numpy(), want[:, -1].std(0, unbiased=False).numpy(), rtol=2e-3, atol=1e-6)
+    # batched: 1000 start states, key per state derived on the device from one key
+    rng = np.random.default_rng(0)
+    P = 1000
+    obs = rng.uniform(-1, 1, (P, 4)).astype(np.float32) * np.array([2, 3, np.pi, 6], np.float32)
+    act = rng.uniform(-1, 1, (P, 1)).astype(np.float32)
+    nxt = sim.predict(obs, act, R.PRNGKey(3))
+    assert tuple(nxt.shape) == (P, 4)
+    keys = tf.split(tf.PRNGKey(3), P)
+    for p in (0, 17, 999):
+        w, _ = orc.sample_rollouts(om, obs[p], act[p][None], keys[p], 10)
+        np.testing.assert_allclose(nxt[p].cpu().numpy(), w[:, -1].mean(0).numpy(), rtol=2e-5, atol=2e-6)

@@ -1,0 +1,63 @@
+"""Training-loss path (BASELINE configs[4] second half): data term of
+create_model_loss_fn(...).loss_fn and its gradient w.r.t. the network parameters (K2 training
+variant + K5) vs the oracle's float64 autograd."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as hp
+from oracle import nsde_oracle as orc
+from oracle import threefry as tf
+from sde4mbrl_b200 import configs, sde_models
+
+pytestmark = pytest.mark.gpu
+
+
+def _tree64(nn):
+    return {m: {k: torch.tensor(np.asarray(v), dtype=torch.float64, requires_grad=True) for k, v in d.items()}
+            for m, d in nn.items()}
+
+
+@pytest.mark.parametrize("kind,cls,oname,B,N,H", [("cartpole", sde_models.CartPoleSDE, "cart_pole_sde", 12, 2, 10),
+                                                    ("cartpole_bb", sde_models.CartPoleSDE, "cart_pole_sde", 5, 1, 30),
+                                                    ("msd", sde_models.MassSpringDamper, "mass_spring_damper", 7, 3, 20)])
+def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H):
+    from sde4mbrl_b200 import nsde, random as R
+    mk = hp.KINDS[kind][0]
+    pm = mk(horizon=1, num_particles=1)
+    ow = [9, 5, 1, 1.0, 10] if oname == "cart_pole_sde" else [0.5, 2.0]
+    lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 4,
+          "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 1e-3, "default_weights": 1.0,
+          "special_parameters_pen": {"scaler": 0, "density": 0}}
+    _, loss_fn, nonneg, test_fn = nsde.create_model_loss_fn(pm, lp, sde_constr=cls, verbose=False)
+    nn = configs.random_params(cls(pm), seed=4)
+    rng = np.random.default_rng(0)
+    nx, nu = pm["n_x"], pm["n_u"]
+    y = (rng.normal(0, 0.5, (B, H + 1, nx)) + (np.array([0, 0, 3.0, 0]) if nx == 4 else 0)).astype(np.float32)
+    u = rng.uniform(-1, 1, (B, H, nu)).astype(np.float32)
+    total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(3))
+    # oracle: same noise chain, float64 autograd w.r.t. the parameter tree
+    tree = _tree64(nn)
+    om = orc.make_model(oname, pm, tree, torch.float64)
+    dw = torch.tensor(orc.loss_noise(tf.PRNGKey(3), B, N, H, nx), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, oname, torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw, ow)
+    coeffs = {m: {k: (0.0 if ("scaler" in m or "scaler" in k or "density" in m) else 1.0) for k in d} for m, d in tree.items()}
+    nominal = {m: {k: torch.zeros_like(v) for k, v in d.items()} for m, d in tree.items()}
+    Lw = orc.weight_penalty(tree, nominal, coeffs)
+    Lt = Ld + 1e-3 * Lw
+    Lt.backward()
+    assert abs(info["dataLoss"] - float(Ld)) < 3e-5 * abs(float(Ld))
+    assert abs(total - float(Lt)) < 3e-5 * abs(float(Lt))
+    gmax = max(float(v.grad.abs().max()) for d in tree.values() for v in d.values())
+    for m, d in tree.items():
+        for k, v in d.items():
+            got, want = grads[m][k], v.grad.numpy()
+            assert got.shape == want.shape
+            # per-leaf: 2e-3 of the leaf's own max, plus a floor at 1e-5 of the global max (the scaler's
+            # gradient is ~1e-9 of the others: exp(scaler)*1e-7, nsde.py:413)
+            assert np.max(np.abs(got - want)) <= 2e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (m, k)
+    # loss_fn without gradient gives the same value; test_fn runs and returns the reference's keys
+    t2, _ = loss_fn(nn, y, u, R.PRNGKey(3))
+    assert abs(t2 - total) < 1e-6 * abs(total)
+    err, td = test_fn(nn, y, u, R.PRNGKey(5))
+    assert set(td) == {"TestErrorData", "TestStdData"} and np.isfinite(err)
