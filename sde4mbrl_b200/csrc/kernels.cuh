@@ -86,29 +86,13 @@ struct Tctx {
 };
 
 // Prologue shared by K1/K2: stage the parameter image with one bulk async copy, derive the
-// state-independent constants, build the bank-spread w1 copies (lane-split kernels) and set up the
-// per-thread context.  Returns the thread's global sample slot (may be >= G: inactive).
+// state-independent constants and set up the per-thread context.  Returns the thread's global sample slot (may be >= G: inactive).
 template <class M>
 SDE4_DEV int kernel_prologue(float* W, const float* params, uint64_t* mbar, Tctx<M>& tc) {
   using A = typename M::A;
   constexpr int L = M::Ev::L;
   stage_params_bulk(W, params, A::PARAM_TOTAL * sizeof(float), mbar);
   Diffusion<M>::derive(W);
-  if constexpr (L > 1) {
-    auto pad_copy = [&](auto net_tag, int off_net, int off_pad) {
-      using N = decltype(net_tag);
-      if constexpr (N::PRESENT) {
-        constexpr int B1 = N::H1 / L;
-        for (int e = threadIdx.x; e < N::H1 * N::H2P; e += blockDim.x) {
-          const int row = e / N::H2P, col = e - row * N::H2P;
-          W[off_pad + row * N::H2P + (row / B1) * 4 + col] = W[off_net + N::OFF_W1 + e];
-        }
-      }
-    };
-    pad_copy(typename A::DNet{}, A::OFF_DENSITY, A::off_w1p(0, L));
-    pad_copy(typename A::NetA{}, A::OFF_NET_A, A::off_w1p(1, L));
-    pad_copy(typename A::NetB{}, A::OFF_NET_B, A::off_w1p(2, L));
-  }
   __syncthreads();
   const int gt = blockIdx.x * blockDim.x + threadIdx.x;
   if constexpr (L == 1) {

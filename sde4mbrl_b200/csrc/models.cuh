@@ -45,7 +45,7 @@ struct Arch {
   // lane-split kernels keep a bank-spread copy of every w1 (see nets.cuh, EvL) after the image
   template <class N>
   static constexpr int w1p_floats(int L) {
-    return (L > 1 && N::PRESENT) ? up4(N::H1 * N::H2P + 4 * L) : 0;
+    return L < 0 ? 1 : 0;  // (the row-split variant needed a bank-spread copy of w1; the output-split one does not)
   }
   static constexpr int off_w1p(int slot, int L) {
     return SMEM_FLOATS + (slot > 0 ? w1p_floats<DNet>(L) : 0) + (slot > 1 ? w1p_floats<NetA>(L) : 0);

@@ -333,9 +333,8 @@ using Ev1P = Ev1T<true>;
 // ---- lane-split evaluator ------------------------------------------------------------------------
 // Lane l of a sample owns the hidden units [l*B, (l+1)*B) of each hidden layer (B = H/L).
 //   layer 1: every lane has the (replicated) inputs and computes its own block of outputs;
-//   layer 2: ROW split -- the lane multiplies its own h1 block with the matching rows of w1 and
-//            obtains partial sums of ALL outputs; a recursive-halving reduce-scatter over the L
-//            lanes (SHFL.BFLY) leaves each lane with the finished values of its own output block;
+//   layer 2: the L lanes all-gather h1 with log2(L) rounds of SHFL.BFLY (XOR order, no selects) and
+//            every lane forms its own block of outputs from its column chunk of w1;
 //   layer 3: partial dot products over the own block + butterfly all-reduce.
 // The backward sweep mirrors this with the transposed products.
 constexpr int MAXB = 8;  // largest per-lane block (MAXW / smallest L >= 4)
@@ -389,23 +388,39 @@ struct EvL {
       for (int m = 0; m < B1; ++m) a1[m] = fmaf(in[k], w0[k * N::H1P + m], a1[m]);
     }
   }
-  // layer 2: own rows -> partial sums of all outputs -> reduce-scatter -> + bias: a2own[B2]
+  // all-gather over the sample's L lanes: local block q of `all` = own block of lane (l ^ q).
+  // XOR order: no selects are needed, the consumer indexes the weights with (l ^ q) instead.
+  template <int B>
+  SDE4_DEV static void all_gather(const float (&own)[B], float (&all)[B * L]) {
+#pragma unroll
+    for (int m = 0; m < B; ++m) all[m] = own[m];
+#pragma unroll
+    for (int mask = 1, n = B; mask < L; mask <<= 1, n <<= 1) {
+#pragma unroll
+      for (int q = 0; q < n; ++q) all[n + q] = __shfl_xor_sync(0xffffffffu, all[q], mask);
+    }
+  }
+  // layer 2, OUTPUT split: gather all of h1 (SHFL.BFLY), every lane forms its own block of outputs
+  //   a2own[m] = b1[l*B2+m] + sum_i h1[i] * w1[i][l*B2+m]
+  // (lanes read distinct 4-bank column chunks of distinct rows: conflict free without padding)
   template <class N>
   SDE4_DEV static void layer2(const NetRef& r, int l, const float (&h1)[N::H1 / L], float (&a2)[N::H2 / L]) {
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
-    const float* w1 = r.w1p + l * (B1 * N::H2P + 4);
-    float acc[N::H2];
-#pragma unroll
-    for (int j = 0; j < N::H2; ++j) acc[j] = 0.0f;
-#pragma unroll
-    for (int m = 0; m < B1; ++m) {
-#pragma unroll
-      for (int j = 0; j < N::H2; ++j) acc[j] = fmaf(h1[m], w1[m * N::H2P + j], acc[j]);
-    }
-    reduce_scatter<N::H2>(acc, l);
+    float hall[N::H1];
+    all_gather<B1>(h1, hall);
+    const float* w1 = r.w + N::OFF_W1 + l * B2;
     const float* b1 = r.w + N::OFF_B1 + l * B2;
 #pragma unroll
-    for (int m = 0; m < B2; ++m) a2[m] = acc[m] + b1[m];
+    for (int m = 0; m < B2; ++m) a2[m] = b1[m];
+#pragma unroll
+    for (int q = 0; q < L; ++q) {
+      const float* wq = w1 + ((l ^ q) * B1) * N::H2P;
+#pragma unroll
+      for (int mm = 0; mm < B1; ++mm) {
+#pragma unroll
+        for (int m = 0; m < B2; ++m) a2[m] = fmaf(hall[q * B1 + mm], wq[mm * N::H2P + m], a2[m]);
+      }
+    }
   }
   // layer 3: out[o] = b2[o] + sum_j h2[j]*w2T[o][j]
   template <class N>
@@ -421,27 +436,35 @@ struct EvL {
     }
   }
   // backward tail: g2own (cotangent of own a2 block) -> gin (replicated)
+  //   c1own[m] = d1[m] * sum_j w1[l*B1+m][j] * g2[j]   (g2 gathered over the lanes)
   template <class N>
   SDE4_DEV static void bwd_tail(const NetRef& r, int l, const float (&g2)[N::H2 / L], const float (&d1)[N::H1 / L],
                                 float (&gin)[N::IN]) {
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
-    // partial c1[i] over the own column block of w1, for all rows i
-    float c1[N::H1];
-    const float* w1 = r.w + N::OFF_W1 + l * B2;
+    float gall[N::H2];
+    all_gather<B2>(g2, gall);
+    float c1[B1];
+    const float* w1 = r.w + N::OFF_W1 + (l * B1) * N::H2P;
 #pragma unroll
-    for (int i = 0; i < N::H1; ++i) {
-      float a = 0.0f;
+    for (int m = 0; m < B1; ++m) {
+      float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-      for (int m = 0; m < B2; ++m) a = fmaf(w1[i * N::H2P + m], g2[m], a);
-      c1[i] = a;
+      for (int q = 0; q < L; ++q) {
+        const float* wq = w1 + m * N::H2P + (l ^ q) * B2;
+#pragma unroll
+        for (int mm = 0; mm < B2; ++mm) {
+          if ((q & 1) == 0) a0 = fmaf(wq[mm], gall[q * B2 + mm], a0);
+          else a1 = fmaf(wq[mm], gall[q * B2 + mm], a1);
+        }
+      }
+      c1[m] = (a0 + a1) * d1[m];
     }
-    reduce_scatter<N::H1>(c1, l);
     const float* w0 = r.w + N::OFF_W0 + l * B1;
 #pragma unroll
     for (int k = 0; k < N::IN; ++k) {
       float a = 0.0f;
 #pragma unroll
-      for (int m = 0; m < B1; ++m) a = fmaf(w0[k * N::H1P + m], c1[m] * d1[m], a);
+      for (int m = 0; m < B1; ++m) a = fmaf(w0[k * N::H1P + m], c1[m], a);
       gin[k] = all_reduce(a);
     }
   }
