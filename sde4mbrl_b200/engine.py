@@ -12,22 +12,31 @@ from . import _lib as L
 from ._lib import Sde4Error
 
 
+_HAVE_CUDA = None
+
+
 def _dev():
-    if not torch.cuda.is_available():
+    global _HAVE_CUDA
+    if _HAVE_CUDA is None:
+        _HAVE_CUDA = torch.cuda.is_available()
+    if not _HAVE_CUDA:
         raise Sde4Error("sde4mbrl_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     return torch.device("cuda", torch.cuda.current_device())
 
 
 def as_f32(x, device=None):
     """numpy / list / torch -> float32 CUDA tensor (no copy if already there)."""
-    device = _dev() if device is None else device
     if isinstance(x, torch.Tensor):
-        return x.to(device=device, dtype=torch.float32)
-    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=device)
+        if x.is_cuda and x.dtype == torch.float32 and device is None:
+            return x
+        return x.to(device=_dev() if device is None else device, dtype=torch.float32)
+    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=_dev() if device is None else device)
 
 
 def as_key(k, device=None):
     """jax-layout key(s) uint32[...,2] -> int32 CUDA tensor holding the same bits."""
+    if isinstance(k, torch.Tensor) and k.is_cuda and k.dtype == torch.int32 and device is None and k.is_contiguous():
+        return k
     device = _dev() if device is None else device
     if isinstance(k, torch.Tensor):
         if k.dtype == torch.uint32:
@@ -74,6 +83,8 @@ class Engine:
         self._packed = None
         self._ws = None
         self._dt_cache = {}
+        self._dt_last = None
+        self._ws_bytes = {}
 
     # ---- parameters -----------------------------------------------------
     def packed(self, nn_params):
@@ -84,11 +95,17 @@ class Engine:
         return self._packed
 
     def dt_tensor(self, dt):
-        key = tuple(float(v) for v in np.asarray(dt).ravel())
+        hit = self._dt_last
+        if hit is not None and hit[0] is dt:  # same READ-ONLY time-step array as last call
+            return hit[1]
+        arr = np.ascontiguousarray(np.asarray(dt, np.float32))
+        key = arr.tobytes()
         t = self._dt_cache.get(key)
         if t is None:
-            t = torch.as_tensor(np.asarray(dt, np.float32), device=_dev())
+            t = torch.as_tensor(arr, device=_dev())
             self._dt_cache[key] = t
+        if isinstance(dt, np.ndarray) and not dt.flags.writeable:
+            self._dt_last = (dt, t)
         return t
 
     def workspace(self, nbytes):
@@ -179,8 +196,12 @@ class Engine:
             raise Sde4Error("xref must be [H+1, n_x]")
         G = P * N
         lib = L.load()
-        ws_bytes = lib.sde4_cost_workspace_bytes(C.byref(self.desc), P, N, H, stage.n_slack, int(want_grad),
-                                                 int(want_xtraj))
+        wkey = (P, N, H, stage.n_slack, bool(want_grad), bool(want_xtraj))
+        ws_bytes = self._ws_bytes.get(wkey)
+        if ws_bytes is None:
+            ws_bytes = lib.sde4_cost_workspace_bytes(C.byref(self.desc), P, N, H, stage.n_slack, int(want_grad),
+                                                     int(want_xtraj))
+            self._ws_bytes[wkey] = ws_bytes
         ws = self.workspace(ws_bytes)
         cost = torch.empty(P, dtype=torch.float32, device=y0.device) if cost_out is None else cost_out
         grad = None

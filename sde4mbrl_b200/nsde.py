@@ -101,6 +101,7 @@ def _make_multi_sampling(engine, params_model, num_samples, squeeze_single):
         if extra_args is not None:
             raise Sde4Error("extra_args must be None (no shipped model uses extra drift/diffusion arguments)")
         time_steps = compute_timesteps(params_model)
+        time_steps.setflags(write=False)
         H = time_steps.shape[0]
         y = as_f32(y)
         batched = y.dim() == 2  # extension: a leading batch of start states (vmap in nsde.py:1322-1323)
@@ -199,6 +200,7 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
     params_model["short_step_dt"] = params_mpc["short_step_dt"]
     params_model["long_step_dt"] = params_mpc["long_step_dt"]
     time_steps = compute_timesteps(params_model)
+    time_steps.setflags(write=False)  # lets the engine cache its device copy by identity
     H = time_steps.shape[0]
 
     (has_ubound, input_lb, input_ub), \
