@@ -14,6 +14,7 @@
 // reads / writes 128 B lines.
 #pragma once
 #include "cost.cuh"
+#pragma nv_diag_suppress 128  // the value-only instantiation returns before the backward sweep
 
 namespace sde4 {
 
@@ -274,13 +275,17 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   for (int j = 0; j < NU; ++j) u[j] = __ldg(op + (size_t)j * a.o_sj);
   float dummy_gx[NX], dummy_gu[NU], dummy_gs[NX];
   float cost = 0.0f;
-  float c_prev;
+  float c_prev = 0.0f;
+  // With GRAD the stage costs are evaluated once, in the backward sweep (value and gradient together);
+  // the value-only kernel accumulates the trapezoid here, in the reference's order.
   {
-    c_prev = stage_cost<NX, NU, false>(cd, x, u, xr, true, 0.0f, dummy_gx, dummy_gu);
-    if (CONSTR) c_prev += constr_cost<NX, false>(cd, x, x0s, 0.0f, dummy_gx, dummy_gs);  // slack_0 := x0 (nsde.py:1510)
+    if constexpr (!GRAD) {
+      c_prev = stage_cost<NX, NU, false>(cd, x, u, xr, true, 0.0f, dummy_gx, dummy_gu);
+      if (CONSTR) c_prev += constr_cost<NX, false>(cd, x, x0s, 0.0f, dummy_gx, dummy_gs);  // slack_0 := x0 (nsde.py:1510)
+    }
     if (keep && a.xbuf) {
       store_state<M>(a.xbuf + g, G, x, tc.l, active);
-      if (a.write_stage_cost && contrib) a.xbuf[(size_t)NX * G + g] = c_prev;
+      if (!GRAD && a.write_stage_cost && contrib) a.xbuf[(size_t)NX * G + g] = c_prev;
     }
   }
   for (int t = 0; t < H; ++t) {
@@ -296,38 +301,45 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     const int tn = t + 1 < H ? t + 1 : H - 1;
 #pragma unroll
     for (int j = 0; j < NU; ++j) unext[j] = __ldg(op + (size_t)tn * a.o_st + (size_t)j * a.o_sj);
-    float c_next = stage_cost<NX, NU, false>(cd, x, unext, xr + (size_t)(t + 1) * NX, true, 0.0f, dummy_gx, dummy_gu);
-    if (CONSTR) {
-      float sl[NX];
+    float c_next = 0.0f;
+    if constexpr (!GRAD) {
+      c_next = stage_cost<NX, NU, false>(cd, x, unext, xr + (size_t)(t + 1) * NX, true, 0.0f, dummy_gx, dummy_gu);
+      if (CONSTR) {
+        float sl[NX];
 #pragma unroll
-      for (int i = 0; i < NX; ++i)
-        sl[i] = (cd.slack_col[i] >= 0 && cd.constr_mode == SDE4_CONSTR_WITHPROX)
-                    ? __ldg(op + (size_t)t * a.o_st + (size_t)(NU + cd.slack_col[i]) * a.o_sj)
-                    : 0.0f;
-      c_next += constr_cost<NX, false>(cd, x, sl, 0.0f, dummy_gx, dummy_gs);
+        for (int i = 0; i < NX; ++i)
+          sl[i] = (cd.slack_col[i] >= 0 && cd.constr_mode == SDE4_CONSTR_WITHPROX)
+                      ? __ldg(op + (size_t)t * a.o_st + (size_t)(NU + cd.slack_col[i]) * a.o_sj)
+                      : 0.0f;
+        c_next += constr_cost<NX, false>(cd, x, sl, 0.0f, dummy_gx, dummy_gs);
+      }
+      if (a.sum_mode) cost += c_next;  // data term of the training loss: sum over t >= 1 (nsde.py:766)
+      else cost = fmaf(0.5f * dt, c_prev + c_next, cost);  // trapezoid (nsde.py:1515)
+      c_prev = c_next;
     }
-    if (a.sum_mode) cost += c_next;  // data term of the training loss: sum over t >= 1 (nsde.py:766)
-    else cost = fmaf(0.5f * dt, c_prev + c_next, cost);  // trapezoid (nsde.py:1515)
-    c_prev = c_next;
     if (keep && a.xbuf) {
       float* out = a.xbuf + (size_t)(t + 1) * a.x_rows * G + g;
       store_state<M>(out, G, x, tc.l, active);
-      if (a.write_stage_cost && contrib) out[(size_t)NX * G] = c_next;
+      if (!GRAD && a.write_stage_cost && contrib) out[(size_t)NX * G] = c_next;
     }
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = unext[j];
   }
-  if (a.has_terminal) cost += stage_cost<NX, NU, false>(td, x, u, xr + (size_t)H * NX, false, 0.0f, dummy_gx, dummy_gu);
+  if (!GRAD && a.has_terminal)
+    cost += stage_cost<NX, NU, false>(td, x, u, xr + (size_t)H * NX, false, 0.0f, dummy_gx, dummy_gu);
 
   // partial index of this thread's sample: per warp (all its samples in one problem) or per sample
   const int pw = a.warp_reduce ? (g / SPW) : g;
   const bool writer = a.warp_reduce ? (active && (threadIdx.x & 31) == 0) : contrib;
-  {
+  auto emit_cost = [&]() {
     float cv = contrib ? cost : 0.0f;
     if (a.warp_reduce) cv = warp_sum(cv);
     if (writer) a.cpart[pw] = cv;
+  };
+  if (!GRAD) {
+    emit_cost();
+    return;
   }
-  if (!GRAD) return;
   if constexpr (L > 1) __syncwarp();  // checkpoints written by sibling lanes are read back below
 
   // ---------------- backward sweep ----------------
@@ -343,7 +355,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   for (int j = 0; j < NU; ++j) gu[j] = 0.0f;  // row H-1 also receives the u-gradient of stage H
   {
     const float wH = a.sum_mode ? 1.0f : 0.5f * __ldg(a.dt + H - 1);
-    stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
+    float cH = stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
     if (CONSTR) {
       float sl[NX];
 #pragma unroll
@@ -351,11 +363,13 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
         sl[i] = (cd.slack_col[i] >= 0 && cd.constr_mode == SDE4_CONSTR_WITHPROX)
                     ? __ldg(op + (size_t)(H - 1) * a.o_st + (size_t)(NU + cd.slack_col[i]) * a.o_sj)
                     : 0.0f;
-      constr_cost<NX, true>(cd, x, sl, wH, lam, gs_pend);
+      cH += constr_cost<NX, true>(cd, x, sl, wH, lam, gs_pend);
     }
+    cost = wH * cH;
+    if (a.write_stage_cost && contrib) a.xbuf[((size_t)H * a.x_rows + NX) * G + g] = cH;
     if (a.has_terminal) {
       float gu_unused[NU];
-      stage_cost<NX, NU, true>(td, x, u, xr + (size_t)H * NX, false, 1.0f, lam, gu_unused);
+      cost += stage_cost<NX, NU, true>(td, x, u, xr + (size_t)H * NX, false, 1.0f, lam, gu_unused);
     }
   }
   const float* nz = a.noise_mode == SDE4_NOISE_GIVEN ? a.noise : a.dwbuf;
@@ -366,17 +380,46 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     tc.ev.dnet[2] = a.pd_net[2];
     tc.ev.dstride = a.pd_stride;
   }
+  // The lane-split kernels have registers to spare: they load the checkpoint x_t one iteration ahead so
+  // that the L2 / HBM latency hides behind the previous step's arithmetic.
+  constexpr bool PREFETCH = L > 1;
+  float xpre[PREFETCH ? NX : 1], auxpre = 0.0f;
+  if constexpr (PREFETCH) {
+    const float* in = a.xbuf + (size_t)(H - 1) * a.x_rows * G + g;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xpre[i] = in[(size_t)i * G];
+    if (M::NAUX) auxpre = a.auxbuf[(size_t)(H - 1) * G + g];
+  }
   for (int t = H - 1; t >= 0; --t) {
     const float dt = __ldg(a.dt + t);
     if constexpr (M::Ev::PGRAD) tc.ev.dcol = (size_t)t * G + g;
-    // through the projection (needs the projected x_{t+1}, still in the checkpoint buffer)
+    // noise of this step, requested before the long drift adjoint that precedes its use
+    float nzv[PREFETCH ? NX : 1];
+    if constexpr (PREFETCH) {
+      if (noisy) {
+        const float* nzt = nz + (size_t)t * NX * G + g;
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+          if ((M::A::NOUT_MASK >> i) & 1u) nzv[i] = d.noise_prior[i] != 0.0f ? nzt[(size_t)i * G] : 0.0f;
+      }
+    }
+    // through the projection: x still holds the projected x_{t+1}
     {
-      float aux = 0.0f;
-      if (M::NAUX) aux = a.auxbuf[(size_t)t * G + g];
-      M::project_vjp(a.xbuf + (size_t)(t + 1) * a.x_rows * G + g, (size_t)G, aux, lam);
+      float aux = auxpre;
+      if (!PREFETCH && M::NAUX) aux = a.auxbuf[(size_t)t * G + g];
+      M::project_vjp(x, aux, lam);
     }
     // checkpoint x_t and control u_t
-    {
+    if constexpr (PREFETCH) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) x[i] = xpre[i];
+      if (t > 0) {
+        const float* in = a.xbuf + (size_t)(t - 1) * a.x_rows * G + g;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) xpre[i] = in[(size_t)i * G];
+        if (M::NAUX) auxpre = a.auxbuf[(size_t)(t - 1) * G + g];
+      }
+    } else {
       const float* in = a.xbuf + (size_t)t * a.x_rows * G + g;
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = in[(size_t)i * G];
@@ -396,12 +439,15 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       M::drift_vjp(W, tc.ev, d, x, u, vf, gx, gu);
     }
     if (noisy) {
-      const float* nzt = nz + (size_t)t * NX * G + g;
-      Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
+      if constexpr (PREFETCH) Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzv[i]; }, gx);
+      else {
+        const float* nzt = nz + (size_t)t * NX * G + g;
+        Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
+      }
     }
     // stage cost at t: trapezoid weight w_t
     const float wt = a.sum_mode ? (t > 0 ? 1.0f : 0.0f) : (t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt);
-    stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)t * NX, true, wt, gx, gu);
+    float ct = stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)t * NX, true, wt, gx, gu);
     if (CONSTR) {
       float sl[NX];
 #pragma unroll
@@ -410,8 +456,10 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
         if (cd.slack_col[i] >= 0 && cd.constr_mode == SDE4_CONSTR_WITHPROX)
           sl[i] = t > 0 ? __ldg(op + (size_t)(t - 1) * a.o_st + (size_t)(NU + cd.slack_col[i]) * a.o_sj) : x0s[i];
       }
-      constr_cost<NX, true>(cd, x, sl, wt, gx, gs_pend);  // slack of stage t lives in opt row t-1
+      ct += constr_cost<NX, true>(cd, x, sl, wt, gx, gs_pend);  // slack of stage t lives in opt row t-1
     }
+    cost = fmaf(wt, ct, cost);
+    if (a.write_stage_cost && contrib) a.xbuf[((size_t)t * a.x_rows + NX) * G + g] = ct;
     // emit row t of the per-sample gradient
     {
       float* gp = a.gpart + (size_t)t * (NU + a.n_slack) * a.PW;
@@ -455,6 +503,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
 #pragma unroll
     for (int i = 0; i < NX; ++i) lam[i] = gx[i];
   }
+  emit_cost();
 }
 
 }  // namespace sde4

@@ -275,7 +275,7 @@ struct MsdModel {
   }
 
   SDE4_DEV static void project(float (&)[NX], float&) {}
-  SDE4_DEV static void project_vjp(const float*, size_t, float, float (&)[NX]) {}
+  SDE4_DEV static void project_vjp(const float (&)[NX], float, float (&)[NX]) {}
 };
 
 // ----------------------------------------------------------------------------
@@ -370,7 +370,7 @@ struct CartpoleModel {
   }
 
   SDE4_DEV static void project(float (&)[NX], float&) {}
-  SDE4_DEV static void project_vjp(const float*, size_t, float, float (&)[NX]) {}
+  SDE4_DEV static void project_vjp(const float (&)[NX], float, float (&)[NX]) {}
 };
 
 // ----------------------------------------------------------------------------
@@ -658,10 +658,10 @@ struct RotorModel {
     z[9] *= r;
     aux = r;
   }
-  // lam (wrt projected state) -> lam (wrt z); the projected quaternion is re-read from the
-  // checkpoint buffer (xn[i*stride] = state i of x_{t+1}) and aux = 1/|q_z|
-  SDE4_DEV static void project_vjp(const float* __restrict__ xn, size_t stride, float aux, float (&lam)[NX]) {
-    const float q0 = xn[6 * stride], q1 = xn[7 * stride], q2 = xn[8 * stride], q3 = xn[9 * stride];
+  // lam (wrt projected state) -> lam (wrt z); xn = the projected x_{t+1} (still in registers from the
+  // previous backward iteration) and aux = 1/|q_z|
+  SDE4_DEV static void project_vjp(const float (&xn)[NX], float aux, float (&lam)[NX]) {
+    const float q0 = xn[6], q1 = xn[7], q2 = xn[8], q3 = xn[9];
     const float dot = q0 * lam[6] + q1 * lam[7] + q2 * lam[8] + q3 * lam[9];
     lam[6] = (lam[6] - q0 * dot) * aux;
     lam[7] = (lam[7] - q1 * dot) * aux;

@@ -68,7 +68,9 @@ def test_cost_and_grad_given_noise(cuda, kind, H, N):
     # value-only launch gives the same value
     cost2, g2, _ = eng.cost_grad(nn, y0[None], opt, orc.compute_timesteps(pm), xref, stage.desc, N=N,
                                  noise=hp.to_native_noise(dw), want_grad=False)
-    assert g2 is None and float(cost2[0]) == float(cost[0])
+    # (the fused value+grad kernel accumulates the trapezoid in its backward sweep, the value-only one in
+    # the reference's forward order: same terms, different rounding)
+    assert g2 is None and abs(float(cost2[0]) - float(cost[0])) <= 2e-6 * abs(float(cost[0]))
 
 
 def test_grad_matches_finite_differences(cuda):

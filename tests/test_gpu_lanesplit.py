@@ -64,7 +64,8 @@ def test_lane_split_cost_grad(cuda, kind, H, N):
     ca, ga, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=8)
     cb, gb, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=1)
     cc, _, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=8, want_grad=False)
-    assert abs(float(ca[0]) - float(cb[0])) <= 2e-5 * abs(float(cb[0])) and float(cc[0]) == float(ca[0])
+    assert abs(float(ca[0]) - float(cb[0])) <= 2e-5 * abs(float(cb[0])) \
+        and abs(float(cc[0]) - float(ca[0])) <= 2e-6 * abs(float(ca[0]))
     assert hp.rel_err(ga.cpu().numpy(), gb.cpu().numpy()) < 2e-4
 
 
