@@ -264,10 +264,13 @@ typedef struct sde4_apg_state {
   float *x_opt, *xk, *yk, *grad_yk;
 } sde4_apg_state;
 
+/* floats of the `scratch` buffer sde4_apg_init / sde4_apg_update need (|grad|^2 partials); the candidate
+ * buffer `cand` is dead at both points and large enough, so callers may pass it. */
+int sde4_apg_scratch_floats(const sde4_apg_params* prm);
 /* init_apg after the value+gradient evaluation at x0: cost0[P], grad0 -> state (apg.py:82-112). */
 int sde4_apg_init(const sde4_apg_params* prm, const sde4_apg_state* st, const float* x0, const float* cost0,
                   const float* grad0, const float* momentum_or_null, const float* stepsize_or_null,
-                  float init_stepsize, float beta_init, void* stream);
+                  float init_stepsize, float beta_init, float* scratch, void* stream);
 /* candidates cand[H][n_opt][(maxls+1)*P] = yk - s_k*grad_yk, svals[(maxls+1)][P] (apg.py:179-184,312-321,358). */
 int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals, void* stream);
 /* Armijo selection (apg.py:324-329,362-379), prox, momentum point: xv[H][n_opt][2P] = [xcurr | vcurr];
@@ -280,7 +283,7 @@ int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_c
 /* state update with grad(ynext) (apg.py:224-273); problems with not_done == 0 are left untouched */
 int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
                     const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,
-                    const int32_t* sel_ls, void* stream);
+                    const int32_t* sel_ls, float* scratch, void* stream);
 
 /* ---- layout of the packed parameter block -------------------------------------
  * Returns the number of floats of the block for `model` (<0 on error).  The

@@ -104,6 +104,7 @@ EXPORTED_SYMBOLS = (
     "sde4_rng_split", "sde4_param_layout", "sde4_model_supported", "sde4_supported_archs",
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
+    "sde4_apg_scratch_floats",
 )
 
 _lib = None
@@ -153,11 +154,13 @@ def load():
     for name in ("sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update"):
         getattr(lib, name).restype = C.c_int
     lib.sde4_apg_init.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState), C.c_void_p, C.c_void_p, C.c_void_p,
-                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p]
+                                  C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    lib.sde4_apg_scratch_floats.argtypes = [C.POINTER(ApgParams)]
+    lib.sde4_apg_scratch_floats.restype = C.c_int
     lib.sde4_apg_candidates.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState), C.c_void_p, C.c_void_p, C.c_void_p]
     lib.sde4_apg_select.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 7
     lib.sde4_apg_pick.argtypes = [C.POINTER(ApgParams)] + [C.c_void_p] * 6
-    lib.sde4_apg_update.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 8
+    lib.sde4_apg_update.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 9
     asz = (C.c_int32 * 2)()
     lib.sde4_apg_struct_sizes(asz)
     if list(asz) != [C.sizeof(ApgParams), C.sizeof(ApgState)]:

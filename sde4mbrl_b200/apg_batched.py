@@ -76,6 +76,7 @@ class BatchedAPG:
             for j in range(n):
                 prm.lb[j], prm.ub[j] = float(lbv[j]), float(ubv[j])
         self.prm = prm
+        assert L.load().sde4_apg_scratch_floats(C.byref(prm)) <= self.cand.numel()
 
     def _pm_view(self, buf):
         """[H, n, Q] problem-minor buffer -> [Q, H, n] strided view the cost launcher accepts."""
@@ -117,7 +118,8 @@ class BatchedAPG:
         L.check(lib.sde4_apg_init(C.byref(self.prm), C.byref(self.st), _ptr(self.y), _ptr(self.y_cost), _ptr(self.y_grad),
                                   _ptr(None if momentum is None else as_f32(momentum).contiguous()),
                                   _ptr(None if stepsize is None else as_f32(stepsize).contiguous()),
-                                  C.c_float(ls["init_stepsize"]), C.c_float(self.op.get("beta_init", 0.25)), _stream()))
+                                  C.c_float(ls["init_stepsize"]), C.c_float(self.op.get("beta_init", 0.25)),
+                                  _ptr(self.cand), _stream()))
         return self
 
     def step(self):
@@ -132,7 +134,8 @@ class BatchedAPG:
                                   _ptr(self.pick), _stream()))
         self._cost(self.y, self.cost_tmp, grad_buf=self.y_grad)
         L.check(lib.sde4_apg_update(C.byref(prm), C.byref(st), _ptr(self.xv), _ptr(self.y), _ptr(self.y_cost),
-                                    _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
+                                    _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls),
+                                    _ptr(self.cand), _stream()))  # cand is dead here: |grad|^2 partials scratch
 
     def _capture(self):
         """Capture one masked iteration (4 bookkeeping + 3 cost + 3 reduce launches) in a CUDA graph.

@@ -2,20 +2,27 @@
 // Restates sde4mbrl/apg.py for P independent problems with masks instead of lax.cond / lax.scan:
 //   init_apg :53-113, one_step_apg :164-274, armijo_line_search :332-379, update_search :312-321,
 //   wolfe_cond_violated :324-329, _while_loop :451-464.
-// One thread per problem; every [H][n_opt][*] array is problem-minor, so a warp touches full lines.
+// Every [H][n_opt][*] array is problem-minor.  The vector kernels run on a 2-D grid: x covers the problems,
+// y covers chunks of APG_CH consecutive elements e = t*n_opt + j, so a warp touches full 128 B lines and the
+// serial work per thread is APG_CH elements; the (cheap) per-problem scalar logic is recomputed by every
+// chunk and written by chunk 0 only.  Kernels that both read and write per-problem scalars are split into a
+// vector kernel and a one-thread-per-problem `_fin` kernel, which also sums the |grad|^2 partials of the
+// chunks in a fixed order.
 #pragma once
 #include "common.cuh"
 
 namespace sde4 {
 
+constexpr int APG_CH = 4;
+
 __global__ void k_apg_init(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
-                           const float* x0, const float* cost0, const float* grad0, const float* momentum,
-                           const float* stepsize, float init_stepsize, float beta_init) {
+                           const float* __restrict__ x0, const float* __restrict__ grad0, float* __restrict__ gsq_part) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   const int P = prm.P, E = prm.H * prm.n_opt;
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
   float gsq = 0.0f;
-  for (int e = 0; e < E; ++e) {
+  for (int e = e0; e < e1; ++e) {
     const float x = x0[(size_t)e * P + p], g = grad0[(size_t)e * P + p];
     st.x_opt[(size_t)e * P + p] = x;
     st.xk[(size_t)e * P + p] = x;
@@ -23,6 +30,16 @@ __global__ void k_apg_init(const __grid_constant__ sde4_apg_params prm, const __
     st.grad_yk[(size_t)e * P + p] = g;
     gsq = fmaf(g, g, gsq);
   }
+  gsq_part[(size_t)blockIdx.y * P + p] = gsq;
+}
+
+__global__ void k_apg_init_fin(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
+                               const float* cost0, const float* momentum, const float* stepsize, float init_stepsize,
+                               float beta_init, const float* __restrict__ gsq_part, int chunks) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= prm.P) return;
+  float gsq = 0.0f;
+  for (int c = 0; c < chunks; ++c) gsq += gsq_part[(size_t)c * prm.P + p];
   const float mom = momentum ? momentum[p] : beta_init;
   const float s = stepsize ? stepsize[p] : init_stepsize;
   st.num_steps[p] = 1;
@@ -46,27 +63,37 @@ SDE4_DEV float apg_first_step(const sde4_apg_params& prm, float s) {
 }
 
 __global__ void k_apg_candidates(const __grid_constant__ sde4_apg_params prm,
-                                 const __grid_constant__ sde4_apg_state st, float* cand, float* svals) {
+                                 const __grid_constant__ sde4_apg_state st, float* __restrict__ cand,
+                                 float* __restrict__ svals) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   const int P = prm.P, E = prm.H * prm.n_opt, K = prm.maxls + 1;
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
+  float y[APG_CH], g[APG_CH];
+#pragma unroll
+  for (int i = 0; i < APG_CH; ++i) {
+    const int e = min(e0 + i, E - 1);
+    y[i] = st.yk[(size_t)e * P + p];
+    g[i] = st.grad_yk[(size_t)e * P + p];
+  }
   float s = apg_first_step(prm, st.stepsize[p]);
   for (int k = 0; k < K; ++k) {
     if (k > 0) s = fminf(s * prm.decrease_factor, prm.max_stepsize);  // update_search, apg.py:318
-    svals[(size_t)k * P + p] = s;
-    for (int e = 0; e < E; ++e) {
-      const float y = st.yk[(size_t)e * P + p], g = st.grad_yk[(size_t)e * P + p];
-      cand[(size_t)e * K * P + (size_t)k * P + p] = y - s * g;  // apg.py:319,358
-    }
+    if (blockIdx.y == 0) svals[(size_t)k * P + p] = s;
+#pragma unroll
+    for (int i = 0; i < APG_CH; ++i)
+      if (e0 + i < e1) cand[(size_t)(e0 + i) * K * P + (size_t)k * P + p] = y[i] - s * g[i];  // apg.py:319,358
   }
 }
 
 __global__ void k_apg_select(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
-                             const float* cand, const float* svals, const float* cand_cost, float* xv,
-                             float* sel_step, int32_t* sel_ls) {
+                             const float* __restrict__ cand, const float* __restrict__ svals,
+                             const float* __restrict__ cand_cost, float* __restrict__ xv, float* __restrict__ sel_step,
+                             int32_t* __restrict__ sel_ls) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   const int P = prm.P, E = prm.H * prm.n_opt, K = prm.maxls + 1;
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
   const float f_cur = st.curr_cost[p], gsq = st.grad_sqr[p];
   const float eps = 1.1920929e-07f;  // finfo(float32).eps, apg.py:328
   int ks = prm.maxls;
@@ -78,10 +105,12 @@ __global__ void k_apg_select(const __grid_constant__ sde4_apg_params prm, const 
       break;
     }
   }
-  sel_step[p] = svals[(size_t)ks * P + p];
-  sel_ls[p] = 1 + ks;  // num_iter of armijo_line_search
+  if (blockIdx.y == 0) {
+    sel_step[p] = svals[(size_t)ks * P + p];
+    sel_ls[p] = 1 + ks;  // num_iter of armijo_line_search
+  }
   const float mom = st.momentum[p];
-  for (int e = 0; e < E; ++e) {
+  for (int e = e0; e < e1; ++e) {
     float x = cand[(size_t)e * K * P + (size_t)ks * P + p];
     if (prm.has_prox) {
       const int j = e % prm.n_opt;
@@ -93,25 +122,51 @@ __global__ void k_apg_select(const __grid_constant__ sde4_apg_params prm, const 
   }
 }
 
-__global__ void k_apg_pick(const __grid_constant__ sde4_apg_params prm, const float* xv, const float* xv_cost,
-                           float* y, float* y_cost, int32_t* pick) {
+__global__ void k_apg_pick(const __grid_constant__ sde4_apg_params prm, const float* __restrict__ xv,
+                           const float* __restrict__ xv_cost, float* __restrict__ y, float* __restrict__ y_cost,
+                           int32_t* __restrict__ pick) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   const int P = prm.P, E = prm.H * prm.n_opt;
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
   const float cx = xv_cost[p], cv = xv_cost[P + p];
   const int x_le_v = cx <= cv;  // apg.py:219
-  pick[p] = x_le_v;
-  y_cost[p] = x_le_v ? cx : cv;
-  for (int e = 0; e < E; ++e) y[(size_t)e * P + p] = xv[(size_t)e * 2 * P + (x_le_v ? 0 : P) + p];
+  if (blockIdx.y == 0) {
+    pick[p] = x_le_v;
+    y_cost[p] = x_le_v ? cx : cv;
+  }
+  for (int e = e0; e < e1; ++e) y[(size_t)e * P + p] = xv[(size_t)e * 2 * P + (x_le_v ? 0 : P) + p];
 }
 
+// vector part of the state update: reads the OLD per-problem scalars, writes vectors and |grad|^2 partials
 __global__ void k_apg_update(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
-                             const float* xv, const float* y, const float* y_cost, const float* y_grad,
-                             const int32_t* pick, const float* sel_step, const int32_t* sel_ls) {
+                             const float* __restrict__ xv, const float* __restrict__ y,
+                             const float* __restrict__ y_cost, const float* __restrict__ y_grad,
+                             float* __restrict__ gsq_part) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   if (!st.not_done[p]) return;  // the scan body is the identity once the condition is false (apg.py:451-464)
   const int P = prm.P, E = prm.H * prm.n_opt;
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
+  const bool improv = st.opt_cost[p] > y_cost[p];
+  float gsq = 0.0f;
+  for (int e = e0; e < e1; ++e) {
+    const float g = y_grad[(size_t)e * P + p], yy = y[(size_t)e * P + p];
+    gsq = fmaf(g, g, gsq);
+    st.grad_yk[(size_t)e * P + p] = g;
+    st.yk[(size_t)e * P + p] = yy;
+    st.xk[(size_t)e * P + p] = xv[(size_t)e * 2 * P + p];
+    if (improv) st.x_opt[(size_t)e * P + p] = yy;
+  }
+  gsq_part[(size_t)blockIdx.y * P + p] = gsq;
+}
+
+__global__ void k_apg_update_fin(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
+                                 const float* y_cost, const int32_t* pick, const float* sel_step, const int32_t* sel_ls,
+                                 const float* __restrict__ gsq_part, int chunks) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= prm.P) return;
+  if (!st.not_done[p]) return;
   const int ns = st.num_steps[p];
   const float cost_y = y_cost[p], opt_cost = st.opt_cost[p], mom = st.momentum[p];
   float moment_next;
@@ -125,14 +180,7 @@ __global__ void k_apg_update(const __grid_constant__ sde4_apg_params prm, const 
   const int noimp = improv ? 0 : st.num_iter_no_improv[p] + 1;
   stop_not_sat = stop_not_sat && (noimp < prm.max_no_improvement_iter);
   float gsq = 0.0f;
-  for (int e = 0; e < E; ++e) {
-    const float g = y_grad[(size_t)e * P + p], yy = y[(size_t)e * P + p];
-    gsq = fmaf(g, g, gsq);
-    st.grad_yk[(size_t)e * P + p] = g;
-    st.yk[(size_t)e * P + p] = yy;
-    st.xk[(size_t)e * P + p] = xv[(size_t)e * 2 * P + p];
-    if (improv) st.x_opt[(size_t)e * P + p] = yy;
-  }
+  for (int c = 0; c < chunks; ++c) gsq += gsq_part[(size_t)c * prm.P + p];
   const float tot = (float)(ns + 1), s = sel_step[p];
   st.avg_linesearch[p] = ((float)ns * st.avg_linesearch[p] + (float)sel_ls[p]) / tot;
   st.avg_stepsize[p] = ((float)ns * st.avg_stepsize[p] + s) / tot;

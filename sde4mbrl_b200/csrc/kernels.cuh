@@ -71,6 +71,7 @@ struct ReduceK {
   float* grad;
   int P, N, H, n_u, n_opt, PW, NP;  // NP partials per problem; N = total particles (divisor)
   int has_slew;
+  int lpi;  // lanes per reduced item: 1 or 32
   float res_mult;
   float slew[SDE4_MAX_NU];
 };

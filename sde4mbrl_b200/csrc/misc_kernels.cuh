@@ -7,41 +7,62 @@ namespace sde4 {
 
 // ----------------------------------------------------------------------------
 // K3: fixed-order reduction of the partials of each problem, 1/N, + control-slew term.
-// thread <-> (row = t*n_opt + j, p), p fastest.  Row index H*n_opt is the cost.
+// item <-> (row = t*n_opt + j, p), p fastest.  Row index H*n_opt is the cost.  a.lpi lanes work on
+// one item: 1 (many problems, few partials each) or 32 (one warp per item: lane-strided, coalesced
+// partial sums in a fixed order, then a butterfly) -- deterministic either way.
 // ----------------------------------------------------------------------------
+SDE4_DEV float reduce_lanes(float v, int lpi) {
+  if (lpi == 32) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  }
+  return v;
+}
+
+SDE4_DEV float strided_sum(const float* __restrict__ src, int n, int sub, int lpi) {
+  float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  int k = sub;
+  for (; k + 3 * lpi < n; k += 4 * lpi) {
+    s0 += src[k];
+    s1 += src[k + lpi];
+    s2 += src[k + 2 * lpi];
+    s3 += src[k + 3 * lpi];
+  }
+  for (; k < n; k += lpi) s0 += src[k];
+  return (s0 + s1) + (s2 + s3);
+}
+
 __global__ void k_reduce(const __grid_constant__ ReduceK a) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int rows = a.H * a.n_opt + 1;
-  if (idx >= (long long)rows * a.P) return;
+  const int lpi = a.lpi;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long idx = gid / lpi;
+  const int sub = (int)(gid - idx * lpi);
+  const int rows = a.grad ? a.H * a.n_opt + 1 : 1;  // value only: just the cost row
+  if (idx >= (long long)rows * a.P) return;  // warp-uniform for lpi = 32 (blockDim is a multiple of 32)
   const int p = (int)(idx % a.P);
-  const int row = (int)(idx / a.P);
+  const int row = a.grad ? (int)(idx / a.P) : a.H * a.n_opt;
   const float invN = 1.0f / (float)a.N;
   const float* op = a.opt + (size_t)p * a.o_sp;
   if (row == a.H * a.n_opt) {
-    const float* src = a.cpart + (size_t)p * a.NP;
-    float s = 0.0f;
-    for (int k = 0; k < a.NP; ++k) s += src[k];
-    s *= invN;
+    float s = reduce_lanes(strided_sum(a.cpart + (size_t)p * a.NP, a.NP, sub, lpi), lpi) * invN;
     if (a.has_slew) {  // sum_t sum_j coeff_j ((u_{t+1,j}-u_{t,j})/dt_t)^2 * res_mult
       float sl = 0.0f;
-      for (int t = 0; t + 1 < a.H; ++t) {
+      for (int t = sub; t + 1 < a.H; t += lpi) {
         const float idt = 1.0f / a.dt[t];
         for (int j = 0; j < a.n_u; ++j) {
           const float dv = (op[(size_t)(t + 1) * a.o_st + (size_t)j * a.o_sj] - op[(size_t)t * a.o_st + (size_t)j * a.o_sj]) * idt;
           sl = fmaf(a.slew[j] * dv, dv, sl);
         }
       }
-      s = fmaf(sl, a.res_mult, s);
+      s = fmaf(reduce_lanes(sl, lpi), a.res_mult, s);
     }
-    a.cost[p] = s;
+    if (sub == 0) a.cost[p] = s;
     return;
   }
   if (a.grad == nullptr) return;
   const int t = row / a.n_opt, j = row - t * a.n_opt;
-  const float* src = a.gpart + (size_t)row * a.PW + (size_t)p * a.NP;
-  float s = 0.0f;
-  for (int k = 0; k < a.NP; ++k) s += src[k];
-  s *= invN;
+  float s = reduce_lanes(strided_sum(a.gpart + (size_t)row * a.PW + (size_t)p * a.NP, a.NP, sub, lpi), lpi) * invN;
+  if (sub != 0) return;
   if (a.has_slew && j < a.n_u) {
     const float uj = op[(size_t)t * a.o_st + (size_t)j * a.o_sj];
     float gsl = 0.0f;

@@ -354,9 +354,11 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   r.has_slew = (cd.has_slew && k.n_off == 0) ? 1 : 0;
   r.res_mult = cd.res_mult;
   for (int j = 0; j < SDE4_MAX_NU; ++j) r.slew[j] = cd.u_slew_coeff[j];
-  const long long items = (long long)(a->H * r.n_opt + 1) * a->P;
+  // value-only launches reduce the cost row only
+  const long long items = (long long)(r.grad ? a->H * r.n_opt + 1 : 1) * a->P;
+  r.lpi = (r.NP >= 16 && items * 32 <= (1ll << 24)) ? 32 : 1;  // few problems, many partials: a warp per item
   const int rthreads = 128;
-  k_reduce<<<(int)((items + rthreads - 1) / rthreads), rthreads, 0, s>>>(r);
+  k_reduce<<<(int)((items * r.lpi + rthreads - 1) / rthreads), rthreads, 0, s>>>(r);
   err = cudaGetLastError();
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(err));
   if (lo.enabled) {
@@ -454,45 +456,60 @@ static int apg_check(const sde4_apg_params* prm, const sde4_apg_state* st) {
     return fail(SDE4_ERR_INVALID, "null apg state buffer");
   return SDE4_OK;
 }
-#define SDE4_APG_LAUNCH(KERNEL, ...)                                                          \
+static inline int apg_chunks(const sde4_apg_params* prm) { return (prm->H * prm->n_opt + APG_CH - 1) / APG_CH; }
+// VEC: 2-D grid (problems x element chunks); FIN: one thread per problem
+#define SDE4_APG_LAUNCH(KERNEL, VEC, ...)                                                     \
   do {                                                                                        \
     const int th = 128;                                                                       \
-    KERNEL<<<(prm->P + th - 1) / th, th, 0, (cudaStream_t)stream>>>(__VA_ARGS__);            \
+    const dim3 grid((prm->P + th - 1) / th, (VEC) ? apg_chunks(prm) : 1);                     \
+    KERNEL<<<grid, th, 0, (cudaStream_t)stream>>>(__VA_ARGS__);                               \
     cudaError_t err = cudaGetLastError();                                                     \
     if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, #KERNEL ": %s", cudaGetErrorString(err)); \
-    return SDE4_OK;                                                                           \
   } while (0)
 
+int sde4_apg_scratch_floats(const sde4_apg_params* prm) {
+  if (int rc = apg_check(prm, nullptr)) return rc;
+  return apg_chunks(prm) * prm->P;
+}
 int sde4_apg_init(const sde4_apg_params* prm, const sde4_apg_state* st, const float* x0, const float* cost0,
                   const float* grad0, const float* momentum_or_null, const float* stepsize_or_null,
-                  float init_stepsize, float beta_init, void* stream) {
+                  float init_stepsize, float beta_init, float* scratch, void* stream) {
   if (int rc = apg_check(prm, st)) return rc;
-  if (!st || !x0 || !cost0 || !grad0) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_init, *prm, *st, x0, cost0, grad0, momentum_or_null, stepsize_or_null, init_stepsize, beta_init);
+  if (!st || !x0 || !cost0 || !grad0 || !scratch) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_init, 1, *prm, *st, x0, grad0, scratch);
+  SDE4_APG_LAUNCH(k_apg_init_fin, 0, *prm, *st, cost0, momentum_or_null, stepsize_or_null, init_stepsize, beta_init,
+                  scratch, apg_chunks(prm));
+  return SDE4_OK;
 }
 int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals, void* stream) {
   if (int rc = apg_check(prm, st)) return rc;
   if (!st || !cand || !svals) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_candidates, *prm, *st, cand, svals);
+  SDE4_APG_LAUNCH(k_apg_candidates, 1, *prm, *st, cand, svals);
+  return SDE4_OK;
 }
 int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, const float* svals,
                     const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, void* stream) {
   if (int rc = apg_check(prm, st)) return rc;
   if (!st || !cand || !svals || !cand_cost || !xv || !sel_step || !sel_ls) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_select, *prm, *st, cand, svals, cand_cost, xv, sel_step, sel_ls);
+  SDE4_APG_LAUNCH(k_apg_select, 1, *prm, *st, cand, svals, cand_cost, xv, sel_step, sel_ls);
+  return SDE4_OK;
 }
 int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
                   int32_t* pick, void* stream) {
   if (int rc = apg_check(prm, nullptr)) return rc;
   if (!xv || !xv_cost || !y || !y_cost || !pick) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_pick, *prm, xv, xv_cost, y, y_cost, pick);
+  SDE4_APG_LAUNCH(k_apg_pick, 1, *prm, xv, xv_cost, y, y_cost, pick);
+  return SDE4_OK;
 }
 int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
                     const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,
-                    const int32_t* sel_ls, void* stream) {
+                    const int32_t* sel_ls, float* scratch, void* stream) {
   if (int rc = apg_check(prm, st)) return rc;
-  if (!st || !xv || !y || !y_cost || !y_grad || !pick || !sel_step || !sel_ls) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_update, *prm, *st, xv, y, y_cost, y_grad, pick, sel_step, sel_ls);
+  if (!st || !xv || !y || !y_cost || !y_grad || !pick || !sel_step || !sel_ls || !scratch)
+    return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_update, 1, *prm, *st, xv, y, y_cost, y_grad, scratch);
+  SDE4_APG_LAUNCH(k_apg_update_fin, 0, *prm, *st, y_cost, pick, sel_step, sel_ls, scratch, apg_chunks(prm));
+  return SDE4_OK;
 }
 
 int sde4_fma_peak(int32_t variant, int32_t blocks, int32_t threads, int32_t iters, float* sink, double* flops,
