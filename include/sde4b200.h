@@ -209,6 +209,18 @@ size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_
                                  int32_t n_slack, int32_t want_grad, int32_t have_xtraj);
 int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* args, void* stream);
 
+/* Host-buffer variant of sde4_cost_grad: the call a jitted `multi_sampling` + `jax.value_and_grad`
+ * (sde4mbrl/nsde.py:1576-1586, apg.py:82,224) makes when its arguments live in host memory.
+ * In `args`, y0 / opt / xref / key / cost / grad are HOST pointers (contiguous [P][n_x], [P][H][n_opt],
+ * [P or 1][H+1][n_x], [P or 1][2]); params, dt, noise, xtraj and workspace stay device pointers.
+ * The inputs are packed into `staging_pinned` (page-locked host memory), moved with ONE async copy into
+ * `staging_device`, evaluated, and [cost | grad] comes back with ONE copy; the call returns after the
+ * stream has been synchronised.  Both staging buffers are caller-owned and at least
+ * sde4_cost_grad_host_staging_bytes() long. */
+size_t sde4_cost_grad_host_staging_bytes(const sde4_model_desc* model, int32_t P, int32_t H, int32_t n_slack);
+int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* args, void* staging_pinned,
+                        void* staging_device, size_t staging_bytes, void* stream);
+
 /* ---- RNG self-test: jax.random.{split, bits, normal} (call sites
  *      sde4mbrl/sde_solver.py:276,277,283; sde4mbrl/nsde.py:1026,1581).
  *      out[i] = element (offset+i) of random_bits(key, (total,)), uint32, bit-exact. */

@@ -104,7 +104,7 @@ EXPORTED_SYMBOLS = (
     "sde4_rng_split", "sde4_param_layout", "sde4_model_supported", "sde4_supported_archs",
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
-    "sde4_apg_scratch_floats",
+    "sde4_apg_scratch_floats", "sde4_cost_grad_host", "sde4_cost_grad_host_staging_bytes",
 )
 
 _lib = None
@@ -131,6 +131,11 @@ def load():
     lib.sde4_cost_workspace_bytes.restype = C.c_size_t
     lib.sde4_cost_grad.argtypes = [C.POINTER(ModelDesc), C.POINTER(CostArgs), C.c_void_p]
     lib.sde4_cost_grad.restype = C.c_int
+    lib.sde4_cost_grad_host.argtypes = [C.POINTER(ModelDesc), C.POINTER(CostArgs), C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_void_p]
+    lib.sde4_cost_grad_host.restype = C.c_int
+    lib.sde4_cost_grad_host_staging_bytes.argtypes = [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int32]
+    lib.sde4_cost_grad_host_staging_bytes.restype = C.c_size_t
     lib.sde4_loss_workspace_bytes.argtypes = [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int32]
     lib.sde4_loss_workspace_bytes.restype = C.c_size_t
     lib.sde4_loss_grad.argtypes = [C.POINTER(ModelDesc), C.POINTER(CostArgs), C.c_void_p, C.c_void_p]

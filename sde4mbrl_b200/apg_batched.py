@@ -35,7 +35,9 @@ class BatchedAPG:
         self.H = int(self.ts.shape[0])
         self.N = int(num_particles)
         self.n_opt = engine.n_u + stage.desc.n_slack
-        self.lanes = lanes
+        # lanes per sample of the three cost launches of an iteration: one int for all (0 = the library
+        # picks from the launch size) or {"cand": .., "xv": .., "y": ..}
+        self.lanes = lanes if isinstance(lanes, dict) else {"cand": lanes, "xv": lanes, "y": lanes}
         self.lb, self.ub = lb, ub
         self.P = None
         self._graph = None
@@ -82,11 +84,11 @@ class BatchedAPG:
         """[H, n, Q] problem-minor buffer -> [Q, H, n] strided view the cost launcher accepts."""
         return buf.permute(2, 0, 1)
 
-    def _cost(self, buf, cost_out, grad_buf=None, data_mod=0):
+    def _cost(self, buf, cost_out, grad_buf=None, data_mod=0, which="y"):
         self.eng.cost_grad(self.pk, self.y0, self._pm_view(buf), self.ts, self.xref, self.stage.desc,
                            terminal=None if self.terminal is None else self.terminal.desc, key=self.keys, N=self.N,
                            want_grad=grad_buf is not None, grad_out=None if grad_buf is None else self._pm_view(grad_buf),
-                           lanes=self.lanes, data_mod=data_mod, cost_out=cost_out)
+                           lanes=self.lanes.get(which, 0), data_mod=data_mod, cost_out=cost_out)
 
     # ------------------------------------------------------------------
     def init(self, x0, y0, xref, keys, momentum=None, stepsize=None):
@@ -126,10 +128,10 @@ class BatchedAPG:
         """One masked ``one_step_apg`` for all problems (apg.py:164-274)."""
         lib, prm, st, P = L.load(), self.prm, self.st, self.P
         L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _stream()))
-        self._cost(self.cand, self.cand_cost, data_mod=P)
+        self._cost(self.cand, self.cand_cost, data_mod=P, which="cand")
         L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(self.cand_cost),
                                     _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
-        self._cost(self.xv, self.xv_cost, data_mod=P)
+        self._cost(self.xv, self.xv_cost, data_mod=P, which="xv")
         L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
                                   _ptr(self.pick), _stream()))
         self._cost(self.y, self.cost_tmp, grad_buf=self.y_grad)

@@ -212,6 +212,81 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* a, void* 
   return cost_grad_impl(model, a, stream, LossOpts());
 }
 
+// ---- host-buffer variant -----------------------------------------------------------------------
+// staging layout (floats): [ y0 P*n_x | opt P*H*n_opt | xref Px*(H+1)*n_x | key 2*Pk ] in, [ cost P | grad P*H*n_opt ] out
+namespace {
+struct HostStage {
+  size_t y0, opt, xref, key, in_floats, cost, grad, total;
+};
+HostStage host_stage(int P, int H, int nx, int n_opt, int xref_rows, int key_rows) {
+  HostStage h;
+  h.y0 = 0;
+  h.opt = h.y0 + (size_t)P * nx;
+  h.xref = h.opt + (size_t)P * H * n_opt;
+  h.key = h.xref + (size_t)xref_rows * (H + 1) * nx;
+  h.in_floats = (h.key + 2 * (size_t)key_rows + 3) & ~(size_t)3;
+  h.cost = h.in_floats;
+  h.grad = h.cost + (((size_t)P + 3) & ~(size_t)3);
+  h.total = h.grad + (size_t)P * H * n_opt;
+  return h;
+}
+}  // namespace
+
+size_t sde4_cost_grad_host_staging_bytes(const sde4_model_desc* model, int32_t P, int32_t H, int32_t n_slack) {
+  if (!model) return 0;
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return 0;
+  return host_stage(P, H, e->nx, e->nu + n_slack, P, P).total * sizeof(float);
+}
+
+int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* a, void* staging_pinned,
+                        void* staging_device, size_t staging_bytes, void* stream) {
+  if (!model || !a) return fail(SDE4_ERR_INVALID, "null argument");
+  if (a->struct_size != (int)sizeof(sde4_cost_args)) return fail(SDE4_ERR_INVALID, "sde4_cost_args size mismatch (ABI)");
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return fail(SDE4_ERR_UNSUPPORTED, "no compiled specialisation for %s; compiled: %s", describe(*model).c_str(), sde4_supported_archs());
+  if (!a->y0 || !a->opt || !a->xref || !a->stage || !a->cost || !staging_pinned || !staging_device)
+    return fail(SDE4_ERR_INVALID, "null buffer");
+  if (a->P <= 0 || a->N <= 0 || a->H <= 0) return fail(SDE4_ERR_INVALID, "P, N, H must be positive");
+  if (a->data_mod != 0 && a->data_mod != a->P) return fail(SDE4_ERR_UNSUPPORTED, "host variant: data_mod must be 0 or P");
+  const int P = a->P, H = a->H, nx = e->nx, n_opt = e->nu + a->stage->n_slack;
+  if (a->opt_stride_j != 1 || a->opt_stride_t != n_opt || (P > 1 && a->opt_stride_p != (long long)H * n_opt))
+    return fail(SDE4_ERR_INVALID, "host variant: opt / grad must be contiguous [P][H][n_opt]");
+  const int xrows = a->xref_stride_p == 0 ? 1 : P;
+  if (a->xref_stride_p != 0 && a->xref_stride_p != (long long)(H + 1) * nx)
+    return fail(SDE4_ERR_INVALID, "host variant: xref must be contiguous [P][H+1][n_x] or shared");
+  const bool keyed = a->noise_mode == SDE4_NOISE_THREEFRY;
+  if (keyed && !a->key) return fail(SDE4_ERR_INVALID, "threefry noise needs a key");
+  const int krows = !keyed ? 0 : (a->key_stride_p == 0 ? 1 : P);
+  if (keyed && a->key_stride_p != 0 && a->key_stride_p != 2) return fail(SDE4_ERR_INVALID, "host variant: keys must be contiguous [P][2]");
+  const HostStage h = host_stage(P, H, nx, n_opt, xrows, krows);
+  if (staging_bytes < h.total * sizeof(float)) return fail(SDE4_ERR_WORKSPACE, "staging buffers too small (see sde4_cost_grad_host_staging_bytes)");
+  float* hp = static_cast<float*>(staging_pinned);
+  float* dp = static_cast<float*>(staging_device);
+  std::memcpy(hp + h.y0, a->y0, (size_t)P * nx * 4);
+  std::memcpy(hp + h.opt, a->opt, (size_t)P * H * n_opt * 4);
+  std::memcpy(hp + h.xref, a->xref, (size_t)xrows * (H + 1) * nx * 4);
+  if (keyed) std::memcpy(hp + h.key, a->key, (size_t)krows * 8);
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t err = cudaMemcpyAsync(dp, hp, h.in_floats * 4, cudaMemcpyHostToDevice, s);
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "H2D: %s", cudaGetErrorString(err));
+  sde4_cost_args d = *a;
+  d.y0 = dp + h.y0;
+  d.opt = dp + h.opt;
+  d.xref = dp + h.xref;
+  d.key = keyed ? reinterpret_cast<const uint32_t*>(dp + h.key) : nullptr;
+  d.cost = dp + h.cost;
+  d.grad = a->grad ? dp + h.grad : nullptr;
+  if (int rc = cost_grad_impl(model, &d, stream, LossOpts())) return rc;
+  const size_t out_floats = a->grad ? h.total - h.cost : (size_t)P;
+  err = cudaMemcpyAsync(hp + h.cost, dp + h.cost, out_floats * 4, cudaMemcpyDeviceToHost, s);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(s);
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "D2H: %s", cudaGetErrorString(err));
+  std::memcpy(a->cost, hp + h.cost, (size_t)P * 4);
+  if (a->grad) std::memcpy(a->grad, hp + h.grad, (size_t)P * H * n_opt * 4);
+  return SDE4_OK;
+}
+
 static size_t loss_dump_floats(const ArchEntry& e, size_t K, size_t off[3]) {
   size_t tot = 0;
   for (int s = 0; s < 3; ++s) {

@@ -52,6 +52,27 @@ def as_key(k, device=None):
     return torch.as_tensor(arr.view(np.int32), device=device).contiguous()
 
 
+def host_f32(x):
+    """numpy / list / CPU tensor -> C-contiguous float32 numpy array (no copy when it already is one)."""
+    if isinstance(x, torch.Tensor):
+        x = x.detach().numpy()
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def host_key(k):
+    """jax-layout key(s) -> C-contiguous uint32 numpy array."""
+    if isinstance(k, torch.Tensor):
+        k = k.detach().cpu().numpy()
+    k = np.asarray(k)
+    if k.dtype == np.int32:
+        k = k.view(np.uint32)
+    return np.ascontiguousarray(k, dtype=np.uint32)
+
+
+def is_host(x):
+    return not (isinstance(x, torch.Tensor) and x.is_cuda)
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
@@ -85,6 +106,8 @@ class Engine:
         self._dt_cache = {}
         self._dt_last = None
         self._ws_bytes = {}
+        self._host_plans = {}
+        self._stage = None
 
     # ---- parameters -----------------------------------------------------
     def packed(self, nn_params):
@@ -240,6 +263,79 @@ class Engine:
         L.check(lib.sde4_cost_grad(C.byref(self.desc), C.byref(a), _stream()))
         if squeeze and grad is not None:
             grad = grad.squeeze(0)
+        return cost, grad, xtraj
+
+    # ---- K2 + K3 with HOST buffers (one packed copy each way) ----------------
+    def cost_grad_host(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, want_grad=True,
+                       want_xtraj=False, block_threads=0, lanes=0):
+        """Same evaluation as ``cost_grad`` for arguments that live in HOST memory (numpy arrays / CPU
+        tensors): ``sde4_cost_grad_host`` packs them into a pinned staging buffer, does one H2D copy,
+        the launches, one D2H copy of [cost | grad] and a stream synchronise.  Returns numpy
+        ``cost[P]``, ``grad`` (shape of ``opt``) or None, and the device ``xtraj`` or None."""
+        pk = self.packed(nn_params)
+        y0 = host_f32(y0).reshape(-1, self.n_x)
+        P = y0.shape[0]
+        dt_t = self.dt_tensor(dt)
+        H = dt_t.numel()
+        opt = host_f32(opt)
+        n_opt = self.n_u + stage.n_slack
+        squeeze = opt.ndim == 2
+        opt3 = opt[None] if squeeze else opt
+        if opt3.shape != (P, H, n_opt):
+            raise AssertionError("Shape of the opt params do not match: %s vs (%d,%d,%d)" % (opt3.shape, P, H, n_opt))
+        xref = host_f32(xref)
+        if xref.shape[-2:] != (H + 1, self.n_x) or (xref.ndim == 3 and xref.shape[0] not in (1, P)):
+            raise Sde4Error("xref must be [H+1, n_x] or [P, H+1, n_x]")
+        xsp = (H + 1) * self.n_x if (xref.ndim == 3 and xref.shape[0] == P and P > 1) else 0
+        lib = L.load()
+        dev = pk.dev.device
+        keyed = self.noisy
+        keyh = None
+        if keyed:
+            keyh = host_key(key).reshape(-1, 2)
+            if keyh.shape[0] not in (1, P):
+                raise Sde4Error("need one key or one key per problem")
+        # everything that only depends on the call shape is prepared once per shape
+        pkey = (P, N, H, bytes(stage), None if terminal is None else bytes(terminal), bool(want_grad), bool(want_xtraj),
+                lanes, block_threads, xsp,
+                0 if keyh is None else keyh.shape[0])
+        plan = self._host_plans.get(pkey)
+        if plan is None:
+            ws_bytes = lib.sde4_cost_workspace_bytes(C.byref(self.desc), P, N, H, stage.n_slack, int(want_grad),
+                                                     int(want_xtraj))
+            sbytes = lib.sde4_cost_grad_host_staging_bytes(C.byref(self.desc), P, H, stage.n_slack)
+            a = L.CostArgs()
+            a.struct_size = C.sizeof(L.CostArgs)
+            a.P, a.N, a.H = P, N, H
+            a.opt_stride_p, a.opt_stride_t, a.opt_stride_j = H * n_opt, n_opt, 1
+            a.dt, a.xref_stride_p = _ptr(dt_t), xsp
+            a.key_stride_p = 0 if (keyh is None or keyh.shape[0] == 1) else 2
+            a.noise_mode = L.NOISE_THREEFRY if keyed else L.NOISE_NONE
+            a.stage = C.pointer(stage)
+            a.terminal = C.pointer(terminal) if terminal is not None else None
+            a.block_threads, a.lanes = block_threads, lanes
+            if len(self._host_plans) > 64:
+                self._host_plans.clear()
+            plan = (a, ws_bytes, sbytes, stage, terminal, dt_t)  # keeps the pointed-to descriptors alive
+            self._host_plans[pkey] = plan
+        a, ws_bytes, sbytes = plan[0], plan[1], plan[2]
+        ws = self.workspace(ws_bytes)
+        if self._stage is None or self._stage[0].numel() < sbytes:
+            self._stage = (torch.empty(sbytes, dtype=torch.uint8).pin_memory(),
+                           torch.empty(sbytes, dtype=torch.uint8, device=dev))
+        cost = np.empty(P, np.float32)
+        grad = np.empty_like(opt3) if want_grad else None
+        xtraj = torch.empty((H + 1, self.n_x + 1, P * N), dtype=torch.float32, device=dev) if want_xtraj else None
+        a.params, a.y0, a.opt, a.xref = pk.dev.data_ptr(), y0.ctypes.data, opt3.ctypes.data, xref.ctypes.data
+        a.key = keyh.ctypes.data if keyed else None
+        a.rng_mode = self.rng_mode
+        a.cost, a.grad = cost.ctypes.data, (grad.ctypes.data if want_grad else None)
+        a.xtraj = xtraj.data_ptr() if want_xtraj else None
+        a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        L.check(lib.sde4_cost_grad_host(C.byref(self.desc), C.byref(a), _ptr(self._stage[0]), _ptr(self._stage[1]),
+                                        sbytes, _stream()))
+        if squeeze and grad is not None:
+            grad = grad[0]
         return cost, grad, xtraj
 
     # ---- K2 (training variant) + K3 + K5 -----------------------------------

@@ -21,7 +21,7 @@ from . import _lib as L
 from . import costs as _costs
 from . import random as _random
 from ._lib import Sde4Error
-from .engine import Engine, as_f32, as_key
+from .engine import Engine, as_f32, as_key, is_host, host_f32
 from .sde_models import ControlledSDE
 
 
@@ -248,8 +248,9 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
     nn_params = model.init_params(seed)
     engine = Engine(model, _random.rng_mode())
 
-    def multi_sampling(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost=None, extra_dyn_args=None,
-                       extra_cost_args=None, extra_cost_terminal_args=None):
+    def _prepare(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost, extra_dyn_args, extra_cost_args):
+        """Argument checks shared by ``multi_sampling`` and ``multi_sampling.value_and_grad``.  Returns
+        ``(opt, run)`` with ``run(opt, need_grad) -> (cost, grad or None, xbuf)``."""
         if extra_dyn_args is not None:
             raise Sde4Error("extra_dyn_args must be None (no shipped model uses them)")
         if not isinstance(_cost_fn, _costs.StageCost):
@@ -259,33 +260,63 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
             raise Sde4Error("_terminal_cost must be a costs.StageCost or None")
         if extra_cost_args is None:
             raise Sde4Error("extra_cost_args (the reference trajectory xref[H+1, n_x]) is required")
-        opt = opt_params if isinstance(opt_params, torch.Tensor) else as_f32(opt_params)
+        stage = _cost_fn if constr is None else _costs.with_constraints(_cost_fn, constr, n_u)
+        term = None if _terminal_cost is None else _terminal_cost.desc
+        engine.rng_mode = _random.rng_mode()
+        host = is_host(y) and is_host(opt_params) and is_host(rng) and is_host(extra_cost_args)
+        if host:
+            # every argument lives in host memory (numpy arrays / CPU tensors, as when the reference's jitted
+            # function is fed numpy arrays): one packed copy each way through sde4_cost_grad_host; the cost
+            # (and its gradient) come back as CPU tensors, the trajectories stay on the device
+            opt = opt_params if isinstance(opt_params, torch.Tensor) else torch.from_numpy(host_f32(opt_params))
+        else:
+            opt = opt_params if isinstance(opt_params, torch.Tensor) else as_f32(opt_params)
         opt = opt.to(dtype=torch.float32)
         assert opt.dim() in (2, 3), "The parameters must be a two dimension array"
         assert opt.shape[-1] == opt_params_size, "Shape of the opt params do not match"
-        key = as_key(rng)
-        assert key.dim() == 1 or opt.dim() == 3, "RNG must be a single key for vmapping"
-        stage = _cost_fn if constr is None else _costs.with_constraints(_cost_fn, constr, n_u)
-        term = _terminal_cost
-        engine.rng_mode = _random.rng_mode()
-        y_t = as_f32(y)
-        xref = as_f32(extra_cost_args)
+        if host:
+            y_h, xref_h = host_f32(y), host_f32(extra_cost_args)
 
-        def run(opt_d, need_grad):
-            cost, grad, xtraj = engine.cost_grad(_nn_params, y_t, opt_d, time_steps, xref, stage.desc,
-                                                 terminal=None if term is None else term.desc, key=key,
-                                                 N=num_sample, want_grad=need_grad, want_xtraj=True)
-            return (cost if opt_d.dim() == 3 else cost[0]), grad, xtraj
+            def run(opt_h, need_grad):
+                cost, grad, xtraj = engine.cost_grad_host(_nn_params, y_h, opt_h, time_steps, xref_h, stage.desc,
+                                                          terminal=term, key=rng, N=num_sample, want_grad=need_grad,
+                                                          want_xtraj=True)
+                cost_t = torch.from_numpy(cost)
+                return (cost_t if opt_h.dim() == 3 else cost_t[0]), (None if grad is None else torch.from_numpy(grad)), xtraj
+        else:
+            key = as_key(rng)
+            assert key.dim() == 1 or opt.dim() == 3, "RNG must be a single key for vmapping"
+            y_t = as_f32(y)
+            xref = as_f32(extra_cost_args)
+            if opt.device.type != "cuda":
+                opt = opt.to(y_t.device)
 
-        if opt.device.type != "cuda":
-            opt = opt.to(y_t.device)
-        cost, xbuf = _CostSampling.apply(opt, run)
+            def run(opt_d, need_grad):
+                cost, grad, xtraj = engine.cost_grad(_nn_params, y_t, opt_d, time_steps, xref, stage.desc, terminal=term,
+                                                     key=key, N=num_sample, want_grad=need_grad, want_xtraj=True)
+                return (cost if opt_d.dim() == 3 else cost[0]), grad, xtraj
+        return opt, run
+
+    def _xtraj_view(xbuf, opt):
         P = opt.shape[0] if opt.dim() == 3 else 1
         xtraj = xbuf.view(H + 1, n_x + 1, P, num_sample).permute(2, 3, 0, 1)
-        if opt.dim() == 2:
-            xtraj = xtraj[0]
-        return cost, xtraj
+        return xtraj[0] if opt.dim() == 2 else xtraj
 
+    def multi_sampling(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost=None, extra_dyn_args=None,
+                       extra_cost_args=None, extra_cost_terminal_args=None):
+        opt, run = _prepare(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost, extra_dyn_args, extra_cost_args)
+        cost, xbuf = _CostSampling.apply(opt, run)
+        return cost, _xtraj_view(xbuf, opt)
+
+    def value_and_grad(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost=None, extra_dyn_args=None,
+                       extra_cost_args=None, extra_cost_terminal_args=None):
+        """``jax.value_and_grad(multi_sampling, argnums=2, has_aux=True)`` (how ``apg.py:82,224`` obtains the
+        gradient): ``((mean_cost, xtraj), grad)`` from ONE fused launch, without building an autograd graph."""
+        opt, run = _prepare(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost, extra_dyn_args, extra_cost_args)
+        cost, grad, xbuf = run(opt.detach(), True)
+        return (cost, _xtraj_view(xbuf, opt)), grad
+
+    multi_sampling.value_and_grad = value_and_grad
     multi_sampling.engine = engine
     multi_sampling.time_steps = time_steps
 

@@ -93,6 +93,50 @@ def test_online_cost_sampling_value_grad_and_xtraj(cuda):
     assert abs(lo - 1e-4) < 1e-9  # box clip to [1e-4, 1] (mpc_test_cfg.yaml:10-13)
 
 
+def test_host_buffer_path_matches_device_path(cuda):
+    """numpy / CPU-tensor arguments go through sde4_cost_grad_host (one packed copy each way) and must give
+    the device path's numbers bit for bit; results come back on the host."""
+    from sde4mbrl_b200 import random as R
+    N, H = 16, 20
+    pm, mpc, nn, (_, multi_cost, _, _, construct_opt) = _mpc_setup(N, H)
+    cp = mpc["cost_params"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    rng = np.random.default_rng(4)
+    y0 = hp.start_state("hexa", rng)
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    opt_np = hp.controls("hexa", H, rng)
+    key_np = tf.PRNGKey(9)
+    o_dev = torch.as_tensor(opt_np, device="cuda").requires_grad_(True)
+    c_dev, xt_dev = multi_cost(nn, y0, o_dev, R.PRNGKey(9), stage, extra_cost_args=xref)
+    (g_dev,) = torch.autograd.grad(c_dev, o_dev)
+    o_host = torch.as_tensor(opt_np).clone().requires_grad_(True)
+    c_host, xt_host = multi_cost(nn, y0, o_host, key_np, stage, extra_cost_args=xref)
+    (g_host,) = torch.autograd.grad(c_host, o_host)
+    assert not c_host.is_cuda and not g_host.is_cuda and xt_host.is_cuda
+    assert float(c_host) == float(c_dev)
+    np.testing.assert_array_equal(g_host.numpy(), g_dev.cpu().numpy())
+    np.testing.assert_array_equal(xt_host.cpu().numpy(), xt_dev.cpu().numpy())
+    # value_and_grad = jax.value_and_grad(multi_sampling, argnums=2, has_aux=True): no autograd graph
+    (c3, xt3), g3 = multi_cost.value_and_grad(nn, y0, opt_np, key_np, stage, extra_cost_args=xref)
+    assert float(c3) == float(c_dev) and tuple(xt3.shape) == (N, H + 1, 14)
+    np.testing.assert_array_equal(g3.numpy(), g_dev.cpu().numpy())
+    (c4, _), g4 = multi_cost.value_and_grad(nn, y0, o_dev.detach(), R.PRNGKey(9), stage, extra_cost_args=xref)
+    assert c4.is_cuda and float(c4) == float(c_dev) and torch.equal(g4, g_dev)
+    # value only, numpy in (no autograd)
+    c2, _ = multi_cost(nn, y0, opt_np, key_np, stage, extra_cost_args=xref)
+    assert abs(float(c2) - float(c_dev)) <= 2e-6 * abs(float(c_dev))
+    # batched problems [P, H, n_opt] with per-problem start states, references and keys
+    P = 3
+    y0b = np.stack([hp.start_state("hexa", rng) for _ in range(P)])
+    optb = np.stack([hp.controls("hexa", H, rng) for _ in range(P)])
+    keyb = np.stack([tf.PRNGKey(20 + i) for i in range(P)])
+    eng = multi_cost.engine
+    ch, gh, _ = eng.cost_grad_host(nn, y0b, optb, multi_cost.time_steps, xref, stage.desc, key=keyb, N=N)
+    cd_, gd_, _ = eng.cost_grad(nn, y0b, optb, multi_cost.time_steps, xref, stage.desc, key=keyb, N=N)
+    np.testing.assert_array_equal(ch, cd_.cpu().numpy())
+    np.testing.assert_array_equal(gh, gd_.cpu().numpy())
+
+
 def test_apg_mpc_trace_matches_oracle(cuda):
     """One MPC solve: host APG (CUDA cost/grad) vs oracle APG (oracle cost/grad), same noise."""
     from sde4mbrl_b200 import apg, random as R
