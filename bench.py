@@ -398,6 +398,60 @@ def main():
     except Exception as ex:  # never lose the headline line because of the extra
         mpc_extra = {"error": repr(ex)}
 
+    # ---- BASELINE configs[1]: cartpole APG-MPC, ONE problem, 1024 particles, horizon 50, 20 APG iterations
+    # (latency of a single solve): (i) device-side APG, one CUDA-graph replay per iteration; (ii) the
+    # reference-facing apg.py entry point driven with host arrays (every cost call = sde4_cost_grad_host)
+    c2_extra = {}
+    if rank == 0:
+        try:
+            import contextlib, io
+            from sde4mbrl_b200 import apg as _apg, costs as _costs
+            from sde4mbrl_b200.apg_batched import BatchedAPG
+            HC, NC = 50, 1024
+            pmc = configs.cartpole_model(horizon=HC, num_particles=NC)
+            mpcc = configs.cartpole_mpc(horizon=HC, dt=0.02, num_particles=NC, max_iter=20)
+            mpcc["apg_mpc"].update(atol=0.0, rtol=0.0, max_no_improvement_iter=20)  # exactly 20 iterations
+            with contextlib.redirect_stdout(io.StringIO()):
+                _, mcost, vprox, _, _ = nsde.create_online_cost_sampling_fn(pmc, mpcc, sde_constr=sde_models.CartPoleSDE)
+            modc = mcost.engine.model
+            nnc = configs.random_params(modc, seed=0)
+            for k_, v_ in nnc.items():  # random_params damps the residual nets (x0.02) for long rollouts; an MPC problem
+                if k_.endswith("linear_2") and "init_residual_networks" in k_:  # needs dynamics that react to the control
+                    v_["w"] = v_["w"] * np.float32(25.0)
+                    v_["b"] = v_["b"] * np.float32(25.0)
+            cpc = mpcc["cost_params"]
+            stagec = _costs.QuadraticCost(cpc["xerr"], cpc["uerr"], cpc["uref"], feat="cartpole", res_mult=cpc["res_mult"])
+            y0c = np.array([0.0, 0.0, np.pi, 0.0], np.float32) + np.random.default_rng(3).normal(0, 0.01, 4).astype(np.float32)
+            xrefc = np.zeros((HC + 1, 4), np.float32)
+            keyc = np.array([0, 7], np.uint32)
+            x0c = np.full((HC, 1), 1e-4, np.float32)
+            solver = BatchedAPG(mcost.engine, nnc, stagec, mpcc["apg_mpc"], mcost.time_steps, NC, lb=-1.0, ub=1.0)
+            tms = []
+            for rep in range(6):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                solver.init(torch.as_tensor(x0c, device=dev), y0c[None], xrefc, keyc).run(20)
+                e1.record()
+                torch.cuda.synchronize()
+                if rep:
+                    tms.append(e0.elapsed_time(e1))
+            dev_ms, dev_cost = float(np.mean(tms)), float(solver.t["opt_cost"][0])
+            cost_h = lambda o: mcost(nnc, y0c, o, keyc, stagec, extra_cost_args=xrefc)[0]
+            prox_h = lambda x, stepsize=None: vprox(x)
+            tms = []
+            for rep in range(4):
+                t0 = time.perf_counter()
+                st_h = _apg.apg(_apg.init_apg(torch.as_tensor(x0c), cost_h, mpcc["apg_mpc"]), cost_h, mpcc["apg_mpc"],
+                                proximal_fn=prox_h)
+                if rep:
+                    tms.append((time.perf_counter() - t0) * 1e3)
+            c2_extra = {"problem": "cartpole swing-up, 1 problem, %d particles, horizon %d, 20 APG iterations" % (NC, HC),
+                        "device_apg_ms_per_solve": dev_ms, "device_apg_opt_cost": dev_cost,
+                        "host_apg_api_ms_per_solve": float(np.mean(tms)), "host_apg_opt_cost": float(st_h.opt_cost),
+                        "host_apg_iterations": int(st_h.num_steps) - 1}
+        except Exception as ex:
+            c2_extra = {"error": repr(ex)}
+
     # ---- extras (rank 0, N=1 only): forward rollout, FP32 peak, CPU baseline
     extras = {}
     roof = None
@@ -491,6 +545,7 @@ def main():
         if cpu_b:
             line["cpu_baseline"] = cpu_b
         line.update(extras)
+        line["cartpole_mpc_single"] = c2_extra
         line["mpc_batch"] = mpc_extra
         line["simulator_rollouts"] = sim_extra
         line["training_loss"] = train_extra

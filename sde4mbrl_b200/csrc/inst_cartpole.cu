@@ -13,8 +13,10 @@ using CartBbD32 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, CartD32, 0xE, 0xA, true, Ca
 using CartBbD8 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, CartD8, 0xE, 0xA, true, CartResBb, 0, NoNet, 0>;
 using CartSiOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, SDE4_CART_SIDE_INFO, NoNet, 0, 0, false, CartResSi, 0, CartCtrl, 0>;
 using CartBbOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, NoNet, 0, 0, false, CartResBb, 0, NoNet, 0>;
-SDE4_REGISTER_TRAIN(cartpole_si_d32, CartpoleModel, CartSiD32)
-SDE4_REGISTER_TRAIN(cartpole_bb_d32, CartpoleModel, CartBbD32)
+// latency-bound single-problem MPC (BASELINE configs[1]) uses the lane-split kernels; the control net of the
+// side-info model (2->6->8) only divides by 2, the black-box nets divide by 8
+SDE4_REGISTER_TRAIN_LS(cartpole_si_d32, CartpoleModel, CartSiD32, 2)
+SDE4_REGISTER_TRAIN_LS(cartpole_bb_d32, CartpoleModel, CartBbD32, 8)
 SDE4_REGISTER(cartpole_bb_d8, CartpoleModel<CartBbD8>)
 SDE4_REGISTER(cartpole_si_ode, CartpoleModel<CartSiOde>)
 SDE4_REGISTER(cartpole_bb_ode, CartpoleModel<CartBbOde>)

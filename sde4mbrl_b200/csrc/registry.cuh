@@ -155,6 +155,9 @@ struct ArchRegistrar {
 #define SDE4_REGISTER_TRAIN(NAME, MODEL_T, ARCH)                                                     \
   static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, ::sde4::NoLaneSplit, ::sde4::NoLaneSplit, \
                                                               MODEL_T<ARCH, ::sde4::Ev1P>>(#NAME));
+#define SDE4_REGISTER_TRAIN_LS(NAME, MODEL_T, ARCH, LANES)                                             \
+  static ::sde4::ArchRegistrar reg_##NAME(                                                             \
+      ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>, ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::Ev1P>>(#NAME));
 #define SDE4_REGISTER_LS(NAME, MODEL_T, ARCH, LANES) \
   static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>>(#NAME));
 #define SDE4_REGISTER_LS2(NAME, MODEL_T, ARCH, LANES_A, LANES_B)                                          \

@@ -219,28 +219,41 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
                       state_lb=state_lb, state_ub=state_ub,
                       slack_scaling=np.broadcast_to(np.asarray(slack_scaling, np.float32), (ns,)))
 
-    def _t(a):
-        return as_f32(a)
+    class _Box:
+        """``constr_vect`` (nsde.py:1422): clip to [lb, ub] on the device the argument lives on (numpy
+        arguments are moved to the GPU, as every other entry point does)."""
 
-    def constr_vect(a, lb, ub):
-        return torch.minimum(torch.maximum(a, lb), ub)
+        def __init__(self, lb, ub, first=0):
+            self.lb_np, self.ub_np = np.asarray(lb, np.float32), np.asarray(ub, np.float32)
+            self.first = first  # columns before `first` pass through unclipped
+            self._dev = {}
+
+        def bounds(self, device):
+            b = self._dev.get(device)
+            if b is None:
+                b = (torch.as_tensor(self.lb_np, device=device), torch.as_tensor(self.ub_np, device=device))
+                self._dev[device] = b
+            return b
+
+        def __call__(self, u_slack):
+            a = u_slack.to(torch.float32) if isinstance(u_slack, torch.Tensor) else as_f32(u_slack)
+            lb, ub = self.bounds(a.device)
+            if self.first:
+                return torch.cat((a[..., :self.first], torch.minimum(torch.maximum(a[..., self.first:], lb), ub)), dim=-1)
+            return torch.minimum(torch.maximum(a, lb), ub)
 
     # proximal operators (nsde.py:1435-1460); they act on [H, n_opt] (or [..., H, n_opt]) tensors
     proximal_fn = None
     constr_cost = None
     if has_ubound and (not has_xbound):
-        lb, ub = _t(input_lb), _t(input_ub)
-        proximal_fn = lambda u_slack: constr_vect(as_f32(u_slack), lb, ub)
+        proximal_fn = _Box(input_lb, input_ub)
     if (not has_ubound) and has_xbound and slack_proximal:
-        slb, sub = _t(state_lb), _t(state_ub)
-        proximal_fn = lambda u_slack: torch.cat((as_f32(u_slack)[..., :n_u], constr_vect(as_f32(u_slack)[..., n_u:], slb, sub)), dim=-1)
+        proximal_fn = _Box(state_lb, state_ub, first=n_u)
     if has_ubound and has_xbound and (not slack_proximal):
-        lb, ub = _t(input_lb), _t(input_ub)
-        proximal_fn = lambda u_slack: constr_vect(as_f32(u_slack), lb, ub)
+        proximal_fn = _Box(input_lb, input_ub)
     if has_ubound and has_xbound and slack_proximal:
-        lb = torch.cat((_t(input_lb), _t(state_lb)))
-        ub = torch.cat((_t(input_ub), _t(state_ub)))
-        proximal_fn = lambda u_slack: constr_vect(as_f32(u_slack), lb, ub)
+        proximal_fn = _Box(np.concatenate((np.asarray(input_lb, np.float32), np.asarray(state_lb, np.float32))),
+                           np.concatenate((np.asarray(input_ub, np.float32), np.asarray(state_ub, np.float32))))
     if has_xbound:
         constr_cost = "constr_cost_withprox" if slack_proximal else "constr_cost_noprox"  # evaluated in-kernel
 

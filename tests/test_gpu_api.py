@@ -168,6 +168,29 @@ def test_apg_mpc_trace_matches_oracle(cuda):
     assert hp.rel_err(s.x_opt.cpu().numpy(), so.x_opt.numpy()) < 2e-3
 
 
+def test_apg_with_host_tensors_matches_device_tensors(cuda):
+    """apg.py driven with CPU tensors / numpy keys (every cost call goes through sde4_cost_grad_host and the
+    box prox runs on the CPU) follows the same iterates as with CUDA tensors."""
+    from sde4mbrl_b200 import apg, random as R
+    N, H, iters = 8, 20, 5
+    pm, mpc, nn, (_, multi_cost, vprox, _, construct_opt) = _mpc_setup(N, H, iters)
+    cp, op = mpc["cost_params"], mpc["apg_mpc"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    y0 = hp.start_state("hexa", np.random.default_rng(2))
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    prox = lambda x, stepsize=None: vprox(x)
+    x0 = construct_opt(u=np.full(6, 0.33, np.float32))
+    cost_dev = lambda o: multi_cost(nn, y0, o, R.PRNGKey(21), stage, extra_cost_args=xref)[0]
+    s_dev = apg.apg(apg.init_apg(x0, cost_dev, op), cost_dev, op, proximal_fn=prox)
+    cost_host = lambda o: multi_cost(nn, y0, o, tf.PRNGKey(21), stage, extra_cost_args=xref)[0]
+    s_host = apg.apg(apg.init_apg(x0.cpu(), cost_host, op), cost_host, op, proximal_fn=prox)
+    assert not s_host.x_opt.is_cuda and s_dev.x_opt.is_cuda
+    assert int(s_host.num_steps) == int(s_dev.num_steps)
+    assert abs(float(s_host.opt_cost) - float(s_dev.opt_cost)) <= 1e-5 * abs(float(s_dev.opt_cost))
+    assert hp.rel_err(s_host.x_opt.numpy(), s_dev.x_opt.cpu().numpy()) < 1e-4
+
+
 def test_rejects_python_cost_callables(cuda):
     from sde4mbrl_b200 import random as R
     from sde4mbrl_b200._lib import Sde4Error

@@ -76,3 +76,27 @@ def test_requesting_missing_lane_kernel_is_an_error(cuda):
     with pytest.raises(Sde4Error):
         Engine(model).rollout(nn, np.zeros((1, 4), np.float32), np.zeros((5, 1), np.float32),
                               orc.compute_timesteps(pm), key=tf.PRNGKey(0), N=2, lanes=8)
+
+
+@pytest.mark.parametrize("kind,lanes,H,N", [("cartpole", 2, 50, 37), ("cartpole_bb", 8, 30, 21)])
+def test_lane_split_cartpole(cuda, kind, lanes, H, N):
+    """Cartpole lane-split kernels (side-info: 2 lanes, black-box: 8 lanes) vs the one-thread-per-sample ones."""
+    from sde4mbrl_b200.engine import Engine
+    rng = np.random.default_rng(7)
+    pm, model, nn = hp.build(kind, H, N, seed=5)
+    y0, opt = hp.start_state(kind, rng), hp.controls(kind, H, rng)
+    cp = configs.cartpole_mpc()["cost_params"]
+    stage = costs.QuadraticCost(cp["xerr"], cp["uerr"], cp["uref"], feat="cartpole", res_mult=cp["res_mult"])
+    xref = np.zeros((H + 1, 4), np.float32)
+    eng = Engine(model)
+    ts = orc.compute_timesteps(pm)
+    key = tf.PRNGKey(4)
+    xl = eng.rollout(nn, y0[None], opt, ts, key=key, N=N, lanes=lanes)
+    x1 = eng.rollout(nn, y0[None], opt, ts, key=key, N=N, lanes=1)
+    assert hp.rel_err(xl.cpu().numpy(), x1.cpu().numpy()) < 2e-5
+    cl, gl, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=lanes)
+    c1, g1, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=1)
+    assert abs(float(cl[0]) - float(c1[0])) <= 2e-5 * abs(float(c1[0]))
+    assert hp.rel_err(gl.cpu().numpy(), g1.cpu().numpy()) < 2e-4
+    cv, _, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=lanes, want_grad=False)
+    assert abs(float(cv[0]) - float(c1[0])) <= 2e-5 * abs(float(c1[0]))
