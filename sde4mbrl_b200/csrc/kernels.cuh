@@ -115,7 +115,8 @@ SDE4_DEV int kernel_prologue(float* W, const float* params, uint64_t* mbar, Tctx
 // `keep` (optional) receives a copy for the backward sweep: keep[i*G] = dw_i.
 template <class M>
 SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode, const float* __restrict__ noise,
-                         uint32_t b0, uint32_t b1, int t, int H, int G, int g, Tctx<M>& tc, float (&dw)[M::NX],
+                         uint32_t b0, uint32_t b1, int t, int H, unsigned G, int g, uint32_t nzmask, Tctx<M>& tc,
+                         float (&dw)[M::NX],
                          float* keep) {
   constexpr int NX = M::NX, L = M::Ev::L;
   if constexpr (L == 1) {
@@ -128,7 +129,7 @@ SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode,
       for (int q = 0; q < 4; ++q) {
         const int i = i0 + q;
         v[q] = 0.0f;
-        if (i < NX && d.noise_prior[i < NX ? i : 0] != 0.0f) {
+        if (i < NX && ((nzmask >> i) & 1u)) {
           if (noise_mode == SDE4_NOISE_GIVEN) {
             v[q] = __ldg(noise + ((size_t)t * NX + i) * G + g);
           } else {
@@ -150,7 +151,7 @@ SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode,
     for (int q = 0; q < PER; ++q) {
       const int i = tc.l + q * L;
       v[q] = 0.0f;
-      if (i < NX && d.noise_prior[i < NX ? i : 0] != 0.0f) {
+      if (i < NX && ((nzmask >> i) & 1u)) {
         if (noise_mode == SDE4_NOISE_GIVEN) {
           v[q] = __ldg(noise + ((size_t)t * NX + i) * G + g);
         } else {
@@ -183,13 +184,47 @@ SDE4_DEV void em_step(const float* W, Tctx<M>& tc, const sde4_model_desc& d, flo
   M::project(x, aux);
 }
 
-// state rows of one time slice: element i is written by lane (i mod L) of the sample's group
-template <class M>
-SDE4_DEV void store_state(float* out, int G, const float (&x)[M::NX], int l, bool active) {
-  constexpr int L = M::Ev::L;
+// x[base + l] for l in [0, L) by a select tree over the bits of l (all indices compile-time)
+template <int L, int N>
+SDE4_DEV float lane_pick(const float (&x)[N], int base, int l) {
+  float v[L];
 #pragma unroll
-  for (int i = 0; i < M::NX; ++i)
-    if (active && (L == 1 || (i % L) == l)) out[(size_t)i * G] = x[i];
+  for (int j = 0; j < L; ++j) v[j] = x[base + j < N ? base + j : N - 1];
+#pragma unroll
+  for (int s = 1; s < L; s <<= 1) {
+    const bool bit = (l & s) != 0;
+#pragma unroll
+    for (int j = 0; j + s < L; j += 2 * s) v[j] = bit ? v[j + s] : v[j];
+  }
+  return v[0];
+}
+
+// state rows of one time slice: element i is written by lane (i mod L) of the sample's group (the state is
+// replicated over the group; every lane selects its ceil(NX/L) elements and issues that many stores)
+template <class M>
+SDE4_DEV void store_state(float* out, unsigned G, const float (&x)[M::NX], int l, bool active) {
+  constexpr int L = M::Ev::L, NX = M::NX;
+  if constexpr (L == 1) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+      if (active) out[(size_t)i * G] = x[i];
+  } else {
+    float* row = out + (size_t)l * G;
+#pragma unroll
+    for (int k = 0; k * L < NX; ++k) {
+      const float v = lane_pick<L, NX>(x, k * L, l);
+      if (active && k * L + l < NX) row[(size_t)(k * L) * G] = v;
+    }
+  }
+}
+
+// bit i set <=> state i has a non-zero prior diffusion (its noise sample exists)
+template <int NX>
+SDE4_DEV uint32_t noise_mask(const sde4_model_desc& d) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < NX; ++i) m |= d.noise_prior[i] != 0.0f ? (1u << i) : 0u;
+  return m;
 }
 
 // ----------------------------------------------------------------------------
@@ -211,6 +246,7 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
   for (int i = 0; i < NX; ++i) x[i] = __ldg(a.y0 + (size_t)p * NX + i);
   store_state<M>(a.xevol + g, a.G, x, tc.l, active);
   const bool noisy = a.noise_mode != SDE4_NOISE_NONE;
+  const uint32_t nzmask = noise_mask<NX>(d);
   uint32_t b0 = 0, b1 = 0;
   if (a.noise_mode == SDE4_NOISE_THREEFRY) {
     const uint32_t* k = a.key + (size_t)p * a.key_sp;
@@ -221,7 +257,7 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
     float u[NU], dw[NX];
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = __ldg(up + (size_t)t * a.u_st + (size_t)j * a.u_sj);
-    if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, a.G, g, tc, dw, nullptr);
+    if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, (unsigned)a.G, g, nzmask, tc, dw, nullptr);
     float aux;
     em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
     store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
@@ -251,11 +287,13 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   const int g = active ? g0 : a.G - 1;  // inactive lanes shadow a valid sample, contribute nothing
   const bool contrib = active && tc.l == 0;  // one lane per sample feeds the particle reductions
   const int p = g / a.N, n = g - p * a.N;
-  const int G = a.G, H = a.H;
+  const unsigned G = (unsigned)a.G;
+  const int H = a.H;
   const int pd = p % a.data_mod;  // stacked candidate evaluations share the problem data
   const float* op = a.opt + (size_t)p * a.o_sp;
   const float* xr = a.xref + (size_t)pd * a.xref_sp;
   const bool noisy = a.noise_mode != SDE4_NOISE_NONE;
+  const uint32_t nzmask = noise_mask<NX>(d);
   const bool keep = GRAD || a.xbuf != nullptr;
 
   float x[NX], x0s[NX];
@@ -293,7 +331,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     const float dt = __ldg(a.dt + t);
     float dw[NX];
     if (noisy)
-      draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, tc, dw,
+      draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, nzmask, tc, dw,
                     (GRAD && active && a.dwbuf) ? a.dwbuf + (size_t)t * NX * G + g : nullptr);
     float aux = 0.0f;
     em_step<M>(W, tc, d, x, u, dw, dt, noisy, aux);
@@ -401,7 +439,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
         const float* nzt = nz + (size_t)t * NX * G + g;
 #pragma unroll
         for (int i = 0; i < NX; ++i)
-          if ((M::A::NOUT_MASK >> i) & 1u) nzv[i] = d.noise_prior[i] != 0.0f ? nzt[(size_t)i * G] : 0.0f;
+          if ((M::A::NOUT_MASK >> i) & 1u) nzv[i] = ((nzmask >> i) & 1u) ? nzt[(size_t)i * G] : 0.0f;
       }
     }
     // through the projection: x still holds the projected x_{t+1}
