@@ -125,7 +125,7 @@ class Engine:
         key = arr.tobytes()
         t = self._dt_cache.get(key)
         if t is None:
-            t = torch.as_tensor(arr, device=_dev())
+            t = torch.as_tensor(np.array(arr), device=_dev())  # private writable copy (dt may be a read-only array)
             self._dt_cache[key] = t
         if isinstance(dt, np.ndarray) and not dt.flags.writeable:
             self._dt_last = (dt, t)
