@@ -78,3 +78,43 @@ def test_errors_for_unsupported_requests():
         sde_models.CartPoleSDE(dict(configs.cartpole_model(2, 1), control_dependent_noise=True))
     with pytest.raises(L.Sde4Error):
         sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), sde_solver="stratonovich_heun"))
+
+
+def test_rotor_mpc_frames_and_targets():
+    """Host-side helpers of sde4mbrl_b200/rotor_mpc.py (sde_mpc_design.py:37-70, rotor_uav/utils.py)."""
+    from sde4mbrl_b200 import rotor_mpc as rm
+    rng = np.random.default_rng(0)
+    # NED <-> ENU: positions (x, y, z) -> (y, x, -z); body rates (x, y, z) -> (x, -y, -z); involution
+    q = rng.standard_normal(4)
+    q /= np.linalg.norm(q)
+    x = np.concatenate((rng.standard_normal(6), q, rng.standard_normal(3))).astype(np.float32)
+    y = rm.ned2enu(x)
+    np.testing.assert_allclose(y[:3], [x[1], x[0], -x[2]], atol=1e-6)
+    np.testing.assert_allclose(y[3:6], [x[4], x[3], -x[5]], atol=1e-6)
+    np.testing.assert_allclose(y[10:13], [x[10], -x[11], -x[12]], atol=1e-6)
+    assert abs(np.linalg.norm(y[6:10]) - 1) < 1e-6
+    back = rm.ned2enu(y)
+    # quaternions are equal up to sign
+    np.testing.assert_allclose(back[:6], x[:6], atol=1e-6)
+    assert min(np.abs(back[6:10] - x[6:10]).max(), np.abs(back[6:10] + x[6:10]).max()) < 1e-6
+    # level attitude with yaw psi in NED is level with yaw pi/2 - psi in ENU
+    psi = 0.3
+    lvl = np.concatenate((np.zeros(6), rm.quat_from_euler(0.0, 0.0, psi), np.zeros(3)))
+    qe = rm.ned2enu(lvl)[6:10]
+    want = rm.quat_from_euler(0.0, 0.0, np.pi / 2 - psi)
+    assert min(np.abs(qe - want).max(), np.abs(qe + want).max()) < 1e-6
+    # extract_targets: piecewise-linear look-up == np.interp inside the table, linear extrapolation outside
+    t = np.cumsum(rng.uniform(0.05, 0.2, 40))
+    xs = rng.standard_normal((40, 13))
+    steps = np.cumsum(np.full(20, 0.05))
+    cur, seq = rm.extract_targets(t[3] + 0.01, t, xs, steps)
+    assert seq.shape == (21, 13)
+    for i in range(13):
+        np.testing.assert_allclose(seq[:, i], np.interp(np.concatenate(([t[3] + 0.01], t[3] + 0.01 + steps)), t, xs[:, i]),
+                                   atol=1e-5)
+    np.testing.assert_allclose(cur, seq[0])
+    _, late = rm.extract_targets(t[-1] - 0.2, t, xs, steps)
+    slope = (xs[-1] - xs[-2]) / (t[-1] - t[-2])
+    np.testing.assert_allclose(late[-1], xs[-1] + slope * (t[-1] - 0.2 + steps[-1] - t[-1]), atol=1e-4)
+    tv, sv = rm.parse_trajectory({"t": t, **{n: xs[:, i] for i, n in enumerate(rm.state_names)}})
+    np.testing.assert_array_equal(sv, xs)
