@@ -57,3 +57,74 @@ class SDESimulator:
         if return_particles:
             return xbuf.view(self.H + 1, n_x, P, self.N).permute(2, 3, 0, 1)
         return xbuf[self.H].view(n_x, P, self.N).mean(dim=2).t()
+
+
+# ---------------------------------------------------------------------------------------------
+# mbrl-lib ``ModelEnv`` contract (mbrlLibUtils/modified_model_env.py:12-57) around ``SDESimulator``
+# ---------------------------------------------------------------------------------------------
+def cartpole_swingup_reward(act, next_obs):
+    """``mbrlLibUtils/reward_functions.py:3-9`` on observations [x, xdot, sin th, cos th, thdot].  Kept verbatim:
+    the reference takes ``cos`` of observation 3, which already is ``cos th`` (sic)."""
+    assert next_obs.dim() == act.dim() == 2
+    return (torch.cos(next_obs[:, 3]) - 0.1 * torch.abs(next_obs[:, 0])).float().view(-1, 1)
+
+
+def cartpole_swingup_termination(act, next_obs):
+    """``mbrlLibUtils/termination_functions.py:3-14``: done when |x| >= 120."""
+    assert next_obs.dim() == 2
+    x = next_obs[:, 0]
+    return (~((x > -120.0) & (x < 120.0)))[:, None]
+
+
+def cartpole_obs(state):
+    """``CartPoleSDEEnv.get_obs`` (cartpole_sde.py:255-257): [x, xdot, sin th, cos th, thdot]."""
+    return torch.stack((state[..., 0], state[..., 1], torch.sin(state[..., 2]), torch.cos(state[..., 2]), state[..., 3]), dim=-1)
+
+
+class SDEModelEnv:
+    """``reset(initial_states) -> model_state`` / ``step(actions, model_state) -> (next_obs, rewards, dones,
+    model_state)`` / ``evaluate_action_sequences`` with the nSDE as the dynamics model.  States are the SDE
+    states; ``obs_fn`` maps them to what the reward / termination functions expect."""
+
+    def __init__(self, simulator, termination_fn, reward_fn, obs_fn=None, seed=0):
+        self.sim = simulator
+        self.termination_fn, self.reward_fn = termination_fn, reward_fn
+        self.obs_fn = obs_fn if obs_fn is not None else (lambda s: s)
+        self._rng = R.PRNGKey(seed)
+
+    def _next_key(self):
+        ks = R.split(self._rng)
+        self._rng = ks[0]
+        return ks[1]
+
+    def reset(self, initial_states):
+        return {"state": as_f32(initial_states).reshape(-1, self.sim.engine.n_x).clone()}
+
+    def step(self, actions, model_state):
+        """One simulator step for every state of the batch (mean over the particles, as ``_my_pred_fn``)."""
+        actions = as_f32(actions).reshape(model_state["state"].shape[0], -1)
+        nxt = self.sim.predict(model_state["state"], actions, self._next_key())
+        obs = self.obs_fn(nxt)
+        rewards = self.reward_fn(actions, obs)
+        dones = self.termination_fn(actions, obs)
+        return obs, rewards, dones, {"state": nxt}
+
+    def evaluate_action_sequences(self, action_sequences, initial_state, num_particles):
+        """Total reward of every candidate sequence ``[B, H, n_u]`` from one start state, averaged over
+        ``num_particles`` particles -- ONE rollout launch (B problems x particles x H steps) instead of H model
+        steps (mbrl ``ModelEnv.evaluate_action_sequences``); rewards stop accumulating after termination."""
+        seqs = as_f32(action_sequences)
+        B, Hs, _ = seqs.shape
+        sim = self.sim
+        if (sim.H, sim.N) != (Hs, num_particles):
+            sim = SDESimulator(type(self.sim.model), self.sim.params_model, self.sim.pk, num_particles=num_particles,
+                               horizon=Hs)
+            self._seq_sim = sim
+        x0 = as_f32(initial_state).reshape(1, -1).expand(B, -1)
+        traj = sim.predict(x0, seqs, self._next_key(), return_particles=True)  # [B, N, H+1, n_x]
+        obs = self.obs_fn(traj[:, :, 1:, :]).reshape(B * num_particles * Hs, -1)
+        act = seqs[:, None, :, :].expand(B, num_particles, Hs, seqs.shape[-1]).reshape(B * num_particles * Hs, -1)
+        rew = self.reward_fn(act, obs).view(B, num_particles, Hs)
+        done = self.termination_fn(act, obs).view(B, num_particles, Hs)
+        alive = (torch.cumsum(done.to(torch.int32), dim=2) - done.to(torch.int32)) == 0  # the terminal step still counts
+        return (rew * alive).sum(dim=2).mean(dim=1)

@@ -227,3 +227,56 @@ def test_simulator_adapter(cuda):
     for p in (0, 17, 999):
         w, _ = orc.sample_rollouts(om, obs[p], act[p][None], keys[p], 10)
         np.testing.assert_allclose(nxt[p].cpu().numpy(), w[:, -1].mean(0).numpy(), rtol=2e-5, atol=2e-6)
+
+
+def test_model_env_adapter(cuda):
+    """mbrl ModelEnv contract around the simulator: step() chains keys like CartPoleSDEEnv.step_dynamics
+    (cartpole_sde.py:243-253), evaluate_action_sequences() equals stepping the same particles one by one."""
+    import os
+    from sde4mbrl_b200 import io, random as R
+    from sde4mbrl_b200.simulator import (SDEModelEnv, SDESimulator, cartpole_obs, cartpole_swingup_reward,
+                                         cartpole_swingup_termination)
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nn, nominal = io.load_npz_fixture(os.path.join(gold, "ref_weights_cartpole_bb_learned_si.npz"))
+    sim = SDESimulator(sde_models.CartPoleSDE, nominal, nn, num_particles=5, tau=0.02, horizon=1)
+    env = SDEModelEnv(sim, cartpole_swingup_termination, cartpole_swingup_reward, obs_fn=cartpole_obs, seed=10)
+    rng = np.random.default_rng(1)
+    P = 64
+    s0 = rng.uniform(-1, 1, (P, 4)).astype(np.float32) * np.array([2, 3, np.pi, 6], np.float32)
+    act = rng.uniform(-1, 1, (P, 1)).astype(np.float32)
+    ms = env.reset(s0)
+    obs, rew, done, ms2 = env.step(act, ms)
+    assert tuple(obs.shape) == (P, 5) and tuple(rew.shape) == (P, 1) and tuple(done.shape) == (P, 1)
+    # the step used split(PRNGKey(10))[1], one key per state split from it, mean over 5 particles
+    k = tf.split(tf.PRNGKey(10))[1]
+    keys = tf.split(k, P)
+    pm = dict(nominal, horizon=1, num_particles=5, stepsize=0.02)
+    om = orc.make_model("cart_pole_sde", pm, nn)
+    for p in (0, 31, 63):
+        w, _ = orc.sample_rollouts(om, s0[p], act[p][None], keys[p], 5)
+        nxt = w[:, -1].mean(0).numpy()
+        np.testing.assert_allclose(ms2["state"][p].cpu().numpy(), nxt, rtol=2e-5, atol=2e-6)
+        # (sic) the reference takes the cosine of observation 3, which already is cos(theta)
+        np.testing.assert_allclose(float(rew[p]), np.cos(np.cos(nxt[2])) - 0.1 * abs(nxt[0]), rtol=1e-4, atol=1e-5)
+    assert not bool(done.any())
+    far = s0.copy()
+    far[0, 0] = 500.0
+    _, _, d2, _ = env.step(act, env.reset(far))
+    assert bool(d2[0]) and not bool(d2[1:].any())
+    # candidate action sequences: one launch (B x particles x H) == per-particle trajectories rewarded step by step
+    B, Hs, Np = 16, 12, 3
+    seqs = rng.uniform(-1, 1, (B, Hs, 1)).astype(np.float32)
+    env2 = SDEModelEnv(sim, cartpole_swingup_termination, cartpole_swingup_reward, obs_fn=cartpole_obs, seed=4)
+    tot = env2.evaluate_action_sequences(seqs, s0[0], Np)
+    assert tuple(tot.shape) == (B,)
+    k2 = tf.split(tf.PRNGKey(4))[1]
+    kb = tf.split(k2, B)
+    pm2 = dict(nominal, horizon=Hs, num_particles=Np, stepsize=0.02)
+    for kk in ("num_short_dt", "short_step_dt", "long_step_dt"):
+        pm2.pop(kk, None)
+    om2 = orc.make_model("cart_pole_sde", pm2, nn)
+    for b in (0, 7, 15):
+        w, _ = orc.sample_rollouts(om2, s0[0], seqs[b], kb[b], Np)
+        st = w[:, 1:].numpy()
+        r = (np.cos(np.cos(st[..., 2])) - 0.1 * np.abs(st[..., 0])).sum(1).mean()
+        np.testing.assert_allclose(float(tot[b]), r, rtol=2e-4)
