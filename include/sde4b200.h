@@ -231,6 +231,10 @@ int sde4_rng_normal(const uint32_t* key_host, uint64_t total, uint64_t offset, u
                     int32_t rng_mode, float* out, void* stream);
 /* out[num][2] = jax.random.split(key, num); key_dev is a DEVICE uint32[2] */
 int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint32_t* out, void* stream);
+/* batched forms for the key chains of the training loss (sde4mbrl/nsde.py:615,709,781): keys_dev[K][2] (device);
+ * out[K][num][2] = split(keys[k], num);  out[K][n] = normal(keys[k], (n,)) */
+int sde4_rng_split_many(const uint32_t* keys_dev, uint64_t K, int32_t num, int32_t rng_mode, uint32_t* out, void* stream);
+int sde4_rng_normal_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32_t rng_mode, float* out, void* stream);
 
 /* ---- training loss: create_model_loss_fn(...).loss_fn data term and jax.grad of it w.r.t. the model
  *      parameters, sde4mbrl/nsde.py:683-804 (sample_for_loss_computation), :1185-1203 (multi_sampling,

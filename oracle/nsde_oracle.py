@@ -589,3 +589,75 @@ def weight_penalty(tree, nominal, coeffs):
         for name in tree[mod]:
             tot = tot + ((tree[mod][name] - nominal[mod][name]) ** 2).sum() * coeffs[mod][name]
     return tot
+
+
+# ---------------------------------------------------------------------------------------------
+# distance-aware regulariser of the training loss
+# ---------------------------------------------------------------------------------------------
+def density_function(model, z):
+    """sigmoid(density_net(z) - 7)   (sde4mbrl/nsde.py:395)."""
+    return torch.sigmoid(model.density_net(z) - 7.0)
+
+
+def mu_coeff(model, z, dl):
+    """``mu_coeff_nn`` (nsde.py:657-680): constant, learned global scale, or exp(MLP) * mu_coeff."""
+    lm = dl["learn_mucoeff"]
+    mu0 = dl["mu_coeff"]
+    if lm["type"] == "constant":
+        return torch.as_tensor(mu0, dtype=z.dtype).expand(z.shape[:-1])
+    if lm["type"] == "global":
+        return (mu0 * torch.exp(_t(model.scalar("mu_coeff"), z))).expand(z.shape[:-1])
+    pre = "%s/~mu_coeff_nn/mu_coeff/~" % model.module_name
+    return torch.exp(mlp_apply(model.nn, pre, z, lm["activation_fn"])[..., 0]) * mu0
+
+
+def density_loss_terms(model, ymeas, uval, rng, N, dl, mode=tf.MODE_ORIGINAL):
+    """``density_loss`` (nsde.py:597-654) over the data points as ``sample_for_loss_computation`` calls it
+    (:771-804): for minibatch element b and particle n the key is split(split(split(rng,B)[b],N)[n],3)[2]
+    (:1196,:1187,:709), split over the Hd data steps (:781); each step splits once more and uses the SECOND key for
+    the ball (:615).  ymeas[B, Hd+1, n_y], uval[B, Hd, n_u] torch tensors.
+    Returns grad_norm[B,N] (mean over t), sconvex[B,N] (sum over t), mu[B,N] (mean), density[B,N] (mean)."""
+    B, Hd = ymeas.shape[0], ymeas.shape[1] - 1
+    ns = int(dl["ball_nsamples"])
+    kb = tf.split(rng, B, mode)
+    out = [[None] * N for _ in range(B)]
+    for b in range(B):
+        z = model.noise_aug_state_ctrl(ymeas[b, :-1], uval[b]).detach().requires_grad_(True)  # [Hd, dim]
+        dim = z.shape[-1]
+        den = density_function(model, z)
+        (gz,) = torch.autograd.grad(den.sum(), z, create_graph=True)
+        mu = mu_coeff(model, z, dl)
+        radius = _t(np.broadcast_to(np.asarray(dl["ball_radius"], np.float64), (dim,)).copy(), z)
+        kbn = tf.split(kb[b], N, mode)
+        for n in range(N):
+            kt = tf.split(tf.split(kbn[n], 3, mode)[2], Hd, mode)
+            ball = torch.stack([_t(tf.normal(tf.split(kt[t], 2, mode)[1], (ns, dim), mode), z) for t in range(Hd)]) * radius
+            den_ball = density_function(model, z[:, None, :] + ball)  # [Hd, ns]
+            cond = den_ball - den[:, None] - (gz[:, None, :] * ball).sum(-1) - 0.5 * mu[:, None] * (ball ** 2).sum(-1)
+            sconvex = (torch.clamp(cond, max=0.0) ** 2).sum(-1)
+            out[b][n] = ((gz ** 2).sum(-1).mean(), sconvex.sum(), mu.mean(), den.mean())
+    stack = lambda i: torch.stack([torch.stack([out[b][n][i] for n in range(N)]) for b in range(B)])
+    return stack(0), stack(1), stack(2), stack(3)
+
+
+def training_total(loss_params, dl, loss_data, grad_norm, sconvex, mu, w_loss):
+    """``total_sum`` of ``create_model_loss_fn.loss_fn`` (nsde.py:1203-1254)."""
+    lgd, lsc, mum = grad_norm.mean(1).mean(), sconvex.mean(1).mean(), mu.mean(1).mean()
+    mult = loss_params.get("pen_scvex_mult", 1.0)
+    tot = 0.0
+    if loss_params.get("pen_data", 0) > 0:
+        tot = tot + loss_data * loss_params["pen_data"]
+    if loss_params.get("pen_grad_density", 0) > 0:
+        p_mu = dl["mu_coeff"]
+        tot = tot + loss_params["pen_grad_density"] * p_mu * dl.get("grad_scaler", 1.0 / p_mu) * lgd * mult
+    if loss_params.get("pen_density_scvex", 0) > 0:
+        tot = tot + loss_params["pen_density_scvex"] * lsc * mult
+    lmu = 0.0
+    if loss_params.get("pen_mu_coeff", 0) > 0:
+        kind = loss_params.get("pen_mu_type", "quad_inv")
+        lmu = {"quad_inv": lambda: 1.0 / mum ** 2, "lin_inv": lambda: 1.0 / mum,
+               "exp_inv": lambda: torch.exp(-mum * loss_params["pen_mu_temp"])}[kind]()
+        tot = tot + lmu * loss_params["pen_mu_coeff"] * mult
+    if loss_params.get("pen_weights", 0) > 0:
+        tot = tot + loss_params["pen_weights"] * w_loss
+    return tot, {"gradDensity": lgd, "densitySCVEX": lsc, "muCoeff": mum, "lossMuCoeff": lmu}

@@ -100,6 +100,27 @@ __global__ void k_rng_split(const uint32_t* key, int num, int mode, uint32_t* ou
   out[2 * i + 1] = c1;
 }
 
+// batched forms (training-loss key chains, nsde.py:615,709,781): K keys at once
+__global__ void k_rng_split_many(const uint32_t* __restrict__ keys, unsigned long long K, int num, int mode,
+                                 uint32_t* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * (unsigned long long)num) return;
+  const unsigned long long k = i / num;
+  const uint32_t j = (uint32_t)(i - k * num);
+  uint32_t c0, c1;
+  jax_split(keys[2 * k], keys[2 * k + 1], j, (uint32_t)num, mode, c0, c1);
+  out[2 * i] = c0;
+  out[2 * i + 1] = c1;
+}
+
+__global__ void k_rng_normal_many(const uint32_t* __restrict__ keys, unsigned long long K, unsigned long long n, int mode,
+                                  float* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * n) return;
+  const unsigned long long k = i / n;
+  out[i] = bits_to_normal(jax_bits(keys[2 * k], keys[2 * k + 1], i - k * n, n, mode));
+}
+
 // ----------------------------------------------------------------------------
 // FP32 FMA peak micro-benchmark (roofline denominator)
 // ----------------------------------------------------------------------------

@@ -523,6 +523,27 @@ int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint3
   return SDE4_OK;
 }
 
+int sde4_rng_split_many(const uint32_t* keys_dev, uint64_t K, int32_t num, int32_t rng_mode, uint32_t* out, void* stream) {
+  if (!keys_dev || !out || num <= 0) return fail(SDE4_ERR_INVALID, "bad argument");
+  if (K == 0) return SDE4_OK;
+  const uint64_t tot = K * (uint64_t)num;
+  k_rng_split_many<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keys_dev, K, num, rng_mode, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+int sde4_rng_normal_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32_t rng_mode, float* out, void* stream) {
+  if (!keys_dev || !out) return fail(SDE4_ERR_INVALID, "bad argument");
+  if (K == 0 || n == 0) return SDE4_OK;
+  if (rng_mode == SDE4_RNG_ORIGINAL && n > 0xffffffffull) return fail(SDE4_ERR_UNSUPPORTED, "original layout beyond 2^32 elements");
+  const uint64_t tot = K * n;
+  k_rng_normal_many<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keys_dev, K, n, rng_mode, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
 static int apg_check(const sde4_apg_params* prm, const sde4_apg_state* st) {
   if (!prm) return fail(SDE4_ERR_INVALID, "null apg params");
   if (prm->P <= 0 || prm->H <= 0 || prm->n_opt <= 0 || prm->n_opt > SDE4_MAX_NOPT || prm->maxls < 0)

@@ -1,0 +1,162 @@
+"""Distance-aware regulariser of the training loss: gradient-norm, local strong-convexity hinge and
+mu-coefficient terms of ``ControlledSDE.density_loss`` / ``mu_coeff_nn`` / ``sample_for_loss_computation``
+and their weighting in ``create_model_loss_fn.loss_fn``
+(``sde4mbrl/nsde.py:597-680, 771-804, 1205-1254``).
+
+NOT the sequential hot path: the terms are evaluated at the DATA points (``ymeas[:-1]``, ``uVal``), i.i.d. over
+(minibatch, particle, time), with no rollout.  That is a batch of K = B*N*H_d*(1+ball_nsamples) independent
+evaluations of two small MLPs plus a second-order derivative (the parameter gradient of ``|grad_z density|^2``),
+i.e. plain library GEMMs + reverse-over-reverse differentiation -- the work the reference leaves to XLA.  Here it is
+torch (cuBLAS) on the device with ``torch.autograd``; what is hand-written is the bit-exact key chain and the ball
+noise (``sde4_rng_split_many`` / ``sde4_rng_normal_many``), so that the terms are comparable with the reference for
+the same ``rng``.
+"""
+import numpy as np
+import torch
+
+from . import random as _random
+from ._lib import Sde4Error
+
+_ACT = {"tanh": torch.tanh, "swish": torch.nn.functional.silu, "sigmoid": torch.sigmoid, "relu": torch.relu}
+
+
+def _mlp(tree, prefix, z, act_name):
+    """``hk.nets.MLP``: ``act(z @ w + b)`` for all but the last layer."""
+    act = _ACT[act_name]
+    n = 0
+    while "%s/linear_%d" % (prefix, n) in tree:
+        n += 1
+    if n == 0:
+        raise Sde4Error("no MLP parameters under " + prefix)
+    for k in range(n):
+        leaf = tree["%s/linear_%d" % (prefix, k)]
+        z = z @ leaf["w"] + leaf["b"]
+        if k + 1 < n:
+            z = act(z)
+    return z
+
+
+def reduced_inputs(model, x, u):
+    """``noise_aug_state_ctrl(x, u)`` (nsde.py:353-363) on batches: reduced state of the model, restricted to
+    ``indx_noise_in``."""
+    p = model.params
+    name = model.module_name
+    if name == "cart_pole_sde" and "state_scaling" in p:  # cartpole_sde.py:41
+        red = torch.stack((x[..., 1], torch.sin(x[..., 2]), torch.cos(x[..., 2]), x[..., 3]), dim=-1) / float(p["state_scaling"][-1])
+    elif name == "sde_rotor_model" and "state_scaling" in p:  # sde_rotor_model.py:139-144
+        red = x[..., :13] / float(max(p["state_scaling"]))
+    else:
+        red = x
+    nin = list(p["diffusion_density_nn"].get("indx_noise_in", range(model.n_x)))
+    z = red[..., nin] if len(nin) < red.shape[-1] else red
+    if p.get("control_dependent_noise", False):
+        raise Sde4Error("control_dependent_noise has no compiled kernel")
+    return z
+
+
+def init_mu_params(model, dl, rng):
+    """Parameters ``mu_coeff_nn`` adds to the tree (nsde.py:657-680)."""
+    lm = dl["learn_mucoeff"]
+    m = model.module_name
+    if lm["type"] == "constant":
+        return {}
+    if lm["type"] == "global":
+        return {m: {"mu_coeff": rng.uniform(-0.001, 0.001, ()).astype(np.float32)}}
+    iv = lm.get("init_value", 0.01)
+    nin = len(list(model.params["diffusion_density_nn"].get("indx_noise_in", range(model.n_x))))
+    dims = [nin] + list(lm["hidden_layers"]) + [1]
+    return {"%s/~mu_coeff_nn/mu_coeff/~/linear_%d" % (m, k): {"w": rng.uniform(-iv, iv, (dims[k], dims[k + 1])).astype(np.float32),
+                                                              "b": np.zeros(dims[k + 1], np.float32)}
+            for k in range(len(dims) - 1)}
+
+
+def density_keys(rng, B, N, Hd):
+    """rng_ball for every (b, n, t): ``split(rng, B)[b]`` (nsde.py:1196) -> ``split(., N)[n]`` (:1187) ->
+    ``split(., 3)[2]`` (:709) -> ``split(., Hd)[t]`` (:781) -> ``split(.)[1]`` (:615)."""
+    kb = _random.split(rng, B)
+    kbn = _random.split_many(kb, N)                      # [B, N, 2]
+    kd = _random.split_many(kbn, 3)[:, :, 2].contiguous()  # [B, N, 2]
+    kt = _random.split_many(kd, Hd)                      # [B, N, Hd, 2]
+    return _random.split_many(kt, 2)[..., 1, :].contiguous()
+
+
+def density_terms(model, tree, y, u, rng, N, dl):
+    """Per (minibatch element, particle) terms of ``sample_for_loss_computation`` (nsde.py:771-804).
+    ``tree``: torch parameter tree (requires_grad leaves), ``y[B, Hd+1, n_y]``, ``u[B, Hd, n_u]`` device tensors.
+    Returns ``grad_norm[B, N]`` (mean over time), ``sconvex[B, N]`` (sum over time), ``mu[B, N]`` (mean),
+    ``density[B, N]`` (mean)."""
+    if dl["learn_mucoeff"].get("quad_approx", False):
+        raise Sde4Error("density_loss with quad_approx (density_loss_theory) is not built")
+    B, Hd = y.shape[0], y.shape[1] - 1
+    m = model.module_name
+    dn = model.params["diffusion_density_nn"]["density_nn"]
+    pre = "%s/~construct_diffusion_density_nn/density/~" % m
+    act = dn.get("activation_fn", "tanh")
+
+    def density(zz):  # density_function, nsde.py:395
+        return torch.sigmoid(_mlp(tree, pre, zz, act)[..., 0] - 7.0)
+
+    z = reduced_inputs(model, y[:, :-1], u)  # [B, Hd, dim]: obs2state is the identity for the shipped models
+    z = z.detach().requires_grad_(True)
+    dim = z.shape[-1]
+    den = density(z)  # [B, Hd]
+    (gz,) = torch.autograd.grad(den.sum(), z, create_graph=True)  # rows are independent: d den_k / d z_k
+    grad_norm = (gz ** 2).sum(-1)  # [B, Hd]
+    ns = int(dl["ball_nsamples"])
+    radius = torch.as_tensor(np.broadcast_to(np.asarray(dl["ball_radius"], np.float32), (dim,)).copy(), device=y.device)
+    keys = density_keys(rng, B, N, Hd)  # [B, N, Hd, 2]
+    ball = _random.normal_many(keys, (ns, dim)) * radius  # [B, N, Hd, ns, dim]
+    zb = z[:, None, :, None, :] + ball
+    den_ball = density(zb)  # [B, N, Hd, ns]
+    lm = dl["learn_mucoeff"]
+    mu0 = float(dl["mu_coeff"])
+    if lm["type"] == "constant":
+        mu = torch.full_like(den, mu0)
+    elif lm["type"] == "global":
+        mu = (mu0 * torch.exp(tree[m]["mu_coeff"])).expand_as(den)
+    else:
+        mu = torch.exp(_mlp(tree, "%s/~mu_coeff_nn/mu_coeff/~" % m, z, lm["activation_fn"])[..., 0]) * mu0
+    cond = den_ball - den[:, None, :, None] - (gz[:, None, :, None, :] * ball).sum(-1) \
+        - 0.5 * mu[:, None, :, None] * (ball ** 2).sum(-1)
+    sconvex = (torch.clamp(cond, max=0.0) ** 2).sum(-1)  # [B, N, Hd]
+    expand = lambda a: a[:, None, :].expand(B, N, Hd)
+    return expand(grad_norm).mean(-1), sconvex.sum(-1), expand(mu).mean(-1), expand(den).mean(-1)
+
+
+def to_torch_tree(nn_params, device, names=("density", "mu_coeff")):
+    """float32 device copies (requires_grad) of the leaves the regulariser depends on."""
+    out = {}
+    for mod, leaves in nn_params.items():
+        if not (any(n in mod for n in names) or any(n in leaves for n in ("mu_coeff",))):
+            continue
+        out[mod] = {k: torch.as_tensor(np.asarray(v, np.float32), device=device).requires_grad_(True) for k, v in leaves.items()}
+    return out
+
+
+def weighted_terms(loss_params, dl, grad_norm, sconvex, mu):
+    """The regulariser's share of ``total_sum`` (nsde.py:1205-1250) and the logged scalars."""
+    loss_grad_density = grad_norm.mean(dim=1).mean()
+    loss_density_scvex = sconvex.mean(dim=1).mean()
+    mu_mean = mu.mean(dim=1).mean()
+    mult = loss_params.get("pen_scvex_mult", 1.0)
+    total = torch.zeros((), device=grad_norm.device)
+    if loss_params.get("pen_grad_density", 0) > 0:
+        p_mu = dl["mu_coeff"]
+        eff = loss_params["pen_grad_density"] * p_mu * dl.get("grad_scaler", 1.0 / p_mu)
+        total = total + eff * loss_grad_density * mult
+    if loss_params.get("pen_density_scvex", 0) > 0:
+        total = total + loss_params["pen_density_scvex"] * loss_density_scvex * mult
+    loss_mu = torch.zeros((), device=grad_norm.device)
+    if loss_params.get("pen_mu_coeff", 0) > 0:
+        kind = loss_params.get("pen_mu_type", "quad_inv")
+        if kind == "quad_inv":
+            loss_mu = 1.0 / mu_mean ** 2
+        elif kind == "lin_inv":
+            loss_mu = 1.0 / mu_mean
+        elif kind == "exp_inv":
+            loss_mu = torch.exp(-mu_mean * loss_params["pen_mu_temp"])
+        else:
+            raise ValueError("Unknown pen_mu_type: {}. Choose from quad_inv, lin_inv, exp_inv".format(kind))
+        total = total + loss_mu * loss_params["pen_mu_coeff"] * mult
+    return total, {"gradDensity": loss_grad_density, "densitySCVEX": loss_density_scvex, "muCoeff": mu_mean,
+                   "lossMuCoeff": loss_mu}

@@ -19,6 +19,7 @@ import torch
 
 from . import _lib as L
 from . import costs as _costs
+from . import density_loss as _density
 from . import random as _random
 from ._lib import Sde4Error
 from .engine import Engine, as_f32, as_key, is_host, host_f32
@@ -393,8 +394,10 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
     un-differentiated leaves get zeros).  Like the reference this MUTATES ``model_params`` /
     ``loss_params`` (nsde.py:1064-1134).
 
-    Not covered (each raises): ``density_loss`` terms with a non-zero penalty, ``num_sample2consider``
-    below the horizon, ``u_sampling_strategy='random'`` (they need more of jax.random)."""
+    The distance-aware regulariser (``density_loss`` gradient-norm / strong-convexity / mu terms) is evaluated by
+    ``density_loss.py`` at the data points with the reference's key chain.  Not covered (each raises):
+    ``num_sample2consider`` below the horizon (``jax.random.choice``), ``u_sampling_strategy='random'``,
+    ``learn_mucoeff.quad_approx``."""
     _check_constr(sde_constr)
     vprint = print if verbose else (lambda *a, **k: None)
     params_model = model_params
@@ -423,10 +426,18 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         params_model.pop(k, None)
     if "diffusion_density_nn" not in params_model or "density_nn" not in params_model["diffusion_density_nn"]:
         loss_params.pop("density_loss", None)
-    if "density_loss" in loss_params and (loss_params.get("pen_grad_density", 0) > 0 or
-                                          loss_params.get("pen_density_scvex", 0) > 0 or
-                                          loss_params.get("pen_mu_coeff", 0) > 0):
-        raise Sde4Error("density_loss terms (pen_grad_density / pen_density_scvex / pen_mu_coeff > 0) have no compiled kernel yet")
+    if "density_loss" in loss_params:  # nsde.py:1118-1132
+        _lm = loss_params["density_loss"].get("learn_mucoeff", False)
+        if type(_lm) is bool:
+            loss_params["density_loss"]["learn_mucoeff"] = {"quad_approx": False, "type": "constant" if not _lm else "global"}
+        loss_params["density_loss"]["learn_mucoeff"].setdefault("quad_approx", False)
+        loss_params["density_loss"]["learn_mucoeff"].setdefault("type", "constant")
+        params_model["density_loss"] = loss_params["density_loss"]
+        if loss_params["density_loss"]["learn_mucoeff"]["type"] == "constant":
+            loss_params["pen_mu_coeff"] = 0.0
+    else:
+        loss_params["pen_mu_coeff"] = 0.0
+    dl = loss_params.get("density_loss", None)
     if params_model.get("num_sample2consider", horizon) < horizon:
         raise Sde4Error("num_sample2consider < horizon (jax.random.choice subsampling) has no compiled kernel yet")
     strategy = params_model.get("u_sampling_strategy", "first")
@@ -435,6 +446,9 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
 
     model = sde_constr(params_model, **extra_args_sde_constr)
     nn_params = model.init_params(loss_params.get("seed", 0))
+    if dl is not None:  # parameters created by mu_coeff_nn (nsde.py:657-680)
+        for mod, leaves in _density.init_mu_params(model, dl, np.random.default_rng(loss_params.get("seed", 0) + 17)).items():
+            nn_params.setdefault(mod, {}).update(leaves)
     engine = Engine(model, _random.rng_mode())
     time_steps = compute_timesteps(params_model)
     n_feat = 5 if model.module_name == "cart_pole_sde" else model.n_x  # state_transform_for_loss
@@ -491,11 +505,23 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         total = 0.0
         if loss_params.get("pen_data", 0) > 0:
             total += loss_data * loss_params["pen_data"]
+        dinfo, dgrads = {}, {}
+        if dl is not None:
+            # distance-aware regulariser at the data points (density_loss.py): library GEMMs + autograd
+            tt = _density.to_torch_tree(_nn_params, y_values.device)
+            gn, sc, mu, _dv = _density.density_terms(model, tt, as_f32(y), as_f32(u), key, num_sample, dl)
+            dtot, dinfo = _density.weighted_terms(loss_params, dl, gn, sc, mu)
+            if want_grad and dtot.requires_grad:
+                dtot.backward()
+                dgrads = {mod: {k: v.grad for k, v in leaves.items() if v.grad is not None} for mod, leaves in tt.items()}
+            total += float(dtot)
+            dinfo = {k: float(v) for k, v in dinfo.items()}
         w_loss, wgrads = _penalty(_nn_params, want_grad) if pen_w > 0 else (0.0, {})
         if pen_w > 0:
             total += pen_w * w_loss
         info = {"totalLoss": total, "gradDensity": 0.0, "lossMuCoeff": 0.0, "densitySCVEX": 0.0, "weights": w_loss,
                 "muCoeff": 0.0, "dataLoss": loss_data}
+        info.update(dinfo)
         if not want_grad:
             return total, info, None
         gtree = model.unpack_grads(gpacked.cpu().numpy(), engine.desc)
@@ -508,6 +534,8 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
                     g = g + pd * gtree[mod][name]
                 if mod in wgrads and name in wgrads[mod]:
                     g = g + wgrads[mod][name]
+                if mod in dgrads and name in dgrads[mod]:
+                    g = g + dgrads[mod][name].cpu().numpy()
                 grads.setdefault(mod, {})[name] = g
         return total, info, grads
 

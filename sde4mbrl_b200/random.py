@@ -64,3 +64,24 @@ def normal(key, shape):
     k = (C.c_uint32 * 2)(int(kd[0]), int(kd[1]))
     L.check(L.load().sde4_rng_normal(k, n, 0, n, rng_mode(), _ptr(out), _stream()))
     return out.reshape(shape)
+
+
+def split_many(keys, num=2):
+    """``jax.vmap(lambda k: jax.random.split(k, num))(keys)``: keys[..., 2] -> int32 CUDA tensor [..., num, 2]."""
+    keys = as_key(keys)
+    lead = tuple(keys.shape[:-1])
+    flat = keys.reshape(-1, 2).contiguous()
+    out = torch.empty((flat.shape[0], num, 2), dtype=torch.int32, device=flat.device)
+    L.check(L.load().sde4_rng_split_many(_ptr(flat), flat.shape[0], int(num), rng_mode(), _ptr(out), _stream()))
+    return out.reshape(lead + (num, 2))
+
+
+def normal_many(keys, shape):
+    """``jax.vmap(lambda k: jax.random.normal(k, shape))(keys)``: keys[..., 2] -> float32 [..., *shape]."""
+    keys = as_key(keys)
+    lead = tuple(keys.shape[:-1])
+    flat = keys.reshape(-1, 2).contiguous()
+    n = int(np.prod(shape)) if len(shape) else 1
+    out = torch.empty((flat.shape[0], n), dtype=torch.float32, device=flat.device)
+    L.check(L.load().sde4_rng_normal_many(_ptr(flat), flat.shape[0], n, rng_mode(), _ptr(out), _stream()))
+    return out.reshape(lead + tuple(shape))

@@ -61,3 +61,58 @@ def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H):
     assert abs(t2 - total) < 1e-6 * abs(total)
     err, td = test_fn(nn, y, u, R.PRNGKey(5))
     assert set(td) == {"TestErrorData", "TestStdData"} and np.isfinite(err)
+
+
+@pytest.mark.parametrize("mu_type,N", [("dnn", 2), ("global", 1), ("constant", 1)])
+def test_density_regulariser_terms_and_grads(cuda, mu_type, N):
+    """Full training loss of cartpole_sde.yaml:95-137 (data term + distance-aware regulariser + weight penalty):
+    gradient-norm / strong-convexity / mu terms with the reference's key chain for the ball samples, and the
+    gradient w.r.t. every parameter, vs the oracle's float64 autograd."""
+    from sde4mbrl_b200 import nsde, random as R
+    B, H = 4, 8
+    pm = configs.cartpole_model(horizon=1, num_particles=1)
+    ow = [9, 5, 1, 1.0, 10]
+    lm = {"dnn": {"type": "dnn", "init_value": 0.3, "activation_fn": "tanh", "hidden_layers": [8, 8]},
+          "global": True, "constant": False}[mu_type]
+    lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 4,
+          "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 1e-3, "default_weights": 1.0,
+          "special_parameters_pen": {"scaler": 0, "density": 0},
+          "density_loss": {"learn_mucoeff": lm, "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4], "ball_nsamples": 6},
+          "pen_grad_density": 1.0, "pen_density_scvex": 1.0, "pen_mu_type": "lin_inv", "pen_mu_coeff": 1000.0,
+          "pen_scvex_mult": 0.01}
+    nn0, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.CartPoleSDE, verbose=False)
+    dl = lp["density_loss"]
+    assert dl["learn_mucoeff"]["type"] == mu_type and (lp["pen_mu_coeff"] == 0.0) == (mu_type == "constant")
+    nn = configs.random_params(sde_models.CartPoleSDE(pm), seed=4)
+    # spread the density output so that sigmoid(d - 7) and the hinge are active
+    nn["cart_pole_sde/~construct_diffusion_density_nn/density/~/linear_2"]["w"] *= np.float32(3.0)
+    mu_names = [m for m in nn0 if "mu_coeff" in m]
+    for m in mu_names:
+        nn[m] = {k: np.array(v) for k, v in nn0[m].items()}
+    if mu_type == "global":
+        nn["cart_pole_sde"]["mu_coeff"] = np.float32(0.2)
+    assert (len(mu_names) == 3) == (mu_type == "dnn")
+    rng = np.random.default_rng(0)
+    y = (rng.normal(0, 0.5, (B, H + 1, 4)) + np.array([0, 0, 3.0, 0])).astype(np.float32)
+    u = rng.uniform(-1, 1, (B, H, 1)).astype(np.float32)
+    total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(3))
+    tree = _tree64(nn)
+    om = orc.make_model("cart_pole_sde", pm, tree, torch.float64)
+    y64, u64 = torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64)
+    dw = torch.tensor(orc.loss_noise(tf.PRNGKey(3), B, N, H, 4), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, "cart_pole_sde", y64, u64, dw, ow)
+    gn, sc, mu, _ = orc.density_loss_terms(om, y64, u64, tf.PRNGKey(3), N, dl)
+    coeffs = {m: {k: (0.0 if ("scaler" in m or "scaler" in k or "density" in m) else 1.0) for k in d} for m, d in tree.items()}
+    nominal = {m: {k: torch.zeros_like(v) for k, v in d.items()} for m, d in tree.items()}
+    Lw = orc.weight_penalty(tree, nominal, coeffs)
+    Lt, oi = orc.training_total(lp, dl, Ld, gn, sc, mu, Lw)
+    Lt.backward()
+    assert float(oi["densitySCVEX"]) > 0 and float(oi["gradDensity"]) > 0  # the terms are exercised
+    for k in ("gradDensity", "densitySCVEX", "muCoeff"):
+        assert abs(info[k] - float(oi[k])) <= 2e-4 * abs(float(oi[k])) + 1e-12, k
+    assert abs(total - float(Lt)) < 5e-5 * abs(float(Lt))
+    gmax = max(float(v.grad.abs().max()) for d in tree.values() for v in d.values() if v.grad is not None)
+    for m, d in tree.items():
+        for k, v in d.items():
+            want = v.grad.numpy() if v.grad is not None else np.zeros(v.shape)
+            assert np.max(np.abs(grads[m][k] - want)) <= 3e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (m, k)

@@ -55,3 +55,24 @@ def test_normal_close(cuda, mode):
         assert abs(got.mean()) < 0.02 and abs(got.std() - 1.0) < 0.02
     finally:
         R.set_threefry_partitionable(False)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_batched_split_and_normal(cuda, mode):
+    """sde4_rng_split_many / sde4_rng_normal_many == vmap of jax.random.split / normal over a batch of keys."""
+    from sde4mbrl_b200 import random as R
+    R.set_threefry_partitionable(bool(mode))
+    try:
+        keys = tf.split(tf.PRNGKey(77), 9, mode)
+        got = R.split_many(keys, 5).cpu().numpy().view(np.uint32)
+        for k in range(9):
+            np.testing.assert_array_equal(got[k], tf.split(keys[k], 5, mode))
+        deep = R.split_many(keys.reshape(3, 3, 2), 2).cpu().numpy().view(np.uint32)
+        assert deep.shape == (3, 3, 2, 2)
+        np.testing.assert_array_equal(deep[1, 2], tf.split(keys[5], 2, mode))
+        z = R.normal_many(keys, (7, 3)).cpu().numpy()
+        for k in range(9):
+            want = tf.normal(keys[k], (7, 3), mode)
+            assert np.max(np.abs(z[k] - want) / np.maximum(np.abs(want), 1.0)) < 1e-6
+    finally:
+        R.set_threefry_partitionable(False)

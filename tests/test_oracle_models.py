@@ -96,3 +96,39 @@ def test_shipped_weights_pack_for_every_fixture():
         m = cls(nominal)
         packed = m.pack(nn)
         assert packed.dtype == np.float32 and np.isfinite(packed).all() and np.abs(packed).sum() > 0
+
+
+def test_density_regulariser_oracle_against_definitions():
+    """oracle.density_loss_terms vs the definitions (nsde.py:632-652) evaluated by hand for one (b, n, t):
+    finite-difference gradient of sigmoid(density_net - 7), the ball drawn from the documented key chain, the hinge."""
+    pm = configs.cartpole_model(horizon=1, num_particles=1)
+    nn = configs.random_params(sde_models.CartPoleSDE(pm), seed=2)
+    nn["cart_pole_sde/~construct_diffusion_density_nn/density/~/linear_2"]["w"] *= np.float32(3.0)
+    tree = {m: {k: torch.tensor(np.asarray(v), dtype=torch.float64) for k, v in d.items()} for m, d in nn.items()}
+    om = orc.make_model("cart_pole_sde", pm, tree, torch.float64)
+    dl = {"learn_mucoeff": {"type": "constant", "quad_approx": False}, "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4],
+          "ball_nsamples": 5}
+    rng = np.random.default_rng(0)
+    B, N, Hd = 2, 2, 3
+    y = torch.tensor(rng.normal(0, 0.5, (B, Hd + 1, 4)) + np.array([0, 0, 3.0, 0]))
+    u = torch.tensor(rng.uniform(-1, 1, (B, Hd, 1)))
+    key = tf.PRNGKey(9)
+    gn, sc, mu, den = orc.density_loss_terms(om, y, u, key, N, dl)
+    assert tuple(gn.shape) == (B, N) and float(mu[0, 0]) == 10.0 and bool((sc >= 0).all())
+    # by hand for b = 1, n = 1
+    b, n = 1, 1
+    f = lambda z: float(orc.density_function(om, torch.tensor(z)))
+    gsum, ssum = 0.0, 0.0
+    kt = tf.split(tf.split(tf.split(tf.split(key, B)[b], N)[n], 3)[2], Hd)
+    for t in range(Hd):
+        z = om.noise_aug_state_ctrl(y[b, t], u[b, t]).numpy()
+        g = np.array([(f(z + 1e-6 * e) - f(z - 1e-6 * e)) / 2e-6 for e in np.eye(3)])
+        gsum += (g ** 2).sum()
+        ball = tf.normal(tf.split(kt[t])[1], (5, 3)).astype(np.float64) * np.array([0.1, 0.1, 0.4])
+        for j in range(5):
+            cond = f(z + ball[j]) - f(z) - g @ ball[j] - 0.5 * 10.0 * (ball[j] ** 2).sum()
+            ssum += min(cond, 0.0) ** 2
+    assert abs(float(gn[b, n]) - gsum / Hd) <= 1e-6 * gsum / Hd
+    assert abs(float(sc[b, n]) - ssum) <= 1e-6 * ssum + 1e-15
+    # both particles see the same data points, different balls
+    assert float(gn[b, 0]) == float(gn[b, 1]) and float(sc[b, 0]) != float(sc[b, 1])
