@@ -311,6 +311,28 @@ def main():
             train_extra = {"batch": BT, "particles": 1, "horizon": HT, "ms_fwd_bwd": tm,
                            "particle_steps_per_s": BT * HT / (tm * 1e-3),
                            "fp32_tflops_algorithmic": 3.0 * 3135.0 * BT * HT / (tm * 1e-3) / 1e12}
+            # the complete loss_fn of cartpole_sde.yaml:95-137 through the public API: data term (above) +
+            # distance-aware regulariser at the data points (20 ball samples) + weight penalty, value and gradient
+            import contextlib as _cl, io as _io2
+            pml = configs.cartpole_model(horizon=1, num_particles=1)
+            lpl = {"seed": 0, "stepsize": 0.02, "data_stepsize": 0.02, "num_particles": 1, "num_particles_test": 1, "horizon": HT,
+                   "obs_weights": [9, 5, 1, 1.0, 10], "pen_data": 1.0, "pen_weights": 1e-3, "default_weights": 1.0,
+                   "special_parameters_pen": {"scaler": 0, "density": 0},
+                   "density_loss": {"learn_mucoeff": {"type": "dnn", "init_value": 0.01, "activation_fn": "tanh", "hidden_layers": [8, 8]},
+                                    "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4], "ball_nsamples": 20},
+                   "pen_grad_density": 1.0, "pen_density_scvex": 1.0, "pen_mu_type": "lin_inv", "pen_mu_coeff": 1000.0,
+                   "pen_scvex_mult": 0.01}
+            with _cl.redirect_stdout(_io2.StringIO()):
+                nnl, loss_fn_l, _, _ = nsde.create_model_loss_fn(pml, lpl, sde_constr=sde_models.CartPoleSDE, verbose=False)
+            tws = []
+            for rep in range(5):
+                t0 = time.perf_counter()
+                tot_l, info_l, grads_l = loss_fn_l.value_and_grad(nnl, ym, ut, R.PRNGKey(rep))
+                torch.cuda.synchronize()
+                if rep > 1:
+                    tws.append((time.perf_counter() - t0) * 1e3)
+            train_extra["ms_full_loss_value_and_grad_api"] = float(np.mean(tws))
+            train_extra["full_loss_terms"] = {k: float(v) for k, v in info_l.items()}
         except Exception as ex:
             train_extra = {"error": repr(ex)}
     # ---- BASELINE configs[4] (first half): cartpole nSDE as an MBRL simulator, 2^20 start states x
