@@ -13,7 +13,7 @@ y0m = np.tile(w["y0"], (P, 1)); y0m[:, 3:6] += rng.normal(0, 0.05, (P, 3)).astyp
 keys = np.stack([np.zeros(P, np.uint32), np.arange(P, dtype=np.uint32)], axis=1)
 xref = np.tile(w["xref"][:1], (HM + 1, 1))
 n_part = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-combos = [dict(cand=c, xv=x, y=y) for c, x, y in [(0, 0, 0), (1, 8, 8), (4, 8, 8), (8, 8, 8), (4, 4, 8), (4, 4, 4), (1, 4, 8), (1, 1, 1), (1, 1, 4), (1, 1, 8)]]
+combos = [dict(cand=0, xv=0, y=0)] if "--default-only" in sys.argv else [dict(cand=c, xv=x, y=y) for c, x, y in [(0, 0, 0), (1, 8, 8), (4, 8, 8), (8, 8, 8), (4, 4, 8), (4, 4, 4), (1, 4, 8), (1, 1, 1), (1, 1, 4), (1, 1, 8)]]
 for lanes in combos:
     pmm = configs.hexa_model(horizon=HM, num_particles=n_part, stepsize=0.05)
     mpcm = configs.hexa_mpc(horizon=HM, dt=0.05, num_particles=n_part, max_iter=20)

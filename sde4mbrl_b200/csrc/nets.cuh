@@ -54,10 +54,11 @@ struct Scratch {
   float* base;
   int bs;
   static constexpr int SLOT_H = 0;   // activations feeding the rolled row loop
-  static constexpr int SLOT_D1 = 1;  // act'(a1) kept for the backward sweep
-  static constexpr int SLOT_D2 = 2;  // act'(a2)
-  static constexpr int SLOT_X = 3;   // noise dw[] / misc (NX <= 16 entries)
-  static constexpr int NSLOTS = 4;
+  static constexpr int SLOT_X = 1;   // noise dw[] / misc (NX <= 16 entries)
+  static constexpr int SLOT_D1 = 2;  // act'(a1) kept for the backward sweep
+  static constexpr int SLOT_D2 = 3;  // act'(a2)
+  static constexpr int NSLOTS = 4;      // kernels with a backward sweep
+  static constexpr int NSLOTS_FWD = 2;  // forward-only kernels (rollout, value-only cost): 2x the resident CTAs
   SDE4_DEV float* slot(int s) const { return base + (size_t)s * MAXW * bs; }
   // parameter-gradient streams (training-loss kernel only, DUMP evaluators): for network `slot` the
   // rows [in | h1 | h2 | c1 | g2 | gout] of this thread's (step, sample) column, see wgrad in misc_kernels.cuh

@@ -31,19 +31,20 @@ std::vector<ArchEntry>& arch_table();
 
 // dynamic shared memory: parameter image + derived constants + per-thread scratch columns
 template <class M>
-constexpr size_t smem_bytes(int threads) {
+constexpr size_t smem_bytes(int threads, bool backward = true) {
   using A = typename M::A;
   constexpr int L = M::Ev::L;
-  return sizeof(float) * ((size_t)A::smem_floats(L) + (L == 1 ? (size_t)Scratch::NSLOTS * MAXW * threads : 0));
+  const size_t slots = backward ? Scratch::NSLOTS : Scratch::NSLOTS_FWD;
+  return sizeof(float) * ((size_t)A::smem_floats(L) + (L == 1 ? slots * MAXW * threads : 0));
 }
 
 template <class M>
 cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
-  const size_t sm = smem_bytes<M>(threads);
+  const size_t sm = smem_bytes<M>(threads, false);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256));
+    cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256, false));
     attr_set = true;
   }
   k_rollout<M><<<blocks, threads, sm, s>>>(d, a);
@@ -54,7 +55,7 @@ template <class M>
 cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td,
                           const CostK& a, bool grad, bool constr, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
-  const size_t sm = smem_bytes<M>(threads);
+  const size_t sm = smem_bytes<M>(threads, grad);
   static bool attr_set = false;
   if (!attr_set) {
     const int mx = (int)smem_bytes<M>(256);

@@ -514,7 +514,7 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
             if want_grad and dtot.requires_grad:
                 dtot.backward()
                 dgrads = {mod: {k: v.grad for k, v in leaves.items() if v.grad is not None} for mod, leaves in tt.items()}
-            total += float(dtot)
+            total += float(dtot.detach())
             dinfo = {k: float(v) for k, v in dinfo.items()}
         w_loss, wgrads = _penalty(_nn_params, want_grad) if pen_w > 0 else (0.0, {})
         if pen_w > 0:
