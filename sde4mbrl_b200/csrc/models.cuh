@@ -42,19 +42,11 @@ struct Arch {
   static constexpr int N_DERIVED = up4(2 * NO);
   static constexpr int SMEM_FLOATS = PARAM_TOTAL + N_DERIVED;
   static constexpr int MACS = DNet::MACS + NetA::MACS + NetB::MACS;
-  // lane-split kernels keep a bank-spread copy of every w1 (see nets.cuh, EvL) after the image
-  template <class N>
-  static constexpr int w1p_floats(int L) {
-    return L < 0 ? 1 : 0;  // (the row-split variant needed a bank-spread copy of w1; the output-split one does not)
-  }
-  static constexpr int off_w1p(int slot, int L) {
-    return SMEM_FLOATS + (slot > 0 ? w1p_floats<DNet>(L) : 0) + (slot > 1 ? w1p_floats<NetA>(L) : 0);
-  }
-  static constexpr int smem_floats(int L) { return off_w1p(2, L) + w1p_floats<NetB>(L); }
+  static constexpr int smem_floats(int /*L*/) { return SMEM_FLOATS; }
   template <int SLOT, int L>
   SDE4_DEV static NetRef ref(const float* W) {
     constexpr int off = SLOT == 0 ? OFF_DENSITY : (SLOT == 1 ? OFF_NET_A : OFF_NET_B);
-    return NetRef{SLOT, W + off, W + off_w1p(SLOT, L)};
+    return NetRef{SLOT, W + off};
   }
 
   static bool matches(const sde4_model_desc& d) {

@@ -301,7 +301,6 @@ SDE4_DEV void mlp_scalar_value_grad(const float* W, const Scratch& sc, const flo
 struct NetRef {
   int slot;          // 0 density, 1 net A, 2 net B
   const float* w;    // packed network image (layout above)
-  const float* w1p;  // EvL only: copy of w1 with a 4-float gap after every H1/L rows (bank spread)
 };
 
 template <bool DUMP>
@@ -338,8 +337,6 @@ using Ev1P = Ev1T<true>;
 //            every lane forms its own block of outputs from its column chunk of w1;
 //   layer 3: partial dot products over the own block + butterfly all-reduce.
 // The backward sweep mirrors this with the transposed products.
-constexpr int MAXB = 8;  // largest per-lane block (MAXW / smallest L >= 4)
-
 template <int L_>
 struct EvL {
   static constexpr int L = L_;
@@ -354,21 +351,6 @@ struct EvL {
     return N::H1 % L == 0 && N::H2 % L == 0;
   }
 
-  // acc[0..LEN) summed over the L lanes; lane l ends with elements [l*LEN/L, (l+1)*LEN/L) in acc[0..LEN/L)
-  template <int LEN>
-  SDE4_DEV static void reduce_scatter(float (&acc)[LEN], int l) {
-#pragma unroll
-    for (int mask = L / 2, n = LEN; mask >= 1; mask >>= 1, n >>= 1) {
-      const bool up = (l & mask) != 0;
-#pragma unroll
-      for (int q = 0; q < n / 2; ++q) {
-        const float lo = acc[q], hi = acc[q + n / 2];
-        const float send = up ? lo : hi;
-        const float keep = up ? hi : lo;
-        acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
-      }
-    }
-  }
   SDE4_DEV static float all_reduce(float v) {
 #pragma unroll
     for (int mask = L / 2; mask >= 1; mask >>= 1) v += __shfl_xor_sync(0xffffffffu, v, mask);
