@@ -46,6 +46,11 @@ SDE4_DEV float fast_rcp(float x) {
   return y;
 }
 
+SDE4_DEV float fast_sqrt(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 SDE4_DEV float sigmoidf_(float a) { return fast_rcp(1.0f + fast_ex2(a * -1.44269504088896341f)); }
 
 // tanh(a) = 1 - 2/(exp(2a) + 1): 2 MUFU + 3 FP32 ops, absolute error ~1.5e-7 (saturates correctly
@@ -111,22 +116,21 @@ SDE4_HD void threefry2x32(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, ui
   o1 = x1;
 }
 
-// element j of random_bits(key, (total,)) -- 32-bit, both jax layouts
+// element j of random_bits(key, (total,)) -- 32-bit, both jax layouts.  Branch free (ONE threefry instance,
+// selects around it) so that it can be scheduled inside a straight-line block:
+//   partitionable: counter (hi32(j), lo32(j)), word = o0 ^ o1
+//   original:      counts iota(total) (padded with one 0 if odd) hashed by halves: element j < half is word 0 of
+//                  the block (j, j + half), element j >= half is word 1 of the block (j - half, j)
 SDE4_HD uint32_t jax_bits(uint32_t k0, uint32_t k1, uint64_t j, uint64_t total, int mode) {
-  uint32_t o0, o1;
-  if (mode == SDE4_RNG_PARTITIONABLE) {
-    threefry2x32(k0, k1, (uint32_t)(j >> 32), (uint32_t)j, o0, o1);
-    return o0 ^ o1;
-  }
-  // original: counts iota(total) (padded with one 0 if odd) hashed by halves
+  const bool part = mode == SDE4_RNG_PARTITIONABLE;
   const uint64_t half = (total + 1) >> 1;
-  if (j < half) {
-    const uint64_t hi = j + half;
-    threefry2x32(k0, k1, (uint32_t)j, hi < total ? (uint32_t)hi : 0u, o0, o1);
-    return o0;
-  }
-  threefry2x32(k0, k1, (uint32_t)(j - half), (uint32_t)j, o0, o1);
-  return o1;
+  const bool low = j < half;
+  const uint64_t hi = j + half;
+  const uint32_t c0 = part ? (uint32_t)(j >> 32) : (low ? (uint32_t)j : (uint32_t)(j - half));
+  const uint32_t c1 = (part || !low) ? (uint32_t)j : (hi < total ? (uint32_t)hi : 0u);
+  uint32_t o0, o1;
+  threefry2x32(k0, k1, c0, c1, o0, o1);
+  return part ? (o0 ^ o1) : (low ? o0 : o1);
 }
 
 // child `i` of jax.random.split(key, num)
@@ -140,35 +144,32 @@ SDE4_HD void jax_split(uint32_t k0, uint32_t k1, uint32_t i, uint32_t num, int m
   c1 = jax_bits(k0, k1, 2ull * i + 1, 2ull * num, SDE4_RNG_ORIGINAL);
 }
 
-// XLA float32 erf_inv (Giles) -- see SURVEY appendix F
+// XLA float32 erf_inv (Giles) -- see SURVEY appendix F.  Both polynomial branches are evaluated and selected
+// (the tail one, |x| > 0.9966, is rare but a data-dependent branch would split the caller's basic block).
 SDE4_DEV float erfinv_f32(float x) {
   // XLA evaluates -log1p(-(x*x)) with the product rounded first; keep that (no FMA contraction)
-  float w = -__logf(1.0f - __fmul_rn(x, x));
-  float p;
-  if (w < 5.0f) {
-    w = w - 2.5f;
-    p = 2.81022636e-08f;
-    p = fmaf(p, w, 3.43273939e-07f);
-    p = fmaf(p, w, -3.5233877e-06f);
-    p = fmaf(p, w, -4.39150654e-06f);
-    p = fmaf(p, w, 0.00021858087f);
-    p = fmaf(p, w, -0.00125372503f);
-    p = fmaf(p, w, -0.00417768164f);
-    p = fmaf(p, w, 0.246640727f);
-    p = fmaf(p, w, 1.50140941f);
-  } else {
-    w = sqrtf(w) - 3.0f;
-    p = -0.000200214257f;
-    p = fmaf(p, w, 0.000100950558f);
-    p = fmaf(p, w, 0.00134934322f);
-    p = fmaf(p, w, -0.00367342844f);
-    p = fmaf(p, w, 0.00573950773f);
-    p = fmaf(p, w, -0.0076224613f);
-    p = fmaf(p, w, 0.00943887047f);
-    p = fmaf(p, w, 1.00167406f);
-    p = fmaf(p, w, 2.83297682f);
-  }
-  return p * x;
+  const float w = -__logf(1.0f - __fmul_rn(x, x));
+  const float wc = w - 2.5f;
+  float p = 2.81022636e-08f;
+  p = fmaf(p, wc, 3.43273939e-07f);
+  p = fmaf(p, wc, -3.5233877e-06f);
+  p = fmaf(p, wc, -4.39150654e-06f);
+  p = fmaf(p, wc, 0.00021858087f);
+  p = fmaf(p, wc, -0.00125372503f);
+  p = fmaf(p, wc, -0.00417768164f);
+  p = fmaf(p, wc, 0.246640727f);
+  p = fmaf(p, wc, 1.50140941f);
+  const float wt = fast_sqrt(fmaxf(w, 0.0f)) - 3.0f;  // MUFU.SQRT (<= 2 ulp); IEEE sqrtf carries a slow-path branch
+  float r = -0.000200214257f;
+  r = fmaf(r, wt, 0.000100950558f);
+  r = fmaf(r, wt, 0.00134934322f);
+  r = fmaf(r, wt, -0.00367342844f);
+  r = fmaf(r, wt, 0.00573950773f);
+  r = fmaf(r, wt, -0.0076224613f);
+  r = fmaf(r, wt, 0.00943887047f);
+  r = fmaf(r, wt, 1.00167406f);
+  r = fmaf(r, wt, 2.83297682f);
+  return (w < 5.0f ? p : r) * x;
 }
 
 // jax.random.normal transform of one 32-bit word

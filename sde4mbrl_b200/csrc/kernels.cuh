@@ -166,6 +166,40 @@ SDE4_DEV void draw_noise(const sde4_model_desc& d, int noise_mode, int rng_mode,
   }
 }
 
+// ---- lane-split kernels with in-kernel threefry noise (template flag TFP): the noise of step t+1 is generated
+// while step t is evaluated.  Everything below is branch free, so that the integer threefry chain and the
+// floating-point step end up in ONE basic block and ptxas interleaves them (the ALU and FMA pipes run side by side).
+template <class M>
+struct NoiseLanes {
+  static constexpr int NX = M::NX, L = M::Ev::L, PER = (NX + L - 1) / L;
+  // lane l's elements l, l+L, ... of dw_t
+  SDE4_DEV static void gen(uint32_t b0, uint32_t b1, int rng_mode, uint32_t nzmask, int t, int H, int l,
+                           float (&v)[PER]) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = l + q * L;
+      const bool valid = i < NX && ((nzmask >> i) & 1u);
+      const int ii = valid ? i : 0;
+      const float z = bits_to_normal(jax_bits(b0, b1, (uint64_t)t * NX + ii, (uint64_t)H * NX, rng_mode));
+      v[q] = valid ? z : 0.0f;
+    }
+  }
+  SDE4_DEV static void distribute(const float (&v)[PER], float (&dw)[NX]) {
+    const int base = (threadIdx.x & 31) & ~(L - 1);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) dw[i] = __shfl_sync(0xffffffffu, v[i / L], base + (i % L));
+  }
+  // keep[i*G] = dw_i for the backward sweep, written by the owning lane
+  SDE4_DEV static void keep(const float (&v)[PER], float* kp, unsigned G, uint32_t nzmask, int l, bool active) {
+    float* row = kp + (size_t)l * G;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = l + q * L;
+      if (active && i < NX && ((nzmask >> i) & 1u)) row[(size_t)(q * L) * G] = v[q];
+    }
+  }
+};
+
 // One Euler-Maruyama step in place: x <- proj(x + f dt + sigma dw)   (sde_solver.py:301-304)
 template <class M>
 SDE4_DEV void em_step(const float* W, Tctx<M>& tc, const sde4_model_desc& d, float (&x)[M::NX],
@@ -230,10 +264,11 @@ SDE4_DEV uint32_t noise_mask(const sde4_model_desc& d) {
 // ----------------------------------------------------------------------------
 // K1: forward rollout
 // ----------------------------------------------------------------------------
-template <class M>
+template <class M, bool TFP = false>
 __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_model_desc d,
                                                   const __grid_constant__ RolloutK a) {
   constexpr int NX = M::NX, NU = M::NU;
+  static_assert(!TFP || M::Ev::L > 1, "the pipelined-noise variant is a lane-split kernel");
   extern __shared__ __align__(16) float W[];
   __shared__ __align__(8) uint64_t mbar;
   Tctx<M> tc;
@@ -245,19 +280,27 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = __ldg(a.y0 + (size_t)p * NX + i);
   store_state<M>(a.xevol + g, a.G, x, tc.l, active);
-  const bool noisy = a.noise_mode != SDE4_NOISE_NONE;
+  const bool noisy = TFP ? true : a.noise_mode != SDE4_NOISE_NONE;
   const uint32_t nzmask = noise_mask<NX>(d);
   uint32_t b0 = 0, b1 = 0;
-  if (a.noise_mode == SDE4_NOISE_THREEFRY) {
+  if (TFP || a.noise_mode == SDE4_NOISE_THREEFRY) {
     const uint32_t* k = a.key + (size_t)p * a.key_sp;
     brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1);
   }
   const float* up = a.u + (size_t)p * a.u_sp;
+  using NL = NoiseLanes<M>;
+  float vn[NL::PER];
+  if constexpr (TFP) NL::gen(b0, b1, a.rng_mode, nzmask, 0, a.H, tc.l, vn);
   for (int t = 0; t < a.H; ++t) {
     float u[NU], dw[NX];
 #pragma unroll
     for (int j = 0; j < NU; ++j) u[j] = __ldg(up + (size_t)t * a.u_st + (size_t)j * a.u_sj);
-    if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, (unsigned)a.G, g, nzmask, tc, dw, nullptr);
+    if constexpr (TFP) {
+      NL::distribute(vn, dw);
+      NL::gen(b0, b1, a.rng_mode, nzmask, t + 1 < a.H ? t + 1 : t, a.H, tc.l, vn);  // overlaps the step below
+    } else {
+      if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, (unsigned)a.G, g, nzmask, tc, dw, nullptr);
+    }
     float aux;
     em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
     store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
@@ -273,7 +316,7 @@ SDE4_DEV float warp_sum(float v) {
   return v;
 }
 
-template <class M, bool GRAD, bool CONSTR>
+template <class M, bool GRAD, bool CONSTR, bool TFP = false>
 __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model_desc d,
                                                const __grid_constant__ sde4_cost_desc cd,
                                                const __grid_constant__ sde4_cost_desc td,
@@ -292,7 +335,8 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   const int pd = p % a.data_mod;  // stacked candidate evaluations share the problem data
   const float* op = a.opt + (size_t)p * a.o_sp;
   const float* xr = a.xref + (size_t)pd * a.xref_sp;
-  const bool noisy = a.noise_mode != SDE4_NOISE_NONE;
+  static_assert(!TFP || L > 1, "the pipelined-noise variant is a lane-split kernel");
+  const bool noisy = TFP ? true : a.noise_mode != SDE4_NOISE_NONE;
   const uint32_t nzmask = noise_mask<NX>(d);
   const bool keep = GRAD || a.xbuf != nullptr;
 
@@ -303,7 +347,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     x0s[i] = x[i];
   }
   uint32_t b0 = 0, b1 = 0;
-  if (a.noise_mode == SDE4_NOISE_THREEFRY) {
+  if (TFP || a.noise_mode == SDE4_NOISE_THREEFRY) {
     const uint32_t* k = a.key + (size_t)pd * a.key_sp;
     brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1, a.rng_chain);
   }
@@ -327,12 +371,21 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       if (!GRAD && a.write_stage_cost && contrib) a.xbuf[(size_t)NX * G + g] = c_prev;
     }
   }
+  using NL = NoiseLanes<M>;
+  float vn[NL::PER];
+  if constexpr (TFP) NL::gen(b0, b1, a.rng_mode, nzmask, 0, H, tc.l, vn);
   for (int t = 0; t < H; ++t) {
     const float dt = __ldg(a.dt + t);
     float dw[NX];
-    if (noisy)
-      draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, nzmask, tc, dw,
-                    (GRAD && active && a.dwbuf) ? a.dwbuf + (size_t)t * NX * G + g : nullptr);
+    if constexpr (TFP) {
+      NL::distribute(vn, dw);
+      if constexpr (GRAD) NL::keep(vn, a.dwbuf + (size_t)t * NX * G + g, G, nzmask, tc.l, active);  // dwbuf is never null here
+      NL::gen(b0, b1, a.rng_mode, nzmask, t + 1 < H ? t + 1 : t, H, tc.l, vn);  // overlaps the step below
+    } else {
+      if (noisy)
+        draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, H, G, g, nzmask, tc, dw,
+                      (GRAD && active && a.dwbuf) ? a.dwbuf + (size_t)t * NX * G + g : nullptr);
+    }
     float aux = 0.0f;
     em_step<M>(W, tc, d, x, u, dw, dt, noisy, aux);
     if (GRAD && M::NAUX && contrib) a.auxbuf[(size_t)t * G + g] = aux;
@@ -356,7 +409,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       else cost = fmaf(0.5f * dt, c_prev + c_next, cost);  // trapezoid (nsde.py:1515)
       c_prev = c_next;
     }
-    if (keep && a.xbuf) {
+    if (GRAD || (keep && a.xbuf)) {  // GRAD: the checkpoint buffer always exists (no branch in the loop body)
       float* out = a.xbuf + (size_t)(t + 1) * a.x_rows * G + g;
       store_state<M>(out, G, x, tc.l, active);
       if (!GRAD && a.write_stage_cost && contrib) out[(size_t)NX * G] = c_next;
@@ -452,11 +505,12 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     if constexpr (PREFETCH) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) x[i] = xpre[i];
-      if (t > 0) {
-        const float* in = a.xbuf + (size_t)(t - 1) * a.x_rows * G + g;
+      {  // unconditional (t = 0 re-reads row 0): no branch in the loop body
+        const int tp = t > 0 ? t - 1 : 0;
+        const float* in = a.xbuf + (size_t)tp * a.x_rows * G + g;
 #pragma unroll
         for (int i = 0; i < NX; ++i) xpre[i] = in[(size_t)i * G];
-        if (M::NAUX) auxpre = a.auxbuf[(size_t)(t - 1) * G + g];
+        if (M::NAUX) auxpre = a.auxbuf[(size_t)tp * G + g];
       }
     } else {
       const float* in = a.xbuf + (size_t)t * a.x_rows * G + g;

@@ -47,6 +47,12 @@ cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int bl
     cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256, false));
     attr_set = true;
   }
+  if constexpr (M::Ev::L > 1) {
+    if (a.noise_mode == SDE4_NOISE_THREEFRY) {  // lane-split + in-kernel noise: the pipelined-noise instantiation
+      k_rollout<M, true><<<blocks, threads, sm, s>>>(d, a);
+      return cudaGetLastError();
+    }
+  }
   k_rollout<M><<<blocks, threads, sm, s>>>(d, a);
   return cudaGetLastError();
 }
@@ -64,6 +70,22 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
     cudaFuncSetAttribute(k_cost<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_cost<M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     attr_set = true;
+  }
+  if constexpr (M::Ev::L > 1) {
+    if (a.noise_mode == SDE4_NOISE_THREEFRY && (!grad || a.dwbuf)) {
+      if (grad) {
+        if (constr)
+          k_cost<M, true, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+        else
+          k_cost<M, true, false, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+      } else {
+        if (constr)
+          k_cost<M, false, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+        else
+          k_cost<M, false, false, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+      }
+      return cudaGetLastError();
+    }
   }
   if (grad) {
     if (constr)
