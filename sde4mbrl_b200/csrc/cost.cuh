@@ -10,8 +10,13 @@
 namespace sde4 {
 
 // value of the shaping  e -> sig ? sigmoid(e*w - 7)*wsig : e*w   and d/d(e)
+template <bool PLAIN = false>
 SDE4_DEV float shaped(float e, float w, float wsig, bool sig, float& dde) {
   const float v = e * w;
+  if constexpr (PLAIN) {
+    dde = w;
+    return v;
+  }
   if (__builtin_expect(sig, 0)) {  // warp-uniform (descriptor flag): a real branch, not a select
     const float s = sigmoidf_(v - 7.0f);
     dde = s * (1.0f - s) * wsig * w;
@@ -23,9 +28,12 @@ SDE4_DEV float shaped(float e, float w, float wsig, bool sig, float& dde) {
 
 // Stage cost c(x, u, xref) and (optionally) its gradient scaled by `wt`:
 //   gx += wt * dc/dx,  gu += wt * dc/du.
-template <int NX, int NU, bool GRAD>
+// PLAIN (13-state models): the caller guarantees kind == ROTOR_TRACK without sigmoid / tanh shaping, which makes
+// the evaluation branch free (the lane-split kernels rely on straight-line loop bodies, see kernels.cuh).
+template <int NX, int NU, bool GRAD, bool PLAIN = false>
 SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const float (&u)[NU],
                           const float* __restrict__ xref, bool with_u, float wt, float (&gx)[NX], float (&gu)[NU]) {
+  static_assert(!PLAIN || NX == 13, "plain tracking cost: multirotor states");
   float tot = 0.0f;
   float dx[NX], du[NU];  // d tot / d x, d tot / d u  (before the outer shaping)
 #pragma unroll
@@ -33,7 +41,7 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
 #pragma unroll
   for (int j = 0; j < NU; ++j) du[j] = 0.0f;
 
-  if (c.kind == SDE4_COST_ROTOR_TRACK) {
+  if (PLAIN || c.kind == SDE4_COST_ROTOR_TRACK) {
     if constexpr (NX == 13) {
       // p (0-2), v (3-5), w (10-12): squared error times weight
 #pragma unroll
@@ -42,7 +50,7 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
         const int grp = i < 3 ? 0 : (i < 6 ? 1 : 3);
         const float diff = x[i] - xref[i];
         float dde;
-        tot += shaped(diff * diff, c.w_x[i], c.w_x_sig[i], (c.sig_mask >> grp) & 1u, dde);
+        tot += shaped<PLAIN>(diff * diff, c.w_x[i], c.w_x_sig[i], (c.sig_mask >> grp) & 1u, dde);
         dx[i] = 2.0f * diff * dde;
       }
       // attitude: (q_ref (x) q^-1)[1:]^2   (sde_mpc_design.py:83)
@@ -51,9 +59,9 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
         const Quat qx{x[6], x[7], x[8], x[9]};
         const Quat r = qmul(qr, qconj(qx));
         float d1, d2, d3;
-        tot += shaped(r.x * r.x, c.w_x[7], c.w_x_sig[7], (c.sig_mask >> 2) & 1u, d1);
-        tot += shaped(r.y * r.y, c.w_x[8], c.w_x_sig[8], (c.sig_mask >> 2) & 1u, d2);
-        tot += shaped(r.z * r.z, c.w_x[9], c.w_x_sig[9], (c.sig_mask >> 2) & 1u, d3);
+        tot += shaped<PLAIN>(r.x * r.x, c.w_x[7], c.w_x_sig[7], (c.sig_mask >> 2) & 1u, d1);
+        tot += shaped<PLAIN>(r.y * r.y, c.w_x[8], c.w_x_sig[8], (c.sig_mask >> 2) & 1u, d2);
+        tot += shaped<PLAIN>(r.z * r.z, c.w_x[9], c.w_x_sig[9], (c.sig_mask >> 2) & 1u, d3);
         if (GRAD) {
           const Quat gr{0.0f, 2.0f * r.x * d1, 2.0f * r.y * d2, 2.0f * r.z * d3};
           const Quat gq = qconj(qmul(qconj(qr), gr));  // r = qr (x) conj(q)
@@ -69,7 +77,7 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
       for (int j = 0; j < NU; ++j) {
         const float diff = u[j] - c.uref[j];
         float dde;
-        tot += shaped(diff * diff, c.w_u[j], c.w_u_sig[j], (c.sig_mask >> 4) & 1u, dde);
+        tot += shaped<PLAIN>(diff * diff, c.w_u[j], c.w_u_sig[j], (c.sig_mask >> 4) & 1u, dde);
         du[j] = 2.0f * diff * dde;
       }
     }
@@ -109,7 +117,7 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
     return 0.0f;
   }
   float val, outer;
-  if (c.use_res_sig) {  // tanh(tot - lo) * mult   (sde_mpc_design.py:128-130)
+  if (!PLAIN && c.use_res_sig) {  // tanh(tot - lo) * mult   (sde_mpc_design.py:128-130)
     const float th = tanhf_(tot - c.res_sig_lo);
     val = th * c.res_sig_mult;
     outer = (1.0f - th * th) * c.res_sig_mult;

@@ -316,7 +316,9 @@ SDE4_DEV float warp_sum(float v) {
   return v;
 }
 
-template <class M, bool GRAD, bool CONSTR, bool TFP = false>
+// MODE 0: generic.  MODE 1 (lane-split only): in-kernel threefry noise generated one step ahead, branch free.
+// MODE 2: MODE 1 + the plain multirotor tracking cost (no sigmoid / tanh shaping), also branch free.
+template <class M, bool GRAD, bool CONSTR, int MODE = 0>
 __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model_desc d,
                                                const __grid_constant__ sde4_cost_desc cd,
                                                const __grid_constant__ sde4_cost_desc td,
@@ -335,6 +337,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   const int pd = p % a.data_mod;  // stacked candidate evaluations share the problem data
   const float* op = a.opt + (size_t)p * a.o_sp;
   const float* xr = a.xref + (size_t)pd * a.xref_sp;
+  constexpr bool TFP = MODE >= 1, PLAINC = MODE == 2;
   static_assert(!TFP || L > 1, "the pipelined-noise variant is a lane-split kernel");
   const bool noisy = TFP ? true : a.noise_mode != SDE4_NOISE_NONE;
   const uint32_t nzmask = noise_mask<NX>(d);
@@ -363,7 +366,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   // the value-only kernel accumulates the trapezoid here, in the reference's order.
   {
     if constexpr (!GRAD) {
-      c_prev = stage_cost<NX, NU, false>(cd, x, u, xr, true, 0.0f, dummy_gx, dummy_gu);
+      c_prev = stage_cost<NX, NU, false, PLAINC>(cd, x, u, xr, true, 0.0f, dummy_gx, dummy_gu);
       if (CONSTR) c_prev += constr_cost<NX, false>(cd, x, x0s, 0.0f, dummy_gx, dummy_gs);  // slack_0 := x0 (nsde.py:1510)
     }
     if (keep && a.xbuf) {
@@ -395,7 +398,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     for (int j = 0; j < NU; ++j) unext[j] = __ldg(op + (size_t)tn * a.o_st + (size_t)j * a.o_sj);
     float c_next = 0.0f;
     if constexpr (!GRAD) {
-      c_next = stage_cost<NX, NU, false>(cd, x, unext, xr + (size_t)(t + 1) * NX, true, 0.0f, dummy_gx, dummy_gu);
+      c_next = stage_cost<NX, NU, false, PLAINC>(cd, x, unext, xr + (size_t)(t + 1) * NX, true, 0.0f, dummy_gx, dummy_gu);
       if (CONSTR) {
         float sl[NX];
 #pragma unroll
@@ -447,7 +450,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   for (int j = 0; j < NU; ++j) gu[j] = 0.0f;  // row H-1 also receives the u-gradient of stage H
   {
     const float wH = a.sum_mode ? 1.0f : 0.5f * __ldg(a.dt + H - 1);
-    float cH = stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
+    float cH = stage_cost<NX, NU, true, PLAINC>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
     if (CONSTR) {
       float sl[NX];
 #pragma unroll
@@ -540,7 +543,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     }
     // stage cost at t: trapezoid weight w_t
     const float wt = a.sum_mode ? (t > 0 ? 1.0f : 0.0f) : (t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt);
-    float ct = stage_cost<NX, NU, true>(cd, x, u, xr + (size_t)t * NX, true, wt, gx, gu);
+    float ct = stage_cost<NX, NU, true, PLAINC>(cd, x, u, xr + (size_t)t * NX, true, wt, gx, gu);
     if (CONSTR) {
       float sl[NX];
 #pragma unroll
@@ -566,13 +569,13 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
           gu[j] = 0.0f;
         }
         if (!active) v = 0.0f;
-        if (a.warp_reduce) {
+        // branch free: the butterflies always run, their sum is used only when the warp's samples share a problem
+        float vs = v;
 #pragma unroll
-          for (int o = 16; o >= L; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-          if (active && (int)(threadIdx.x & 31) < NU) gp[(size_t)tc.l * a.PW + pw] = v;
-        } else if (active && tc.l < NU) {
-          gp[(size_t)tc.l * a.PW + pw] = v;
-        }
+        for (int o = 16; o >= L; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
+        const bool wr = a.warp_reduce != 0;
+        const bool st = active && (wr ? (int)(threadIdx.x & 31) < NU : tc.l < NU);
+        if (st) gp[(size_t)tc.l * a.PW + pw] = wr ? vs : v;
       } else {
 #pragma unroll
         for (int j = 0; j < NU; ++j) {

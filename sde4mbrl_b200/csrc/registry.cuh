@@ -73,16 +73,35 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
   }
   if constexpr (M::Ev::L > 1) {
     if (a.noise_mode == SDE4_NOISE_THREEFRY && (!grad || a.dwbuf)) {
+      // lane-split + in-kernel noise: the straight-line instantiations (kernels.cuh, MODE 1 / 2)
+      bool plain = false;
+      if constexpr (M::NX == 13) plain = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
+      if constexpr (M::NX == 13) {
+        if (plain) {
+          if (grad) {
+            if (constr)
+              k_cost<M, true, true, 2><<<blocks, threads, sm, s>>>(d, cd, td, a);
+            else
+              k_cost<M, true, false, 2><<<blocks, threads, sm, s>>>(d, cd, td, a);
+          } else {
+            if (constr)
+              k_cost<M, false, true, 2><<<blocks, threads, sm, s>>>(d, cd, td, a);
+            else
+              k_cost<M, false, false, 2><<<blocks, threads, sm, s>>>(d, cd, td, a);
+          }
+          return cudaGetLastError();
+        }
+      }
       if (grad) {
         if (constr)
-          k_cost<M, true, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+          k_cost<M, true, true, 1><<<blocks, threads, sm, s>>>(d, cd, td, a);
         else
-          k_cost<M, true, false, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+          k_cost<M, true, false, 1><<<blocks, threads, sm, s>>>(d, cd, td, a);
       } else {
         if (constr)
-          k_cost<M, false, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+          k_cost<M, false, true, 1><<<blocks, threads, sm, s>>>(d, cd, td, a);
         else
-          k_cost<M, false, false, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
+          k_cost<M, false, false, 1><<<blocks, threads, sm, s>>>(d, cd, td, a);
       }
       return cudaGetLastError();
     }
