@@ -515,7 +515,7 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
                 dtot.backward()
                 dgrads = {mod: {k: v.grad for k, v in leaves.items() if v.grad is not None} for mod, leaves in tt.items()}
             total += float(dtot.detach())
-            dinfo = {k: float(v) for k, v in dinfo.items()}
+            dinfo = {k: float(v.detach()) if isinstance(v, torch.Tensor) else float(v) for k, v in dinfo.items()}
         w_loss, wgrads = _penalty(_nn_params, want_grad) if pen_w > 0 else (0.0, {})
         if pen_w > 0:
             total += pen_w * w_loss
