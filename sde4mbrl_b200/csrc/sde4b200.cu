@@ -46,17 +46,22 @@ static int pick_threads(int requested, long long threads_total) {
   return 128;
 }
 
-// lanes per sample: with few samples one thread per sample leaves most of the 592 warp schedulers
-// idle and each resident warp latency-bound, so the lane-split kernel is used when it exists
-static int pick_lanes(const ArchEntry& e, int requested, long long G) {
+// lanes per sample: with few samples one thread per sample leaves most of the 592 warp schedulers idle and each
+// resident warp latency bound, so a lane-split kernel is used when it exists.  Rule fitted to scripts/lane_sweep.py
+// (hexacopter, H = 20, G problems): the widest compiled split whose launch stays near one wave of 7 warps per SM
+// (G*L <= 40960 threads); otherwise the narrowest compiled split while the launch stays below ~98 k threads
+// (value only) / ~229 k threads (value + gradient); beyond that the one-thread-per-sample throughput kernel.
+static int pick_lanes(const ArchEntry& e, int requested, long long G, bool grad) {
   if (requested == 1) return 1;
   if (requested > 1) {
     const int i = ilog2(requested);
     return (i < 5 && (1 << i) == requested && e.launch_cost[i]) ? requested : -1;
   }
-  // widest compiled variant that still leaves <= ~16 warps per SM
   for (int i = 4; i >= 1; --i)
-    if (e.launch_cost[i] && G * (1LL << i) <= 148LL * 32 * 16) return 1 << i;
+    if (e.launch_cost[i] && G * (1LL << i) <= 40960) return 1 << i;
+  const long long limit = grad ? 229376 : 98304;
+  for (int i = 1; i <= 4; ++i)
+    if (e.launch_cost[i] && G * (1LL << i) <= limit) return 1 << i;
   return 1;
 }
 
@@ -177,7 +182,7 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void*
   k.n_off = a->particle_total > 0 ? a->particle_offset : 0;
   k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
-  const int lanes = pick_lanes(*e, a->lanes, G);
+  const int lanes = pick_lanes(*e, a->lanes, G, false);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const long long nthr = G * lanes;
   const int threads = pick_threads(a->block_threads, nthr);
@@ -338,7 +343,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     if (!e->launch_loss) return fail(SDE4_ERR_UNSUPPORTED, "no training-loss kernel compiled for %s", e->name);
     if (constr || cd.kind != SDE4_COST_QUADRATIC || a->xtraj) return fail(SDE4_ERR_INVALID, "training loss: QUADRATIC data cost, no constraints, no xtraj");
   }
-  const int lanes = lo.enabled ? 1 : pick_lanes(*e, a->lanes, G);
+  const int lanes = lo.enabled ? 1 : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
   size_t dump_off[3] = {0, 0, 0};
