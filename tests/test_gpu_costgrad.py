@@ -169,3 +169,39 @@ def test_particle_sharding(cuda, lanes):
                               particle_total=N, lanes=lanes)
     assert abs(float(ca[0] + cb[0]) - float(c[0])) <= 1e-6 * abs(float(c[0]))  # reduction order only
     assert hp.rel_err((ga + gb).cpu().numpy(), g.cpu().numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("variant", ["group_sigmoids", "res_sig", "both"])
+@pytest.mark.parametrize("lanes,use_key", [(1, False), (8, False), (8, True), (4, True)])
+def test_shaped_rotor_cost(cuda, variant, lanes, use_key):
+    """The optional shaping of one_step_cost_f (sde_mpc_design.py:84-130): per-group sigmoid(e*w - 7)*w_sig and the
+    outer tanh(tot - lo)*mult, through the generic kernels (given noise), and the lane-split MODE-1 kernels
+    (in-kernel threefry + shaped cost, which cannot use the branch-free plain-cost instantiation)."""
+    from sde4mbrl_b200.engine import Engine
+    from oracle import threefry as tf
+    N, H = 24, 20
+    pm, model, nn, y0, opt, dw, _, _, xref = _setup("hexa", H, N, seed=5)
+    cp = {"uref": [0.33] * 6, "uerr": 300.0, "perr": [30.0, 30.0, 60.0], "verr": [40.0, 40.0, 40.0], "qerr": [50.0, 50.0, 500.0],
+          "werr": [30.0, 30.0, 30.0], "res_mult": 0.01, "u_slew_coeff": 0.1}
+    if variant in ("group_sigmoids", "both"):
+        cp.update({"perr_sig": [2.0, 2.0, 4.0], "verr_sig": 1.5, "qerr_sig": [1.0, 1.0, 3.0], "werr_sig": 0.5, "uerr_sig": 0.7})
+    if variant in ("res_sig", "both"):
+        cp["res_sig"] = [3.0, 2.5] if variant == "res_sig" else [1.0, 2.5]
+        if variant == "res_sig":
+            for k in ("perr", "verr", "qerr", "werr"):
+                cp[k] = [0.1 * v for v in cp[k]]
+            cp["uerr"] = 30.0
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    assert (stage.desc.sig_mask != 0) == (variant != "res_sig") and bool(stage.desc.use_res_sig) == (variant != "group_sigmoids")
+    eng = Engine(model)
+    ts = orc.compute_timesteps(pm)
+    if use_key:
+        key = tf.PRNGKey(17)
+        dw = tf.rollout_noise(key, N, H, 13)
+        cost, grad, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, key=key, N=N, lanes=lanes)
+    else:
+        cost, grad, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, noise=hp.to_native_noise(dw), lanes=lanes)
+    c64, g64, _ = _oracle("hexa", pm, nn, y0, opt, dw, cp, xref, torch.float64, True)
+    assert abs(float(cost[0]) - c64) <= 3e-5 * abs(c64) + 1e-7
+    assert hp.rel_err(grad.cpu().numpy(), g64) < 2e-3
+    assert np.abs(g64).max() > 1e-4  # the shaped cost is not saturated: the gradient test means something
