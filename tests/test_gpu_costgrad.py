@@ -205,3 +205,38 @@ def test_shaped_rotor_cost(cuda, variant, lanes, use_key):
     assert abs(float(cost[0]) - c64) <= 3e-5 * abs(c64) + 1e-7
     assert hp.rel_err(grad.cpu().numpy(), g64) < 2e-3
     assert np.abs(g64).max() > 1e-4  # the shaped cost is not saturated: the gradient test means something
+
+
+@pytest.mark.parametrize("lanes,use_key", [(1, False), (8, False), (8, True)])
+def test_terminal_cost(cuda, lanes, use_key):
+    """Terminal cost of compute_cost_function (nsde.py:1517-1521) in the form load_mpc_from_cfgfile builds from
+    `cost_params_end` (sde_mpc_design.py:353-361): the stage-cost expression without control terms, at x_H."""
+    from sde4mbrl_b200.engine import Engine
+    from oracle import threefry as tf
+    N, H = 20, 20
+    pm, model, nn, y0, opt, dw, cp, stage, xref = _setup("hexa", H, N, seed=9)
+    cpe = {"perr": [80.0, 80.0, 120.0], "verr": [10.0, 10.0, 10.0], "qerr": [5.0, 5.0, 50.0], "werr": 2.0, "res_mult": 0.05}
+    term = costs.one_step_cost_f(cpe, 6)
+    eng = Engine(model)
+    ts = orc.compute_timesteps(pm)
+    if use_key:
+        key = tf.PRNGKey(23)
+        dw = tf.rollout_noise(key, N, H, 13)
+        kw = dict(key=key)
+    else:
+        kw = dict(noise=hp.to_native_noise(dw))
+    cost, grad, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, terminal=term.desc, N=N, lanes=lanes, **kw)
+    cost0, grad0, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, lanes=lanes, **kw)
+    om = hp.oracle_model("hexa", pm, nn, torch.float64)
+    o = torch.tensor(opt, dtype=torch.float64, requires_grad=True)
+    xr64 = torch.tensor(xref, dtype=torch.float64)
+    c64, _ = orc.compute_cost(om, torch.tensor(y0, dtype=torch.float64), o, torch.tensor(dw, dtype=torch.float64),
+                              hp.stage_cost_fn("hexa", cp), xr64,
+                              terminal_cost=lambda x, xr: orc.rotor_one_step_cost(x, None, xr, cpe))
+    c64 = c64 + orc.u_slew_cost(o, ts, cp, 6)
+    (g64,) = torch.autograd.grad(c64, o)
+    assert abs(float(cost[0]) - float(c64)) <= 2e-5 * abs(float(c64))
+    assert hp.rel_err(grad.cpu().numpy(), g64.numpy()) < 1e-3
+    assert float(cost[0]) > float(cost0[0]) * 1.05  # the terminal term is a visible part of the total
+    cv, _, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, terminal=term.desc, N=N, lanes=lanes, want_grad=False, **kw)
+    assert abs(float(cv[0]) - float(cost[0])) <= 2e-6 * abs(float(cost[0]))
