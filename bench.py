@@ -474,6 +474,36 @@ def main():
         except Exception as ex:
             c2_extra = {"error": repr(ex)}
 
+    # ---- latency of ONE hexacopter MPC solve as the reference deploys it (mpc_test_cfg.yaml: H=20, dt=0.05, 1 particle;
+    # also 32 and 1024 particles), 20 APG iterations, device-side APG (one CUDA-graph replay per iteration)
+    single_extra = {}
+    if rank == 0:
+        try:
+            from sde4mbrl_b200.apg_batched import BatchedAPG
+            HM1 = 20
+            for n_part in (1, 32, 1024):
+                pm1 = configs.hexa_model(horizon=HM1, num_particles=n_part, stepsize=0.05)
+                mpc1 = configs.hexa_mpc(horizon=HM1, dt=0.05, num_particles=n_part, max_iter=20)
+                eng1 = Engine(sde_models.SDERotorModel(pm1))
+                sol1 = BatchedAPG(eng1, w["nn"], w["stage"], mpc1["apg_mpc"], np.full(HM1, 0.05, np.float32), n_part,
+                                  lb=1e-4, ub=1.0)
+                x01 = torch.full((HM1, 6), 0.33 + 2e-4, device=dev)
+                xr1 = np.tile(w["xref"][:1], (HM1 + 1, 1))
+                tms = []
+                for rep in range(6):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    sol1.init(x01, w["y0"][None], xr1, w["key"]).run(20)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if rep > 1:
+                        tms.append(e0.elapsed_time(e1))
+                single_extra["N%d" % n_part] = {"ms_per_solve": float(np.mean(tms)), "particles": n_part, "horizon": HM1,
+                                                "apg_iterations": 20, "opt_cost": float(sol1.t["opt_cost"][0]),
+                                                "init_cost": float(sol1.t["init_cost"][0])}
+        except Exception as ex:
+            single_extra = {"error": repr(ex)}
+
     # ---- extras (rank 0, N=1 only): forward rollout, FP32 peak, CPU baseline
     extras = {}
     roof = None
@@ -568,6 +598,7 @@ def main():
             line["cpu_baseline"] = cpu_b
         line.update(extras)
         line["cartpole_mpc_single"] = c2_extra
+        line["hexa_mpc_single"] = single_extra
         line["mpc_batch"] = mpc_extra
         line["simulator_rollouts"] = sim_extra
         line["training_loss"] = train_extra

@@ -258,8 +258,9 @@ int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* args, flo
  *      a problem whose `not_done` flag is 0 keeps its state, exactly like the no-op iterations
  *      of the reference's scan.  All [H][n_opt][*] arrays are PROBLEM-MINOR (problem index fastest).
  *      One iteration = sde4_apg_candidates -> sde4_cost_grad on (maxls+1)*P problems (value only)
- *      -> sde4_apg_select -> sde4_cost_grad on 2P problems (value only) -> sde4_apg_pick ->
- *      sde4_cost_grad on P problems (value + gradient) -> sde4_apg_update. */
+ *      -> sde4_apg_select -> sde4_cost_grad on 2P problems (value only) -> sde4_apg_pick -> sde4_cost_grad on P
+ *      problems (value + gradient) -> sde4_apg_update; or, for latency-bound sizes, value + gradient on the 2P
+ *      problems and sde4_apg_pick copying the gradient of the better of x / v (one sequential rollout less). */
 typedef struct sde4_apg_params {
   int32_t P, H, n_opt;
   int32_t maxls;               /* linesearch.maxls                                            */
@@ -293,9 +294,11 @@ int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, fl
  * sel_step[P], sel_ls[P] (stepsize, number of line-search steps). */
 int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, const float* svals,
                     const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, void* stream);
-/* ynext = where(cost_x <= cost_v, xcurr, vcurr) (apg.py:219-221): y[H][n_opt][P], pick[P] */
+/* ynext = where(cost_x <= cost_v, xcurr, vcurr) (apg.py:219-221): y[H][n_opt][P], pick[P].  If the x / v evaluation
+ * was a value+gradient launch, xv_grad[H][n_opt][2P] is given and the gradient of the chosen point is copied into
+ * y_grad[H][n_opt][P] (apg.py:224 then needs no further launch); both NULL otherwise. */
 int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
-                  int32_t* pick, void* stream);
+                  int32_t* pick, const float* xv_grad_or_null, float* y_grad_or_null, void* stream);
 /* state update with grad(ynext) (apg.py:224-273); problems with not_done == 0 are left untouched */
 int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
                     const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,

@@ -8,6 +8,9 @@ evaluates all branches; here the same semantics are obtained with per-problem ma
     Armijo selection + box prox + momentum point -> ONE value-only launch over 2P problems (x and v)
     ynext = where(cost_x <= cost_v, x, v)        -> ONE value+gradient launch over P problems
     state update (masked by not_done)
+For latency-bound sizes (2*P*N <= 65536 samples) the last two launches are merged: value+gradient for x AND v, then
+point, cost and gradient of the better one are copied -- ~15 % more arithmetic, one sequential rollout less per
+iteration (a single hexacopter solve: 3.8 -> 2.9 ms).
 
 All arithmetic (cost evaluations and the APG bookkeeping) runs in ``libsde4b200.so``; torch only
 owns the buffers.  Arrays are problem-minor: ``[H, n_opt, P]``.
@@ -24,7 +27,7 @@ from .engine import as_f32, as_key, _ptr, _stream
 
 class BatchedAPG:
     def __init__(self, engine, nn_params, stage, optimizer_params, time_steps, num_particles, lb=None, ub=None,
-                 terminal=None, lanes=0):
+                 terminal=None, lanes=0, merge_xv_grad=None):
         self.eng = engine
         self.pk = engine.packed(nn_params)
         self.stage = stage
@@ -39,6 +42,7 @@ class BatchedAPG:
         # picks from the launch size) or {"cand": .., "xv": .., "y": ..}
         self.lanes = lanes if isinstance(lanes, dict) else {"cand": lanes, "xv": lanes, "y": lanes}
         self.lb, self.ub = lb, ub
+        self.merge_xv_grad = merge_xv_grad  # None: decided from the launch size (see step)
         self.P = None
         self._graph = None
 
@@ -53,6 +57,9 @@ class BatchedAPG:
         self.t.update({n_: f(H, n, P) for n_ in L.APG_STATE_VEC})
         self.cand, self.svals, self.cand_cost = f(H, n, K * P), f(K, P), f(K * P)
         self.xv, self.xv_cost = f(H, n, 2 * P), f(2 * P)
+        if self.merge_xv_grad is None:
+            self.merge_xv_grad = 2 * P * self.N <= 65536
+        self.xv_grad = f(H, n, 2 * P) if self.merge_xv_grad else None
         self.y, self.y_cost, self.y_grad = f(H, n, P), f(P), f(H, n, P)
         self.cost_tmp = f(P)
         self.sel_step, self.sel_ls, self.pick = f(P), i(P), i(P)
@@ -131,16 +138,24 @@ class BatchedAPG:
         self._cost(self.cand, self.cand_cost, data_mod=P, which="cand")
         L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(self.cand_cost),
                                     _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
-        self._cost(self.xv, self.xv_cost, data_mod=P, which="xv")
-        L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
-                                  _ptr(self.pick), _stream()))
-        self._cost(self.y, self.cost_tmp, grad_buf=self.y_grad)
+        if self.merge_xv_grad:
+            # latency-bound sizes: ONE value+gradient launch over the 2P problems x and v; pick copies point, cost
+            # and gradient of the better one (one sequential rollout less per iteration, ~15 % more arithmetic)
+            self._cost(self.xv, self.xv_cost, grad_buf=self.xv_grad, data_mod=P, which="xv")
+            L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
+                                      _ptr(self.pick), _ptr(self.xv_grad), _ptr(self.y_grad), _stream()))
+        else:
+            # throughput-bound sizes: the reference's order -- value-only x / v, then the gradient at the chosen point
+            self._cost(self.xv, self.xv_cost, data_mod=P, which="xv")
+            L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
+                                      _ptr(self.pick), _ptr(None), _ptr(None), _stream()))
+            self._cost(self.y, self.cost_tmp, grad_buf=self.y_grad)
         L.check(lib.sde4_apg_update(C.byref(prm), C.byref(st), _ptr(self.xv), _ptr(self.y), _ptr(self.y_cost),
                                     _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls),
                                     _ptr(self.cand), _stream()))  # cand is dead here: |grad|^2 partials scratch
 
     def _capture(self):
-        """Capture one masked iteration (4 bookkeeping + 3 cost + 3 reduce launches) in a CUDA graph.
+        """Capture one masked iteration (6 bookkeeping + 2-3 cost + 2-3 reduce launches) in a CUDA graph.
         A throw-away eager iteration first makes every lazy set-up (workspace growth, func attributes)
         happen outside the capture; the solver state is restored afterwards."""
         names = L.APG_STATE_INT + L.APG_STATE_F32 + L.APG_STATE_VEC

@@ -122,9 +122,12 @@ __global__ void k_apg_select(const __grid_constant__ sde4_apg_params prm, const 
   }
 }
 
+// ynext = where(cost_x <= cost_v, x, v).  When the x / v evaluation also produced gradients (xv_grad != nullptr:
+// ONE value+gradient launch over the 2P problems instead of a value launch followed by a gradient launch of the
+// chosen point -- same arithmetic work, one sequential rollout less per iteration) the chosen gradient is copied too.
 __global__ void k_apg_pick(const __grid_constant__ sde4_apg_params prm, const float* __restrict__ xv,
                            const float* __restrict__ xv_cost, float* __restrict__ y, float* __restrict__ y_cost,
-                           int32_t* __restrict__ pick) {
+                           int32_t* __restrict__ pick, const float* __restrict__ xv_grad, float* __restrict__ y_grad) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   const int P = prm.P, E = prm.H * prm.n_opt;
@@ -135,7 +138,11 @@ __global__ void k_apg_pick(const __grid_constant__ sde4_apg_params prm, const fl
     pick[p] = x_le_v;
     y_cost[p] = x_le_v ? cx : cv;
   }
-  for (int e = e0; e < e1; ++e) y[(size_t)e * P + p] = xv[(size_t)e * 2 * P + (x_le_v ? 0 : P) + p];
+  for (int e = e0; e < e1; ++e) {
+    const size_t src = (size_t)e * 2 * P + (x_le_v ? 0 : P) + p;
+    y[(size_t)e * P + p] = xv[src];
+    if (xv_grad) y_grad[(size_t)e * P + p] = xv_grad[src];
+  }
 }
 
 // vector part of the state update: reads the OLD per-problem scalars, writes vectors and |grad|^2 partials

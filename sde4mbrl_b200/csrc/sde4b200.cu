@@ -596,10 +596,11 @@ int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const 
   return SDE4_OK;
 }
 int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
-                  int32_t* pick, void* stream) {
+                  int32_t* pick, const float* xv_grad_or_null, float* y_grad_or_null, void* stream) {
   if (int rc = apg_check(prm, nullptr)) return rc;
   if (!xv || !xv_cost || !y || !y_cost || !pick) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_pick, 1, *prm, xv, xv_cost, y, y_cost, pick);
+  if ((xv_grad_or_null == nullptr) != (y_grad_or_null == nullptr)) return fail(SDE4_ERR_INVALID, "xv_grad and y_grad go together");
+  SDE4_APG_LAUNCH(k_apg_pick, 1, *prm, xv, xv_cost, y, y_cost, pick, xv_grad_or_null, y_grad_or_null);
   return SDE4_OK;
 }
 int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,

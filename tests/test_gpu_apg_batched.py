@@ -14,8 +14,11 @@ from sde4mbrl_b200 import configs, costs, sde_models
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("merge", [True, False])
 @pytest.mark.parametrize("N,iters,rtol", [(1, 8, 0.0), (4, 6, 0.0), (1, 12, 0.05)])
-def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol):
+def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge):
+    """`merge`: x and v evaluated by one value+gradient launch (latency-bound sizes) or, as in the reference, value
+    only followed by the gradient at the chosen point (throughput-bound sizes)."""
     from sde4mbrl_b200 import apg, nsde, random as R
     from sde4mbrl_b200.apg_batched import BatchedAPG
     P, H = 5, 20
@@ -34,7 +37,7 @@ def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol):
     keys = tf.split(tf.PRNGKey(31), P)
     x0 = construct_opt(u=np.full(6, 0.33, np.float32))
     eng = multi_cost.engine
-    solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0)
+    solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0, merge_xv_grad=merge)
     solver.init(x0, y0, xref, keys).run(use_graph=False)
     x_eager = solver.x_opt().clone()
     solver.init(x0, y0, xref, keys).run(use_graph=True)  # CUDA-graph replay must give the same iterates
