@@ -145,7 +145,7 @@ void add_lane_variant(ArchEntry& e) {
   }
 }
 
-template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit, class MTRAIN = NoLaneSplit>
+template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit, class MTRAIN = NoLaneSplit, class MLS3 = NoLaneSplit>
 ArchEntry make_entry(const char* name) {
   using A = typename M::A;
   ArchEntry e;
@@ -171,6 +171,7 @@ ArchEntry make_entry(const char* name) {
   e.launch_cost[0] = &launch_cost_t<M>;
   add_lane_variant<MLS>(e);
   add_lane_variant<MLS2>(e);
+  add_lane_variant<MLS3>(e);
   e.launch_loss = nullptr;
   if constexpr (!std::is_same<MTRAIN, NoLaneSplit>::value) e.launch_loss = &launch_loss_t<MTRAIN>;
   using D = typename A::DNet;
@@ -205,6 +206,11 @@ struct ArchRegistrar {
 #define SDE4_REGISTER_LS2(NAME, MODEL_T, ARCH, LANES_A, LANES_B)                                          \
   static ::sde4::ArchRegistrar reg_##NAME(                                                                \
       ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES_A>>, MODEL_T<ARCH, ::sde4::EvL<LANES_B>>>(#NAME));
+
+#define SDE4_REGISTER_LS3(NAME, MODEL_T, ARCH, LANES_A, LANES_B, LANES_C)                                  \
+  static ::sde4::ArchRegistrar reg_##NAME(                                                                \
+      ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES_A>>, MODEL_T<ARCH, ::sde4::EvL<LANES_B>>, \
+                         ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::EvL<LANES_C>>>(#NAME));
 
 // shorthand for the architecture zoo
 constexpr int TANH = SDE4_ACT_TANH, SWISH = SDE4_ACT_SWISH;
