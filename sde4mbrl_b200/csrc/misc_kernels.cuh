@@ -163,52 +163,71 @@ __global__ void __launch_bounds__(1024) k_fma_peak(int iters, float* sink) {
 // ----------------------------------------------------------------------------
 // K5: parameter gradients of the training loss from the streams written by the DUMP evaluators:
 //   out[a*ldo + b] = scale * sum_k A[a][k] * B[b][k]     (A == nullptr: A = 1, i.e. bias / scaler sums)
-// One CTA per output row a; threads stride over the K = H*G columns (coalesced), 32 register
-// accumulators per thread, fixed-order block reduction (deterministic, no atomics).
+// Tiny GEMMs with a long K = H*G (n_a, n_b <= 33).  Stage 1: grid (K chunks, tasks); a CTA stages its
+// [n_a + n_b] x WG_KC slab of the streams in shared memory with coalesced row reads (every stream element is read
+// from global memory ONCE), each thread forms whole (a, b) dot products over the slab (rows padded by one float:
+// conflict-free).  Stage 2 sums the per-chunk partials in a fixed order -- deterministic, no atomics.
 // ----------------------------------------------------------------------------
+constexpr int WG_KC = 256;
 struct WgradTask {
   const float* A;
   const float* B;
   float* out;
-  int n_a, n_b, ldo, row0;  // row0: first CTA of this task
+  int n_a, n_b, ldo, pair0;  // pair0: first (a, b) pair of this task in the partial buffer
 };
 struct WgradK {
   WgradTask task[24];
-  int n_tasks;
+  int n_tasks, n_pairs, n_chunks;
   unsigned long long K;  // columns; row stride of A and B
   float scale;
+  float* partial;  // [n_chunks][n_pairs]
 };
 
-__global__ void __launch_bounds__(256) k_wgrad(const __grid_constant__ WgradK a) {
-  int ti = 0;
-  while (ti + 1 < a.n_tasks && (int)blockIdx.x >= a.task[ti + 1].row0) ++ti;
-  const WgradTask& t = a.task[ti];
-  const int row = blockIdx.x - t.row0;
-  float acc[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) acc[j] = 0.0f;
-  const float* Ar = t.A ? t.A + (size_t)row * a.K : nullptr;
-  for (unsigned long long k = threadIdx.x; k < a.K; k += blockDim.x) {
-    const float av = Ar ? Ar[k] : 1.0f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < t.n_b) acc[j] = fmaf(av, t.B[(size_t)j * a.K + k], acc[j]);
-  }
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    float v = acc[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) red[warp][j] = v;
+__global__ void __launch_bounds__(256) k_wgrad_partial(const __grid_constant__ WgradK a) {
+  extern __shared__ float slab[];  // [n_a + n_b][WG_KC + 1]
+  const WgradTask& t = a.task[blockIdx.y];
+  const unsigned long long k0 = (unsigned long long)blockIdx.x * WG_KC;
+  const int kn = (int)min((unsigned long long)WG_KC, a.K - k0);
+  constexpr int LD = WG_KC + 1;
+  const int rows = t.n_a + t.n_b;
+  for (int idx = threadIdx.x; idx < rows * WG_KC; idx += blockDim.x) {
+    const int r = idx / WG_KC, c = idx - r * WG_KC;
+    float v = 0.0f;
+    if (c < kn) {
+      if (r < t.n_a) v = t.A ? t.A[(size_t)r * a.K + k0 + c] : 1.0f;
+      else v = t.B[(size_t)(r - t.n_a) * a.K + k0 + c];
+    }
+    slab[r * LD + c] = v;
   }
   __syncthreads();
-  if (threadIdx.x < t.n_b) {
-    float s = 0.0f;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w][threadIdx.x];
-    t.out[(size_t)row * t.ldo + threadIdx.x] = s * a.scale;
+  const int pairs = t.n_a * t.n_b;
+  for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+    const int ia = p / t.n_b, ib = p - ia * t.n_b;
+    const float* sa = slab + ia * LD;
+    const float* sb = slab + (t.n_a + ib) * LD;
+    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll 4
+    for (int c = 0; c < WG_KC; c += 4) {  // the slab is zero-padded beyond kn
+      s0 = fmaf(sa[c], sb[c], s0);
+      s1 = fmaf(sa[c + 1], sb[c + 1], s1);
+      s2 = fmaf(sa[c + 2], sb[c + 2], s2);
+      s3 = fmaf(sa[c + 3], sb[c + 3], s3);
+    }
+    a.partial[(size_t)blockIdx.x * a.n_pairs + t.pair0 + p] = (s0 + s1) + (s2 + s3);
   }
+}
+
+__global__ void k_wgrad_final(const __grid_constant__ WgradK a) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n_pairs) return;
+  int ti = 0;
+  while (ti + 1 < a.n_tasks && q >= a.task[ti + 1].pair0) ++ti;
+  const WgradTask& t = a.task[ti];
+  const int p = q - t.pair0;
+  const int ia = p / t.n_b, ib = p - ia * t.n_b;
+  float s = 0.0f;
+  for (int c = 0; c < a.n_chunks; ++c) s += a.partial[(size_t)c * a.n_pairs + q];
+  t.out[(size_t)ia * t.ldo + ib] = s * a.scale;
 }
 
 }  // namespace sde4

@@ -302,13 +302,27 @@ static size_t loss_dump_floats(const ArchEntry& e, size_t K, size_t off[3]) {
   return tot;
 }
 
+// number of (a, b) output pairs of the K5 tasks (weights, biases, scaler) of an architecture
+static int loss_wgrad_pairs(const ArchEntry& e) {
+  int pairs = 0;
+  for (int s = 0; s < 3; ++s) {
+    const int* d = e.net_dims[s];
+    if (d[0] == 0) continue;
+    pairs += d[0] * d[1] + d[1] + d[1] * d[2] + d[2] + d[3] * d[2] + d[3];
+    if (s == 0) pairs += e.n_scaler;
+  }
+  return pairs;
+}
+
 size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t H) {
   if (!model) return 0;
   const ArchEntry* e = find_arch(*model);
   if (!e || !e->launch_loss) return 0;
   size_t off[3];
-  const size_t dump = loss_dump_floats(*e, (size_t)B * N * H, off) * 4;
-  return cost_layout(*e, B, N, H, 0, true, false, SDE4_NOISE_THREEFRY, 1).total + ((dump + 255) & ~(size_t)255);
+  const size_t K = (size_t)B * N * H;
+  const size_t dump = loss_dump_floats(*e, K, off) * 4;
+  const size_t partial = ((K + WG_KC - 1) / WG_KC) * (size_t)loss_wgrad_pairs(*e) * 4;
+  return cost_layout(*e, B, N, H, 0, true, false, SDE4_NOISE_THREEFRY, 1).total + ((dump + 255) & ~(size_t)255) + partial;
 }
 
 int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* a, float* grad_params, void* stream) {
@@ -349,7 +363,9 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   size_t dump_off[3] = {0, 0, 0};
   const size_t Kcols = (size_t)G * a->H;
   const size_t dump_bytes = lo.enabled ? loss_dump_floats(*e, Kcols, dump_off) * 4 : 0;
-  if (a->workspace_bytes < L.total + dump_bytes) return fail(SDE4_ERR_WORKSPACE, "workspace too small");
+  const size_t wg_bytes = lo.enabled ? ((Kcols + WG_KC - 1) / WG_KC) * (size_t)loss_wgrad_pairs(*e) * 4 : 0;
+  if (a->workspace_bytes < L.total + ((dump_bytes + 255) & ~(size_t)255) + wg_bytes)
+    return fail(SDE4_ERR_WORKSPACE, "workspace too small");
   if (((uintptr_t)a->workspace & 255) != 0) return fail(SDE4_ERR_INVALID, "workspace must be 256-byte aligned");
   char* ws = (char*)a->workspace;
   CostK k;
@@ -449,7 +465,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     wk.n_tasks = 0;
     wk.K = Kcols;
     wk.scale = 1.0f / (float)((double)a->P * k.n_tot);
-    int row0 = 0;
+    int pair0 = 0, max_rows = 0;
     auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo) {
       WgradTask& t = wk.task[wk.n_tasks++];
       t.A = A;
@@ -458,8 +474,9 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
       t.n_a = n_a;
       t.n_b = n_b;
       t.ldo = ldo;
-      t.row0 = row0;
-      row0 += n_a;
+      t.pair0 = pair0;
+      pair0 += n_a * n_b;
+      if (n_a + n_b > max_rows) max_rows = n_a + n_b;
     };
     auto up4l = [](int n) { return (n + 3) & ~3; };
     for (int s2 = 0; s2 < 3; ++s2) {
@@ -489,7 +506,18 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
       add(nullptr, 1, r_go, OUT, b2, 4);
       if (s2 == 0 && e->n_scaler) add(nullptr, 1, r_go + (size_t)OUT * Kcols, e->n_scaler, lo.grad_params + e->off_scaler, e->n_scaler);
     }
-    k_wgrad<<<row0, 256, 0, s>>>(wk);
+    wk.n_pairs = pair0;
+    wk.n_chunks = (int)((Kcols + WG_KC - 1) / WG_KC);
+    wk.partial = (float*)(ws + L.total + ((dump_bytes + 255) & ~(size_t)255));
+    if (pair0 != loss_wgrad_pairs(*e)) return fail(SDE4_ERR_INVALID, "internal: wgrad pair count");
+    const size_t slab = (size_t)max_rows * (WG_KC + 1) * sizeof(float);
+    static bool wg_attr = false;
+    if (!wg_attr) {
+      cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(66 * (WG_KC + 1) * sizeof(float)));
+      wg_attr = true;
+    }
+    k_wgrad_partial<<<dim3(wk.n_chunks, wk.n_tasks), 256, slab, s>>>(wk);
+    k_wgrad_final<<<(wk.n_pairs + 255) / 256, 256, 0, s>>>(wk);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(err));
   }
