@@ -337,14 +337,23 @@ using Ev1P = Ev1T<true>;
 //            every lane forms its own block of outputs from its column chunk of w1;
 //   layer 3: partial dot products over the own block + butterfly all-reduce.
 // The backward sweep mirrors this with the transposed products.
-template <int L_>
-struct EvL {
+// DUMP (training loss): every lane also streams the rows of its own hidden units -- and its share of the
+// replicated input / output rows -- of [in | h1 | h2 | c1 | g2 | gout] for the weight-gradient kernels (K5).
+template <int L_, bool DUMP_ = false>
+struct EvLT {
   static constexpr int L = L_;
-  static constexpr bool PGRAD = false;
+  static constexpr bool PGRAD = DUMP_, DUMP = DUMP_;
   static_assert(L_ == 2 || L_ == 4 || L_ == 8 || L_ == 16, "lanes per sample");
   struct Ctx {
     int l;             // lane within the sample's group
     float d1[32 / L_ > 0 ? 32 / L_ : 1], d2[32 / L_ > 0 ? 32 / L_ : 1];  // act' of the own blocks (KEEP)
+    float* dnet[3];    // DUMP: see Scratch
+    size_t dstride, dcol;
+    SDE4_DEV void dump(int slot_, int row, float v) const { dnet[slot_][(size_t)row * dstride + dcol] = v; }
+    // a replicated row (inputs, output cotangents): written by lane (k mod L)
+    SDE4_DEV void dump_rep(int slot_, int row0, int k, float v) const {
+      if ((k & (L_ - 1)) == l) dump(slot_, row0 + k, v);
+    }
   };
   template <class N>
   static constexpr bool ok() {
@@ -421,9 +430,10 @@ struct EvL {
   // backward tail: g2own (cotangent of own a2 block) -> gin (replicated)
   //   c1own[m] = d1[m] * sum_j w1[l*B1+m][j] * g2[j]   (g2 gathered over the lanes)
   template <class N>
-  SDE4_DEV static void bwd_tail(const NetRef& r, int l, const float (&g2)[N::H2 / L], const float (&d1)[N::H1 / L],
+  SDE4_DEV static void bwd_tail(const NetRef& r, const Ctx& c, const float (&g2)[N::H2 / L], const float (&d1)[N::H1 / L],
                                 float (&gin)[N::IN]) {
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    const int l = c.l;
     float gall[N::H2];
     all_gather<B2>(g2, gall);
     float c1[B1];
@@ -441,6 +451,7 @@ struct EvL {
         }
       }
       c1[m] = (a0 + a1) * d1[m];
+      if constexpr (DUMP) c.dump(r.slot, N::R_C1 + l * B1 + m, c1[m]);
     }
     const float* w0 = r.w + N::OFF_W0 + l * B1;
 #pragma unroll
@@ -457,17 +468,23 @@ struct EvL {
     static_assert(ok<N>(), "hidden widths must be multiples of the lane count");
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
     float a1[B1], a2[B2];
+    if constexpr (DUMP && KEEP) {
+#pragma unroll
+      for (int k = 0; k < N::IN; ++k) c.dump_rep(r.slot, N::R_IN, k, in[k]);
+    }
     layer1<N>(r, c.l, in, a1);
 #pragma unroll
     for (int m = 0; m < B1; ++m) {
       if (KEEP) act_fwd_d<N::ACT>(a1[m], a1[m], c.d1[m]);
       else a1[m] = act_fwd<N::ACT>(a1[m]);
+      if constexpr (DUMP && KEEP) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
     }
     layer2<N>(r, c.l, a1, a2);
 #pragma unroll
     for (int m = 0; m < B2; ++m) {
       if (KEEP) act_fwd_d<N::ACT>(a2[m], a2[m], c.d2[m]);
       else a2[m] = act_fwd<N::ACT>(a2[m]);
+      if constexpr (DUMP && KEEP) c.dump(r.slot, N::R_H2 + c.l * B2 + m, a2[m]);
     }
     layer3<N>(r, c.l, a2, out);
   }
@@ -476,16 +493,21 @@ struct EvL {
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
     float g2[B2], d1[B1];
     const float* w2 = r.w + N::OFF_W2 + c.l * B2;
+    if constexpr (DUMP) {
+#pragma unroll
+      for (int o = 0; o < N::OUT; ++o) c.dump_rep(r.slot, N::R_GOUT, o, gout[o]);
+    }
 #pragma unroll
     for (int m = 0; m < B2; ++m) {
       float s = 0.0f;
 #pragma unroll
       for (int o = 0; o < N::OUT; ++o) s = fmaf(w2[o * N::H2P + m], gout[o], s);
       g2[m] = s * c.d2[m];
+      if constexpr (DUMP) c.dump(r.slot, N::R_G2 + c.l * B2 + m, g2[m]);
     }
 #pragma unroll
     for (int m = 0; m < B1; ++m) d1[m] = c.d1[m];
-    bwd_tail<N>(r, c.l, g2, d1, gin);
+    bwd_tail<N>(r, c, g2, d1, gin);
   }
   template <class N>
   SDE4_DEV static void fwd_vjp(const NetRef& r, Ctx& c, const float (&in)[N::IN], const float (&gout)[N::OUT],
@@ -493,9 +515,18 @@ struct EvL {
     static_assert(ok<N>(), "hidden widths must be multiples of the lane count");
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
     float a1[B1], d1[B1], a2[B2];
+    if constexpr (DUMP) {
+#pragma unroll
+      for (int k = 0; k < N::IN; ++k) c.dump_rep(r.slot, N::R_IN, k, in[k]);
+#pragma unroll
+      for (int o = 0; o < N::OUT; ++o) c.dump_rep(r.slot, N::R_GOUT, o, gout[o]);
+    }
     layer1<N>(r, c.l, in, a1);
 #pragma unroll
-    for (int m = 0; m < B1; ++m) act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
+    for (int m = 0; m < B1; ++m) {
+      act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
+      if constexpr (DUMP) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+    }
     layer2<N>(r, c.l, a1, a2);
     const float* w2 = r.w + N::OFF_W2 + c.l * B2;
 #pragma unroll
@@ -506,8 +537,12 @@ struct EvL {
 #pragma unroll
       for (int o = 0; o < N::OUT; ++o) s = fmaf(w2[o * N::H2P + m], gout[o], s);
       a2[m] = s * dd;
+      if constexpr (DUMP) {
+        c.dump(r.slot, N::R_H2 + c.l * B2 + m, h);
+        c.dump(r.slot, N::R_G2 + c.l * B2 + m, a2[m]);
+      }
     }
-    bwd_tail<N>(r, c.l, a2, d1, gin);
+    bwd_tail<N>(r, c, a2, d1, gin);
   }
   template <class N, class GdFn>
   SDE4_DEV static void scalar_value_grad(const NetRef& r, Ctx& c, const float (&in)[N::IN], float& out,
@@ -515,9 +550,16 @@ struct EvL {
     static_assert(N::OUT == 1 && ok<N>(), "scalar-output network with lane-divisible widths expected");
     constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
     float a1[B1], d1[B1], a2[B2];
+    if constexpr (DUMP) {
+#pragma unroll
+      for (int k = 0; k < N::IN; ++k) c.dump_rep(r.slot, N::R_IN, k, in[k]);
+    }
     layer1<N>(r, c.l, in, a1);
 #pragma unroll
-    for (int m = 0; m < B1; ++m) act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
+    for (int m = 0; m < B1; ++m) {
+      act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
+      if constexpr (DUMP) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+    }
     layer2<N>(r, c.l, a1, a2);
     const float* w2 = r.w + N::OFF_W2 + c.l * B2;
     float o = 0.0f;
@@ -527,13 +569,20 @@ struct EvL {
       act_fwd_d<N::ACT>(a2[m], h, dd);
       o = fmaf(w2[m], h, o);
       a2[m] = w2[m] * dd;
+      if constexpr (DUMP) c.dump(r.slot, N::R_H2 + c.l * B2 + m, h);
     }
     out = all_reduce(o) + r.w[N::OFF_B2];
     const float gd = gd_of(out);
 #pragma unroll
-    for (int m = 0; m < B2; ++m) a2[m] *= gd;
-    bwd_tail<N>(r, c.l, a2, d1, J);
+    for (int m = 0; m < B2; ++m) {
+      a2[m] *= gd;
+      if constexpr (DUMP) c.dump(r.slot, N::R_G2 + c.l * B2 + m, a2[m]);
+    }
+    if constexpr (DUMP) c.dump_rep(r.slot, N::R_GOUT, 0, gd);
+    bwd_tail<N>(r, c, a2, d1, J);
   }
 };
+template <int L_>
+using EvL = EvLT<L_, false>;
 
 }  // namespace sde4

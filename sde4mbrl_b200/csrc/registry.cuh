@@ -20,6 +20,9 @@ struct ArchEntry {
   cudaError_t (*launch_cost[5])(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
                                 bool grad, bool constr, int blocks, int threads, cudaStream_t);
   // training loss (value + input gradient + parameter-gradient streams); null = not compiled
+  int loss_lanes;  // lanes per sample of launch_loss_ls (0: none compiled)
+  cudaError_t (*launch_loss_ls)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&, int, int,
+                                cudaStream_t);
   cudaError_t (*launch_loss)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
                              int blocks, int threads, cudaStream_t);
   int net_dims[3][4];   // IN, H1, H2, OUT of density / net A / net B (0 = absent)
@@ -126,6 +129,12 @@ template <class M>
 cudaError_t launch_loss_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td, const CostK& a,
                           int blocks, int threads, cudaStream_t s) {
   const size_t sm = smem_bytes<M>(threads);
+  if constexpr (M::Ev::L > 1) {
+    if (a.noise_mode == SDE4_NOISE_THREEFRY) {  // straight-line instantiation (noise generated one step ahead)
+      k_cost<M, true, false, 1><<<blocks, threads, sm, s>>>(d, cd, td, a);
+      return cudaGetLastError();
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_cost<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256));
@@ -145,7 +154,8 @@ void add_lane_variant(ArchEntry& e) {
   }
 }
 
-template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit, class MTRAIN = NoLaneSplit, class MLS3 = NoLaneSplit>
+template <class M, class MLS = NoLaneSplit, class MLS2 = NoLaneSplit, class MTRAIN = NoLaneSplit, class MLS3 = NoLaneSplit,
+          class MTRAINLS = NoLaneSplit>
 ArchEntry make_entry(const char* name) {
   using A = typename M::A;
   ArchEntry e;
@@ -174,6 +184,12 @@ ArchEntry make_entry(const char* name) {
   add_lane_variant<MLS3>(e);
   e.launch_loss = nullptr;
   if constexpr (!std::is_same<MTRAIN, NoLaneSplit>::value) e.launch_loss = &launch_loss_t<MTRAIN>;
+  e.launch_loss_ls = nullptr;
+  e.loss_lanes = 0;
+  if constexpr (!std::is_same<MTRAINLS, NoLaneSplit>::value) {
+    e.launch_loss_ls = &launch_loss_t<MTRAINLS>;
+    e.loss_lanes = MTRAINLS::Ev::L;
+  }
   using D = typename A::DNet;
   using NA = typename A::NetA;
   using NB = typename A::NetB;
@@ -198,9 +214,11 @@ struct ArchRegistrar {
 #define SDE4_REGISTER_TRAIN(NAME, MODEL_T, ARCH)                                                     \
   static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, ::sde4::NoLaneSplit, ::sde4::NoLaneSplit, \
                                                               MODEL_T<ARCH, ::sde4::Ev1P>>(#NAME));
+// one-thread-per-sample + LANES-lane kernels for rollout / cost AND for the training loss (latency-bound minibatches)
 #define SDE4_REGISTER_TRAIN_LS(NAME, MODEL_T, ARCH, LANES)                                             \
   static ::sde4::ArchRegistrar reg_##NAME(                                                             \
-      ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>, ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::Ev1P>>(#NAME));
+      ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>, ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::Ev1P>, \
+                         ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::EvLT<LANES, true>>>(#NAME));
 #define SDE4_REGISTER_LS(NAME, MODEL_T, ARCH, LANES) \
   static ::sde4::ArchRegistrar reg_##NAME(::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES>>>(#NAME));
 #define SDE4_REGISTER_LS2(NAME, MODEL_T, ARCH, LANES_A, LANES_B)                                          \

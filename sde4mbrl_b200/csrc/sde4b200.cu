@@ -322,7 +322,12 @@ size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_
   const size_t K = (size_t)B * N * H;
   const size_t dump = loss_dump_floats(*e, K, off) * 4;
   const size_t partial = ((K + WG_KC - 1) / WG_KC) * (size_t)loss_wgrad_pairs(*e) * 4;
-  return cost_layout(*e, B, N, H, 0, true, false, SDE4_NOISE_THREEFRY, 1).total + ((dump + 255) & ~(size_t)255) + partial;
+  size_t lay = cost_layout(*e, B, N, H, 0, true, false, SDE4_NOISE_THREEFRY, 1).total;
+  if (e->loss_lanes > 1) {
+    const size_t l2 = cost_layout(*e, B, N, H, 0, true, false, SDE4_NOISE_THREEFRY, e->loss_lanes).total;
+    if (l2 > lay) lay = l2;
+  }
+  return lay + ((dump + 255) & ~(size_t)255) + partial;
 }
 
 int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* a, float* grad_params, void* stream) {
@@ -357,7 +362,9 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     if (!e->launch_loss) return fail(SDE4_ERR_UNSUPPORTED, "no training-loss kernel compiled for %s", e->name);
     if (constr || cd.kind != SDE4_COST_QUADRATIC || a->xtraj) return fail(SDE4_ERR_INVALID, "training loss: QUADRATIC data cost, no constraints, no xtraj");
   }
-  const int lanes = lo.enabled ? 1 : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
+  // training loss: the lane-split kernel while the minibatch is latency bound (G*L <= 64 k threads)
+  const int lanes = lo.enabled ? ((e->launch_loss_ls && a->lanes != 1 && G * e->loss_lanes <= 65536) ? e->loss_lanes : 1)
+                               : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
   size_t dump_off[3] = {0, 0, 0};
@@ -425,7 +432,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   cudaError_t err;
   if (lo.enabled) {
     err = cudaMemsetAsync(dump_base, 0, dump_bytes, s);  // rows of networks that are not evaluated (ODE mode) stay 0
-    if (err == cudaSuccess) err = e->launch_loss(*model, cd, td, k, blocks, threads, s);
+    if (err == cudaSuccess) err = (lanes > 1 ? e->launch_loss_ls : e->launch_loss)(*model, cd, td, k, blocks, threads, s);
   } else {
     err = e->launch_cost[ilog2(lanes)](*model, cd, td, k, grad, constr, blocks, threads, s);
   }

@@ -30,7 +30,10 @@ def as_f32(x, device=None):
         if x.is_cuda and x.dtype == torch.float32 and device is None:
             return x
         return x.to(device=_dev() if device is None else device, dtype=torch.float32)
-    return torch.as_tensor(np.asarray(x, dtype=np.float32), device=_dev() if device is None else device)
+    arr = np.asarray(x, dtype=np.float32)
+    if not arr.flags.writeable:  # torch refuses to alias read-only arrays silently
+        arr = arr.copy()
+    return torch.as_tensor(arr, device=_dev() if device is None else device)
 
 
 def as_key(k, device=None):
@@ -339,7 +342,7 @@ class Engine:
         return cost, grad, xtraj
 
     # ---- K2 (training variant) + K3 + K5 -----------------------------------
-    def loss_grad(self, nn_params, ymeas, u, dt, data_cost, key, N=1, noise=None, noise_mode=None, block_threads=0):
+    def loss_grad(self, nn_params, ymeas, u, dt, data_cost, key, N=1, noise=None, noise_mode=None, block_threads=0, lanes=0):
         """Data term of the training loss and its gradient w.r.t. the PACKED parameter block.
         ymeas[B, H+1, n_x] (rows = solver steps), u[B, H, n_u], key[B, 2] = split(rng, B).
         Returns (loss[B], grad_packed[param_total]); d(mean_b loss)/d params = grad_packed."""
@@ -381,5 +384,6 @@ class Engine:
         a.cost = _ptr(loss)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
         a.block_threads = block_threads
+        a.lanes = lanes  # 0: lane-split training kernel while the minibatch is latency bound; 1: one thread per sample
         L.check(lib.sde4_loss_grad(C.byref(self.desc), C.byref(a), _ptr(gpar), _stream()))
         return loss, gpar

@@ -116,3 +116,29 @@ def test_density_regulariser_terms_and_grads(cuda, mu_type, N):
         for k, v in d.items():
             want = v.grad.numpy() if v.grad is not None else np.zeros(v.shape)
             assert np.max(np.abs(grads[m][k] - want)) <= 3e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (m, k)
+
+
+@pytest.mark.parametrize("kind,cls,B,N,H", [("cartpole", sde_models.CartPoleSDE, 9, 2, 12), ("cartpole_bb", sde_models.CartPoleSDE, 33, 1, 30)])
+def test_lane_split_training_kernel_matches_one_thread_per_sample(cuda, kind, cls, B, N, H):
+    """The lane-split training kernel (EvLT<L, true>: every lane streams the rows of its own hidden units) and the
+    one-thread-per-sample one give the same loss and parameter gradients."""
+    from sde4mbrl_b200 import costs
+    from sde4mbrl_b200.engine import Engine
+    pm = hp.KINDS[kind][0](horizon=H, num_particles=N)
+    model = cls(pm)
+    nn = configs.random_params(model, seed=6)
+    eng = Engine(model)
+    rng = np.random.default_rng(2)
+    y = (rng.normal(0, 0.5, (B, H + 1, 4)) + np.array([0, 0, 3.0, 0])).astype(np.float32)
+    u = rng.uniform(-1, 1, (B, H, 1)).astype(np.float32)
+    ow = np.array([9, 5, 1, 1.0, 10])
+    dc = costs.QuadraticCost(list(1.0 / ow ** 2), [0.0], [0.0], feat="cartpole")
+    keys = tf.split(tf.PRNGKey(8), B)
+    ts = orc.compute_timesteps(pm)
+    l1, g1 = eng.loss_grad(nn, y, u, ts, dc.desc, keys, N=N, lanes=1)
+    l1, g1 = l1.clone(), g1.clone()
+    l0, g0 = eng.loss_grad(nn, y, u, ts, dc.desc, keys, N=N, lanes=0)
+    assert hp.rel_err(l0.cpu().numpy(), l1.cpu().numpy()) < 2e-5
+    g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
+    assert np.abs(g1).max() > 0
+    assert np.max(np.abs(g0 - g1)) <= 2e-4 * np.abs(g1).max()
