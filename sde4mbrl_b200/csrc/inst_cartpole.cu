@@ -13,9 +13,9 @@ using CartBbD32 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, CartD32, 0xE, 0xA, true, Ca
 using CartBbD8 = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, CartD8, 0xE, 0xA, true, CartResBb, 0, NoNet, 0>;
 using CartSiOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, SDE4_CART_SIDE_INFO, NoNet, 0, 0, false, CartResSi, 0, CartCtrl, 0>;
 using CartBbOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, NoNet, 0, 0, false, CartResBb, 0, NoNet, 0>;
-// latency-bound single-problem MPC (BASELINE configs[1]) uses the lane-split kernels; the control net of the
-// side-info model (2->6->8) only divides by 2, the black-box nets divide by 8
-SDE4_REGISTER_TRAIN_LS(cartpole_si_d32, CartpoleModel, CartSiD32, 2)
+// latency-bound single-problem MPC (BASELINE configs[1]) and small training minibatches use the lane-split kernels;
+// the control net of the side-info model (2->6->8) is padded to 8 units by the evaluator (nets.cuh, EvLT::blk)
+SDE4_REGISTER_TRAIN_LS(cartpole_si_d32, CartpoleModel, CartSiD32, 8)
 SDE4_REGISTER_TRAIN_LS(cartpole_bb_d32, CartpoleModel, CartBbD32, 8)
 SDE4_REGISTER(cartpole_bb_d8, CartpoleModel<CartBbD8>)
 SDE4_REGISTER(cartpole_si_ode, CartpoleModel<CartSiOde>)

@@ -355,9 +355,23 @@ struct EvLT {
       if ((k & (L_ - 1)) == l) dump(slot_, row0 + k, v);
     }
   };
+  // own block size of a hidden layer of width H: ceil(H / L).  Widths that are not multiples of L are PADDED: the
+  // packed image stores every layer with its width rounded up to a multiple of 4 (zero weights / biases), so ghost
+  // units l*B+m >= H are legal to address as long as L*B <= up4(H); their activations and cotangents are forced to 0.
+  static constexpr int blk(int H) { return (H + L_ - 1) / L_; }
   template <class N>
   static constexpr bool ok() {
-    return N::H1 % L == 0 && N::H2 % L == 0;
+    return blk(N::H1) * L <= N::H1P && blk(N::H2) * L <= N::H2P;
+  }
+  template <int H, int B>
+  SDE4_DEV static float live(int l, int m, float v) {  // v for a real unit, 0 for a ghost one
+    if constexpr (B * L_ == H) return v;
+    else return (l * B + m < H) ? v : 0.0f;
+  }
+  template <int H, int B>
+  SDE4_DEV static bool is_live(int l, int m) {
+    if constexpr (B * L_ == H) return true;
+    else return l * B + m < H;
   }
 
   SDE4_DEV static float all_reduce(float v) {
@@ -368,8 +382,8 @@ struct EvLT {
 
   // layer 1 own block: a1[m] = b0[l*B1+m] + sum_k in[k]*w0[k][l*B1+m]
   template <class N>
-  SDE4_DEV static void layer1(const NetRef& r, int l, const float (&in)[N::IN], float (&a1)[N::H1 / L]) {
-    constexpr int B1 = N::H1 / L;
+  SDE4_DEV static void layer1(const NetRef& r, int l, const float (&in)[N::IN], float (&a1)[EvLT::blk(N::H1)]) {
+    constexpr int B1 = EvLT::blk(N::H1);
     const float* w0 = r.w + N::OFF_W0 + l * B1;
     const float* b0 = r.w + N::OFF_B0 + l * B1;
 #pragma unroll
@@ -396,9 +410,9 @@ struct EvLT {
   //   a2own[m] = b1[l*B2+m] + sum_i h1[i] * w1[i][l*B2+m]
   // (lanes read distinct 4-bank column chunks of distinct rows: conflict free without padding)
   template <class N>
-  SDE4_DEV static void layer2(const NetRef& r, int l, const float (&h1)[N::H1 / L], float (&a2)[N::H2 / L]) {
-    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
-    float hall[N::H1];
+  SDE4_DEV static void layer2(const NetRef& r, int l, const float (&h1)[EvLT::blk(N::H1)], float (&a2)[EvLT::blk(N::H2)]) {
+    constexpr int B1 = EvLT::blk(N::H1), B2 = EvLT::blk(N::H2);
+    float hall[B1 * L];
     all_gather<B1>(h1, hall);
     const float* w1 = r.w + N::OFF_W1 + l * B2;
     const float* b1 = r.w + N::OFF_B1 + l * B2;
@@ -406,18 +420,21 @@ struct EvLT {
     for (int m = 0; m < B2; ++m) a2[m] = b1[m];
 #pragma unroll
     for (int q = 0; q < L; ++q) {
-      const float* wq = w1 + ((l ^ q) * B1) * N::H2P;
 #pragma unroll
       for (int mm = 0; mm < B1; ++mm) {
+        // row of w1 = gathered unit; ghost units (h = 0) are redirected to the last real row (no out-of-image read)
+        int row = (l ^ q) * B1 + mm;
+        if constexpr (B1 * L != N::H1) row = min(row, N::H1 - 1);
+        const float* wq = w1 + row * N::H2P;
 #pragma unroll
-        for (int m = 0; m < B2; ++m) a2[m] = fmaf(hall[q * B1 + mm], wq[mm * N::H2P + m], a2[m]);
+        for (int m = 0; m < B2; ++m) a2[m] = fmaf(hall[q * B1 + mm], wq[m], a2[m]);
       }
     }
   }
   // layer 3: out[o] = b2[o] + sum_j h2[j]*w2T[o][j]
   template <class N>
-  SDE4_DEV static void layer3(const NetRef& r, int l, const float (&h2)[N::H2 / L], float (&out)[N::OUT]) {
-    constexpr int B2 = N::H2 / L;
+  SDE4_DEV static void layer3(const NetRef& r, int l, const float (&h2)[EvLT::blk(N::H2)], float (&out)[N::OUT]) {
+    constexpr int B2 = EvLT::blk(N::H2);
     const float* w2 = r.w + N::OFF_W2 + l * B2;
 #pragma unroll
     for (int o = 0; o < N::OUT; ++o) {
@@ -430,28 +447,32 @@ struct EvLT {
   // backward tail: g2own (cotangent of own a2 block) -> gin (replicated)
   //   c1own[m] = d1[m] * sum_j w1[l*B1+m][j] * g2[j]   (g2 gathered over the lanes)
   template <class N>
-  SDE4_DEV static void bwd_tail(const NetRef& r, const Ctx& c, const float (&g2)[N::H2 / L], const float (&d1)[N::H1 / L],
+  SDE4_DEV static void bwd_tail(const NetRef& r, const Ctx& c, const float (&g2)[EvLT::blk(N::H2)], const float (&d1)[EvLT::blk(N::H1)],
                                 float (&gin)[N::IN]) {
-    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    constexpr int B1 = EvLT::blk(N::H1), B2 = EvLT::blk(N::H2);
     const int l = c.l;
-    float gall[N::H2];
+    float gall[B2 * L];
     all_gather<B2>(g2, gall);
     float c1[B1];
-    const float* w1 = r.w + N::OFF_W1 + (l * B1) * N::H2P;
 #pragma unroll
     for (int m = 0; m < B1; ++m) {
       float a0 = 0.0f, a1 = 0.0f;
+      int row = l * B1 + m;
+      if constexpr (B1 * L != N::H1) row = min(row, N::H1 - 1);  // ghost unit: any real row, the result is masked
+      const float* w1 = r.w + N::OFF_W1 + row * N::H2P;
 #pragma unroll
       for (int q = 0; q < L; ++q) {
-        const float* wq = w1 + m * N::H2P + (l ^ q) * B2;
+        const float* wq = w1 + (l ^ q) * B2;
 #pragma unroll
         for (int mm = 0; mm < B2; ++mm) {
           if ((q & 1) == 0) a0 = fmaf(wq[mm], gall[q * B2 + mm], a0);
           else a1 = fmaf(wq[mm], gall[q * B2 + mm], a1);
         }
       }
-      c1[m] = (a0 + a1) * d1[m];
-      if constexpr (DUMP) c.dump(r.slot, N::R_C1 + l * B1 + m, c1[m]);
+      c1[m] = live<N::H1, B1>(l, m, (a0 + a1) * d1[m]);
+      if constexpr (DUMP) {
+        if (is_live<N::H1, B1>(l, m)) c.dump(r.slot, N::R_C1 + l * B1 + m, c1[m]);
+      }
     }
     const float* w0 = r.w + N::OFF_W0 + l * B1;
 #pragma unroll
@@ -465,8 +486,8 @@ struct EvLT {
 
   template <class N, bool KEEP>
   SDE4_DEV static void fwd(const NetRef& r, Ctx& c, const float (&in)[N::IN], float (&out)[N::OUT]) {
-    static_assert(ok<N>(), "hidden widths must be multiples of the lane count");
-    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    static_assert(ok<N>(), "hidden widths (rounded up to a multiple of 4) must cover ceil(H/L)*L units");
+    constexpr int B1 = EvLT::blk(N::H1), B2 = EvLT::blk(N::H2);
     float a1[B1], a2[B2];
     if constexpr (DUMP && KEEP) {
 #pragma unroll
@@ -477,20 +498,26 @@ struct EvLT {
     for (int m = 0; m < B1; ++m) {
       if (KEEP) act_fwd_d<N::ACT>(a1[m], a1[m], c.d1[m]);
       else a1[m] = act_fwd<N::ACT>(a1[m]);
-      if constexpr (DUMP && KEEP) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+      a1[m] = live<N::H1, B1>(c.l, m, a1[m]);
+      if constexpr (DUMP && KEEP) {
+        if (is_live<N::H1, B1>(c.l, m)) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+      }
     }
     layer2<N>(r, c.l, a1, a2);
 #pragma unroll
     for (int m = 0; m < B2; ++m) {
       if (KEEP) act_fwd_d<N::ACT>(a2[m], a2[m], c.d2[m]);
       else a2[m] = act_fwd<N::ACT>(a2[m]);
-      if constexpr (DUMP && KEEP) c.dump(r.slot, N::R_H2 + c.l * B2 + m, a2[m]);
+      a2[m] = live<N::H2, B2>(c.l, m, a2[m]);
+      if constexpr (DUMP && KEEP) {
+        if (is_live<N::H2, B2>(c.l, m)) c.dump(r.slot, N::R_H2 + c.l * B2 + m, a2[m]);
+      }
     }
     layer3<N>(r, c.l, a2, out);
   }
   template <class N>
   SDE4_DEV static void bwd(const NetRef& r, Ctx& c, const float (&gout)[N::OUT], float (&gin)[N::IN]) {
-    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    constexpr int B1 = EvLT::blk(N::H1), B2 = EvLT::blk(N::H2);
     float g2[B2], d1[B1];
     const float* w2 = r.w + N::OFF_W2 + c.l * B2;
     if constexpr (DUMP) {
@@ -502,8 +529,10 @@ struct EvLT {
       float s = 0.0f;
 #pragma unroll
       for (int o = 0; o < N::OUT; ++o) s = fmaf(w2[o * N::H2P + m], gout[o], s);
-      g2[m] = s * c.d2[m];
-      if constexpr (DUMP) c.dump(r.slot, N::R_G2 + c.l * B2 + m, g2[m]);
+      g2[m] = live<N::H2, B2>(c.l, m, s * c.d2[m]);
+      if constexpr (DUMP) {
+        if (is_live<N::H2, B2>(c.l, m)) c.dump(r.slot, N::R_G2 + c.l * B2 + m, g2[m]);
+      }
     }
 #pragma unroll
     for (int m = 0; m < B1; ++m) d1[m] = c.d1[m];
@@ -512,8 +541,8 @@ struct EvLT {
   template <class N>
   SDE4_DEV static void fwd_vjp(const NetRef& r, Ctx& c, const float (&in)[N::IN], const float (&gout)[N::OUT],
                                float (&gin)[N::IN]) {
-    static_assert(ok<N>(), "hidden widths must be multiples of the lane count");
-    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    static_assert(ok<N>(), "hidden widths (rounded up to a multiple of 4) must cover ceil(H/L)*L units");
+    constexpr int B1 = EvLT::blk(N::H1), B2 = EvLT::blk(N::H2);
     float a1[B1], d1[B1], a2[B2];
     if constexpr (DUMP) {
 #pragma unroll
@@ -525,7 +554,10 @@ struct EvLT {
 #pragma unroll
     for (int m = 0; m < B1; ++m) {
       act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
-      if constexpr (DUMP) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+      a1[m] = live<N::H1, B1>(c.l, m, a1[m]);
+      if constexpr (DUMP) {
+        if (is_live<N::H1, B1>(c.l, m)) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+      }
     }
     layer2<N>(r, c.l, a1, a2);
     const float* w2 = r.w + N::OFF_W2 + c.l * B2;
@@ -536,10 +568,12 @@ struct EvLT {
       float s = 0.0f;
 #pragma unroll
       for (int o = 0; o < N::OUT; ++o) s = fmaf(w2[o * N::H2P + m], gout[o], s);
-      a2[m] = s * dd;
+      a2[m] = live<N::H2, B2>(c.l, m, s * dd);
       if constexpr (DUMP) {
-        c.dump(r.slot, N::R_H2 + c.l * B2 + m, h);
-        c.dump(r.slot, N::R_G2 + c.l * B2 + m, a2[m]);
+        if (is_live<N::H2, B2>(c.l, m)) {
+          c.dump(r.slot, N::R_H2 + c.l * B2 + m, h);
+          c.dump(r.slot, N::R_G2 + c.l * B2 + m, a2[m]);
+        }
       }
     }
     bwd_tail<N>(r, c, a2, d1, gin);
@@ -547,8 +581,8 @@ struct EvLT {
   template <class N, class GdFn>
   SDE4_DEV static void scalar_value_grad(const NetRef& r, Ctx& c, const float (&in)[N::IN], float& out,
                                          float (&J)[N::IN], GdFn gd_of) {
-    static_assert(N::OUT == 1 && ok<N>(), "scalar-output network with lane-divisible widths expected");
-    constexpr int B1 = N::H1 / L, B2 = N::H2 / L;
+    static_assert(N::OUT == 1 && ok<N>(), "scalar-output network with lane-coverable widths expected");
+    constexpr int B1 = EvLT::blk(N::H1), B2 = EvLT::blk(N::H2);
     float a1[B1], d1[B1], a2[B2];
     if constexpr (DUMP) {
 #pragma unroll
@@ -558,7 +592,10 @@ struct EvLT {
 #pragma unroll
     for (int m = 0; m < B1; ++m) {
       act_fwd_d<N::ACT>(a1[m], a1[m], d1[m]);
-      if constexpr (DUMP) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+      a1[m] = live<N::H1, B1>(c.l, m, a1[m]);
+      if constexpr (DUMP) {
+        if (is_live<N::H1, B1>(c.l, m)) c.dump(r.slot, N::R_H1 + c.l * B1 + m, a1[m]);
+      }
     }
     layer2<N>(r, c.l, a1, a2);
     const float* w2 = r.w + N::OFF_W2 + c.l * B2;
@@ -567,16 +604,21 @@ struct EvLT {
     for (int m = 0; m < B2; ++m) {
       float h, dd;
       act_fwd_d<N::ACT>(a2[m], h, dd);
+      h = live<N::H2, B2>(c.l, m, h);
       o = fmaf(w2[m], h, o);
-      a2[m] = w2[m] * dd;
-      if constexpr (DUMP) c.dump(r.slot, N::R_H2 + c.l * B2 + m, h);
+      a2[m] = live<N::H2, B2>(c.l, m, w2[m] * dd);
+      if constexpr (DUMP) {
+        if (is_live<N::H2, B2>(c.l, m)) c.dump(r.slot, N::R_H2 + c.l * B2 + m, h);
+      }
     }
     out = all_reduce(o) + r.w[N::OFF_B2];
     const float gd = gd_of(out);
 #pragma unroll
     for (int m = 0; m < B2; ++m) {
       a2[m] *= gd;
-      if constexpr (DUMP) c.dump(r.slot, N::R_G2 + c.l * B2 + m, a2[m]);
+      if constexpr (DUMP) {
+        if (is_live<N::H2, B2>(c.l, m)) c.dump(r.slot, N::R_G2 + c.l * B2 + m, a2[m]);
+      }
     }
     if constexpr (DUMP) c.dump_rep(r.slot, N::R_GOUT, 0, gd);
     bwd_tail<N>(r, c, a2, d1, J);

@@ -72,15 +72,16 @@ def test_lane_split_cost_grad(cuda, kind, H, N):
 def test_requesting_missing_lane_kernel_is_an_error(cuda):
     from sde4mbrl_b200.engine import Engine
     from sde4mbrl_b200._lib import Sde4Error
-    pm, model, nn = hp.build("cartpole", 5, 2, seed=1)
+    pm, model, nn = hp.build("cartpole", 5, 2, seed=1)  # compiled with 1 and 8 lanes per sample, not 4
     with pytest.raises(Sde4Error):
         Engine(model).rollout(nn, np.zeros((1, 4), np.float32), np.zeros((5, 1), np.float32),
-                              orc.compute_timesteps(pm), key=tf.PRNGKey(0), N=2, lanes=8)
+                              orc.compute_timesteps(pm), key=tf.PRNGKey(0), N=2, lanes=4)
 
 
-@pytest.mark.parametrize("kind,lanes,H,N", [("cartpole", 2, 50, 37), ("cartpole_bb", 8, 30, 21)])
+@pytest.mark.parametrize("kind,lanes,H,N", [("cartpole", 8, 50, 37), ("cartpole_bb", 8, 30, 21)])
 def test_lane_split_cartpole(cuda, kind, lanes, H, N):
-    """Cartpole lane-split kernels (side-info: 2 lanes, black-box: 8 lanes) vs the one-thread-per-sample ones."""
+    """Cartpole lane-split kernels (8 lanes; the 2->6->8 control net of the side-info model runs PADDED: 6 real + 2 ghost
+    units) vs the one-thread-per-sample ones."""
     from sde4mbrl_b200.engine import Engine
     rng = np.random.default_rng(7)
     pm, model, nn = hp.build(kind, H, N, seed=5)
