@@ -474,6 +474,34 @@ def main():
         except Exception as ex:
             c2_extra = {"error": repr(ex)}
 
+    # ---- BASELINE configs[0]: mass-spring-damper nSDE, 200 particles x 100-step Euler-Maruyama rollout (the case the
+    # reference runs on CPU via JAX), device time of one rollout call
+    msd_extra = {}
+    if rank == 0:
+        try:
+            pmm0 = configs.msd_model(horizon=100, num_particles=200)
+            mm0 = sde_models.MassSpringDamper(pmm0)
+            engm0 = Engine(mm0)
+            pkm0 = PackedParams(mm0, configs.random_params(mm0, seed=0), engm0.desc)
+            y0m0 = torch.tensor([[0.05, -0.02]], device=dev)
+            um0 = torch.zeros((100, 1), device=dev)
+            tsm0 = np.full(100, float(pmm0["stepsize"]), np.float32)
+            km0 = torch.as_tensor(np.array([0, 1], np.uint32).view(np.int32), device=dev)
+            outm0 = torch.empty((101, 2, 200), device=dev)
+            tms = []
+            for rep in range(13):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                engm0.rollout(pkm0, y0m0, um0, tsm0, key=km0, N=200, out=outm0)
+                e1.record()
+                torch.cuda.synchronize()
+                if rep > 2:
+                    tms.append(e0.elapsed_time(e1))
+            msd_extra = {"particles": 200, "horizon": 100, "ms": float(np.mean(tms)),
+                         "particle_steps_per_s": 200 * 100 / (float(np.mean(tms)) * 1e-3)}
+        except Exception as ex:
+            msd_extra = {"error": repr(ex)}
+
     # ---- latency of ONE hexacopter MPC solve as the reference deploys it (mpc_test_cfg.yaml: H=20, dt=0.05, 1 particle;
     # also 32 and 1024 particles), 20 APG iterations, device-side APG (one CUDA-graph replay per iteration)
     single_extra = {}
@@ -597,6 +625,7 @@ def main():
         if cpu_b:
             line["cpu_baseline"] = cpu_b
         line.update(extras)
+        line["msd_rollout"] = msd_extra
         line["cartpole_mpc_single"] = c2_extra
         line["hexa_mpc_single"] = single_extra
         line["mpc_batch"] = mpc_extra
