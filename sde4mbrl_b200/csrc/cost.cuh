@@ -28,12 +28,14 @@ SDE4_DEV float shaped(float e, float w, float wsig, bool sig, float& dde) {
 
 // Stage cost c(x, u, xref) and (optionally) its gradient scaled by `wt`:
 //   gx += wt * dc/dx,  gu += wt * dc/du.
-// PLAIN (13-state models): the caller guarantees kind == ROTOR_TRACK without sigmoid / tanh shaping, which makes
-// the evaluation branch free (the lane-split kernels rely on straight-line loop bodies, see kernels.cuh).
+// PLAIN: the caller guarantees the unshaped cost that goes with the model's state dimension -- 13 states: kind ==
+// ROTOR_TRACK without sigmoid / tanh shaping; 4 states: QUADRATIC on the cartpole features; otherwise: QUADRATIC on
+// the state itself -- which makes the evaluation branch free (the lane-split kernels rely on straight-line loop
+// bodies, see kernels.cuh).
 template <int NX, int NU, bool GRAD, bool PLAIN = false>
 SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const float (&u)[NU],
                           const float* __restrict__ xref, bool with_u, float wt, float (&gx)[NX], float (&gu)[NU]) {
-  static_assert(!PLAIN || NX == 13, "plain tracking cost: multirotor states");
+  constexpr bool PLAIN_ROTOR = PLAIN && NX == 13, PLAIN_QUAD = PLAIN && NX != 13;
   float tot = 0.0f;
   float dx[NX], du[NU];  // d tot / d x, d tot / d u  (before the outer shaping)
 #pragma unroll
@@ -41,7 +43,7 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
 #pragma unroll
   for (int j = 0; j < NU; ++j) du[j] = 0.0f;
 
-  if (PLAIN || c.kind == SDE4_COST_ROTOR_TRACK) {
+  if (PLAIN_ROTOR || (!PLAIN && c.kind == SDE4_COST_ROTOR_TRACK)) {
     if constexpr (NX == 13) {
       // p (0-2), v (3-5), w (10-12): squared error times weight
 #pragma unroll
@@ -81,10 +83,10 @@ SDE4_DEV float stage_cost(const sde4_cost_desc& c, const float (&x)[NX], const f
         du[j] = 2.0f * diff * dde;
       }
     }
-  } else if (c.kind == SDE4_COST_QUADRATIC) {
+  } else if (PLAIN_QUAD || c.kind == SDE4_COST_QUADRATIC) {
     bool done = false;
     if constexpr (NX == 4) {
-      if (c.feat == 1) {  // cartpole features [x, xdot, sin th, cos th, thdot]
+      if (PLAIN_QUAD || c.feat == 1) {  // cartpole features [x, xdot, sin th, cos th, thdot]
         float s, co, sr, cr;
         sincosf(x[2], &s, &co);
         sincosf(xref[2], &sr, &cr);

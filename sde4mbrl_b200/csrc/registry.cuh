@@ -77,9 +77,12 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
   if constexpr (M::Ev::L > 1) {
     if (a.noise_mode == SDE4_NOISE_THREEFRY && (!grad || a.dwbuf)) {
       // lane-split + in-kernel noise: the straight-line instantiations (kernels.cuh, MODE 1 / 2)
+      // the unshaped cost that goes with the model (cost.cuh, PLAIN) has a branch-free instantiation
       bool plain = false;
       if constexpr (M::NX == 13) plain = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
-      if constexpr (M::NX == 13) {
+      else if constexpr (M::NX == 4) plain = cd.kind == SDE4_COST_QUADRATIC && cd.feat == 1 && !cd.use_res_sig;
+      else plain = cd.kind == SDE4_COST_QUADRATIC && cd.feat == 0 && !cd.use_res_sig;
+      {
         if (plain) {
           if (grad) {
             if (constr)
