@@ -331,6 +331,10 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
         return (cost, _xtraj_view(xbuf, opt)), grad
 
     multi_sampling.value_and_grad = value_and_grad
+    # what a device-side solver (apg_batched.BatchedAPG) needs to evaluate the same cost without this closure
+    multi_sampling.final_stage = lambda _cost_fn: _cost_fn if constr is None else _costs.with_constraints(_cost_fn, constr, n_u)
+    multi_sampling.num_particles = num_sample
+    multi_sampling.n_opt = opt_params_size
     multi_sampling.engine = engine
     multi_sampling.time_steps = time_steps
 

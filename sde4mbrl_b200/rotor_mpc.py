@@ -214,6 +214,35 @@ def create_full_cost_function(xt, rng, target_x, multi_cost_sampling, cfg_dict, 
     return cost_xt, red_cost_f
 
 
+# The APG solve of ``apg_mpc`` runs on the device-side solver (apg_batched.BatchedAPG with P = 1: line search, prox,
+# momentum and stop test in CUDA kernels, one graph replay per iteration, stop flag polled every few iterations) when
+# the pieces are the ones this module hands out; set to False to force the host ``apg.py`` loop.
+USE_DEVICE_APG = True
+_POLL_EVERY = 4
+
+
+def _device_solver(multi_cost_sampling, cfg_dict, _sde_learned, stage, term, box):
+    from .apg_batched import BatchedAPG
+    import json
+    op = cfg_dict["apg_mpc"]
+    key = (bytes(stage.desc), None if term is None else bytes(term.desc), json.dumps(op, sort_keys=True, default=float),
+           id(_sde_learned))
+    cache = multi_cost_sampling.__dict__.setdefault("_device_solvers", {})
+    solver = cache.get(key)
+    if solver is None:
+        lb = ub = None
+        if box is not None:
+            n = multi_cost_sampling.n_opt
+            lb, ub = np.full(n, -np.inf, np.float32), np.full(n, np.inf, np.float32)
+            lb[box.first:], ub[box.first:] = box.lb_np, box.ub_np
+        if len(cache) > 8:
+            cache.clear()
+        solver = BatchedAPG(multi_cost_sampling.engine, _sde_learned, stage, op, multi_cost_sampling.time_steps,
+                            multi_cost_sampling.num_particles, lb=lb, ub=ub, terminal=term)
+        cache[key] = solver
+    return solver
+
+
 def apg_mpc(xt, rng, past_solution, target_x, multi_cost_sampling, proximal_fn, cfg_dict, _sde_learned,
             _terminal_cost=None, extra_dyn_args=None, convert_to_enu=True, mod_cost_params={}):
     """sde_mpc_design.py:221-262.  Returns ``(uopt[H, n_u], new_solution, rng_next, vehicle_states)``."""
@@ -227,9 +256,23 @@ def apg_mpc(xt, rng, past_solution, target_x, multi_cost_sampling, proximal_fn, 
     cost_xt, red_cost_f = create_full_cost_function(xt, rng, target_x, multi_cost_sampling, cfg_dict, _sde_learned,
                                                     _terminal_cost, extra_dyn_args, convert_x=False,
                                                     mod_cost_params=mod_cost_params)
-    opt_state = init_apg(past_solution.x_opt, cost_xt, cfg_dict["apg_mpc"], momentum=past_solution.momentum,
-                         stepsize=past_solution.avg_stepsize)
-    new_opt_state = apg(opt_state, cost_xt, cfg_dict["apg_mpc"], proximal_fn=proximal_fn)
+    box = getattr(proximal_fn, "box", None)
+    on_device = (USE_DEVICE_APG and extra_dyn_args is None and "linesearch" in cfg_dict["apg_mpc"]
+                 and hasattr(multi_cost_sampling, "final_stage") and (proximal_fn is None or box is not None))
+    if on_device:
+        solver = _device_solver(multi_cost_sampling, cfg_dict, _sde_learned, multi_cost_sampling.final_stage(red_cost_f),
+                                _terminal_cost, box)
+        solver.init(past_solution.x_opt, np.asarray(xt, np.float32)[None], target_x, rng,
+                    momentum=np.float32(past_solution.momentum), stepsize=np.float32(past_solution.avg_stepsize))
+        solver.run(check_every=_POLL_EVERY)
+        st = solver.state_of(0)
+        new_opt_state = st._replace(**{k: getattr(st, k).clone() for k in ("x_opt", "xk", "yk", "grad_yk")})
+        if not isinstance(past_solution.x_opt, torch.Tensor) or not past_solution.x_opt.is_cuda:
+            new_opt_state = new_opt_state._replace(**{k: getattr(new_opt_state, k).cpu() for k in ("x_opt", "xk", "yk", "grad_yk")})
+    else:
+        opt_state = init_apg(past_solution.x_opt, cost_xt, cfg_dict["apg_mpc"], momentum=past_solution.momentum,
+                             stepsize=past_solution.avg_stepsize)
+        new_opt_state = apg(opt_state, cost_xt, cfg_dict["apg_mpc"], proximal_fn=proximal_fn)
     with torch.no_grad():
         _, vehicle_states = multi_cost_sampling(_sde_learned, xt, new_opt_state.x_opt, rng, red_cost_f,
                                                 _terminal_cost=_terminal_cost, extra_dyn_args=extra_dyn_args,
@@ -248,7 +291,10 @@ def load_mpc_from_cfgfile(path_config, convert_to_enu=True, nominal_model=False,
     if cfg_dict["model"].get("control_augmented_state", False):
         raise Sde4Error("control_augmented_state has no compiled kernel")
     cfg_dict["cost_params"].pop("urate_err", None)
-    proximal_fn = None if vmapped_prox is None else (lambda x, stepsize=None: vmapped_prox(x))
+    proximal_fn = None
+    if vmapped_prox is not None:
+        proximal_fn = lambda x, stepsize=None: vmapped_prox(x)
+        proximal_fn.box = vmapped_prox  # lets apg_mpc hand the box to the device-side solver
     cfg_dict["_time_steps"] = np.array(compute_timesteps(cfg_dict["model"]), dtype=np.float32)
     n_u = cfg_dict["model"]["n_u"]
     horizon_keys = {k: cfg_dict["model"][k] for k in ("horizon", "num_short_dt", "short_step_dt", "long_step_dt")}

@@ -110,3 +110,34 @@ def test_trajectory_mode_targets(cuda, tmp_path):
     (uopt, sol, key, states), xref = m_mpc(x, R.PRNGKey(0), sol, curr_t=0.0, return_ref=True)
     np.testing.assert_allclose(xref, get_state_at_t(0.0, _return_evol=True)[1])
     assert tuple(uopt.shape) == (20, 6) and float(sol.opt_cost) <= float(sol.init_cost)
+
+
+def test_apg_mpc_device_solver_matches_host_loop(cuda, tmp_path):
+    """apg_mpc with the device-side solver (default) and with the host apg.py loop: same optimum, same key chain,
+    warm start (momentum / average step size of the previous solution) included."""
+    from sde4mbrl_b200 import random as R, rotor_mpc as rm
+    path, _, _ = _write_cfg(tmp_path)
+    cfg, (m_reset, m_mpc), _, _ = _quiet(rm.load_mpc_from_cfgfile, path, convert_to_enu=False)
+    x = configs.hover_state()
+    x[3:6] = [0.2, -0.1, 0.05]
+    xdes = configs.hover_state()
+    xdes[:3] = [0.0, 0.5, 1.4]
+    res = {}
+    for dev_solver in (True, False):
+        rm.USE_DEVICE_APG = dev_solver
+        try:
+            sol = m_reset(x, uref=np.full(6, 0.33, np.float32))
+            key = R.PRNGKey(5)
+            for _ in range(2):  # the second call starts from the first solution (warm start)
+                uopt, sol, key, states = m_mpc(x, key, sol, xdes=xdes)
+            res[dev_solver] = (uopt.cpu().numpy(), float(sol.opt_cost), int(sol.num_steps), states.cpu().numpy(),
+                               key.cpu().numpy())
+        finally:
+            rm.USE_DEVICE_APG = True
+    ud, cd_, nd, sd, kd = res[True]
+    uh, ch, nh, sh, kh = res[False]
+    np.testing.assert_array_equal(kd, kh)
+    assert nd == nh
+    assert abs(cd_ - ch) <= 2e-4 * abs(ch)
+    assert hp.rel_err(ud, uh) < 5e-3
+    assert hp.rel_err(sd[..., :13], sh[..., :13]) < 5e-3
