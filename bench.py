@@ -55,7 +55,9 @@ def build_workload(seed=0):
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML (what nvidia-smi reads) polled every
+    2 ms from a thread -- the timed region is only ~10-20 ms long; `nvidia-smi` itself (one process per sample) is the
+    fall-back when the NVML binding is missing."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -65,10 +67,34 @@ class ClockSampler:
         self.samples = []
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        nv = self._nvml
+        sm = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        try:
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        except Exception:
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        flag = lambda bit: "Active" if (r & bit) else "Not Active"
+        # bit masks of nvmlClocksEventReasons: SwPowerCap 0x4, HwSlowdown 0x8, SwThermalSlowdown 0x20, HwThermalSlowdown 0x40
+        return [str(sm), str(mx), "", flag(0x8), flag(0x40), flag(0x20), flag(0x4)]
 
     def _run(self):
         while not self._stop.is_set():
             try:
+                if self._nvml is not None:
+                    self.samples.append(self._sample_nvml())
+                    self._stop.wait(0.002)
+                    continue
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 parts = [p.strip() for p in out.strip().split(",")]
@@ -94,7 +120,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+                "reasons": sorted(reasons), "samples": len(self.samples), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 def cpu_reference_step(w, n_particles, threads):
