@@ -139,6 +139,8 @@ typedef struct sde4_cost_desc {
 /* ---- rollout: create_sampling_fn(...).multi_sampling, sde4mbrl/nsde.py:1024-1028
  *      -> sample_sde (:544-556) -> euler_maruyama, sde4mbrl/sde_solver.py:243-317.
  *      One call = P problems x N particles x H steps. */
+enum sde4_solver { SDE4_SOLVER_EULER_MARUYAMA = 0, SDE4_SOLVER_STRAT_HEUN = 1, SDE4_SOLVER_STRAT_MILSTEIN = 2 };
+
 typedef struct sde4_rollout_args {
   int32_t struct_size;          /* sizeof(sde4_rollout_args), ABI check               */
   int32_t P, N, H;
@@ -162,6 +164,12 @@ typedef struct sde4_rollout_args {
   /* lanes per sample: 0 = library heuristic, 1 = one thread per sample, L > 1 = lane-split kernel
    * (only if compiled for this architecture, else an error) */
   int32_t lanes;
+  /* fixed-step scheme, sde4_solver.  EULER_MARUYAMA is the reference's only registered solver
+   * (sde4mbrl/sde_solver.py:243-317, :321-325).  The two Stratonovich schemes exist in the reference as commented-out
+   * code only (sde_solver.py:9-57 Heun, :114-177 derivative-free Milstein); they are offered here as an EXTENSION
+   * of the rollout kernel (no reference to check against; unlike the live Euler-Maruyama step they scale the noise
+   * by sqrt(dt), as the comments do).  The cost / gradient kernels are Euler-Maruyama only. */
+  int32_t solver;
 } sde4_rollout_args;
 
 int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, void* stream);

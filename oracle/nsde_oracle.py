@@ -661,3 +661,44 @@ def training_total(loss_params, dl, loss_data, grad_norm, sconvex, mu, w_loss):
     if loss_params.get("pen_weights", 0) > 0:
         tot = tot + loss_params["pen_weights"] * w_loss
     return tot, {"gradDensity": lgd, "densitySCVEX": lsc, "muCoeff": mum, "lossMuCoeff": lmu}
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's commented-out Stratonovich schemes (never registered, sde_solver.py:321-325): restated for the
+# rollout-only extension of the CUDA kernel.  xi[..., H, n_x] are the standard normals of the rollout.
+# ---------------------------------------------------------------------------------------------
+def stratonovich_heun(model, time_step, y0, us, xi):
+    """sde_solver.py:9-57: dW = sqrt(dt) xi (:37); predictor with (f0, g0), corrector with the averages (:44-49);
+    projection after the step (:50)."""
+    H = len(time_step)
+    x = y0.expand(*xi.shape[:-2], y0.shape[-1]) if y0.dim() == 1 else y0
+    xs = [x]
+    for t in range(H):
+        dt = float(time_step[t])
+        u = us[..., t, :]
+        dw = np.sqrt(np.float32(dt)).item() * xi[..., t, :]
+        f0, g0 = model.compositional_drift(x, u), model.diffusion(x, u)
+        xb = x + f0 * dt + g0 * dw
+        f1, g1 = model.compositional_drift(xb, u), model.diffusion(xb, u)
+        x = model.projection_fn(x + 0.5 * (f0 + f1) * dt + 0.5 * (g0 + g1) * dw)
+        xs.append(x)
+    return torch.stack(xs, dim=-2)
+
+
+def stratonovich_milstein(model, time_step, y0, us, xi):
+    """sde_solver.py:114-177 (derivative-free): xbar = x + f0 dt + g0 sqrt(dt) (:158-161);
+    x+ = x + f0 dt + g0 sqrt(dt) xi + (0.5/sqrt(dt)) (g(xbar) - g0) xi^2 (:165); projection (:166)."""
+    H = len(time_step)
+    x = y0.expand(*xi.shape[:-2], y0.shape[-1]) if y0.dim() == 1 else y0
+    xs = [x]
+    for t in range(H):
+        dt = float(time_step[t])
+        sq = np.sqrt(np.float32(dt)).item()
+        u = us[..., t, :]
+        z = xi[..., t, :]
+        f0, g0 = model.compositional_drift(x, u), model.diffusion(x, u)
+        xt = x + f0 * dt
+        g1 = model.diffusion(xt + g0 * sq, u)
+        x = model.projection_fn(xt + g0 * (sq * z) + (0.5 / sq) * (g1 - g0) * z ** 2)
+        xs.append(x)
+    return torch.stack(xs, dim=-2)

@@ -63,7 +63,13 @@ class RolloutArgs(C.Structure):
                 ("dt", C.c_void_p), ("key", C.c_void_p), ("key_stride_p", C.c_int64),
                 ("rng_mode", C.c_int32), ("noise_mode", C.c_int32), ("noise", C.c_void_p),
                 ("xevol", C.c_void_p), ("x_rows", C.c_int32), ("block_threads", C.c_int32),
-                ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32)]
+                ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32),
+                ("solver", C.c_int32)]
+
+
+SOLVER_EULER_MARUYAMA, SOLVER_STRAT_HEUN, SOLVER_STRAT_MILSTEIN = 0, 1, 2
+SOLVERS = {"euler_maruyama": SOLVER_EULER_MARUYAMA, "stratonovich_heun": SOLVER_STRAT_HEUN,
+           "stratonovich_milstein": SOLVER_STRAT_MILSTEIN}
 
 
 class CostArgs(C.Structure):

@@ -31,6 +31,7 @@ struct RolloutK {
   int P, N, H, G;
   int x_rows, rng_mode, noise_mode;
   int n_off, n_tot;
+  int solver;  // sde4_solver
 };
 
 struct CostK {
@@ -233,6 +234,50 @@ SDE4_DEV float lane_pick(const float (&x)[N], int base, int l) {
   return v[0];
 }
 
+// The two Stratonovich schemes of the reference's commented-out code, offered as an extension of K1 (xi = the
+// step's standard normals).  Heun (sde_solver.py:37-50): dW = sqrt(dt) xi, predictor xb = x + f0 dt + g0 dW,
+// x+ = x + (f0+f1)/2 dt + (g0+g1)/2 dW.  Derivative-free Milstein (:146-169): xb = x + f0 dt + g0 sqrt(dt),
+// x+ = x + f0 dt + g0 sqrt(dt) xi + (0.5/sqrt(dt)) (g(xb) - g0) xi^2.  Projection after the step, as in the comments.
+template <class M>
+SDE4_DEV void strat_step(int solver, const float* W, Tctx<M>& tc, const sde4_model_desc& d, float (&x)[M::NX],
+                         const float (&u)[M::NU], const float (&xi)[M::NX], float dt, bool noisy, float& aux) {
+  constexpr int NX = M::NX;
+  float f0[NX], g0[NX], xb[NX];
+  M::drift(W, tc.ev, d, x, u, f0);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) g0[i] = 0.0f;
+  if (noisy) Diffusion<M>::fwd(W, tc.ev, d, x, g0);
+  const float sq = sqrtf(dt);
+  if (solver == SDE4_SOLVER_STRAT_HEUN) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xb[i] = fmaf(g0[i], noisy ? sq * xi[i] : 0.0f, fmaf(f0[i], dt, x[i]));
+    float f1[NX], g1[NX];
+    M::drift(W, tc.ev, d, xb, u, f1);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) g1[i] = 0.0f;
+    if (noisy) Diffusion<M>::fwd(W, tc.ev, d, xb, g1);
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+      x[i] = fmaf(0.5f * (g0[i] + g1[i]), noisy ? sq * xi[i] : 0.0f, fmaf(0.5f * (f0[i] + f1[i]), dt, x[i]));
+  } else {
+    float g1[NX], xt[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      xt[i] = fmaf(f0[i], dt, x[i]);
+      xb[i] = fmaf(g0[i], sq, xt[i]);
+      g1[i] = 0.0f;
+    }
+    if (noisy) Diffusion<M>::fwd(W, tc.ev, d, xb, g1);
+    const float c = 0.5f / sq;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      const float z = noisy ? xi[i] : 0.0f;
+      x[i] = fmaf(c * (g1[i] - g0[i]), z * z, fmaf(g0[i], sq * z, xt[i]));
+    }
+  }
+  M::project(x, aux);
+}
+
 // state rows of one time slice: element i is written by lane (i mod L) of the sample's group (the state is
 // replicated over the group; every lane selects its ceil(NX/L) elements and issues that many stores)
 template <class M>
@@ -302,7 +347,8 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
       if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, (unsigned)a.G, g, nzmask, tc, dw, nullptr);
     }
     float aux;
-    em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
+    if (TFP || a.solver == SDE4_SOLVER_EULER_MARUYAMA) em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
+    else strat_step<M>(a.solver, W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
     store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
   }
 }

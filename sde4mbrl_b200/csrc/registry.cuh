@@ -51,7 +51,7 @@ cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int bl
     attr_set = true;
   }
   if constexpr (M::Ev::L > 1) {
-    if (a.noise_mode == SDE4_NOISE_THREEFRY) {  // lane-split + in-kernel noise: the pipelined-noise instantiation
+    if (a.noise_mode == SDE4_NOISE_THREEFRY && a.solver == SDE4_SOLVER_EULER_MARUYAMA) {  // pipelined-noise instantiation
       k_rollout<M, true><<<blocks, threads, sm, s>>>(d, a);
       return cudaGetLastError();
     }

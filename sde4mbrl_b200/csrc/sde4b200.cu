@@ -182,6 +182,8 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void*
   k.n_off = a->particle_total > 0 ? a->particle_offset : 0;
   k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
+  if (a->solver < SDE4_SOLVER_EULER_MARUYAMA || a->solver > SDE4_SOLVER_STRAT_MILSTEIN) return fail(SDE4_ERR_INVALID, "unknown solver");
+  k.solver = a->solver;
   const int lanes = pick_lanes(*e, a->lanes, G, false);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const long long nthr = G * lanes;

@@ -139,9 +139,14 @@ class Engine:
             self._ws = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=_dev())
         return self._ws
 
+    def _em_only(self):
+        if self.model.params.get("sde_solver", "euler_maruyama") != "euler_maruyama":
+            raise Sde4Error("the cost / gradient / training kernels integrate with euler_maruyama only "
+                            "(the Stratonovich schemes are a rollout-only extension)")
+
     # ---- K1 --------------------------------------------------------------
     def rollout(self, nn_params, y0, u, dt, key=None, N=1, noise=None, noise_mode=None, x_rows=None,
-                block_threads=0, out=None, particle_offset=0, particle_total=0, lanes=0):
+                block_threads=0, out=None, particle_offset=0, particle_total=0, lanes=0, solver=None):
         """y0[P,n_x], u[P,H,n_u] (or [H,n_u], shared), key [2] or [P,2].  Returns the native
         buffer ``xevol[H+1, x_rows, P*N]`` (sample-minor)."""
         pk = self.packed(nn_params)
@@ -187,6 +192,10 @@ class Engine:
         a.rng_mode, a.noise_mode = self.rng_mode, noise_mode
         a.xevol, a.x_rows, a.block_threads = _ptr(out), x_rows, block_threads
         a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
+        name = self.model.params.get("sde_solver", "euler_maruyama") if solver is None else solver
+        if name not in L.SOLVERS:
+            raise Sde4Error("unknown sde_solver '%s' (known: %s)" % (name, ", ".join(L.SOLVERS)))
+        a.solver = L.SOLVERS[name]
         L.check(L.load().sde4_rollout(C.byref(self.desc), C.byref(a), _stream()))
         return out
 
@@ -196,6 +205,7 @@ class Engine:
                   particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None):
         """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
         Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
+        self._em_only()
         pk = self.packed(nn_params)
         y0 = as_f32(y0).reshape(-1, self.n_x).contiguous()
         P = y0.shape[0]
@@ -275,6 +285,7 @@ class Engine:
         tensors): ``sde4_cost_grad_host`` packs them into a pinned staging buffer, does one H2D copy,
         the launches, one D2H copy of [cost | grad] and a stream synchronise.  Returns numpy
         ``cost[P]``, ``grad`` (shape of ``opt``) or None, and the device ``xtraj`` or None."""
+        self._em_only()
         pk = self.packed(nn_params)
         y0 = host_f32(y0).reshape(-1, self.n_x)
         P = y0.shape[0]
@@ -346,6 +357,7 @@ class Engine:
         """Data term of the training loss and its gradient w.r.t. the PACKED parameter block.
         ymeas[B, H+1, n_x] (rows = solver steps), u[B, H, n_u], key[B, 2] = split(rng, B).
         Returns (loss[B], grad_packed[param_total]); d(mean_b loss)/d params = grad_packed."""
+        self._em_only()
         pk = self.packed(nn_params)
         ymeas = as_f32(ymeas).contiguous()
         B = ymeas.shape[0]

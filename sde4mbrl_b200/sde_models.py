@@ -54,9 +54,10 @@ class ControlledSDE:
         for k in ("n_x", "n_u", "n_y", "horizon", "stepsize"):
             if k not in params:
                 raise AssertionError("'%s' must be specified in the params" % k)
-        if params.get("sde_solver", "euler_maruyama") != "euler_maruyama":
-            # sde_solver.py:321-325: euler_maruyama is the only registered solver
-            raise Sde4Error("only 'euler_maruyama' is a registered sde_solver")
+        if params.get("sde_solver", "euler_maruyama") not in L.SOLVERS:
+            # sde_solver.py:321-325: euler_maruyama is the reference's only registered solver; the two Stratonovich
+            # schemes of its commented-out code are offered as an extension of the ROLLOUT kernel (sde4b200.h)
+            raise Sde4Error("unknown sde_solver '%s' (known: %s)" % (params["sde_solver"], ", ".join(L.SOLVERS)))
         if params["n_x"] != params["n_y"]:
             raise Sde4Error("only identity observation maps are supported (n_x == n_y)")
         if params.get("control_dependent_noise", False):

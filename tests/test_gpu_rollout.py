@@ -88,3 +88,32 @@ def test_ode_mode_is_deterministic(cuda):
     om = hp.oracle_model("hexa", pm0, nn)
     want, _ = orc.sample_rollouts(om, y0, u, None, 1, noise=np.zeros((1, 20, 13), np.float32))
     assert hp.rel_err(got[:1], want.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("solver", ["stratonovich_heun", "stratonovich_milstein"])
+@pytest.mark.parametrize("kind,H,N,lanes", [("hexa", 30, 20, 1), ("hexa", 30, 20, 8), ("cartpole", 40, 33, 0), ("msd", 50, 12, 1)])
+def test_stratonovich_extension(cuda, solver, kind, H, N, lanes):
+    """Rollout-only extension: the two Stratonovich schemes of the reference's commented-out code
+    (sde_solver.py:9-57, :114-177) against their restatement in the oracle, same normals."""
+    from sde4mbrl_b200.engine import Engine
+    from sde4mbrl_b200._lib import Sde4Error
+    from sde4mbrl_b200 import costs
+    pm, model, nn = hp.build(kind, H, N, seed=4)
+    pm = dict(pm, sde_solver=solver)
+    model = type(model)(pm)
+    rng = np.random.default_rng(3)
+    y0, u = hp.start_state(kind, rng), hp.controls(kind, H, rng)
+    key = tf.PRNGKey(12)
+    ts = orc.compute_timesteps(pm)
+    xi = torch.tensor(tf.rollout_noise(key, N, H, model.n_x))
+    om = hp.oracle_model(kind, pm, nn)
+    fn = orc.stratonovich_heun if solver == "stratonovich_heun" else orc.stratonovich_milstein
+    want = fn(om, ts, torch.tensor(y0), torch.tensor(u), xi).numpy()
+    eng = Engine(model)
+    got = hp.from_native_x(eng.rollout(nn, y0[None], u, ts, key=key, N=N, lanes=lanes), model.n_x)
+    assert hp.rel_err(got, want) < 3e-5
+    em = hp.from_native_x(eng.rollout(nn, y0[None], u, ts, key=key, N=N, lanes=lanes, solver="euler_maruyama"), model.n_x)
+    assert hp.rel_err(got, em) > 1e-4  # it really is a different scheme
+    with pytest.raises(Sde4Error):  # cost / gradient kernels are Euler-Maruyama only
+        eng.cost_grad(nn, y0[None], u, ts, np.zeros((H + 1, model.n_x), np.float32),
+                      costs.QuadraticCost([1.0] * model.n_x, [0.0] * model.n_u, [0.0] * model.n_u).desc, key=key, N=N)

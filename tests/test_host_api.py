@@ -77,7 +77,7 @@ def test_errors_for_unsupported_requests():
     with pytest.raises(L.Sde4Error):
         sde_models.CartPoleSDE(dict(configs.cartpole_model(2, 1), control_dependent_noise=True))
     with pytest.raises(L.Sde4Error):
-        sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), sde_solver="stratonovich_heun"))
+        sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), sde_solver="runge_kutta"))
 
 
 def test_rotor_mpc_frames_and_targets():
