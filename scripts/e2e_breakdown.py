@@ -16,12 +16,17 @@ opt_leaf = torch.as_tensor(w["opt"]).clone().requires_grad_(True)
 key_np = np.ascontiguousarray(w["key"])
 out_h = torch.empty(601)
 def step():
+    (c, _), g = multi_cost.value_and_grad(pk, w["y0"], w["opt"], key_np, w["stage"], extra_cost_args=w["xref"])
+def step_autograd():
     c, _ = multi_cost(pk, w["y0"], opt_leaf, key_np, w["stage"], extra_cost_args=w["xref"])
     (g,) = torch.autograd.grad(c, opt_leaf)
-    out_h[0] = c; out_h[1:] = g.reshape(-1)
 def raw():
     return eng.cost_grad_host(pk, w["y0"], w["opt"], multi_cost.time_steps, w["xref"], w["stage"].desc, key=key_np, N=4096)
-for fn, name in ((step, "public API"), (raw, "Engine.cost_grad_host")):
+def dev_only():
+    eng.cost_grad(pk, y0_d, opt_d, multi_cost.time_steps, xref_d, w["stage"].desc, key=key_d, N=4096); torch.cuda.synchronize()
+y0_d = torch.as_tensor(w["y0"], device="cuda")[None]; opt_d = torch.as_tensor(w["opt"], device="cuda")
+xref_d = torch.as_tensor(w["xref"], device="cuda"); key_d = torch.as_tensor(key_np.view(np.int32), device="cuda")
+for fn, name in ((step, "value_and_grad (host arrays)"), (step_autograd, "multi_cost + autograd.grad (host arrays)"), (raw, "Engine.cost_grad_host"), (dev_only, "Engine.cost_grad on device tensors + sync")):
     for _ in range(5): fn()
     t0 = time.perf_counter()
     for _ in range(100): fn()
