@@ -309,11 +309,14 @@ SDE4_DEV uint32_t noise_mask(const sde4_model_desc& d) {
 // ----------------------------------------------------------------------------
 // K1: forward rollout
 // ----------------------------------------------------------------------------
-template <class M, bool TFP = false>
+// STRAT: the instantiation that carries the Stratonovich extension steps (kept out of the Euler-Maruyama kernels:
+// the extra inlined drift / diffusion evaluations cost the throughput kernels 20 % through code size alone)
+template <class M, bool TFP = false, bool STRAT = false>
 __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_model_desc d,
                                                   const __grid_constant__ RolloutK a) {
   constexpr int NX = M::NX, NU = M::NU;
   static_assert(!TFP || M::Ev::L > 1, "the pipelined-noise variant is a lane-split kernel");
+  static_assert(!(TFP && STRAT), "the extension steps use the generic noise path");
   extern __shared__ __align__(16) float W[];
   __shared__ __align__(8) uint64_t mbar;
   Tctx<M> tc;
@@ -347,8 +350,8 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
       if (noisy) draw_noise<M>(d, a.noise_mode, a.rng_mode, a.noise, b0, b1, t, a.H, (unsigned)a.G, g, nzmask, tc, dw, nullptr);
     }
     float aux;
-    if (TFP || a.solver == SDE4_SOLVER_EULER_MARUYAMA) em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
-    else strat_step<M>(a.solver, W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
+    if constexpr (STRAT) strat_step<M>(a.solver, W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
+    else em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
     store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
   }
 }

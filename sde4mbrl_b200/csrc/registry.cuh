@@ -56,6 +56,16 @@ cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int bl
       return cudaGetLastError();
     }
   }
+  if (a.solver != SDE4_SOLVER_EULER_MARUYAMA) {
+    static bool attr_set2 = false;
+    if (!attr_set2) {
+      cudaFuncSetAttribute(k_rollout<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_bytes<M>(256, false));
+      attr_set2 = true;
+    }
+    k_rollout<M, false, true><<<blocks, threads, sm, s>>>(d, a);
+    return cudaGetLastError();
+  }
   k_rollout<M><<<blocks, threads, sm, s>>>(d, a);
   return cudaGetLastError();
 }
