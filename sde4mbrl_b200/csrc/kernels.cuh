@@ -366,7 +366,8 @@ SDE4_DEV float warp_sum(float v) {
 }
 
 // MODE 0: generic.  MODE 1 (lane-split only): in-kernel threefry noise generated one step ahead, branch free.
-// MODE 2: MODE 1 + the plain multirotor tracking cost (no sigmoid / tanh shaping), also branch free.
+// MODE 2: MODE 1 + the model's plain (unshaped) stage cost, also branch free.
+// MODE 3: generic noise path + the plain stage cost (one-thread-per-sample kernels: less code, fewer branches).
 template <class M, bool GRAD, bool CONSTR, int MODE = 0>
 __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model_desc d,
                                                const __grid_constant__ sde4_cost_desc cd,
@@ -386,7 +387,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   const int pd = p % a.data_mod;  // stacked candidate evaluations share the problem data
   const float* op = a.opt + (size_t)p * a.o_sp;
   const float* xr = a.xref + (size_t)pd * a.xref_sp;
-  constexpr bool TFP = MODE >= 1, PLAINC = MODE == 2;
+  constexpr bool TFP = MODE == 1 || MODE == 2, PLAINC = MODE >= 2;
   static_assert(!TFP || L > 1, "the pipelined-noise variant is a lane-split kernel");
   const bool noisy = TFP ? true : a.noise_mode != SDE4_NOISE_NONE;
   const uint32_t nzmask = noise_mask<NX>(d);

@@ -122,6 +122,36 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
       return cudaGetLastError();
     }
   }
+  if constexpr (M::Ev::L == 1) {
+    // one thread per sample with the model's plain stage cost: the smaller instantiation (MODE 3)
+    bool plain1 = false;
+    if constexpr (M::NX == 13) plain1 = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
+    else if constexpr (M::NX == 4) plain1 = cd.kind == SDE4_COST_QUADRATIC && cd.feat == 1 && !cd.use_res_sig;
+    else plain1 = cd.kind == SDE4_COST_QUADRATIC && cd.feat == 0 && !cd.use_res_sig;
+    if (plain1) {
+      static bool attr3 = false;
+      if (!attr3) {
+        const int mx = (int)smem_bytes<M>(256);
+        cudaFuncSetAttribute(k_cost<M, true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_cost<M, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_cost<M, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        cudaFuncSetAttribute(k_cost<M, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+        attr3 = true;
+      }
+      if (grad) {
+        if (constr)
+          k_cost<M, true, true, 3><<<blocks, threads, sm, s>>>(d, cd, td, a);
+        else
+          k_cost<M, true, false, 3><<<blocks, threads, sm, s>>>(d, cd, td, a);
+      } else {
+        if (constr)
+          k_cost<M, false, true, 3><<<blocks, threads, sm, s>>>(d, cd, td, a);
+        else
+          k_cost<M, false, false, 3><<<blocks, threads, sm, s>>>(d, cd, td, a);
+      }
+      return cudaGetLastError();
+    }
+  }
   if (grad) {
     if (constr)
       k_cost<M, true, true><<<blocks, threads, sm, s>>>(d, cd, td, a);
