@@ -535,6 +535,11 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     for (int i = 0; i < NX; ++i) xpre[i] = in[(size_t)i * G];
     if (M::NAUX) auxpre = a.auxbuf[(size_t)(H - 1) * G + g];
   }
+  // software pipeline (straight-line lane-split kernels): the cotangent-independent half of the diffusion adjoint of
+  // step t-1 is evaluated inside the block that applies step t
+  constexpr bool PIPE = TFP && PREFETCH && !M::Ev::PGRAD && M::A::HAS_DENSITY;
+  typename Diffusion<M>::Tape dtape, dtape_next;
+  if constexpr (PIPE) Diffusion<M>::prep(W, tc.ev, d, xpre, dtape);
   for (int t = H - 1; t >= 0; --t) {
     const float dt = __ldg(a.dt + t);
     if constexpr (M::Ev::PGRAD) tc.ev.dcol = (size_t)t * G + g;
@@ -584,7 +589,10 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       const Scaled<NX> vf{lam, dt};
       M::drift_vjp(W, tc.ev, d, x, u, vf, gx, gu);
     }
-    if (noisy) {
+    if constexpr (PIPE) {
+      Diffusion<M>::apply(W, d, x, lam, [&](int i) { return nzv[i]; }, dtape, gx);
+      Diffusion<M>::prep(W, tc.ev, d, xpre, dtape_next);  // xpre = x_{t-1}, requested at the top of this iteration
+    } else if (noisy) {
       if constexpr (PREFETCH) Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzv[i]; }, gx);
       else {
         const float* nzt = nz + (size_t)t * NX * G + g;
@@ -648,6 +656,7 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i) lam[i] = gx[i];
+    if constexpr (PIPE) dtape = dtape_next;
   }
   emit_cost();
 }

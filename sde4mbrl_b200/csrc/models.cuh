@@ -192,6 +192,43 @@ struct Diffusion {
     }
   }
 
+  // The same VJP in two halves for the software-pipelined backward sweep of the straight-line lane-split kernels:
+  // `prep` is everything that does not depend on the cotangent -- the density value and its UNSCALED input gradient
+  // J = d dens / d z (the longest dependency chain of a backward step) -- and is evaluated for step t-1 while step t
+  // is applied; `apply` scales J by the density cotangent gd(lam, dw, dens) and pushes it through reduced_state.
+  struct Tape {
+    float dens, J[DNet::IN > 0 ? DNet::IN : 1];
+  };
+  SDE4_DEV static void prep(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX], Tape& tp) {
+    if constexpr (A::HAS_DENSITY) {
+      float z[DNet::IN];
+      gather_in(x, d, z);
+      Ev::template scalar_value_grad<DNet>(A::template ref<0, Ev::L>(W), sc, z, tp.dens, tp.J, [](float) { return 1.0f; });
+    }
+  }
+  template <class NoiseAt>
+  SDE4_DEV static void apply(const float* W, const sde4_model_desc& d, const float (&x)[NX], const float (&lam)[NX],
+                             NoiseAt noise_at, const Tape& tp, float (&gx)[NX]) {
+    if constexpr (A::HAS_DENSITY) {
+      float gd = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NO; ++k) {
+        const int i = nth_bit(A::NOUT_MASK, k);
+        float coeff = 0.0f;
+        if constexpr (A::HAS_SCALER) coeff = W[A::OFF_DERIVED + k];
+        const float e = eta_of(W, d, tp.dens, k);
+        const float dwi = d.noise_prior[i] != 0.0f ? noise_at(i) : 0.0f;
+        gd = fmaf(dwi * lam[i] * d.noise_prior[i] * (e * (1.0f - e)), d.aggr + coeff, gd);
+      }
+      float gred[M::NR];
+#pragma unroll
+      for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = tp.J[k] * gd;
+      M::reduced_state_vjp(x, d, gred, gx);
+    }
+  }
+
   // prologue: threads compute exp(scaler)*1e-7 once per block (nsde.py:413)
   SDE4_DEV static void derive(float* __restrict__ W) {
     if constexpr (A::HAS_SCALER) {
