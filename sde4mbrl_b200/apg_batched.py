@@ -135,7 +135,10 @@ class BatchedAPG:
         """One masked ``one_step_apg`` for all problems (apg.py:164-274)."""
         lib, prm, st, P = L.load(), self.prm, self.st, self.P
         L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _stream()))
-        self._cost(self.cand, self.cand_cost, data_mod=P, which="cand")
+        # the cost of the LAST candidate is never looked at (armijo_line_search tests k = 0..maxls-1 and falls back
+        # to candidate maxls unseen, apg.py:362-379): evaluate the first maxls candidates only
+        n_eval = max(prm.maxls, 1) * P
+        self._cost(self.cand[:, :, :n_eval], self.cand_cost[:n_eval], data_mod=P, which="cand")
         L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(self.cand_cost),
                                     _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
         if self.merge_xv_grad:
