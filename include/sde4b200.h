@@ -210,6 +210,10 @@ typedef struct sde4_cost_args {
   /* stacked evaluations: problem p reads y0 / xref / key of problem (p mod data_mod) when data_mod > 0
    * (several candidate control sequences of the same problem, e.g. the APG line search) */
   int32_t data_mod;
+  /* optional device int32[P]: problems with mask 0 are skipped -- their cost / grad entries are left untouched (the
+   * batched APG solver evaluates line-search candidates one step size at a time and drops the problems that have
+   * already accepted one; whole warps of skipped problems exit at once).  NULL: every problem is evaluated. */
+  const int32_t* problem_mask;
 } sde4_cost_args;
 
 /* Upper bound over the lane / noise modes the launcher may pick. */
@@ -307,6 +311,11 @@ int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const 
  * y_grad[H][n_opt][P] (apg.py:224 then needs no further launch); both NULL otherwise. */
 int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
                   int32_t* pick, const float* xv_grad_or_null, float* y_grad_or_null, void* stream);
+/* progressive line search: after the costs of candidate k are known, active[p] &= wolfe_cond_violated(k)
+ * (apg.py:324-329, 362-379); problems that accepted candidate k are skipped by the next candidate's launch.
+ * k == 0 first sets active[p] = not_done[p]. */
+int sde4_apg_ls_step(const sde4_apg_params* prm, const sde4_apg_state* st, const float* svals, const float* cand_cost,
+                     int32_t k, int32_t* active, void* stream);
 /* state update with grad(ynext) (apg.py:224-273); problems with not_done == 0 are left untouched */
 int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
                     const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,

@@ -27,7 +27,7 @@ from .engine import as_f32, as_key, _ptr, _stream
 
 class BatchedAPG:
     def __init__(self, engine, nn_params, stage, optimizer_params, time_steps, num_particles, lb=None, ub=None,
-                 terminal=None, lanes=0, merge_xv_grad=None):
+                 terminal=None, lanes=0, merge_xv_grad=None, progressive_ls=None):
         self.eng = engine
         self.pk = engine.packed(nn_params)
         self.stage = stage
@@ -43,6 +43,7 @@ class BatchedAPG:
         self.lanes = lanes if isinstance(lanes, dict) else {"cand": lanes, "xv": lanes, "y": lanes}
         self.lb, self.ub = lb, ub
         self.merge_xv_grad = merge_xv_grad  # None: decided from the launch size (see step)
+        self.progressive_ls = progressive_ls  # None: decided from the launch size (see _alloc)
         self.P = None
         self._graph = None
 
@@ -59,6 +60,10 @@ class BatchedAPG:
         self.xv, self.xv_cost = f(H, n, 2 * P), f(2 * P)
         if self.merge_xv_grad is None:
             self.merge_xv_grad = 2 * P * self.N <= 65536
+        if self.progressive_ls is None:
+            # worth it when the launches are throughput bound and every warp belongs to one problem
+            self.progressive_ls = self.N % 32 == 0 and P * self.N >= 65536 and self.op["linesearch"]["maxls"] > 1
+        self.ls_active = i(P)
         self.xv_grad = f(H, n, 2 * P) if self.merge_xv_grad else None
         self.y, self.y_cost, self.y_grad = f(H, n, P), f(P), f(H, n, P)
         self.cost_tmp = f(P)
@@ -91,11 +96,11 @@ class BatchedAPG:
         """[H, n, Q] problem-minor buffer -> [Q, H, n] strided view the cost launcher accepts."""
         return buf.permute(2, 0, 1)
 
-    def _cost(self, buf, cost_out, grad_buf=None, data_mod=0, which="y"):
+    def _cost(self, buf, cost_out, grad_buf=None, data_mod=0, which="y", mask=None):
         self.eng.cost_grad(self.pk, self.y0, self._pm_view(buf), self.ts, self.xref, self.stage.desc,
                            terminal=None if self.terminal is None else self.terminal.desc, key=self.keys, N=self.N,
                            want_grad=grad_buf is not None, grad_out=None if grad_buf is None else self._pm_view(grad_buf),
-                           lanes=self.lanes.get(which, 0), data_mod=data_mod, cost_out=cost_out)
+                           lanes=self.lanes.get(which, 0), data_mod=data_mod, cost_out=cost_out, problem_mask=mask)
 
     # ------------------------------------------------------------------
     def init(self, x0, y0, xref, keys, momentum=None, stepsize=None):
@@ -137,8 +142,17 @@ class BatchedAPG:
         L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _stream()))
         # the cost of the LAST candidate is never looked at (armijo_line_search tests k = 0..maxls-1 and falls back
         # to candidate maxls unseen, apg.py:362-379): evaluate the first maxls candidates only
-        n_eval = max(prm.maxls, 1) * P
-        self._cost(self.cand[:, :, :n_eval], self.cand_cost[:n_eval], data_mod=P, which="cand")
+        if self.progressive_ls:
+            # throughput-bound sizes whose problems fill whole warps: one launch per step size, problems that have
+            # accepted a candidate (or are finished) are skipped -- ~1.5 evaluations per problem instead of maxls
+            for k in range(max(prm.maxls, 1)):
+                self._cost(self.cand[:, :, k * P:(k + 1) * P], self.cand_cost[k * P:(k + 1) * P], which="cand",
+                           mask=self.ls_active if k > 0 else None)
+                L.check(lib.sde4_apg_ls_step(C.byref(prm), C.byref(st), _ptr(self.svals), _ptr(self.cand_cost), k,
+                                             _ptr(self.ls_active), _stream()))
+        else:
+            n_eval = max(prm.maxls, 1) * P
+            self._cost(self.cand[:, :, :n_eval], self.cand_cost[:n_eval], data_mod=P, which="cand")
         L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(self.cand_cost),
                                     _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
         if self.merge_xv_grad:

@@ -145,6 +145,22 @@ __global__ void k_apg_pick(const __grid_constant__ sde4_apg_params prm, const fl
   }
 }
 
+// progressive line search (apg.py:362-379 evaluated one step size at a time over the whole batch)
+__global__ void k_apg_ls_step(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
+                              const float* __restrict__ svals, const float* __restrict__ cand_cost, int k,
+                              int32_t* __restrict__ active) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= prm.P) return;
+  const int on = k == 0 ? st.not_done[p] : active[p];
+  if (!on) {
+    active[p] = 0;
+    return;
+  }
+  const float s = svals[(size_t)k * prm.P + p], f = cand_cost[(size_t)k * prm.P + p];
+  const bool violated = s * prm.coef * st.grad_sqr[p] > st.curr_cost[p] - f + 1.1920929e-07f;
+  active[p] = violated ? 1 : 0;
+}
+
 // vector part of the state update: reads the OLD per-problem scalars, writes vectors and |grad|^2 partials
 __global__ void k_apg_update(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
                              const float* __restrict__ xv, const float* __restrict__ y,

@@ -54,6 +54,7 @@ struct CostK {
   int x_rows, rng_mode, noise_mode;
   int n_slack, warp_reduce, PW, has_terminal, write_stage_cost;
   int n_off, n_tot;
+  const int32_t* mask;  // optional [P]: problems with mask 0 are skipped
   int data_mod;  // y0 / xref / key of problem p are those of (p mod data_mod)
   // training loss (sde4_loss_grad): plain sum over t >= 1 instead of the trapezoid, training key chain,
   // parameter-gradient streams of the three networks ([rows][H*G], column = t*G + g)
@@ -72,6 +73,7 @@ struct ReduceK {
   float* grad;
   int P, N, H, n_u, n_opt, PW, NP;  // NP partials per problem; N = total particles (divisor)
   int has_slew;
+  const int32_t* mask;  // optional [P]: skipped problems keep their old outputs
   int lpi;  // lanes per reduced item: 1 or 32
   float res_mult;
   float slew[SDE4_MAX_NU];
@@ -385,6 +387,10 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
   const unsigned G = (unsigned)a.G;
   const int H = a.H;
   const int pd = p % a.data_mod;  // stacked candidate evaluations share the problem data
+  if (a.mask) {  // skipped problems: a warp leaves when none of its samples is wanted (warp-uniform exit; a partly
+    const bool on = __ldg(a.mask + p) != 0;  // wanted warp computes everything, its unwanted results are ignored)
+    if (!__any_sync(0xffffffffu, on)) return;
+  }
   const float* op = a.opt + (size_t)p * a.o_sp;
   const float* xr = a.xref + (size_t)pd * a.xref_sp;
   constexpr bool TFP = MODE == 1 || MODE == 2, PLAINC = MODE >= 2;

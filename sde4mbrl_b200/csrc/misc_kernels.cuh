@@ -41,6 +41,7 @@ __global__ void k_reduce(const __grid_constant__ ReduceK a) {
   if (idx >= (long long)rows * a.P) return;  // warp-uniform for lpi = 32 (blockDim is a multiple of 32)
   const int p = (int)(idx % a.P);
   const int row = a.grad ? (int)(idx / a.P) : a.H * a.n_opt;
+  if (a.mask && a.mask[p] == 0) return;  // skipped problem (uniform over the lanes of an item)
   const float invN = 1.0f / (float)a.N;
   const float* op = a.opt + (size_t)p * a.o_sp;
   if (row == a.H * a.n_opt) {

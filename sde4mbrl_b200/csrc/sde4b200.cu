@@ -420,6 +420,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   k.n_tot = a->particle_total > 0 ? a->particle_total : a->N;
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   k.data_mod = a->data_mod > 0 ? a->data_mod : a->P;
+  k.mask = a->problem_mask;
   k.sum_mode = lo.enabled ? 1 : 0;
   k.rng_chain = lo.enabled ? 1 : 0;
   k.pd_stride = Kcols;
@@ -457,6 +458,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   r.PW = L.PW;
   r.NP = L.NP;
   r.has_slew = (cd.has_slew && k.n_off == 0) ? 1 : 0;
+  r.mask = a->problem_mask;
   r.res_mult = cd.res_mult;
   for (int j = 0; j < SDE4_MAX_NU; ++j) r.slew[j] = cd.u_slew_coeff[j];
   // value-only launches reduce the cost row only
@@ -630,6 +632,13 @@ int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const 
   if (int rc = apg_check(prm, st)) return rc;
   if (!st || !cand || !svals || !cand_cost || !xv || !sel_step || !sel_ls) return fail(SDE4_ERR_INVALID, "null argument");
   SDE4_APG_LAUNCH(k_apg_select, 1, *prm, *st, cand, svals, cand_cost, xv, sel_step, sel_ls);
+  return SDE4_OK;
+}
+int sde4_apg_ls_step(const sde4_apg_params* prm, const sde4_apg_state* st, const float* svals, const float* cand_cost,
+                     int32_t k, int32_t* active, void* stream) {
+  if (int rc = apg_check(prm, st)) return rc;
+  if (!st || !svals || !cand_cost || !active || k < 0 || k > prm->maxls) return fail(SDE4_ERR_INVALID, "bad argument");
+  SDE4_APG_LAUNCH(k_apg_ls_step, 0, *prm, *st, svals, cand_cost, (int)k, active);
   return SDE4_OK;
 }
 int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,

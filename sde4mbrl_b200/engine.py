@@ -202,7 +202,7 @@ class Engine:
     # ---- K2 + K3 ----------------------------------------------------------
     def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,
                   noise_mode=None, want_grad=True, want_xtraj=False, block_threads=0, grad_out=None,
-                  particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None):
+                  particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None, problem_mask=None):
         """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
         Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
         self._em_only()
@@ -273,6 +273,9 @@ class Engine:
         a.block_threads = block_threads
         a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
         a.data_mod = data_mod
+        if problem_mask is not None:  # int32[P] device tensor: problems with 0 are skipped, their outputs untouched
+            assert problem_mask.dtype == torch.int32 and problem_mask.is_cuda and problem_mask.numel() == P
+            a.problem_mask = problem_mask.data_ptr()
         L.check(lib.sde4_cost_grad(C.byref(self.desc), C.byref(a), _stream()))
         if squeeze and grad is not None:
             grad = grad.squeeze(0)

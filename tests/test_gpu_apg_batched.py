@@ -64,3 +64,41 @@ def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge):
         assert float(s.opt_cost) < float(s.init_cost)
     if rtol > 0:
         assert n_done > 0  # the masked path was exercised
+
+
+@pytest.mark.parametrize("N", [4, 32])
+def test_progressive_line_search_gives_the_same_solution(cuda, N):
+    """One launch per step size with the already-accepted problems masked out (problem_mask) vs all step sizes in
+    one stacked launch: same accepted candidates, same iterates."""
+    from sde4mbrl_b200 import nsde
+    from sde4mbrl_b200.apg_batched import BatchedAPG
+    P, H, iters = 37, 20, 10
+    pm = configs.hexa_model(horizon=H, num_particles=N, stepsize=0.05)
+    mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=N, max_iter=iters)
+    mpc["apg_mpc"]["rtol"] = 0.02  # some problems finish early: finished problems are masked out as well
+    mpc["apg_mpc"]["linesearch"]["init_stepsize"] = 0.5  # large first step: the line search has to back-track
+    with contextlib.redirect_stdout(_io.StringIO()):
+        _, multi_cost, _, _, construct_opt = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.SDERotorModel)
+    nn = configs.random_params(sde_models.SDERotorModel(pm), seed=3)
+    cp, op = mpc["cost_params"], mpc["apg_mpc"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    rng = np.random.default_rng(11)
+    y0 = np.stack([hp.start_state("hexa", rng) for _ in range(P)])
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    keys = tf.split(tf.PRNGKey(5), P)
+    x0 = construct_opt(u=np.full(6, 0.33, np.float32))
+    res = []
+    for prog in (False, True):
+        s = BatchedAPG(multi_cost.engine, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0, progressive_ls=prog,
+                       lanes=1)
+        s.init(x0, y0, xref, keys).run()
+        res.append((s.x_opt().cpu().numpy(), s.t["opt_cost"].cpu().numpy(), s.t["num_steps"].cpu().numpy(),
+                    s.t["avg_linesearch"].cpu().numpy(), s.t["not_done"].cpu().numpy()))
+    (xa, ca, na, la, da), (xb, cb, nb, lb_, db) = res
+    np.testing.assert_array_equal(na, nb)
+    np.testing.assert_array_equal(da, db)
+    np.testing.assert_allclose(la, lb_, rtol=1e-6)
+    np.testing.assert_allclose(ca, cb, rtol=1e-6)
+    assert hp.rel_err(xa, xb) < 1e-6
+    assert (la > 1.0).any() and (da == 0).any()  # back-tracking and early stopping both happened
