@@ -201,16 +201,21 @@ def main():
     key_d = torch.as_tensor(w["key"].view(np.int32), device=dev)
     n_total = N_PART * world
     red = torch.zeros(HORIZON * 6 + 1, device=dev)
+    # N > 1: K3 writes its [cost | grad] straight into the reducer's (symmetric-memory) buffer, ONE small all-reduce
+    from sde4mbrl_b200.dist import CostGradReducer
+    reducer = CostGradReducer(HORIZON * 6 + 1, dev, grad_shape=(HORIZON, 6)) if world > 1 else None
 
     def step_device():
+        if world > 1:
+            c_out, g_out = reducer.views(1)
+            eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART, want_grad=True,
+                          block_threads=args.block_threads, lanes=args.lanes, particle_offset=rank * N_PART,
+                          particle_total=n_total, cost_out=c_out, grad_out=g_out)
+            tot = reducer.reduce()
+            return tot[0:1], tot[1:].view(HORIZON, 6)
         cost, grad, _ = eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART,
                                       want_grad=True, block_threads=args.block_threads, lanes=args.lanes,
                                       particle_offset=rank * N_PART, particle_total=n_total)
-        if world > 1:
-            red[0:1].copy_(cost)
-            red[1:].copy_(grad.reshape(-1))
-            dist.all_reduce(red)
-            return red[0:1], red[1:].view(HORIZON, 6)
         return cost, grad
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -645,8 +650,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "hexacopter nSDE (13 states, 6 rotors), 1 problem, 4096 particles per GPU x 100 steps, "
                                    "distance-aware diffusion with in-kernel threefry noise + gradient pass (BASELINE configs[2])",
-                       "particles_per_gpu": N_PART, "horizon": HORIZON, "parallelism": "particles sharded over %d GPU(s), "
-                       "NCCL all-reduce of [cost, grad] (601 floats)" % world,
+                       "particles_per_gpu": N_PART, "horizon": HORIZON, "parallelism": "particles sharded over %d GPU(s), one all-reduce of [cost, grad] (601 floats): %s"
+                       % (world, "none (1 GPU)" if world == 1 else
+                          ("torch symmetric-memory one-shot all-reduce over NVLink" if reducer.symm else "NCCL all-reduce")),
                        "l2": "flushed between timed steps (256 MB write)", "timing": "CUDA events per step, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": total_ps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,

