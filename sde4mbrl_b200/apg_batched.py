@@ -8,7 +8,7 @@ evaluates all branches; here the same semantics are obtained with per-problem ma
     Armijo selection + box prox + momentum point -> ONE value-only launch over 2P problems (x and v)
     ynext = where(cost_x <= cost_v, x, v)        -> ONE value+gradient launch over P problems
     state update (masked by not_done)
-For latency-bound sizes (2*P*N <= 65536 samples) the last two launches are merged: value+gradient for x AND v, then
+For latency-bound sizes (2*P*N <= 8192 samples) the last two launches are merged: value+gradient for x AND v, then
 point, cost and gradient of the better one are copied -- ~15 % more arithmetic, one sequential rollout less per
 iteration (a single hexacopter solve: 3.8 -> 2.9 ms).
 
@@ -59,10 +59,11 @@ class BatchedAPG:
         self.cand, self.svals, self.cand_cost = f(H, n, K * P), f(K, P), f(K * P)
         self.xv, self.xv_cost = f(H, n, 2 * P), f(2 * P)
         if self.merge_xv_grad is None:
-            self.merge_xv_grad = 2 * P * self.N <= 65536
+            self.merge_xv_grad = 2 * P * self.N <= 8192  # scripts/apg_modes.py: better up to 8 k samples, worse from 32 k
         if self.progressive_ls is None:
             # worth it when the launches are throughput bound and every warp belongs to one problem
-            self.progressive_ls = self.N % 32 == 0 and P * self.N >= 65536 and self.op["linesearch"]["maxls"] > 1
+            # (scripts/apg_modes.py: better from 16 k samples per candidate on)
+            self.progressive_ls = self.N % 32 == 0 and P * self.N >= 16384 and self.op["linesearch"]["maxls"] > 1
         self.ls_active = i(P)
         self.xv_grad = f(H, n, 2 * P) if self.merge_xv_grad else None
         self.y, self.y_cost, self.y_grad = f(H, n, P), f(P), f(H, n, P)
