@@ -301,11 +301,16 @@ int sde4_apg_init(const sde4_apg_params* prm, const sde4_apg_state* st, const fl
                   const float* grad0, const float* momentum_or_null, const float* stepsize_or_null,
                   float init_stepsize, float beta_init, float* scratch, void* stream);
 /* candidates cand[H][n_opt][(maxls+1)*P] = yk - s_k*grad_yk, svals[(maxls+1)][P] (apg.py:179-184,312-321,358). */
-int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals, void* stream);
+/* xmask[P] (optional): cleared here, raised by sde4_apg_select for the problems whose x = prox(accepted candidate)
+ * differs from the candidate (or is the never-evaluated fall-back); for the others select copies the candidate's cost
+ * into xv_cost[p], and the x / v evaluation may skip x (sde4_cost_args.problem_mask = [xmask | ones]). */
+int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals,
+                        int32_t* xmask_or_null, void* stream);
 /* Armijo selection (apg.py:324-329,362-379), prox, momentum point: xv[H][n_opt][2P] = [xcurr | vcurr];
  * sel_step[P], sel_ls[P] (stepsize, number of line-search steps). */
 int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, const float* svals,
-                    const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, void* stream);
+                    const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, int32_t* xmask_or_null,
+                    float* xv_cost_or_null, void* stream);
 /* ynext = where(cost_x <= cost_v, xcurr, vcurr) (apg.py:219-221): y[H][n_opt][P], pick[P].  If the x / v evaluation
  * was a value+gradient launch, xv_grad[H][n_opt][2P] is given and the gradient of the chosen point is copied into
  * y_grad[H][n_opt][P] (apg.py:224 then needs no further launch); both NULL otherwise. */

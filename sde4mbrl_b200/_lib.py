@@ -176,8 +176,9 @@ def load():
     lib.sde4_apg_ls_step.restype = C.c_int
     lib.sde4_apg_scratch_floats.argtypes = [C.POINTER(ApgParams)]
     lib.sde4_apg_scratch_floats.restype = C.c_int
-    lib.sde4_apg_candidates.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState), C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.sde4_apg_select.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 7
+    lib.sde4_apg_candidates.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]
+    lib.sde4_apg_select.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 9
     lib.sde4_apg_pick.argtypes = [C.POINTER(ApgParams)] + [C.c_void_p] * 8
     lib.sde4_apg_update.argtypes = [C.POINTER(ApgParams), C.POINTER(ApgState)] + [C.c_void_p] * 9
     asz = (C.c_int32 * 2)()

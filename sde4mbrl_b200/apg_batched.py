@@ -65,6 +65,7 @@ class BatchedAPG:
             # (scripts/apg_modes.py: better from 16 k samples per candidate on)
             self.progressive_ls = self.N % 32 == 0 and P * self.N >= 16384 and self.op["linesearch"]["maxls"] > 1
         self.ls_active = i(P)
+        self.xvmask = torch.ones(2 * P, dtype=torch.int32, device=dev)  # [x needs evaluation | v always]
         self.xv_grad = f(H, n, 2 * P) if self.merge_xv_grad else None
         self.y, self.y_cost, self.y_grad = f(H, n, P), f(P), f(H, n, P)
         self.cost_tmp = f(P)
@@ -140,7 +141,9 @@ class BatchedAPG:
     def step(self):
         """One masked ``one_step_apg`` for all problems (apg.py:164-274)."""
         lib, prm, st, P = L.load(), self.prm, self.st, self.P
-        L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _stream()))
+        reuse_x = not self.merge_xv_grad  # cost(x) = cost(accepted candidate) unless the prox moved it
+        xmask = self.xvmask[:P] if reuse_x else None
+        L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(xmask), _stream()))
         # the cost of the LAST candidate is never looked at (armijo_line_search tests k = 0..maxls-1 and falls back
         # to candidate maxls unseen, apg.py:362-379): evaluate the first maxls candidates only
         if self.progressive_ls:
@@ -155,7 +158,8 @@ class BatchedAPG:
             n_eval = max(prm.maxls, 1) * P
             self._cost(self.cand[:, :, :n_eval], self.cand_cost[:n_eval], data_mod=P, which="cand")
         L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(self.cand_cost),
-                                    _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _stream()))
+                                    _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _ptr(xmask),
+                                    _ptr(self.xv_cost if reuse_x else None), _stream()))
         if self.merge_xv_grad:
             # latency-bound sizes: ONE value+gradient launch over the 2P problems x and v; pick copies point, cost
             # and gradient of the better one (one sequential rollout less per iteration, ~15 % more arithmetic)
@@ -164,7 +168,7 @@ class BatchedAPG:
                                       _ptr(self.pick), _ptr(self.xv_grad), _ptr(self.y_grad), _stream()))
         else:
             # throughput-bound sizes: the reference's order -- value-only x / v, then the gradient at the chosen point
-            self._cost(self.xv, self.xv_cost, data_mod=P, which="xv")
+            self._cost(self.xv, self.xv_cost, data_mod=P, which="xv", mask=self.xvmask)  # x skipped where its cost is known
             L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
                                       _ptr(self.pick), _ptr(None), _ptr(None), _stream()))
             self._cost(self.y, self.cost_tmp, grad_buf=self.y_grad)

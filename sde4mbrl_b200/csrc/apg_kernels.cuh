@@ -64,9 +64,10 @@ SDE4_DEV float apg_first_step(const sde4_apg_params& prm, float s) {
 
 __global__ void k_apg_candidates(const __grid_constant__ sde4_apg_params prm,
                                  const __grid_constant__ sde4_apg_state st, float* __restrict__ cand,
-                                 float* __restrict__ svals) {
+                                 float* __restrict__ svals, int32_t* __restrict__ xmask) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
+  if (xmask && blockIdx.y == 0) xmask[p] = 0;  // "x must be re-evaluated" flags, raised by k_apg_select
   const int P = prm.P, E = prm.H * prm.n_opt, K = prm.maxls + 1;
   const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
   float y[APG_CH], g[APG_CH];
@@ -89,7 +90,7 @@ __global__ void k_apg_candidates(const __grid_constant__ sde4_apg_params prm,
 __global__ void k_apg_select(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
                              const float* __restrict__ cand, const float* __restrict__ svals,
                              const float* __restrict__ cand_cost, float* __restrict__ xv, float* __restrict__ sel_step,
-                             int32_t* __restrict__ sel_ls) {
+                             int32_t* __restrict__ sel_ls, int32_t* __restrict__ xmask, float* __restrict__ xv_cost) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= prm.P) return;
   const int P = prm.P, E = prm.H * prm.n_opt, K = prm.maxls + 1;
@@ -108,18 +109,28 @@ __global__ void k_apg_select(const __grid_constant__ sde4_apg_params prm, const 
   if (blockIdx.y == 0) {
     sel_step[p] = svals[(size_t)ks * P + p];
     sel_ls[p] = 1 + ks;  // num_iter of armijo_line_search
+    if (xmask) {
+      // cost(x) = cost of the accepted candidate when the prox leaves it untouched: reuse it (the x / v launch then
+      // skips x); the fall-back candidate maxls was never evaluated, so x has to be
+      xv_cost[p] = cand_cost[(size_t)(ks < prm.maxls ? ks : 0) * P + p];
+      if (ks >= prm.maxls) atomicOr(xmask + p, 1);
+    }
   }
   const float mom = st.momentum[p];
+  bool moved = false;
   for (int e = e0; e < e1; ++e) {
     float x = cand[(size_t)e * K * P + (size_t)ks * P + p];
     if (prm.has_prox) {
       const int j = e % prm.n_opt;
-      x = fminf(fmaxf(x, prm.lb[j]), prm.ub[j]);  // constr_vect, nsde.py:1422
+      const float xc = fminf(fmaxf(x, prm.lb[j]), prm.ub[j]);  // constr_vect, nsde.py:1422
+      moved = moved || (xc != x);
+      x = xc;
     }
     const float xp = st.xk[(size_t)e * P + p];
     xv[(size_t)e * 2 * P + p] = x;
     xv[(size_t)e * 2 * P + P + p] = xp + mom * (x - xp);  // vcurr, apg.py:215
   }
+  if (xmask && moved) atomicOr(xmask + p, 1);  // (an OR: order independent, deterministic)
 }
 
 // ynext = where(cost_x <= cost_v, x, v).  When the x / v evaluation also produced gradients (xv_grad != nullptr:

@@ -621,17 +621,20 @@ int sde4_apg_init(const sde4_apg_params* prm, const sde4_apg_state* st, const fl
                   scratch, apg_chunks(prm));
   return SDE4_OK;
 }
-int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals, void* stream) {
+int sde4_apg_candidates(const sde4_apg_params* prm, const sde4_apg_state* st, float* cand, float* svals,
+                        int32_t* xmask_or_null, void* stream) {
   if (int rc = apg_check(prm, st)) return rc;
   if (!st || !cand || !svals) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_candidates, 1, *prm, *st, cand, svals);
+  SDE4_APG_LAUNCH(k_apg_candidates, 1, *prm, *st, cand, svals, xmask_or_null);
   return SDE4_OK;
 }
 int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, const float* svals,
-                    const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, void* stream) {
+                    const float* cand_cost, float* xv, float* sel_step, int32_t* sel_ls, int32_t* xmask_or_null,
+                    float* xv_cost_or_null, void* stream) {
   if (int rc = apg_check(prm, st)) return rc;
   if (!st || !cand || !svals || !cand_cost || !xv || !sel_step || !sel_ls) return fail(SDE4_ERR_INVALID, "null argument");
-  SDE4_APG_LAUNCH(k_apg_select, 1, *prm, *st, cand, svals, cand_cost, xv, sel_step, sel_ls);
+  if ((xmask_or_null == nullptr) != (xv_cost_or_null == nullptr)) return fail(SDE4_ERR_INVALID, "xmask and xv_cost go together");
+  SDE4_APG_LAUNCH(k_apg_select, 1, *prm, *st, cand, svals, cand_cost, xv, sel_step, sel_ls, xmask_or_null, xv_cost_or_null);
   return SDE4_OK;
 }
 int sde4_apg_ls_step(const sde4_apg_params* prm, const sde4_apg_state* st, const float* svals, const float* cand_cost,

@@ -15,16 +15,22 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("merge", [True, False])
-@pytest.mark.parametrize("N,iters,rtol", [(1, 8, 0.0), (4, 6, 0.0), (1, 12, 0.05)])
-def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge):
+@pytest.mark.parametrize("N,iters,rtol,box", [(1, 8, 0.0, None), (4, 6, 0.0, None), (1, 12, 0.05, None),
+                                              (4, 8, 0.0, (0.325, 0.338))])
+def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge, box):
     """`merge`: x and v evaluated by one value+gradient launch (latency-bound sizes) or, as in the reference, value
-    only followed by the gradient at the chosen point (throughput-bound sizes)."""
+    only followed by the gradient at the chosen point (throughput-bound sizes; there the cost of x is taken from the
+    accepted line-search candidate unless the box prox moved it -- `box`: tight control bounds, the prox clips)."""
     from sde4mbrl_b200 import apg, nsde, random as R
     from sde4mbrl_b200.apg_batched import BatchedAPG
     P, H = 5, 20
     pm = configs.hexa_model(horizon=H, num_particles=N, stepsize=0.05)
     mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=N, max_iter=iters)
     mpc["apg_mpc"]["rtol"] = rtol  # rtol > 0: some problems stop early -> exercises the not_done masks
+    lo, hi = (1e-4, 1.0) if box is None else box
+    mpc["input_constr"]["input_bound"] = [[lo, hi]] * 6
+    if box is not None:
+        mpc["apg_mpc"]["linesearch"]["init_stepsize"] = 0.3
     with contextlib.redirect_stdout(_io.StringIO()):
         _, multi_cost, vprox, _, construct_opt = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.SDERotorModel)
     nn = configs.random_params(sde_models.SDERotorModel(pm), seed=3)
@@ -37,7 +43,7 @@ def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge):
     keys = tf.split(tf.PRNGKey(31), P)
     x0 = construct_opt(u=np.full(6, 0.33, np.float32))
     eng = multi_cost.engine
-    solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0, merge_xv_grad=merge)
+    solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=lo, ub=hi, merge_xv_grad=merge)
     solver.init(x0, y0, xref, keys).run(use_graph=False)
     x_eager = solver.x_opt().clone()
     solver.init(x0, y0, xref, keys).run(use_graph=True)  # CUDA-graph replay must give the same iterates
@@ -64,6 +70,8 @@ def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge):
         assert float(s.opt_cost) < float(s.init_cost)
     if rtol > 0:
         assert n_done > 0  # the masked path was exercised
+    if box is not None:
+        assert (xb <= lo + 1e-7).any() or (xb >= hi - 1e-7).any()  # the prox really clipped
 
 
 @pytest.mark.parametrize("N", [4, 32])
