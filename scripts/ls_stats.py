@@ -19,3 +19,9 @@ for n_part in (1, 32):
     s.init(torch.full((HM, 6), 0.33 + 2e-4, device=dev), torch.as_tensor(y0m, device=dev), xref, torch.as_tensor(keys.view(np.int32), device=dev)).run(20)
     al = s.t["avg_linesearch"].cpu().numpy()
     print(n_part, "avg linesearch steps: mean %.3f max %.3f; fraction of problems with avg<=1.5: %.2f" % (al.mean(), al.max(), (al <= 1.5).mean()), "not_done", int(s.t["not_done"].sum()))
+    # fraction of problems whose x (plain step) beats v (momentum point), per iteration
+    s.init(torch.full((HM, 6), 0.33 + 2e-4, device=dev), torch.as_tensor(y0m, device=dev), xref, torch.as_tensor(keys.view(np.int32), device=dev))
+    fr = []
+    for it in range(20):
+        s.step(); fr.append(float(s.pick.float().mean()))
+    print(n_part, "fraction x <= v per iteration:", " ".join("%.2f" % f for f in fr))

@@ -240,3 +240,32 @@ def test_terminal_cost(cuda, lanes, use_key):
     assert float(cost[0]) > float(cost0[0]) * 1.05  # the terminal term is a visible part of the total
     cv, _, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, terminal=term.desc, N=N, lanes=lanes, want_grad=False, **kw)
     assert abs(float(cv[0]) - float(cost[0])) <= 2e-6 * abs(float(cost[0]))
+
+
+@pytest.mark.parametrize("N,lanes", [(32, 1), (5, 0), (3, 8)])
+def test_problem_mask_skips_and_leaves_outputs_untouched(cuda, N, lanes):
+    """sde4_cost_args.problem_mask: masked-out problems keep their previous cost / grad entries, the others are
+    evaluated as without a mask (whole warps of masked problems exit early; partly wanted warps compute everything)."""
+    from sde4mbrl_b200.engine import Engine
+    from oracle import threefry as tf
+    P, H = 9, 20
+    pm, model, nn, _, _, _, cp, stage, xref = _setup("hexa", H, N, seed=3)
+    rng = np.random.default_rng(8)
+    y0 = np.stack([hp.start_state("hexa", rng) for _ in range(P)])
+    opt = np.stack([hp.controls("hexa", H, rng) for _ in range(P)])
+    keys = tf.split(tf.PRNGKey(2), P)
+    eng = Engine(model)
+    ts = orc.compute_timesteps(pm)
+    c_all, g_all, _ = eng.cost_grad(nn, y0, opt, ts, xref, stage.desc, key=keys, N=N, lanes=lanes)
+    c_all, g_all = c_all.clone(), g_all.clone()
+    mask = torch.tensor([1, 0, 0, 1, 1, 0, 1, 0, 0], dtype=torch.int32, device="cuda")
+    c_out = torch.full((P,), -7.0, device="cuda")
+    g_out = torch.full((P, H, 6), -7.0, device="cuda")
+    eng.cost_grad(nn, y0, opt, ts, xref, stage.desc, key=keys, N=N, lanes=lanes, cost_out=c_out, grad_out=g_out,
+                  problem_mask=mask)
+    on = mask.bool()
+    assert torch.equal(c_out[on], c_all[on]) and torch.equal(g_out[on], g_all[on])
+    assert bool((c_out[~on] == -7.0).all()) and bool((g_out[~on] == -7.0).all())
+    cv = torch.full((P,), -7.0, device="cuda")
+    eng.cost_grad(nn, y0, opt, ts, xref, stage.desc, key=keys, N=N, lanes=lanes, want_grad=False, cost_out=cv, problem_mask=mask)
+    assert bool((cv[~on] == -7.0).all()) and hp.rel_err(cv[on].cpu().numpy(), c_all[on].cpu().numpy()) < 2e-6
