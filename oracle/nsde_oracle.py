@@ -275,7 +275,8 @@ class RotorOracle(OracleSDE):
         init_value = self.init_params.get(name, 1e-3)
         if name in self.init_params and self.params.get("fixed_init_params", False):
             return float(init_value)
-        return float(self.scalar(name))
+        v = self.scalar(name)
+        return v if isinstance(v, torch.Tensor) else float(v)  # tensors keep their autograd history (training loss)
 
     def reduced_state(self, x):
         if "state_scaling" in self.params:
@@ -302,11 +303,9 @@ class RotorOracle(OracleSDE):
         mx = self.get_param("Lmx")
         my = mx if assume_sym else self.get_param("Lmy")
         mz = self.get_param("CoeffDrag")
-        mixer = (QUAD_MIXER if u.shape[-1] == 4 else HEXA_MIXER).copy()
-        mixer[0] *= mx
-        mixer[1] *= my
-        mixer[2] *= mz
-        tm = thrust_per_motor @ _t(mixer, u).T
+        mixer = _t((QUAD_MIXER if u.shape[-1] == 4 else HEXA_MIXER).copy(), u)
+        scale = torch.stack([torch.as_tensor(v, dtype=u.dtype) for v in (mx, my, mz, 1.0)])  # rows x Lmx, Lmy, CoeffDrag
+        tm = thrust_per_motor @ (mixer * scale[:, None]).T
         return tm[..., 3], tm[..., :3]
 
     def _nn_in(self, x, v_b):
@@ -327,7 +326,8 @@ class RotorOracle(OracleSDE):
             pre = "%s/~init_residual_networks/res_forces/~" % self.module_name
             Fres = Fres + mlp_apply(self.nn, pre, iv, rf["activation_fn"])
         if self.params.get("aero_drag_effect", False):
-            kdx, kdy, kdz, kh = (float(self.scalar(n)) for n in ("aero_kdx", "aero_kdy", "aero_kdz", "aero_kh"))
+            kdx, kdy, kdz, kh = (self.scalar(n) if isinstance(self.scalar(n), torch.Tensor) else float(self.scalar(n))
+                                 for n in ("aero_kdx", "aero_kdy", "aero_kdz", "aero_kh"))
             drag = torch.stack([-kdx * v_b[..., 0], -kdy * v_b[..., 1],
                                 -kdz * v_b[..., 2] + kh * (v_b[..., 0] ** 2 + v_b[..., 1] ** 2)], dim=-1)  # :277
             Fres = Fres + drag
@@ -363,7 +363,7 @@ class RotorOracle(OracleSDE):
         F = quat_rotatevector(q, F)
         a = F / m + _t([0.0, 0.0, -g], x)
         # rotational_dynamics :212-250
-        I = _t([self.get_param("Ixx"), self.get_param("Iyy"), self.get_param("Izz")], x)
+        I = torch.stack([torch.as_tensor(self.get_param(n), dtype=x.dtype) for n in ("Ixx", "Iyy", "Izz")])
         M = moment
         if Mres is not None:
             M = M + Mres

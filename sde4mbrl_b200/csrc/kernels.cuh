@@ -60,6 +60,7 @@ struct CostK {
   // parameter-gradient streams of the three networks ([rows][H*G], column = t*G + g)
   int sum_mode, rng_chain;
   float* pd_net[3];
+  float* pd_phys;  // [NPHYS][pd_stride]: per-sample cotangents of the physical scalars in column g (t = 0)
   unsigned long long pd_stride;
 };
 
@@ -530,6 +531,8 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
     tc.ev.dnet[1] = a.pd_net[1];
     tc.ev.dnet[2] = a.pd_net[2];
     tc.ev.dstride = a.pd_stride;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tc.ev.gS[i] = 0.0f;
   }
   // The lane-split kernels have registers to spare: they load the checkpoint x_t one iteration ahead so
   // that the L2 / HBM latency hides behind the previous step's arithmetic.
@@ -663,6 +666,12 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
 #pragma unroll
     for (int i = 0; i < NX; ++i) lam[i] = gx[i];
     if constexpr (PIPE) dtape = dtape_next;
+  }
+  if constexpr (M::Ev::PGRAD && M::NPHYS > 0) {
+    if (a.pd_phys && contrib) {  // one lane per sample (the accumulators are replicated over a sample's lanes)
+#pragma unroll
+      for (int i = 0; i < M::NPHYS; ++i) a.pd_phys[(size_t)i * a.pd_stride + g] = tc.ev.gS[i];
+    }
   }
   emit_cost();
 }

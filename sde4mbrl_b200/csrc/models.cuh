@@ -245,7 +245,7 @@ struct MsdModel {
   using A = A_;
   using Ev = Ev_;
   using Ctx = typename Ev_::Ctx;
-  static constexpr int NX = 2, NU = 1, NR = 2, NAUX = 0;
+  static constexpr int NX = 2, NU = 1, NR = 2, NAUX = 0, NPHYS = 0;
   static constexpr bool GT = (A::FLAGS & SDE4_MSD_GROUND_TRUTH) != 0;
   static constexpr bool SI = (A::FLAGS & SDE4_MSD_SIDE_INFO) != 0;
   static constexpr bool CTRL = (A::FLAGS & SDE4_MSD_CONTROL) != 0;
@@ -315,7 +315,7 @@ struct CartpoleModel {
   using A = A_;
   using Ev = Ev_;
   using Ctx = typename Ev_::Ctx;
-  static constexpr int NX = 4, NU = 1, NR = 4, NAUX = 0;
+  static constexpr int NX = 4, NU = 1, NR = 4, NAUX = 0, NPHYS = 0;
   static constexpr bool SI = (A::FLAGS & SDE4_CART_SIDE_INFO) != 0;
   using NetA = typename A::NetA;
   using NetB = typename A::NetB;
@@ -437,6 +437,7 @@ struct RotorModel {
   using Ev = Ev_;
   using Ctx = typename Ev_::Ctx;
   static constexpr int NX = 13, NU = A::NU, NR = 13, NAUX = 1;
+  static constexpr int NPHYS = 16;  // physical scalars of the packed block whose gradients the training kernel forms
   static constexpr bool DRAG = (A::FLAGS & SDE4_ROTOR_AERO_DRAG) != 0;
   using NetA = typename A::NetA;  // res_forces
   using NetB = typename A::NetB;  // res_moments
@@ -640,13 +641,71 @@ struct RotorModel {
         gu[i] = fmaf(gth, motor_thrust_du(S, u[i]), gu[i]);
       }
     }
+    float Mt[3] = {0.0f, 0.0f, 0.0f};  // residual moment (only needed for the scalar gradients)
     if constexpr (HAS_M) {
       float in[NetB::IN > 0 ? NetB::IN : 1], gi[NetB::IN > 0 ? NetB::IN : 1];
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      Ev::template fwd_vjp<NetB>(A::template ref<2, Ev::L>(W), sc, in, gM, gi);
+      if constexpr (Ev::PGRAD) {
+        Ev::template fwd<NetB, true>(A::template ref<2, Ev::L>(W), sc, in, Mt);
+        Ev::template bwd<NetB>(A::template ref<2, Ev::L>(W), sc, gM, gi);
+      } else {
+        Ev::template fwd_vjp<NetB>(A::template ref<2, Ev::L>(W), sc, in, gM, gi);
+      }
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) gin6[nth_bit(A::B_MASK, k)] += gi[k];
+    }
+    if constexpr (Ev::PGRAD) {
+      // ---- cotangents of the physical scalars S (packed order: mass Ixx Iyy Izz Lmx Lmy CoeffDrag c3 c2 c1 c0
+      //      kdx kdy kdz kh), accumulated over the sweep; vf = lambda * dt is the cotangent of the drift
+      float th[NU], sm0 = 0.0f, sm1 = 0.0f, sm2 = 0.0f, T = 0.0f;
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        th[i] = motor_thrust(S, u[i]);
+        sm0 = fmaf(Mixer<NU>::m(0, i), th[i], sm0);
+        sm1 = fmaf(Mixer<NU>::m(1, i), th[i], sm1);
+        sm2 = fmaf(Mixer<NU>::m(2, i), th[i], sm2);
+        T = fmaf(Mixer<NU>::m(3, i), th[i], T);
+      }
+      // a = rot(q, Fb)/m + g  =>  d/dm = -(a - g)/m ; Fb here already holds residual + drag + thrust
+      {
+        const Quat t2 = qmul_qv(q, Fb[0], Fb[1], Fb[2]);
+        const Quat r2 = qmul(t2, qc);
+        sc.gS[0] -= (vf[3] * r2.x + vf[4] * r2.y + vf[5] * r2.z) * inv_m * inv_m;
+      }
+      // alpha_k = (Mm_k + Mt_k - c_k)/I_k, c = w x (I w)
+      {
+        const float Mm0 = S[4] * sm0, Mm1 = S[5] * sm1, Mm2 = S[6] * sm2;
+        const float c0 = w1 * I2 * w2 - w2 * I1 * w1, c1 = w2 * I0 * w0 - w0 * I2 * w2, c2 = w0 * I1 * w1 - w1 * I0 * w0;
+        const float a0 = (Mm0 + Mt[0] - c0) * fast_rcp(I0), a1 = (Mm1 + Mt[1] - c1) * fast_rcp(I1),
+                    a2 = (Mm2 + Mt[2] - c2) * fast_rcp(I2);
+        sc.gS[1] += -gM[0] * a0 - gM[1] * (w2 * w0) + gM[2] * (w1 * w0);
+        sc.gS[2] += -gM[1] * a1 + gM[0] * (w2 * w1) - gM[2] * (w0 * w1);
+        sc.gS[3] += -gM[2] * a2 - gM[0] * (w1 * w2) + gM[1] * (w0 * w2);
+        sc.gS[4] = fmaf(gM[0], sm0, sc.gS[4]);
+        sc.gS[5] = fmaf(gM[1], sm1, sc.gS[5]);
+        sc.gS[6] = fmaf(gM[2], sm2, sc.gS[6]);
+      }
+      // motor polynomial th(u) = ((c3 u + c2) u + c1) u + c0, cotangent gth_i as in the motor block above
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        float gth = Mixer<NU>::m(3, i) * gFb[2];
+        gth = fmaf(Mixer<NU>::m(0, i) * S[4], gM[0], gth);
+        gth = fmaf(Mixer<NU>::m(1, i) * S[5], gM[1], gth);
+        gth = fmaf(Mixer<NU>::m(2, i) * S[6], gM[2], gth);
+        const float ui = u[i];
+        sc.gS[7] = fmaf(gth, ui * ui * ui, sc.gS[7]);
+        sc.gS[8] = fmaf(gth, ui * ui, sc.gS[8]);
+        sc.gS[9] = fmaf(gth, ui, sc.gS[9]);
+        sc.gS[10] += gth;
+      }
+      if constexpr (DRAG) {
+        sc.gS[11] -= gFb[0] * vb[0];
+        sc.gS[12] -= gFb[1] * vb[1];
+        sc.gS[13] -= gFb[2] * vb[2];
+        sc.gS[14] = fmaf(gFb[2], vb[0] * vb[0] + vb[1] * vb[1], sc.gS[14]);
+      }
+      (void)T;
     }
     gvb[0] = fmaf(gin6[0], d.inv_state_scaling[3], gvb[0]);
     gvb[1] = fmaf(gin6[1], d.inv_state_scaling[4], gvb[1]);

@@ -65,6 +65,9 @@ struct Scratch {
   float* dnet[3];
   size_t dstride, dcol;
   SDE4_DEV void dump(int slot_, int row, float v) const { dnet[slot_][(size_t)row * dstride + dcol] = v; }
+  // training loss: cotangents of the model's physical scalars, accumulated over the backward sweep (registers;
+  // unused members vanish in the other instantiations)
+  float gS[16];
 };
 
 // ---- layer 1: few inputs (registers), fully unrolled ----------------------------------------
@@ -349,6 +352,7 @@ struct EvLT {
     float d1[32 / L_ > 0 ? 32 / L_ : 1], d2[32 / L_ > 0 ? 32 / L_ : 1];  // act' of the own blocks (KEEP)
     float* dnet[3];    // DUMP: see Scratch
     size_t dstride, dcol;
+    float gS[16];      // DUMP: cotangents of the model's physical scalars (see Scratch)
     SDE4_DEV void dump(int slot_, int row, float v) const { dnet[slot_][(size_t)row * dstride + dcol] = v; }
     // a replicated row (inputs, output cotangents): written by lane (k mod L)
     SDE4_DEV void dump_rep(int slot_, int row0, int k, float v) const {

@@ -20,6 +20,7 @@ struct ArchEntry {
   cudaError_t (*launch_cost[5])(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&,
                                 bool grad, bool constr, int blocks, int threads, cudaStream_t);
   // training loss (value + input gradient + parameter-gradient streams); null = not compiled
+  int n_phys;      // physical scalars whose gradients the training kernel forms (rotor: 16; packed offset offsets[0])
   int loss_lanes;  // lanes per sample of launch_loss_ls (0: none compiled)
   cudaError_t (*launch_loss_ls)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&, int, int,
                                 cudaStream_t);
@@ -227,6 +228,8 @@ ArchEntry make_entry(const char* name) {
   add_lane_variant<MLS3>(e);
   e.launch_loss = nullptr;
   if constexpr (!std::is_same<MTRAIN, NoLaneSplit>::value) e.launch_loss = &launch_loss_t<MTRAIN>;
+  e.n_phys = 0;
+  if constexpr (!std::is_same<MTRAIN, NoLaneSplit>::value) e.n_phys = MTRAIN::NPHYS;
   e.launch_loss_ls = nullptr;
   e.loss_lanes = 0;
   if constexpr (!std::is_same<MTRAINLS, NoLaneSplit>::value) {
@@ -272,6 +275,12 @@ struct ArchRegistrar {
   static ::sde4::ArchRegistrar reg_##NAME(                                                                \
       ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES_A>>, MODEL_T<ARCH, ::sde4::EvL<LANES_B>>, \
                          ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::EvL<LANES_C>>>(#NAME));
+
+// two lane-split variants for rollout / cost + training kernels (one thread per sample and LT lanes)
+#define SDE4_REGISTER_LS2_TRAIN(NAME, MODEL_T, ARCH, LANES_A, LANES_B, LT)                                 \
+  static ::sde4::ArchRegistrar reg_##NAME(                                                                \
+      ::sde4::make_entry<MODEL_T<ARCH>, MODEL_T<ARCH, ::sde4::EvL<LANES_A>>, MODEL_T<ARCH, ::sde4::EvL<LANES_B>>, \
+                         MODEL_T<ARCH, ::sde4::Ev1P>, ::sde4::NoLaneSplit, MODEL_T<ARCH, ::sde4::EvLT<LT, true>>>(#NAME));
 
 // shorthand for the architecture zoo
 constexpr int TANH = SDE4_ACT_TANH, SWISH = SDE4_ACT_SWISH;

@@ -294,13 +294,17 @@ int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* a, v
   return SDE4_OK;
 }
 
-static size_t loss_dump_floats(const ArchEntry& e, size_t K, size_t off[3]) {
+// rows of the parameter-gradient streams: per network [in | h1 | h2 | c1 | g2 | gout] (+ scaler rows after the density
+// net), then the physical-scalar rows (rotor); off[3] = offset of the latter
+static size_t loss_dump_floats(const ArchEntry& e, size_t K, size_t off[4]) {
   size_t tot = 0;
   for (int s = 0; s < 3; ++s) {
     off[s] = tot;
     const int* d = e.net_dims[s];
     if (d[0] > 0) tot += (size_t)(d[0] + 2 * d[1] + 2 * d[2] + d[3] + (s == 0 ? e.n_scaler : 0)) * K;
   }
+  off[3] = tot;
+  tot += (size_t)e.n_phys * K;
   return tot;
 }
 
@@ -313,14 +317,14 @@ static int loss_wgrad_pairs(const ArchEntry& e) {
     pairs += d[0] * d[1] + d[1] + d[1] * d[2] + d[2] + d[3] * d[2] + d[3];
     if (s == 0) pairs += e.n_scaler;
   }
-  return pairs;
+  return pairs + e.n_phys;
 }
 
 size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t H) {
   if (!model) return 0;
   const ArchEntry* e = find_arch(*model);
   if (!e || !e->launch_loss) return 0;
-  size_t off[3];
+  size_t off[4];
   const size_t K = (size_t)B * N * H;
   const size_t dump = loss_dump_floats(*e, K, off) * 4;
   const size_t partial = ((K + WG_KC - 1) / WG_KC) * (size_t)loss_wgrad_pairs(*e) * 4;
@@ -369,7 +373,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
                                : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
-  size_t dump_off[3] = {0, 0, 0};
+  size_t dump_off[4] = {0, 0, 0, 0};
   const size_t Kcols = (size_t)G * a->H;
   const size_t dump_bytes = lo.enabled ? loss_dump_floats(*e, Kcols, dump_off) * 4 : 0;
   const size_t wg_bytes = lo.enabled ? ((Kcols + WG_KC - 1) / WG_KC) * (size_t)loss_wgrad_pairs(*e) * 4 : 0;
@@ -426,6 +430,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   k.pd_stride = Kcols;
   float* dump_base = (float*)(ws + L.total);
   for (int s2 = 0; s2 < 3; ++s2) k.pd_net[s2] = lo.enabled ? dump_base + dump_off[s2] : nullptr;
+  k.pd_phys = (lo.enabled && e->n_phys) ? dump_base + dump_off[3] : nullptr;
   k.has_terminal = (a->terminal && a->terminal->kind != SDE4_COST_NONE) ? 1 : 0;
   const sde4_cost_desc td = k.has_terminal ? *a->terminal : empty_cost();
   const long long nthr = G * lanes;
@@ -517,6 +522,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
       add(nullptr, 1, r_go, OUT, b2, 4);
       if (s2 == 0 && e->n_scaler) add(nullptr, 1, r_go + (size_t)OUT * Kcols, e->n_scaler, lo.grad_params + e->off_scaler, e->n_scaler);
     }
+    if (e->n_phys) add(nullptr, 1, k.pd_phys, e->n_phys, lo.grad_params + e->offsets[0], e->n_phys);
     wk.n_pairs = pair0;
     wk.n_chunks = (int)((Kcols + WG_KC - 1) / WG_KC);
     wk.partial = (float*)(ws + L.total + ((dump_bytes + 255) & ~(size_t)255));

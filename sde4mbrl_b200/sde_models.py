@@ -373,6 +373,42 @@ class SDERotorModel(ControlledSDE):
             for k, n in enumerate(("aero_kdx", "aero_kdy", "aero_kdz", "aero_kh")):
                 out[base + 11 + k] = float(top[n])
 
+    def unpack_grads(self, gpacked, desc=None):
+        """Network / scaler gradients as in the base class, plus the gradients of the LEARNABLE physical scalars
+        (chain rule through ``_pack_scalars``: ``Lmy = Lmx`` when ``assume_sym``, motor polynomial coefficients)."""
+        desc = self.describe() if desc is None else desc
+        tree = super().unpack_grads(gpacked, desc)
+        off, _ = self.layout(desc)
+        g = np.asarray(gpacked, np.float32)[off[0]:off[0] + 16]
+        ip = self.params["init_params"]
+        fixed = self.params.get("fixed_init_params", False)
+        fm = ip["fm_model"]
+        order, const = int(fm.get("order", 1)), bool(fm.get("use_constant_term", False))
+        assume_sym = bool(fm.get("assume_sym", True))
+        out = {}
+        idx = {n: k for k, n in enumerate(_ROTOR_SCALARS)}
+
+        def learnable(n):
+            return not (n in ip and fixed)
+        for n in ("mass", "Ixx", "Iyy", "Izz", "Lmx", "CoeffDrag"):
+            if learnable(n):
+                out[n] = np.float32(g[idx[n]])
+        if assume_sym:
+            if "Lmx" in out:
+                out["Lmx"] = np.float32(out["Lmx"] + g[idx["Lmy"]])
+        elif learnable("Lmy"):
+            out["Lmy"] = np.float32(g[idx["Lmy"]])
+        for i in range(order + (1 if const else 0)):
+            n = "coeffMot%d" % i
+            if learnable(n):
+                out[n] = np.float32(g[7 + (3 - (order - i) if i < order else 3)])
+        if self.params.get("aero_drag_effect", False):
+            for k, n in enumerate(("aero_kdx", "aero_kdy", "aero_kdz", "aero_kh")):
+                out[n] = np.float32(g[11 + k])
+        if out:
+            tree.setdefault(self.module_name, {}).update(out)
+        return tree
+
     def _init_scalars(self, rng):
         ip = self.params["init_params"]
         top = {}

@@ -142,3 +142,49 @@ def test_lane_split_training_kernel_matches_one_thread_per_sample(cuda, kind, cl
     g0, g1 = g0.cpu().numpy(), g1.cpu().numpy()
     assert np.abs(g1).max() > 0
     assert np.max(np.abs(g0 - g1)) <= 2e-4 * np.abs(g1).max()
+
+
+@pytest.mark.parametrize("lanes", [0, 1])
+def test_rotor_training_loss_and_physical_scalar_gradients(cuda, lanes):
+    """Training loss of the multirotor nSDE: gradients w.r.t. the three networks, the scaler AND the learnable physical
+    scalars (mass, inertia, arm lengths, drag / motor coefficients, aerodynamic drag terms) vs float64 autograd of
+    the oracle; lane-split (8 lanes) and one-thread-per-sample training kernels."""
+    from sde4mbrl_b200 import nsde, random as R
+    B, N, H = 6, 2, 8
+    pm = configs.hexa_model(horizon=1, num_particles=1, stepsize=0.01)
+    lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 2,
+          "horizon": H, "obs_weights": [2.6, 3.1, 2.7, 3.2, 3.5, 1.5, 1, 0.3, 0.3, 0.4, 4, 3.5, 1.4], "pen_data": 1.0,
+          "pen_weights": 0.0}
+    _, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.SDERotorModel, verbose=False)
+    model = sde_models.SDERotorModel(pm)
+    nn = configs.random_params(model, seed=4)
+    rng = np.random.default_rng(0)
+    y = np.stack([np.stack([hp.start_state("hexa", rng) for _ in range(H + 1)]) for _ in range(B)]).astype(np.float32)
+    u = rng.uniform(0.25, 0.45, (B, H, 6)).astype(np.float32)
+    eng = loss_fn.engine
+    keys = tf.split(tf.PRNGKey(3), B)
+    from sde4mbrl_b200 import costs
+    ow = np.asarray(lp["obs_weights"], np.float64)
+    dc = costs.QuadraticCost(list(1.0 / ow ** 2), [0.0] * 6, [0.0] * 6)
+    loss_b, gpacked = eng.loss_grad(nn, y, u, orc.compute_timesteps(dict(pm, horizon=H)), dc.desc, keys, N=N, lanes=lanes)
+    grads = model.unpack_grads(gpacked.cpu().numpy(), eng.desc)
+    tree = _tree64(nn)
+    om = orc.make_model("sde_rotor_model", dict(pm, horizon=H), tree, torch.float64)
+    dw = torch.tensor(orc.loss_noise(tf.PRNGKey(3), B, N, H, 13), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, "sde_rotor_model", torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw,
+                          lp["obs_weights"])
+    Ld.backward()
+    assert abs(float(loss_b.mean()) - float(Ld)) < 3e-5 * abs(float(Ld))
+    top = tree["sde_rotor_model"]
+    phys = [k for k in top if k != "scaler"]
+    assert {"mass", "Ixx", "Iyy", "Izz", "Lmx", "CoeffDrag", "coeffMot0", "coeffMot1"} <= set(phys)
+    for k in phys:
+        want = float(top[k].grad)
+        got = float(grads["sde_rotor_model"][k])
+        assert abs(got - want) <= 2e-3 * abs(want) + 1e-6 * max(abs(float(t.grad)) for t in (top[n] for n in phys)), (k, got, want)
+    gmax = max(float(v.grad.abs().max()) for m, d in tree.items() if m != "sde_rotor_model" for v in d.values())
+    for m, d in tree.items():
+        if m == "sde_rotor_model":
+            continue
+        for k, v in d.items():
+            assert np.max(np.abs(grads[m][k] - v.grad.numpy())) <= 2e-3 * float(v.grad.abs().max()) + 1e-5 * gmax, (m, k)
