@@ -21,7 +21,7 @@ SDE4_REGISTER(hexa_ode, RotorModel<HexaOde>)
 SDE4_REGISTER(hexa_ode_m3, RotorModel<HexaOdeM3>)
 SDE4_REGISTER(hexa_ode_w24, RotorModel<HexaOde24>)
 SDE4_REGISTER(hexa_prior, RotorModel<HexaPrior>)
-SDE4_REGISTER(iris_d32_swish, RotorModel<IrisD32s>)
+SDE4_REGISTER_TRAIN_LS(iris_d32_swish, RotorModel, IrisD32s, 8)
 SDE4_REGISTER(iris_ode, RotorModel<IrisOde>)
 SDE4_REGISTER(iris_prior, RotorModel<IrisPrior>)
 }  // namespace sde4

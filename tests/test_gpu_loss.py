@@ -144,14 +144,14 @@ def test_lane_split_training_kernel_matches_one_thread_per_sample(cuda, kind, cl
     assert np.max(np.abs(g0 - g1)) <= 2e-4 * np.abs(g1).max()
 
 
-@pytest.mark.parametrize("lanes", [0, 1])
-def test_rotor_training_loss_and_physical_scalar_gradients(cuda, lanes):
+@pytest.mark.parametrize("lanes,dens", [(0, (32, 32, "swish")), (1, (32, 32, "swish")), (0, (16, 16, "tanh"))])
+def test_rotor_training_loss_and_physical_scalar_gradients(cuda, lanes, dens):
     """Training loss of the multirotor nSDE: gradients w.r.t. the three networks, the scaler AND the learnable physical
     scalars (mass, inertia, arm lengths, drag / motor coefficients, aerodynamic drag terms) vs float64 autograd of
     the oracle; lane-split (8 lanes) and one-thread-per-sample training kernels."""
     from sde4mbrl_b200 import nsde, random as R
     B, N, H = 6, 2, 8
-    pm = configs.hexa_model(horizon=1, num_particles=1, stepsize=0.01)
+    pm = configs.hexa_model(horizon=1, num_particles=1, stepsize=0.01, density=dens[:2], density_act=dens[2])
     lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 2,
           "horizon": H, "obs_weights": [2.6, 3.1, 2.7, 3.2, 3.5, 1.5, 1, 0.3, 0.3, 0.4, 4, 3.5, 1.4], "pen_data": 1.0,
           "pen_weights": 0.0}
@@ -188,3 +188,42 @@ def test_rotor_training_loss_and_physical_scalar_gradients(cuda, lanes):
             continue
         for k, v in d.items():
             assert np.max(np.abs(grads[m][k] - v.grad.numpy())) <= 2e-3 * float(v.grad.abs().max()) + 1e-5 * gmax, (m, k)
+
+
+@pytest.mark.parametrize("fixture,n_u", [("ref_weights_hexa_ahg_v4.npz", 6), ("ref_weights_iris_sitl.npz", 4)])
+def test_training_gradients_on_shipped_rotor_models(cuda, fixture, n_u):
+    """The reference's own learned multirotor models (hexacopter 16x16 tanh density, quadrotor 32x32 swish): training
+    loss value and every parameter gradient -- networks, scaler, physical scalars -- vs the oracle's autograd."""
+    import os
+    from sde4mbrl_b200 import io, nsde
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nn, nominal = io.load_npz_fixture(os.path.join(gold, fixture))
+    B, N, H = 5, 2, 6
+    pm = dict(nominal)
+    pm.pop("density_loss", None)
+    pm.pop("num_sample2consider", None)  # random time-index subsampling (jax.random.choice) is not built: all steps count
+    lp = {"seed": 0, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 2,
+          "horizon": H, "obs_weights": list(pm.get("state_scaling", [1.0] * 13)), "pen_data": 1.0, "pen_weights": 0.0}
+    _, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.SDERotorModel, verbose=False)
+    rng = np.random.default_rng(1)
+    y = np.stack([np.stack([hp.start_state("hexa", rng) for _ in range(H + 1)]) for _ in range(B)]).astype(np.float32)
+    u = rng.uniform(0.25, 0.45, (B, H, n_u)).astype(np.float32)
+    from sde4mbrl_b200 import random as R
+    total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(9))
+    tree = _tree64(nn)
+    om = orc.make_model("sde_rotor_model", pm, tree, torch.float64)
+    dw = torch.tensor(orc.loss_noise(tf.PRNGKey(9), B, N, H, 13), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, "sde_rotor_model", torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw,
+                          lp["obs_weights"])
+    Ld.backward()
+    assert abs(info["dataLoss"] - float(Ld)) < 5e-5 * abs(float(Ld))
+    checked = 0
+    gm = max(float(v.grad.abs().max()) for d in tree.values() for v in d.values() if v.grad is not None)
+    for m, d in tree.items():
+        for k, v in d.items():
+            if v.grad is None:
+                continue
+            want = v.grad.numpy()
+            assert np.max(np.abs(np.asarray(grads[m][k]) - want)) <= 3e-3 * np.max(np.abs(want)) + 1e-6 * gm, (m, k)
+            checked += 1
+    assert checked >= 20
