@@ -214,6 +214,10 @@ typedef struct sde4_cost_args {
    * batched APG solver evaluates line-search candidates one step size at a time and drops the problems that have
    * already accepted one; whole warps of skipped problems exit at once).  NULL: every problem is evaluated. */
   const int32_t* problem_mask;
+  /* sde4_loss_grad only (ignored by sde4_cost_grad): optional device float[H][P*N], weight of the data term of
+   * sample g = p*N + n at time t+1 in step_weight[t*P*N + g] -- the 0/1 indicator of the time indexes
+   * `num_sample2consider` keeps (sde4mbrl/nsde.py:753-760), see sde4_rng_choice_mask.  NULL: every step counts. */
+  const float* step_weight;
 } sde4_cost_args;
 
 /* Upper bound over the lane / noise modes the launcher may pick. */
@@ -247,6 +251,10 @@ int sde4_rng_split(const uint32_t* key_dev, int32_t num, int32_t rng_mode, uint3
  * out[K][num][2] = split(keys[k], num);  out[K][n] = normal(keys[k], (n,)) */
 int sde4_rng_split_many(const uint32_t* keys_dev, uint64_t K, int32_t num, int32_t rng_mode, uint32_t* out, void* stream);
 int sde4_rng_normal_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32_t rng_mode, float* out, void* stream);
+/* out[t*K + k] = 1.0f if t is among jax.random.choice(keys[k], n, shape=(m,), replace=False), else 0.0f
+ * (sde4mbrl/nsde.py:755; jax: permutation(key, n)[:m] = one round of a stable sort of arange(n) by
+ * random_bits(split(key)[1], 32, (n,)), valid for n <= 1625 where jax needs a single round). */
+int sde4_rng_choice_mask(const uint32_t* keys_dev, uint64_t K, int32_t n, int32_t m, int32_t rng_mode, float* out, void* stream);
 
 /* ---- training loss: create_model_loss_fn(...).loss_fn data term and jax.grad of it w.r.t. the model
  *      parameters, sde4mbrl/nsde.py:683-804 (sample_for_loss_computation), :1185-1203 (multi_sampling,
@@ -259,8 +267,9 @@ int sde4_rng_normal_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32
  *      split(k_b, N)[n] -> split(., 3)[0] -> split(., 2)[0] as nsde.py:1187,709 / sde_solver.py:276).
  *      grad_params (device, sde4_param_layout() floats, same layout as the parameter block) receives
  *      d (mean_b loss[b]) / d params; args->grad (may be NULL) the gradient w.r.t. the controls.
- *      Not covered: density_loss / mu_coeff terms and num_sample2consider, the
- *      multirotor's physical scalars (kernel exists for the MSD and cartpole architectures). */
+ *      args->step_weight restricts the sum over t to the steps `num_sample2consider` draws per sample.
+ *      The density_loss / mu_coeff terms are i.i.d. work at the data points and live above this call
+ *      (sde4mbrl_b200/density_loss.py). */
 size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t H);
 int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* args, float* grad_params, void* stream);
 

@@ -565,10 +565,22 @@ def state_transform_for_loss(kind, x):
     return x
 
 
-def data_loss(model, kind, ymeas, uval, dw, obs_weights=1.0, num_steps2data=1):
+def loss_step_indices(rng, B, N, H, m, mode=tf.MODE_ORIGINAL):
+    """idx[B, N, m]: time indexes ``num_sample2consider`` keeps for sample (b, n) (nsde.py:753-760):
+    ``choice(split(k_bn, 3)[1], H, (m,), replace=False)`` with k_bn as in ``loss_noise``."""
+    kb = tf.split(rng, B, mode)
+    out = np.zeros((B, N, m), np.int64)
+    for b in range(B):
+        kbn = tf.split(kb[b], N, mode)
+        for n in range(N):
+            out[b, n] = tf.choice_without_replacement(tf.split(kbn[n], 3, mode)[1], H, m, mode)
+    return out
+
+
+def data_loss(model, kind, ymeas, uval, dw, obs_weights=1.0, num_steps2data=1, step_idx=None):
     """mean over (batch, particles) of sum_t sum_i ((T(y_meas) - T(y_pred)) / w)^2 (nsde.py:766, :1203) with
-    u_sampling_strategy 'first' and no num_sample2consider.  ymeas[B, Hd+1, n_y], uval[B, Hd, n_u],
-    dw[B, N, H, n_x] (H = Hd / num_steps2data)."""
+    u_sampling_strategy 'first'.  ymeas[B, Hd+1, n_y], uval[B, Hd, n_u], dw[B, N, H, n_x] (H = Hd / num_steps2data);
+    ``step_idx[B, N, m]`` (``loss_step_indices``) restricts the sum to the kept time indexes."""
     ts = compute_timesteps(model.params)
     H = len(ts)
     B = ymeas.shape[0]
@@ -578,7 +590,10 @@ def data_loss(model, kind, ymeas, uval, dw, obs_weights=1.0, num_steps2data=1):
     pred = state_transform_for_loss(kind, xs[:, :, 1:])
     meas = state_transform_for_loss(kind, y_values[:, None, 1:])
     w = _t(np.broadcast_to(np.asarray(obs_weights, np.float64), (pred.shape[-1],)), pred)
-    err = (((meas - pred) / w) ** 2).sum(dim=(-1, -2))  # [B, N]
+    e2 = (((meas - pred) / w) ** 2).sum(dim=-1)  # [B, N, H]
+    if step_idx is not None:
+        e2 = torch.gather(e2, 2, torch.as_tensor(step_idx))
+    err = e2.sum(dim=-1)  # [B, N]
     return err.mean(dim=1).mean(), err
 
 

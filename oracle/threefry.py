@@ -142,6 +142,19 @@ def normal(key, shape, mode=MODE_ORIGINAL):
 # ---------------------------------------------------------------------------
 # Key-derivation chains of the hot path
 # ---------------------------------------------------------------------------
+def choice_without_replacement(key, n, m, mode=MODE_ORIGINAL):
+    """``jax.random.choice(key, n, shape=(m,), replace=False)`` (sde4mbrl/nsde.py:755): jax draws
+    ``permutation(key, n)[:m]``; ``permutation`` -> ``_shuffle(key, arange(n))`` = ``ceil(3 ln n / ln(2^32-1))`` rounds
+    of ``key, subkey = split(key); x = stable_sort_by(random_bits(subkey, 32, (n,)), x)`` (jax/_src/random.py, restated
+    from the published algorithm -- jax is not installable here, parity unpinned)."""
+    x = np.arange(n)
+    rounds = int(np.ceil(3 * np.log(max(1, n)) / np.log(np.iinfo(np.uint32).max)))
+    for _ in range(rounds):
+        key, sub = split(key, 2, mode)
+        x = x[np.argsort(random_bits(sub, (n,), mode), kind="stable")]
+    return x[:m]
+
+
 def rollout_particle_brownian_keys(rng, num_particles, mode=MODE_ORIGINAL):
     """Per-particle Brownian keys: ``split(rng, N)[p]`` (nsde.py:1026) followed
     by ``rng_brownian, _ = split(k_p)`` (sde_solver.py:276)."""

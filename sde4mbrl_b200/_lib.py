@@ -83,7 +83,7 @@ class CostArgs(C.Structure):
                 ("cost", C.c_void_p), ("grad", C.c_void_p), ("xtraj", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("block_threads", C.c_int32),
                 ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32),
-                ("data_mod", C.c_int32), ("problem_mask", C.c_void_p)]
+                ("data_mod", C.c_int32), ("problem_mask", C.c_void_p), ("step_weight", C.c_void_p)]
 
 
 class ApgParams(C.Structure):
@@ -111,7 +111,7 @@ EXPORTED_SYMBOLS = (
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
     "sde4_apg_scratch_floats", "sde4_cost_grad_host", "sde4_cost_grad_host_staging_bytes",
-    "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_apg_ls_step",
+    "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_apg_ls_step",
 )
 
 _lib = None
@@ -164,6 +164,8 @@ def load():
     lib.sde4_rng_split_many.restype = C.c_int
     lib.sde4_rng_normal_many.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p, C.c_void_p]
     lib.sde4_rng_normal_many.restype = C.c_int
+    lib.sde4_rng_choice_mask.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.sde4_rng_choice_mask.restype = C.c_int
     lib.sde4_fma_peak.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_double),
                                   C.c_void_p]
     lib.sde4_fma_peak.restype = C.c_int

@@ -60,6 +60,7 @@ struct CostK {
   // parameter-gradient streams of the three networks ([rows][H*G], column = t*G + g)
   int sum_mode, rng_chain;
   float* pd_net[3];
+  const float* step_w;  // training loss only: optional [H][G] weight of the data term at t+1 (num_sample2consider)
   float* pd_phys;  // [NPHYS][pd_stride]: per-sample cotangents of the physical scalars in column g (t = 0)
   unsigned long long pd_stride;
 };
@@ -506,7 +507,10 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
 #pragma unroll
   for (int j = 0; j < NU; ++j) gu[j] = 0.0f;  // row H-1 also receives the u-gradient of stage H
   {
-    const float wH = a.sum_mode ? 1.0f : 0.5f * __ldg(a.dt + H - 1);
+    float wH = a.sum_mode ? 1.0f : 0.5f * __ldg(a.dt + H - 1);
+    if constexpr (M::Ev::PGRAD) {  // training instantiations only: the MPC kernels do not carry the load
+      if (a.step_w) wH = __ldg(a.step_w + (size_t)(H - 1) * G + g);
+    }
     float cH = stage_cost<NX, NU, true, PLAINC>(cd, x, u, xr + (size_t)H * NX, true, wH, lam, gu);
     if (CONSTR) {
       float sl[NX];
@@ -609,7 +613,10 @@ __global__ void __launch_bounds__(256) k_cost(const __grid_constant__ sde4_model
       }
     }
     // stage cost at t: trapezoid weight w_t
-    const float wt = a.sum_mode ? (t > 0 ? 1.0f : 0.0f) : (t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt);
+    float wt = a.sum_mode ? (t > 0 ? 1.0f : 0.0f) : (t > 0 ? 0.5f * (__ldg(a.dt + t - 1) + dt) : 0.5f * dt);
+    if constexpr (M::Ev::PGRAD) {
+      if (a.step_w && t > 0) wt = __ldg(a.step_w + (size_t)(t - 1) * G + g);
+    }
     float ct = stage_cost<NX, NU, true, PLAINC>(cd, x, u, xr + (size_t)t * NX, true, wt, gx, gu);
     if (CONSTR) {
       float sl[NX];

@@ -122,6 +122,26 @@ __global__ void k_rng_normal_many(const uint32_t* __restrict__ keys, unsigned lo
   out[i] = bits_to_normal(jax_bits(keys[2 * k], keys[2 * k + 1], i - k * n, n, mode));
 }
 
+// jax.random.choice(key, n, (m,), replace=False) as a 0/1 indicator over [0, n): permutation(key, n) is one round of
+// a stable sort of arange(n) by random_bits(split(key)[1], 32, (n,)); index t is drawn iff its rank is below m.
+// One thread per (t, key); n is a training horizon (tens), so the O(n) rank count per thread is noise.
+__global__ void k_rng_choice_mask(const uint32_t* __restrict__ keys, unsigned long long K, int n, int m, int mode,
+                                  float* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * (unsigned long long)n) return;
+  const unsigned long long k = i % K;
+  const int t = (int)(i / K);
+  uint32_t s0, s1;
+  jax_split(keys[2 * k], keys[2 * k + 1], 1, 2, mode, s0, s1);
+  const uint32_t mine = jax_bits(s0, s1, t, n, mode);
+  int rank = 0;
+  for (int j = 0; j < n; ++j) {
+    const uint32_t b = jax_bits(s0, s1, j, n, mode);
+    rank += (b < mine || (b == mine && j < t)) ? 1 : 0;
+  }
+  out[i] = rank < m ? 1.0f : 0.0f;
+}
+
 // ----------------------------------------------------------------------------
 // FP32 FMA peak micro-benchmark (roofline denominator)
 // ----------------------------------------------------------------------------

@@ -425,6 +425,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   k.data_mod = a->data_mod > 0 ? a->data_mod : a->P;
   k.mask = a->problem_mask;
+  k.step_w = lo.enabled ? a->step_weight : nullptr;
   k.sum_mode = lo.enabled ? 1 : 0;
   k.rng_chain = lo.enabled ? 1 : 0;
   k.pd_stride = Kcols;
@@ -589,6 +590,18 @@ int sde4_rng_normal_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32
   if (rng_mode == SDE4_RNG_ORIGINAL && n > 0xffffffffull) return fail(SDE4_ERR_UNSUPPORTED, "original layout beyond 2^32 elements");
   const uint64_t tot = K * n;
   k_rng_normal_many<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keys_dev, K, n, rng_mode, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
+int sde4_rng_choice_mask(const uint32_t* keys_dev, uint64_t K, int32_t n, int32_t m, int32_t rng_mode, float* out, void* stream) {
+  if (!keys_dev || !out) return fail(SDE4_ERR_INVALID, "bad argument");
+  if (n <= 0 || m < 0 || m > n) return fail(SDE4_ERR_INVALID, "choice: need 0 <= m <= n, n > 0");
+  if (n > 1625) return fail(SDE4_ERR_UNSUPPORTED, "choice: jax shuffles in several rounds beyond n = 1625");
+  if (K == 0) return SDE4_OK;
+  const uint64_t tot = K * (uint64_t)n;
+  k_rng_choice_mask<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keys_dev, K, n, m, rng_mode, out);
   cudaError_t err = cudaGetLastError();
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
   return SDE4_OK;

@@ -356,7 +356,8 @@ class Engine:
         return cost, grad, xtraj
 
     # ---- K2 (training variant) + K3 + K5 -----------------------------------
-    def loss_grad(self, nn_params, ymeas, u, dt, data_cost, key, N=1, noise=None, noise_mode=None, block_threads=0, lanes=0):
+    def loss_grad(self, nn_params, ymeas, u, dt, data_cost, key, N=1, noise=None, noise_mode=None, block_threads=0, lanes=0,
+                  step_weight=None):
         """Data term of the training loss and its gradient w.r.t. the PACKED parameter block.
         ymeas[B, H+1, n_x] (rows = solver steps), u[B, H, n_u], key[B, 2] = split(rng, B).
         Returns (loss[B], grad_packed[param_total]); d(mean_b loss)/d params = grad_packed."""
@@ -400,5 +401,9 @@ class Engine:
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
         a.block_threads = block_threads
         a.lanes = lanes  # 0: lane-split training kernel while the minibatch is latency bound; 1: one thread per sample
+        if step_weight is not None:  # float32[H, B*N]: weight of the data term of sample g at time t+1 (num_sample2consider)
+            assert step_weight.dtype == torch.float32 and step_weight.is_cuda and tuple(step_weight.shape) == (H, B * N)
+            step_weight = step_weight.contiguous()
+            a.step_weight = step_weight.data_ptr()
         L.check(lib.sde4_loss_grad(C.byref(self.desc), C.byref(a), _ptr(gpar), _stream()))
         return loss, gpar

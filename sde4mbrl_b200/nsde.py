@@ -399,9 +399,9 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
     ``loss_params`` (nsde.py:1064-1134).
 
     The distance-aware regulariser (``density_loss`` gradient-norm / strong-convexity / mu terms) is evaluated by
-    ``density_loss.py`` at the data points with the reference's key chain.  Not covered (each raises):
-    ``num_sample2consider`` below the horizon (``jax.random.choice``), ``u_sampling_strategy='random'``,
-    ``learn_mucoeff.quad_approx``."""
+    ``density_loss.py`` at the data points with the reference's key chain; ``num_sample2consider`` below the horizon
+    becomes a per-sample 0/1 step weight drawn on the device (``sde4_rng_choice_mask``).  Not covered (each raises):
+    ``u_sampling_strategy='random'``, ``learn_mucoeff.quad_approx``, ``density_on_partial`` with subsampling."""
     _check_constr(sde_constr)
     vprint = print if verbose else (lambda *a, **k: None)
     params_model = model_params
@@ -442,8 +442,9 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
     else:
         loss_params["pen_mu_coeff"] = 0.0
     dl = loss_params.get("density_loss", None)
-    if params_model.get("num_sample2consider", horizon) < horizon:
-        raise Sde4Error("num_sample2consider < horizon (jax.random.choice subsampling) has no compiled kernel yet")
+    n_consider = int(params_model.get("num_sample2consider", horizon))
+    if n_consider < horizon and dl is not None and params_model.get("density_on_partial", False):
+        raise Sde4Error("density_on_partial together with num_sample2consider is not built")
     strategy = params_model.get("u_sampling_strategy", "first")
     if strategy not in ("first", "mean", "median"):
         raise Sde4Error("u_sampling_strategy '%s' has no compiled kernel" % strategy)
@@ -504,7 +505,13 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         B = y_values.shape[0]
         keys = _random.split(key, B)  # nsde.py:1196
         engine.rng_mode = _random.rng_mode()
-        loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample)
+        step_weight = None
+        if n_consider < horizon:  # nsde.py:753-760: every (b, n) keeps its own random subset of the time indexes
+            k_bn = _random.split_many(keys, num_sample)  # [B, N, 2]  (nsde.py:1187)
+            k_s2c = _random.split_many(k_bn, 3)[:, :, 1].reshape(-1, 2)  # rng_sample2consider (nsde.py:709)
+            step_weight = _random.choice_mask_many(k_s2c, horizon, n_consider)
+        loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample,
+                                           step_weight=step_weight)
         loss_data = float(loss_b.mean())
         total = 0.0
         if loss_params.get("pen_data", 0) > 0:

@@ -85,3 +85,13 @@ def normal_many(keys, shape):
     out = torch.empty((flat.shape[0], n), dtype=torch.float32, device=flat.device)
     L.check(L.load().sde4_rng_normal_many(_ptr(flat), flat.shape[0], n, rng_mode(), _ptr(out), _stream()))
     return out.reshape(lead + tuple(shape))
+
+
+def choice_mask_many(keys, n, m):
+    """0/1 indicator of ``jax.vmap(lambda k: jax.random.choice(k, n, shape=(m,), replace=False))(keys)``:
+    keys[K, 2] -> float32 [n, K] (time-major, the layout ``sde4_cost_args.step_weight`` reads)."""
+    keys = as_key(keys)
+    flat = keys.reshape(-1, 2).contiguous()
+    out = torch.empty((int(n), flat.shape[0]), dtype=torch.float32, device=flat.device)
+    L.check(L.load().sde4_rng_choice_mask(_ptr(flat), flat.shape[0], int(n), int(m), rng_mode(), _ptr(out), _stream()))
+    return out

@@ -201,9 +201,10 @@ def test_training_gradients_on_shipped_rotor_models(cuda, fixture, n_u):
     B, N, H = 5, 2, 6
     pm = dict(nominal)
     pm.pop("density_loss", None)
-    pm.pop("num_sample2consider", None)  # random time-index subsampling (jax.random.choice) is not built: all steps count
+    pm.pop("num_sample2consider", None)
     lp = {"seed": 0, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 2,
-          "horizon": H, "obs_weights": list(pm.get("state_scaling", [1.0] * 13)), "pen_data": 1.0, "pen_weights": 0.0}
+          "horizon": H, "obs_weights": list(pm.get("state_scaling", [1.0] * 13)), "pen_data": 1.0, "pen_weights": 0.0,
+          "num_sample2consider": 4}  # the reference's training configs subsample the time indexes
     _, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.SDERotorModel, verbose=False)
     rng = np.random.default_rng(1)
     y = np.stack([np.stack([hp.start_state("hexa", rng) for _ in range(H + 1)]) for _ in range(B)]).astype(np.float32)
@@ -214,7 +215,7 @@ def test_training_gradients_on_shipped_rotor_models(cuda, fixture, n_u):
     om = orc.make_model("sde_rotor_model", pm, tree, torch.float64)
     dw = torch.tensor(orc.loss_noise(tf.PRNGKey(9), B, N, H, 13), dtype=torch.float64)
     Ld, _ = orc.data_loss(om, "sde_rotor_model", torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw,
-                          lp["obs_weights"])
+                          lp["obs_weights"], step_idx=orc.loss_step_indices(tf.PRNGKey(9), B, N, H, 4))
     Ld.backward()
     assert abs(info["dataLoss"] - float(Ld)) < 5e-5 * abs(float(Ld))
     checked = 0
@@ -227,3 +228,50 @@ def test_training_gradients_on_shipped_rotor_models(cuda, fixture, n_u):
             assert np.max(np.abs(np.asarray(grads[m][k]) - want)) <= 3e-3 * np.max(np.abs(want)) + 1e-6 * gm, (m, k)
             checked += 1
     assert checked >= 20
+
+
+@pytest.mark.parametrize("kind,cls,oname,B,N,H,m,lanes", [("cartpole", sde_models.CartPoleSDE, "cart_pole_sde", 6, 3, 12, 5, 0),
+                                                          ("cartpole", sde_models.CartPoleSDE, "cart_pole_sde", 6, 3, 12, 5, 1),
+                                                          ("msd", sde_models.MassSpringDamper, "mass_spring_damper", 4, 2, 9, 1, 0)])
+def test_num_sample2consider_subsampled_loss(cuda, kind, cls, oname, B, N, H, m, lanes):
+    """``num_sample2consider`` < horizon (nsde.py:753-760): every (minibatch element, particle) keeps its own random
+    subset of time indexes -- drawn on the device with the reference's key chain -- and only those enter the data
+    term and its gradient."""
+    from sde4mbrl_b200 import nsde, random as R
+    pm = hp.KINDS[kind][0](horizon=1, num_particles=1)
+    ow = [9, 5, 1, 1.0, 10] if oname == "cart_pole_sde" else [0.5, 2.0]
+    lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 4,
+          "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 0.0, "num_sample2consider": m}
+    _, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=cls, verbose=False)
+    nn = configs.random_params(cls(pm), seed=4)
+    rng = np.random.default_rng(0)
+    nx, nu = pm["n_x"], pm["n_u"]
+    y = (rng.normal(0, 0.5, (B, H + 1, nx)) + (np.array([0, 0, 3.0, 0]) if nx == 4 else 0)).astype(np.float32)
+    u = rng.uniform(-1, 1, (B, H, nu)).astype(np.float32)
+    if lanes:
+        eng = loss_fn.engine
+        orig = eng.loss_grad
+        eng.loss_grad = lambda *a, **k: orig(*a, **dict(k, lanes=lanes))
+    total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(11))
+    idx = orc.loss_step_indices(tf.PRNGKey(11), B, N, H, m)
+    assert all(len(set(idx[b, n])) == m for b in range(B) for n in range(N))
+    # the device indicator itself, bit for bit
+    kbn = R.split_many(R.split(R.PRNGKey(11), B), N)
+    mask = R.choice_mask_many(R.split_many(kbn, 3)[:, :, 1].reshape(-1, 2), H, m).cpu().numpy()  # [H, B*N]
+    want_mask = np.zeros((H, B * N), np.float32)
+    for b in range(B):
+        for n in range(N):
+            want_mask[idx[b, n], b * N + n] = 1.0
+    np.testing.assert_array_equal(mask, want_mask)
+    tree = _tree64(nn)
+    om = orc.make_model(oname, pm, tree, torch.float64)
+    dw = torch.tensor(orc.loss_noise(tf.PRNGKey(11), B, N, H, nx), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, oname, torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw, ow,
+                          step_idx=idx)
+    Ld.backward()
+    assert abs(info["dataLoss"] - float(Ld)) < 3e-5 * abs(float(Ld))
+    gmax = max(float(v.grad.abs().max()) for d in tree.values() for v in d.values())
+    for mod, d in tree.items():
+        for k, v in d.items():
+            want = v.grad.numpy()
+            assert np.max(np.abs(grads[mod][k] - want)) <= 2e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (mod, k)

@@ -76,3 +76,21 @@ def test_batched_split_and_normal(cuda, mode):
             assert np.max(np.abs(z[k] - want) / np.maximum(np.abs(want), 1.0)) < 1e-6
     finally:
         R.set_threefry_partitionable(False)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_choice_mask(cuda, mode):
+    """sde4_rng_choice_mask == indicator of jax.random.choice(key, n, (m,), replace=False) for a batch of keys."""
+    from sde4mbrl_b200 import random as R
+    R.set_threefry_partitionable(bool(mode))
+    try:
+        keys = tf.split(tf.PRNGKey(5), 33, mode)
+        for n, m in ((7, 3), (30, 29), (1, 1), (50, 0), (64, 64)):
+            got = R.choice_mask_many(keys, n, m).cpu().numpy()
+            assert got.shape == (n, 33) and (got.sum(0) == m).all()
+            for k in range(33):
+                want = np.zeros(n, np.float32)
+                want[tf.choice_without_replacement(keys[k], n, m, mode)] = 1.0
+                np.testing.assert_array_equal(got[:, k], want)
+    finally:
+        R.set_threefry_partitionable(False)

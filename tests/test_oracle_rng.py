@@ -65,3 +65,16 @@ def test_rollout_noise_chain():
     kp = tf.split(rng, 4)
     kb = tf.split(kp[2], 2)[0]
     np.testing.assert_array_equal(dw[2], tf.normal(kb, (5, 3)))
+
+
+def test_choice_without_replacement_is_a_stable_sort_of_the_bit_stream():
+    """jax.random.choice(key, n, (m,), replace=False) = permutation(key, n)[:m]: one stable sort of arange(n) by
+    random_bits(split(key)[1], (n,)) for n <= 1625."""
+    for mode in (tf.MODE_ORIGINAL, tf.MODE_PARTITIONABLE):
+        key = tf.PRNGKey(12)
+        full = tf.choice_without_replacement(key, 40, 40, mode)
+        assert sorted(full.tolist()) == list(range(40))
+        bits = tf.random_bits(tf.split(key, 2, mode)[1], (40,), mode)
+        assert (np.diff(bits[full].astype(np.int64)) >= 0).all()
+        np.testing.assert_array_equal(tf.choice_without_replacement(key, 40, 7, mode), full[:7])
+        assert tf.choice_without_replacement(key, 1, 1, mode).tolist() == [0]
