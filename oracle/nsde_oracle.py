@@ -626,16 +626,39 @@ def mu_coeff(model, z, dl):
     return torch.exp(mlp_apply(model.nn, pre, z, lm["activation_fn"])[..., 0]) * mu0
 
 
-def density_loss_terms(model, ymeas, uval, rng, N, dl, mode=tf.MODE_ORIGINAL):
+def density_loss_terms(model, ymeas, uval, rng, N, dl, mode=tf.MODE_ORIGINAL, step_idx=None, num_steps2data=1):
     """``density_loss`` (nsde.py:597-654) over the data points as ``sample_for_loss_computation`` calls it
     (:771-804): for minibatch element b and particle n the key is split(split(split(rng,B)[b],N)[n],3)[2]
     (:1196,:1187,:709), split over the Hd data steps (:781); each step splits once more and uses the SECOND key for
     the ball (:615).  ymeas[B, Hd+1, n_y], uval[B, Hd, n_u] torch tensors.
+    ``step_idx[B, N, m]`` (``density_on_partial`` with ``num_sample2consider``, :794-797): the terms are taken at
+    ``y_values[:-1][idx]``, ``u_values[idx]`` (strategy 'first') with the keys ``split(., Hd)[idx]``.
     Returns grad_norm[B,N] (mean over t), sconvex[B,N] (sum over t), mu[B,N] (mean), density[B,N] (mean)."""
     B, Hd = ymeas.shape[0], ymeas.shape[1] - 1
     ns = int(dl["ball_nsamples"])
     kb = tf.split(rng, B, mode)
     out = [[None] * N for _ in range(B)]
+    if step_idx is not None:
+        y_values = ymeas[:, ::num_steps2data]
+        u_values = uval.reshape(B, -1, num_steps2data, uval.shape[-1])[:, :, 0]
+        for b in range(B):
+            kbn = tf.split(kb[b], N, mode)
+            for n in range(N):
+                idx = torch.as_tensor(step_idx[b, n])
+                z = model.noise_aug_state_ctrl(y_values[b, :-1][idx], u_values[b][idx]).detach().requires_grad_(True)
+                dim = z.shape[-1]
+                den = density_function(model, z)
+                (gz,) = torch.autograd.grad(den.sum(), z, create_graph=True)
+                mu = mu_coeff(model, z, dl)
+                radius = _t(np.broadcast_to(np.asarray(dl["ball_radius"], np.float64), (dim,)).copy(), z)
+                kt = tf.split(tf.split(kbn[n], 3, mode)[2], Hd, mode)
+                ball = torch.stack([_t(tf.normal(tf.split(kt[int(t)], 2, mode)[1], (ns, dim), mode), z) for t in idx]) * radius
+                den_ball = density_function(model, z[:, None, :] + ball)
+                cond = den_ball - den[:, None] - (gz[:, None, :] * ball).sum(-1) - 0.5 * mu[:, None] * (ball ** 2).sum(-1)
+                sconvex = (torch.clamp(cond, max=0.0) ** 2).sum(-1)
+                out[b][n] = ((gz ** 2).sum(-1).mean(), sconvex.sum(), mu.mean(), den.mean())
+        stack = lambda i: torch.stack([torch.stack([out[b][n][i] for n in range(N)]) for b in range(B)])
+        return stack(0), stack(1), stack(2), stack(3)
     for b in range(B):
         z = model.noise_aug_state_ctrl(ymeas[b, :-1], uval[b]).detach().requires_grad_(True)  # [Hd, dim]
         dim = z.shape[-1]

@@ -80,14 +80,23 @@ def density_keys(rng, B, N, Hd):
     return _random.split_many(kt, 2)[..., 1, :].contiguous()
 
 
-def density_terms(model, tree, y, u, rng, N, dl):
+def density_terms(model, tree, y, u, rng, N, dl, partial=None):
     """Per (minibatch element, particle) terms of ``sample_for_loss_computation`` (nsde.py:771-804).
     ``tree``: torch parameter tree (requires_grad leaves), ``y[B, Hd+1, n_y]``, ``u[B, Hd, n_u]`` device tensors.
+    ``partial = (y_values[B, H+1, n_y], u_values[B, H, n_u], step_weight[H, B*N])``: ``density_on_partial`` with
+    ``num_sample2consider`` (nsde.py:794-797) -- the terms are taken at the solver-step data points the sample keeps
+    (0/1 weights), with the keys ``split(rng_density, Hd)[idx]``.
     Returns ``grad_norm[B, N]`` (mean over time), ``sconvex[B, N]`` (sum over time), ``mu[B, N]`` (mean),
     ``density[B, N]`` (mean)."""
     if dl["learn_mucoeff"].get("quad_approx", False):
         raise Sde4Error("density_loss with quad_approx (density_loss_theory) is not built")
     B, Hd = y.shape[0], y.shape[1] - 1
+    Hk = Hd  # rng_density is always split over the DATA horizon (nsde.py:790)
+    wgt = None
+    if partial is not None:
+        y, u, sw = partial
+        Hd = y.shape[1] - 1
+        wgt = sw.t().reshape(B, N, Hd)
     m = model.module_name
     dn = model.params["diffusion_density_nn"]["density_nn"]
     pre = "%s/~construct_diffusion_density_nn/density/~" % m
@@ -104,7 +113,7 @@ def density_terms(model, tree, y, u, rng, N, dl):
     grad_norm = (gz ** 2).sum(-1)  # [B, Hd]
     ns = int(dl["ball_nsamples"])
     radius = torch.as_tensor(np.broadcast_to(np.asarray(dl["ball_radius"], np.float32), (dim,)).copy(), device=y.device)
-    keys = density_keys(rng, B, N, Hd)  # [B, N, Hd, 2]
+    keys = density_keys(rng, B, N, Hk)[:, :, :Hd].contiguous()  # [B, N, Hd, 2]
     ball = _random.normal_many(keys, (ns, dim)) * radius  # [B, N, Hd, ns, dim]
     zb = z[:, None, :, None, :] + ball
     den_ball = density(zb)  # [B, N, Hd, ns]
@@ -120,6 +129,10 @@ def density_terms(model, tree, y, u, rng, N, dl):
         - 0.5 * mu[:, None, :, None] * (ball ** 2).sum(-1)
     sconvex = (torch.clamp(cond, max=0.0) ** 2).sum(-1)  # [B, N, Hd]
     expand = lambda a: a[:, None, :].expand(B, N, Hd)
+    if wgt is not None:
+        cnt = wgt.sum(-1)
+        wmean = lambda a: (expand(a) * wgt).sum(-1) / cnt
+        return wmean(grad_norm), (sconvex * wgt).sum(-1), wmean(mu), wmean(den)
     return expand(grad_norm).mean(-1), sconvex.sum(-1), expand(mu).mean(-1), expand(den).mean(-1)
 
 

@@ -401,7 +401,7 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
     The distance-aware regulariser (``density_loss`` gradient-norm / strong-convexity / mu terms) is evaluated by
     ``density_loss.py`` at the data points with the reference's key chain; ``num_sample2consider`` below the horizon
     becomes a per-sample 0/1 step weight drawn on the device (``sde4_rng_choice_mask``).  Not covered (each raises):
-    ``u_sampling_strategy='random'``, ``learn_mucoeff.quad_approx``, ``density_on_partial`` with subsampling."""
+    ``u_sampling_strategy='random'``, ``learn_mucoeff.quad_approx`` (undefined in the reference itself)."""
     _check_constr(sde_constr)
     vprint = print if verbose else (lambda *a, **k: None)
     params_model = model_params
@@ -443,8 +443,9 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         loss_params["pen_mu_coeff"] = 0.0
     dl = loss_params.get("density_loss", None)
     n_consider = int(params_model.get("num_sample2consider", horizon))
-    if n_consider < horizon and dl is not None and params_model.get("density_on_partial", False):
-        raise Sde4Error("density_on_partial together with num_sample2consider is not built")
+    if dl is not None and dl["learn_mucoeff"].get("quad_approx", False):
+        # the reference dispatches to self.density_loss_theory, which it never defines (nsde.py:778): AttributeError there
+        raise Sde4Error("density_loss.learn_mucoeff.quad_approx: the reference has no density_loss_theory to mirror")
     strategy = params_model.get("u_sampling_strategy", "first")
     if strategy not in ("first", "mean", "median"):
         raise Sde4Error("u_sampling_strategy '%s' has no compiled kernel" % strategy)
@@ -520,7 +521,12 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         if dl is not None:
             # distance-aware regulariser at the data points (density_loss.py): library GEMMs + autograd
             tt = _density.to_torch_tree(_nn_params, y_values.device)
-            gn, sc, mu, _dv = _density.density_terms(model, tt, as_f32(y), as_f32(u), key, num_sample, dl)
+            partial = None
+            if step_weight is not None and params_model.get("density_on_partial", False):  # nsde.py:794-797
+                if strategy != "first":
+                    raise Sde4Error("density_on_partial needs u_sampling_strategy 'first'")
+                partial = (y_values, u_values, step_weight)
+            gn, sc, mu, _dv = _density.density_terms(model, tt, as_f32(y), as_f32(u), key, num_sample, dl, partial)
             dtot, dinfo = _density.weighted_terms(loss_params, dl, gn, sc, mu)
             if want_grad and dtot.requires_grad:
                 dtot.backward()

@@ -63,8 +63,8 @@ def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H):
     assert set(td) == {"TestErrorData", "TestStdData"} and np.isfinite(err)
 
 
-@pytest.mark.parametrize("mu_type,N", [("dnn", 2), ("global", 1), ("constant", 1)])
-def test_density_regulariser_terms_and_grads(cuda, mu_type, N):
+@pytest.mark.parametrize("mu_type,N,partial", [("dnn", 2, 0), ("global", 1, 0), ("constant", 1, 0), ("dnn", 2, 5), ("global", 3, 2)])
+def test_density_regulariser_terms_and_grads(cuda, mu_type, N, partial):
     """Full training loss of cartpole_sde.yaml:95-137 (data term + distance-aware regulariser + weight penalty):
     gradient-norm / strong-convexity / mu terms with the reference's key chain for the ball samples, and the
     gradient w.r.t. every parameter, vs the oracle's float64 autograd."""
@@ -80,6 +80,8 @@ def test_density_regulariser_terms_and_grads(cuda, mu_type, N):
           "density_loss": {"learn_mucoeff": lm, "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4], "ball_nsamples": 6},
           "pen_grad_density": 1.0, "pen_density_scvex": 1.0, "pen_mu_type": "lin_inv", "pen_mu_coeff": 1000.0,
           "pen_scvex_mult": 0.01}
+    if partial:  # num_sample2consider + density_on_partial (nsde.py:753-760, 794-797)
+        lp.update(num_sample2consider=partial, density_on_partial=True)
     nn0, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.CartPoleSDE, verbose=False)
     dl = lp["density_loss"]
     assert dl["learn_mucoeff"]["type"] == mu_type and (lp["pen_mu_coeff"] == 0.0) == (mu_type == "constant")
@@ -100,8 +102,9 @@ def test_density_regulariser_terms_and_grads(cuda, mu_type, N):
     om = orc.make_model("cart_pole_sde", pm, tree, torch.float64)
     y64, u64 = torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64)
     dw = torch.tensor(orc.loss_noise(tf.PRNGKey(3), B, N, H, 4), dtype=torch.float64)
-    Ld, _ = orc.data_loss(om, "cart_pole_sde", y64, u64, dw, ow)
-    gn, sc, mu, _ = orc.density_loss_terms(om, y64, u64, tf.PRNGKey(3), N, dl)
+    idx = orc.loss_step_indices(tf.PRNGKey(3), B, N, H, partial) if partial else None
+    Ld, _ = orc.data_loss(om, "cart_pole_sde", y64, u64, dw, ow, step_idx=idx)
+    gn, sc, mu, _ = orc.density_loss_terms(om, y64, u64, tf.PRNGKey(3), N, dl, step_idx=idx)
     coeffs = {m: {k: (0.0 if ("scaler" in m or "scaler" in k or "density" in m) else 1.0) for k in d} for m, d in tree.items()}
     nominal = {m: {k: torch.zeros_like(v) for k, v in d.items()} for m, d in tree.items()}
     Lw = orc.weight_penalty(tree, nominal, coeffs)
