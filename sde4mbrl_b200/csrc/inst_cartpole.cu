@@ -18,6 +18,6 @@ using CartBbOde = Arch<SDE4_MODEL_CARTPOLE, 4, 1, 0, NoNet, 0, 0, false, CartRes
 SDE4_REGISTER_TRAIN_LS(cartpole_si_d32, CartpoleModel, CartSiD32, 8)
 SDE4_REGISTER_TRAIN_LS(cartpole_bb_d32, CartpoleModel, CartBbD32, 8)
 SDE4_REGISTER(cartpole_bb_d8, CartpoleModel<CartBbD8>)
-SDE4_REGISTER(cartpole_si_ode, CartpoleModel<CartSiOde>)
-SDE4_REGISTER(cartpole_bb_ode, CartpoleModel<CartBbOde>)
+SDE4_REGISTER_TRAIN(cartpole_si_ode, CartpoleModel, CartSiOde)
+SDE4_REGISTER_TRAIN(cartpole_bb_ode, CartpoleModel, CartBbOde)
 }  // namespace sde4

@@ -17,11 +17,11 @@ using HexaPrior = Arch<SDE4_MODEL_ROTOR, 13, 6, 0, NoNet, 0, 0, false, NoNet, 0,
 using IrisD32s = Arch<SDE4_MODEL_ROTOR, 13, 4, SDE4_ROTOR_AERO_DRAG, Net<6, 32, 32, 1, SWISH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
 using IrisOde = Arch<SDE4_MODEL_ROTOR, 13, 4, SDE4_ROTOR_AERO_DRAG, NoNet, 0, 0, false, ResF, 0x7, ResM, 0x3F>;
 using IrisPrior = Arch<SDE4_MODEL_ROTOR, 13, 4, 0, NoNet, 0, 0, false, NoNet, 0, NoNet, 0>;
-SDE4_REGISTER(hexa_ode, RotorModel<HexaOde>)
+SDE4_REGISTER_TRAIN(hexa_ode, RotorModel, HexaOde)
 SDE4_REGISTER(hexa_ode_m3, RotorModel<HexaOdeM3>)
 SDE4_REGISTER(hexa_ode_w24, RotorModel<HexaOde24>)
 SDE4_REGISTER(hexa_prior, RotorModel<HexaPrior>)
 SDE4_REGISTER_TRAIN_LS(iris_d32_swish, RotorModel, IrisD32s, 8)
-SDE4_REGISTER(iris_ode, RotorModel<IrisOde>)
+SDE4_REGISTER_TRAIN(iris_ode, RotorModel, IrisOde)
 SDE4_REGISTER(iris_prior, RotorModel<IrisPrior>)
 }  // namespace sde4

@@ -278,3 +278,46 @@ def test_num_sample2consider_subsampled_loss(cuda, kind, cls, oname, B, N, H, m,
         for k, v in d.items():
             want = v.grad.numpy()
             assert np.max(np.abs(grads[mod][k] - want)) <= 2e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (mod, k)
+
+
+@pytest.mark.parametrize("kind,B,H", [("cartpole", 6, 12), ("cartpole_bb", 5, 20), ("hexa", 4, 8)])
+def test_training_gradients_of_the_neural_ode_variants(cuda, kind, B, H):
+    """Models without a diffusion term (the reference's `*_ode` configurations: no `diffusion_density_nn`, one
+    deterministic particle): data term and parameter gradients vs the oracle's autograd."""
+    from sde4mbrl_b200 import nsde, random as R
+    mk, cls, oname = hp.KINDS[kind]
+    pm = mk(horizon=1, num_particles=1)
+    pm.pop("diffusion_density_nn", None)
+    nx, nu = pm["n_x"], pm["n_u"]
+    pm["noise_prior_params"] = [0.0] * nx
+    ow = [9, 5, 1, 1.0, 10] if oname == "cart_pole_sde" else [1.0] * nx
+    lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": 1, "num_particles_test": 1,
+          "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 0.0}
+    _, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=cls, verbose=False)
+    model = cls(pm)
+    assert not loss_fn.engine.noisy
+    nn = configs.random_params(model, seed=4)
+    rng = np.random.default_rng(0)
+    if kind == "hexa":
+        y = np.stack([np.stack([hp.start_state("hexa", rng) for _ in range(H + 1)]) for _ in range(B)]).astype(np.float32)
+        u = rng.uniform(0.25, 0.45, (B, H, nu)).astype(np.float32)
+    else:
+        y = (rng.normal(0, 0.5, (B, H + 1, nx)) + np.array([0, 0, 3.0, 0])).astype(np.float32)
+        u = rng.uniform(-1, 1, (B, H, nu)).astype(np.float32)
+    total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(3))
+    tree = _tree64(nn)
+    om = orc.make_model(oname, pm, tree, torch.float64)
+    dw = torch.zeros((B, 1, H, nx), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, oname, torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw, ow)
+    Ld.backward()
+    assert abs(info["dataLoss"] - float(Ld)) < 3e-5 * abs(float(Ld))
+    gmax = max(float(v.grad.abs().max()) for d in tree.values() for v in d.values() if v.grad is not None)
+    checked = 0
+    for m, d in tree.items():
+        for k, v in d.items():
+            if v.grad is None:
+                continue
+            want = v.grad.numpy()
+            assert np.max(np.abs(np.asarray(grads[m][k]) - want)) <= 2e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (m, k)
+            checked += 1
+    assert checked >= 6
