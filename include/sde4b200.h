@@ -325,6 +325,15 @@ int sde4_apg_select(const sde4_apg_params* prm, const sde4_apg_state* st, const 
  * y_grad[H][n_opt][P] (apg.py:224 then needs no further launch); both NULL otherwise. */
 int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_cost, float* y, float* y_cost,
                   int32_t* pick, const float* xv_grad_or_null, float* y_grad_or_null, void* stream);
+/* Speculative iteration for latency-bound sizes: with Q = 2(maxls+1) + (has_prox ? maxls : 0),
+ * spec[H][n_opt][Q*P] = [ x_k = prox(cand_k), k = 0..maxls | v_k = xk + momentum (x_k - xk) | (has_prox) cand_k, k < maxls ]
+ * is evaluated by ONE value+gradient sde4_cost_grad launch over Q*P problems (data_mod = P); sde4_apg_select then
+ * takes cand_cost = the cost block of the un-projected candidates (the x block when there is no prox), and
+ * sde4_apg_spec_gather copies cost and gradient of the accepted step's x / v into xv_cost[2P] / xv_grad[H][n_opt][2P]
+ * for sde4_apg_pick -- one sequential rollout per iteration instead of two (apg.py:164-224 unchanged in effect). */
+int sde4_apg_spec_points(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, float* spec, void* stream);
+int sde4_apg_spec_gather(const sde4_apg_params* prm, const int32_t* sel_ls, const float* spec_cost, const float* spec_grad,
+                         float* xv_cost, float* xv_grad, void* stream);
 /* progressive line search: after the costs of candidate k are known, active[p] &= wolfe_cond_violated(k)
  * (apg.py:324-329, 362-379); problems that accepted candidate k are skipped by the next candidate's launch.
  * k == 0 first sets active[p] = not_done[p]. */

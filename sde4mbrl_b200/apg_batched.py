@@ -10,7 +10,10 @@ evaluates all branches; here the same semantics are obtained with per-problem ma
     state update (masked by not_done)
 For latency-bound sizes (2*P*N <= 8192 samples) the last two launches are merged: value+gradient for x AND v, then
 point, cost and gradient of the better one are copied -- ~15 % more arithmetic, one sequential rollout less per
-iteration (a single hexacopter solve: 3.8 -> 2.9 ms).
+iteration (a single hexacopter solve: 3.8 -> 2.9 ms).  Smaller still (Q*P*N <= 4096 samples, Q = 2(maxls+1) [+ maxls with
+a prox]) the iteration is SPECULATIVE: the x_k / v_k of every step size are evaluated with their gradients in the one
+launch that also yields the line search's costs, and the accepted step's results are gathered afterwards -- one
+sequential rollout per iteration.
 
 All arithmetic (cost evaluations and the APG bookkeeping) runs in ``libsde4b200.so``; torch only
 owns the buffers.  Arrays are problem-minor: ``[H, n_opt, P]``.
@@ -24,10 +27,13 @@ from . import _lib as L
 from .apg import APGState
 from .engine import as_f32, as_key, _ptr, _stream
 
+# speculative iterations while (points per problem) * P * N stays at or below this many samples (scripts/apg_spec.py)
+SPECULATIVE_MAX_SAMPLES = 4096
+
 
 class BatchedAPG:
     def __init__(self, engine, nn_params, stage, optimizer_params, time_steps, num_particles, lb=None, ub=None,
-                 terminal=None, lanes=0, merge_xv_grad=None, progressive_ls=None):
+                 terminal=None, lanes=0, merge_xv_grad=None, progressive_ls=None, speculative=None):
         self.eng = engine
         self.pk = engine.packed(nn_params)
         self.stage = stage
@@ -44,12 +50,15 @@ class BatchedAPG:
         self.lb, self.ub = lb, ub
         self.merge_xv_grad = merge_xv_grad  # None: decided from the launch size (see step)
         self.progressive_ls = progressive_ls  # None: decided from the launch size (see _alloc)
+        self.speculative = speculative  # None: decided from the launch size (see _alloc)
+        self._modes_given = merge_xv_grad is not None or progressive_ls is not None  # an explicit two-launch request wins
         self.P = None
         self._graph = None
 
     # ------------------------------------------------------------------
     def _alloc(self, P, dev):
         H, n, K = self.H, self.n_opt, self.op["linesearch"]["maxls"] + 1
+        ls_ = self.op["linesearch"]
         self.P, self.K = P, K
         f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
         i = lambda *s: torch.empty(s, dtype=torch.int32, device=dev)
@@ -64,6 +73,14 @@ class BatchedAPG:
             # worth it when the launches are throughput bound and every warp belongs to one problem
             # (scripts/apg_modes.py: better from 16 k samples per candidate on)
             self.progressive_ls = self.N % 32 == 0 and P * self.N >= 16384 and self.op["linesearch"]["maxls"] > 1
+        # speculative iteration: all points an iteration can end at in ONE value+gradient launch (one sequential
+        # rollout per iteration instead of two); pays while that launch is still latency bound
+        self.Q = 2 * K + (ls_["maxls"] if self.lb is not None else 0)
+        if self.speculative is None:
+            self.speculative = (not self._modes_given) and self.Q * P * self.N <= SPECULATIVE_MAX_SAMPLES
+        if self.speculative:
+            self.merge_xv_grad, self.progressive_ls = True, False
+            self.spec, self.spec_cost, self.spec_grad = f(H, n, self.Q * P), f(self.Q * P), f(H, n, self.Q * P)
         self.ls_active = i(P)
         self.xvmask = torch.ones(2 * P, dtype=torch.int32, device=dev)  # [x needs evaluation | v always]
         self.xv_grad = f(H, n, 2 * P) if self.merge_xv_grad else None
@@ -141,6 +158,8 @@ class BatchedAPG:
     def step(self):
         """One masked ``one_step_apg`` for all problems (apg.py:164-274)."""
         lib, prm, st, P = L.load(), self.prm, self.st, self.P
+        if self.speculative:
+            return self._step_speculative()
         reuse_x = not self.merge_xv_grad  # cost(x) = cost(accepted candidate) unless the prox moved it
         xmask = self.xvmask[:P] if reuse_x else None
         L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(xmask), _stream()))
@@ -175,6 +194,25 @@ class BatchedAPG:
         L.check(lib.sde4_apg_update(C.byref(prm), C.byref(st), _ptr(self.xv), _ptr(self.y), _ptr(self.y_cost),
                                     _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls),
                                     _ptr(self.cand), _stream()))  # cand is dead here: |grad|^2 partials scratch
+
+    def _step_speculative(self):
+        """The same iteration with ONE cost launch: candidates -> every x_k = prox(cand_k), v_k and (with a prox) the raw
+        candidates, value + gradient over Q*P problems -> Armijo selection on the raw costs -> gather the accepted
+        step's x / v cost and gradient -> pick -> update."""
+        lib, prm, st, P, K = L.load(), self.prm, self.st, self.P, self.K
+        L.check(lib.sde4_apg_candidates(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(None), _stream()))
+        L.check(lib.sde4_apg_spec_points(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.spec), _stream()))
+        self._cost(self.spec, self.spec_cost, grad_buf=self.spec_grad, data_mod=P, which="xv")
+        raw_cost = self.spec_cost[2 * K * P:] if self.lb is not None else self.spec_cost
+        L.check(lib.sde4_apg_select(C.byref(prm), C.byref(st), _ptr(self.cand), _ptr(self.svals), _ptr(raw_cost),
+                                    _ptr(self.xv), _ptr(self.sel_step), _ptr(self.sel_ls), _ptr(None), _ptr(None), _stream()))
+        L.check(lib.sde4_apg_spec_gather(C.byref(prm), _ptr(self.sel_ls), _ptr(self.spec_cost), _ptr(self.spec_grad),
+                                         _ptr(self.xv_cost), _ptr(self.xv_grad), _stream()))
+        L.check(lib.sde4_apg_pick(C.byref(prm), _ptr(self.xv), _ptr(self.xv_cost), _ptr(self.y), _ptr(self.y_cost),
+                                  _ptr(self.pick), _ptr(self.xv_grad), _ptr(self.y_grad), _stream()))
+        L.check(lib.sde4_apg_update(C.byref(prm), C.byref(st), _ptr(self.xv), _ptr(self.y), _ptr(self.y_cost),
+                                    _ptr(self.y_grad), _ptr(self.pick), _ptr(self.sel_step), _ptr(self.sel_ls),
+                                    _ptr(self.cand), _stream()))
 
     def _capture(self):
         """Capture one masked iteration (6 bookkeeping + 2-3 cost + 2-3 reduce launches) in a CUDA graph.

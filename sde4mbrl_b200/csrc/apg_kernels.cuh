@@ -156,6 +156,56 @@ __global__ void k_apg_pick(const __grid_constant__ sde4_apg_params prm, const fl
   }
 }
 
+// ---- speculative iteration (latency-bound sizes): every point the iteration can end at is laid out BEFORE the line
+// search is known, so that ONE value+gradient launch replaces "candidate values -> select -> x / v value+gradient":
+//   spec[H][n_opt][Q*P]: blocks of P problems  [ x_0..x_maxls | v_0..v_maxls | (has_prox) raw_0..raw_{maxls-1} ]
+// with x_k = prox(raw_k), v_k = xk + momentum (x_k - xk)   (apg.py:201-215; same expressions as k_apg_select).
+// The Armijo test needs the cost of the UN-projected candidate (apg.py:362-379), hence the raw block.
+__global__ void k_apg_spec_points(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
+                                  const float* __restrict__ cand, float* __restrict__ spec) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= prm.P) return;
+  const int P = prm.P, E = prm.H * prm.n_opt, K = prm.maxls + 1;
+  const int Q = 2 * K + (prm.has_prox ? prm.maxls : 0);
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
+  const float mom = st.momentum[p];
+  for (int e = e0; e < e1; ++e) {
+    const float xp = st.xk[(size_t)e * P + p];
+    const int j = e % prm.n_opt;
+    float* row = spec + (size_t)e * Q * P + p;
+    for (int k = 0; k < K; ++k) {
+      float x = cand[(size_t)e * K * P + (size_t)k * P + p];
+      if (prm.has_prox) {
+        if (k < prm.maxls) row[(size_t)(2 * K + k) * P] = x;
+        x = fminf(fmaxf(x, prm.lb[j]), prm.ub[j]);
+      }
+      row[(size_t)k * P] = x;
+      row[(size_t)(K + k) * P] = xp + mom * (x - xp);
+    }
+  }
+}
+
+// after k_apg_select: cost and gradient of [xcurr | vcurr] are those of the speculated points of the accepted step
+__global__ void k_apg_spec_gather(const __grid_constant__ sde4_apg_params prm, const int32_t* __restrict__ sel_ls,
+                                  const float* __restrict__ spec_cost, const float* __restrict__ spec_grad,
+                                  float* __restrict__ xv_cost, float* __restrict__ xv_grad) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= prm.P) return;
+  const int P = prm.P, E = prm.H * prm.n_opt, K = prm.maxls + 1;
+  const int Q = 2 * K + (prm.has_prox ? prm.maxls : 0);
+  const int e0 = blockIdx.y * APG_CH, e1 = min(e0 + APG_CH, E);
+  const int ks = sel_ls[p] - 1;
+  if (blockIdx.y == 0) {
+    xv_cost[p] = spec_cost[(size_t)ks * P + p];
+    xv_cost[P + p] = spec_cost[(size_t)(K + ks) * P + p];
+  }
+  for (int e = e0; e < e1; ++e) {
+    const float* row = spec_grad + (size_t)e * Q * P + p;
+    xv_grad[(size_t)e * 2 * P + p] = row[(size_t)ks * P];
+    xv_grad[(size_t)e * 2 * P + P + p] = row[(size_t)(K + ks) * P];
+  }
+}
+
 // progressive line search (apg.py:362-379 evaluated one step size at a time over the whole batch)
 __global__ void k_apg_ls_step(const __grid_constant__ sde4_apg_params prm, const __grid_constant__ sde4_apg_state st,
                               const float* __restrict__ svals, const float* __restrict__ cand_cost, int k,

@@ -671,6 +671,19 @@ int sde4_apg_pick(const sde4_apg_params* prm, const float* xv, const float* xv_c
   SDE4_APG_LAUNCH(k_apg_pick, 1, *prm, xv, xv_cost, y, y_cost, pick, xv_grad_or_null, y_grad_or_null);
   return SDE4_OK;
 }
+int sde4_apg_spec_points(const sde4_apg_params* prm, const sde4_apg_state* st, const float* cand, float* spec, void* stream) {
+  if (int rc = apg_check(prm, st)) return rc;
+  if (!st || !cand || !spec) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_spec_points, 1, *prm, *st, cand, spec);
+  return SDE4_OK;
+}
+int sde4_apg_spec_gather(const sde4_apg_params* prm, const int32_t* sel_ls, const float* spec_cost, const float* spec_grad,
+                         float* xv_cost, float* xv_grad, void* stream) {
+  if (int rc = apg_check(prm, nullptr)) return rc;
+  if (!sel_ls || !spec_cost || !spec_grad || !xv_cost || !xv_grad) return fail(SDE4_ERR_INVALID, "null argument");
+  SDE4_APG_LAUNCH(k_apg_spec_gather, 1, *prm, sel_ls, spec_cost, spec_grad, xv_cost, xv_grad);
+  return SDE4_OK;
+}
 int sde4_apg_update(const sde4_apg_params* prm, const sde4_apg_state* st, const float* xv, const float* y,
                     const float* y_cost, const float* y_grad, const int32_t* pick, const float* sel_step,
                     const int32_t* sel_ls, float* scratch, void* stream) {

@@ -14,13 +14,15 @@ from sde4mbrl_b200 import configs, costs, sde_models
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("merge", [True, False])
+@pytest.mark.parametrize("merge", [True, False, "speculative"])
 @pytest.mark.parametrize("N,iters,rtol,box", [(1, 8, 0.0, None), (4, 6, 0.0, None), (1, 12, 0.05, None),
                                               (4, 8, 0.0, (0.325, 0.338))])
 def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge, box):
     """`merge`: x and v evaluated by one value+gradient launch (latency-bound sizes) or, as in the reference, value
     only followed by the gradient at the chosen point (throughput-bound sizes; there the cost of x is taken from the
-    accepted line-search candidate unless the box prox moved it -- `box`: tight control bounds, the prox clips)."""
+    accepted line-search candidate unless the box prox moved it -- `box`: tight control bounds, the prox clips);
+    "speculative": x_k / v_k of every step size with their gradients in the one launch that also gives the line
+    search its costs (smallest sizes)."""
     from sde4mbrl_b200 import apg, nsde, random as R
     from sde4mbrl_b200.apg_batched import BatchedAPG
     P, H = 5, 20
@@ -43,8 +45,12 @@ def test_batched_apg_matches_per_problem_host_apg(cuda, N, iters, rtol, merge, b
     keys = tf.split(tf.PRNGKey(31), P)
     x0 = construct_opt(u=np.full(6, 0.33, np.float32))
     eng = multi_cost.engine
-    solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=lo, ub=hi, merge_xv_grad=merge)
+    if merge == "speculative":
+        solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=lo, ub=hi, speculative=True)
+    else:
+        solver = BatchedAPG(eng, nn, stage, op, multi_cost.time_steps, N, lb=lo, ub=hi, merge_xv_grad=merge)
     solver.init(x0, y0, xref, keys).run(use_graph=False)
+    assert solver.speculative == (merge == "speculative")
     x_eager = solver.x_opt().clone()
     solver.init(x0, y0, xref, keys).run(use_graph=True)  # CUDA-graph replay must give the same iterates
     assert torch.equal(solver.x_opt(), x_eager)
