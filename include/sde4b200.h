@@ -230,7 +230,8 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* args, voi
  * In `args`, y0 / opt / xref / key / cost / grad are HOST pointers (contiguous [P][n_x], [P][H][n_opt],
  * [P or 1][H+1][n_x], [P or 1][2]); params, dt, noise, xtraj and workspace stay device pointers.
  * The inputs are packed into `staging_pinned` (page-locked host memory), moved with ONE async copy into
- * `staging_device`, evaluated, and [cost | grad] comes back with ONE copy; the call returns after the
+ * `staging_device`, evaluated, and [cost | grad] comes back with ONE copy (or, when the pinned buffer is mapped
+ * into the device's address space -- unified addressing -- stored straight into it by the reduce kernel); the call returns after the
  * stream has been synchronised.  Both staging buffers are caller-owned and at least
  * sde4_cost_grad_host_staging_bytes() long. */
 size_t sde4_cost_grad_host_staging_bytes(const sde4_model_desc* model, int32_t P, int32_t H, int32_t n_slack);

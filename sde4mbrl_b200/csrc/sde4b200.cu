@@ -282,11 +282,21 @@ int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* a, v
   d.opt = dp + h.opt;
   d.xref = dp + h.xref;
   d.key = keyed ? reinterpret_cast<const uint32_t*>(dp + h.key) : nullptr;
-  d.cost = dp + h.cost;
-  d.grad = a->grad ? dp + h.grad : nullptr;
+  // [cost | grad] (P*(1 + H*n_opt) floats, written once by K3): when the pinned staging buffer is mapped into the
+  // device's address space (always the case under unified addressing) K3 stores them straight into it -- posted
+  // writes over the host link, visible after the stream synchronise -- and the separate D2H copy disappears
+  float* hp_dev = nullptr;
+  if (cudaHostGetDevicePointer(reinterpret_cast<void**>(&hp_dev), hp, 0) != cudaSuccess) {
+    (void)cudaGetLastError();
+    hp_dev = nullptr;
+  }
+  float* outp = hp_dev ? hp_dev : dp;
+  d.cost = outp + h.cost;
+  d.grad = a->grad ? outp + h.grad : nullptr;
   if (int rc = cost_grad_impl(model, &d, stream, LossOpts())) return rc;
   const size_t out_floats = a->grad ? h.total - h.cost : (size_t)P;
-  err = cudaMemcpyAsync(hp + h.cost, dp + h.cost, out_floats * 4, cudaMemcpyDeviceToHost, s);
+  err = cudaSuccess;
+  if (!hp_dev) err = cudaMemcpyAsync(hp + h.cost, dp + h.cost, out_floats * 4, cudaMemcpyDeviceToHost, s);
   if (err == cudaSuccess) err = cudaStreamSynchronize(s);
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "D2H: %s", cudaGetErrorString(err));
   std::memcpy(a->cost, hp + h.cost, (size_t)P * 4);

@@ -80,7 +80,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream():
+    """Raw handle of torch's current CUDA stream (the launches of this library are ordered with torch's own work)."""
+    if _raw_stream is not None:  # ~0.3 us instead of ~4 us for the Stream object round trip
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
