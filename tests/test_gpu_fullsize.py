@@ -163,3 +163,38 @@ def test_c4_batch_of_4096_solves(cuda):
         s = apg.apg(apg.init_apg(x0.cpu(), cost_p, op), cost_p, op, proximal_fn=prox)
         assert abs(float(s.opt_cost) - float(opt_cost[p])) <= 2e-4 * abs(float(s.opt_cost))
         assert hp.rel_err(xb[p], s.x_opt.numpy()) < 5e-3
+
+
+def test_c2_cartpole_mpc_solve_device_vs_host_apg(cuda):
+    """configs[1]: one cartpole swing-up MPC problem, 1024 particles x horizon 50, 20 APG iterations: the device-side
+    solver (one CUDA-graph replay per iteration) and the reference-facing host `apg.py` loop driving the same fused
+    cost kernel reach the same optimum, and it improves on the initial cost."""
+    from sde4mbrl_b200 import apg, nsde
+    from sde4mbrl_b200.apg_batched import BatchedAPG
+    H, N, iters = 50, 1024, 20
+    pm = configs.cartpole_model(horizon=H, num_particles=N)
+    mpc = configs.cartpole_mpc(horizon=H, dt=0.02, num_particles=N, max_iter=iters)
+    mpc["apg_mpc"].update(atol=0.0, rtol=0.0, max_no_improvement_iter=iters)
+    with contextlib.redirect_stdout(_io.StringIO()):
+        _, mcost, vprox, _, _ = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.CartPoleSDE)
+    nn = configs.random_params(mcost.engine.model, seed=0)
+    for k_, v_ in nn.items():  # dynamics that react to the control (random_params damps the residual nets)
+        if k_.endswith("linear_2") and "init_residual_networks" in k_:
+            v_["w"], v_["b"] = v_["w"] * np.float32(25.0), v_["b"] * np.float32(25.0)
+    cp = mpc["cost_params"]
+    stage = costs.QuadraticCost(cp["xerr"], cp["uerr"], cp["uref"], feat="cartpole", res_mult=cp["res_mult"])
+    y0 = np.array([0.0, 0.0, np.pi, 0.0], np.float32) + np.random.default_rng(3).normal(0, 0.01, 4).astype(np.float32)
+    xref = np.zeros((H + 1, 4), np.float32)
+    key = np.array([0, 7], np.uint32)
+    x0 = np.full((H, 1), 1e-4, np.float32)
+    solver = BatchedAPG(mcost.engine, nn, stage, mpc["apg_mpc"], mcost.time_steps, N, lb=-1.0, ub=1.0)
+    solver.init(torch.as_tensor(x0, device="cuda"), y0[None], xref, key).run(iters)
+    sb = solver.state_of(0)
+    cost_h = lambda o: mcost(nn, y0, o, key, stage, extra_cost_args=xref)[0]
+    sh = apg.apg(apg.init_apg(torch.as_tensor(x0), cost_h, mpc["apg_mpc"]), cost_h, mpc["apg_mpc"],
+                 proximal_fn=lambda x, stepsize=None: vprox(x))
+    assert sb.num_steps == sh.num_steps == iters + 1
+    assert float(sb.opt_cost) < float(sb.init_cost)
+    assert abs(float(sb.opt_cost) - float(sh.opt_cost)) <= 1e-4 * abs(float(sh.opt_cost))
+    assert hp.rel_err(sb.x_opt.cpu().numpy(), sh.x_opt.cpu().numpy()) < 2e-3
+    assert float(sb.x_opt.min()) >= -1.0 and float(sb.x_opt.max()) <= 1.0
