@@ -256,6 +256,11 @@ int sde4_rng_normal_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32
  * (sde4mbrl/nsde.py:755; jax: permutation(key, n)[:m] = one round of a stable sort of arange(n) by
  * random_bits(split(key)[1], 32, (n,)), valid for n <= 1625 where jax needs a single round). */
 int sde4_rng_choice_mask(const uint32_t* keys_dev, uint64_t K, int32_t n, int32_t m, int32_t rng_mode, float* out, void* stream);
+/* out[k*n + j] = jax.random.randint(keys[k], (n,), minval, maxval)[j] (int32; the per-step index the 'random'
+ * u_sampling_strategy draws, sde4mbrl/nsde.py:65 and :1308).  jax: k1, k2 = split(key); offset =
+ * ((bits(k1) % span) * (2^32 % span) + bits(k2) % span) % span in uint32, span = maxval - minval (1 if not positive). */
+int sde4_rng_randint_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32_t minval, int32_t maxval, int32_t rng_mode,
+                          int32_t* out, void* stream);
 
 /* ---- training loss: create_model_loss_fn(...).loss_fn data term and jax.grad of it w.r.t. the model
  *      parameters, sde4mbrl/nsde.py:683-804 (sample_for_loss_computation), :1185-1203 (multi_sampling,

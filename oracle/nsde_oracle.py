@@ -577,16 +577,35 @@ def loss_step_indices(rng, B, N, H, m, mode=tf.MODE_ORIGINAL):
     return out
 
 
-def data_loss(model, kind, ymeas, uval, dw, obs_weights=1.0, num_steps2data=1, step_idx=None):
+def loss_u_indices(rng, B, N, H, num_steps2data, mode=tf.MODE_ORIGINAL):
+    """idx[B, N, H]: the data sub-step whose control sample (b, n) uses at solver step t under
+    ``u_sampling_strategy: random`` (nsde.py:65, :735): ``randint(split(k_bn, 3)[1], (H,), 0, num_steps2data)`` with
+    k_bn as in ``loss_noise`` (the same ``rng_sample2consider`` key that ``num_sample2consider`` reuses at :755)."""
+    kb = tf.split(rng, B, mode)
+    out = np.zeros((B, N, H), np.int64)
+    for b in range(B):
+        kbn = tf.split(kb[b], N, mode)
+        for n in range(N):
+            out[b, n] = tf.randint(tf.split(kbn[n], 3, mode)[1], (H,), 0, num_steps2data, mode)
+    return out
+
+
+def data_loss(model, kind, ymeas, uval, dw, obs_weights=1.0, num_steps2data=1, step_idx=None, u_idx=None):
     """mean over (batch, particles) of sum_t sum_i ((T(y_meas) - T(y_pred)) / w)^2 (nsde.py:766, :1203) with
-    u_sampling_strategy 'first'.  ymeas[B, Hd+1, n_y], uval[B, Hd, n_u], dw[B, N, H, n_x] (H = Hd / num_steps2data);
+    u_sampling_strategy 'first', or 'random' when ``u_idx[B, N, H]`` (``loss_u_indices``) is given.
+    ymeas[B, Hd+1, n_y], uval[B, Hd, n_u], dw[B, N, H, n_x] (H = Hd / num_steps2data);
     ``step_idx[B, N, m]`` (``loss_step_indices``) restricts the sum to the kept time indexes."""
     ts = compute_timesteps(model.params)
     H = len(ts)
     B = ymeas.shape[0]
     y_values = ymeas[:, ::num_steps2data]
-    u_values = uval.reshape(B, H, num_steps2data, -1)[:, :, 0]
-    xs = euler_maruyama(model, ts, y_values[:, None, 0, :].expand(B, dw.shape[1], -1), u_values[:, None], dw)
+    uu = uval.reshape(B, H, num_steps2data, -1)
+    if u_idx is None:
+        u_values = uu[:, None, :, 0]
+    else:  # arr[arange(H), rnd_indx] per sample (nsde.py:66)
+        ii = torch.as_tensor(u_idx)[..., None, None].expand(B, dw.shape[1], H, 1, uu.shape[-1])
+        u_values = torch.gather(uu[:, None].expand(B, dw.shape[1], H, num_steps2data, uu.shape[-1]), 3, ii)[:, :, :, 0]
+    xs = euler_maruyama(model, ts, y_values[:, None, 0, :].expand(B, dw.shape[1], -1), u_values, dw)
     pred = state_transform_for_loss(kind, xs[:, :, 1:])
     meas = state_transform_for_loss(kind, y_values[:, None, 1:])
     w = _t(np.broadcast_to(np.asarray(obs_weights, np.float64), (pred.shape[-1],)), pred)

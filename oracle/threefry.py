@@ -155,6 +155,23 @@ def choice_without_replacement(key, n, m, mode=MODE_ORIGINAL):
     return x[:m]
 
 
+def randint(key, shape, minval, maxval, mode=MODE_ORIGINAL):
+    """``jax.random.randint(key, shape, minval, maxval)`` for int32 (sde4mbrl/nsde.py:65, :1308): ``k1, k2 = split(key)``,
+    ``hi, lo = random_bits(k1), random_bits(k2)``, ``span = maxval - minval`` (1 if not positive),
+    ``mult = ((2^16 % span)^2) % span`` (= 2^32 % span), ``offset = ((hi % span) * mult + lo % span) % span`` in wrapping
+    uint32 arithmetic (jax/_src/random.py ``_randint``, restated from the published algorithm -- parity unpinned)."""
+    ks = split(key, 2, mode)
+    hi = random_bits(ks[0], shape, mode).astype(np.uint64)
+    lo = random_bits(ks[1], shape, mode).astype(np.uint64)
+    span = np.uint64(1 if maxval <= minval else int(maxval) - int(minval))
+    m32 = np.uint64(0xFFFFFFFF)
+    mult = np.uint64(65536) % span
+    mult = ((mult * mult) & m32) % span
+    off = ((((hi % span) * mult) & m32) + (lo % span)) & m32
+    off = off % span
+    return (np.int64(minval) + off.astype(np.int64)).astype(np.int32)
+
+
 def rollout_particle_brownian_keys(rng, num_particles, mode=MODE_ORIGINAL):
     """Per-particle Brownian keys: ``split(rng, N)[p]`` (nsde.py:1026) followed
     by ``rng_brownian, _ = split(k_p)`` (sde_solver.py:276)."""

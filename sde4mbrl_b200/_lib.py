@@ -111,7 +111,7 @@ EXPORTED_SYMBOLS = (
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
     "sde4_apg_scratch_floats", "sde4_cost_grad_host", "sde4_cost_grad_host_staging_bytes",
-    "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_apg_ls_step", "sde4_apg_spec_points", "sde4_apg_spec_gather",
+    "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_rng_randint_many", "sde4_apg_ls_step", "sde4_apg_spec_points", "sde4_apg_spec_gather",
 )
 
 _lib = None
@@ -166,6 +166,8 @@ def load():
     lib.sde4_rng_normal_many.restype = C.c_int
     lib.sde4_rng_choice_mask.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.sde4_rng_choice_mask.restype = C.c_int
+    lib.sde4_rng_randint_many.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.sde4_rng_randint_many.restype = C.c_int
     lib.sde4_fma_peak.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_double),
                                   C.c_void_p]
     lib.sde4_fma_peak.restype = C.c_int

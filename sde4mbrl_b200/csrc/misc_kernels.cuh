@@ -142,6 +142,27 @@ __global__ void k_rng_choice_mask(const uint32_t* __restrict__ keys, unsigned lo
   out[i] = rank < m ? 1.0f : 0.0f;
 }
 
+// jax.random.randint(key, (n,), minval, minval + span) for int32 (sde4mbrl/nsde.py:65, :1308 -- the 'random'
+// u_sampling_strategy): k1, k2 = split(key); hi = random_bits(k1), lo = random_bits(k2);
+// offset = ((hi % span) * (2^32 % span) + lo % span) % span in wrapping uint32 arithmetic, with 2^32 % span formed as
+// ((2^16 % span)^2) % span.  One thread per (key, element).
+__global__ void k_rng_randint_many(const uint32_t* __restrict__ keys, unsigned long long K, unsigned long long n,
+                                   int minval, uint32_t span, int mode, int32_t* __restrict__ out) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * n) return;
+  const unsigned long long k = i / n;
+  const unsigned long long j = i - k * n;
+  uint32_t a0, a1, b0, b1;
+  jax_split(keys[2 * k], keys[2 * k + 1], 0u, 2u, mode, a0, a1);
+  jax_split(keys[2 * k], keys[2 * k + 1], 1u, 2u, mode, b0, b1);
+  const uint32_t hi = jax_bits(a0, a1, j, n, mode);
+  const uint32_t lo = jax_bits(b0, b1, j, n, mode);
+  uint32_t mult = 65536u % span;
+  mult = (mult * mult) % span;
+  const uint32_t off = ((hi % span) * mult + lo % span) % span;
+  out[i] = minval + (int32_t)off;
+}
+
 // ----------------------------------------------------------------------------
 // FP32 FMA peak micro-benchmark (roofline denominator)
 // ----------------------------------------------------------------------------

@@ -617,6 +617,19 @@ int sde4_rng_choice_mask(const uint32_t* keys_dev, uint64_t K, int32_t n, int32_
   return SDE4_OK;
 }
 
+int sde4_rng_randint_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int32_t minval, int32_t maxval, int32_t rng_mode,
+                          int32_t* out, void* stream) {
+  if (!keys_dev || !out) return fail(SDE4_ERR_INVALID, "bad argument");
+  if (K == 0 || n == 0) return SDE4_OK;
+  // jax: span = 1 when maxval <= minval, so minval is always returned
+  const uint32_t span = maxval <= minval ? 1u : (uint32_t)((int64_t)maxval - (int64_t)minval);
+  const uint64_t tot = K * n;
+  k_rng_randint_many<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(keys_dev, K, n, minval, span, rng_mode, out);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rng launch: %s", cudaGetErrorString(err));
+  return SDE4_OK;
+}
+
 static int apg_check(const sde4_apg_params* prm, const sde4_apg_state* st) {
   if (!prm) return fail(SDE4_ERR_INVALID, "null apg params");
   if (prm->P <= 0 || prm->H <= 0 || prm->n_opt <= 0 || prm->n_opt > SDE4_MAX_NOPT || prm->maxls < 0)

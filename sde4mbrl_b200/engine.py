@@ -363,10 +363,13 @@ class Engine:
 
     # ---- K2 (training variant) + K3 + K5 -----------------------------------
     def loss_grad(self, nn_params, ymeas, u, dt, data_cost, key, N=1, noise=None, noise_mode=None, block_threads=0, lanes=0,
-                  step_weight=None):
+                  step_weight=None, particle_offset=0, particle_total=0):
         """Data term of the training loss and its gradient w.r.t. the PACKED parameter block.
         ymeas[B, H+1, n_x] (rows = solver steps), u[B, H, n_u], key[B, 2] = split(rng, B).
-        Returns (loss[B], grad_packed[param_total]); d(mean_b loss)/d params = grad_packed."""
+        Returns (loss[B], grad_packed[param_total]); d(mean_b loss)/d params = grad_packed.
+        ``particle_offset`` / ``particle_total``: this launch evaluates particles [offset, offset + N) of
+        ``particle_total`` per element (their keys, the 1 / particle_total of both means); the partial results of the
+        launches that cover all particles add up."""
         self._em_only()
         pk = self.packed(nn_params)
         ymeas = as_f32(ymeas).contiguous()
@@ -406,6 +409,7 @@ class Engine:
         a.cost = _ptr(loss)
         a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
         a.block_threads = block_threads
+        a.particle_offset, a.particle_total = particle_offset, particle_total
         a.lanes = lanes  # 0: lane-split training kernel while the minibatch is latency bound; 1: one thread per sample
         if step_weight is not None:  # float32[H, B*N]: weight of the data term of sample g at time t+1 (num_sample2consider)
             assert step_weight.dtype == torch.float32 and step_weight.is_cuda and tuple(step_weight.shape) == (H, B * N)

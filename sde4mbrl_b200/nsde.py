@@ -400,8 +400,11 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
 
     The distance-aware regulariser (``density_loss`` gradient-norm / strong-convexity / mu terms) is evaluated by
     ``density_loss.py`` at the data points with the reference's key chain; ``num_sample2consider`` below the horizon
-    becomes a per-sample 0/1 step weight drawn on the device (``sde4_rng_choice_mask``).  Not covered (each raises):
-    ``u_sampling_strategy='random'``, ``learn_mucoeff.quad_approx`` (undefined in the reference itself)."""
+    becomes a per-sample 0/1 step weight drawn on the device (``sde4_rng_choice_mask``);
+    ``u_sampling_strategy='random'`` draws each sample's per-step data index on the device (``sde4_rng_randint_many``,
+    nsde.py:65) and, with more than one particle, evaluates the particles of a minibatch element in one launch per
+    particle index (each particle has its own controls).  Not covered (raises): ``learn_mucoeff.quad_approx``
+    (undefined in the reference itself)."""
     _check_constr(sde_constr)
     vprint = print if verbose else (lambda *a, **k: None)
     params_model = model_params
@@ -447,8 +450,8 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         # the reference dispatches to self.density_loss_theory, which it never defines (nsde.py:778): AttributeError there
         raise Sde4Error("density_loss.learn_mucoeff.quad_approx: the reference has no density_loss_theory to mirror")
     strategy = params_model.get("u_sampling_strategy", "first")
-    if strategy not in ("first", "mean", "median"):
-        raise Sde4Error("u_sampling_strategy '%s' has no compiled kernel" % strategy)
+    if strategy not in ("first", "mean", "median", "random"):  # nsde.py:69
+        raise ValueError("Unknown u_sampling_strategy: {}. Choose from first, mean, median, random".format(strategy))
 
     model = sde_constr(params_model, **extra_args_sde_constr)
     nn_params = model.init_params(loss_params.get("seed", 0))
@@ -493,9 +496,17 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
             u_values = uu[:, :, 0]
         elif strategy == "mean":
             u_values = uu.mean(dim=2)
-        else:
+        elif strategy == "median":
             u_values = uu.median(dim=2).values
+        else:  # 'random': the caller gathers with its own indexes (per sample in loss_fn, per call in test_fn)
+            u_values = uu
         return y_values.contiguous(), u_values.contiguous()
+
+    def _pick(uu, idx):
+        """uu[B, H, num_steps2data, n_u], idx[..., H] (int32, broadcast against B) -> uu[b, t, idx[.., t]] (nsde.py:66)."""
+        ii = idx.long()[..., None, None].expand(*idx.shape, 1, uu.shape[-1])
+        src = uu if idx.dim() == 2 else uu[:, None].expand(uu.shape[0], idx.shape[1], *uu.shape[1:])
+        return torch.gather(src, idx.dim(), ii).squeeze(idx.dim()).contiguous()
 
     def value_and_grad(_nn_params, y, u, rng, extra_args=None, want_grad=True):
         if extra_args is not None:
@@ -507,12 +518,26 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         keys = _random.split(key, B)  # nsde.py:1196
         engine.rng_mode = _random.rng_mode()
         step_weight = None
-        if n_consider < horizon:  # nsde.py:753-760: every (b, n) keeps its own random subset of the time indexes
+        k_s2c = None
+        if n_consider < horizon or strategy == "random":
             k_bn = _random.split_many(keys, num_sample)  # [B, N, 2]  (nsde.py:1187)
             k_s2c = _random.split_many(k_bn, 3)[:, :, 1].reshape(-1, 2)  # rng_sample2consider (nsde.py:709)
+        if n_consider < horizon:  # nsde.py:753-760: every (b, n) keeps its own random subset of the time indexes
             step_weight = _random.choice_mask_many(k_s2c, horizon, n_consider)
-        loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample,
-                                           step_weight=step_weight)
+        if strategy == "random":  # nsde.py:735: every (b, n) draws its own data sub-step per solver step
+            ridx = _random.randint_many(k_s2c, horizon, 0, num_steps2data).reshape(B, num_sample, horizon)
+            u_bn = _pick(u_values, ridx)  # [B, N, H, n_u]
+            loss_b, gpacked = None, None
+            for n in range(num_sample):  # one launch per particle index: particle n of every element, its own controls
+                sw = None if step_weight is None else step_weight[:, n::num_sample].contiguous()
+                lb, gp = engine.loss_grad(_nn_params, y_values, u_bn[:, n].contiguous(), time_steps, data_cost.desc, keys, N=1,
+                                          step_weight=sw, particle_offset=n, particle_total=num_sample)
+                loss_b = lb.clone() if loss_b is None else loss_b + lb
+                gpacked = gp.clone() if gpacked is None else gpacked + gp
+            u_values = u_bn[:, 0]
+        else:
+            loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample,
+                                               step_weight=step_weight)
         loss_data = float(loss_b.mean())
         total = 0.0
         if loss_params.get("pen_data", 0) > 0:
@@ -589,6 +614,9 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         key = as_key(rng)
         y_values, u_values = _prepare(y, u)
         B = y_values.shape[0]
+        if strategy == "random":  # nsde.py:1306-1310: one index per solver step, shared by the minibatch
+            key, rng_u = _random.split(key, 2)
+            u_values = _pick(u_values, _random.randint(rng_u, (horizon,), 0, num_steps2data).reshape(1, horizon).expand(B, horizon))
         keys = _random.split(key, B)
         _, yevol, _ = multi_sampling_sde(_nn_params, y_values[:, 0], u_values, keys)  # [B, N, H+1, n_y]
 

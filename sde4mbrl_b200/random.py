@@ -95,3 +95,21 @@ def choice_mask_many(keys, n, m):
     out = torch.empty((int(n), flat.shape[0]), dtype=torch.float32, device=flat.device)
     L.check(L.load().sde4_rng_choice_mask(_ptr(flat), flat.shape[0], int(n), int(m), rng_mode(), _ptr(out), _stream()))
     return out
+
+
+def randint_many(keys, n, minval, maxval):
+    """``jax.vmap(lambda k: jax.random.randint(k, (n,), minval, maxval))(keys)``: keys[..., 2] -> int32 CUDA tensor
+    [..., n] (the per-step data index of ``u_sampling_strategy: random``, sde4mbrl/nsde.py:65, :1308)."""
+    keys = as_key(keys)
+    lead = tuple(keys.shape[:-1])
+    flat = keys.reshape(-1, 2).contiguous()
+    out = torch.empty((flat.shape[0], int(n)), dtype=torch.int32, device=flat.device)
+    L.check(L.load().sde4_rng_randint_many(_ptr(flat), flat.shape[0], int(n), int(minval), int(maxval), rng_mode(), _ptr(out),
+                                           _stream()))
+    return out.reshape(lead + (int(n),))
+
+
+def randint(key, shape, minval, maxval):
+    """``jax.random.randint(key, shape, minval, maxval)`` int32."""
+    n = int(np.prod(shape)) if len(shape) else 1
+    return randint_many(as_key(key).reshape(1, 2), n, minval, maxval).reshape(shape)

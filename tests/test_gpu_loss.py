@@ -321,3 +321,61 @@ def test_training_gradients_of_the_neural_ode_variants(cuda, kind, B, H):
             assert np.max(np.abs(np.asarray(grads[m][k]) - want)) <= 2e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (m, k)
             checked += 1
     assert checked >= 6
+
+
+@pytest.mark.parametrize("kind,cls,oname,B,N,H,nsd,m", [("cartpole", sde_models.CartPoleSDE, "cart_pole_sde", 6, 1, 10, 3, None),
+                                                        ("cartpole", sde_models.CartPoleSDE, "cart_pole_sde", 5, 3, 8, 4, 5),
+                                                        ("msd", sde_models.MassSpringDamper, "mass_spring_damper", 4, 2, 9, 2, None)])
+def test_u_sampling_strategy_random(cuda, kind, cls, oname, B, N, H, nsd, m):
+    """``u_sampling_strategy: random`` with a dataset finer than the solver step (nsde.py:43-70, :735): every
+    (minibatch element, particle) draws, per solver step, which of the ``num_steps2data`` recorded controls it applies
+    (``randint`` on ``rng_sample2consider``, the device draw checked bit for bit); with ``num_sample2consider`` the same
+    key also subsamples the time indexes."""
+    from sde4mbrl_b200 import nsde, random as R
+    pm = hp.KINDS[kind][0](horizon=1, num_particles=1)
+    ow = [9, 5, 1, 1.0, 10] if oname == "cart_pole_sde" else [0.5, 2.0]
+    lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"] / nsd, "num_particles": N, "num_particles_test": 4,
+          "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 0.0, "u_sampling_strategy": "random"}
+    if m is not None:
+        lp["num_sample2consider"] = m
+    _, loss_fn, _, test_fn = nsde.create_model_loss_fn(pm, lp, sde_constr=cls, verbose=False)
+    assert pm["num_steps2data"] == nsd and pm["u_sampling_strategy"] == "random"
+    nn = configs.random_params(cls(pm), seed=4)
+    rng = np.random.default_rng(0)
+    nx, nu = pm["n_x"], pm["n_u"]
+    Hd = H * nsd
+    y = (rng.normal(0, 0.5, (B, Hd + 1, nx)) + (np.array([0, 0, 3.0, 0]) if nx == 4 else 0)).astype(np.float32)
+    u = rng.uniform(-1, 1, (B, Hd, nu)).astype(np.float32)
+    total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(5))
+    uidx = orc.loss_u_indices(tf.PRNGKey(5), B, N, H, nsd)
+    assert uidx.min() >= 0 and uidx.max() == nsd - 1
+    kbn = R.split_many(R.split(R.PRNGKey(5), B), N)
+    got_idx = R.randint_many(R.split_many(kbn, 3)[:, :, 1], H, 0, nsd).cpu().numpy()
+    np.testing.assert_array_equal(got_idx, uidx)
+    sidx = orc.loss_step_indices(tf.PRNGKey(5), B, N, H, m) if m is not None else None
+    tree = _tree64(nn)
+    om = orc.make_model(oname, pm, tree, torch.float64)
+    dw = torch.tensor(orc.loss_noise(tf.PRNGKey(5), B, N, H, nx), dtype=torch.float64)
+    Ld, _ = orc.data_loss(om, oname, torch.tensor(y, dtype=torch.float64), torch.tensor(u, dtype=torch.float64), dw, ow,
+                          num_steps2data=nsd, step_idx=sidx, u_idx=uidx)
+    Ld.backward()
+    assert abs(info["dataLoss"] - float(Ld)) < 3e-5 * abs(float(Ld))
+    gmax = max(float(v.grad.abs().max()) for d in tree.values() for v in d.values())
+    for mod, d in tree.items():
+        for k, v in d.items():
+            want = v.grad.numpy()
+            assert np.max(np.abs(grads[mod][k] - want)) <= 2e-3 * np.max(np.abs(want)) + 1e-5 * gmax, (mod, k)
+    # test_fn (nsde.py:1306-1310): one index per solver step shared by the minibatch, drawn from split(rng)[1]
+    err, tinfo = test_fn(nn, y, u, R.PRNGKey(6))
+    ks = tf.split(tf.PRNGKey(6), 2)
+    tix = tf.randint(ks[1], (H,), 0, nsd)
+    u_t = u.reshape(B, H, nsd, nu)[:, np.arange(H), tix]
+    kb = tf.split(ks[0], B)
+    om32 = orc.make_model(oname, pm, {mm: {k: torch.tensor(np.asarray(v)) for k, v in d.items()} for mm, d in nn.items()})
+    yv = torch.tensor(y[:, ::nsd])
+    ys = torch.stack([orc.sample_rollouts(om32, yv[b, 0], torch.tensor(u_t[b]), kb[b], 4)[0] for b in range(B)])  # [B, 4, H+1, nx]
+    tfm = lambda z: orc.state_transform_for_loss(oname, z)
+    w = torch.tensor(np.asarray(ow, np.float32))
+    want_err = float((((tfm(yv) - tfm(ys.mean(dim=1))) / w) ** 2).sum(dim=(-1, -2)).mean())
+    assert abs(err - want_err) < 1e-4 * abs(want_err) + 1e-6
+    assert set(tinfo) == {"TestErrorData", "TestStdData"}

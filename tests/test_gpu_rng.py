@@ -94,3 +94,21 @@ def test_choice_mask(cuda, mode):
                 np.testing.assert_array_equal(got[:, k], want)
     finally:
         R.set_threefry_partitionable(False)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_randint_many(cuda, mode):
+    """sde4_rng_randint_many == jax.random.randint per key, bit for bit (odd / even counts, spans that do and do not
+    divide 2^32, a span beyond 2^16 where the uint32 multiplier wraps, the degenerate maxval <= minval)."""
+    from sde4mbrl_b200 import random as R
+    R.set_threefry_partitionable(bool(mode))
+    try:
+        keys = tf.split(tf.PRNGKey(9), 17, mode)
+        for n, lo, hi in ((1, 0, 2), (7, 0, 3), (30, -4, 9), (50, 0, 4), (13, 5, 100008), (6, 2, 2), (9, 0, 1 << 30)):
+            got = R.randint_many(keys, n, lo, hi).cpu().numpy()
+            assert got.shape == (17, n) and got.dtype == np.int32
+            for k in range(17):
+                np.testing.assert_array_equal(got[k], tf.randint(keys[k], (n,), lo, hi, mode))
+        np.testing.assert_array_equal(R.randint(keys[3], (4, 5), 0, 7).cpu().numpy(), tf.randint(keys[3], (4, 5), 0, 7, mode))
+    finally:
+        R.set_threefry_partitionable(False)

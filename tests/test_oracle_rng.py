@@ -78,3 +78,27 @@ def test_choice_without_replacement_is_a_stable_sort_of_the_bit_stream():
         assert (np.diff(bits[full].astype(np.int64)) >= 0).all()
         np.testing.assert_array_equal(tf.choice_without_replacement(key, 40, 7, mode), full[:7])
         assert tf.choice_without_replacement(key, 1, 1, mode).tolist() == [0]
+
+
+def test_randint_restatement_properties():
+    """``jax.random.randint`` restatement (oracle/threefry.py, used by ``u_sampling_strategy: random``): for a span
+    that divides 2^32 the multiplier 2^32 % span is 0 and the draw is the low word's remainder; span <= 0 returns
+    minval; values stay in range and both stream layouts differ."""
+    from oracle import threefry as tf
+    import numpy as np
+    key = tf.PRNGKey(42)
+    for mode in (tf.MODE_ORIGINAL, tf.MODE_PARTITIONABLE):
+        lo = tf.random_bits(tf.split(key, 2, mode)[1], (37,), mode)
+        for span in (1, 2, 8, 1 << 16):
+            got = tf.randint(key, (37,), 3, 3 + span, mode)
+            np.testing.assert_array_equal(got, 3 + (lo % np.uint32(span)).astype(np.int32))
+        np.testing.assert_array_equal(tf.randint(key, (5,), 7, 7, mode), np.full(5, 7, np.int32))
+        for span in (3, 5, 7, 1000, 100003):
+            hi = tf.random_bits(tf.split(key, 2, mode)[0], (37,), mode).astype(object)
+            want = np.array([(int(h) * (1 << 32) + int(l)) % span for h, l in zip(hi, lo.astype(object))])
+            got = tf.randint(key, (37,), -2, -2 + span, mode)
+            assert got.min() >= -2 and got.max() < -2 + span
+            # exact whenever (hi % span) * (2^32 % span) does not wrap uint32 -- true for these spans (< 2^16)
+            if span < (1 << 16):
+                np.testing.assert_array_equal(got, -2 + want)
+    assert not np.array_equal(tf.randint(key, (64,), 0, 5, tf.MODE_ORIGINAL), tf.randint(key, (64,), 0, 5, tf.MODE_PARTITIONABLE))
