@@ -17,6 +17,9 @@ using HexaPrior = Arch<SDE4_MODEL_ROTOR, 13, 6, 0, NoNet, 0, 0, false, NoNet, 0,
 using IrisD32s = Arch<SDE4_MODEL_ROTOR, 13, 4, SDE4_ROTOR_AERO_DRAG, Net<6, 32, 32, 1, SWISH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
 using IrisOde = Arch<SDE4_MODEL_ROTOR, 13, 4, SDE4_ROTOR_AERO_DRAG, NoNet, 0, 0, false, ResF, 0x7, ResM, 0x3F>;
 using IrisPrior = Arch<SDE4_MODEL_ROTOR, 13, 4, 0, NoNet, 0, 0, false, NoNet, 0, NoNet, 0>;
+// control_dependent_noise (nsde.py:362): the hexacopter's density net reads [v, omega]/scale followed by the 6 rotor commands
+using HexaD32sCdn = Arch<SDE4_MODEL_ROTOR, 13, 6, SDE4_ROTOR_AERO_DRAG, Net<12, 32, 32, 1, SWISH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
+SDE4_REGISTER(hexa_d32_swish_cdn, RotorModel<HexaD32sCdn>)
 SDE4_REGISTER_TRAIN(hexa_ode, RotorModel, HexaOde)
 SDE4_REGISTER(hexa_ode_m3, RotorModel<HexaOdeM3>)
 SDE4_REGISTER(hexa_ode_w24, RotorModel<HexaOde24>)

@@ -213,7 +213,7 @@ SDE4_DEV void em_step(const float* W, Tctx<M>& tc, const sde4_model_desc& d, flo
   M::drift(W, tc.ev, d, x, u, f);
   if (noisy) {
     float sig[M::NX];
-    Diffusion<M>::fwd(W, tc.ev, d, x, sig);
+    Diffusion<M>::fwd(W, tc.ev, d, x, u, sig);
 #pragma unroll
     for (int i = 0; i < M::NX; ++i) x[i] = fmaf(sig[i], dw[i], fmaf(f[i], dt, x[i]));
   } else {
@@ -250,7 +250,7 @@ SDE4_DEV void strat_step(int solver, const float* W, Tctx<M>& tc, const sde4_mod
   M::drift(W, tc.ev, d, x, u, f0);
 #pragma unroll
   for (int i = 0; i < NX; ++i) g0[i] = 0.0f;
-  if (noisy) Diffusion<M>::fwd(W, tc.ev, d, x, g0);
+  if (noisy) Diffusion<M>::fwd(W, tc.ev, d, x, u, g0);
   const float sq = sqrtf(dt);
   if (solver == SDE4_SOLVER_STRAT_HEUN) {
 #pragma unroll
@@ -259,7 +259,7 @@ SDE4_DEV void strat_step(int solver, const float* W, Tctx<M>& tc, const sde4_mod
     M::drift(W, tc.ev, d, xb, u, f1);
 #pragma unroll
     for (int i = 0; i < NX; ++i) g1[i] = 0.0f;
-    if (noisy) Diffusion<M>::fwd(W, tc.ev, d, xb, g1);
+    if (noisy) Diffusion<M>::fwd(W, tc.ev, d, xb, u, g1);
 #pragma unroll
     for (int i = 0; i < NX; ++i)
       x[i] = fmaf(0.5f * (g0[i] + g1[i]), noisy ? sq * xi[i] : 0.0f, fmaf(0.5f * (f0[i] + f1[i]), dt, x[i]));
@@ -271,7 +271,7 @@ SDE4_DEV void strat_step(int solver, const float* W, Tctx<M>& tc, const sde4_mod
       xb[i] = fmaf(g0[i], sq, xt[i]);
       g1[i] = 0.0f;
     }
-    if (noisy) Diffusion<M>::fwd(W, tc.ev, d, xb, g1);
+    if (noisy) Diffusion<M>::fwd(W, tc.ev, d, xb, u, g1);
     const float c = 0.5f / sq;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
@@ -555,7 +555,12 @@ __global__ void __launch_bounds__((M::Ev::L == 1 && GRAD && !M::Ev::PGRAD && M::
   // step t-1 is evaluated inside the block that applies step t
   constexpr bool PIPE = TFP && PREFETCH && !M::Ev::PGRAD && M::A::HAS_DENSITY;
   typename Diffusion<M>::Tape dtape, dtape_next;
-  if constexpr (PIPE) Diffusion<M>::prep(W, tc.ev, d, xpre, dtape);
+  [[maybe_unused]] float upre[NU];  // controls of the pipelined step (read by the density net under control_dependent_noise only)
+  if constexpr (PIPE) {
+#pragma unroll
+    for (int j = 0; j < NU; ++j) upre[j] = Diffusion<M>::CDN ? __ldg(op + (size_t)(H - 1) * a.o_st + (size_t)j * a.o_sj) : 0.0f;
+    Diffusion<M>::prep(W, tc.ev, d, xpre, upre, dtape);
+  }
   for (int t = H - 1; t >= 0; --t) {
     const float dt = __ldg(a.dt + t);
     if constexpr (M::Ev::PGRAD) tc.ev.dcol = (size_t)t * G + g;
@@ -606,13 +611,18 @@ __global__ void __launch_bounds__((M::Ev::L == 1 && GRAD && !M::Ev::PGRAD && M::
       M::drift_vjp(W, tc.ev, d, x, u, vf, gx, gu);
     }
     if constexpr (PIPE) {
-      Diffusion<M>::apply(W, d, x, lam, [&](int i) { return nzv[i]; }, dtape, gx);
-      Diffusion<M>::prep(W, tc.ev, d, xpre, dtape_next);  // xpre = x_{t-1}, requested at the top of this iteration
+      Diffusion<M>::apply(W, d, x, lam, [&](int i) { return nzv[i]; }, dtape, gx, gu);
+      if constexpr (Diffusion<M>::CDN) {
+        const int tp = t > 0 ? t - 1 : 0;
+#pragma unroll
+        for (int j = 0; j < NU; ++j) upre[j] = __ldg(op + (size_t)tp * a.o_st + (size_t)j * a.o_sj);
+      }
+      Diffusion<M>::prep(W, tc.ev, d, xpre, upre, dtape_next);  // xpre = x_{t-1}, requested at the top of this iteration
     } else if (noisy) {
-      if constexpr (PREFETCH) Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzv[i]; }, gx);
+      if constexpr (PREFETCH) Diffusion<M>::vjp(W, tc.ev, d, x, u, lam, [&](int i) { return nzv[i]; }, gx, gu);
       else {
         const float* nzt = nz + (size_t)t * NX * G + g;
-        Diffusion<M>::vjp(W, tc.ev, d, x, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx);
+        Diffusion<M>::vjp(W, tc.ev, d, x, u, lam, [&](int i) { return nzt[(size_t)i * G]; }, gx, gu);
       }
     }
     // stage cost at t: trapezoid weight w_t

@@ -118,13 +118,23 @@ struct Diffusion {
   using DNet = typename A::DNet;
   using Ev = typename M::Ev;
   using Ctx = typename Ev::Ctx;
-  static constexpr int NX = A::NX, NO = A::NO;
+  static constexpr int NX = A::NX, NO = A::NO, NU = A::NU;
+  // control_dependent_noise (nsde.py:362): the density network reads concat(reduced_state[indx_noise_in], u), i.e. its
+  // input is wider than the noise-input mask by the number of controls
+  static constexpr int NZ = DNet::IN > 0 ? popc(A::NIN_MASK) : 0;
+  static constexpr bool CDN = DNet::IN > NZ;
+  static_assert(DNet::IN == NZ || DNet::IN == NZ + NU, "density input = noise inputs (+ all controls)");
 
-  SDE4_DEV static void gather_in(const float (&x)[NX], const sde4_model_desc& d, float (&z)[DNet::IN > 0 ? DNet::IN : 1]) {
+  SDE4_DEV static void gather_in(const float (&x)[NX], const float (&u)[NU], const sde4_model_desc& d,
+                                 float (&z)[DNet::IN > 0 ? DNet::IN : 1]) {
     float red[M::NR];
     M::reduced_state(x, d, red);
 #pragma unroll
-    for (int k = 0; k < DNet::IN; ++k) z[k] = red[nth_bit(A::NIN_MASK, k)];
+    for (int k = 0; k < NZ; ++k) z[k] = red[nth_bit(A::NIN_MASK, k)];
+    if constexpr (CDN) {
+#pragma unroll
+      for (int j = 0; j < NU; ++j) z[NZ + j] = u[j];
+    }
   }
 
   SDE4_DEV static float eta_of(const float* W, const sde4_model_desc& d, float dens, int k) {
@@ -138,12 +148,12 @@ struct Diffusion {
 
   // sig[i] = eta_full[i] * prior[i]
   SDE4_DEV static void fwd(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
-                           float (&sig)[NX]) {
+                           const float (&u)[NU], float (&sig)[NX]) {
 #pragma unroll
     for (int i = 0; i < NX; ++i) sig[i] = d.noise_prior[i];  // non-noise outputs: eta = 1 (nsde.py:363)
     if constexpr (A::HAS_DENSITY) {
       float z[DNet::IN > 0 ? DNet::IN : 1];
-      gather_in(x, d, z);
+      gather_in(x, u, d, z);
       float dens[1];
       Ev::template fwd<DNet, false>(A::template ref<0, Ev::L>(W), sc, z, dens);
 #pragma unroll
@@ -151,17 +161,19 @@ struct Diffusion {
     }
   }
 
-  // Reverse mode of sig wrt x:  gx += (d sig / d x)^T (dw o lam), with the noise read on the fly.
+  // Reverse mode of sig wrt x (and u, control_dependent_noise):  gx += (d sig / d x)^T (dw o lam), gu likewise, with
+  // the noise read on the fly.
   // The density gradient J = d dens / d x does not depend on the cotangent, so it is formed
   // first (fused value+gradient pass) and scaled afterwards.
   template <class NoiseAt>
   SDE4_DEV static void vjp(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
-                           const float (&lam)[NX], NoiseAt noise_at, float (&gx)[NX]) {
+                           const float (&u)[NU], const float (&lam)[NX], NoiseAt noise_at, float (&gx)[NX],
+                           float (&gu)[NU]) {
     if constexpr (!A::HAS_DENSITY) {
       return;
     } else {
       float z[DNet::IN], J[DNet::IN], dens;
-      gather_in(x, d, z);
+      gather_in(x, u, d, z);
       // cotangent of the density output: gd = sum_k (dw_i lam_i prior_i) eta'(.) (aggr + coeff_k)
       auto gd_of = [&](float dv) {
         float gd = 0.0f;
@@ -187,8 +199,12 @@ struct Diffusion {
 #pragma unroll
       for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = J[k];
+      for (int k = 0; k < NZ; ++k) gred[nth_bit(A::NIN_MASK, k)] = J[k];
       M::reduced_state_vjp(x, d, gred, gx);
+      if constexpr (CDN) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) gu[j] += J[NZ + j];
+      }
     }
   }
 
@@ -199,16 +215,17 @@ struct Diffusion {
   struct Tape {
     float dens, J[DNet::IN > 0 ? DNet::IN : 1];
   };
-  SDE4_DEV static void prep(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX], Tape& tp) {
+  SDE4_DEV static void prep(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
+                            const float (&u)[NU], Tape& tp) {
     if constexpr (A::HAS_DENSITY) {
       float z[DNet::IN];
-      gather_in(x, d, z);
+      gather_in(x, u, d, z);
       Ev::template scalar_value_grad<DNet>(A::template ref<0, Ev::L>(W), sc, z, tp.dens, tp.J, [](float) { return 1.0f; });
     }
   }
   template <class NoiseAt>
   SDE4_DEV static void apply(const float* W, const sde4_model_desc& d, const float (&x)[NX], const float (&lam)[NX],
-                             NoiseAt noise_at, const Tape& tp, float (&gx)[NX]) {
+                             NoiseAt noise_at, const Tape& tp, float (&gx)[NX], float (&gu)[NU]) {
     if constexpr (A::HAS_DENSITY) {
       float gd = 0.0f;
 #pragma unroll
@@ -224,8 +241,12 @@ struct Diffusion {
 #pragma unroll
       for (int r = 0; r < M::NR; ++r) gred[r] = 0.0f;
 #pragma unroll
-      for (int k = 0; k < DNet::IN; ++k) gred[nth_bit(A::NIN_MASK, k)] = tp.J[k] * gd;
+      for (int k = 0; k < NZ; ++k) gred[nth_bit(A::NIN_MASK, k)] = tp.J[k] * gd;
       M::reduced_state_vjp(x, d, gred, gx);
+      if constexpr (CDN) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) gu[j] = fmaf(tp.J[NZ + j], gd, gu[j]);
+      }
     }
   }
 

@@ -49,8 +49,8 @@ def reduced_inputs(model, x, u):
         red = x
     nin = list(p["diffusion_density_nn"].get("indx_noise_in", range(model.n_x)))
     z = red[..., nin] if len(nin) < red.shape[-1] else red
-    if p.get("control_dependent_noise", False):
-        raise Sde4Error("control_dependent_noise has no compiled kernel")
+    if p.get("control_dependent_noise", False):  # nsde.py:362
+        z = torch.cat((z, u.expand(*z.shape[:-1], u.shape[-1])), dim=-1)
     return z
 
 
@@ -64,6 +64,8 @@ def init_mu_params(model, dl, rng):
         return {m: {"mu_coeff": rng.uniform(-0.001, 0.001, ()).astype(np.float32)}}
     iv = lm.get("init_value", 0.01)
     nin = len(list(model.params["diffusion_density_nn"].get("indx_noise_in", range(model.n_x))))
+    if model.params.get("control_dependent_noise", False):  # mu_coeff_nn reads the same augmented vector (nsde.py:640)
+        nin += model.n_u
     dims = [nin] + list(lm["hidden_layers"]) + [1]
     return {"%s/~mu_coeff_nn/mu_coeff/~/linear_%d" % (m, k): {"w": rng.uniform(-iv, iv, (dims[k], dims[k + 1])).astype(np.float32),
                                                               "b": np.zeros(dims[k + 1], np.float32)}

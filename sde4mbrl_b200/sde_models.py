@@ -60,8 +60,6 @@ class ControlledSDE:
             raise Sde4Error("unknown sde_solver '%s' (known: %s)" % (params["sde_solver"], ", ".join(L.SOLVERS)))
         if params["n_x"] != params["n_y"]:
             raise Sde4Error("only identity observation maps are supported (n_x == n_y)")
-        if params.get("control_dependent_noise", False):
-            raise Sde4Error("control_dependent_noise=True has no compiled kernel")
         self.n_x, self.n_u, self.n_y = params["n_x"], params["n_u"], params["n_y"]
 
     # ---- to be specialised ----------------------------------------------
@@ -89,7 +87,10 @@ class ControlledSDE:
         d.noise_in_mask = _mask(nin)
         d.noise_out_mask = _mask(nout)
         dn = dd["density_nn"]
-        d.density = _net_desc(len(nin), dn["hidden_layers"], 1, dn.get("activation_fn", "tanh"))
+        # control_dependent_noise (nsde.py:362): the density net reads concat(noise inputs, u); the kernels recognise it
+        # by a density input wider than the noise-input mask (csrc/models.cuh, Diffusion::CDN)
+        n_in = len(nin) + (self.n_u if p.get("control_dependent_noise", False) else 0)
+        d.density = _net_desc(n_in, dn["hidden_layers"], 1, dn.get("activation_fn", "tanh"))
         d.aggr = float(dn.get("aggressiveness", 1.0))
         sc = dd.get("scaler_nn", None)
         if sc is not None and sc.get("type", "none") != "none":

@@ -63,21 +63,25 @@ def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H):
     assert set(td) == {"TestErrorData", "TestStdData"} and np.isfinite(err)
 
 
-@pytest.mark.parametrize("mu_type,N,partial", [("dnn", 2, 0), ("global", 1, 0), ("constant", 1, 0), ("dnn", 2, 5), ("global", 3, 2)])
-def test_density_regulariser_terms_and_grads(cuda, mu_type, N, partial):
+@pytest.mark.parametrize("mu_type,N,partial,cdn", [("dnn", 2, 0, False), ("global", 1, 0, False), ("constant", 1, 0, False),
+                                                   ("dnn", 2, 5, False), ("global", 3, 2, False),
+                                                   ("dnn", 2, 0, True), ("global", 2, 3, True)])
+def test_density_regulariser_terms_and_grads(cuda, mu_type, N, partial, cdn):
     """Full training loss of cartpole_sde.yaml:95-137 (data term + distance-aware regulariser + weight penalty):
     gradient-norm / strong-convexity / mu terms with the reference's key chain for the ball samples, and the
     gradient w.r.t. every parameter, vs the oracle's float64 autograd."""
     from sde4mbrl_b200 import nsde, random as R
     B, H = 4, 8
     pm = configs.cartpole_model(horizon=1, num_particles=1)
+    if cdn:  # control_dependent_noise (nsde.py:362): density / mu nets and the ball live in [reduced state, u]
+        pm["control_dependent_noise"] = True
     ow = [9, 5, 1, 1.0, 10]
     lm = {"dnn": {"type": "dnn", "init_value": 0.3, "activation_fn": "tanh", "hidden_layers": [8, 8]},
           "global": True, "constant": False}[mu_type]
     lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 4,
           "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 1e-3, "default_weights": 1.0,
           "special_parameters_pen": {"scaler": 0, "density": 0},
-          "density_loss": {"learn_mucoeff": lm, "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4], "ball_nsamples": 6},
+          "density_loss": {"learn_mucoeff": lm, "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4] + ([0.3] if cdn else []), "ball_nsamples": 6},
           "pen_grad_density": 1.0, "pen_density_scvex": 1.0, "pen_mu_type": "lin_inv", "pen_mu_coeff": 1000.0,
           "pen_scvex_mult": 0.01}
     if partial:  # num_sample2consider + density_on_partial (nsde.py:753-760, 794-797)

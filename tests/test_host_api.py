@@ -74,8 +74,13 @@ def test_errors_for_unsupported_requests():
         nsde.create_sampling_fn(configs.hexa_model(2, 1), sde_constr=object)
     with pytest.raises(L.Sde4Error):
         sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), control_augmented_state=True)).describe()
+    # control_dependent_noise widens the density input by n_u (nsde.py:362); architectures without such an
+    # instantiation are rejected by the library, not silently evaluated without the controls
+    m = sde_models.CartPoleSDE(dict(configs.cartpole_model(2, 1), control_dependent_noise=True))
+    assert m.describe().density.n_in == 3 + 1 and m.layout(m.describe())[1] > 0
     with pytest.raises(L.Sde4Error):
-        sde_models.CartPoleSDE(dict(configs.cartpole_model(2, 1), control_dependent_noise=True))
+        mb = sde_models.CartPoleSDE(dict(configs.cartpole_model(2, 1, side_info=False), control_dependent_noise=True))
+        mb.layout(mb.describe())
     with pytest.raises(L.Sde4Error):
         sde_models.SDERotorModel(dict(configs.hexa_model(2, 1), sde_solver="runge_kutta"))
 
