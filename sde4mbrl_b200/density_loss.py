@@ -48,7 +48,8 @@ def reduced_inputs(model, x, u):
     else:
         red = x
     nin = list(p["diffusion_density_nn"].get("indx_noise_in", range(model.n_x)))
-    z = red[..., nin] if len(nin) < red.shape[-1] else red
+    # (columns picked by slicing, not by an index tensor: no host -> device copy, so the chain can be graph-captured)
+    z = torch.stack([red[..., i] for i in nin], dim=-1) if len(nin) < red.shape[-1] else red
     if p.get("control_dependent_noise", False):  # nsde.py:362
         z = torch.cat((z, u.expand(*z.shape[:-1], u.shape[-1])), dim=-1)
     return z
@@ -82,7 +83,12 @@ def density_keys(rng, B, N, Hd):
     return _random.split_many(kt, 2)[..., 1, :].contiguous()
 
 
-def density_terms(model, tree, y, u, rng, N, dl, partial=None):
+def ball_radius(dl, dim, device):
+    """``params['density_loss']['ball_radius']`` broadcast to the augmented vector (nsde.py:625-627) as a device tensor."""
+    return torch.as_tensor(np.broadcast_to(np.asarray(dl["ball_radius"], np.float32), (dim,)).copy(), device=device)
+
+
+def density_terms(model, tree, y, u, rng, N, dl, partial=None, radius=None):
     """Per (minibatch element, particle) terms of ``sample_for_loss_computation`` (nsde.py:771-804).
     ``tree``: torch parameter tree (requires_grad leaves), ``y[B, Hd+1, n_y]``, ``u[B, Hd, n_u]`` device tensors.
     ``partial = (y_values[B, H+1, n_y], u_values[B, H, n_u], step_weight[H, B*N])``: ``density_on_partial`` with
@@ -114,7 +120,8 @@ def density_terms(model, tree, y, u, rng, N, dl, partial=None):
     (gz,) = torch.autograd.grad(den.sum(), z, create_graph=True)  # rows are independent: d den_k / d z_k
     grad_norm = (gz ** 2).sum(-1)  # [B, Hd]
     ns = int(dl["ball_nsamples"])
-    radius = torch.as_tensor(np.broadcast_to(np.asarray(dl["ball_radius"], np.float32), (dim,)).copy(), device=y.device)
+    if radius is None:  # (a host -> device copy: the graphed path passes the device tensor in)
+        radius = ball_radius(dl, dim, y.device)
     keys = density_keys(rng, B, N, Hk)[:, :, :Hd].contiguous()  # [B, N, Hd, 2]
     ball = _random.normal_many(keys, (ns, dim)) * radius  # [B, N, Hd, ns, dim]
     zb = z[:, None, :, None, :] + ball
@@ -175,3 +182,96 @@ def weighted_terms(loss_params, dl, grad_norm, sconvex, mu):
         total = total + loss_mu * loss_params["pen_mu_coeff"] * mult
     return total, {"gradDensity": loss_grad_density, "densitySCVEX": loss_density_scvex, "muCoeff": mu_mean,
                    "lossMuCoeff": loss_mu}
+
+
+_INFO_KEYS = ("gradDensity", "densitySCVEX", "muCoeff", "lossMuCoeff")
+
+
+class GraphedRegulariser:
+    """The regulariser's value, logged scalars and parameter gradient as ONE CUDA-graph replay per call.
+
+    ``density_terms`` + ``weighted_terms`` + the reverse-over-reverse backward are ~250 small launches that cost ~4 ms of
+    host dispatch per call against well under 1 ms of GPU work at the cartpole_sde.yaml shape (B = 512, H = 30,
+    20 ball samples; scripts/loss_api_breakdown.py).  The whole chain -- key derivation (``sde4_rng_split_many``), ball
+    noise (``sde4_rng_normal_many``), the cuBLAS evaluations, ``torch.autograd.grad`` -- is captured once per input
+    shape on static buffers; a call then copies [parameters | y | u | key] into them, replays, and reads back one
+    packed result [total | 4 scalars | gradient block].  ``density_on_partial`` (per-sample step weights) keeps the
+    eager path."""
+
+    def __init__(self, model, loss_params, dl, num_particles):
+        self.model, self.lp, self.dl, self.N = model, loss_params, dl, num_particles
+        self._cache = {}
+
+    def _leaves(self, nn_params):
+        out = []
+        for mod, leaves in nn_params.items():
+            if not (any(n in mod for n in ("density", "mu_coeff")) or "mu_coeff" in leaves):
+                continue
+            for k, v in leaves.items():
+                out.append((mod, k, tuple(np.shape(v))))
+        return out
+
+    def _body(self, st):
+        p = st["flat"].clone().requires_grad_(True)
+        tree, o = {}, 0
+        for mod, k, shp in st["leaves"]:
+            n = int(np.prod(shp)) if len(shp) else 1
+            tree.setdefault(mod, {})[k] = p[o:o + n].view(shp)
+            o += n
+        gn, sc, mu, _ = density_terms(self.model, tree, st["y"], st["u"], st["key"], self.N, self.dl, None, st["radius"])
+        dtot, dinfo = weighted_terms(self.lp, self.dl, gn, sc, mu)
+        g = torch.autograd.grad(dtot, p, allow_unused=True)[0] if dtot.requires_grad else None
+        scal = torch.stack([dtot.detach().float()] + [torch.as_tensor(dinfo[k], dtype=torch.float32, device=p.device).detach().reshape(())
+                                                      for k in _INFO_KEYS])
+        return torch.cat((scal, g if g is not None else torch.zeros_like(p)))
+
+    def _capture(self, leaves, y, u, key):
+        dev = y.device
+        ntot = sum(int(np.prod(s)) if len(s) else 1 for _, _, s in leaves)
+        st = {"leaves": leaves, "flat": torch.zeros(ntot, dtype=torch.float32, device=dev),
+              "host": torch.zeros(ntot, dtype=torch.float32).pin_memory(),
+              "y": y.clone(), "u": u.clone(), "key": key.clone()}
+        with torch.no_grad():
+            st["radius"] = ball_radius(self.dl, reduced_inputs(self.model, y[:, :-1], u).shape[-1], dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up off the capture (cuBLAS handles / workspaces, autograd threads)
+            for _ in range(2):
+                self._body(st)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        st["graph"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st["graph"]):
+            st["out"] = self._body(st)
+        st["out_host"] = torch.zeros(st["out"].numel(), dtype=torch.float32).pin_memory()
+        return st
+
+    def __call__(self, nn_params, y, u, key):
+        """-> (total, {logged scalars}, {mod: {leaf: numpy gradient}}) for device tensors y[B, Hd+1, n_y], u[B, Hd, n_u]
+        and a device key int32[2]."""
+        leaves = self._leaves(nn_params)
+        sig = (tuple(y.shape), tuple(u.shape), tuple(leaves), str(y.device), _random.rng_mode())
+        st = self._cache.get(sig)
+        if st is None:
+            st = self._cache[sig] = self._capture(leaves, y, u, key)
+        o = 0
+        hv = st["host"].numpy()
+        for mod, k, shp in leaves:
+            n = int(np.prod(shp)) if len(shp) else 1
+            hv[o:o + n] = np.asarray(nn_params[mod][k], np.float32).reshape(-1)
+            o += n
+        st["flat"].copy_(st["host"], non_blocking=True)
+        st["y"].copy_(y)
+        st["u"].copy_(u)
+        st["key"].copy_(key)
+        st["graph"].replay()
+        st["out_host"].copy_(st["out"], non_blocking=True)
+        torch.cuda.current_stream(y.device).synchronize()
+        res = st["out_host"].numpy()
+        info = {k: float(res[1 + i]) for i, k in enumerate(_INFO_KEYS)}
+        grads, o = {}, 1 + len(_INFO_KEYS)
+        for mod, k, shp in leaves:
+            n = int(np.prod(shp)) if len(shp) else 1
+            grads.setdefault(mod, {})[k] = res[o:o + n].reshape(shp).copy()
+            o += n
+        return float(res[0]), info, grads

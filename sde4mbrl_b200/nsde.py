@@ -485,6 +485,10 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
                     grads.setdefault(mod, {})[name] = (2.0 * coeff * pen_w * (a - default_val)).astype(np.float32)
         return tot, grads
 
+    # loss_params["graph_regulariser"] = False keeps the regulariser on the eager torch path
+    graphed = _density.GraphedRegulariser(model, loss_params, dl, num_sample) \
+        if (dl is not None and loss_params.get("graph_regulariser", True)) else None
+
     def _prepare(y, u):
         y, u = as_f32(y), as_f32(u)
         assert y.shape[1] == u.shape[1] + 1, "Trajectory horizon must match"
@@ -543,11 +547,18 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         if loss_params.get("pen_data", 0) > 0:
             total += loss_data * loss_params["pen_data"]
         dinfo, dgrads = {}, {}
-        if dl is not None:
+        on_partial = step_weight is not None and params_model.get("density_on_partial", False)
+        if dl is not None and graphed is not None and not on_partial:
+            # distance-aware regulariser at the data points as one CUDA-graph replay (density_loss.GraphedRegulariser)
+            dval, dinfo, dgrads_np = graphed(_nn_params, as_f32(y), as_f32(u), key)
+            total += dval
+            if want_grad:
+                dgrads = {mod: {k: torch.from_numpy(v) for k, v in leaves.items()} for mod, leaves in dgrads_np.items()}
+        elif dl is not None:
             # distance-aware regulariser at the data points (density_loss.py): library GEMMs + autograd
             tt = _density.to_torch_tree(_nn_params, y_values.device)
             partial = None
-            if step_weight is not None and params_model.get("density_on_partial", False):  # nsde.py:794-797
+            if on_partial:  # nsde.py:794-797
                 if strategy != "first":
                     raise Sde4Error("density_on_partial needs u_sampling_strategy 'first'")
                 partial = (y_values, u_values, step_weight)

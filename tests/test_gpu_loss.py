@@ -383,3 +383,42 @@ def test_u_sampling_strategy_random(cuda, kind, cls, oname, B, N, H, nsd, m):
     want_err = float((((tfm(yv) - tfm(ys.mean(dim=1))) / w) ** 2).sum(dim=(-1, -2)).mean())
     assert abs(err - want_err) < 1e-4 * abs(want_err) + 1e-6
     assert set(tinfo) == {"TestErrorData", "TestStdData"}
+
+
+def test_graphed_regulariser_replays_match_the_eager_path(cuda):
+    """The CUDA-graph replay of the regulariser (density_loss.GraphedRegulariser) tracks new parameters, data and keys:
+    three consecutive calls with different inputs give the eager path's totals, logged scalars and gradients."""
+    from sde4mbrl_b200 import nsde, random as R
+    B, H, N = 6, 9, 2
+
+    def make(graph):
+        pm = configs.cartpole_model(horizon=1, num_particles=1)
+        lp = {"seed": 1, "stepsize": pm["stepsize"], "data_stepsize": pm["stepsize"], "num_particles": N, "num_particles_test": 4,
+              "horizon": H, "obs_weights": [9, 5, 1, 1.0, 10], "pen_data": 1.0, "pen_weights": 1e-3, "default_weights": 1.0,
+              "density_loss": {"learn_mucoeff": {"type": "dnn", "init_value": 0.3, "activation_fn": "tanh", "hidden_layers": [8, 8]},
+                               "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4], "ball_nsamples": 6},
+              "pen_grad_density": 1.0, "pen_density_scvex": 1.0, "pen_mu_type": "lin_inv", "pen_mu_coeff": 1000.0,
+              "pen_scvex_mult": 0.01, "graph_regulariser": graph}
+        nn0, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.CartPoleSDE, verbose=False)
+        return pm, nn0, loss_fn
+
+    pm, nn0, f_graph = make(True)
+    _, _, f_eager = make(False)
+    rng = np.random.default_rng(0)
+    for rep in range(3):
+        nn = configs.random_params(sde_models.CartPoleSDE(pm), seed=4 + rep)
+        nn["cart_pole_sde/~construct_diffusion_density_nn/density/~/linear_2"]["w"] *= np.float32(3.0)
+        for m in nn0:
+            if "mu_coeff" in m:
+                nn[m] = {k: np.array(v) * np.float32(1.0 + rep) for k, v in nn0[m].items()}
+        y = (rng.normal(0, 0.5, (B, H + 1, 4)) + np.array([0, 0, 3.0, 0])).astype(np.float32)
+        u = rng.uniform(-1, 1, (B, H, 1)).astype(np.float32)
+        tg, ig, gg = f_graph.value_and_grad(nn, y, u, R.PRNGKey(20 + rep))
+        te, ie, ge = f_eager.value_and_grad(nn, y, u, R.PRNGKey(20 + rep))
+        assert abs(tg - te) <= 1e-5 * abs(te)
+        for k in ie:
+            assert abs(ig[k] - ie[k]) <= 1e-5 * abs(ie[k]) + 1e-12, k
+        for m in ge:
+            for k in ge[m]:
+                assert np.max(np.abs(gg[m][k] - ge[m][k])) <= 1e-4 * np.max(np.abs(ge[m][k])) + 1e-9, (m, k)
+        assert ig["densitySCVEX"] > 0
