@@ -253,6 +253,8 @@ class GraphedRegulariser:
         sig = (tuple(y.shape), tuple(u.shape), tuple(leaves), str(y.device), _random.rng_mode())
         st = self._cache.get(sig)
         if st is None:
+            if len(self._cache) >= 8:  # a training loop has one or two batch shapes; do not hoard graphs for more
+                self._cache.pop(next(iter(self._cache)))
             st = self._cache[sig] = self._capture(leaves, y, u, key)
         o = 0
         hv = st["host"].numpy()
