@@ -20,7 +20,7 @@ using CartSiD32Cdn = Arch<SDE4_MODEL_CARTPOLE, 4, 1, SDE4_CART_SIDE_INFO, Net<4,
 SDE4_REGISTER_TRAIN_LS(cartpole_si_d32, CartpoleModel, CartSiD32, 8)
 SDE4_REGISTER_TRAIN_LS(cartpole_bb_d32, CartpoleModel, CartBbD32, 8)
 SDE4_REGISTER(cartpole_bb_d8, CartpoleModel<CartBbD8>)
-SDE4_REGISTER_TRAIN(cartpole_si_d32_cdn, CartpoleModel, CartSiD32Cdn)
+SDE4_REGISTER_TRAIN_LS(cartpole_si_d32_cdn, CartpoleModel, CartSiD32Cdn, 8)
 SDE4_REGISTER_TRAIN(cartpole_si_ode, CartpoleModel, CartSiOde)
 SDE4_REGISTER_TRAIN(cartpole_bb_ode, CartpoleModel, CartBbOde)
 }  // namespace sde4

@@ -15,5 +15,5 @@ using MsdBbD32Cdn = Arch<SDE4_MODEL_MSD, 2, 1, 0, Net<3, 32, 32, 1, SWISH>, 0x3,
 SDE4_REGISTER_TRAIN_LS(msd_bb_d32, MsdModel, MsdBbD32, 4)
 SDE4_REGISTER_LS(msd_si_d32, MsdModel, MsdSiD32, 4)
 SDE4_REGISTER(msd_gt, MsdModel<MsdGt>)
-SDE4_REGISTER(msd_bb_d32_cdn, MsdModel<MsdBbD32Cdn>)
+SDE4_REGISTER_LS(msd_bb_d32_cdn, MsdModel, MsdBbD32Cdn, 4)
 }  // namespace sde4

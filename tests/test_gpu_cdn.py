@@ -149,3 +149,36 @@ def test_architectures_without_a_control_dependent_instantiation_are_rejected(cu
     pm["control_dependent_noise"] = True
     with pytest.raises(Sde4Error):
         Engine(cls(pm)).packed(configs.random_params(cls(pm), seed=0))
+
+
+@pytest.mark.parametrize("kind,lanes,H,N", [("cartpole", 8, 40, 37), ("msd", 4, 30, 21)])
+def test_lane_split_kernels_with_control_dependent_noise(cuda, kind, lanes, H, N):
+    """Lane-split instantiations (in-kernel threefry noise, straight-line loop bodies; for the gradient the
+    software-pipelined diffusion adjoint that evaluates the density net of step t-1 -- with u_{t-1} -- while step t is
+    applied) vs the one-thread-per-sample kernels and the oracle on the same key."""
+    from sde4mbrl_b200.engine import Engine
+    pm, model, nn, oname = _build(kind, H, N, seed=5)
+    rng = np.random.default_rng(7)
+    y0, opt, cp, stage, xref = _problem(kind, H, model, rng)
+    eng = Engine(model)
+    ts = orc.compute_timesteps(pm)
+    key = tf.PRNGKey(4)
+    xl = eng.rollout(nn, y0[None], opt, ts, key=key, N=N, lanes=lanes)
+    x1 = eng.rollout(nn, y0[None], opt, ts, key=key, N=N, lanes=1)
+    assert hp.rel_err(xl.cpu().numpy(), x1.cpu().numpy()) < 2e-5
+    cl, gl, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=lanes)
+    c1, g1, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=1)
+    assert abs(float(cl[0]) - float(c1[0])) <= 2e-5 * abs(float(c1[0]))
+    assert hp.rel_err(gl.cpu().numpy(), g1.cpu().numpy()) < 2e-4
+    cv, _, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, key=key, lanes=lanes, want_grad=False)
+    assert abs(float(cv[0]) - float(c1[0])) <= 2e-5 * abs(float(c1[0]))
+    # oracle with the noise the key chain produces (nsde.py:1581 -> sde_solver.py:276,283)
+    dw = tf.rollout_noise(key, N, H, model.n_x)
+    c64, g64, _ = _oracle_cost(kind, oname, pm, nn, y0, opt, dw, cp, xref, torch.float64)
+    assert abs(float(cl[0]) - c64) <= 2e-5 * abs(c64) + 1e-7
+    assert hp.rel_err(gl.cpu().numpy(), g64) < 1e-3
+    # shaped (sigmoid-residual) cost -> the MODE-1 instantiation; given noise -> the generic lane-split kernel
+    nat = hp.to_native_noise(dw)
+    cg, gg, _ = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, N=N, noise=nat, lanes=lanes)
+    assert abs(float(cg[0]) - c64) <= 2e-5 * abs(c64) + 1e-7
+    assert hp.rel_err(gg.cpu().numpy(), g64) < 1e-3
