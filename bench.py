@@ -280,9 +280,15 @@ def main():
         (c, _), g = multi_cost.value_and_grad(e2e_pk, w["y0"], opt_host, key_np, w["stage"], extra_cost_args=w["xref"])
         return c, g  # CPU tensors: the device->host read of [cost | grad] happened inside the call
 
+    if world > 1:
+        # N > 1: the same host-array call with the particles of the problem sharded over the ranks -- one packed pinned
+        # H2D copy, K2 + K3 into the symmetric-memory buffer, one-shot all-reduce, one D2H copy (nsde.py, particle_reducer)
+        multi_cost.particle_reducer = CostGradReducer(HORIZON * 6 + 1, dev, grad_shape=(HORIZON, 6))
+
     def step_e2e():
-        if world == 1:
-            return step_e2e_host()
+        return step_e2e_host()
+
+    def step_e2e_autograd():  # (the generic autograd route, kept for scripts/e2e_breakdown.py comparisons)
         y = y0_h.to(dev, non_blocking=True)
         o = opt_h.to(dev, non_blocking=True).requires_grad_(True)
         xr = xref_h.to(dev, non_blocking=True)
@@ -301,6 +307,12 @@ def main():
 
     for _ in range(3):
         step_e2e()
+    if world > 1:  # the host-array route and the device-resident step agree on the all-reduced [cost | grad]
+        c_chk, g_chk = step_e2e()
+        c_dev, g_dev = step_device()
+        torch.cuda.synchronize()
+        assert abs(float(c_chk) - float(c_dev[0])) <= 1e-5 * abs(float(c_dev[0])), (float(c_chk), float(c_dev[0]))
+        assert float((g_chk - g_dev.cpu()).abs().max()) <= 1e-5 * float(g_dev.abs().max()) + 1e-9
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -660,7 +672,9 @@ def main():
                     "api": "nsde.create_online_cost_sampling_fn(...).multi_sampling.value_and_grad on HOST numpy arrays "
                            "(sde4_cost_grad_host: pinned staging, one H2D + one D2H copy, stream sync inside)"
                            if world == 1 else
-                           "nsde.create_online_cost_sampling_fn(...).multi_sampling + torch.autograd.grad, pinned host buffers"},
+                           "nsde.create_online_cost_sampling_fn(...).multi_sampling.value_and_grad on HOST numpy arrays with "
+                           "multi_sampling.particle_reducer = dist.CostGradReducer (one packed pinned H2D copy, K2 + K3 into the "
+                           "symmetric-memory buffer, one-shot all-reduce over NVLink, one D2H copy, stream sync inside)"},
             "gpu_launches": 2 * args.steps,
             "wall_s_timed_region": t_wall,
         }

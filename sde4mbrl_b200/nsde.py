@@ -22,7 +22,7 @@ from . import costs as _costs
 from . import density_loss as _density
 from . import random as _random
 from ._lib import Sde4Error
-from .engine import Engine, as_f32, as_key, is_host, host_f32
+from .engine import Engine, as_f32, as_key, is_host, host_f32, host_key
 from .sde_models import ControlledSDE
 
 
@@ -326,11 +326,74 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
                        extra_cost_args=None, extra_cost_terminal_args=None):
         """``jax.value_and_grad(multi_sampling, argnums=2, has_aux=True)`` (how ``apg.py:82,224`` obtains the
         gradient): ``((mean_cost, xtraj), grad)`` from ONE fused launch, without building an autograd graph."""
+        if multi_sampling.particle_reducer is not None:
+            return _value_and_grad_sharded(multi_sampling.particle_reducer, _nn_params, y, opt_params, rng, _cost_fn,
+                                           _terminal_cost, extra_dyn_args, extra_cost_args)
         opt, run = _prepare(_nn_params, y, opt_params, rng, _cost_fn, _terminal_cost, extra_dyn_args, extra_cost_args)
         cost, grad, xbuf = run(opt.detach(), True)
         return (cost, _xtraj_view(xbuf, opt)), grad
 
+    _stg = {}
+
+    def _value_and_grad_sharded(red, _nn_params, y, opt_params, rng, _cost_fn, _terminal_cost, extra_dyn_args, extra_cost_args):
+        """One problem whose particles span the ranks of ``red`` (a ``dist.CostGradReducer`` over H*n_opt + 1 floats):
+        every rank evaluates its ``num_particles`` particles of ``world * num_particles`` (keys
+        ``split(rng, N_total)[rank*N + n]``, both means scaled by 1/N_total), K3 writes [cost | grad] straight into the
+        reducer's buffer, ONE all-reduce (``jnp.mean`` over all particles, nsde.py:1586).  Host arguments travel as one
+        packed pinned copy each way; the returned trajectories are this rank's particles."""
+        from . import dist as _dist
+        if extra_dyn_args is not None:
+            raise Sde4Error("extra_dyn_args must be None (no shipped model uses them)")
+        if not isinstance(_cost_fn, _costs.StageCost) or (_terminal_cost is not None and not isinstance(_terminal_cost, _costs.StageCost)):
+            raise Sde4Error("_cost_fn / _terminal_cost must be costs.StageCost objects")
+        if extra_cost_args is None:
+            raise Sde4Error("extra_cost_args (the reference trajectory xref[H+1, n_x]) is required")
+        stage = _cost_fn if constr is None else _costs.with_constraints(_cost_fn, constr, n_u)
+        term = None if _terminal_cost is None else _terminal_cost.desc
+        engine.rng_mode = _random.rng_mode()
+        rank, world = _dist.world()
+        n_o, n_ref = H * opt_params_size, (H + 1) * n_x
+        if red.n != n_o + 1:
+            raise Sde4Error("particle_reducer must hold H*n_opt + 1 = %d floats" % (n_o + 1))
+        host = is_host(y) and is_host(opt_params) and is_host(rng) and is_host(extra_cost_args)
+        dev = red.buf.device
+        if host:
+            st = _stg.get(dev)
+            if st is None:
+                nin = n_x + n_o + n_ref + 2
+                st = _stg[dev] = (torch.empty(nin, dtype=torch.float32).pin_memory(), torch.empty(nin, dtype=torch.float32, device=dev),
+                                  torch.empty(n_o + 1, dtype=torch.float32).pin_memory())
+            pin, dbuf, out = st
+            hv = pin.numpy()
+            hv[:n_x] = host_f32(y).reshape(-1)
+            o_h = opt_params.numpy() if isinstance(opt_params, torch.Tensor) else opt_params
+            hv[n_x:n_x + n_o] = np.asarray(o_h, np.float32).reshape(-1)
+            hv[n_x + n_o:n_x + n_o + n_ref] = host_f32(extra_cost_args).reshape(-1)
+            hv[n_x + n_o + n_ref:].view(np.uint32)[:] = host_key(rng).reshape(2)
+            dbuf.copy_(pin, non_blocking=True)
+            y_t, opt_d = dbuf[:n_x], dbuf[n_x:n_x + n_o].view(H, opt_params_size)
+            xref, key = dbuf[n_x + n_o:n_x + n_o + n_ref].view(H + 1, n_x), dbuf[n_x + n_o + n_ref:].view(torch.int32)
+        else:
+            y_t, opt_d, xref, key = as_f32(y), as_f32(opt_params), as_f32(extra_cost_args), as_key(rng)
+        assert opt_d.dim() == 2 and opt_d.shape[-1] == opt_params_size, "one problem: opt_params must be [H, n_opt]"
+        c_out, g_out = red.views(1)
+        _, _, xbuf = engine.cost_grad(_nn_params, y_t.reshape(1, n_x), opt_d.detach(), time_steps, xref, stage.desc, terminal=term,
+                                      key=key, N=num_sample, want_grad=True, want_xtraj=True,
+                                      particle_offset=rank * num_sample, particle_total=world * num_sample,
+                                      cost_out=c_out, grad_out=g_out.view(1, H, opt_params_size))
+        tot = red.reduce()
+        xtraj = xbuf.view(H + 1, n_x + 1, 1, num_sample).permute(2, 3, 0, 1)[0]
+        if host:
+            out.copy_(tot, non_blocking=True)
+            torch.cuda.current_stream(dev).synchronize()
+            res = out.clone()
+            return (res[0], xtraj), res[1:].view(H, opt_params_size)
+        return (tot[0], xtraj), tot[1:].view(H, opt_params_size)
+
     multi_sampling.value_and_grad = value_and_grad
+    # set to a dist.CostGradReducer(H*n_opt + 1, device) to shard the particles of ONE problem over the process group
+    # (value_and_grad only); None: single-GPU evaluation
+    multi_sampling.particle_reducer = None
     # what a device-side solver (apg_batched.BatchedAPG) needs to evaluate the same cost without this closure
     multi_sampling.final_stage = lambda _cost_fn: _cost_fn if constr is None else _costs.with_constraints(_cost_fn, constr, n_u)
     multi_sampling.num_particles = num_sample

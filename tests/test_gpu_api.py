@@ -280,3 +280,35 @@ def test_model_env_adapter(cuda):
         st = w[:, 1:].numpy()
         r = (np.cos(np.cos(st[..., 2])) - 0.1 * np.abs(st[..., 0])).sum(1).mean()
         np.testing.assert_allclose(float(tot[b]), r, rtol=2e-4)
+
+
+def test_particle_sharded_value_and_grad_single_rank(cuda):
+    """``multi_sampling.particle_reducer`` (particles of one problem sharded over the process group; here a group of
+    one): the packed host-buffer route and the device route give the plain ``value_and_grad`` result."""
+    from sde4mbrl_b200 import nsde, random as R, costs
+    from sde4mbrl_b200.dist import CostGradReducer
+    import helpers as hp
+    H, N = 12, 9
+    mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=N)
+    pm = configs.hexa_model(horizon=H, num_particles=N, stepsize=0.05)
+    _, ms, _, _, _ = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.SDERotorModel)
+    nn = configs.random_params(sde_models.SDERotorModel(pm), seed=3)
+    rng = np.random.default_rng(2)
+    y0, opt = hp.start_state("hexa", rng), hp.controls("hexa", H, rng)
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    cp = mpc["cost_params"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    key = np.array([0, 77], np.uint32)
+    (c0, xt0), g0 = ms.value_and_grad(nn, y0, opt, key, stage, extra_cost_args=xref)
+    ms.particle_reducer = CostGradReducer(H * ms.n_opt + 1, torch.device("cuda:0"), grad_shape=(H, ms.n_opt))
+    try:
+        (c1, xt1), g1 = ms.value_and_grad(nn, y0, opt, key, stage, extra_cost_args=xref)  # host arrays
+        assert not c1.is_cuda and not g1.is_cuda
+        (c2, _), g2 = ms.value_and_grad(nn, torch.as_tensor(y0).cuda(), torch.as_tensor(opt).cuda(), R.PRNGKey(77), stage,
+                                        extra_cost_args=torch.as_tensor(xref).cuda())
+    finally:
+        ms.particle_reducer = None
+    for c, g in ((c1, g1), (c2, g2)):
+        assert abs(float(c) - float(c0)) <= 1e-6 * abs(float(c0))
+        np.testing.assert_allclose(g.cpu().numpy(), np.asarray(g0), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(xt1.cpu().numpy(), xt0.cpu().numpy(), rtol=1e-6, atol=1e-7)
