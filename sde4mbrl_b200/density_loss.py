@@ -211,6 +211,7 @@ class GraphedRegulariser:
                 out.append((mod, k, tuple(np.shape(v))))
         return out
 
+    @torch.enable_grad()
     def _body(self, st):
         p = st["flat"].clone().requires_grad_(True)
         tree, o = {}, 0
