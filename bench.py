@@ -172,6 +172,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flush-mode", default="write", choices=["write", "write+read", "none"],
+                    help="diagnostic: how L2 is flushed between timed steps (the bench line is quoted with 'write')")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per sample (0 = library heuristic)")
     args = ap.parse_args()
@@ -236,8 +238,12 @@ def main():
     evs = []
     barrier()
     t_wall0 = time.perf_counter()
+    flush_rd = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if args.flush_mode == "write+read" else None
     for _ in range(args.steps):
-        flush.fill_(1)
+        if args.flush_mode != "none":
+            flush.fill_(1)
+        if flush_rd is not None:
+            flush_rd.view(torch.int32).sum()  # evicts the dirty flush lines: nothing of the flush is written back in the timed region
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         step_device()
@@ -665,7 +671,7 @@ def main():
                        "particles_per_gpu": N_PART, "horizon": HORIZON, "parallelism": "particles sharded over %d GPU(s), one all-reduce of [cost, grad] (601 floats): %s"
                        % (world, "none (1 GPU)" if world == 1 else
                           ("torch symmetric-memory one-shot all-reduce over NVLink" if reducer.symm else "NCCL all-reduce")),
-                       "l2": "flushed between timed steps (256 MB write)", "timing": "CUDA events per step, max over ranks"},
+                       "l2": {"write": "flushed between timed steps (256 MB write)", "write+read": "DIAGNOSTIC: 256 MB write then 256 MB read between timed steps", "none": "DIAGNOSTIC: not flushed"}[args.flush_mode], "timing": "CUDA events per step, max over ranks"},
             "clocks": clocks,
             "e2e": {"value": total_ps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,
