@@ -366,7 +366,7 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
             pin, dbuf, out = st
             hv = pin.numpy()
             hv[:n_x] = host_f32(y).reshape(-1)
-            o_h = opt_params.numpy() if isinstance(opt_params, torch.Tensor) else opt_params
+            o_h = opt_params.detach().numpy() if isinstance(opt_params, torch.Tensor) else opt_params
             hv[n_x:n_x + n_o] = np.asarray(o_h, np.float32).reshape(-1)
             hv[n_x + n_o:n_x + n_o + n_ref] = host_f32(extra_cost_args).reshape(-1)
             hv[n_x + n_o + n_ref:].view(np.uint32)[:] = host_key(rng).reshape(2)
