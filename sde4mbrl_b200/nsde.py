@@ -8,7 +8,9 @@ buffers.
 
 Differences that cannot be hidden (all raise instead of silently changing behaviour):
   * ``sde_constr`` must be one of the descriptor classes in ``sde4mbrl_b200.sde_models``;
-  * controls must be arrays (a callable ``us(y)``, ``sde_solver.py:292``) is rejected;
+  * a callable ``us(y)`` (``sde_solver.py:292``) is accepted by the sampling functions only, receives the batch of
+    particle observations as a CUDA tensor, and is stepped from the host (one launch per step); the cost / gradient
+    factories need control arrays;
   * ``extra_args`` / ``extra_dyn_args`` must be ``None`` (no shipped model uses them);
   * ``_cost_fn`` must be a ``costs.StageCost`` (the shipped cost families), not a Python callable.
 """
@@ -107,6 +109,8 @@ def _make_multi_sampling(engine, params_model, num_samples, squeeze_single):
         y = as_f32(y)
         batched = y.dim() == 2  # extension: a leading batch of start states (vmap in nsde.py:1322-1323)
         assert y.dim() in (1, 2), "Not the right dimension for the initial observation and the random key"
+        if callable(u):
+            return _closed_loop(_nn_params, y, u, as_key(rng), time_steps)
         u = _controls(u, H, n_u)
         key = as_key(rng)
         assert key.dim() == (2 if (batched and key.dim() == 2) else 1), "RNG must be a single key for vmapping"
@@ -124,6 +128,37 @@ def _make_multi_sampling(engine, params_model, num_samples, squeeze_single):
         if squeeze_single and num_samples == 1:
             x, uev = x.select(-3, 0), uev.select(-3, 0)
         return x, x, uev  # identity observation map: yevol is xevol
+
+    def _closed_loop(_nn_params, y, u_fn, key, time_steps):
+        """Controls given as a function of the observation, ``u_t = us(y_t)`` (sde_solver.py:292).  A Python callable
+        cannot run inside the rollout kernel, so the horizon is stepped from the host: one K1 launch per step over all
+        particles (each particle = one problem with its own control), with the Brownian increments drawn up front on the
+        device by the reference's key chain (``split(rng, N)[p]`` nsde.py:1026 -> ``split(.)[0]``, ``normal(., (H, n_x))``
+        sde_solver.py:276,283).  The reference vmaps ``us`` over particles; here it receives the batch ``y[N, n_y]`` (a
+        CUDA tensor) and returns ``[N, n_u]`` (or ``[n_u]``, shared)."""
+        assert y.dim() == 1 and key.dim() == 1, "closed-loop controls: one start observation and one key"
+        engine.rng_mode = _random.rng_mode()
+        N, H = num_samples, time_steps.shape[0]
+        noise = None
+        if engine.noisy:
+            kb = _random.split_many(_random.split(key, N), 2)[:, 0].contiguous()
+            noise = _random.normal_many(kb, (H, n_x)).permute(1, 2, 0).contiguous()  # [H, n_x, N]
+        x = y[None].expand(N, n_x).contiguous()
+        xs, us = [x], []
+        for t in range(H):
+            ut = as_f32(u_fn(x))
+            if ut.dim() == 1:
+                ut = ut[None].expand(N, n_u)
+            assert tuple(ut.shape) == (N, n_u), "us(y) must return [N, n_u] or [n_u]"
+            xb = engine.rollout(_nn_params, x, ut.reshape(N, 1, n_u).contiguous(), time_steps[t:t + 1], N=1,
+                                noise=None if noise is None else noise[t:t + 1])
+            x = xb[1].t().contiguous()
+            xs.append(x)
+            us.append(ut)
+        xev, uev = torch.stack(xs, dim=1), torch.stack(us, dim=1)
+        if squeeze_single and num_samples == 1:
+            xev, uev = xev[0], uev[0]
+        return xev, xev, uev
 
     multi_sampling.engine = engine
     return multi_sampling

@@ -312,3 +312,37 @@ def test_particle_sharded_value_and_grad_single_rank(cuda):
         assert abs(float(c) - float(c0)) <= 1e-6 * abs(float(c0))
         np.testing.assert_allclose(g.cpu().numpy(), np.asarray(g0), rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(xt1.cpu().numpy(), xt0.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind", ["cartpole", "hexa"])
+def test_controls_as_a_function_of_the_observation(cuda, kind):
+    """``us`` callable (sde_solver.py:292): closed-loop rollout, one kernel launch per step, noise from the reference's
+    key chain; checked against the oracle stepped with the same feedback law."""
+    from sde4mbrl_b200 import nsde, random as R
+    H, N = 15, 11
+    mk, cls, oname = hp.KINDS[kind]
+    pm = mk(horizon=H, num_particles=N)
+    nn = configs.random_params(cls(pm), seed=2)
+    _, ms = nsde.create_sampling_fn(pm, sde_constr=cls, seed=0)
+    rng = np.random.default_rng(4)
+    y0 = hp.start_state(kind, rng)
+    n_x, n_u = pm["n_x"], pm["n_u"]
+    K = rng.normal(0, 0.05, (n_x, n_u)).astype(np.float32)
+    c = (np.full(n_u, 0.33) if kind == "hexa" else np.zeros(n_u)).astype(np.float32)
+    Kt, ct = torch.as_tensor(K).cuda(), torch.as_tensor(c).cuda()
+    policy = lambda yy: torch.clamp(yy @ Kt + ct, -1.0, 1.0)
+    xevol, yevol, uevol = ms(nn, y0, policy, R.PRNGKey(9))
+    assert tuple(xevol.shape) == (N, H + 1, n_x) and tuple(uevol.shape) == (N, H, n_u)
+    om = orc.make_model(oname, pm, {m: {k: torch.tensor(np.asarray(v)) for k, v in d.items()} for m, d in nn.items()})
+    dw = torch.tensor(tf.rollout_noise(tf.PRNGKey(9), N, H, n_x))
+    ts = orc.compute_timesteps(pm)
+    x = torch.tensor(y0)[None].expand(N, n_x)
+    Kc, cc = torch.tensor(K), torch.tensor(c)
+    xs = [x]
+    for t in range(H):
+        u = torch.clamp(x @ Kc + cc, -1.0, 1.0)
+        x = orc.euler_maruyama(om, ts[t:t + 1], x, u[:, None, :], dw[:, t:t + 1])[:, 1]
+        xs.append(x)
+    want = torch.stack(xs, dim=1).numpy()
+    assert hp.rel_err(xevol.cpu().numpy(), want) < 5e-5
+    np.testing.assert_allclose(uevol.cpu().numpy()[:, 0], np.clip(want[:, 0] @ K + c, -1, 1), rtol=1e-5, atol=1e-6)
