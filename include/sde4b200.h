@@ -34,6 +34,7 @@ extern "C" {
 #define SDE4_MAX_NX 16
 #define SDE4_MAX_NU 8
 #define SDE4_MAX_NOPT 24
+#define SDE4_LANES_WS 64
 
 typedef enum sde4_status {
   SDE4_OK = 0,
@@ -162,7 +163,9 @@ typedef struct sde4_rollout_args {
    * particle_total == 0 means (offset 0, total N). */
   int32_t particle_offset, particle_total;
   /* lanes per sample: 0 = library heuristic, 1 = one thread per sample, L > 1 = lane-split kernel
-   * (only if compiled for this architecture, else an error) */
+   * (only if compiled for this architecture, else an error).  sde4_cost_args only: SDE4_LANES_WS = the
+   * warp-specialised value + gradient kernel (the two halves of a step on different warps; an error when the
+   * architecture has none or the call is not value + gradient with threefry noise and no state constraints). */
   int32_t lanes;
   /* fixed-step scheme, sde4_solver.  EULER_MARUYAMA is the reference's only registered solver
    * (sde4mbrl/sde_solver.py:243-317, :321-325).  The two Stratonovich schemes exist in the reference as commented-out

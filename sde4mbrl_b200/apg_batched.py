@@ -35,7 +35,8 @@ class BatchedAPG:
     def __init__(self, engine, nn_params, stage, optimizer_params, time_steps, num_particles, lb=None, ub=None,
                  terminal=None, lanes=0, merge_xv_grad=None, progressive_ls=None, speculative=None):
         self.eng = engine
-        self.pk = engine.packed(nn_params)
+        self.pk = engine.packed(nn_params).private_copy()  # this solver's own device block (see set_params)
+        self._ws = None
         self.stage = stage
         self.terminal = terminal
         self.op = optimizer_params
@@ -111,6 +112,28 @@ class BatchedAPG:
         self.prm = prm
         assert L.load().sde4_apg_scratch_floats(C.byref(prm)) <= self.cand.numel()
 
+    def set_params(self, nn_params):
+        """New parameter values for the next solves.  The packed block is copied INTO this solver's device buffer, so a
+        captured CUDA graph (which holds that buffer's address) stays valid."""
+        pk = self.eng.packed(nn_params)
+        if pk.fingerprint != self.pk.fingerprint:
+            self.pk.assign(pk)
+        return self
+
+    def _workspace(self):
+        """Scratch of the cost launches, owned by this solver: the CUDA graph of an iteration bakes its address in, so
+        it must not be the engine's shared grow-only buffer (a later, larger call elsewhere would replace that one and
+        leave the graph pointing at freed memory)."""
+        if self._ws is None:
+            lib, d, ns = L.load(), C.byref(self.eng.desc), self.stage.desc.n_slack
+            P, K = self.P, self.K
+            need = 1 << 16
+            for probs, grad in ((K * P, False), (2 * P, True), (P, True), ((self.Q * P) if self.speculative else P, True)):
+                need = max(need, lib.sde4_cost_workspace_bytes(d, probs, self.N, self.H, ns, int(grad), 0))
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.y0.device if getattr(self, "y0", None) is not None
+                                   else torch.device("cuda", torch.cuda.current_device()))
+        return self._ws
+
     def _pm_view(self, buf):
         """[H, n, Q] problem-minor buffer -> [Q, H, n] strided view the cost launcher accepts."""
         return buf.permute(2, 0, 1)
@@ -119,7 +142,8 @@ class BatchedAPG:
         self.eng.cost_grad(self.pk, self.y0, self._pm_view(buf), self.ts, self.xref, self.stage.desc,
                            terminal=None if self.terminal is None else self.terminal.desc, key=self.keys, N=self.N,
                            want_grad=grad_buf is not None, grad_out=None if grad_buf is None else self._pm_view(grad_buf),
-                           lanes=self.lanes.get(which, 0), data_mod=data_mod, cost_out=cost_out, problem_mask=mask)
+                           lanes=self.lanes.get(which, 0), data_mod=data_mod, cost_out=cost_out, problem_mask=mask,
+                           workspace=self._workspace())
 
     # ------------------------------------------------------------------
     def init(self, x0, y0, xref, keys, momentum=None, stepsize=None):
@@ -131,6 +155,7 @@ class BatchedAPG:
         if self.P != P:
             self._alloc(P, dev)
             self._graph = None
+            self._ws = None
         # persistent input buffers: a captured CUDA graph keeps pointing at them across init() calls
         xref_t, keys_t = as_f32(xref).contiguous(), as_key(keys).reshape(-1, 2)
         if getattr(self, "y0", None) is None or self.y0.shape != y0.shape or self.xref.shape != xref_t.shape \

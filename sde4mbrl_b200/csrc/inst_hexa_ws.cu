@@ -1,0 +1,34 @@
+// inst_hexa_ws.cu -- warp-specialised cost + gradient kernels (kernels_ws.cuh) of the multirotor SDE architectures
+// whose single-problem launches are bound by the serial instruction chain (BASELINE configs[2]).
+#include "kernels_ws.cuh"
+#include "registry.cuh"
+namespace sde4 {
+using ResF = Net<3, 8, 16, 3, TANH>;
+using ResM = Net<6, 8, 16, 3, TANH>;
+using HexaD32s = Arch<SDE4_MODEL_ROTOR, 13, 6, SDE4_ROTOR_AERO_DRAG, Net<6, 32, 32, 1, SWISH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
+using HexaD16t = Arch<SDE4_MODEL_ROTOR, 13, 6, SDE4_ROTOR_AERO_DRAG, Net<6, 16, 16, 1, TANH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
+using IrisD32s = Arch<SDE4_MODEL_ROTOR, 13, 4, SDE4_ROTOR_AERO_DRAG, Net<6, 32, 32, 1, SWISH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
+
+template <class MA, class MB>
+cudaError_t launch_cost_ws_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td, const CostK& a,
+                             int dev, cudaStream_t s) {
+  using Cfg = WsCfg<MA, MB>;
+  const size_t sm = Cfg::smem_bytes();
+  static DevOnce once;
+  if (once.need(dev)) {
+    cudaFuncSetAttribute(k_cost_ws<MA, MB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<MA, MB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    once.mark(dev);
+  }
+  const int blocks = (a.G + Cfg::NPART - 1) / Cfg::NPART;
+  const bool plain = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
+  if (plain) k_cost_ws<MA, MB, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a);
+  else k_cost_ws<MA, MB, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a);
+  return cudaGetLastError();
+}
+
+#define SDE4_REGISTER_WS(NAME, ARCH, LA, LB)                                                                      \
+  static WsRegistrar wsreg_##NAME(WsEntry{#NAME, &ARCH::matches, LB,                                              \
+                                          &launch_cost_ws_t<RotorModel<ARCH, EvL<LA>>, RotorModel<ARCH, EvL<LB>>>});
+SDE4_REGISTER_WS(hexa_d32_swish, HexaD32s, 8, 8)
+}  // namespace sde4

@@ -561,8 +561,65 @@ struct RotorModel {
     f[9] = 0.5f * qd.z;
   }
 
+  // Cotangent-independent half of drift_vjp for the warp-specialised kernels (kernels_ws.cuh): the forward passes of
+  // the two residual networks at x_t.  What the cotangent-dependent half needs of them is the residual force itself
+  // and act' of the hidden units this lane owns.
+  static constexpr int TB1A = HAS_F ? Ev_::L > 1 ? (NetA::H1 + Ev_::L - 1) / Ev_::L : NetA::H1 : 1;
+  static constexpr int TB2A = HAS_F ? Ev_::L > 1 ? (NetA::H2 + Ev_::L - 1) / Ev_::L : NetA::H2 : 1;
+  static constexpr int TB1B = HAS_M ? Ev_::L > 1 ? (NetB::H1 + Ev_::L - 1) / Ev_::L : NetB::H1 : 1;
+  static constexpr int TB2B = HAS_M ? Ev_::L > 1 ? (NetB::H2 + Ev_::L - 1) / Ev_::L : NetB::H2 : 1;
+  struct DriftTape {
+    float Fb[3];                  // residual force (network output only)
+    float dA1[TB1A], dA2[TB2A];   // act' of the own hidden units, res_forces
+    float dB1[TB1B], dB2[TB2B];   // res_moments
+  };
+  SDE4_DEV static void drift_prep(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
+                                  DriftTape& tp) {
+    static_assert(Ev_::L > 1, "tape split is a lane-split evaluator feature");
+    const Quat q{x[6], x[7], x[8], x[9]};
+    const Quat t1 = qmul_vq(x[3], x[4], x[5], q);
+    const Quat r1 = qmul(qconj(q), t1);
+    const float vb[3] = {r1.x, r1.y, r1.z};
+    float in6[6];
+    nn_features(x, d, vb, in6);
+    tp.Fb[0] = tp.Fb[1] = tp.Fb[2] = 0.0f;
+    if constexpr (HAS_F) {
+      float in[NetA::IN > 0 ? NetA::IN : 1];
+#pragma unroll
+      for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
+      Ev::template fwd<NetA, true>(A::template ref<1, Ev::L>(W), sc, in, tp.Fb);
+#pragma unroll
+      for (int m = 0; m < TB1A; ++m) tp.dA1[m] = sc.d1[m];
+#pragma unroll
+      for (int m = 0; m < TB2A; ++m) tp.dA2[m] = sc.d2[m];
+    }
+    if constexpr (HAS_M) {
+      float in[NetB::IN > 0 ? NetB::IN : 1], out[3];
+#pragma unroll
+      for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
+      Ev::template fwd<NetB, true>(A::template ref<2, Ev::L>(W), sc, in, out);
+#pragma unroll
+      for (int m = 0; m < TB1B; ++m) tp.dB1[m] = sc.d1[m];
+#pragma unroll
+      for (int m = 0; m < TB2B; ++m) tp.dB2[m] = sc.d2[m];
+    }
+  }
+  // cotangent-dependent half: drift_vjp with the network forward passes replaced by the tape
+  SDE4_DEV static void drift_apply(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
+                                   const float (&u)[NU], const Scaled<NX>& vf, const DriftTape& tp, float (&gx)[NX],
+                                   float (&gu)[NU]) {
+    drift_vjp_impl<true>(W, sc, d, x, u, vf, &tp, gx, gu);
+  }
   SDE4_DEV static void drift_vjp(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
                                  const float (&u)[NU], const Scaled<NX>& vf, float (&gx)[NX], float (&gu)[NU]) {
+    drift_vjp_impl<false>(W, sc, d, x, u, vf, nullptr, gx, gu);
+  }
+
+  template <bool FROM_TAPE>
+  SDE4_DEV static void drift_vjp_impl(const float* W, Ctx& sc, const sde4_model_desc& d, const float (&x)[NX],
+                                      const float (&u)[NU], const Scaled<NX>& vf, const DriftTape* tp, float (&gx)[NX],
+                                      float (&gu)[NU]) {
+    static_assert(!(FROM_TAPE && Ev::PGRAD), "the training kernels evaluate the networks in place");
     const float* __restrict__ S = W + A::OFF_SCALARS;
     const Quat q{x[6], x[7], x[8], x[9]};
     const Quat qc = qconj(q);
@@ -624,7 +681,17 @@ struct RotorModel {
       float in[NetA::IN > 0 ? NetA::IN : 1], gi[NetA::IN > 0 ? NetA::IN : 1], out[3];
 #pragma unroll
       for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      Ev::template fwd<NetA, true>(A::template ref<1, Ev::L>(W), sc, in, out);
+      if constexpr (FROM_TAPE) {
+        out[0] = tp->Fb[0];
+        out[1] = tp->Fb[1];
+        out[2] = tp->Fb[2];
+#pragma unroll
+        for (int m = 0; m < TB1A; ++m) sc.d1[m] = tp->dA1[m];
+#pragma unroll
+        for (int m = 0; m < TB2A; ++m) sc.d2[m] = tp->dA2[m];
+      } else {
+        Ev::template fwd<NetA, true>(A::template ref<1, Ev::L>(W), sc, in, out);
+      }
       Fb[0] = out[0];
       Fb[1] = out[1];
       Fb[2] = out[2];
@@ -667,7 +734,13 @@ struct RotorModel {
       float in[NetB::IN > 0 ? NetB::IN : 1], gi[NetB::IN > 0 ? NetB::IN : 1];
 #pragma unroll
       for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      if constexpr (Ev::PGRAD) {
+      if constexpr (FROM_TAPE) {
+#pragma unroll
+        for (int m = 0; m < TB1B; ++m) sc.d1[m] = tp->dB1[m];
+#pragma unroll
+        for (int m = 0; m < TB2B; ++m) sc.d2[m] = tp->dB2[m];
+        Ev::template bwd<NetB>(A::template ref<2, Ev::L>(W), sc, gM, gi);
+      } else if constexpr (Ev::PGRAD) {
         Ev::template fwd<NetB, true>(A::template ref<2, Ev::L>(W), sc, in, Mt);
         Ev::template bwd<NetB>(A::template ref<2, Ev::L>(W), sc, gM, gi);
       } else {

@@ -33,6 +33,35 @@ struct ArchEntry {
 
 std::vector<ArchEntry>& arch_table();
 
+// warp-specialised cost + gradient kernels (kernels_ws.cuh), registered per architecture from their own translation
+// units; looked up by descriptor at dispatch time
+struct WsEntry {
+  const char* name;
+  bool (*matches)(const sde4_model_desc&);
+  int lanes_c;  // lanes per particle of the role that emits the partials (sizes the partial buffers)
+  cudaError_t (*launch)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&, int dev,
+                        cudaStream_t);
+};
+std::vector<WsEntry>& ws_table();
+struct WsRegistrar {
+  explicit WsRegistrar(const WsEntry& e) { ws_table().push_back(e); }
+};
+
+// cudaFuncSetAttribute is per device and per function: remember which devices a function has been configured on
+// (bit mask, relaxed atomics: setting the attribute twice is harmless, skipping it is not)
+struct DevOnce {
+  unsigned long long done = 0;
+  bool need(int dev) const { return dev < 0 || dev >= 64 || !((__atomic_load_n(&done, __ATOMIC_RELAXED) >> dev) & 1ull); }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 64) __atomic_fetch_or(&done, 1ull << dev, __ATOMIC_RELAXED);
+  }
+};
+inline int current_device() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  return dev;
+}
+
 // dynamic shared memory: parameter image + derived constants + per-thread scratch columns
 template <class M>
 constexpr size_t smem_bytes(int threads, bool backward = true) {
@@ -46,10 +75,13 @@ template <class M>
 cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
   const size_t sm = smem_bytes<M>(threads, false);
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int dev = current_device();
+  static DevOnce attr_set;
+  if (attr_set.need(dev)) {
     cudaFuncSetAttribute(k_rollout<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256, false));
-    attr_set = true;
+    if constexpr (M::Ev::L > 1)
+      cudaFuncSetAttribute(k_rollout<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256, false));
+    attr_set.mark(dev);
   }
   if constexpr (M::Ev::L > 1) {
     if (a.noise_mode == SDE4_NOISE_THREEFRY && a.solver == SDE4_SOLVER_EULER_MARUYAMA) {  // pipelined-noise instantiation
@@ -58,11 +90,11 @@ cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int bl
     }
   }
   if (a.solver != SDE4_SOLVER_EULER_MARUYAMA) {
-    static bool attr_set2 = false;
-    if (!attr_set2) {
+    static DevOnce attr_set2;
+    if (attr_set2.need(dev)) {
       cudaFuncSetAttribute(k_rollout<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                            (int)smem_bytes<M>(256, false));
-      attr_set2 = true;
+      attr_set2.mark(dev);
     }
     k_rollout<M, false, true><<<blocks, threads, sm, s>>>(d, a);
     return cudaGetLastError();
@@ -76,14 +108,15 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
                           const CostK& a, bool grad, bool constr, int blocks, int threads, cudaStream_t s) {
   using A = typename M::A;
   const size_t sm = smem_bytes<M>(threads, grad);
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int dev = current_device();
+  static DevOnce attr_set;
+  if (attr_set.need(dev)) {
     const int mx = (int)smem_bytes<M>(256);
     cudaFuncSetAttribute(k_cost<M, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_cost<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_cost<M, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
     cudaFuncSetAttribute(k_cost<M, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-    attr_set = true;
+    attr_set.mark(dev);
   }
   if constexpr (M::Ev::L > 1) {
     if (a.noise_mode == SDE4_NOISE_THREEFRY && (!grad || a.dwbuf)) {
@@ -130,14 +163,14 @@ cudaError_t launch_cost_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
     else if constexpr (M::NX == 4) plain1 = cd.kind == SDE4_COST_QUADRATIC && cd.feat == 1 && !cd.use_res_sig;
     else plain1 = cd.kind == SDE4_COST_QUADRATIC && cd.feat == 0 && !cd.use_res_sig;
     if (plain1) {
-      static bool attr3 = false;
-      if (!attr3) {
+      static DevOnce attr3;
+      if (attr3.need(dev)) {
         const int mx = (int)smem_bytes<M>(256);
         cudaFuncSetAttribute(k_cost<M, true, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k_cost<M, true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k_cost<M, false, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
         cudaFuncSetAttribute(k_cost<M, false, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
-        attr3 = true;
+        attr3.mark(dev);
       }
       if (grad) {
         if (constr)
@@ -179,10 +212,11 @@ cudaError_t launch_loss_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
       return cudaGetLastError();
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int dev = current_device();
+  static DevOnce attr_set;
+  if (attr_set.need(dev)) {
     cudaFuncSetAttribute(k_cost<M, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256));
-    attr_set = true;
+    attr_set.mark(dev);
   }
   k_cost<M, true, false><<<blocks, threads, sm, s>>>(d, cd, td, a);
   return cudaGetLastError();

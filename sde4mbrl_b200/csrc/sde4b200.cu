@@ -13,6 +13,11 @@ std::vector<ArchEntry>& arch_table() {
   return table;
 }
 
+std::vector<WsEntry>& ws_table() {
+  static std::vector<WsEntry> table;
+  return table;
+}
+
 static thread_local char g_err[512] = "";
 
 static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
@@ -24,6 +29,25 @@ static const ArchEntry* find_arch(const sde4_model_desc& d) {
   for (const ArchEntry& e : arch_table())
     if (e.matches(d)) return &e;
   return nullptr;
+}
+static const WsEntry* find_ws(const sde4_model_desc& d) {
+  for (const WsEntry& e : ws_table())
+    if (e.matches(d)) return &e;
+  return nullptr;
+}
+
+// number of SMs of the current device (queried once per device; 148 on a B200)
+static int sm_count() {
+  static int cached[64] = {0};
+  const int dev = current_device();
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) return cached[dev];
+  int n = 0;
+  if (dev < 0 || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+    (void)cudaGetLastError();
+    return 148;
+  }
+  if (dev < 64) cached[dev] = n;
+  return n;
 }
 
 static std::string describe(const sde4_model_desc& d) {
@@ -40,9 +64,10 @@ static std::string describe(const sde4_model_desc& d) {
 
 static int pick_threads(int requested, long long threads_total) {
   if (requested > 0) return requested;
-  // few threads: one warp per CTA so the warps spread over all 148 SMs; many: fatter CTAs
-  if (threads_total <= 148LL * 32 * 8) return 32;
-  if (threads_total <= 148LL * 64 * 8) return 64;
+  // few threads: one warp per CTA so the warps spread over all SMs; many: fatter CTAs
+  const long long sms = sm_count();
+  if (threads_total <= sms * 32 * 8) return 32;
+  if (threads_total <= sms * 64 * 8) return 64;
   return 128;
 }
 
@@ -201,7 +226,9 @@ size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_
   if (!e) return 0;
   // worst case over noise modes (threefry keeps a dw buffer)
   size_t a = cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY, 1).total;
-  for (int l = 2; l <= max_lanes(*e); l *= 2) {
+  int lmax = max_lanes(*e);
+  if (const WsEntry* ws = find_ws(*model)) lmax = ws->lanes_c > lmax ? ws->lanes_c : lmax;
+  for (int l = 2; l <= lmax; l *= 2) {
     size_t b = cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY, l).total;
     if (b > a) a = b;
   }
@@ -378,9 +405,24 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     if (!e->launch_loss) return fail(SDE4_ERR_UNSUPPORTED, "no training-loss kernel compiled for %s", e->name);
     if (constr || cd.kind != SDE4_COST_QUADRATIC || a->xtraj) return fail(SDE4_ERR_INVALID, "training loss: QUADRATIC data cost, no constraints, no xtraj");
   }
+  // warp-specialised value + gradient kernel (kernels_ws.cuh): on request, or by itself while the launch is bound by
+  // the serial instruction chain of a step (the regime where the widest lane split would be chosen)
+  const WsEntry* wse = nullptr;
+  {
+    const bool ws_ok = !lo.enabled && a->grad != nullptr && !constr && a->noise_mode == SDE4_NOISE_THREEFRY;
+    if (a->lanes == SDE4_LANES_WS) {
+      wse = ws_ok ? find_ws(*model) : nullptr;
+      if (!wse)
+        return fail(SDE4_ERR_UNSUPPORTED, "no warp-specialised kernel for this call (%s; needs value + gradient, "
+                    "threefry noise, no state constraints)", e->name);
+    } else if (a->lanes == 0 && ws_ok && G * 8 <= 40960) {
+      wse = find_ws(*model);
+    }
+  }
   // training loss: the lane-split kernel while the minibatch is latency bound (G*L <= 64 k threads)
-  const int lanes = lo.enabled ? ((e->launch_loss_ls && a->lanes != 1 && G * e->loss_lanes <= 65536) ? e->loss_lanes : 1)
-                               : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
+  const int lanes = wse ? wse->lanes_c
+                       : lo.enabled ? ((e->launch_loss_ls && a->lanes != 1 && G * e->loss_lanes <= 65536) ? e->loss_lanes : 1)
+                                    : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
   size_t dump_off[4] = {0, 0, 0, 0};
@@ -452,6 +494,8 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   if (lo.enabled) {
     err = cudaMemsetAsync(dump_base, 0, dump_bytes, s);  // rows of networks that are not evaluated (ODE mode) stay 0
     if (err == cudaSuccess) err = (lanes > 1 ? e->launch_loss_ls : e->launch_loss)(*model, cd, td, k, blocks, threads, s);
+  } else if (wse) {
+    err = wse->launch(*model, cd, td, k, current_device(), s);
   } else {
     err = e->launch_cost[ilog2(lanes)](*model, cd, td, k, grad, constr, blocks, threads, s);
   }
@@ -539,10 +583,11 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     wk.partial = (float*)(ws + L.total + ((dump_bytes + 255) & ~(size_t)255));
     if (pair0 != loss_wgrad_pairs(*e)) return fail(SDE4_ERR_INVALID, "internal: wgrad pair count");
     const size_t slab = (size_t)max_rows * (WG_KC + 1) * sizeof(float);
-    static bool wg_attr = false;
-    if (!wg_attr) {
+    static DevOnce wg_attr;
+    const int wg_dev = current_device();
+    if (wg_attr.need(wg_dev)) {
       cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(66 * (WG_KC + 1) * sizeof(float)));
-      wg_attr = true;
+      wg_attr.mark(wg_dev);
     }
     k_wgrad_partial<<<dim3(wk.n_chunks, wk.n_tasks), 256, slab, s>>>(wk);
     k_wgrad_final<<<(wk.n_pairs + 255) / 256, 256, 0, s>>>(wk);

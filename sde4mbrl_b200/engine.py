@@ -4,6 +4,7 @@ steps and a grow-only workspace, and turns torch CUDA tensors into the pointer/s
 hot path happens inside ``libsde4b200.so``.
 """
 import ctypes as C
+import zlib
 
 import numpy as np
 import torch
@@ -90,13 +91,41 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def params_fingerprint(nn_params):
+    """CRC-32 over the leaves of a haiku-style parameter tree, in tree order (~8 us for the hexacopter's 32 leaves).
+    The engine caches the packed device block of the last tree it saw; a training loop that updates the leaves IN
+    PLACE keeps the same dict object, so identity alone would keep launching with the first values."""
+    c = 0
+    for mod in nn_params.values():
+        for leaf in (mod.values() if isinstance(mod, dict) else (mod,)):
+            try:
+                c = zlib.crc32(leaf, c)
+            except (TypeError, ValueError, BufferError):  # python scalars, CPU tensors, non-contiguous arrays
+                if isinstance(leaf, torch.Tensor):
+                    leaf = leaf.detach().cpu().numpy()
+                c = zlib.crc32(np.ascontiguousarray(np.asarray(leaf, dtype=np.float32)), c)
+    return c
+
+
 class PackedParams:
     """Device-resident packed parameter block (see ``sde4_param_layout``)."""
 
-    def __init__(self, model, nn_params, desc):
+    def __init__(self, model, nn_params, desc, fingerprint=None):
         self.host = model.pack(nn_params, desc)
         self.dev = torch.as_tensor(self.host, device=_dev())
         self.source = nn_params
+        self.fingerprint = params_fingerprint(nn_params) if fingerprint is None else fingerprint
+
+    def private_copy(self):
+        """A block with its own device buffer (for owners that bake the address into a CUDA graph)."""
+        c = PackedParams.__new__(PackedParams)
+        c.host, c.dev, c.source, c.fingerprint = self.host, self.dev.clone(), self.source, self.fingerprint
+        return c
+
+    def assign(self, other):
+        """Take the values of ``other`` while keeping this block's device buffer (and address)."""
+        self.dev.copy_(other.dev)
+        self.host, self.source, self.fingerprint = other.host, other.source, other.fingerprint
 
 
 class Engine:
@@ -120,11 +149,19 @@ class Engine:
 
     # ---- parameters -----------------------------------------------------
     def packed(self, nn_params):
+        """Device block of ``nn_params``.  Cached for the last tree seen, keyed on the tree's identity AND a CRC of its
+        leaves, so leaves updated in place are re-packed (a ``PackedParams`` passes through untouched)."""
         if isinstance(nn_params, PackedParams):
             return nn_params
-        if self._packed is None or self._packed.source is not nn_params:
-            self._packed = PackedParams(self.model, nn_params, self.desc)
-        return self._packed
+        fp = params_fingerprint(nn_params)
+        pk = self._packed
+        if pk is None or pk.source is not nn_params or pk.fingerprint != fp:
+            self._packed = pk = PackedParams(self.model, nn_params, self.desc, fp)
+        return pk
+
+    def invalidate_params(self):
+        """Forget the cached parameter block (the next call packs and uploads again)."""
+        self._packed = None
 
     def dt_tensor(self, dt):
         hit = self._dt_last
@@ -208,7 +245,8 @@ class Engine:
     # ---- K2 + K3 ----------------------------------------------------------
     def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,
                   noise_mode=None, want_grad=True, want_xtraj=False, block_threads=0, grad_out=None,
-                  particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None, problem_mask=None):
+                  particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None, problem_mask=None,
+                  workspace=None):
         """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
         Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
         self._em_only()
@@ -244,12 +282,25 @@ class Engine:
             ws_bytes = lib.sde4_cost_workspace_bytes(C.byref(self.desc), P, N, H, stage.n_slack, int(want_grad),
                                                      int(want_xtraj))
             self._ws_bytes[wkey] = ws_bytes
-        ws = self.workspace(ws_bytes)
+        if workspace is None:
+            ws = self.workspace(ws_bytes)
+        else:  # caller-owned scratch (a CUDA graph bakes its address in: it must not be the engine's grow-only one)
+            ws = workspace
+            if ws.numel() * ws.element_size() < ws_bytes:
+                raise Sde4Error("caller-supplied workspace too small: %d < %d bytes" % (ws.numel() * ws.element_size(), ws_bytes))
         cost = torch.empty(P, dtype=torch.float32, device=y0.device) if cost_out is None else cost_out
         grad = None
         if want_grad:
-            grad = torch.empty_strided(opt.shape, opt.stride(), dtype=torch.float32, device=y0.device) \
-                if grad_out is None else grad_out
+            if grad_out is None:
+                grad = torch.empty_strided(opt.shape, opt.stride(), dtype=torch.float32, device=y0.device)
+            else:
+                # K3 writes the gradient with opt's element strides (misc_kernels.cuh): the output must be laid out alike
+                grad = grad_out.unsqueeze(0) if (squeeze and grad_out.dim() == 2) else grad_out
+                if tuple(grad.shape) != tuple(opt.shape) or tuple(grad.stride()) != tuple(opt.stride()):
+                    opt = opt.contiguous()
+                    if tuple(grad.shape) != tuple(opt.shape) or tuple(grad.stride()) != tuple(opt.stride()):
+                        raise Sde4Error("grad_out must have the shape and strides of opt (got %s/%s vs %s/%s)" % (
+                            tuple(grad.shape), tuple(grad.stride()), tuple(opt.shape), tuple(opt.stride())))
         xtraj = torch.empty((H + 1, self.n_x + 1, G), dtype=torch.float32, device=y0.device) if want_xtraj else None
         if noise_mode is None:
             noise_mode = L.NOISE_GIVEN if noise is not None else (L.NOISE_THREEFRY if self.noisy else L.NOISE_NONE)
@@ -275,7 +326,7 @@ class Engine:
         a.stage = C.pointer(stage)
         a.terminal = C.pointer(terminal) if terminal is not None else None
         a.cost, a.grad, a.xtraj = _ptr(cost), _ptr(grad), _ptr(xtraj)
-        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel()
+        a.workspace, a.workspace_bytes = _ptr(ws), ws.numel() * ws.element_size()
         a.block_threads = block_threads
         a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
         a.data_mod = data_mod
@@ -350,6 +401,7 @@ class Engine:
         grad = np.empty_like(opt3) if want_grad else None
         xtraj = torch.empty((H + 1, self.n_x + 1, P * N), dtype=torch.float32, device=dev) if want_xtraj else None
         a.params, a.y0, a.opt, a.xref = pk.dev.data_ptr(), y0.ctypes.data, opt3.ctypes.data, xref.ctypes.data
+        a.dt = dt_t.data_ptr()  # the plan is keyed on the call shape only: a different time-step array with the same H
         a.key = keyh.ctypes.data if keyed else None
         a.rng_mode = self.rng_mode
         a.cost, a.grad = cost.ctypes.data, (grad.ctypes.data if want_grad else None)

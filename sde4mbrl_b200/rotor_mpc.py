@@ -225,10 +225,13 @@ def _device_solver(multi_cost_sampling, cfg_dict, _sde_learned, stage, term, box
     from .apg_batched import BatchedAPG
     import json
     op = cfg_dict["apg_mpc"]
-    key = (bytes(stage.desc), None if term is None else bytes(term.desc), json.dumps(op, sort_keys=True, default=float),
-           id(_sde_learned))
+    # keyed on everything that shapes the solver; the parameter VALUES are refreshed below on every call (a tree whose
+    # leaves were updated in place, or a new tree of the same architecture, reuses the solver and its CUDA graph)
+    key = (bytes(stage.desc), None if term is None else bytes(term.desc), json.dumps(op, sort_keys=True, default=float))
     cache = multi_cost_sampling.__dict__.setdefault("_device_solvers", {})
     solver = cache.get(key)
+    if solver is not None:
+        solver.set_params(_sde_learned)
     if solver is None:
         lb = ub = None
         if box is not None:
