@@ -404,11 +404,21 @@ struct EvLT {
   SDE4_DEV static void all_gather(const float (&own)[B], float (&all)[B * L]) {
 #pragma unroll
     for (int m = 0; m < B; ++m) all[m] = own[m];
+#ifdef SDE4_GATHER_BUTTERFLY
 #pragma unroll
     for (int mask = 1, n = B; mask < L; mask <<= 1, n <<= 1) {
 #pragma unroll
       for (int q = 0; q < n; ++q) all[n + q] = __shfl_xor_sync(0xffffffffu, all[q], mask);
     }
+#else
+    // every block straight from its owner: the same (L-1)*B shuffles as the doubling butterfly, but none of them
+    // depends on another one (one shuffle latency on the critical path instead of log2(L))
+#pragma unroll
+    for (int q = 1; q < L; ++q) {
+#pragma unroll
+      for (int m = 0; m < B; ++m) all[q * B + m] = __shfl_xor_sync(0xffffffffu, own[m], q);
+    }
+#endif
   }
   // layer 2, OUTPUT split: gather all of h1 (SHFL.BFLY), every lane forms its own block of outputs
   //   a2own[m] = b1[l*B2+m] + sum_i h1[i] * w1[i][l*B2+m]

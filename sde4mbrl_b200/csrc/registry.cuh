@@ -38,9 +38,9 @@ std::vector<ArchEntry>& arch_table();
 struct WsEntry {
   const char* name;
   bool (*matches)(const sde4_model_desc&);
-  int lanes_c;  // lanes per particle of the role that emits the partials (sizes the partial buffers)
-  cudaError_t (*launch)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&, int dev,
-                        cudaStream_t);
+  int npart;  // particles per CTA = samples per cost / gradient partial (sizes the partial buffers)
+  cudaError_t (*launch)(const sde4_model_desc&, const sde4_cost_desc&, const sde4_cost_desc&, const CostK&, float* ftape,
+                        int dev, cudaStream_t);
 };
 std::vector<WsEntry>& ws_table();
 struct WsRegistrar {

@@ -1,5 +1,6 @@
 // sde4b200.cu -- C-ABI of libsde4b200.so (see include/sde4b200.h for the contract).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "registry.cuh"
@@ -30,10 +31,20 @@ static const ArchEntry* find_arch(const sde4_model_desc& d) {
     if (e.matches(d)) return &e;
   return nullptr;
 }
+// first registered variant of the architecture; SDE4_WS_NPART (environment, tuning experiments only) picks another
+// particles-per-CTA variant when one is compiled
 static const WsEntry* find_ws(const sde4_model_desc& d) {
-  for (const WsEntry& e : ws_table())
-    if (e.matches(d)) return &e;
-  return nullptr;
+  static const int want = [] {
+    const char* v = getenv("SDE4_WS_NPART");
+    return v ? atoi(v) : 0;
+  }();
+  const WsEntry* first = nullptr;
+  for (const WsEntry& e : ws_table()) {
+    if (!e.matches(d)) continue;
+    if (want > 0 && e.npart == want) return &e;
+    if (!first) first = &e;
+  }
+  return first;
 }
 
 // number of SMs of the current device (queried once per device; 148 on a B200)
@@ -104,12 +115,14 @@ static sde4_cost_desc empty_cost() {
 }
 
 struct CostLayout {
-  size_t xbuf, dwbuf, auxbuf, gpart, cpart, total;
+  size_t xbuf, dwbuf, auxbuf, gpart, cpart, ftape, total;
   int PW, NP, warp_reduce;
 };
 
+// lanes: lanes per sample of the kernel that writes the partials (32 / lanes samples share one partial when they all
+// belong to one problem); ws: the warp-specialised kernel also keeps the residual-net inputs of every step
 static CostLayout cost_layout(const ArchEntry& e, int P, int N, int H, int n_slack, bool grad, bool have_xtraj,
-                              int noise_mode, int lanes) {
+                              int noise_mode, int lanes, bool ws = false) {
   CostLayout L;
   const size_t G = (size_t)P * N;
   const int spw = 32 / lanes;  // samples per warp
@@ -128,6 +141,8 @@ static CostLayout cost_layout(const ArchEntry& e, int P, int N, int H, int n_sla
   if (grad) off += al((size_t)H * (e.nu + n_slack) * L.PW * 4);
   L.cpart = off;
   off += al((size_t)L.PW * 4);
+  L.ftape = off;
+  if (ws) off += al((size_t)H * 6 * G * 4);
   L.total = off;
   return L;
 }
@@ -226,11 +241,15 @@ size_t sde4_cost_workspace_bytes(const sde4_model_desc* model, int32_t P, int32_
   if (!e) return 0;
   // worst case over noise modes (threefry keeps a dw buffer)
   size_t a = cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY, 1).total;
-  int lmax = max_lanes(*e);
-  if (const WsEntry* ws = find_ws(*model)) lmax = ws->lanes_c > lmax ? ws->lanes_c : lmax;
-  for (int l = 2; l <= lmax; l *= 2) {
+  for (int l = 2; l <= max_lanes(*e); l *= 2) {
     size_t b = cost_layout(*e, P, N, H, n_slack, want_grad != 0, have_xtraj != 0, SDE4_NOISE_THREEFRY, l).total;
     if (b > a) a = b;
+  }
+  if (const WsEntry* ws = find_ws(*model)) {
+    if (want_grad) {
+      size_t b = cost_layout(*e, P, N, H, n_slack, true, have_xtraj != 0, SDE4_NOISE_THREEFRY, 32 / ws->npart, true).total;
+      if (b > a) a = b;
+    }
   }
   return a;
 }
@@ -420,11 +439,11 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     }
   }
   // training loss: the lane-split kernel while the minibatch is latency bound (G*L <= 64 k threads)
-  const int lanes = wse ? wse->lanes_c
+  const int lanes = wse ? 32 / wse->npart
                        : lo.enabled ? ((e->launch_loss_ls && a->lanes != 1 && G * e->loss_lanes <= 65536) ? e->loss_lanes : 1)
                                     : pick_lanes(*e, a->lanes, G, a->grad != nullptr);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
-  const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes);
+  const CostLayout L = cost_layout(*e, a->P, a->N, a->H, cd.n_slack, grad, a->xtraj != nullptr, a->noise_mode, lanes, wse != nullptr);
   size_t dump_off[4] = {0, 0, 0, 0};
   const size_t Kcols = (size_t)G * a->H;
   const size_t dump_bytes = lo.enabled ? loss_dump_floats(*e, Kcols, dump_off) * 4 : 0;
@@ -495,7 +514,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     err = cudaMemsetAsync(dump_base, 0, dump_bytes, s);  // rows of networks that are not evaluated (ODE mode) stay 0
     if (err == cudaSuccess) err = (lanes > 1 ? e->launch_loss_ls : e->launch_loss)(*model, cd, td, k, blocks, threads, s);
   } else if (wse) {
-    err = wse->launch(*model, cd, td, k, current_device(), s);
+    err = wse->launch(*model, cd, td, k, (float*)(ws + L.ftape), current_device(), s);
   } else {
     err = e->launch_cost[ilog2(lanes)](*model, cd, td, k, grad, constr, blocks, threads, s);
   }
