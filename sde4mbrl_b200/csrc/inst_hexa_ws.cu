@@ -9,27 +9,35 @@ using HexaD32s = Arch<SDE4_MODEL_ROTOR, 13, 6, SDE4_ROTOR_AERO_DRAG, Net<6, 32, 
 using HexaD16t = Arch<SDE4_MODEL_ROTOR, 13, 6, SDE4_ROTOR_AERO_DRAG, Net<6, 16, 16, 1, TANH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
 using IrisD32s = Arch<SDE4_MODEL_ROTOR, 13, 4, SDE4_ROTOR_AERO_DRAG, Net<6, 32, 32, 1, SWISH>, ROTOR_NOISE_MASK, ROTOR_NOISE_MASK, true, ResF, 0x7, ResM, 0x3F>;
 
-template <class A, int NPART>
+template <class A>
 cudaError_t launch_cost_ws_t(const sde4_model_desc& d, const sde4_cost_desc& cd, const sde4_cost_desc& td, const CostK& a,
                              float* ftape, int dev, cudaStream_t s) {
-  using Cfg = WsCfg<A, NPART>;
+  using Cfg = WsCfg<A>;
   const size_t sm = Cfg::smem_bytes();
   static DevOnce once;
   if (once.need(dev)) {
-    cudaFuncSetAttribute(k_cost_ws<A, NPART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_cost_ws<A, NPART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     once.mark(dev);
   }
-  const int blocks = (a.G + NPART - 1) / NPART;
+  const int blocks = (a.G + Cfg::NPART - 1) / Cfg::NPART;
   const bool plain = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
-  if (plain) k_cost_ws<A, NPART, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
-  else k_cost_ws<A, NPART, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+  if (plain) k_cost_ws<A, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+  else k_cost_ws<A, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
   return cudaGetLastError();
 }
 
-#define SDE4_REGISTER_WS(NAME, ARCH, NPART) \
-  static WsRegistrar wsreg_##NAME##_##NPART(WsEntry{#NAME, &ARCH::matches, NPART, &launch_cost_ws_t<ARCH, NPART>});
-SDE4_REGISTER_WS(hexa_d32_swish, HexaD32s, 16)
-SDE4_REGISTER_WS(hexa_d32_swish, HexaD32s, 32)
-SDE4_REGISTER_WS(hexa_d32_swish, HexaD32s, 8)
+#define SDE4_REGISTER_WS(NAME, ARCH) \
+  static WsRegistrar wsreg_##NAME(WsEntry{#NAME, &ARCH::matches, WsCfg<ARCH>::NPART, &launch_cost_ws_t<ARCH>});
+SDE4_REGISTER_WS(hexa_d32_swish, HexaD32s)
 }  // namespace sde4
+#ifdef SDE4_WS_TRACE
+extern "C" int sde4_debug_ws_trace(long long* out /*[4][1024]*/, int* counts /*[4]*/) {
+  int zero[4] = {0, 0, 0, 0};
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, sde4::g_ws_trace, sizeof(long long) * 4 * 1024);
+  cudaMemcpyFromSymbol(counts, sde4::g_ws_trace_n, sizeof(int) * 4);
+  cudaMemcpyToSymbol(sde4::g_ws_trace_n, zero, sizeof(zero));
+  return 0;
+}
+#endif

@@ -6,21 +6,22 @@
 // jax.value_and_grad, sde4mbrl/apg.py:82,224; drift sde_rotor_model.py:427-458), different mapping.  In the lane-split
 // kernels every one of the 8 lanes of a particle repeats the scalar work (quaternion physics, projection, stage cost,
 // address arithmetic): 40 % of the 289 M warp instructions of a C3 launch, eight times over
-// (profiles/r1_m_kcost_ncu.txt).  Here a CTA owns NPART particles and its warps have two ROLES:
+// (profiles/r1_m_kcost_ncu.txt).  Here a CTA owns 16 particles and its three warps have ROLES:
 //
 //   PHY   one warp, ONE LANE PER PARTICLE: the state x, the Euler-Maruyama update, projection, checkpoints, stage cost,
 //         and in the backward sweep the cotangent lambda and the whole physics adjoint -- nothing is replicated;
-//   DENS  NPART/4 warps, 8 lanes per particle (EvL<8>): the diffusion density network, the in-kernel threefry noise and
-//         sigma o dw; in the backward sweep the density value + input gradient (cotangent independent, so it runs one
-//         step ahead of the cotangent chain and never sits on it);
-//   RES   NPART/8 warps, 4 lanes per particle: the residual force and moment networks (forward; in the backward sweep
-//         their forward passes one step ahead, then the backward passes for the cotangents PHY hands over).
+//   DENS  one warp per 16 particles: the diffusion density network on the TENSOR CORES (mma.sync m16n8k8, 3xTF32,
+//         the 16 particles are the M rows; see MmaNet below); in the backward sweep the density value + input gradient
+//         (cotangent independent, so it runs one step ahead of the cotangent chain and never sits on it);
+//   RES   one warp per 16 particles: the residual force and moment networks on the tensor cores (forward; in the
+//         backward sweep their forward passes one step ahead, then the backward passes for the cotangents PHY hands
+//         over), the in-kernel threefry noise, and the fixed-order sum of the control-gradient rows over the CTA.
 //
 // PHY and the network roles alternate within a step -- v_b -> networks -> forces is a true dependency -- and meet at
-// two CTA-wide barriers per step, exchanging 12 + 19 floats (forward) / 6 + 19 floats (backward) per particle through
-// shared memory.
+// two CTA-wide barriers per step, exchanging a few dozen floats per particle through shared memory.
 //
-// (A first attempt with two symmetric 8-lane roles was slower than the one-role kernel: profiles/r2_a_ws_symmetric_ncu.txt.)
+// (Earlier attempts: two symmetric 8-lane roles, profiles/r2_a_ws_symmetric_ncu.txt; PHY + FP32 lane-split network roles,
+// profiles/r2_b_ws_fp32roles_ncu.txt -- the second one was bound by the LSU data pipe, hence the tensor cores.)
 #pragma once
 #include "kernels.cuh"
 
@@ -225,41 +226,392 @@ struct RotorSplit {
 };
 
 // ----------------------------------------------------------------------------------------------------------------
-template <class A_, int NPART_>
+// Tensor-core evaluation of hk.nets.MLP (two hidden layers) for 16 particles per warp.
+//
+// mma.sync.m16n8k8 (TF32 inputs, FP32 accumulate) with the 3xTF32 split a = a_hi + a_lo, b = b_hi + b_lo,
+// a*b ~ a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (relative error ~2^-21: inside the FP32 parity tolerance, unlike a single
+// TF32 product at 2^-11).  M = 16 particles (rows), N = units of the layer in tiles of 8, K = units of the layer below.
+// The accumulator tile of one layer IS the A operand of the next one: thread (g = lane/4, t = lane%4) holds columns
+// 2t, 2t+1 of rows g, g+8 of every 8-wide tile, and the A operand wants K-indices t, t+4 of the same rows -- so the
+// weight fragments are laid out with K relabelled (k = t -> unit 8j+2t, k = t+4 -> unit 8j+2t+1) and no value ever moves
+// between lanes or through shared memory between layers.  Weight fragments (hi | lo) are pre-split once per CTA into
+// a fragment image in shared memory, one LDS.128 per tile and thread: the FP32 lane-split evaluator pulled every
+// weight through LDS.128 once per 4 FMAs, which left the LSU data pipe 68-79 % busy (profiles/r2_b_ws_fp32roles_ncu.txt).
+// ----------------------------------------------------------------------------------------------------------------
+// x = hi + lo with hi on the TF32 grid.  hi is x with the 13 low mantissa bits cleared (one LOP3; cvt.rna.tf32.f32 is
+// emulated on sm_100a -- FSETP / SEL / IADD3 / LOP3 per value -- and rounding buys nothing here: x - hi is exact
+// either way); lo goes to the tensor core as the FP32 word, which reads its upper 19 bits, leaving a residual of
+// 2^-11 |lo| <= 2^-21 |x|, the same order as the dropped lo*lo product.
+SDE4_DEV void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+SDE4_DEV void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// A operand (hi | lo) of one k-step
+struct AFrag {
+  uint32_t hi[4], lo[4];
+  // from the inputs in the operand's own order: a0 (row g, k = t), a1 (row g+8, k = t), a2 (g, t+4), a3 (g+8, t+4)
+  SDE4_DEV void from_values(const float (&a)[4]) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) tf32_split(a[r], hi[r], lo[r]);
+  }
+  // from an accumulator tile (relabelled K): c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+  SDE4_DEV void from_tile(const float (&c)[4]) {
+    tf32_split(c[0], hi[0], lo[0]);
+    tf32_split(c[2], hi[1], lo[1]);
+    tf32_split(c[1], hi[2], lo[2]);
+    tf32_split(c[3], hi[3], lo[3]);
+  }
+};
+// Accumulator of one 16x8 output tile, one register tile per 3xTF32 term: the three products of a k-step go to
+// different accumulators, so the dependent MMA chain of a layer is its number of k-steps, not three times that
+// (the density value + gradient pass had 51 MMAs in a row on its critical path).
+#ifndef SDE4_WS_NACC
+#define SDE4_WS_NACC 1  // accumulator tiles per 3xTF32 term set (1: smallest code; 2 / 3: one tile per term)
+#endif
+#ifndef SDE4_WS_KSPLIT
+#define SDE4_WS_KSPLIT 0  // 1: even and odd k-steps of a layer accumulate into different tiles (half the dependent chain)
+#endif
+struct Acc3 {
+  float hh[4];
+#if SDE4_WS_NACC >= 2
+  float hl[4];
+#endif
+#if SDE4_WS_NACC >= 3
+  float lh[4];
+#endif
+  SDE4_DEV void init(float c0, float c1) {
+    hh[0] = hh[2] = c0;
+    hh[1] = hh[3] = c1;
+#if SDE4_WS_NACC >= 2
+#pragma unroll
+    for (int r = 0; r < 4; ++r) hl[r] = 0.0f;
+#endif
+#if SDE4_WS_NACC >= 3
+#pragma unroll
+    for (int r = 0; r < 4; ++r) lh[r] = 0.0f;
+#endif
+  }
+  // += A * B for one 8x8 weight tile (x, y = b0, b1 hi; z, w = b0, b1 lo); small terms first when they share a tile
+  SDE4_DEV void mma(const AFrag& a, const float4& b) {
+#if SDE4_WS_NACC >= 3
+    mma_tf32(hh, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+    mma_tf32(hl, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+    mma_tf32(lh, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+#elif SDE4_WS_NACC == 2
+    mma_tf32(hl, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+    mma_tf32(hh, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+    mma_tf32(hl, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+#else
+    mma_tf32(hh, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+    mma_tf32(hh, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+    mma_tf32(hh, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+#endif
+  }
+  SDE4_DEV void sum(float (&c)[4]) const {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#if SDE4_WS_NACC >= 3
+      c[r] = hh[r] + (hl[r] + lh[r]);
+#elif SDE4_WS_NACC == 2
+      c[r] = hh[r] + hl[r];
+#else
+      c[r] = hh[r];
+#endif
+    }
+  }
+};
+
+template <class N>
+struct MmaNet {
+  static constexpr int NT1 = N::H1 / 8, NT2 = N::H2 / 8;
+  static_assert(N::H1 % 8 == 0 && N::H2 % 8 == 0 && N::IN <= 8 && N::OUT <= 4, "tile shapes of the tensor-core evaluator");
+  // tiles of the fragment image, in this order
+  static constexpr int T_L1 = 0, T_L2 = T_L1 + NT1, T_L3 = T_L2 + NT1 * NT2, T_W2T = T_L3 + NT2, T_W1T = T_W2T + NT2,
+                       T_W0T = T_W1T + NT2 * NT1, NTILES = T_W0T + NT1;
+  SDE4_DEV static float w0(const float* w, int k, int u) { return k < N::IN ? w[N::OFF_W0 + k * N::H1P + u] : 0.0f; }
+  SDE4_DEV static float w1(const float* w, int u1, int u2) { return w[N::OFF_W1 + u1 * N::H2P + u2]; }
+  SDE4_DEV static float w2(const float* w, int u2, int o) { return o < N::OUT ? w[N::OFF_W2 + o * N::H2P + u2] : 0.0f; }
+
+  // fragment image [NTILES][32] from the packed network image w (nets.cuh layout)
+  SDE4_DEV static void build(float4* tiles, const float* w, int tid, int nthreads) {
+    for (int e = tid; e < NTILES * 32; e += nthreads) {
+      const int T = e >> 5, ln = e & 31, g = ln >> 2, t = ln & 3;
+      float v0, v1;
+      if (T < T_L2) {  // layer 1: K = inputs (their own order), N = h1 units
+        const int n = T - T_L1;
+        v0 = w0(w, t, 8 * n + g);
+        v1 = w0(w, t + 4, 8 * n + g);
+      } else if (T < T_L3) {  // layer 2: K = h1 units (relabelled), N = h2 units
+        const int q = T - T_L2, j = q / NT2, n = q - j * NT2;
+        v0 = w1(w, 8 * j + 2 * t, 8 * n + g);
+        v1 = w1(w, 8 * j + 2 * t + 1, 8 * n + g);
+      } else if (T < T_W2T) {  // layer 3: K = h2 units (relabelled), N = outputs
+        const int j = T - T_L3;
+        v0 = w2(w, 8 * j + 2 * t, g);
+        v1 = w2(w, 8 * j + 2 * t + 1, g);
+      } else if (T < T_W1T) {  // backward through layer 3: K = outputs (their own order), N = h2 units
+        const int n = T - T_W2T;
+        v0 = w2(w, 8 * n + g, t);
+        v1 = w2(w, 8 * n + g, t + 4);
+      } else if (T < T_W0T) {  // backward through layer 2: K = h2 units (relabelled), N = h1 units
+        const int q = T - T_W1T, j = q / NT1, n = q - j * NT1;
+        v0 = w1(w, 8 * n + g, 8 * j + 2 * t);
+        v1 = w1(w, 8 * n + g, 8 * j + 2 * t + 1);
+      } else {  // backward through layer 1: K = h1 units (relabelled), N = inputs
+        const int j = T - T_W0T;
+        v0 = w0(w, g, 8 * j + 2 * t);
+        v1 = w0(w, g, 8 * j + 2 * t + 1);
+      }
+      uint32_t h0, l0, h1, l1;
+      tf32_split(v0, h0, l0);
+      tf32_split(v1, h1, l1);
+      tiles[e] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0), __uint_as_float(l1));
+    }
+  }
+
+  // bias of columns 2t, 2t+1 of tile n (both rows)
+  SDE4_DEV static void bias_tile(const float* b, int n, int t, Acc3& c) {
+    const float2 v = *reinterpret_cast<const float2*>(b + 8 * n + 2 * t);
+    c.init(v.x, v.y);
+  }
+
+  // forward for the 16 particles of this warp: out tile = columns 2t, 2t+1 (< OUT) of rows g, g+8.
+  // KEEP: act' of both hidden layers stays in d1 / d2 (accumulator layout) for the backward pass.
+  template <bool KEEP>
+  SDE4_DEV static void fwd(const float4* tiles, const float* w, int lane, const float (&ain)[4], float (&out)[4],
+                           float (&d1)[NT1][4], float (&d2)[NT2][4]) {
+    const int t = lane & 3;
+    AFrag a;
+    a.from_values(ain);
+    float c1[NT1][4];
+#pragma unroll
+    for (int n = 0; n < NT1; ++n) {
+      Acc3 acc;
+      bias_tile(w + N::OFF_B0, n, t, acc);
+      acc.mma(a, tiles[(T_L1 + n) * 32 + lane]);
+      acc.sum(c1[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NT1; ++n) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (KEEP) act_fwd_d<N::ACT>(c1[n][r], c1[n][r], d1[n][r]);
+        else c1[n][r] = act_fwd<N::ACT>(c1[n][r]);
+      }
+    }
+    float c2[NT2][4];
+    {
+      constexpr bool KS = SDE4_WS_KSPLIT && NT1 >= 2;
+      Acc3 acc[NT2], odd[KS ? NT2 : 1];
+#pragma unroll
+      for (int n = 0; n < NT2; ++n) bias_tile(w + N::OFF_B1, n, t, acc[n]);
+      if constexpr (KS) {
+#pragma unroll
+        for (int n = 0; n < NT2; ++n) odd[n].init(0.0f, 0.0f);
+      }
+#pragma unroll
+      for (int j = 0; j < NT1; ++j) {
+        a.from_tile(c1[j]);
+#pragma unroll
+        for (int n = 0; n < NT2; ++n) ((KS && (j & 1)) ? odd[n] : acc[n]).mma(a, tiles[(T_L2 + j * NT2 + n) * 32 + lane]);
+      }
+#pragma unroll
+      for (int n = 0; n < NT2; ++n) {
+        acc[n].sum(c2[n]);
+        if constexpr (KS) {
+          float o[4];
+          odd[n].sum(o);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) c2[n][r] += o[r];
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < NT2; ++n) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        if (KEEP) act_fwd_d<N::ACT>(c2[n][r], c2[n][r], d2[n][r]);
+        else c2[n][r] = act_fwd<N::ACT>(c2[n][r]);
+      }
+    }
+    {
+      constexpr bool KS = SDE4_WS_KSPLIT && NT2 >= 2;
+      Acc3 acc, odd;
+      acc.init(2 * t < N::OUT ? w[N::OFF_B2 + 2 * t] : 0.0f, 2 * t + 1 < N::OUT ? w[N::OFF_B2 + 2 * t + 1] : 0.0f);
+      odd.init(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < NT2; ++j) {
+        a.from_tile(c2[j]);
+        ((KS && (j & 1)) ? odd : acc).mma(a, tiles[(T_L3 + j) * 32 + lane]);
+      }
+      acc.sum(out);
+      if constexpr (KS) {
+        float o[4];
+        odd.sum(o);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) out[r] += o[r];
+      }
+    }
+  }
+
+  // g2 (cotangent of the pre-activation of layer 2, accumulator layout) -> input cotangent tile:
+  // gin = columns 2t, 2t+1 (< IN) of rows g, g+8
+  SDE4_DEV static void bwd_from_g2(const float4* tiles, int lane, const float (&g2)[NT2][4], const float (&d1)[NT1][4],
+                                   float (&gin)[4]) {
+    AFrag a;
+    float g1[NT1][4];
+    {
+      constexpr bool KS = SDE4_WS_KSPLIT && NT2 >= 2;
+      Acc3 acc[NT1], odd[KS ? NT1 : 1];
+#pragma unroll
+      for (int n = 0; n < NT1; ++n) acc[n].init(0.0f, 0.0f);
+      if constexpr (KS) {
+#pragma unroll
+        for (int n = 0; n < NT1; ++n) odd[n].init(0.0f, 0.0f);
+      }
+#pragma unroll
+      for (int j = 0; j < NT2; ++j) {
+        a.from_tile(g2[j]);
+#pragma unroll
+        for (int n = 0; n < NT1; ++n) ((KS && (j & 1)) ? odd[n] : acc[n]).mma(a, tiles[(T_W1T + j * NT1 + n) * 32 + lane]);
+      }
+#pragma unroll
+      for (int n = 0; n < NT1; ++n) {
+        acc[n].sum(g1[n]);
+        if constexpr (KS) {
+          float o[4];
+          odd[n].sum(o);
+#pragma unroll
+          for (int r = 0; r < 4; ++r) g1[n][r] += o[r];
+        }
+      }
+    }
+    constexpr bool KS0 = SDE4_WS_KSPLIT && NT1 >= 2;
+    Acc3 acc, odd;
+    acc.init(0.0f, 0.0f);
+    odd.init(0.0f, 0.0f);
+#pragma unroll
+    for (int j = 0; j < NT1; ++j) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) g1[j][r] *= d1[j][r];
+      a.from_tile(g1[j]);
+      ((KS0 && (j & 1)) ? odd : acc).mma(a, tiles[(T_W0T + j) * 32 + lane]);
+    }
+    acc.sum(gin);
+    if constexpr (KS0) {
+      float o[4];
+      odd.sum(o);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) gin[r] += o[r];
+    }
+  }
+  // output cotangent (A operand in its own order: a0 = gout[g][t], a1 = gout[g+8][t], a2 = a3 = 0) -> input cotangent
+  SDE4_DEV static void bwd(const float4* tiles, int lane, const float (&agout)[4], const float (&d1)[NT1][4],
+                           const float (&d2)[NT2][4], float (&gin)[4]) {
+    AFrag a;
+    a.from_values(agout);
+    float g2[NT2][4];
+#pragma unroll
+    for (int n = 0; n < NT2; ++n) {
+      Acc3 acc;
+      acc.init(0.0f, 0.0f);
+      acc.mma(a, tiles[(T_W2T + n) * 32 + lane]);
+      acc.sum(g2[n]);
+#pragma unroll
+      for (int r = 0; r < 4; ++r) g2[n][r] *= d2[n][r];
+    }
+    bwd_from_g2(tiles, lane, g2, d1, gin);
+  }
+  // scalar-output network: value (column 0 of `out`, threads with t == 0) and the input gradient d out / d in
+  SDE4_DEV static void value_grad(const float4* tiles, const float* w, int lane, const float (&ain)[4], float (&out)[4],
+                                  float (&gin)[4]) {
+    static_assert(N::OUT == 1, "scalar-output network expected");
+    const int t = lane & 3;
+    float d1[NT1][4], d2[NT2][4];
+    fwd<true>(tiles, w, lane, ain, out, d1, d2);
+#pragma unroll
+    for (int n = 0; n < NT2; ++n) {
+      const float2 v = *reinterpret_cast<const float2*>(w + N::OFF_W2 + 8 * n + 2 * t);
+      d2[n][0] *= v.x;
+      d2[n][1] *= v.y;
+      d2[n][2] *= v.x;
+      d2[n][3] *= v.y;
+    }
+    bwd_from_g2(tiles, lane, d2, d1, gin);
+  }
+};
+
+// ----------------------------------------------------------------------------------------------------------------
+template <class A_>
 struct WsCfg {
   using A = A_;
-  using M8 = RotorModel<A, EvL<8>>;  // evaluator, diffusion constants and projection of the lane-split model
+  using M8 = RotorModel<A, EvL<8>>;  // diffusion constants and projection of the lane-split model
   using RS = RotorSplit<A>;
   using DNet = typename A::DNet;
   using NetA = typename A::NetA;
   using NetB = typename A::NetB;
-  static_assert(A::MODEL == SDE4_MODEL_ROTOR && A::HAS_DENSITY && !Diffusion<M8>::CDN, "multirotor SDE with a density net");
-  static constexpr int NPART = NPART_;  // particles per CTA: 8, 16 or 32
-  static_assert(NPART == 8 || NPART == 16 || NPART == 32, "particles per CTA");
-  static constexpr int LN = 8;                       // lanes per particle of the DENS role (32-wide layers: 4 units per lane)
-  static constexpr int LR = 4;                       // lanes per particle of the RES role (8 / 16-wide layers: 2 / 4 units per lane)
-  using MR = RotorModel<A, EvL<LR>>;
-  static constexpr int WN = NPART * LN / 32;         // DENS warps
-  static constexpr int WR = NPART * LR / 32;         // RES warps
-  static constexpr int THREADS = 32 * (1 + WN + WR); // warp 0: PHY, then the DENS warps, then the RES warps
+  using MD = MmaNet<DNet>;
+  using MA = MmaNet<NetA>;
+  using MB = MmaNet<NetB>;
+  static_assert(A::MODEL == SDE4_MODEL_ROTOR && A::HAS_DENSITY && !Diffusion<M8>::CDN && NetA::PRESENT && NetB::PRESENT,
+                "multirotor SDE with a density net and both residual nets");
+  static constexpr int NPART = 16;                 // particles per CTA = rows of one MMA tile
+  static constexpr int THREADS = 128;              // warp 0 PHY, warp 1 DENS, warp 2 RES, warp 3 AUX (one role per scheduler)
   static constexpr int NX = 13, NU = A::NU, NZ = DNet::IN, NO = A::NO;
   static constexpr int NIA = RS::NIA, NIB = RS::NIB;
+  // fragment image
+  static constexpr int TILE_D = 0, TILE_A = MD::NTILES, TILE_B = TILE_A + MA::NTILES, NTILES = TILE_B + MB::NTILES;
   // exchange buffer, [value][NPART]
-  static constexpr int X_IN6 = 0, X_Z = 6, X_FN = X_Z + NZ, X_MN = X_FN + 3, X_SDW = X_MN + 3, FWD_VALS = X_SDW + NX;
+  static constexpr int X_IN6 = 0, X_Z = 6, X_FN = X_Z + NZ, X_MN = X_FN + 3, X_ETA = X_MN + 3, X_DW = X_ETA + NO,
+                       FWD_VALS = X_DW + 3 * NX;  // three dw slots in rotation
   static constexpr int B_GF = 0, B_GM = 3, B_GIA = 6, B_GIB = B_GIA + NIA, B_FN = B_GIB + NIB, B_DENS = B_FN + 3,
-                       B_J = B_DENS + 1, BWD_VALS = B_J + NZ;
-  static constexpr int B_GU = BWD_VALS;  // control-gradient row of the step PHY has just finished (summed by the RES role)
-  static constexpr int BWD_ALL = B_GU + NU;
-  static constexpr int VALS = FWD_VALS > BWD_ALL ? FWD_VALS : BWD_ALL;
-  static constexpr int N_PRIOR = 16;  // noise prior staged in shared memory (indexed by a run-time state index)
-  static constexpr int XCH_FLOATS = VALS * NPART + N_PRIOR;
-  static constexpr size_t smem_bytes() { return sizeof(float) * ((size_t)A::SMEM_FLOATS + XCH_FLOATS); }
+                       B_J = B_DENS + 1, B_GU = B_J + NZ, BWD_VALS = B_GU + NU;
+  static constexpr int VALS = FWD_VALS > BWD_VALS ? FWD_VALS : BWD_VALS;
+  static constexpr int N_MISC = 32;  // noise prior [16] | list of the states that carry noise [16]
+  static constexpr int OFF_TILES = A::SMEM_FLOATS;                 // float4-aligned (SMEM_FLOATS is a multiple of 4)
+  static constexpr int OFF_XCH = OFF_TILES + NTILES * 32 * 4;
+  static constexpr int OFF_MISC = OFF_XCH + VALS * NPART;
+  static constexpr size_t smem_bytes() { return sizeof(float) * ((size_t)OFF_MISC + N_MISC); }
 };
 
-template <int THREADS>
-SDE4_DEV void ws_sync() {  // CTA-wide; spelled as a named barrier because the roles run different code
-  asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory");
+#ifdef SDE4_WS_TRACE
+// tuning aid: arrival / departure clocks of every barrier of CTA 64, per role (scripts/ws_trace.py)
+__device__ long long g_ws_trace[4][2 * 512];
+__device__ int g_ws_trace_n[4];
+#endif
+// Named barriers (the roles run different code, so no __syncthreads()).
+template <int ID, int COUNT>
+SDE4_DEV void ws_bar() {
+#ifdef SDE4_WS_TRACE
+  const bool rec = blockIdx.x == 64 && (threadIdx.x & 31) == 0;
+  const int role = threadIdx.x >> 5;
+  int slot = 0;
+  if (rec) {
+    slot = g_ws_trace_n[role];
+    if (slot < 512) g_ws_trace[role][2 * slot] = clock64();
+  }
+#endif
+  asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory");
+#ifdef SDE4_WS_TRACE
+  if (rec) {
+    if (slot < 512) g_ws_trace[role][2 * slot + 1] = clock64();
+    g_ws_trace_n[role] = slot + 1;
+  }
+#endif
 }
+// B2 / B4 (networks -> PHY hand-over): the whole CTA
+template <int THREADS>
+SDE4_DEV void ws_sync() {
+  ws_bar<1, THREADS>();
+}
+// B1 / B3 (PHY -> networks hand-over) involve the first three warps only: the AUX role never reads what PHY publishes
+// there, and keeping it out lets it generate noise during BOTH halves of a step.
+SDE4_DEV void ws_sync3() { ws_bar<2, 96>(); }
 
 // ---- PHY role: one lane per particle ---------------------------------------------------------------------------------
 template <class Cfg, bool PLAINC>
@@ -268,7 +620,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
   using A = typename Cfg::A;
   using RS = typename Cfg::RS;
   using M8 = typename Cfg::M8;
-  constexpr int NX = Cfg::NX, NU = Cfg::NU, NPART = Cfg::NPART, NZ = Cfg::NZ;
+  constexpr int NX = Cfg::NX, NU = Cfg::NU, NPART = Cfg::NPART, NZ = Cfg::NZ, NO = Cfg::NO;
   const float* __restrict__ S = W + A::OFF_SCALARS;
   const unsigned G = (unsigned)a.G;
   const int H = a.H;
@@ -294,13 +646,13 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
     for (int k = 0; k < 6; ++k) xch[(Cfg::X_IN6 + k) * NPART + pl] = in6[k];
 #pragma unroll
     for (int k = 0; k < NZ; ++k) xch[(Cfg::X_Z + k) * NPART + pl] = x[nth_bit(A::NIN_MASK, k)] * d.inv_red_scale;
-    ws_sync<Cfg::THREADS>();  // B1: the networks may start
+    ws_sync3();  // B1: the networks may start
     if (active) {             // network inputs of the residual nets, kept for the backward sweep
       float* ft = ftape + (size_t)t * 6 * G + g;
 #pragma unroll
       for (int k = 0; k < 6; ++k) ft[(size_t)k * G] = in6[k];
     }
-    ws_sync<Cfg::THREADS>();  // B2: network outputs and sigma o dw are there
+    ws_sync<Cfg::THREADS>();  // B2: network outputs, eta and dw_t are there
     float Fn[3], Mn[3], f[NX];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -308,8 +660,14 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
       Mn[k] = xch[(Cfg::X_MN + k) * NPART + pl];
     }
     RS::drift_post(S, d, x, u, vb, Fn, Mn, f);
+    // sigma o dw: sigma_i = prior_i * eta_k(i), eta = 1 outside the noise-output mask (nsde.py:363,449)
+    const float* dwb = xch + (Cfg::X_DW + (t % 3) * NX) * NPART + pl;
 #pragma unroll
-    for (int i = 0; i < NX; ++i) x[i] = fmaf(f[i], dt, x[i]) + xch[(Cfg::X_SDW + i) * NPART + pl];
+    for (int i = 0; i < NX; ++i) {
+      float s = d.noise_prior[i];
+      if ((A::NOUT_MASK >> i) & 1u) s *= xch[(Cfg::X_ETA + popc(A::NOUT_MASK & ((1u << i) - 1u))) * NPART + pl];
+      x[i] = fmaf(f[i], dt, x[i]) + s * dwb[i * NPART];
+    }
     float aux;
     M8::project(x, aux);
     if (active) {
@@ -337,8 +695,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
       cost += stage_cost<NX, NU, true>(td, x, u, xr + (size_t)H * NX, false, 1.0f, lam, gu_unused);
     }
   }
-  constexpr int SPW = NPART;  // samples per partial when the CTA's particles share a problem
-  const int pw = a.warp_reduce ? (g / SPW) : g;
+  const int pw = a.warp_reduce ? (g / NPART) : g;
   const bool writer = a.warp_reduce ? (active && (threadIdx.x & 31) == 0) : active;
   float xpre[NX], auxpre;
   {
@@ -376,7 +733,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
       xch[(Cfg::B_GF + k) * NPART + pl] = at.gFb[k];
       xch[(Cfg::B_GM + k) * NPART + pl] = at.gM[k];
     }
-    ws_sync<Cfg::THREADS>();  // B3: the network backward passes may start
+    ws_sync3();  // B3: the network backward passes may start
     // meanwhile: what does not need them -- features of x_t and the stage cost with its gradient
     Quat t1;
     float vb[3], in6[6];
@@ -404,9 +761,9 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
     for (int k = 0; k < NZ; ++k) dtp.J[k] = xch[(Cfg::B_J + k) * NPART + pl];
     RS::vjp_post(S, d, x, u, vf, t1, vb, Fn, at, giA, giB, gx, gu);
     Diffusion<M8>::apply(W, d, x, lam, [&](int i) { return nzv[i]; }, dtp, gx, gu);
-    // row t of the gradient.  When the CTA's particles share a problem the row is summed over them -- by the RES
-    // role, which has the time (30 dependent shuffle / add pairs here were half of this role's backward sweep);
-    // otherwise one partial per particle, stored directly.
+    // row t of the gradient.  When the CTA's particles share a problem the row is summed over them by the RES role
+    // (30 dependent shuffle / add pairs here were half of this role's backward sweep); otherwise one partial per
+    // particle, stored directly.
     if (a.warp_reduce) {
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
@@ -432,191 +789,267 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
   }
 }
 
-// ---- DENS role: 8 lanes per particle; density network, noise, sigma o dw -------------------------------------------------
-template <class Cfg>
-SDE4_DEV void ws_role_dens(const float* W, float* xch, const sde4_model_desc& d, const CostK& a, int pl, int g, int n,
-                           int pd, bool active) {
-  using A = typename Cfg::A;
-  using M8 = typename Cfg::M8;
-  using Ev = typename M8::Ev;
-  using DNet = typename A::DNet;
-  constexpr int NX = Cfg::NX, NPART = Cfg::NPART, NZ = Cfg::NZ, NO = Cfg::NO, L = Cfg::LN;
-  constexpr int PER = (NX + L - 1) / L;
-  const unsigned G = (unsigned)a.G;
-  const int H = a.H;
-  typename Ev::Ctx ctx;
-  const int l = threadIdx.x & (L - 1);
-  ctx.l = l;
-  const uint32_t nzmask = noise_mask<NX>(d);
-  const float* prior = xch + Cfg::VALS * NPART;  // staged by the kernel prologue
+// A operand of a network input read from the exchange buffer: value (row p, k) at xch[(base + idx(k)) * NPART + p]
+template <int NPART, class IdxFn>
+SDE4_DEV void a_from_xch(const float* xch, int base, int nk, int lane, IdxFn idx, float (&a)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  a[0] = t < nk ? xch[(base + idx(t)) * NPART + g] : 0.0f;
+  a[1] = t < nk ? xch[(base + idx(t)) * NPART + g + 8] : 0.0f;
+  a[2] = t + 4 < nk ? xch[(base + idx(t + 4)) * NPART + g] : 0.0f;
+  a[3] = t + 4 < nk ? xch[(base + idx(t + 4)) * NPART + g + 8] : 0.0f;
+}
+// k-th set bit of a compile-time mask for a run-time k (k < popc(MASK) <= 8)
+template <uint32_t MASK>
+SDE4_DEV int nth_bit_rt(int k) {
+  int r = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < popc(MASK) && k == q) r = nth_bit(MASK, q < popc(MASK) ? q : 0);
+  return r;
+}
+// publish columns 2t, 2t+1 (< n) of rows g, g+8 of an output tile
+template <int NPART>
+SDE4_DEV void tile_to_xch(float* xch, int base, int n, int lane, const float (&c)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  if (2 * t < n) {
+    xch[(base + 2 * t) * NPART + g] = c[0];
+    xch[(base + 2 * t) * NPART + g + 8] = c[2];
+  }
+  if (2 * t + 1 < n) {
+    xch[(base + 2 * t + 1) * NPART + g] = c[1];
+    xch[(base + 2 * t + 1) * NPART + g + 8] = c[3];
+  }
+}
+
+// In-kernel threefry noise of the CTA's 16 particles, shared by the two network warps (PART 0: RES, PART 1: DENS).
+// A thread draws, for ITS particle (lane % 16), the noise-carrying states of list index (lane / 16) + 2 q; the q range
+// is cut in two between the warps.  dw_{t+1} is generated while PHY finishes step t and stored straight into the exchange
+// buffer (three slots in rotation, so no write can meet a read of the slot's previous use) and, for the backward sweep,
+// the global noise buffer.  The loop over q is ROLLED, two independent threefry chains per iteration: fully unrolled the
+// generator was 770 instructions of each network role's loop body, and the three roles' bodies together have to stay
+// inside the 32 KB instruction cache (profiles/r2_c_ws_mma_ncu.txt: no_instruction was the top stall otherwise).
+template <class Cfg, int PART>
+struct WsNoise {
+  static constexpr int NX = Cfg::NX, NPART = Cfg::NPART;
+  float* xch;
+  const CostK& a;
+  const int* nzlist;
+  int nnz, lane, pi, g0, H, qlo, qhi;
+  bool lane_active;
   uint32_t b0, b1;
-  {
+  SDE4_DEV WsNoise(float* xch_, const sde4_model_desc& d, const CostK& a_, int g0_, bool lane_active_, int n, int pd)
+      : xch(xch_), a(a_), g0(g0_), lane_active(lane_active_) {
+    nzlist = reinterpret_cast<const int*>(xch + (Cfg::OFF_MISC - Cfg::OFF_XCH) + 16);
+    nnz = __popc(noise_mask<NX>(d));
+    lane = threadIdx.x & 31;
+    pi = lane & 15;
+    H = a.H;
+    const int nq = (nnz + 1) >> 1, mid = (nq + 1) >> 1;
+    qlo = PART == 1 ? mid : 0;  // PART 2: the whole range
+    qhi = PART == 0 ? mid : nq;
     const uint32_t* k = a.key + (size_t)pd * a.key_sp;
     brownian_key(__ldg(k), __ldg(k + 1), (uint32_t)(n + a.n_off), (uint32_t)a.n_tot, a.rng_mode, b0, b1, a.rng_chain);
   }
-  // this lane's elements l, l + 8 of dw_t: validity, prior and (for eta-scaled states) the index of the scaler entry
-  bool el_ok[PER];
-  int el_k[PER];
-  float el_prior[PER];
-#pragma unroll
-  for (int q = 0; q < PER; ++q) {
-    const int i = l + q * L;
-    el_ok[q] = i < NX && ((nzmask >> i) & 1u);
-    el_prior[q] = i < NX ? prior[i] : 0.0f;
-    el_k[q] = (i < NX && ((A::NOUT_MASK >> i) & 1u)) ? __popc(A::NOUT_MASK & ((1u << i) - 1u)) : -1;
+  SDE4_DEV void one(int ts, int q, bool on) const {
+    const int idx = (lane >> 4) + 2 * q;
+    const bool ok = on && idx < nnz;
+    const int i = nzlist[ok ? idx : 0];
+    const float z = bits_to_normal(jax_bits(b0, b1, (uint64_t)ts * NX + i, (uint64_t)H * NX, a.rng_mode));
+    if (ok) {
+      xch[(Cfg::X_DW + (ts % 3) * NX + i) * NPART + pi] = z;
+      if (lane_active) a.dwbuf[((size_t)ts * NX + i) * (unsigned)a.G + g0 + pi] = z;
+    }
   }
-  auto gen = [&](int t, float (&v)[PER]) {
+  template <int NQ>
+  SDE4_DEV void gen_unrolled(int ts) const {
+    // NQ independent threefry / erf_inv chains in ONE basic block (ptxas interleaves dependency chains only inside a
+    // block: with the predicated stores between them the five chains ran one after the other, 3.3 k cycles per step)
+    int i[NQ];
+    bool ok[NQ];
+    float z[NQ];
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-      const int i = el_ok[q] ? l + q * L : 0;
-      const float z = bits_to_normal(jax_bits(b0, b1, (uint64_t)t * NX + i, (uint64_t)H * NX, a.rng_mode));
-      v[q] = el_ok[q] ? z : 0.0f;
+    for (int q = 0; q < NQ; ++q) {
+      const int idx = (lane >> 4) + 2 * q;
+      ok[q] = idx < nnz;
+      i[q] = nzlist[ok[q] ? idx : 0];
     }
-  };
-  const NetRef rD = A::template ref<0, L>(W);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+      z[q] = bits_to_normal(jax_bits(b0, b1, (uint64_t)ts * NX + i[q], (uint64_t)H * NX, a.rng_mode));
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (ok[q]) {
+        xch[(Cfg::X_DW + (ts % 3) * NX + i[q]) * NPART + pi] = z[q];
+        if (lane_active) a.dwbuf[((size_t)ts * NX + i[q]) * (unsigned)a.G + g0 + pi] = z[q];
+      }
+    }
+  }
+  SDE4_DEV void gen(int ts) const {
+    if (PART == 2 && qhi == 5) {  // 9 or 10 noise-carrying states (the shipped multirotor models): five chains side by side
+      gen_unrolled<5>(ts);
+      return;
+    }
+#pragma unroll 1
+    for (int q = qlo; q < qhi; q += 2) {
+      one(ts, q, true);
+      one(ts, q + 1, q + 1 < qhi);
+    }
+  }
+};
+
+// ---- DENS role: one warp, 16 particles; density network on the tensor cores, eta, half of the noise ----------------------------------------
+template <class Cfg>
+SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const CostK& a,
+                           int g0, int gmax) {
+  using A = typename Cfg::A;
+  using MD = typename Cfg::MD;
+  using DNet = typename A::DNet;
+  constexpr int NPART = Cfg::NPART, NZ = Cfg::NZ, NO = Cfg::NO;
+  const unsigned G = (unsigned)a.G;
+  const int H = a.H;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* wD = W + A::OFF_DENSITY;
+  const float4* tD = tiles + Cfg::TILE_D * 32;
+  auto ident = [](int k) { return k; };
   // ---------------- forward sweep ----------------
-  float vn[PER];
-  gen(0, vn);
-  for (int t = 0; t < H; ++t) {
-    float dwt[PER];
+  for (int ts = 0; ts < H; ++ts) {
+    ws_sync3();  // B1
+    float az[4], out[4];
+    a_from_xch<NPART>(xch, Cfg::X_Z, NZ, lane, ident, az);
+    float d1[MD::NT1][4], d2[MD::NT2][4];
+    MD::template fwd<false>(tD, wD, lane, az, out, d1, d2);
+    // density of rows g, g+8 sits in column 0 (threads with t == 0): hand it to the quad, thread t forms eta_t, eta_{t+4}
+    const float dg = __shfl_sync(0xffffffffu, out[0], lane & ~3), dg8 = __shfl_sync(0xffffffffu, out[2], lane & ~3);
 #pragma unroll
-    for (int q = 0; q < PER; ++q) dwt[q] = vn[q];
-    {  // kept for the backward sweep (the owning lane writes)
-      float* row = a.dwbuf + (size_t)t * NX * G + g + (size_t)l * G;
-#pragma unroll
-      for (int q = 0; q < PER; ++q)
-        if (active && el_ok[q]) row[(size_t)(q * L) * G] = dwt[q];
-    }
-    gen(t + 1 < H ? t + 1 : t, vn);  // integer work of the next step's noise, overlaps the wait for PHY
-    ws_sync<Cfg::THREADS>();  // B1
-    float z[NZ];
-#pragma unroll
-    for (int k = 0; k < NZ; ++k) z[k] = xch[(Cfg::X_Z + k) * NPART + pl];
-    float dens[1];
-    Ev::template fwd<DNet, false>(rD, ctx, z, dens);
-    // sigma o dw for the own elements: sigma_i = prior_i * eta_k(i) (eta = 1 for states outside the noise-output mask)
-#pragma unroll
-    for (int q = 0; q < PER; ++q) {
-      float s = el_prior[q] * dwt[q];
-      if (el_k[q] >= 0) {
+    for (int q = 0; q < 2; ++q) {
+      const int k = t + 4 * q;
+      if (k < NO) {
         float coeff = 0.0f, offs = 0.0f;
         if constexpr (A::HAS_SCALER) {
-          coeff = W[A::OFF_DERIVED + el_k[q]];
-          offs = W[A::OFF_DERIVED + NO + el_k[q]];
+          coeff = W[A::OFF_DERIVED + k];
+          offs = W[A::OFF_DERIVED + NO + k];
         }
-        s *= sigmoidf_((d.aggr + coeff) * dens[0] - 7.0f + offs);  // nsde.py:426
+        xch[(Cfg::X_ETA + k) * NPART + g] = sigmoidf_((d.aggr + coeff) * dg - 7.0f + offs);  // nsde.py:426
+        xch[(Cfg::X_ETA + k) * NPART + g + 8] = sigmoidf_((d.aggr + coeff) * dg8 - 7.0f + offs);
       }
-      if (l + q * L < NX) xch[(Cfg::X_SDW + l + q * L) * NPART + pl] = s;
     }
     ws_sync<Cfg::THREADS>();  // B2
   }
-
   // ---------------- backward sweep: density value + input gradient of step t, one step ahead of its use ----------------
-  float dval = 0.0f, J[NZ], z[NZ];
-  auto load_inputs = [&](int t) {
-    const float* xin = a.xbuf + (size_t)t * a.x_rows * G + g;
-#pragma unroll
-    for (int k = 0; k < NZ; ++k) z[k] = xin[(size_t)nth_bit(A::NIN_MASK, k) * G] * d.inv_red_scale;
+  // rows of the A operand: particles g0 + g, g0 + g + 8 (clamped to the last valid sample)
+  const unsigned ga = min(g0 + g, gmax), gb = min(g0 + g + 8, gmax);
+  float az[4];
+  auto load_inputs = [&](int ts) {
+    const float* xin = a.xbuf + (size_t)ts * a.x_rows * G;
+    const int k0 = nth_bit_rt<A::NIN_MASK>(t), k1 = nth_bit_rt<A::NIN_MASK>(t + 4 < NZ ? t + 4 : 0);
+    az[0] = t < NZ ? xin[(size_t)k0 * G + ga] * d.inv_red_scale : 0.0f;
+    az[1] = t < NZ ? xin[(size_t)k0 * G + gb] * d.inv_red_scale : 0.0f;
+    az[2] = t + 4 < NZ ? xin[(size_t)k1 * G + ga] * d.inv_red_scale : 0.0f;
+    az[3] = t + 4 < NZ ? xin[(size_t)k1 * G + gb] * d.inv_red_scale : 0.0f;
   };
   load_inputs(H - 1);  // the forward sweep's last B2 ordered PHY's checkpoint stores before these loads
-  for (int t = H - 1; t >= 0; --t) {
-    Ev::template scalar_value_grad<DNet>(rD, ctx, z, dval, J, [](float) { return 1.0f; });
-    load_inputs(t > 0 ? t - 1 : 0);
-    ws_sync<Cfg::THREADS>();  // B3 (PHY has read the previous item by now)
-    {
-      float* out = xch + pl;
-      if (l == 7) out[Cfg::B_DENS * NPART] = dval;
-#pragma unroll
-      for (int k = 0; k < NZ; ++k)
-        if (l == (k & (L - 1))) out[(Cfg::B_J + k) * NPART] = J[k];
+  for (int ts = H - 1; ts >= 0; --ts) {
+    float out[4], J[4];
+    MD::value_grad(tD, wD, lane, az, out, J);
+    load_inputs(ts > 0 ? ts - 1 : 0);
+    ws_sync3();  // B3 (PHY has read the previous item by now)
+    if (t == 0) {
+      xch[Cfg::B_DENS * NPART + g] = out[0];
+      xch[Cfg::B_DENS * NPART + g + 8] = out[2];
     }
+    tile_to_xch<NPART>(xch, Cfg::B_J, NZ, lane, J);
     ws_sync<Cfg::THREADS>();  // B4
   }
   ws_sync<Cfg::THREADS>();  // (PHY's last gradient row for the RES role)
 }
 
-// ---- RES role: 4 lanes per particle; residual force / moment networks ---------------------------------------------------
+// ---- RES role: one warp, 16 particles; residual force / moment networks on the tensor cores, in-kernel noise ----------
 template <class Cfg>
-SDE4_DEV void ws_role_res(const float* W, float* xch, const sde4_model_desc& d, const CostK& a, const float* ftape, int pl,
-                          int g, bool active) {
+SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const CostK& a,
+                          const float* ftape, int g0, int gmax) {
   using A = typename Cfg::A;
-  using M8 = typename Cfg::MR;  // this role's lane-split model (4 lanes per particle)
-  using Ev = typename M8::Ev;
+  using MA = typename Cfg::MA;
+  using MB = typename Cfg::MB;
   using NetA = typename A::NetA;
   using NetB = typename A::NetB;
-  using RS = typename Cfg::RS;
-  constexpr int NPART = Cfg::NPART, L = Cfg::LR;
+  constexpr int NPART = Cfg::NPART, NX = Cfg::NX, NU = Cfg::NU;
   const unsigned G = (unsigned)a.G;
   const int H = a.H;
-  typename Ev::Ctx ctx;
-  const int l = threadIdx.x & (L - 1);
-  ctx.l = l;
-  const NetRef rA = A::template ref<1, L>(W), rB = A::template ref<2, L>(W);
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* wA = W + A::OFF_NET_A;
+  const float* wB = W + A::OFF_NET_B;
+  const float4* tA = tiles + Cfg::TILE_A * 32;
+  const float4* tB = tiles + Cfg::TILE_B * 32;
+  auto idxA = [](int k) { return nth_bit_rt<A::A_MASK>(k); };
+  auto idxB = [](int k) { return nth_bit_rt<A::B_MASK>(k); };
   // ---------------- forward sweep ----------------
-  for (int t = 0; t < H; ++t) {
-    ws_sync<Cfg::THREADS>();  // B1
-    float in6[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) in6[k] = xch[(Cfg::X_IN6 + k) * NPART + pl];
-    float Fn[3] = {0.0f, 0.0f, 0.0f}, Mn[3] = {0.0f, 0.0f, 0.0f};
-    if constexpr (RS::HAS_F) {
-      float in[RS::NIA];
-#pragma unroll
-      for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      Ev::template fwd<NetA, false>(rA, ctx, in, Fn);
-    }
-    if constexpr (RS::HAS_M) {
-      float in[RS::NIB];
-#pragma unroll
-      for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      Ev::template fwd<NetB, false>(rB, ctx, in, Mn);
-    }
-    if (l < 3) {  // outputs are replicated over the lanes: lanes 0..2 publish one component each
-      xch[(Cfg::X_FN + l) * NPART + pl] = l == 0 ? Fn[0] : (l == 1 ? Fn[1] : Fn[2]);
-      xch[(Cfg::X_MN + l) * NPART + pl] = l == 0 ? Mn[0] : (l == 1 ? Mn[1] : Mn[2]);
-    }
+  for (int ts = 0; ts < H; ++ts) {
+    ws_sync3();  // B1
+    float aA[4], aB[4], Fn[4], Mn[4];
+    a_from_xch<NPART>(xch, Cfg::X_IN6, NetA::IN, lane, idxA, aA);
+    a_from_xch<NPART>(xch, Cfg::X_IN6, NetB::IN, lane, idxB, aB);
+    float dA1[MA::NT1][4], dA2[MA::NT2][4], dB1[MB::NT1][4], dB2[MB::NT2][4];
+    MA::template fwd<false>(tA, wA, lane, aA, Fn, dA1, dA2);
+    MB::template fwd<false>(tB, wB, lane, aB, Mn, dB1, dB2);
+    tile_to_xch<NPART>(xch, Cfg::X_FN, 3, lane, Fn);
+    tile_to_xch<NPART>(xch, Cfg::X_MN, 3, lane, Mn);
     ws_sync<Cfg::THREADS>();  // B2
   }
-
   // ---------------- backward sweep ----------------
-  float Fn[3] = {0.0f, 0.0f, 0.0f};
-  float dA1[M8::TB1A], dA2[M8::TB2A], dB1[M8::TB1B], dB2[M8::TB2B];
-  float in6[6];
-  auto load_inputs = [&](int t) {
-    const float* ft = ftape + (size_t)t * 6 * G + g;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) in6[k] = ft[(size_t)k * G];
+  const unsigned ga = min(g0 + g, gmax), gb = min(g0 + g + 8, gmax);
+  float aA[4], aB[4], Fn[4];
+  float dA1[MA::NT1][4], dA2[MA::NT2][4], dB1[MB::NT1][4], dB2[MB::NT2][4];
+  auto load_inputs = [&](int ts) {
+    const float* ft = ftape + (size_t)ts * 6 * G;
+    const int a0 = idxA(t), a1 = idxA(t + 4 < NetA::IN ? t + 4 : 0), c0 = idxB(t), c1 = idxB(t + 4 < NetB::IN ? t + 4 : 0);
+    aA[0] = t < NetA::IN ? ft[(size_t)a0 * G + ga] : 0.0f;
+    aA[1] = t < NetA::IN ? ft[(size_t)a0 * G + gb] : 0.0f;
+    aA[2] = t + 4 < NetA::IN ? ft[(size_t)a1 * G + ga] : 0.0f;
+    aA[3] = t + 4 < NetA::IN ? ft[(size_t)a1 * G + gb] : 0.0f;
+    aB[0] = t < NetB::IN ? ft[(size_t)c0 * G + ga] : 0.0f;
+    aB[1] = t < NetB::IN ? ft[(size_t)c0 * G + gb] : 0.0f;
+    aB[2] = t + 4 < NetB::IN ? ft[(size_t)c1 * G + ga] : 0.0f;
+    aB[3] = t + 4 < NetB::IN ? ft[(size_t)c1 * G + gb] : 0.0f;
   };
-  // forward passes of step t keeping act' of the own hidden units (cotangent independent: one step ahead)
-  auto indep = [&]() {
-    if constexpr (RS::HAS_F) {
-      float in[RS::NIA];
-#pragma unroll
-      for (int k = 0; k < NetA::IN; ++k) in[k] = in6[nth_bit(A::A_MASK, k)];
-      Ev::template fwd<NetA, true>(rA, ctx, in, Fn);
-#pragma unroll
-      for (int m = 0; m < M8::TB1A; ++m) dA1[m] = ctx.d1[m];
-#pragma unroll
-      for (int m = 0; m < M8::TB2A; ++m) dA2[m] = ctx.d2[m];
-    }
-    if constexpr (RS::HAS_M) {
-      float in[RS::NIB], out[3];
-#pragma unroll
-      for (int k = 0; k < NetB::IN; ++k) in[k] = in6[nth_bit(A::B_MASK, k)];
-      Ev::template fwd<NetB, true>(rB, ctx, in, out);
-#pragma unroll
-      for (int m = 0; m < M8::TB1B; ++m) dB1[m] = ctx.d1[m];
-#pragma unroll
-      for (int m = 0; m < M8::TB2B; ++m) dB2[m] = ctx.d2[m];
-    }
-  };
-  // Gradient row of step t: fixed-order sum over the CTA's particles of what PHY left in the exchange buffer, by the
-  // first RES warp: lane = (control j, quarter of the particles); serial over the quarter, two butterfly rounds.
-  constexpr int NU = Cfg::NU, QP = NPART / 4;
-  const int rlane = threadIdx.x & 31, rj = rlane >> 2, rq = rlane & 3;
-  const bool sum_warp = a.warp_reduce && (int)(threadIdx.x >> 5) == 1 + Cfg::WN;
-  auto sum_row = [&](int t) {
-    if (!sum_warp) return;  // warp-uniform
+  load_inputs(H - 1);  // the forward sweep's last B2 ordered PHY's feature stores before these loads
+  for (int ts = H - 1; ts >= 0; --ts) {
+    float Mn_unused[4];
+    MA::template fwd<true>(tA, wA, lane, aA, Fn, dA1, dA2);  // cotangent independent: ahead of the barrier
+    MB::template fwd<true>(tB, wB, lane, aB, Mn_unused, dB1, dB2);
+    load_inputs(ts > 0 ? ts - 1 : 0);  // requested one step ahead
+    ws_sync3();  // B3: cotangents of the network outputs are there
+    float agF[4], agM[4], giA[4], giB[4];
+    a_from_xch<NPART>(xch, Cfg::B_GF, 3, lane, [](int k) { return k; }, agF);
+    a_from_xch<NPART>(xch, Cfg::B_GM, 3, lane, [](int k) { return k; }, agM);
+    MA::bwd(tA, lane, agF, dA1, dA2, giA);
+    MB::bwd(tB, lane, agM, dB1, dB2, giB);
+    tile_to_xch<NPART>(xch, Cfg::B_GIA, NetA::IN, lane, giA);
+    tile_to_xch<NPART>(xch, Cfg::B_GIB, NetB::IN, lane, giB);
+    tile_to_xch<NPART>(xch, Cfg::B_FN, 3, lane, Fn);
+    ws_sync<Cfg::THREADS>();  // B4
+  }
+  ws_sync<Cfg::THREADS>();
+}
+
+// ---- AUX role: one warp; in-kernel threefry noise one step ahead (forward sweep), fixed-order sum of the control-gradient
+//      rows over the CTA's particles (backward sweep) ------------------------------------------------------------------
+template <class Cfg>
+SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, int g0, bool lane_active, int n, int pd) {
+  constexpr int NPART = Cfg::NPART, NU = Cfg::NU;
+  const int H = a.H;
+  const int lane = threadIdx.x & 31;
+  WsNoise<Cfg, 2> noise(xch, d, a, g0, lane_active, n, pd);
+  noise.gen(0);
+  for (int ts = 0; ts < H; ++ts) {
+    if (ts + 1 < H) noise.gen(ts + 1);  // slot (ts + 1) % 3: PHY reads it after B2 of the next step
+    ws_sync<Cfg::THREADS>();  // B2
+  }
+  // Gradient row of step ts: fixed-order sum over the CTA's particles of what PHY left in the exchange buffer:
+  // thread = (control j, quarter of the particles); serial over the quarter, two butterfly rounds.
+  constexpr int QP = NPART / 4;
+  const int rj = lane >> 2, rq = lane & 3;
+  auto sum_row = [&](int ts) {
+    if (!a.warp_reduce) return;
     float v = 0.0f;
     if (rj < NU) {
 #pragma unroll
@@ -624,87 +1057,62 @@ SDE4_DEV void ws_role_res(const float* W, float* xch, const sde4_model_desc& d, 
     }
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     v += __shfl_xor_sync(0xffffffffu, v, 2);
-    if (rj < NU && rq == 0) a.gpart[((size_t)t * NU + rj) * a.PW + g / NPART] = v;
+    if (rj < NU && rq == 0) a.gpart[((size_t)ts * NU + rj) * a.PW + g0 / NPART] = v;
   };
-  load_inputs(H - 1);  // the forward sweep's last B2 ordered PHY's feature stores before these loads
-  for (int t = H - 1; t >= 0; --t) {
-    indep();
-    load_inputs(t > 0 ? t - 1 : 0);  // requested one step ahead
-    ws_sync<Cfg::THREADS>();  // B3: cotangents of the network outputs are there
-    if (t + 1 < H) sum_row(t + 1);  // the row PHY finished before this barrier
-    float gF[3], gM[3], giA[RS::NIA], giB[RS::NIB];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      gF[k] = xch[(Cfg::B_GF + k) * NPART + pl];
-      gM[k] = xch[(Cfg::B_GM + k) * NPART + pl];
-    }
-    if constexpr (RS::HAS_F) {
-#pragma unroll
-      for (int m = 0; m < M8::TB1A; ++m) ctx.d1[m] = dA1[m];
-#pragma unroll
-      for (int m = 0; m < M8::TB2A; ++m) ctx.d2[m] = dA2[m];
-      Ev::template bwd<NetA>(rA, ctx, gF, giA);
-    }
-    if constexpr (RS::HAS_M) {
-#pragma unroll
-      for (int m = 0; m < M8::TB1B; ++m) ctx.d1[m] = dB1[m];
-#pragma unroll
-      for (int m = 0; m < M8::TB2B; ++m) ctx.d2[m] = dB2[m];
-      Ev::template bwd<NetB>(rB, ctx, gM, giB);
-    }
-    {  // replicated results: lane k publishes component k
-      float* out = xch + pl;
-      if constexpr (RS::HAS_F) {
-#pragma unroll
-        for (int k = 0; k < NetA::IN; ++k)
-          if (l == (k & (L - 1))) out[(Cfg::B_GIA + k) * NPART] = giA[k];
-      }
-      if constexpr (RS::HAS_M) {
-#pragma unroll
-        for (int k = 0; k < NetB::IN; ++k)
-          if (l == ((k + 3) & (L - 1))) out[(Cfg::B_GIB + k) * NPART] = giB[k];
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (l == ((k + 1) & (L - 1))) out[(Cfg::B_FN + k) * NPART] = Fn[k];
-    }
-    ws_sync<Cfg::THREADS>();  // B4
+  for (int ts = H - 1; ts >= 0; --ts) {
+    ws_sync<Cfg::THREADS>();  // B4 of step ts: PHY stored row ts + 1 before it and rewrites the slot only after it
+    if (ts + 1 < H) sum_row(ts + 1);
   }
   ws_sync<Cfg::THREADS>();
   sum_row(0);
 }
 
-// One CTA = NPART particles: warp 0 is the PHY role, then NPART/4 DENS warps, then NPART/8 RES warps.
+// One CTA = 16 particles, four warps: PHY, DENS, RES, AUX -- warp k of every CTA lands on scheduler k of its SM, so each
+// scheduler (and its L0 instruction cache) runs the code of ONE role.
 // Requirements checked by the launcher: value + gradient, in-kernel threefry noise, no state constraints.
-template <class A, int NPART, bool PLAINC>
-__global__ void __launch_bounds__((WsCfg<A, NPART>::THREADS), (32 / NPART))  // 32 particles per SM resident (<= 16 warps: 128 registers)
-    k_cost_ws(const __grid_constant__ sde4_model_desc d, const __grid_constant__ sde4_cost_desc cd,
-              const __grid_constant__ sde4_cost_desc td, const __grid_constant__ CostK a, float* ftape) {
-  using Cfg = WsCfg<A, NPART>;
+template <class A, bool PLAINC>
+__global__ void __launch_bounds__(128, 3) k_cost_ws(const __grid_constant__ sde4_model_desc d,
+                                                    const __grid_constant__ sde4_cost_desc cd,
+                                                    const __grid_constant__ sde4_cost_desc td,
+                                                    const __grid_constant__ CostK a, float* ftape) {
+  using Cfg = WsCfg<A>;
+  constexpr int NPART = Cfg::NPART;
   extern __shared__ __align__(16) float W[];
   __shared__ __align__(8) uint64_t mbar;
   stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar);
   Diffusion<typename Cfg::M8>::derive(W);
-  float* xch = W + A::SMEM_FLOATS;
-  if (threadIdx.x < Cfg::N_PRIOR) xch[Cfg::VALS * NPART + threadIdx.x] = threadIdx.x < 13 ? d.noise_prior[threadIdx.x] : 0.0f;
+  float4* tiles = reinterpret_cast<float4*>(W + Cfg::OFF_TILES);
+  float* xch = W + Cfg::OFF_XCH;
+  {  // fragment image, zeroed exchange buffer (dw of noise-free states stays 0), noise prior and noise-state list
+    Cfg::MD::build(tiles + Cfg::TILE_D * 32, W + A::OFF_DENSITY, threadIdx.x, Cfg::THREADS);
+    Cfg::MA::build(tiles + Cfg::TILE_A * 32, W + A::OFF_NET_A, threadIdx.x, Cfg::THREADS);
+    Cfg::MB::build(tiles + Cfg::TILE_B * 32, W + A::OFF_NET_B, threadIdx.x, Cfg::THREADS);
+    for (int i = threadIdx.x; i < Cfg::VALS * NPART; i += Cfg::THREADS) xch[i] = 0.0f;
+    if (threadIdx.x == 0) {
+      int* nzlist = reinterpret_cast<int*>(W + Cfg::OFF_MISC + 16);
+      int c = 0;
+      for (int i = 0; i < 13; ++i)
+        if (d.noise_prior[i] != 0.0f) nzlist[c++] = i;
+      for (; c < 16; ++c) nzlist[c] = 0;
+    }
+  }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool phy = warp == 0, dens = warp <= Cfg::WN;
-  const int pl = phy ? (lane & (NPART - 1))
-                     : (dens ? ((warp - 1) * 32 + lane) / Cfg::LN : ((warp - 1 - Cfg::WN) * 32 + lane) / Cfg::LR);
-  const int g0 = blockIdx.x * NPART + pl;
-  // inactive lanes (beyond G; PHY lanes beyond NPART) shadow a valid sample, contribute nothing
-  const bool active = g0 < a.G && (!phy || lane < NPART);
-  const int g = g0 < a.G ? g0 : a.G - 1;
+  const int g0 = blockIdx.x * NPART;                            // first sample of this CTA
+  const int pl = lane & (NPART - 1);                             // PHY / RES-noise: particle of this lane
+  const bool in_range = g0 + pl < a.G;
+  const bool active = in_range && lane < NPART;                  // one lane per particle stores
+  const int g = in_range ? g0 + pl : a.G - 1;                    // lanes beyond G shadow the last sample
   const int p = g / a.N, n = g - p * a.N;
   const int pd = p % a.data_mod;
   if (a.mask) {  // CTA-uniform exit (the roles meet at CTA-wide barriers)
     const int on = __ldg(a.mask + p) != 0;
     if (!__syncthreads_or(on)) return;
   }
-  if (phy) ws_role_phy<Cfg, PLAINC>(W, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
-  else if (dens) ws_role_dens<Cfg>(W, xch, d, a, pl, g, n, pd, active);
-  else ws_role_res<Cfg>(W, xch, d, a, ftape, pl, g, active);
+  if (warp == 0) ws_role_phy<Cfg, PLAINC>(W, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
+  else if (warp == 1) ws_role_dens<Cfg>(W, tiles, xch, d, a, g0, a.G - 1);
+  else if (warp == 2) ws_role_res<Cfg>(W, tiles, xch, d, a, ftape, g0, a.G - 1);
+  else ws_role_aux<Cfg>(xch, d, a, g0, in_range, n, pd);
 }
 
 }  // namespace sde4

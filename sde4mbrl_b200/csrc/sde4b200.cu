@@ -434,7 +434,9 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
       if (!wse)
         return fail(SDE4_ERR_UNSUPPORTED, "no warp-specialised kernel for this call (%s; needs value + gradient, "
                     "threefry noise, no state constraints)", e->name);
-    } else if (a->lanes == 0 && ws_ok && G * 8 <= 40960) {
+    } else if (a->lanes == 0 && ws_ok && G >= 2048 && G <= 98304) {
+      // scripts/ws_sizes.py (hexacopter, H = 20): level with the 8-lane kernel up to ~1 k samples, 13-25 % ahead of the
+      // best lane-split kernel from 3.5 k to 65 k samples, behind the one-thread-per-sample kernel at 131 k
       wse = find_ws(*model);
     }
   }
