@@ -270,61 +270,58 @@ struct AFrag {
 // Accumulator of one 16x8 output tile, one register tile per 3xTF32 term: the three products of a k-step go to
 // different accumulators, so the dependent MMA chain of a layer is its number of k-steps, not three times that
 // (the density value + gradient pass had 51 MMAs in a row on its critical path).
-#ifndef SDE4_WS_NACC
-#define SDE4_WS_NACC 1  // accumulator tiles per 3xTF32 term set (1: smallest code; 2 / 3: one tile per term)
-#endif
-#ifndef SDE4_WS_KSPLIT
-#define SDE4_WS_KSPLIT 0  // 1: even and odd k-steps of a layer accumulate into different tiles (half the dependent chain)
-#endif
-struct Acc3 {
-  float hh[4];
-#if SDE4_WS_NACC >= 2
-  float hl[4];
-#endif
-#if SDE4_WS_NACC >= 3
-  float lh[4];
-#endif
+// Accumulator of one 16x8 output tile.  FAST: one register tile per 3xTF32 term and per k-step parity -- the dependent
+// MMA chain of a layer is then ceil(k-steps / 2) instead of 3 * k-steps (HMMA latency is ~45 cycles here and the density
+// value + gradient pass had 51 MMAs in a row); the compact form keeps one tile (smallest code).
+template <bool FAST>
+struct AccT {
+  static constexpr int NTILE = FAST ? 6 : 1;
+  float t[NTILE][4];
   SDE4_DEV void init(float c0, float c1) {
-    hh[0] = hh[2] = c0;
-    hh[1] = hh[3] = c1;
-#if SDE4_WS_NACC >= 2
+    t[0][0] = t[0][2] = c0;
+    t[0][1] = t[0][3] = c1;
 #pragma unroll
-    for (int r = 0; r < 4; ++r) hl[r] = 0.0f;
-#endif
-#if SDE4_WS_NACC >= 3
-#pragma unroll
-    for (int r = 0; r < 4; ++r) lh[r] = 0.0f;
-#endif
+    for (int k = 1; k < NTILE; ++k) t[k][0] = t[k][1] = t[k][2] = t[k][3] = 0.0f;
   }
-  // += A * B for one 8x8 weight tile (x, y = b0, b1 hi; z, w = b0, b1 lo); small terms first when they share a tile
-  SDE4_DEV void mma(const AFrag& a, const float4& b) {
-#if SDE4_WS_NACC >= 3
-    mma_tf32(hh, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
-    mma_tf32(hl, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
-    mma_tf32(lh, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
-#elif SDE4_WS_NACC == 2
-    mma_tf32(hl, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
-    mma_tf32(hh, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
-    mma_tf32(hl, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
-#else
-    mma_tf32(hh, a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
-    mma_tf32(hh, a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
-    mma_tf32(hh, a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
-#endif
+  // += A * B for one 8x8 weight tile (x, y = b0, b1 hi; z, w = b0, b1 lo) of k-step j
+  SDE4_DEV void mma(const AFrag& a, const float4& b, int j) {
+    if constexpr (FAST) {
+      const int o = (j & 1) * 3;
+      mma_tf32(t[o], a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32(t[o + 1], a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+      mma_tf32(t[o + 2], a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+    } else {  // small terms first
+      mma_tf32(t[0], a.lo, __float_as_uint(b.x), __float_as_uint(b.y));
+      mma_tf32(t[0], a.hi, __float_as_uint(b.z), __float_as_uint(b.w));
+      mma_tf32(t[0], a.hi, __float_as_uint(b.x), __float_as_uint(b.y));
+    }
   }
-  SDE4_DEV void sum(float (&c)[4]) const {
+  SDE4_DEV void sum(float (&c)[4], int ksteps) const {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-#if SDE4_WS_NACC >= 3
-      c[r] = hh[r] + (hl[r] + lh[r]);
-#elif SDE4_WS_NACC == 2
-      c[r] = hh[r] + hl[r];
-#else
-      c[r] = hh[r];
-#endif
+      if constexpr (FAST) {
+        float v = t[0][r] + (t[1][r] + t[2][r]);
+        if (ksteps > 1) v += t[3][r] + (t[4][r] + t[5][r]);
+        c[r] = v;
+      } else {
+        c[r] = t[0][r];
+      }
     }
   }
 };
+
+// which passes use the FAST accumulators.  Measured on C3 (scripts/ws_time.py): none 0.358 ms, forward passes 0.358 ms,
+// + residual-net backward 0.385 ms, all 0.476 ms -- the launch is bound by instruction fetch (four roles share the SM's
+// instruction cache), not by the MMA chains, so the compact accumulators stay the default.
+#ifndef SDE4_WS_FAST_FWD
+#define SDE4_WS_FAST_FWD false
+#endif
+#ifndef SDE4_WS_FAST_RESB
+#define SDE4_WS_FAST_RESB false
+#endif
+#ifndef SDE4_WS_FAST_DENSB
+#define SDE4_WS_FAST_DENSB false
+#endif
 
 template <class N>
 struct MmaNet {
@@ -374,15 +371,9 @@ struct MmaNet {
     }
   }
 
-  // bias of columns 2t, 2t+1 of tile n (both rows)
-  SDE4_DEV static void bias_tile(const float* b, int n, int t, Acc3& c) {
-    const float2 v = *reinterpret_cast<const float2*>(b + 8 * n + 2 * t);
-    c.init(v.x, v.y);
-  }
-
   // forward for the 16 particles of this warp: out tile = columns 2t, 2t+1 (< OUT) of rows g, g+8.
   // KEEP: act' of both hidden layers stays in d1 / d2 (accumulator layout) for the backward pass.
-  template <bool KEEP>
+  template <bool KEEP, bool FAST>
   SDE4_DEV static void fwd(const float4* tiles, const float* w, int lane, const float (&ain)[4], float (&out)[4],
                            float (&d1)[NT1][4], float (&d2)[NT2][4]) {
     const int t = lane & 3;
@@ -391,10 +382,11 @@ struct MmaNet {
     float c1[NT1][4];
 #pragma unroll
     for (int n = 0; n < NT1; ++n) {
-      Acc3 acc;
-      bias_tile(w + N::OFF_B0, n, t, acc);
-      acc.mma(a, tiles[(T_L1 + n) * 32 + lane]);
-      acc.sum(c1[n]);
+      AccT<FAST> acc;
+      const float2 b = *reinterpret_cast<const float2*>(w + N::OFF_B0 + 8 * n + 2 * t);
+      acc.init(b.x, b.y);
+      acc.mma(a, tiles[(T_L1 + n) * 32 + lane], 0);
+      acc.sum(c1[n], 1);
     }
 #pragma unroll
     for (int n = 0; n < NT1; ++n) {
@@ -406,30 +398,20 @@ struct MmaNet {
     }
     float c2[NT2][4];
     {
-      constexpr bool KS = SDE4_WS_KSPLIT && NT1 >= 2;
-      Acc3 acc[NT2], odd[KS ? NT2 : 1];
+      AccT<FAST> acc[NT2];
 #pragma unroll
-      for (int n = 0; n < NT2; ++n) bias_tile(w + N::OFF_B1, n, t, acc[n]);
-      if constexpr (KS) {
-#pragma unroll
-        for (int n = 0; n < NT2; ++n) odd[n].init(0.0f, 0.0f);
+      for (int n = 0; n < NT2; ++n) {
+        const float2 b = *reinterpret_cast<const float2*>(w + N::OFF_B1 + 8 * n + 2 * t);
+        acc[n].init(b.x, b.y);
       }
 #pragma unroll
       for (int j = 0; j < NT1; ++j) {
         a.from_tile(c1[j]);
 #pragma unroll
-        for (int n = 0; n < NT2; ++n) ((KS && (j & 1)) ? odd[n] : acc[n]).mma(a, tiles[(T_L2 + j * NT2 + n) * 32 + lane]);
+        for (int n = 0; n < NT2; ++n) acc[n].mma(a, tiles[(T_L2 + j * NT2 + n) * 32 + lane], j);
       }
 #pragma unroll
-      for (int n = 0; n < NT2; ++n) {
-        acc[n].sum(c2[n]);
-        if constexpr (KS) {
-          float o[4];
-          odd[n].sum(o);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) c2[n][r] += o[r];
-        }
-      }
+      for (int n = 0; n < NT2; ++n) acc[n].sum(c2[n], NT1);
     }
 #pragma unroll
     for (int n = 0; n < NT2; ++n) {
@@ -440,77 +422,50 @@ struct MmaNet {
       }
     }
     {
-      constexpr bool KS = SDE4_WS_KSPLIT && NT2 >= 2;
-      Acc3 acc, odd;
+      AccT<FAST> acc;
       acc.init(2 * t < N::OUT ? w[N::OFF_B2 + 2 * t] : 0.0f, 2 * t + 1 < N::OUT ? w[N::OFF_B2 + 2 * t + 1] : 0.0f);
-      odd.init(0.0f, 0.0f);
 #pragma unroll
       for (int j = 0; j < NT2; ++j) {
         a.from_tile(c2[j]);
-        ((KS && (j & 1)) ? odd : acc).mma(a, tiles[(T_L3 + j) * 32 + lane]);
+        acc.mma(a, tiles[(T_L3 + j) * 32 + lane], j);
       }
-      acc.sum(out);
-      if constexpr (KS) {
-        float o[4];
-        odd.sum(o);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) out[r] += o[r];
-      }
+      acc.sum(out, NT2);
     }
   }
 
   // g2 (cotangent of the pre-activation of layer 2, accumulator layout) -> input cotangent tile:
   // gin = columns 2t, 2t+1 (< IN) of rows g, g+8
+  template <bool FAST>
   SDE4_DEV static void bwd_from_g2(const float4* tiles, int lane, const float (&g2)[NT2][4], const float (&d1)[NT1][4],
                                    float (&gin)[4]) {
     AFrag a;
     float g1[NT1][4];
     {
-      constexpr bool KS = SDE4_WS_KSPLIT && NT2 >= 2;
-      Acc3 acc[NT1], odd[KS ? NT1 : 1];
+      AccT<FAST> acc[NT1];
 #pragma unroll
       for (int n = 0; n < NT1; ++n) acc[n].init(0.0f, 0.0f);
-      if constexpr (KS) {
-#pragma unroll
-        for (int n = 0; n < NT1; ++n) odd[n].init(0.0f, 0.0f);
-      }
 #pragma unroll
       for (int j = 0; j < NT2; ++j) {
         a.from_tile(g2[j]);
 #pragma unroll
-        for (int n = 0; n < NT1; ++n) ((KS && (j & 1)) ? odd[n] : acc[n]).mma(a, tiles[(T_W1T + j * NT1 + n) * 32 + lane]);
+        for (int n = 0; n < NT1; ++n) acc[n].mma(a, tiles[(T_W1T + j * NT1 + n) * 32 + lane], j);
       }
 #pragma unroll
-      for (int n = 0; n < NT1; ++n) {
-        acc[n].sum(g1[n]);
-        if constexpr (KS) {
-          float o[4];
-          odd[n].sum(o);
-#pragma unroll
-          for (int r = 0; r < 4; ++r) g1[n][r] += o[r];
-        }
-      }
+      for (int n = 0; n < NT1; ++n) acc[n].sum(g1[n], NT2);
     }
-    constexpr bool KS0 = SDE4_WS_KSPLIT && NT1 >= 2;
-    Acc3 acc, odd;
+    AccT<FAST> acc;
     acc.init(0.0f, 0.0f);
-    odd.init(0.0f, 0.0f);
 #pragma unroll
     for (int j = 0; j < NT1; ++j) {
 #pragma unroll
       for (int r = 0; r < 4; ++r) g1[j][r] *= d1[j][r];
       a.from_tile(g1[j]);
-      ((KS0 && (j & 1)) ? odd : acc).mma(a, tiles[(T_W0T + j) * 32 + lane]);
+      acc.mma(a, tiles[(T_W0T + j) * 32 + lane], j);
     }
-    acc.sum(gin);
-    if constexpr (KS0) {
-      float o[4];
-      odd.sum(o);
-#pragma unroll
-      for (int r = 0; r < 4; ++r) gin[r] += o[r];
-    }
+    acc.sum(gin, NT1);
   }
   // output cotangent (A operand in its own order: a0 = gout[g][t], a1 = gout[g+8][t], a2 = a3 = 0) -> input cotangent
+  template <bool FAST>
   SDE4_DEV static void bwd(const float4* tiles, int lane, const float (&agout)[4], const float (&d1)[NT1][4],
                            const float (&d2)[NT2][4], float (&gin)[4]) {
     AFrag a;
@@ -518,22 +473,23 @@ struct MmaNet {
     float g2[NT2][4];
 #pragma unroll
     for (int n = 0; n < NT2; ++n) {
-      Acc3 acc;
+      AccT<FAST> acc;
       acc.init(0.0f, 0.0f);
-      acc.mma(a, tiles[(T_W2T + n) * 32 + lane]);
-      acc.sum(g2[n]);
+      acc.mma(a, tiles[(T_W2T + n) * 32 + lane], 0);
+      acc.sum(g2[n], 1);
 #pragma unroll
       for (int r = 0; r < 4; ++r) g2[n][r] *= d2[n][r];
     }
-    bwd_from_g2(tiles, lane, g2, d1, gin);
+    bwd_from_g2<FAST>(tiles, lane, g2, d1, gin);
   }
   // scalar-output network: value (column 0 of `out`, threads with t == 0) and the input gradient d out / d in
+  template <bool FAST>
   SDE4_DEV static void value_grad(const float4* tiles, const float* w, int lane, const float (&ain)[4], float (&out)[4],
                                   float (&gin)[4]) {
     static_assert(N::OUT == 1, "scalar-output network expected");
     const int t = lane & 3;
     float d1[NT1][4], d2[NT2][4];
-    fwd<true>(tiles, w, lane, ain, out, d1, d2);
+    fwd<true, FAST>(tiles, w, lane, ain, out, d1, d2);
 #pragma unroll
     for (int n = 0; n < NT2; ++n) {
       const float2 v = *reinterpret_cast<const float2*>(w + N::OFF_W2 + 8 * n + 2 * t);
@@ -542,7 +498,7 @@ struct MmaNet {
       d2[n][2] *= v.x;
       d2[n][3] *= v.y;
     }
-    bwd_from_g2(tiles, lane, d2, d1, gin);
+    bwd_from_g2<FAST>(tiles, lane, d2, d1, gin);
   }
 };
 
@@ -917,7 +873,7 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
     float az[4], out[4];
     a_from_xch<NPART>(xch, Cfg::X_Z, NZ, lane, ident, az);
     float d1[MD::NT1][4], d2[MD::NT2][4];
-    MD::template fwd<false>(tD, wD, lane, az, out, d1, d2);
+    MD::template fwd<false, SDE4_WS_FAST_FWD>(tD, wD, lane, az, out, d1, d2);
     // density of rows g, g+8 sits in column 0 (threads with t == 0): hand it to the quad, thread t forms eta_t, eta_{t+4}
     const float dg = __shfl_sync(0xffffffffu, out[0], lane & ~3), dg8 = __shfl_sync(0xffffffffu, out[2], lane & ~3);
 #pragma unroll
@@ -950,7 +906,7 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
   load_inputs(H - 1);  // the forward sweep's last B2 ordered PHY's checkpoint stores before these loads
   for (int ts = H - 1; ts >= 0; --ts) {
     float out[4], J[4];
-    MD::value_grad(tD, wD, lane, az, out, J);
+    MD::template value_grad<SDE4_WS_FAST_DENSB>(tD, wD, lane, az, out, J);
     load_inputs(ts > 0 ? ts - 1 : 0);
     ws_sync3();  // B3 (PHY has read the previous item by now)
     if (t == 0) {
@@ -989,8 +945,8 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
     a_from_xch<NPART>(xch, Cfg::X_IN6, NetA::IN, lane, idxA, aA);
     a_from_xch<NPART>(xch, Cfg::X_IN6, NetB::IN, lane, idxB, aB);
     float dA1[MA::NT1][4], dA2[MA::NT2][4], dB1[MB::NT1][4], dB2[MB::NT2][4];
-    MA::template fwd<false>(tA, wA, lane, aA, Fn, dA1, dA2);
-    MB::template fwd<false>(tB, wB, lane, aB, Mn, dB1, dB2);
+    MA::template fwd<false, SDE4_WS_FAST_FWD>(tA, wA, lane, aA, Fn, dA1, dA2);
+    MB::template fwd<false, SDE4_WS_FAST_FWD>(tB, wB, lane, aB, Mn, dB1, dB2);
     tile_to_xch<NPART>(xch, Cfg::X_FN, 3, lane, Fn);
     tile_to_xch<NPART>(xch, Cfg::X_MN, 3, lane, Mn);
     ws_sync<Cfg::THREADS>();  // B2
@@ -1014,15 +970,15 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
   load_inputs(H - 1);  // the forward sweep's last B2 ordered PHY's feature stores before these loads
   for (int ts = H - 1; ts >= 0; --ts) {
     float Mn_unused[4];
-    MA::template fwd<true>(tA, wA, lane, aA, Fn, dA1, dA2);  // cotangent independent: ahead of the barrier
-    MB::template fwd<true>(tB, wB, lane, aB, Mn_unused, dB1, dB2);
+    MA::template fwd<true, SDE4_WS_FAST_RESB>(tA, wA, lane, aA, Fn, dA1, dA2);  // cotangent independent: ahead of the barrier
+    MB::template fwd<true, SDE4_WS_FAST_RESB>(tB, wB, lane, aB, Mn_unused, dB1, dB2);
     load_inputs(ts > 0 ? ts - 1 : 0);  // requested one step ahead
     ws_sync3();  // B3: cotangents of the network outputs are there
     float agF[4], agM[4], giA[4], giB[4];
     a_from_xch<NPART>(xch, Cfg::B_GF, 3, lane, [](int k) { return k; }, agF);
     a_from_xch<NPART>(xch, Cfg::B_GM, 3, lane, [](int k) { return k; }, agM);
-    MA::bwd(tA, lane, agF, dA1, dA2, giA);
-    MB::bwd(tB, lane, agM, dB1, dB2, giB);
+    MA::template bwd<SDE4_WS_FAST_RESB>(tA, lane, agF, dA1, dA2, giA);
+    MB::template bwd<SDE4_WS_FAST_RESB>(tB, lane, agM, dB1, dB2, giB);
     tile_to_xch<NPART>(xch, Cfg::B_GIA, NetA::IN, lane, giA);
     tile_to_xch<NPART>(xch, Cfg::B_GIB, NetB::IN, lane, giB);
     tile_to_xch<NPART>(xch, Cfg::B_FN, 3, lane, Fn);

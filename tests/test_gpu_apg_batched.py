@@ -116,3 +116,56 @@ def test_progressive_line_search_gives_the_same_solution(cuda, N):
     np.testing.assert_allclose(ca, cb, rtol=1e-6)
     assert hp.rel_err(xa, xb) < 1e-6
     assert (la > 1.0).any() and (da == 0).any()  # back-tracking and early stopping both happened
+
+
+@pytest.mark.parametrize("mode", ["merge", "two_launch", "speculative"])
+@pytest.mark.parametrize("rtol", [0.0, 0.05])
+def test_batched_apg_against_oracle_apg_and_oracle_cost(cuda, mode, rtol):
+    """The device-side solver against the ORACLE end to end -- oracle/apg_oracle.py (apg.py restated with Python control
+    flow) driving the torch oracle's cost and autograd gradient, on the noise the kernels draw (regenerated by the
+    oracle's jax.random restatement) -- field by field, including the early-stop masks (rtol > 0).  No product code on
+    the reference side of this comparison."""
+    from oracle import apg_oracle, nsde_oracle as orc
+    from sde4mbrl_b200 import nsde
+    from sde4mbrl_b200.apg_batched import BatchedAPG
+    P, H, N, iters = 4, 12, 4, 7
+    pm = configs.hexa_model(horizon=H, num_particles=N, stepsize=0.05)
+    mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=N, max_iter=iters)
+    mpc["apg_mpc"]["rtol"] = rtol
+    with contextlib.redirect_stdout(_io.StringIO()):
+        _, multi_cost, _, _, construct_opt = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.SDERotorModel)
+    nn = configs.random_params(sde_models.SDERotorModel(pm), seed=5)
+    cp, op = mpc["cost_params"], mpc["apg_mpc"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    rng = np.random.default_rng(17)
+    y0 = np.stack([hp.start_state("hexa", rng) for _ in range(P)])
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    keys = tf.split(tf.PRNGKey(77), P)
+    x0 = construct_opt(u=np.full(6, 0.33, np.float32))
+    x0 = np.asarray(x0.cpu() if isinstance(x0, torch.Tensor) else x0, np.float32)
+    kw = {"merge": dict(merge_xv_grad=True), "two_launch": dict(merge_xv_grad=False), "speculative": dict(speculative=True)}[mode]
+    solver = BatchedAPG(multi_cost.engine, nn, stage, op, multi_cost.time_steps, N, lb=1e-4, ub=1.0, **kw)
+    solver.init(x0, y0, xref, keys).run()
+    xb = solver.x_opt().cpu().numpy()
+    om = hp.oracle_model("hexa", pm, nn)
+    ts = orc.compute_timesteps(pm)
+    lb, ub = torch.full((6,), 1e-4), torch.ones(6)
+    prox = lambda x, stepsize=None: torch.minimum(torch.maximum(x, lb), ub)
+    n_done = 0
+    for p in range(P):
+        _, dw = orc.sample_rollouts(om, y0[p], x0, keys[p], N)
+
+        def cost_fn(o, p=p, dw=dw):
+            c, _ = orc.compute_cost(om, torch.tensor(y0[p]), o, dw, hp.stage_cost_fn("hexa", cp), torch.tensor(xref))
+            return c + orc.u_slew_cost(o, ts, cp, 6)
+        s = apg_oracle.apg(apg_oracle.init_apg(torch.tensor(x0), cost_fn, op), cost_fn, op, proximal_fn=prox)
+        sb = solver.state_of(p)
+        assert sb.num_steps == int(s.num_steps) and bool(sb.not_done) == bool(s.not_done)
+        assert sb.num_iter_no_improv == int(s.num_iter_no_improv)
+        for f in ("opt_cost", "curr_cost", "init_cost", "stepsize", "avg_stepsize", "momentum", "avg_linesearch"):
+            np.testing.assert_allclose(float(getattr(sb, f)), float(getattr(s, f)), rtol=2e-4, atol=1e-7, err_msg=f)
+        assert hp.rel_err(xb[p], s.x_opt.detach().numpy()) < 2e-3
+        n_done += int(not bool(s.not_done))
+    if rtol > 0:
+        assert n_done > 0

@@ -9,7 +9,7 @@ import pytest
 import torch
 
 import helpers as hp
-from oracle import c_oracle
+from oracle import c_oracle, packer
 from oracle import nsde_oracle as orc
 from oracle import threefry as tf
 from sde4mbrl_b200 import configs, costs, sde_models
@@ -42,9 +42,11 @@ def test_c3_full_size_against_c_oracle(cuda):
     key = tf.PRNGKey(2050)
     c, g, xt = eng.cost_grad(nn, y0[None], opt, ts, xref, stage.desc, key=key, N=N, want_xtraj=True)
     c, g, xt = float(c[0]), g.cpu().numpy(), xt.cpu().numpy()
-    desc = model.describe()
-    cw, gw, xw = c_oracle.rotor_cost_grad(desc, stage.desc, model.pack(nn, desc), y0, opt, ts, xref, N, key=key,
-                                          want_xtraj=True)
+    # descriptors and parameter block of the C oracle come from oracle/packer.py (straight from the params dict and the
+    # haiku tree), NOT from the product's describe() / pack(): a packer error is not common mode here
+    odesc = packer.rotor_desc(pm)
+    cw, gw, xw = c_oracle.rotor_cost_grad(odesc, packer.rotor_track_cost_desc(cp, 6), packer.rotor_pack(pm, nn, odesc), y0,
+                                          opt, ts, xref, N, key=key, want_xtraj=True)
     assert abs(c - cw) <= 2e-5 * abs(cw)
     assert hp.rel_err(g, gw) < 1e-3
     got = np.transpose(xt[:, :13, :], (2, 0, 1))  # [N, H+1, 13]

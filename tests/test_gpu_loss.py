@@ -18,10 +18,13 @@ def _tree64(nn):
             for m, d in nn.items()}
 
 
+# scale = "yaml": the reference's initialiser ranges (weights ~1e-3 .. 1e-1), where an ABSOLUTE activation error is
+# largest relative to the hidden activations -- and the parameter gradients are what it would show up in
+@pytest.mark.parametrize("scale", ["fan_in", "yaml"])
 @pytest.mark.parametrize("kind,cls,oname,B,N,H", [("cartpole", sde_models.CartPoleSDE, "cart_pole_sde", 12, 2, 10),
                                                     ("cartpole_bb", sde_models.CartPoleSDE, "cart_pole_sde", 5, 1, 30),
                                                     ("msd", sde_models.MassSpringDamper, "mass_spring_damper", 7, 3, 20)])
-def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H):
+def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H, scale):
     from sde4mbrl_b200 import nsde, random as R
     mk = hp.KINDS[kind][0]
     pm = mk(horizon=1, num_particles=1)
@@ -30,7 +33,7 @@ def test_loss_and_param_grad(cuda, kind, cls, oname, B, N, H):
           "horizon": H, "obs_weights": ow, "pen_data": 1.0, "pen_weights": 1e-3, "default_weights": 1.0,
           "special_parameters_pen": {"scaler": 0, "density": 0}}
     _, loss_fn, nonneg, test_fn = nsde.create_model_loss_fn(pm, lp, sde_constr=cls, verbose=False)
-    nn = configs.random_params(cls(pm), seed=4)
+    nn = configs.random_params(cls(pm), seed=4, scale=scale)
     rng = np.random.default_rng(0)
     nx, nu = pm["n_x"], pm["n_u"]
     y = (rng.normal(0, 0.5, (B, H + 1, nx)) + (np.array([0, 0, 3.0, 0]) if nx == 4 else 0)).astype(np.float32)

@@ -17,11 +17,15 @@ pytestmark = pytest.mark.gpu
 CASES = [("msd", 100, 200), ("cartpole", 50, 96), ("cartpole_bb", 30, 33), ("hexa", 100, 64), ("hexa16", 20, 40)]
 
 
+# scale = "yaml": the reference's own initialiser ranges (weights ~1e-3 .. 1e-1) -- the regime where the
+# ABSOLUTE 1.5e-7 error of the MUFU tanh and the flush-to-zero ex2 / rcp are largest RELATIVE to the hidden activations.
+# The trajectory tolerances stay the same: the network outputs are small against the physics there.
+@pytest.mark.parametrize("scale", ["fan_in", "yaml"])
 @pytest.mark.parametrize("kind,H,N", CASES)
-def test_rollout_given_noise(cuda, kind, H, N):
+def test_rollout_given_noise(cuda, kind, H, N, scale):
     from sde4mbrl_b200.engine import Engine
     rng = np.random.default_rng(1)
-    pm, model, nn = hp.build(kind, H, N, seed=3)
+    pm, model, nn = hp.build(kind, H, N, seed=3, scale=scale)
     om = hp.oracle_model(kind, pm, nn)
     y0 = hp.start_state(kind, rng)
     u = hp.controls(kind, H, rng)
@@ -37,12 +41,13 @@ def test_rollout_given_noise(cuda, kind, H, N):
         assert np.max(np.abs(np.linalg.norm(got[:, 1:, 6:10], axis=-1) - 1.0)) < 5e-7
 
 
+@pytest.mark.parametrize("scale", ["fan_in", "yaml"])
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("kind,H,N", [("msd", 100, 200), ("cartpole", 50, 64), ("hexa", 100, 37)])
-def test_rollout_threefry_noise(cuda, kind, H, N, mode):
+def test_rollout_threefry_noise(cuda, kind, H, N, mode, scale):
     from sde4mbrl_b200.engine import Engine
     rng = np.random.default_rng(2)
-    pm, model, nn = hp.build(kind, H, N, seed=4)
+    pm, model, nn = hp.build(kind, H, N, seed=4, scale=scale)
     om = hp.oracle_model(kind, pm, nn)
     y0 = hp.start_state(kind, rng)
     u = hp.controls(kind, H, rng)
