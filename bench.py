@@ -36,6 +36,16 @@ F_VALGRAD_HEXA = 2.0 * 3880.0
 N_PART, HORIZON = 4096, 100
 
 
+def bench_config(gpus):
+    """`config` of the JSON line -- the SAME dict from both arms (the driver compares them)."""
+    return {"workload": "hexacopter nSDE (13 states, 6 rotors), 1 problem, 4096 particles per GPU x 100 steps, "
+                        "distance-aware diffusion with in-kernel threefry noise + gradient pass (BASELINE configs[2])",
+            "particles_per_gpu": N_PART, "horizon": HORIZON, "gpus": gpus,
+            "parallelism": "particles of the one problem sharded over the GPUs, one all-reduce of [cost, grad] (601 floats)",
+            "l2": "GPU arm: flushed between timed steps (256 MB write); CPU arm: 44 MB working set per step",
+            "timing": "GPU arm: CUDA events per step, max over ranks; CPU arm: perf_counter per step"}
+
+
 def build_workload(seed=0):
     from sde4mbrl_b200 import configs, costs, sde_models
     pm = configs.hexa_model(horizon=HORIZON, num_particles=N_PART, stepsize=0.01)
@@ -127,13 +137,14 @@ def cpu_reference_step(w, n_particles, threads):
     """One value+gradient evaluation with the CPU restatement of the reference's algorithm:
     oracle/c (plain C, AVX2/AVX-512 lanes over particles, OpenMP over particle chunks, in-line
     threefry noise) -- the kind of code XLA:CPU would emit for the reference's vmapped scan."""
-    from oracle import c_oracle
-    if "c_packed" not in w:
-        w["c_desc"] = w["model"].describe()
-        w["c_packed"] = w["model"].pack(w["nn"], w["c_desc"])
+    from oracle import c_oracle, packer
+    if "c_packed" not in w:  # descriptors and parameter block from the oracle-side packer: nothing of libsde4b200.so
+        w["c_desc"] = packer.rotor_desc(w["pm"])
+        w["c_cost"] = packer.rotor_track_cost_desc(w["cp"], 6)
+        w["c_packed"] = packer.rotor_pack(w["pm"], w["nn"], w["c_desc"])
     ts = np.full(HORIZON, 0.01, np.float32)
     t0 = time.perf_counter()
-    c, g, _ = c_oracle.rotor_cost_grad(w["c_desc"], w["stage"].desc, w["c_packed"], w["y0"], w["opt"], ts, w["xref"],
+    c, g, _ = c_oracle.rotor_cost_grad(w["c_desc"], w["c_cost"], w["c_packed"], w["y0"], w["opt"], ts, w["xref"],
                                        n_particles, key=w["key"], nthreads=threads)
     return time.perf_counter() - t0, c, g
 
@@ -145,22 +156,41 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     w = build_workload()
-    from oracle import c_oracle
-    simd = c_oracle.load().sde4o_simd_width()
-    n_sample = N_PART  # the C port is fast enough to run the full 4096-particle workload per step
-    for _ in range(max(1, min(args.warmup, 1))):
-        cpu_reference_step(w, n_sample, threads)
-    times = [cpu_reference_step(w, n_sample, threads)[0] for _ in range(args.steps)]
+    n_sample = N_PART  # both CPU arms run the full 4096-particle workload per step
+    warm = max(args.warmup, 3)
+    # first choice: the reference itself, jit-compiled by jax on the host cores (the arm the >= 100x target is defined
+    # on); only where jax + dm-haiku and a copy of the reference exist (baseline/ref_jax_cpu.py) -- not in the build image
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_jax_cpu
+    ok, why = ref_jax_cpu.available()
+    kind, sample = "port", None
+    if ok:
+        try:
+            from sde4mbrl_b200 import configs
+            mpc = configs.hexa_mpc(horizon=HORIZON, dt=0.01, num_particles=N_PART)
+            times = ref_jax_cpu.time_rotor_value_and_grad(w["pm"], mpc, w["cp"], w["nn"], w["y0"], w["opt"], w["key"],
+                                                          w["xref"], args.steps, warm)
+            kind = "jax"
+            sample = ("%d particles x %d steps value+grad per step; the unmodified reference, jax.jit(jax.value_and_grad("
+                      "cost_xt)) on the CPU backend" % (n_sample, HORIZON))
+        except Exception as ex:  # a broken jax install must not lose the arm
+            why = "jax arm failed: %r" % (ex,)
+            ok = False
+    if not ok:
+        from oracle import c_oracle
+        simd = c_oracle.load().sde4o_simd_width()
+        for _ in range(warm):
+            cpu_reference_step(w, n_sample, threads)
+        times = [cpu_reference_step(w, n_sample, threads)[0] for _ in range(args.steps)]
+        sample = ("%d particles x %d steps value+grad per step; oracle/c (C restatement of the reference, AVX-512/AVX2 + "
+                  "OpenMP, SIMD width %d) because %s" % (n_sample, HORIZON, simd, why))
     t = float(np.mean(times))
     val = n_sample * HORIZON / t
     line = {"impl": "reference", "metric": "particle-steps/s (value+grad, hexacopter nSDE)", "value": val,
-            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "unit": "particle-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": warm,
             "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "hexacopter nSDE, 1 problem, 4096 particles x 100 steps, diffusion + gradient pass "
-                                   "(BASELINE configs[2]); CPU arm runs the full workload per step"},
-            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": "port",
-                             "sample": "%d particles x %d steps value+grad per step; oracle/c (C, AVX-512/AVX2 + OpenMP, SIMD width %d)" % (n_sample, HORIZON, simd)},
+            "dtype": "f32", "data": "synthetic", "config": bench_config(args.gpus),
+            "cpu_baseline": {"value": val, "unit": "particle-steps/s", "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -176,6 +206,8 @@ def main():
                     help="diagnostic: how L2 is flushed between timed steps (the bench line is quoted with 'write')")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per sample (0 = library heuristic)")
+    ap.add_argument("--transport", default="fused", choices=["fused", "symm", "nccl"],
+                    help="cross-GPU sum of [cost, grad] at N > 1: folded into K3 (peer loads over NVLink), torch one-shot, NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -205,14 +237,13 @@ def main():
     red = torch.zeros(HORIZON * 6 + 1, device=dev)
     # N > 1: K3 writes its [cost | grad] straight into the reducer's (symmetric-memory) buffer, ONE small all-reduce
     from sde4mbrl_b200.dist import CostGradReducer
-    reducer = CostGradReducer(HORIZON * 6 + 1, dev, grad_shape=(HORIZON, 6)) if world > 1 else None
+    reducer = CostGradReducer(HORIZON * 6 + 1, dev, grad_shape=(HORIZON, 6), transport=args.transport) if world > 1 else None
 
     def step_device():
         if world > 1:
-            c_out, g_out = reducer.views(1)
             eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART, want_grad=True,
                           block_threads=args.block_threads, lanes=args.lanes, particle_offset=rank * N_PART,
-                          particle_total=n_total, cost_out=c_out, grad_out=g_out)
+                          particle_total=n_total, **reducer.launch_kwargs(1))
             tot = reducer.reduce()
             return tot[0:1], tot[1:].view(HORIZON, 6)
         cost, grad, _ = eng.cost_grad(pk, y0_d, opt_d, ts, xref_d, w["stage"].desc, key=key_d, N=N_PART,
@@ -289,7 +320,7 @@ def main():
     if world > 1:
         # N > 1: the same host-array call with the particles of the problem sharded over the ranks -- one packed pinned
         # H2D copy, K2 + K3 into the symmetric-memory buffer, one-shot all-reduce, one D2H copy (nsde.py, particle_reducer)
-        multi_cost.particle_reducer = CostGradReducer(HORIZON * 6 + 1, dev, grad_shape=(HORIZON, 6))
+        multi_cost.particle_reducer = CostGradReducer(HORIZON * 6 + 1, dev, grad_shape=(HORIZON, 6), transport=args.transport)
 
     def step_e2e():
         return step_e2e_host()
@@ -595,7 +626,7 @@ def main():
                 fl = L.C.c_double(0)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                L.check(L.load().sde4_fma_peak(variant, 148 * 8, 256, 4000, L.C.c_void_p(sink.data_ptr()),
+                L.check(L.load().sde4_fma_peak(variant, torch.cuda.get_device_properties(dev).multi_processor_count * 8, 256, 4000, L.C.c_void_p(sink.data_ptr()),
                                                L.C.byref(fl), L.C.c_void_p(torch.cuda.current_stream().cuda_stream)))
                 e1.record()
                 torch.cuda.synchronize()
@@ -630,7 +661,7 @@ def main():
             pass
         roof = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "hbm_view": hbm_view,
-                "traffic": 557312, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_cost launch, profiles/r1_m_kcost_ncu.txt (checkpoints stay in L2)", "peak_source": "measured in this run by sde4_fma_peak (FFMA / fma.rn.f32x2 loop)",
+                "traffic": 2199040, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_cost_ws launch, profiles/r2_c_ws_mma_ncu.txt (checkpoints stay in L2)", "peak_source": "measured in this run by sde4_fma_peak (FFMA / fma.rn.f32x2 loop)",
                 "peaks_tflops": peaks, "kernel_ms": k_ms,
                 "algorithmic_flop_per_launch": flop,
                 "note": "path is FP32-FMA bound (SURVEY 8d), not HBM/tensor; HBM write-out of this launch = %.1f MB"
@@ -653,7 +684,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_sample = N_PART
-            cpu_reference_step(w, n_sample, threads)
+            for _ in range(3):
+                cpu_reference_step(w, n_sample, threads)
             tcpu = [cpu_reference_step(w, n_sample, threads)[0] for _ in range(20)]
             v = n_sample * HORIZON / float(np.mean(tcpu))
             cpu_b = {"value": v, "unit": "particle-steps/s", "cores": threads, "kind": "port",
@@ -666,12 +698,9 @@ def main():
             "unit": "particle-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "hexacopter nSDE (13 states, 6 rotors), 1 problem, 4096 particles per GPU x 100 steps, "
-                                   "distance-aware diffusion with in-kernel threefry noise + gradient pass (BASELINE configs[2])",
-                       "particles_per_gpu": N_PART, "horizon": HORIZON, "parallelism": "particles sharded over %d GPU(s), one all-reduce of [cost, grad] (601 floats): %s"
-                       % (world, "none (1 GPU)" if world == 1 else
-                          ("torch symmetric-memory one-shot all-reduce over NVLink" if reducer.symm else "NCCL all-reduce")),
-                       "l2": {"write": "flushed between timed steps (256 MB write)", "write+read": "DIAGNOSTIC: 256 MB write then 256 MB read between timed steps", "none": "DIAGNOSTIC: not flushed"}[args.flush_mode], "timing": "CUDA events per step, max over ranks"},
+            "config": bench_config(world),
+            "collective": "none (1 GPU)" if world == 1 else reducer.transport,
+            "l2_flush": {"write": "256 MB write between timed steps", "write+read": "DIAGNOSTIC: 256 MB write then 256 MB read between timed steps", "none": "DIAGNOSTIC: not flushed"}[args.flush_mode],
             "clocks": clocks,
             "e2e": {"value": total_ps / e2e_s, "unit": "particle-steps/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s * 1e3,

@@ -183,6 +183,27 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, vo
  *      augmented_cost (rotor_uav/sde_mpc_design.py:73-167).
  *      cost[p] = mean_n sum_t 0.5*dt_t*(c_t + c_{t+1}) (+ terminal) (+ slew(opt_p));
  *      grad[p] = d cost[p] / d opt[p]   (same strides as opt). */
+/* Cross-GPU sum of [cost | grad] folded into the reduction kernel (K3), for ONE problem's particles sharded over up to 8
+ * GPUs of a box (jnp.mean over particles, sde4mbrl/nsde.py:1586, when the particles span devices).  Every rank's K3 writes
+ * its partial [cost[P] | grad[P][H][n_opt]] into ITS buffer of the epoch's parity; the last CTA of the grid then publishes
+ * the epoch in every peer's flag array (st.release.sys over NVLink), waits until every peer has published it
+ * (ld.acquire.sys), sums the world's buffers with peer loads in rank order -- the same bits on every rank -- and writes
+ * `out`.  Two launches per sharded evaluation (K2, K3) and no library collective.
+ * All pointers are device pointers valid in THIS process: buf[r] / flag[r] are rank r's allocations mapped here (CUDA IPC,
+ * torch symmetric memory, or plain peer access within one process).  The caller alternates buf between two buffers per
+ * rank by epoch parity (a rank may be one evaluation ahead of a peer, never two: it cannot pass the flag wait of epoch
+ * e + 1 before every peer has finished reading epoch e), starts `epoch` at 1 and uses the same sequence on every rank;
+ * flags and `counter` start at zero. */
+typedef struct sde4_xgpu_reduce {
+  int32_t world, rank;
+  int32_t n;                /* floats of [cost | grad] = P * (1 + H * n_opt)                          */
+  uint32_t epoch;
+  float* buf[8];            /* rank r's partial buffer of this epoch's parity, n floats               */
+  uint32_t* flag[8];        /* rank r's flag array, uint32[world]: slot s = last epoch rank s published */
+  float* out;               /* [n] summed result (local memory)                                       */
+  uint32_t* counter;        /* local uint32 (CTA ticket of K3)                                        */
+} sde4_xgpu_reduce;
+
 typedef struct sde4_cost_args {
   int32_t struct_size;
   int32_t P, N, H;
@@ -221,6 +242,10 @@ typedef struct sde4_cost_args {
    * sample g = p*N + n at time t+1 in step_weight[t*P*N + g] -- the 0/1 indicator of the time indexes
    * `num_sample2consider` keeps (sde4mbrl/nsde.py:753-760), see sde4_rng_choice_mask.  NULL: every step counts. */
   const float* step_weight;
+  /* optional HOST pointer: fold the cross-GPU sum of [cost | grad] into K3 (see sde4_xgpu_reduce).  `cost` / `grad` are
+   * then ignored -- the partials go to xgpu->buf[rank] and the summed result to xgpu->out as [cost[P] | grad[P][H][n_opt]];
+   * needs value + gradient.  NULL: single-device evaluation. */
+  const sde4_xgpu_reduce* xgpu;
 } sde4_cost_args;
 
 /* Upper bound over the lane / noise modes the launcher may pick. */

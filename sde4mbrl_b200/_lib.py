@@ -84,7 +84,13 @@ class CostArgs(C.Structure):
                 ("cost", C.c_void_p), ("grad", C.c_void_p), ("xtraj", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t), ("block_threads", C.c_int32),
                 ("particle_offset", C.c_int32), ("particle_total", C.c_int32), ("lanes", C.c_int32),
-                ("data_mod", C.c_int32), ("problem_mask", C.c_void_p), ("step_weight", C.c_void_p)]
+                ("data_mod", C.c_int32), ("problem_mask", C.c_void_p), ("step_weight", C.c_void_p),
+                ("xgpu", C.c_void_p)]
+
+
+class XgpuReduce(C.Structure):  # sde4_xgpu_reduce
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n", C.c_int32), ("epoch", C.c_uint32),
+                ("buf", C.c_void_p * 8), ("flag", C.c_void_p * 8), ("out", C.c_void_p), ("counter", C.c_void_p)]
 
 
 class ApgParams(C.Structure):

@@ -65,6 +65,15 @@ struct CostK {
   unsigned long long pd_stride;
 };
 
+struct XgpuK {  // sde4_xgpu_reduce, by value in the kernel parameters
+  int world, rank, n;
+  unsigned epoch;
+  float* buf[8];
+  unsigned* flag[8];
+  float* out;
+  unsigned* counter;
+};
+
 struct ReduceK {
   const float* gpart;
   const float* cpart;
@@ -79,6 +88,7 @@ struct ReduceK {
   int lpi;  // lanes per reduced item: 1 or 32
   float res_mult;
   float slew[SDE4_MAX_NU];
+  XgpuK x;  // x.world > 1: the last CTA sums the world's partial buffers (see sde4_xgpu_reduce)
 };
 
 // ------------------------------------------------------------------------------------------------

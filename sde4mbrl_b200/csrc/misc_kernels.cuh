@@ -32,7 +32,59 @@ SDE4_DEV float strided_sum(const float* __restrict__ src, int n, int sub, int lp
   return (s0 + s1) + (s2 + s3);
 }
 
+SDE4_DEV void k_reduce_body(const ReduceK& a);
+
+// ---- cross-GPU tail of K3 (sde4_xgpu_reduce): run by the LAST CTA of the grid -------------------------------------------
+SDE4_DEV void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+SDE4_DEV unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+SDE4_DEV float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+SDE4_DEV void xgpu_tail(const XgpuK& x) {
+  // every CTA's stores to this rank's buffer were ordered before its ticket (threadfence + atomic); this CTA took the
+  // last ticket, so after the fence below they are all visible at system scope before the flags go out
+  if (threadIdx.x < x.world && (int)threadIdx.x != x.rank) {
+    __threadfence_system();
+    st_release_sys(x.flag[threadIdx.x] + x.rank, x.epoch);               // "rank's partial of this epoch is in place"
+    while ((int)(ld_acquire_sys(x.flag[x.rank] + threadIdx.x) - x.epoch) < 0) {  // peer's partial is in place
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < x.n; i += blockDim.x) {
+    float s = 0.0f;
+    for (int r = 0; r < x.world; ++r) s += ld_relaxed_sys(x.buf[r] + i);  // rank order: identical bits on every rank
+    x.out[i] = s;
+  }
+}
+SDE4_DEV void xgpu_ticket(const XgpuK& x) {
+  if (x.world <= 1) return;
+  __shared__ unsigned last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(x.counter, 1u);
+    last = t == gridDim.x - 1 ? 1u : 0u;
+    if (last) *x.counter = 0u;  // ready for the next launch (stream ordered)
+  }
+  __syncthreads();
+  if (last) {
+    __threadfence();
+    xgpu_tail(x);
+  }
+}
+
 __global__ void k_reduce(const __grid_constant__ ReduceK a) {
+  k_reduce_body(a);
+  xgpu_ticket(a.x);
+}
+
+SDE4_DEV void k_reduce_body(const ReduceK& a) {
   const int lpi = a.lpi;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long idx = gid / lpi;

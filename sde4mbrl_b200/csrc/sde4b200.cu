@@ -540,6 +540,33 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   r.NP = L.NP;
   r.has_slew = (cd.has_slew && k.n_off == 0) ? 1 : 0;
   r.mask = a->problem_mask;
+  r.x.world = 0;
+  if (a->xgpu && !lo.enabled) {  // cross-GPU sum folded into K3 (sde4_xgpu_reduce)
+    const sde4_xgpu_reduce& x = *a->xgpu;
+    const long long n_opt_ll = e->nu + cd.n_slack;
+    if (x.world < 1 || x.world > 8 || x.rank < 0 || x.rank >= x.world) return fail(SDE4_ERR_INVALID, "xgpu: bad world / rank");
+    if (!a->grad && x.world > 1) return fail(SDE4_ERR_INVALID, "xgpu: needs value + gradient (pass any non-null grad)");
+    if (x.n != a->P * (1 + a->H * (int)n_opt_ll)) return fail(SDE4_ERR_INVALID, "xgpu: n must be P * (1 + H * n_opt)");
+    if (a->opt_stride_j != 1 || a->opt_stride_t != n_opt_ll || (a->P > 1 && a->opt_stride_p != (long long)a->H * n_opt_ll))
+      return fail(SDE4_ERR_INVALID, "xgpu: opt must be contiguous [P][H][n_opt] (the partial buffer is written with opt's strides)");
+    if (a->problem_mask) return fail(SDE4_ERR_UNSUPPORTED, "xgpu: problem_mask is not supported");
+    if (!x.out || !x.counter) return fail(SDE4_ERR_INVALID, "xgpu: null out / counter");
+    for (int q = 0; q < x.world; ++q)
+      if (!x.buf[q] || !x.flag[q]) return fail(SDE4_ERR_INVALID, "xgpu: null peer buffer / flag pointer");
+    r.x.world = x.world;
+    r.x.rank = x.rank;
+    r.x.n = x.n;
+    r.x.epoch = x.epoch;
+    for (int q = 0; q < 8; ++q) {
+      r.x.buf[q] = q < x.world ? x.buf[q] : nullptr;
+      r.x.flag[q] = q < x.world ? x.flag[q] : nullptr;
+    }
+    r.x.out = x.out;
+    r.x.counter = x.counter;
+    r.cost = x.buf[x.rank];
+    r.grad = x.buf[x.rank] + a->P;
+    r.o_sp = (long long)a->H * n_opt_ll;  // (P == 1 callers may pass any problem stride)
+  }
   r.res_mult = cd.res_mult;
   for (int j = 0; j < SDE4_MAX_NU; ++j) r.slew[j] = cd.u_slew_coeff[j];
   // value-only launches reduce the cost row only

@@ -246,7 +246,7 @@ class Engine:
     def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,
                   noise_mode=None, want_grad=True, want_xtraj=False, block_threads=0, grad_out=None,
                   particle_offset=0, particle_total=0, lanes=0, data_mod=0, cost_out=None, problem_mask=None,
-                  workspace=None):
+                  workspace=None, xgpu=None):
         """y0[P,n_x], opt[P,H,n_opt] (any strides) or [H,n_opt], xref[P,H+1,n_x] or [H+1,n_x].
         Returns (cost[P], grad (same shape/strides as opt) or None, xtraj[H+1,n_x+1,G] or None)."""
         self._em_only()
@@ -330,6 +330,8 @@ class Engine:
         a.block_threads = block_threads
         a.particle_offset, a.particle_total, a.lanes = particle_offset, particle_total, lanes
         a.data_mod = data_mod
+        if xgpu is not None:  # _lib.XgpuReduce: the cross-GPU sum of [cost | grad] happens inside K3 (dist.CostGradReducer)
+            a.xgpu = C.addressof(xgpu)
         if problem_mask is not None:  # int32[P] device tensor: problems with 0 are skipped, their outputs untouched
             assert problem_mask.dtype == torch.int32 and problem_mask.is_cuda and problem_mask.numel() == P
             a.problem_mask = problem_mask.data_ptr()

@@ -391,7 +391,7 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
         if red.n != n_o + 1:
             raise Sde4Error("particle_reducer must hold H*n_opt + 1 = %d floats" % (n_o + 1))
         host = is_host(y) and is_host(opt_params) and is_host(rng) and is_host(extra_cost_args)
-        dev = red.buf.device
+        dev = red.device
         if host:
             st = _stg.get(dev)
             if st is None:
@@ -411,11 +411,11 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
         else:
             y_t, opt_d, xref, key = as_f32(y), as_f32(opt_params), as_f32(extra_cost_args), as_key(rng)
         assert opt_d.dim() == 2 and opt_d.shape[-1] == opt_params_size, "one problem: opt_params must be [H, n_opt]"
-        c_out, g_out = red.views(1)
-        _, _, xbuf = engine.cost_grad(_nn_params, y_t.reshape(1, n_x), opt_d.detach(), time_steps, xref, stage.desc, terminal=term,
-                                      key=key, N=num_sample, want_grad=True, want_xtraj=True,
-                                      particle_offset=rank * num_sample, particle_total=world * num_sample,
-                                      cost_out=c_out, grad_out=g_out.view(1, H, opt_params_size))
+        kw = red.launch_kwargs(1)
+        kw["grad_out"] = kw["grad_out"].view(1, H, opt_params_size)
+        _, _, xbuf = engine.cost_grad(_nn_params, y_t.reshape(1, n_x), opt_d.detach().contiguous(), time_steps, xref, stage.desc,
+                                      terminal=term, key=key, N=num_sample, want_grad=True, want_xtraj=True,
+                                      particle_offset=rank * num_sample, particle_total=world * num_sample, **kw)
         tot = red.reduce()
         xtraj = xbuf.view(H + 1, n_x + 1, 1, num_sample).permute(2, 3, 0, 1)[0]
         if host:
