@@ -195,6 +195,120 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def mpc_batch_run(w, n_part, world, rank, dev, barrier, reps=4, e2e=False):
+    """BASELINE configs[3]: 4096 independent hexacopter MPC solves (H = 20, dt = 0.05, 20 APG iterations,
+    mpc_test_cfg.yaml), PARTITIONED over the ranks with no collective (strong scaling).  Device time per batch (CUDA
+    events, max over ranks); with `e2e` also the wall time from pinned host start states / keys to host controls."""
+    import torch
+    import torch.distributed as dist
+    from sde4mbrl_b200 import configs, sde_models
+    from sde4mbrl_b200.apg_batched import BatchedAPG
+    from sde4mbrl_b200.engine import Engine
+    P_TOTAL, HM = 4096, 20
+    p_lo, p_cnt = rank * (P_TOTAL // world), P_TOTAL // world
+    rngm = np.random.default_rng(123)
+    y0m = np.tile(w["y0"], (P_TOTAL, 1))
+    y0m[:, 3:6] += rngm.normal(0, 0.05, (P_TOTAL, 3)).astype(np.float32)
+    y0m[:, 10:13] += rngm.normal(0, 0.05, (P_TOTAL, 3)).astype(np.float32)
+    keysm = np.stack([np.zeros(P_TOTAL, np.uint32), np.arange(P_TOTAL, dtype=np.uint32)], axis=1)
+    xrefm = np.tile(w["xref"][:1], (HM + 1, 1))
+    pmm = configs.hexa_model(horizon=HM, num_particles=n_part, stepsize=0.05)
+    mpcm = configs.hexa_mpc(horizon=HM, dt=0.05, num_particles=n_part, max_iter=20)
+    engm = Engine(sde_models.SDERotorModel(pmm))
+    solver = BatchedAPG(engm, w["nn"], w["stage"], mpcm["apg_mpc"], np.full(HM, 0.05, np.float32), n_part, lb=1e-4, ub=1.0)
+    x0m = torch.full((HM, 6), 0.33 + 2e-4, device=dev)
+    y0d = torch.as_tensor(y0m[p_lo:p_lo + p_cnt], device=dev)
+    kd = torch.as_tensor(keysm[p_lo:p_lo + p_cnt].view(np.int32), device=dev)
+    tms = []
+    for rep in range(reps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        solver.init(x0m, y0d, xrefm, kd).run(20)
+        e1.record()
+        torch.cuda.synchronize()
+        if rep:
+            tms.append(e0.elapsed_time(e1))
+    tm = float(np.mean(tms))
+    if world > 1:
+        t = torch.tensor([tm], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tm = float(t.item())
+    out = {"solves_per_s": P_TOTAL / (tm * 1e-3), "ms_per_batch": tm, "problems": P_TOTAL, "problems_per_gpu": p_cnt,
+           "particles": n_part, "horizon": HM, "apg_iterations": 20, "mean_init_cost": float(solver.t["init_cost"].mean()),
+           "mean_opt_cost": float(solver.t["opt_cost"].mean()), "rollout_equiv_per_solve": 2 + 20 * 9,
+           "mode": "speculative" if solver.speculative else ("merged x/v" if solver.merge_xv_grad else
+                                                             ("progressive line search" if solver.progressive_ls else "stacked line search"))}
+    if e2e:
+        y0p = torch.as_tensor(y0m[p_lo:p_lo + p_cnt]).pin_memory()
+        kp = torch.as_tensor(keysm[p_lo:p_lo + p_cnt].view(np.int32)).pin_memory()
+        uo = torch.empty((p_cnt, HM, 6)).pin_memory()
+        tws = []
+        for rep in range(reps):
+            barrier()
+            t0 = time.perf_counter()
+            solver.init(x0m, y0p.to(dev, non_blocking=True), xrefm, kp.to(dev, non_blocking=True)).run(20)
+            uo.copy_(solver.x_opt(), non_blocking=True)
+            torch.cuda.synchronize()
+            if rep:
+                tws.append(time.perf_counter() - t0)
+        te = float(np.mean(tws))
+        if world > 1:
+            t = torch.tensor([te], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            te = float(t.item())
+        out["e2e_s"] = te
+        out["h2d_bytes"] = int(y0p.numel() * 4 + kp.numel() * 4)
+        out["d2h_bytes"] = int(uo.numel() * 4)
+    return out
+
+
+def run_mpc_batch(args):
+    """--workload mpc_batch: ONE JSON line whose value is whole-job APG-MPC solves/s (strong scaling over the GPUs)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    w = build_workload()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    main_r = mpc_batch_run(w, args.particles, world, rank, dev, barrier, reps=max(args.steps, 3) + 1, e2e=True)
+    other = mpc_batch_run(w, 1 if args.particles != 1 else 32, world, rank, dev, barrier, reps=4)
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        line = {"metric": "APG-MPC solves/s (hexacopter nSDE, 4096 independent problems)", "value": main_r["solves_per_s"],
+                "unit": "solves/s", "n_gpus": world, "steps": max(args.steps, 3), "warmup": 1,
+                "ms_per_step": main_r["ms_per_batch"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": "4096 independent hexacopter MPC solves (H = 20, dt = 0.05, 20 APG iterations, box "
+                                       "prox, line search maxls 4), %d particle(s) per problem, problems partitioned over the "
+                                       "GPUs, no collective (BASELINE configs[3])" % args.particles,
+                           "problems": 4096, "particles": args.particles, "horizon": 20, "apg_iterations": 20, "gpus": world,
+                           "l2": "working set per batch exceeds L2 at 32 particles (283 MB of checkpoints); not flushed",
+                           "timing": "CUDA events around one batch (init + 20 iterations), max over ranks"},
+                "clocks": clocks,
+                "e2e": {"value": 4096 / main_r["e2e_s"], "unit": "solves/s", "h2d_bytes_per_step": main_r["h2d_bytes"],
+                        "d2h_bytes_per_step": main_r["d2h_bytes"], "ms_per_step": main_r["e2e_s"] * 1e3,
+                        "api": "apg_batched.BatchedAPG.init(pinned host start states / keys).run(20) + x_opt to pinned host"},
+                "gpu_launches": "one CUDA-graph replay per APG iteration (6 bookkeeping + 2-4 cost + reduce launches)",
+                "mpc_batch": {"N%d" % args.particles: main_r, "N%d" % other["particles"]: other}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -206,11 +320,17 @@ def main():
                     help="diagnostic: how L2 is flushed between timed steps (the bench line is quoted with 'write')")
     ap.add_argument("--block-threads", type=int, default=0)
     ap.add_argument("--lanes", type=int, default=0, help="lanes per sample (0 = library heuristic)")
+    ap.add_argument("--workload", default="particles", choices=["particles", "mpc_batch"],
+                    help="particles: BASELINE configs[2] (the default line); mpc_batch: BASELINE configs[3], 4096 independent "
+                         "hexacopter MPC solves partitioned over the GPUs, value = solves/s, strong scaling")
+    ap.add_argument("--particles", type=int, default=32, help="mpc_batch: particles per problem (the reference deploys 1)")
     ap.add_argument("--transport", default="fused", choices=["fused", "symm", "nccl"],
                     help="cross-GPU sum of [cost, grad] at N > 1: folded into K3 (peer loads over NVLink), torch one-shot, NCCL")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "mpc_batch":
+        return run_mpc_batch(args)
 
     import torch
     import torch.distributed as dist
@@ -458,45 +578,9 @@ def main():
     # iterations, mpc_test_cfg.yaml), PARTITIONED over the ranks with no collective (strong scaling)
     mpc_extra = {}
     try:
-        from sde4mbrl_b200.apg_batched import BatchedAPG
-        P_TOTAL, HM = 4096, 20
-        p_lo, p_cnt = rank * (P_TOTAL // world), P_TOTAL // world
-        rngm = np.random.default_rng(123)
-        y0m = np.tile(w["y0"], (P_TOTAL, 1))
-        y0m[:, 3:6] += rngm.normal(0, 0.05, (P_TOTAL, 3)).astype(np.float32)
-        y0m[:, 10:13] += rngm.normal(0, 0.05, (P_TOTAL, 3)).astype(np.float32)
-        keysm = np.stack([np.zeros(P_TOTAL, np.uint32), np.arange(P_TOTAL, dtype=np.uint32)], axis=1)
-        xrefm = np.tile(w["xref"][:1], (HM + 1, 1))
         for n_part in (1, 32):
-            pmm = configs.hexa_model(horizon=HM, num_particles=n_part, stepsize=0.05)
-            mpcm = configs.hexa_mpc(horizon=HM, dt=0.05, num_particles=n_part, max_iter=20)
-            engm = Engine(sde_models.SDERotorModel(pmm))
-            solver = BatchedAPG(engm, w["nn"], w["stage"], mpcm["apg_mpc"], np.full(HM, 0.05, np.float32), n_part,
-                                lb=1e-4, ub=1.0)
-            x0m = torch.full((HM, 6), 0.33 + 2e-4, device=dev)
-            y0d = torch.as_tensor(y0m[p_lo:p_lo + p_cnt], device=dev)
-            kd = torch.as_tensor(keysm[p_lo:p_lo + p_cnt].view(np.int32), device=dev)
-            tms = []
-            for rep in range(4):
-                barrier()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                solver.init(x0m, y0d, xrefm, kd).run(20)
-                e1.record()
-                torch.cuda.synchronize()
-                if rep:
-                    tms.append(e0.elapsed_time(e1))
-            tm = float(np.mean(tms))
-            if world > 1:
-                t = torch.tensor([tm], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                tm = float(t.item())
-            init_c = float(solver.t["init_cost"].mean())
-            opt_c = float(solver.t["opt_cost"].mean())
-            mpc_extra["N%d" % n_part] = {"solves_per_s": P_TOTAL / (tm * 1e-3), "ms_per_batch": tm, "problems": P_TOTAL,
-                                         "particles": n_part, "horizon": HM, "apg_iterations": 20,
-                                         "mean_init_cost": init_c, "mean_opt_cost": opt_c,
-                                         "rollout_equiv_per_solve": 2 + 20 * 9}
+            mpc_extra["N%d" % n_part] = mpc_batch_run(w, n_part, world, rank, dev, barrier, reps=4)
+        mpc_extra["scaling"] = "strong: 4096 problems partitioned over the GPUs, no collective (see --workload mpc_batch)"
     except Exception as ex:  # never lose the headline line because of the extra
         mpc_extra = {"error": repr(ex)}
 

@@ -16,7 +16,7 @@ cp = configs.hexa_mpc()["cost_params"]
 stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
 ts = compute_timesteps(pm)
 xd = torch.tensor(np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32), device="cuda")
-for P, N in ((1, 1), (14, 1), (14, 32), (1, 1024), (3584, 1), (256, 16), (8192, 1), (512, 32), (16384, 1), (1024, 32), (2048, 32), (4096, 32)):
+for P, N in ((256, 16), (512, 32), (2048, 32), (4096, 32)):
     y0 = torch.tensor(np.tile(configs.hover_state(), (P, 1)), device="cuda")
     u = torch.tensor(rng.uniform(0.30, 0.36, (P, H, 6)).astype(np.float32), device="cuda")
     keys = tf.split(tf.PRNGKey(1), P)

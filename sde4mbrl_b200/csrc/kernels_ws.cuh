@@ -576,7 +576,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
   using A = typename Cfg::A;
   using RS = typename Cfg::RS;
   using M8 = typename Cfg::M8;
-  constexpr int NX = Cfg::NX, NU = Cfg::NU, NPART = Cfg::NPART, NZ = Cfg::NZ, NO = Cfg::NO;
+  constexpr int NX = Cfg::NX, NU = Cfg::NU, NPART = Cfg::NPART, NZ = Cfg::NZ;
   const float* __restrict__ S = W + A::OFF_SCALARS;
   const unsigned G = (unsigned)a.G;
   const int H = a.H;
@@ -928,7 +928,7 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
   using MB = typename Cfg::MB;
   using NetA = typename A::NetA;
   using NetB = typename A::NetB;
-  constexpr int NPART = Cfg::NPART, NX = Cfg::NX, NU = Cfg::NU;
+  constexpr int NPART = Cfg::NPART;
   const unsigned G = (unsigned)a.G;
   const int H = a.H;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -1023,6 +1023,8 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
   sum_row(0);
 }
 
+// (__launch_bounds__(128, 3): 153 registers.  Capping at 128 for four CTAs per SM helps at 16 k samples (282 -> 225 us, H = 20)
+// and costs everywhere else: C3 0.358 -> 0.377 ms, 131 k samples 2.03 -> 2.24 ms.)
 // One CTA = 16 particles, four warps: PHY, DENS, RES, AUX -- warp k of every CTA lands on scheduler k of its SM, so each
 // scheduler (and its L0 instruction cache) runs the code of ONE role.
 // Requirements checked by the launcher: value + gradient, in-kernel threefry noise, no state constraints.

@@ -404,15 +404,17 @@ struct EvLT {
   SDE4_DEV static void all_gather(const float (&own)[B], float (&all)[B * L]) {
 #pragma unroll
     for (int m = 0; m < B; ++m) all[m] = own[m];
-#ifdef SDE4_GATHER_BUTTERFLY
+#ifndef SDE4_GATHER_DIRECT
+    // doubling butterfly: log2(L) dependent rounds
 #pragma unroll
     for (int mask = 1, n = B; mask < L; mask <<= 1, n <<= 1) {
 #pragma unroll
       for (int q = 0; q < n; ++q) all[n + q] = __shfl_xor_sync(0xffffffffu, all[q], mask);
     }
 #else
-    // every block straight from its owner: the same (L-1)*B shuffles as the doubling butterfly, but none of them
-    // depends on another one (one shuffle latency on the critical path instead of log2(L))
+    // every block straight from its owner: the same (L-1)*B shuffles, none depending on another.  Measured in round 2:
+    // the 8-lane forward rollout of C3 went from 0.178 to 0.235 ms with it (the independent shuffles are hoisted and
+    // lengthen the live ranges), so the butterfly stays the default.
 #pragma unroll
     for (int q = 1; q < L; ++q) {
 #pragma unroll
