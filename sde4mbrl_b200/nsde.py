@@ -567,20 +567,47 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
     special = loss_params.get("special_parameters_pen", {})
     default_val = loss_params.get("default_parameters_val", 0.0)
 
+    nominal_val = loss_params.get("nominal_parameters_val", {})
+    special_val = loss_params.get("special_parameters_val", {})
+
+    def _matched(tree, keyed, default, current=None):
+        """``get_penalty_parameters`` (sde4mbrl/utils.py:119-146) on a two-level haiku tree, as {module: {leaf: scalar}}:
+        a key that is a substring of a MODULE name sets every leaf of that module (later keys of ``keyed`` win) and the
+        module is not looked into any further; in the other modules a key that is a substring of a LEAF name sets that
+        leaf; everything else gets ``default`` (or keeps ``current`` when ``default`` is None)."""
+        out = {}
+        for mod, leaves in tree.items():
+            hit = [v for k, v in keyed.items() if k in mod]
+            if hit:
+                out[mod] = {name: hit[-1] for name in leaves}
+                continue
+            out[mod] = {}
+            for name in leaves:
+                lh = [v for k, v in keyed.items() if k in name]
+                out[mod][name] = lh[-1] if lh else (default if default is not None else current[mod][name])
+        return out
+
     def _penalty(_nn_params, want_grad):
-        """pen_weights * sum_leaves coeff * ||p - nominal||^2 with the key-substring matching of
-        get_penalty_parameters (sde4mbrl/utils.py:119-146); nominal = default_parameters_val."""
+        """pen_weights * sum_leaves coeff * ||p - nominal||^2 (nsde.py:1155-1168, 1216-1219): coefficients from
+        ``special_parameters_pen`` / ``default_weights``; nominal values = ``default_parameters_val`` everywhere, then
+        ``nominal_parameters_val`` ({module: {leaf: value}}, update_same_struct_dict), then ``special_parameters_val``
+        matched like the coefficients."""
+        coeffs = _matched(_nn_params, special, default_w)
+        nom = {mod: {name: default_val for name in leaves} for mod, leaves in _nn_params.items()}
+        for mod, sub in nominal_val.items():
+            if mod in nom and isinstance(sub, dict):
+                for name, v in sub.items():
+                    nom[mod][name] = v
+        nom = _matched(_nn_params, special_val, None, nom)
         tot, grads = 0.0, {}
         for mod, leaves in _nn_params.items():
             for name, arr in leaves.items():
-                coeff = default_w
-                for key, val in special.items():
-                    if key in mod or key in name:
-                        coeff = val
+                coeff = coeffs[mod][name]
                 a = np.asarray(arr, np.float64)
-                tot += float(np.sum((a - default_val) ** 2) * coeff)
+                dlt = a - np.asarray(nom[mod][name], np.float64)
+                tot += float(np.sum(dlt ** 2) * coeff)
                 if want_grad:
-                    grads.setdefault(mod, {})[name] = (2.0 * coeff * pen_w * (a - default_val)).astype(np.float32)
+                    grads.setdefault(mod, {})[name] = (2.0 * coeff * pen_w * dlt).astype(np.float32)
         return tot, grads
 
     # loss_params["graph_regulariser"] = False keeps the regulariser on the eager torch path
@@ -696,6 +723,7 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
 
     loss_fn.value_and_grad = value_and_grad
     loss_fn.engine = engine
+    loss_fn.weight_penalty = _penalty  # (unweighted sum, pen_weights-scaled gradients)
 
     nonneg = set(params_model.get("noneg_params", []))
     nonzero = loss_params.get("nonneg_nonzero", {})

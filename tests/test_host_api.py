@@ -123,3 +123,43 @@ def test_rotor_mpc_frames_and_targets():
     np.testing.assert_allclose(late[-1], xs[-1] + slope * (t[-1] - 0.2 + steps[-1] - t[-1]), atol=1e-4)
     tv, sv = rm.parse_trajectory({"t": t, **{n: xs[:, i] for i, n in enumerate(rm.state_names)}})
     np.testing.assert_array_equal(sv, xs)
+
+
+def test_weight_penalty_matching_follows_get_penalty_parameters():
+    """Penalty coefficients and nominal values of the weight-decay term (nsde.py:1155-1168, utils.py:119-146): a key
+    matching a module name covers the whole module and wins over leaf-name matches; nominal_parameters_val and
+    special_parameters_val move the point the parameters are pulled towards."""
+    import contextlib
+    import io
+    from sde4mbrl_b200 import configs, nsde, sde_models
+    pm = configs.cartpole_model(horizon=1, num_particles=1)
+    lp = {"seed": 0, "stepsize": 0.02, "data_stepsize": 0.02, "num_particles": 1, "num_particles_test": 1, "horizon": 4,
+          "obs_weights": [1, 1, 1, 1, 1], "pen_data": 0.0, "pen_weights": 1.0, "default_weights": 2.0,
+          "special_parameters_pen": {"density": 0.0, "linear_1": 5.0, "b": 3.0},
+          "default_parameters_val": 0.25, "nominal_parameters_val": {"cart_pole_sde": {"scaler": -1.0}},
+          "special_parameters_val": {"linear_2": 0.5}}
+    with contextlib.redirect_stdout(io.StringIO()):
+        nn, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.CartPoleSDE, verbose=False)
+    pen = loss_fn.weight_penalty if hasattr(loss_fn, "weight_penalty") else None
+    assert pen is not None
+    tot, grads = pen(nn, True)
+    want = 0.0
+    for mod, leaves in nn.items():
+        for name, arr in leaves.items():
+            if "linear_1" in mod:
+                coeff = 5.0            # module-level match; the LATER key of the dict wins over "density"
+            elif "density" in mod:
+                coeff = 0.0            # the whole module, leaf names not looked at
+            elif "b" in name:
+                coeff = 3.0            # leaf-level match in the remaining modules (no module name holds a "b")
+            else:
+                coeff = 2.0
+            nom = 0.25
+            if mod == "cart_pole_sde" and name == "scaler":
+                nom = -1.0
+            if "linear_2" in mod:
+                nom = 0.5
+            a = np.asarray(arr, np.float64)
+            want += coeff * float(np.sum((a - nom) ** 2))
+            np.testing.assert_allclose(grads[mod][name], 2.0 * coeff * (a - nom), rtol=1e-6, atol=1e-7)
+    assert abs(tot - want) <= 1e-9 * max(1.0, abs(want))
