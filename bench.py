@@ -571,6 +571,26 @@ def main():
         sim_extra = {"start_states": PS * world, "horizon": HS, "ms": tm, "particle_steps_per_s": tot / (tm * 1e-3),
                      "fp32_tflops": 3135.0 * tot / (tm * 1e-3) / 1e12,
                      "trajectory_writeout_gbs": 4.0 * PS * world * (HS + 1) * 4 / (tm * 1e-3) / 1e9}
+        # the same rollouts as a simulator step (sde4_sim_rollout): only the last states leave the kernel
+        # (16 MB instead of 520 MB), cartpole swing-up reward accumulated in the kernel, particle mean on the device
+        tms = []
+        for rep in range(4):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            engc.sim_rollout(pkc, obs, actc, tsc, keysc, N=1, reward="cartpole_swingup")
+            e1.record()
+            torch.cuda.synchronize()
+            if rep:
+                tms.append(e0.elapsed_time(e1))
+        tmp = float(np.mean(tms))
+        if world > 1:
+            t = torch.tensor([tmp], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tmp = float(t.item())
+        sim_extra["predict_ms"] = tmp
+        sim_extra["predict_particle_steps_per_s"] = tot / (tmp * 1e-3)
+        sim_extra["predict_bytes_written"] = 4 * PS * (4 + 1 + 4 + 1)
         del outc, obs, actc
     except Exception as ex:
         sim_extra = {"error": repr(ex)}

@@ -155,7 +155,7 @@ typedef struct sde4_rollout_args {
   int32_t rng_mode;             /* sde4_rng_mode                                      */
   int32_t noise_mode;           /* sde4_noise_mode                                    */
   const float* noise;           /* NOISE_GIVEN: [H][n_x][G]                           */
-  float* xevol;                 /* out [H+1][x_rows][G]                               */
+  float* xevol;                 /* out [H+1][x_rows][G] (sde4_sim_rollout: may be NULL)  */
   int32_t x_rows;               /* >= n_x (rows beyond n_x are left untouched)        */
   int32_t block_threads;        /* 0 = library heuristic                              */
   /* particle sharding across GPUs: this call holds particles [particle_offset,
@@ -176,6 +176,35 @@ typedef struct sde4_rollout_args {
 } sde4_rollout_args;
 
 int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, void* stream);
+
+/* ---- the nSDE as an MBRL simulator: cartpole_sde_gym._my_pred_fn (sde4mbrlExamples/cartpole/cartpole_sde.py:214-223:
+ *      mean / population std over the particles of the LAST state) batched over P start states, and the per-step
+ *      reward / termination of mbrl-lib's ModelEnv (mbrlLibUtils/reward_functions.py:3-9, termination_functions.py:3-14)
+ *      accumulated inside the rollout.  The same rollout as sde4_rollout, but nothing of the trajectory is written unless
+ *      args->xevol is given: 2^20 start states x 30 steps leave 16 MB + 4 MB instead of 520 MB.
+ *        last[n_x][G]        last state of every sample (required: it is also the reduction's input)
+ *        racc[G]             per sample: sum_t r(u_t, obs(x_{t+1})) over the steps before (and including) its
+ *                            termination; required when reward_kind != 0
+ *        mean / std [P][n_x] over the N particles of each problem (NULL to skip; std is the population std, jnp.std)
+ *        reward_mean[P]      mean over the particles of racc (ModelEnv.evaluate_action_sequences)
+ *        reward_of_mean[P], done_of_mean[P]   reward / termination of the MEAN next state with the LAST control
+ *                            (ModelEnv.step with the nSDE as the dynamics model); NULL to skip */
+typedef enum sde4_reward_kind {
+  SDE4_REWARD_NONE = 0,
+  SDE4_REWARD_CARTPOLE_SWINGUP = 1 /* r = cos(obs[3]) - 0.1 |obs[0]| on obs = [x, xd, sin th, cos th, thd] (sic: the
+                                      reference takes the cosine of cos th); done when |x| >= 120 */
+} sde4_reward_kind;
+typedef struct sde4_sim_out {
+  int32_t reward_kind;
+  float* last;
+  float* racc;
+  float* mean;
+  float* std;
+  float* reward_mean;
+  float* reward_of_mean;
+  int32_t* done_of_mean;
+} sde4_sim_out;
+int sde4_sim_rollout(const sde4_model_desc* model, const sde4_rollout_args* args, const sde4_sim_out* out, void* stream);
 
 /* ---- cost + gradient: create_online_cost_sampling_fn(...).multi_sampling,
  *      sde4mbrl/nsde.py:1485-1527,1576-1586 and jax.value_and_grad of it as used by
@@ -306,6 +335,48 @@ int sde4_rng_randint_many(const uint32_t* keys_dev, uint64_t K, uint64_t n, int3
  *      (sde4mbrl_b200/density_loss.py). */
 size_t sde4_loss_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t H);
 int sde4_loss_grad(const sde4_model_desc* model, const sde4_cost_args* args, float* grad_params, void* stream);
+
+/* ---- distance-aware regulariser of the training loss, value and parameter gradient on the device:
+ *      ControlledSDE.density_loss (sde4mbrl/nsde.py:597-654), mu_coeff_nn (:657-680), their means in
+ *      sample_for_loss_computation (:771-804) and weighting in create_model_loss_fn.loss_fn (:1205-1250).
+ *      Per data point (b, t) of the minibatch (no rollout), z = noise_aug_state_ctrl(y[b][t], u[b][t]):
+ *        den = sigmoid(density_net(z) - 7), g = d den / d z, mu = mu_coeff_nn(z);
+ *        for particle n, ball sample s: delta = normal(rng_ball(b, n, t), (ns, dim))[s] * ball_radius,
+ *          cond = den(z + delta) - den - g.delta - 0.5 mu |delta|^2, hinge^2 = min(cond, 0)^2
+ *      with rng_ball = split(split(split(split(split(key, B)[b], N)[n], 3)[2], Hd)[t])[1].
+ *      out[0] = w_grad * gradDensity + w_scvex * densitySCVEX + w_mu * lossMuCoeff, out[1] = gradDensity = mean |g|^2,
+ *      out[2] = densitySCVEX = mean_{b,n} sum_t sum_s hinge^2, out[3] = muCoeff = mean mu, out[4] = lossMuCoeff =
+ *      1/mu^2 | 1/mu | exp(-temp mu) of that mean (pen_mu_type).  grad_params (sde4_param_layout() floats) receives
+ *      d out[0] / d density network (zero elsewhere), grad_mu the gradient w.r.t. the mu parameters (dnn: packed like a
+ *      model network, w0[in][up4(h1)] b0 w1[h1][up4(h2)] b1 w2T[1][up4(h2)] b2[4]; global: 1 float). */
+typedef enum sde4_mu_type { SDE4_MU_CONSTANT = 0, SDE4_MU_GLOBAL = 1, SDE4_MU_DNN = 2 } sde4_mu_type;
+typedef enum sde4_pen_mu_type { SDE4_PEN_MU_QUAD_INV = 0, SDE4_PEN_MU_LIN_INV = 1, SDE4_PEN_MU_EXP_INV = 2 } sde4_pen_mu_type;
+#define SDE4_REG_MAXD 24
+typedef struct sde4_density_reg_args {
+  uint32_t struct_size;        /* sizeof(sde4_density_reg_args)                                  */
+  int32_t B, N, Hd;            /* minibatch, particles, data horizon                             */
+  const float* params;         /* device, packed model block                                     */
+  const float* y;              /* device float[B][Hd+1][n_x] (observations = states)             */
+  const float* u;              /* device float[B][Hd][n_u]                                       */
+  const uint32_t* key;         /* device uint32[2]: the rng of loss_fn                           */
+  int32_t rng_mode;            /* sde4_rng_mode                                                  */
+  int32_t ball_nsamples;
+  float ball_radius[SDE4_REG_MAXD]; /* per density input                                         */
+  int32_t mu_type;             /* sde4_mu_type                                                   */
+  sde4_net_desc mu_net;        /* SDE4_MU_DNN: hidden sizes / activation of the mu network       */
+  const float* mu_params;      /* device: packed mu network | float[1] (global) | NULL           */
+  float mu_coeff;              /* params['density_loss']['mu_coeff']                             */
+  float w_grad, w_scvex, w_mu; /* weights in out[0], pen_scvex_mult folded in                    */
+  int32_t pen_mu_type;         /* sde4_pen_mu_type                                               */
+  float pen_mu_temp;
+  float* out;                  /* device float[5]                                                */
+  float* grad_params;          /* device float[sde4_param_layout()]                              */
+  float* grad_mu;              /* device: same shape as mu_params (may be NULL for constant)     */
+  void* workspace;             /* device, 256-byte aligned                                       */
+  size_t workspace_bytes;      /* >= sde4_density_reg_workspace_bytes(...)                       */
+} sde4_density_reg_args;
+size_t sde4_density_reg_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t Hd, int32_t ball_nsamples);
+int sde4_density_reg(const sde4_model_desc* model, const sde4_density_reg_args* args, void* stream);
 
 /* ---- batched APG-MPC: sde4mbrl/apg.py (init_apg :53-113, one_step_apg :164-274,
  *      armijo_line_search :332-379, _while_loop :451-464) for P independent problems at once.

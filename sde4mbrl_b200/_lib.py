@@ -88,6 +88,30 @@ class CostArgs(C.Structure):
                 ("xgpu", C.c_void_p)]
 
 
+REWARD_NONE, REWARD_CARTPOLE_SWINGUP = 0, 1
+
+
+class SimOut(C.Structure):  # sde4_sim_out
+    _fields_ = [("reward_kind", C.c_int32), ("last", C.c_void_p), ("racc", C.c_void_p), ("mean", C.c_void_p),
+                ("std", C.c_void_p), ("reward_mean", C.c_void_p), ("reward_of_mean", C.c_void_p),
+                ("done_of_mean", C.c_void_p)]
+
+
+MU_CONSTANT, MU_GLOBAL, MU_DNN = 0, 1, 2
+PEN_MU = {"quad_inv": 0, "lin_inv": 1, "exp_inv": 2}
+REG_MAXD = 24
+
+
+class DensityRegArgs(C.Structure):  # sde4_density_reg_args
+    _fields_ = [("struct_size", C.c_uint32), ("B", C.c_int32), ("N", C.c_int32), ("Hd", C.c_int32),
+                ("params", C.c_void_p), ("y", C.c_void_p), ("u", C.c_void_p), ("key", C.c_void_p),
+                ("rng_mode", C.c_int32), ("ball_nsamples", C.c_int32), ("ball_radius", C.c_float * REG_MAXD),
+                ("mu_type", C.c_int32), ("mu_net", NetDesc), ("mu_params", C.c_void_p), ("mu_coeff", C.c_float),
+                ("w_grad", C.c_float), ("w_scvex", C.c_float), ("w_mu", C.c_float), ("pen_mu_type", C.c_int32),
+                ("pen_mu_temp", C.c_float), ("out", C.c_void_p), ("grad_params", C.c_void_p), ("grad_mu", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 class XgpuReduce(C.Structure):  # sde4_xgpu_reduce
     _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n", C.c_int32), ("epoch", C.c_uint32),
                 ("buf", C.c_void_p * 8), ("flag", C.c_void_p * 8), ("out", C.c_void_p), ("counter", C.c_void_p)]
@@ -118,7 +142,7 @@ EXPORTED_SYMBOLS = (
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
     "sde4_apg_scratch_floats", "sde4_cost_grad_host", "sde4_cost_grad_host_staging_bytes",
-    "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_rng_randint_many", "sde4_apg_ls_step", "sde4_apg_spec_points", "sde4_apg_spec_gather",
+    "sde4_sim_rollout", "sde4_density_reg", "sde4_density_reg_workspace_bytes", "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_rng_randint_many", "sde4_apg_ls_step", "sde4_apg_spec_points", "sde4_apg_spec_gather",
 )
 
 _lib = None
@@ -140,6 +164,12 @@ def load():
     lib = C.CDLL(LIB_PATH)
     lib.sde4_rollout.argtypes = [C.POINTER(ModelDesc), C.POINTER(RolloutArgs), C.c_void_p]
     lib.sde4_rollout.restype = C.c_int
+    lib.sde4_sim_rollout.argtypes = [C.POINTER(ModelDesc), C.POINTER(RolloutArgs), C.POINTER(SimOut), C.c_void_p]
+    lib.sde4_sim_rollout.restype = C.c_int
+    lib.sde4_density_reg.argtypes = [C.POINTER(ModelDesc), C.POINTER(DensityRegArgs), C.c_void_p]
+    lib.sde4_density_reg.restype = C.c_int
+    lib.sde4_density_reg_workspace_bytes.argtypes = [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.sde4_density_reg_workspace_bytes.restype = C.c_size_t
     lib.sde4_cost_workspace_bytes.argtypes = [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                               C.c_int32, C.c_int32]
     lib.sde4_cost_workspace_bytes.restype = C.c_size_t

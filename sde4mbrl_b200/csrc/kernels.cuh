@@ -32,6 +32,11 @@ struct RolloutK {
   int x_rows, rng_mode, noise_mode;
   int n_off, n_tot;
   int solver;  // sde4_solver
+  // simulator summary (sde4_sim_rollout): xevol may be null, the last state goes to last[i*G + g], the accumulated
+  // reward of the sample to racc[g]
+  float* last;
+  float* racc;
+  int reward_kind;
 };
 
 struct CostK {
@@ -320,12 +325,27 @@ SDE4_DEV uint32_t noise_mask(const sde4_model_desc& d) {
   return m;
 }
 
+// mbrl-lib reward / termination of the cartpole swing-up task on the SDE state [x, xd, th, thd]
+// (mbrlLibUtils/reward_functions.py:3-9 on obs = [x, xd, sin th, cos th, thd]: cos(obs[3]) - 0.1 |obs[0]| -- sic, the
+// cosine of cos th; termination_functions.py:3-14: done when |x| >= 120)
+template <int NX>
+SDE4_HD float sim_reward_cartpole(const float (&x)[NX]) {
+  return cosf(cosf(x[2])) - 0.1f * fabsf(x[0]);
+}
+template <int NX>
+SDE4_HD bool sim_done_cartpole(const float (&x)[NX]) {
+  return !(x[0] > -120.0f && x[0] < 120.0f);
+}
+
 // ----------------------------------------------------------------------------
 // K1: forward rollout
 // ----------------------------------------------------------------------------
 // STRAT: the instantiation that carries the Stratonovich extension steps (kept out of the Euler-Maruyama kernels:
 // the extra inlined drift / diffusion evaluations cost the throughput kernels 20 % through code size alone)
-template <class M, bool TFP = false, bool STRAT = false>
+// SIM: the simulator-summary instantiation (sde4_sim_rollout): trajectory stores only on request, per-step reward with
+// termination, last state / accumulated reward of every sample at the end.  Kept out of the plain rollout kernels: the
+// few extra instructions per step cost the 2^20-start-state rollout 5 % when they were run-time branches of one kernel.
+template <class M, bool TFP = false, bool STRAT = false, bool SIM = false>
 __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_model_desc d,
                                                   const __grid_constant__ RolloutK a) {
   constexpr int NX = M::NX, NU = M::NU;
@@ -341,7 +361,10 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
   float x[NX];
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = __ldg(a.y0 + (size_t)p * NX + i);
-  store_state<M>(a.xevol + g, a.G, x, tc.l, active);
+  const bool traj = !SIM || a.xevol != nullptr;  // warp uniform
+  if (traj) store_state<M>(a.xevol + g, a.G, x, tc.l, active);
+  [[maybe_unused]] float racc = 0.0f;
+  [[maybe_unused]] bool alive = true;
   const bool noisy = TFP ? true : a.noise_mode != SDE4_NOISE_NONE;
   const uint32_t nzmask = noise_mask<NX>(d);
   uint32_t b0 = 0, b1 = 0;
@@ -366,7 +389,21 @@ __global__ void __launch_bounds__(256) k_rollout(const __grid_constant__ sde4_mo
     float aux;
     if constexpr (STRAT) strat_step<M>(a.solver, W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
     else em_step<M>(W, tc, d, x, u, dw, __ldg(a.dt + t), noisy, aux);
-    store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
+    if (traj) store_state<M>(a.xevol + (size_t)(t + 1) * a.x_rows * a.G + g, a.G, x, tc.l, active);
+    if constexpr (SIM && NX == 4) {  // cartpole: reward of the step, counted up to and including the terminal one
+      if (a.reward_kind == SDE4_REWARD_CARTPOLE_SWINGUP) {
+        const float r = sim_reward_cartpole(x);
+        racc += alive ? r : 0.0f;
+        alive = alive && !sim_done_cartpole(x);
+      }
+    }
+  }
+  if constexpr (SIM) {  // the last state (and the accumulated reward) of every sample
+    if (active && tc.l == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) a.last[(size_t)i * a.G + g] = x[i];
+      if (a.racc) a.racc[g] = racc;
+    }
   }
 }
 

@@ -133,6 +133,60 @@ SDE4_DEV void k_reduce_body(const ReduceK& a) {
 }
 
 // ----------------------------------------------------------------------------
+// simulator summary: mean / population std over the particles of the last state, mean accumulated reward, reward and
+// termination of the mean state (cartpole_sde.py:219-223, ModelEnv.step / evaluate_action_sequences).
+// One thread per (state i, problem p), p fastest; fixed summation order.
+// ----------------------------------------------------------------------------
+struct SimReduceK {
+  const float* last;   // [n_x][G]
+  const float* racc;   // [G] or null
+  const float* u_last; // control of the last step, element (p, j) at u_last[p*u_sp + j*u_sj]
+  long long u_sp, u_sj;
+  float* mean;
+  float* std;
+  float* reward_mean;
+  float* reward_of_mean;
+  int32_t* done_of_mean;
+  int P, N, n_x, reward_kind;
+};
+__global__ void k_sim_reduce(const __grid_constant__ SimReduceK a) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= (long long)a.P * a.n_x) return;
+  const int p = (int)(gid % a.P), i = (int)(gid / a.P);
+  const size_t G = (size_t)a.P * a.N;
+  const float* src = a.last + (size_t)i * G + (size_t)p * a.N;
+  float m = 0.0f;
+  for (int n = 0; n < a.N; ++n) m += src[n];
+  m /= (float)a.N;
+  if (a.mean) a.mean[(size_t)p * a.n_x + i] = m;
+  if (a.std) {
+    float v = 0.0f;
+    for (int n = 0; n < a.N; ++n) {
+      const float dlt = src[n] - m;
+      v = fmaf(dlt, dlt, v);
+    }
+    a.std[(size_t)p * a.n_x + i] = sqrtf(v / (float)a.N);
+  }
+  if (i != 0) return;
+  if (a.reward_mean && a.racc) {
+    float r = 0.0f;
+    for (int n = 0; n < a.N; ++n) r += a.racc[(size_t)p * a.N + n];
+    a.reward_mean[p] = r / (float)a.N;
+  }
+  if ((a.reward_of_mean || a.done_of_mean) && a.reward_kind == SDE4_REWARD_CARTPOLE_SWINGUP && a.n_x == 4) {
+    float xm[4];
+    for (int k = 0; k < 4; ++k) {
+      const float* s2 = a.last + (size_t)k * G + (size_t)p * a.N;
+      float mk = 0.0f;
+      for (int n = 0; n < a.N; ++n) mk += s2[n];
+      xm[k] = mk / (float)a.N;
+    }
+    if (a.reward_of_mean) a.reward_of_mean[p] = sim_reward_cartpole(xm);
+    if (a.done_of_mean) a.done_of_mean[p] = sim_done_cartpole(xm) ? 1 : 0;
+  }
+}
+
+// ----------------------------------------------------------------------------
 // K0: RNG self-test kernels
 // ----------------------------------------------------------------------------
 __global__ void k_rng_bits(uint32_t k0, uint32_t k1, unsigned long long total, unsigned long long offset,

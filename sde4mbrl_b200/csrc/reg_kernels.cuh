@@ -1,0 +1,425 @@
+// reg_kernels.cuh -- the distance-aware regulariser of the training loss, value AND parameter gradient.
+//
+// Reference: ControlledSDE.density_loss / mu_coeff_nn / sample_for_loss_computation and their weighting in
+// create_model_loss_fn.loss_fn (sde4mbrl/nsde.py:597-680, 771-804, 1205-1254).  Per data point i = (b, t) of the
+// minibatch (no rollout: the terms are taken at the DATA), with z = noise_aug_state_ctrl(y, u):
+//   den = sigmoid(mlp(z) - 7),  g = d den / d z,  mu = mu_coeff_nn(z)
+//   gn  = |g|^2                                                                  (gradient-norm term)
+//   for every particle n, ball sample s:  delta = normal(key_bnt)[s] * radius
+//     cond = den(z + delta) - den - g . delta - 0.5 mu |delta|^2,   sc += min(cond, 0)^2   (strong-convexity hinge)
+//   total = c_g mean(gn) + c_s mean_bn(sum_t sc) + c_mu f(mean(mu))
+//
+// The parameter gradient needs d(g . v)/d theta for a fixed direction v (v = 2 a_g g - a_s sum lambda delta): that is
+// the reverse sweep of the forward-mode tangent program of the 3-layer MLP (no reverse-over-reverse graph):
+//   primal   h1 = W0^T z + b0, a1 = act(h1), h2 = W1^T a1 + b1, a2 = act(h2), s = w2 . a2 + b2
+//   tangent  h1' = W0^T v,     a1' = act'(h1) h1',  h2' = W1^T a1',  a2' = act'(h2) h2',  s' = w2 . a2'
+//   Q = c_den sigmoid(s - 7) + sigmoid'(s - 7) s'
+// whose weight gradients are sums of TWO outer products per layer, (primal input (x) primal adjoint) and (tangent
+// input (x) tangent adjoint).  Both are written as two columns of the stream the existing weight-gradient kernels (K5,
+// misc_kernels.cuh) reduce; the ball samples are plain first-order columns of the same stream.
+//
+// Launch sequence (sde4_density_reg): R1 centres -> R2 ball samples -> R3 scalars -> R4 second-order columns -> K5.
+#pragma once
+#include "models.cuh"
+
+namespace sde4 {
+
+// value, first and second derivative of the activation
+template <int ACT>
+SDE4_DEV void act_fwd_dd(float a, float& h, float& d1, float& d2) {
+  if (ACT == SDE4_ACT_TANH) {
+    h = tanhf_(a);
+    d1 = fmaf(-h, h, 1.0f);
+    d2 = -2.0f * h * d1;
+  } else if (ACT == SDE4_ACT_SWISH) {
+    const float s = sigmoidf_(a);
+    const float sp = s * (1.0f - s);
+    h = a * s;
+    d1 = fmaf(a, sp, s);
+    d2 = sp * fmaf(a, 1.0f - 2.0f * s, 2.0f);
+  } else {
+    h = a;
+    d1 = 1.0f;
+    d2 = 0.0f;
+  }
+}
+
+constexpr int REG_MAXD = 24;  // widest density input (13 reduced states + 8 controls)
+
+struct RegK {
+  const float* params;     // packed model block (density net at A::OFF_DENSITY)
+  const float* mu_params;  // dnn: packed Net<D, M1, M2, 1, act>; global: [1]; constant: unused
+  const float* y;          // [B][Hd + 1][NX]
+  const float* u;          // [B][Hd][NU]
+  const uint32_t* key;     // device uint32[2]: the rng of loss_fn
+  int rng_mode, B, N, Hd, ns, mu_type;
+  float mu0;
+  float radius[REG_MAXD];
+  float a_g, a_s;          // d total / d gn_i, d total / d sc_bnt
+  float c_g, c_s, c_mu;    // weights of the three means in total (pen_scvex_mult included)
+  int pen_mu_type;         // 0 quad_inv, 1 lin_inv, 2 exp_inv
+  float pen_mu_temp;
+  float* cen;              // [2D + 3][K0]: z | g | den | mu | gn          (K0 = B*Hd)
+  float* part;             // [D + 3][K0*N]: sum_s lambda delta | sum lambda | sum lambda |delta|^2 | sum hinge^2
+  float* scal;             // device scalars: [0] d total / d mu_i
+  float* out;              // [5] total, gradDensity, densitySCVEX, muCoeff, lossMuCoeff
+  float* dstream;          // density stream: (DNet::DUMP_ROWS + 1) rows x Ktot columns (last row: 1 on primal columns)
+  float* mstream;          // mu-net stream: MuNet::DUMP_ROWS rows x K0 columns
+  unsigned long long Ktot, K2;  // K2 = B*N*Hd*ns ball columns, then K0 primal and K0 tangent columns
+};
+
+enum { REG_MU_CONSTANT = 0, REG_MU_GLOBAL = 1, REG_MU_DNN = 2 };
+
+template <class N>
+SDE4_DEV void reg_stage_net(float* dst, const float* src) {
+  for (int i = threadIdx.x; i < N::SIZE; i += blockDim.x) dst[i] = src[i];
+}
+
+template <class M, class MuNet>
+struct RegCfg {
+  using A = typename M::A;
+  using DNet = typename A::DNet;
+  using Dif = Diffusion<M>;
+  static constexpr int D = DNet::IN;
+  static constexpr int ONE_ROW = DNet::DUMP_ROWS;  // the "1 on primal columns" row of the density stream
+  static constexpr int W_FLOATS = DNet::SIZE + MuNet::SIZE;
+  static_assert(D <= REG_MAXD, "density input wider than REG_MAXD");
+  static_assert(MuNet::IN == D && MuNet::OUT == 1 && DNet::OUT == 1, "mu net reads the density input");
+  SDE4_DEV static void stage(float* W, const RegK& a) {
+    reg_stage_net<DNet>(W, a.params + A::OFF_DENSITY);
+    if (a.mu_type == REG_MU_DNN) reg_stage_net<MuNet>(W + DNet::SIZE, a.mu_params);
+    __syncthreads();
+  }
+  SDE4_DEV static void load_z(const sde4_model_desc& d, const RegK& a, int b, int t, float (&z)[D]) {
+    float x[A::NX], uu[A::NU];
+    const float* yp = a.y + ((size_t)b * (a.Hd + 1) + t) * A::NX;
+    const float* up = a.u + ((size_t)b * a.Hd + t) * A::NU;
+#pragma unroll
+    for (int k = 0; k < A::NX; ++k) x[k] = yp[k];
+#pragma unroll
+    for (int k = 0; k < A::NU; ++k) uu[k] = up[k];
+    Dif::gather_in(x, uu, d, z);
+  }
+};
+
+// ---- R1: centres -- one thread per data point: z, g = d den / d z, den, mu, |g|^2 -------------------------------
+template <class M, class MuNet>
+__global__ void __launch_bounds__(128) k_reg_centre(const __grid_constant__ sde4_model_desc d, const __grid_constant__ RegK a) {
+  using C = RegCfg<M, MuNet>;
+  using DNet = typename C::DNet;
+  constexpr int D = C::D;
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;
+  C::stage(W, a);
+  const int K0 = a.B * a.Hd;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K0) return;
+  Scratch sc;
+  sc.base = smem + up4(C::W_FLOATS) + threadIdx.x;
+  sc.bs = blockDim.x;
+  float z[D], g[D], o;
+  C::load_z(d, a, i / a.Hd, i % a.Hd, z);
+  float den = 0.0f;
+  mlp_scalar_value_grad<DNet, false>(W, sc, z, o, g, [&](float s) {
+    den = sigmoidf_(s - 7.0f);
+    return den * (1.0f - den);
+  });
+  float mu = a.mu0;
+  if (a.mu_type == REG_MU_GLOBAL) mu = a.mu0 * __expf(a.mu_params[0]);
+  if (a.mu_type == REG_MU_DNN) {
+    float mo[1];
+    mlp_fwd<MuNet, false>(W + DNet::SIZE, sc, z, mo);
+    mu = a.mu0 * __expf(mo[0]);
+  }
+  float gn = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    a.cen[(size_t)k * K0 + i] = z[k];
+    a.cen[(size_t)(D + k) * K0 + i] = g[k];
+    gn = fmaf(g[k], g[k], gn);
+  }
+  a.cen[(size_t)(2 * D) * K0 + i] = den;
+  a.cen[(size_t)(2 * D + 1) * K0 + i] = mu;
+  a.cen[(size_t)(2 * D + 2) * K0 + i] = gn;
+}
+
+// ---- R2: ball samples -- one thread per (b, n, t, s); groups of ns adjacent threads share a data point -----------
+// Column e = ((b*N + n)*Hd + t)*ns + s of the density stream carries the first-order rows of den(z + delta) with the
+// output cotangent a_s * lambda * sigmoid'.  The group leader sums lambda, lambda*delta, lambda*|delta|^2 and hinge^2
+// over the ns samples in index order (deterministic).
+template <class M, class MuNet>
+__global__ void __launch_bounds__(160) k_reg_ball(const __grid_constant__ sde4_model_desc d, const __grid_constant__ RegK a) {
+  using C = RegCfg<M, MuNet>;
+  using DNet = typename C::DNet;
+  constexpr int D = C::D;
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;
+  reg_stage_net<DNet>(W, a.params + C::A::OFF_DENSITY);
+  __syncthreads();
+  const int bs = blockDim.x;
+  // per-thread scratch columns [H | X (unused) | D1] of the evaluator, then the reduction rows [D + 3][bs]
+  float* redl = smem + up4(DNet::SIZE) + 3 * MAXW * bs;
+  const int K0 = a.B * a.Hd;
+  const int gpc = bs / a.ns;  // groups per CTA
+  const int grp = threadIdx.x / a.ns, s = threadIdx.x - grp * a.ns;
+  const long long q = (long long)blockIdx.x * gpc + grp;  // (b*N + n)*Hd + t
+  const long long KQ = (long long)K0 * a.N;
+  const bool live = grp < gpc && q < KQ;
+  float lam = 0.0f, hm = 0.0f, d2 = 0.0f, dl[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) dl[k] = 0.0f;
+  if (live) {
+    const int t = (int)(q % a.Hd);
+    const long long bn = q / a.Hd;
+    const int n = (int)(bn % a.N), b = (int)(bn / a.N);
+    const int i = b * a.Hd + t;
+    // rng_ball: split(rng, B)[b] -> split(., N)[n] -> split(., 3)[2] -> split(., Hd)[t] -> split(.)[1]
+    // (nsde.py:1196, 1187, 709, 781, 615)
+    uint32_t k0 = a.key[0], k1 = a.key[1], c0, c1;
+    jax_split(k0, k1, (uint32_t)b, (uint32_t)a.B, a.rng_mode, c0, c1);
+    jax_split(c0, c1, (uint32_t)n, (uint32_t)a.N, a.rng_mode, k0, k1);
+    jax_split(k0, k1, 2u, 3u, a.rng_mode, c0, c1);
+    jax_split(c0, c1, (uint32_t)t, (uint32_t)a.Hd, a.rng_mode, k0, k1);
+    jax_split(k0, k1, 1u, 2u, a.rng_mode, c0, c1);
+    float z[D], zb[D], J[D], o;
+    float gd_dot = 0.0f;
+    const unsigned long long tot = (unsigned long long)a.ns * D;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      dl[k] = bits_to_normal(jax_bits(c0, c1, (unsigned long long)s * D + k, tot, a.rng_mode)) * a.radius[k];
+      z[k] = a.cen[(size_t)k * K0 + i];
+      zb[k] = z[k] + dl[k];
+      gd_dot = fmaf(a.cen[(size_t)(D + k) * K0 + i], dl[k], gd_dot);
+      d2 = fmaf(dl[k], dl[k], d2);
+    }
+    const float den = a.cen[(size_t)(2 * D) * K0 + i], mu = a.cen[(size_t)(2 * D + 1) * K0 + i];
+    Scratch sc;
+    sc.base = smem + up4(DNet::SIZE) + threadIdx.x;
+    sc.bs = bs;
+    sc.dnet[0] = a.dstream;
+    sc.dstride = a.Ktot;
+    sc.dcol = (size_t)q * a.ns + s;
+    mlp_scalar_value_grad<DNet, true>(W, sc, zb, o, J, [&](float sv) {
+      const float db = sigmoidf_(sv - 7.0f);
+      const float cond = db - den - gd_dot - 0.5f * mu * d2;
+      hm = fminf(cond, 0.0f);
+      lam = 2.0f * hm;
+      return a.a_s * lam * db * (1.0f - db);
+    });
+    sc.dump(0, C::ONE_ROW, 1.0f);
+    (void)J;
+    (void)o;
+  }
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) redl[(size_t)k * bs + threadIdx.x] = lam * dl[k];
+    redl[(size_t)D * bs + threadIdx.x] = lam;
+    redl[(size_t)(D + 1) * bs + threadIdx.x] = lam * d2;
+    redl[(size_t)(D + 2) * bs + threadIdx.x] = hm * hm;
+  }
+  __syncthreads();
+  if (live && s == 0) {
+    for (int r = 0; r < D + 3; ++r) {
+      float acc = 0.0f;
+      for (int j = 0; j < a.ns; ++j) acc += redl[(size_t)r * bs + threadIdx.x + j];
+      a.part[(size_t)r * KQ + q] = acc;
+    }
+  }
+}
+
+// ---- R3: scalars -- one CTA: the three means, the logged terms, total, and d total / d mu_i ----------------------
+template <int D>
+__global__ void __launch_bounds__(256) k_reg_scalars(const __grid_constant__ RegK a) {
+  __shared__ float sh[3][256];
+  const int K0 = a.B * a.Hd;
+  const long long KQ = (long long)K0 * a.N;
+  float smu = 0.0f, sgn = 0.0f, ssc = 0.0f;
+  for (int i = threadIdx.x; i < K0; i += 256) {
+    smu += a.cen[(size_t)(2 * D + 1) * K0 + i];
+    sgn += a.cen[(size_t)(2 * D + 2) * K0 + i];
+  }
+  for (long long q = threadIdx.x; q < KQ; q += 256) ssc += a.part[(size_t)(D + 2) * KQ + q];
+  sh[0][threadIdx.x] = smu;
+  sh[1][threadIdx.x] = sgn;
+  sh[2][threadIdx.x] = ssc;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
+      sh[1][threadIdx.x] += sh[1][threadIdx.x + w];
+      sh[2][threadIdx.x] += sh[2][threadIdx.x + w];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const float m = sh[0][0] / (float)K0;
+    const float gmean = sh[1][0] / (float)K0;
+    const float scmean = sh[2][0] / (float)((long long)a.B * a.N);
+    float lmu = 0.0f, dlmu = 0.0f;
+    if (a.c_mu != 0.0f) {
+      if (a.pen_mu_type == 0) {
+        lmu = 1.0f / (m * m);
+        dlmu = -2.0f / (m * m * m);
+      } else if (a.pen_mu_type == 1) {
+        lmu = 1.0f / m;
+        dlmu = -1.0f / (m * m);
+      } else {
+        lmu = __expf(-m * a.pen_mu_temp);
+        dlmu = -a.pen_mu_temp * lmu;
+      }
+    }
+    a.out[0] = a.c_g * gmean + a.c_s * scmean + a.c_mu * lmu;
+    a.out[1] = gmean;
+    a.out[2] = scmean;
+    a.out[3] = m;
+    a.out[4] = lmu;
+    a.scal[0] = a.c_mu * dlmu / (float)K0;
+  }
+}
+
+// ---- R4: second-order columns -- one thread per data point -------------------------------------------------------
+// Per-thread columns in shared memory (element j of this thread at col[j*bs]): a1 | a1' | act'(h1) | act''(h1) h1'.
+template <class M, class MuNet>
+__global__ void __launch_bounds__(64) k_reg_second(const __grid_constant__ sde4_model_desc d, const __grid_constant__ RegK a) {
+  using C = RegCfg<M, MuNet>;
+  using DNet = typename C::DNet;
+  constexpr int D = C::D, H1 = DNet::H1, H2 = DNet::H2, H1P = DNet::H1P, H2P = DNet::H2P;
+  extern __shared__ __align__(16) float smem[];
+  float* W = smem;
+  C::stage(W, a);
+  const int K0 = a.B * a.Hd;
+  const long long KQ = (long long)K0 * a.N;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K0) return;
+  const int bs = blockDim.x;
+  float* col = smem + up4(C::W_FLOATS) + threadIdx.x;
+  float* cA1 = col;                            // a1, later the primal adjoint of h1
+  float* cT1 = col + (size_t)MAXW * bs;        // a1', later the tangent adjoint of h1'
+  float* cP1 = col + (size_t)2 * MAXW * bs;    // act'(h1)
+  float* cR1 = col + (size_t)3 * MAXW * bs;    // act''(h1) * h1'
+  const int b = i / a.Hd, t = i - b * a.Hd;
+  // sums over the particles of the ball statistics of this data point (fixed order)
+  float V[D], Lam = 0.0f, Gam = 0.0f;
+#pragma unroll
+  for (int k = 0; k < D; ++k) V[k] = 0.0f;
+  for (int n = 0; n < a.N; ++n) {
+    const long long q = ((long long)b * a.N + n) * a.Hd + t;
+#pragma unroll
+    for (int k = 0; k < D; ++k) V[k] += a.part[(size_t)k * KQ + q];
+    Lam += a.part[(size_t)D * KQ + q];
+    Gam += a.part[(size_t)(D + 1) * KQ + q];
+  }
+  float z[D], v[D];
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    z[k] = a.cen[(size_t)k * K0 + i];
+    v[k] = 2.0f * a.a_g * a.cen[(size_t)(D + k) * K0 + i] - a.a_s * V[k];
+  }
+  const float c_den = -a.a_s * Lam;
+  const float mu = a.cen[(size_t)(2 * D + 1) * K0 + i];
+  const float c_mu = a.scal[0] - 0.5f * a.a_s * Gam;  // d total / d mu_i
+  const size_t colA = (size_t)a.K2 + i, colB = (size_t)a.K2 + K0 + i;
+  float* ds = a.dstream;
+  const size_t ld = a.Ktot;
+  auto dumpAB = [&](int row, float va, float vb) {
+    ds[(size_t)row * ld + colA] = va;
+    ds[(size_t)row * ld + colB] = vb;
+  };
+  const float* w0 = W + DNet::OFF_W0;
+  const float* w1 = W + DNet::OFF_W1;
+  const float* w2 = W + DNet::OFF_W2;
+#pragma unroll
+  for (int k = 0; k < D; ++k) dumpAB(DNet::R_IN + k, z[k], v[k]);
+  dumpAB(C::ONE_ROW, 1.0f, 0.0f);
+  // layer 1, primal and tangent
+  for (int j = 0; j < H1; ++j) {
+    float h = W[DNet::OFF_B0 + j], ht = 0.0f;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      const float w = w0[k * H1P + j];
+      h = fmaf(z[k], w, h);
+      ht = fmaf(v[k], w, ht);
+    }
+    float av, p, pp;
+    act_fwd_dd<DNet::ACT>(h, av, p, pp);
+    cA1[(size_t)j * bs] = av;
+    cT1[(size_t)j * bs] = p * ht;
+    cP1[(size_t)j * bs] = p;
+    cR1[(size_t)j * bs] = pp * ht;
+    dumpAB(DNet::R_H1 + j, av, p * ht);
+  }
+  // layer 2: rolled over the input rows, both accumulators in registers
+  float h2[H2], t2[H2];
+#pragma unroll
+  for (int j = 0; j < H2; ++j) {
+    h2[j] = W[DNet::OFF_B1 + j];
+    t2[j] = 0.0f;
+  }
+#pragma unroll 2
+  for (int r = 0; r < H1; ++r) {
+    const float av = cA1[(size_t)r * bs], at = cT1[(size_t)r * bs];
+    const float* row = w1 + r * H2P;
+#pragma unroll
+    for (int j = 0; j < H2; ++j) {
+      h2[j] = fmaf(av, row[j], h2[j]);
+      t2[j] = fmaf(at, row[j], t2[j]);
+    }
+  }
+  // layer 3 + the sigmoid; h2 <- primal adjoint of h2, t2 <- tangent adjoint of h2'
+  float s = W[DNet::OFF_B2], st = 0.0f;
+  float p2[H2];
+#pragma unroll
+  for (int j = 0; j < H2; ++j) {
+    float av, p, pp;
+    act_fwd_dd<DNet::ACT>(h2[j], av, p, pp);
+    const float at = p * t2[j];
+    s = fmaf(w2[j], av, s);
+    st = fmaf(w2[j], at, st);
+    dumpAB(DNet::R_H2 + j, av, at);
+    p2[j] = p;
+    h2[j] = pp * t2[j];  // act''(h2) h2'
+  }
+  const float den = sigmoidf_(s - 7.0f);
+  const float sp = den * (1.0f - den), spp = sp * (1.0f - 2.0f * den);
+  const float adj_st = sp, adj_s = fmaf(c_den, sp, spp * st);
+  dumpAB(DNet::R_GOUT, adj_s, adj_st);
+#pragma unroll
+  for (int j = 0; j < H2; ++j) {
+    const float gA = w2[j] * (h2[j] * adj_st + p2[j] * adj_s);
+    const float gB = w2[j] * p2[j] * adj_st;
+    h2[j] = gA;
+    t2[j] = gB;
+    dumpAB(DNet::R_G2 + j, gA, gB);
+  }
+  // back through layer 2 into the adjoints of h1 / h1'
+#pragma unroll 2
+  for (int r = 0; r < H1; ++r) {
+    const float* row = w1 + r * H2P;
+    float ra = 0.0f, rb = 0.0f;
+#pragma unroll
+    for (int j = 0; j < H2; ++j) {
+      ra = fmaf(row[j], h2[j], ra);
+      rb = fmaf(row[j], t2[j], rb);
+    }
+    const float cB = cP1[(size_t)r * bs] * rb;
+    const float cA = fmaf(cR1[(size_t)r * bs], rb, cP1[(size_t)r * bs] * ra);
+    dumpAB(DNet::R_C1 + r, cA, cB);
+  }
+  // mu: d total / d (net output) = c_mu * mu
+  if (a.mu_type == REG_MU_DNN) {
+    Scratch sc;
+    sc.base = col;
+    sc.bs = bs;
+    sc.dnet[1] = a.mstream;
+    sc.dstride = (size_t)K0;
+    sc.dcol = (size_t)i;
+    float gout[1] = {c_mu * mu}, gin[D];
+    mlp_fwd_vjp<MuNet, true>(W + DNet::SIZE, sc, z, gout, gin, 1);
+    (void)gin;
+  } else if (a.mu_type == REG_MU_GLOBAL) {
+    a.mstream[i] = c_mu * mu;  // summed by K5 (bias-type task)
+  }
+  (void)d;
+}
+
+}  // namespace sde4

@@ -4,6 +4,7 @@
 #include <type_traits>
 #include <vector>
 #include "kernels.cuh"
+#include "reg_kernels.cuh"
 
 namespace sde4 {
 
@@ -29,6 +30,9 @@ struct ArchEntry {
   int net_dims[3][4];   // IN, H1, H2, OUT of density / net A / net B (0 = absent)
   int net_off[3];       // offsets of the three networks in the packed block
   int n_scaler, off_scaler;
+  // distance-aware regulariser (reg_kernels.cuh); mu network of the compiled instance: D -> 8 -> 8 -> 1, tanh
+  cudaError_t (*launch_reg)(const sde4_model_desc&, const RegK&, cudaStream_t);
+  int act_density;
 };
 
 std::vector<ArchEntry>& arch_table();
@@ -82,6 +86,16 @@ cudaError_t launch_rollout_t(const sde4_model_desc& d, const RolloutK& a, int bl
     if constexpr (M::Ev::L > 1)
       cudaFuncSetAttribute(k_rollout<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<M>(256, false));
     attr_set.mark(dev);
+  }
+  if (a.last) {  // simulator summary (sde4_sim_rollout): its own instantiation, generic noise path
+    static DevOnce attr_sim;
+    if (attr_sim.need(dev)) {
+      cudaFuncSetAttribute(k_rollout<M, false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)smem_bytes<M>(256, false));
+      attr_sim.mark(dev);
+    }
+    k_rollout<M, false, false, true><<<blocks, threads, sm, s>>>(d, a);
+    return cudaGetLastError();
   }
   if constexpr (M::Ev::L > 1) {
     if (a.noise_mode == SDE4_NOISE_THREEFRY && a.solver == SDE4_SOLVER_EULER_MARUYAMA) {  // pipelined-noise instantiation
@@ -222,6 +236,35 @@ cudaError_t launch_loss_t(const sde4_model_desc& d, const sde4_cost_desc& cd, co
   return cudaGetLastError();
 }
 
+// distance-aware regulariser: R1 centres -> R2 ball samples -> R3 scalars -> R4 second-order columns (reg_kernels.cuh)
+template <class M, class MuNet>
+cudaError_t launch_reg_t(const sde4_model_desc& d, const RegK& a, cudaStream_t s) {
+  using C = RegCfg<M, MuNet>;
+  using DNet = typename C::DNet;
+  const int K0 = a.B * a.Hd;
+  const long long KQ = (long long)K0 * a.N;
+  const int dev = current_device();
+  static DevOnce attr_set;
+  const size_t sm1 = (size_t)(up4(C::W_FLOATS) + Scratch::NSLOTS * MAXW * 128) * 4;
+  const int bs2 = a.ns <= 160 ? (160 / a.ns) * a.ns : 0;
+  if (bs2 == 0) return cudaErrorInvalidValue;
+  const size_t sm2 = (size_t)(up4(DNet::SIZE) + (3 * MAXW + C::D + 3) * bs2) * 4;
+  const size_t sm4 = (size_t)(up4(C::W_FLOATS) + 4 * MAXW * 64) * 4;
+  if (attr_set.need(dev)) {
+    cudaFuncSetAttribute(k_reg_centre<M, MuNet>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1);
+    cudaFuncSetAttribute(k_reg_ball<M, MuNet>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((up4(DNet::SIZE) + (3 * MAXW + C::D + 3) * 160) * 4));
+    cudaFuncSetAttribute(k_reg_second<M, MuNet>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm4);
+    attr_set.mark(dev);
+  }
+  k_reg_centre<M, MuNet><<<(K0 + 127) / 128, 128, sm1, s>>>(d, a);
+  const int gpc = bs2 / a.ns;
+  k_reg_ball<M, MuNet><<<(unsigned)((KQ + gpc - 1) / gpc), bs2, sm2, s>>>(d, a);
+  k_reg_scalars<C::D><<<1, 256, 0, s>>>(a);
+  k_reg_second<M, MuNet><<<(K0 + 63) / 64, 64, sm4, s>>>(d, a);
+  return cudaGetLastError();
+}
+
 constexpr int ilog2(int v) { return v <= 1 ? 0 : 1 + ilog2(v / 2); }
 
 template <class MLS>
@@ -281,6 +324,12 @@ ArchEntry make_entry(const char* name) {
   e.net_off[2] = A::OFF_NET_B;
   e.n_scaler = A::N_SCALER;
   e.off_scaler = A::OFF_SCALER;
+  e.launch_reg = nullptr;
+  e.act_density = D::ACT;
+  if constexpr (!std::is_same<MTRAIN, NoLaneSplit>::value && A::HAS_DENSITY) {
+    // every learn_mucoeff network of the reference's configurations is [8, 8] tanh (cartpole_sde.yaml:103-107, ...)
+    e.launch_reg = &launch_reg_t<MTRAIN, Net<D::IN, 8, 8, 1, SDE4_ACT_TANH>>;
+  }
   return e;
 }
 

@@ -186,13 +186,32 @@ int sde4_param_layout(const sde4_model_desc* model, int32_t* offsets) {
   return e->param_total;
 }
 
+static int rollout_impl(const sde4_model_desc* model, const sde4_rollout_args* a, const sde4_sim_out* so, void* stream);
+
 int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void* stream) {
+  return rollout_impl(model, a, nullptr, stream);
+}
+
+int sde4_sim_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, const sde4_sim_out* so, void* stream) {
+  if (!so) return fail(SDE4_ERR_INVALID, "null sde4_sim_out");
+  if (!so->last) return fail(SDE4_ERR_INVALID, "sim: `last` is required");
+  if (so->reward_kind != SDE4_REWARD_NONE && so->reward_kind != SDE4_REWARD_CARTPOLE_SWINGUP)
+    return fail(SDE4_ERR_UNSUPPORTED, "sim: unknown reward kind");
+  if (so->reward_kind != SDE4_REWARD_NONE && !so->racc) return fail(SDE4_ERR_INVALID, "sim: `racc` is required with a reward");
+  if (so->reward_kind == SDE4_REWARD_CARTPOLE_SWINGUP && (!model || model->n_x != 4))
+    return fail(SDE4_ERR_UNSUPPORTED, "sim: the cartpole swing-up reward needs the 4-state cartpole model");
+  if (a && a->solver != SDE4_SOLVER_EULER_MARUYAMA)
+    return fail(SDE4_ERR_UNSUPPORTED, "sim: the simulator summary integrates with Euler-Maruyama only");
+  return rollout_impl(model, a, so, stream);
+}
+
+static int rollout_impl(const sde4_model_desc* model, const sde4_rollout_args* a, const sde4_sim_out* so, void* stream) {
   if (!model || !a) return fail(SDE4_ERR_INVALID, "null argument");
   if (a->struct_size != (int)sizeof(sde4_rollout_args)) return fail(SDE4_ERR_INVALID, "sde4_rollout_args size mismatch (ABI)");
   const ArchEntry* e = find_arch(*model);
   if (!e) return fail(SDE4_ERR_UNSUPPORTED, "no compiled specialisation for %s; compiled: %s", describe(*model).c_str(), sde4_supported_archs());
   if (a->P <= 0 || a->N <= 0 || a->H <= 0) return fail(SDE4_ERR_INVALID, "P, N, H must be positive");
-  if (!a->params || !a->y0 || !a->u || !a->dt || !a->xevol) return fail(SDE4_ERR_INVALID, "null buffer");
+  if (!a->params || !a->y0 || !a->u || !a->dt || (!so && !a->xevol)) return fail(SDE4_ERR_INVALID, "null buffer");
   if (((uintptr_t)a->params & 15) != 0) return fail(SDE4_ERR_INVALID, "params must be 16-byte aligned");
   if (a->x_rows < e->nx) return fail(SDE4_ERR_INVALID, "x_rows < n_x");
   if (a->noise_mode == SDE4_NOISE_THREEFRY && !a->key) return fail(SDE4_ERR_INVALID, "threefry noise needs a key");
@@ -224,6 +243,9 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void*
   if (k.n_off < 0 || k.n_off + a->N > k.n_tot) return fail(SDE4_ERR_INVALID, "bad particle shard");
   if (a->solver < SDE4_SOLVER_EULER_MARUYAMA || a->solver > SDE4_SOLVER_STRAT_MILSTEIN) return fail(SDE4_ERR_INVALID, "unknown solver");
   k.solver = a->solver;
+  k.last = so ? so->last : nullptr;
+  k.racc = so ? so->racc : nullptr;
+  k.reward_kind = so ? so->reward_kind : SDE4_REWARD_NONE;
   const int lanes = pick_lanes(*e, a->lanes, G, false);
   if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
   const long long nthr = G * lanes;
@@ -231,6 +253,27 @@ int sde4_rollout(const sde4_model_desc* model, const sde4_rollout_args* a, void*
   const int blocks = (int)((nthr + threads - 1) / threads);
   cudaError_t err = e->launch_rollout[ilog2(lanes)](*model, k, blocks, threads, (cudaStream_t)stream);
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rollout launch (%s): %s", e->name, cudaGetErrorString(err));
+  if (so && (so->mean || so->std || so->reward_mean || so->reward_of_mean || so->done_of_mean)) {
+    SimReduceK r;
+    r.last = so->last;
+    r.racc = so->racc;
+    r.u_last = a->u + (size_t)(a->H - 1) * a->u_stride_t;
+    r.u_sp = a->u_stride_p;
+    r.u_sj = a->u_stride_j;
+    r.mean = so->mean;
+    r.std = so->std;
+    r.reward_mean = so->reward_mean;
+    r.reward_of_mean = so->reward_of_mean;
+    r.done_of_mean = so->done_of_mean;
+    r.P = a->P;
+    r.N = a->N;
+    r.n_x = e->nx;
+    r.reward_kind = so->reward_kind;
+    const long long items = (long long)a->P * e->nx;
+    k_sim_reduce<<<(unsigned)((items + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r);
+    err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "sim reduce launch: %s", cudaGetErrorString(err));
+  }
   return SDE4_OK;
 }
 
@@ -640,6 +683,210 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     k_wgrad_partial<<<dim3(wk.n_chunks, wk.n_tasks), 256, slab, s>>>(wk);
     k_wgrad_final<<<(wk.n_pairs + 255) / 256, 256, 0, s>>>(wk);
     err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(err));
+  }
+  return SDE4_OK;
+}
+
+// ---- distance-aware regulariser (reg_kernels.cuh) -----------------------------------------------------------------
+struct RegLayout {
+  size_t cen, part, scal, dstream, mstream, partial, total;
+  unsigned long long K0, KQ, K2, Ktot;
+  int d_rows, m_rows, d_pairs, m_pairs;
+};
+static RegLayout reg_layout(const ArchEntry& e, int B, int N, int Hd, int ns, int mu_type) {
+  RegLayout L;
+  const int* dm = e.net_dims[0];
+  const int D = dm[0], H1 = dm[1], H2 = dm[2];
+  L.K0 = (unsigned long long)B * Hd;
+  L.KQ = L.K0 * N;
+  L.K2 = L.KQ * ns;
+  L.Ktot = L.K2 + 2 * L.K0;
+  L.d_rows = D + 2 * H1 + 2 * H2 + 1 + 1;  // [in | h1 | h2 | c1 | g2 | gout | one]
+  L.m_rows = mu_type == SDE4_MU_DNN ? D + 2 * 8 + 2 * 8 + 1 : (mu_type == SDE4_MU_GLOBAL ? 1 : 0);
+  L.d_pairs = D * H1 + H1 + H1 * H2 + H2 + H2 + 1;
+  L.m_pairs = mu_type == SDE4_MU_DNN ? D * 8 + 8 + 8 * 8 + 8 + 8 + 1 : (mu_type == SDE4_MU_GLOBAL ? 1 : 0);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+  size_t o = 0;
+  L.cen = o;
+  o = al(o + (size_t)(2 * D + 3) * L.K0 * 4);
+  L.part = o;
+  o = al(o + (size_t)(D + 3) * L.KQ * 4);
+  L.scal = o;
+  o = al(o + 64);
+  L.dstream = o;
+  o = al(o + (size_t)L.d_rows * L.Ktot * 4);
+  L.mstream = o;
+  o = al(o + (size_t)L.m_rows * L.K0 * 4);
+  L.partial = o;
+  const size_t pd = ((L.Ktot + WG_KC - 1) / WG_KC) * (size_t)L.d_pairs * 4;
+  const size_t pm = ((L.K0 + WG_KC - 1) / WG_KC) * (size_t)L.m_pairs * 4;
+  o = al(o + (pd > pm ? pd : pm));
+  L.total = o;
+  return L;
+}
+
+size_t sde4_density_reg_workspace_bytes(const sde4_model_desc* model, int32_t B, int32_t N, int32_t Hd, int32_t ns) {
+  if (!model || B <= 0 || N <= 0 || Hd <= 0 || ns <= 0) return 0;
+  const ArchEntry* e = find_arch(*model);
+  if (!e || !e->launch_reg) return 0;
+  return reg_layout(*e, B, N, Hd, ns, SDE4_MU_DNN).total;
+}
+
+static cudaError_t run_wgrad(WgradK& wk, int max_rows, cudaStream_t s) {
+  const size_t slab = (size_t)max_rows * (WG_KC + 1) * sizeof(float);
+  static DevOnce wg_attr;
+  const int wg_dev = current_device();
+  if (wg_attr.need(wg_dev)) {
+    cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(66 * (WG_KC + 1) * sizeof(float)));
+    wg_attr.mark(wg_dev);
+  }
+  k_wgrad_partial<<<dim3(wk.n_chunks, wk.n_tasks), 256, slab, s>>>(wk);
+  k_wgrad_final<<<(wk.n_pairs + 255) / 256, 256, 0, s>>>(wk);
+  return cudaGetLastError();
+}
+
+// K5 tasks of one 3-layer network whose stream rows are [in | h1 | h2 | c1 | g2 | gout (| one)] with row stride K:
+// `one` (may be null: all columns count) weights the bias sums
+static void add_net_tasks(WgradK& wk, int& pair0, int& max_rows, const float* base, size_t K, int IN, int H1, int H2,
+                          int OUT, const float* one, float* gp) {
+  auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo) {
+    WgradTask& t = wk.task[wk.n_tasks++];
+    t.A = A;
+    t.B = B;
+    t.out = out;
+    t.n_a = n_a;
+    t.n_b = n_b;
+    t.ldo = ldo;
+    t.pair0 = pair0;
+    pair0 += n_a * n_b;
+    if (n_a + n_b > max_rows) max_rows = n_a + n_b;
+  };
+  auto up4l = [](int n) { return (n + 3) & ~3; };
+  const float* r_in = base;
+  const float* r_h1 = base + (size_t)IN * K;
+  const float* r_h2 = base + (size_t)(IN + H1) * K;
+  const float* r_c1 = base + (size_t)(IN + H1 + H2) * K;
+  const float* r_g2 = base + (size_t)(IN + 2 * H1 + H2) * K;
+  const float* r_go = base + (size_t)(IN + 2 * H1 + 2 * H2) * K;
+  const int h1p = up4l(H1), h2p = up4l(H2);
+  float* w0 = gp;
+  float* b0 = w0 + IN * h1p;
+  float* w1 = b0 + h1p;
+  float* b1 = w1 + H1 * h2p;
+  float* w2 = b1 + h2p;  // transposed: [OUT][h2p]
+  float* b2 = w2 + OUT * h2p;
+  add(r_in, IN, r_c1, H1, w0, h1p);
+  add(one, 1, r_c1, H1, b0, h1p);
+  add(r_h1, H1, r_g2, H2, w1, h2p);
+  add(one, 1, r_g2, H2, b1, h2p);
+  add(r_go, OUT, r_h2, H2, w2, h2p);
+  add(one, 1, r_go, OUT, b2, 4);
+}
+
+int sde4_density_reg(const sde4_model_desc* model, const sde4_density_reg_args* a, void* stream) {
+  if (!model || !a) return fail(SDE4_ERR_INVALID, "null argument");
+  if (a->struct_size != (uint32_t)sizeof(sde4_density_reg_args)) return fail(SDE4_ERR_INVALID, "sde4_density_reg_args size mismatch (ABI)");
+  const ArchEntry* e = find_arch(*model);
+  if (!e) return fail(SDE4_ERR_UNSUPPORTED, "no compiled specialisation for %s; compiled: %s", describe(*model).c_str(), sde4_supported_archs());
+  if (!e->launch_reg) return fail(SDE4_ERR_UNSUPPORTED, "no regulariser kernels compiled for %s (needs a density network and a training kernel)", e->name);
+  if (a->B <= 0 || a->N <= 0 || a->Hd <= 0) return fail(SDE4_ERR_INVALID, "B, N, Hd must be positive");
+  if (a->ball_nsamples <= 0 || a->ball_nsamples > 160) return fail(SDE4_ERR_INVALID, "ball_nsamples must be in 1..160");
+  if (!a->params || !a->y || !a->u || !a->key || !a->out || !a->grad_params || !a->workspace) return fail(SDE4_ERR_INVALID, "null buffer");
+  if (a->rng_mode < 0 || a->rng_mode > 1) return fail(SDE4_ERR_INVALID, "bad rng mode");
+  if (a->mu_type < SDE4_MU_CONSTANT || a->mu_type > SDE4_MU_DNN) return fail(SDE4_ERR_INVALID, "bad mu_type");
+  if (a->pen_mu_type < 0 || a->pen_mu_type > 2) return fail(SDE4_ERR_INVALID, "bad pen_mu_type");
+  const int D = e->net_dims[0][0], H1 = e->net_dims[0][1], H2 = e->net_dims[0][2];
+  if (a->mu_type != SDE4_MU_CONSTANT && (!a->mu_params || !a->grad_mu)) return fail(SDE4_ERR_INVALID, "mu parameters / gradient buffer missing");
+  if (a->mu_type == SDE4_MU_DNN) {
+    const sde4_net_desc& m = a->mu_net;
+    if (m.n_in != D || m.h1 != 8 || m.h2 != 8 || m.n_out != 1 || m.act != SDE4_ACT_TANH)
+      return fail(SDE4_ERR_UNSUPPORTED, "mu_coeff network: compiled for hidden_layers [8, 8], tanh, on the density input");
+  }
+  const unsigned long long kq = (unsigned long long)a->B * a->N * a->Hd;
+  if (kq * (unsigned long long)a->ball_nsamples > 0x7fffffffull) return fail(SDE4_ERR_INVALID, "B*N*Hd*ball_nsamples exceeds 2^31-1");
+  const RegLayout L = reg_layout(*e, a->B, a->N, a->Hd, a->ball_nsamples, a->mu_type);
+  if (a->workspace_bytes < L.total) return fail(SDE4_ERR_WORKSPACE, "workspace too small");
+  if (((uintptr_t)a->workspace & 255) != 0) return fail(SDE4_ERR_INVALID, "workspace must be 256-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  char* ws = (char*)a->workspace;
+  RegK k;
+  k.params = a->params;
+  k.mu_params = a->mu_params;
+  k.y = a->y;
+  k.u = a->u;
+  k.key = a->key;
+  k.rng_mode = a->rng_mode;
+  k.B = a->B;
+  k.N = a->N;
+  k.Hd = a->Hd;
+  k.ns = a->ball_nsamples;
+  k.mu_type = a->mu_type;
+  k.mu0 = a->mu_coeff;
+  for (int i = 0; i < REG_MAXD; ++i) k.radius[i] = a->ball_radius[i];
+  k.c_g = a->w_grad;
+  k.c_s = a->w_scvex;
+  k.c_mu = a->w_mu;
+  k.a_g = a->w_grad / (float)L.K0;
+  k.a_s = a->w_scvex / (float)((double)a->B * a->N);
+  k.pen_mu_type = a->pen_mu_type;
+  k.pen_mu_temp = a->pen_mu_temp;
+  k.cen = (float*)(ws + L.cen);
+  k.part = (float*)(ws + L.part);
+  k.scal = (float*)(ws + L.scal);
+  k.out = a->out;
+  k.dstream = (float*)(ws + L.dstream);
+  k.mstream = (float*)(ws + L.mstream);
+  k.Ktot = L.Ktot;
+  k.K2 = L.K2;
+  cudaError_t err = cudaMemsetAsync(a->grad_params, 0, (size_t)e->param_total * 4, s);
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "memset: %s", cudaGetErrorString(err));
+  if (a->mu_type != SDE4_MU_CONSTANT) {
+    const size_t n_mu = a->mu_type == SDE4_MU_DNN ? (size_t)(D * 8 + 8 + 8 * 8 + 8 + 8 + 4) : 1;
+    err = cudaMemsetAsync(a->grad_mu, 0, n_mu * 4, s);
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "memset: %s", cudaGetErrorString(err));
+  }
+  err = e->launch_reg(*model, k, s);
+  if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "regulariser launch: %s", cudaGetErrorString(err));
+  {  // density network: ball columns + primal / tangent columns, biases over the `one` row
+    WgradK wk;
+    wk.n_tasks = 0;
+    wk.K = L.Ktot;
+    wk.scale = 1.0f;
+    int pair0 = 0, max_rows = 0;
+    const float* one = k.dstream + (size_t)(L.d_rows - 1) * L.Ktot;
+    add_net_tasks(wk, pair0, max_rows, k.dstream, L.Ktot, D, H1, H2, 1, one, a->grad_params + e->net_off[0]);
+    wk.n_pairs = pair0;
+    wk.n_chunks = (int)((L.Ktot + WG_KC - 1) / WG_KC);
+    wk.partial = (float*)(ws + L.partial);
+    if (pair0 != L.d_pairs) return fail(SDE4_ERR_INVALID, "internal: regulariser pair count");
+    err = run_wgrad(wk, max_rows, s);
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(err));
+  }
+  if (a->mu_type != SDE4_MU_CONSTANT) {  // (stream-ordered after the density pass: the partial buffer is shared)
+    WgradK wk;
+    wk.n_tasks = 0;
+    wk.K = L.K0;
+    wk.scale = 1.0f;
+    int pair0 = 0, max_rows = 0;
+    if (a->mu_type == SDE4_MU_DNN) {
+      add_net_tasks(wk, pair0, max_rows, k.mstream, L.K0, D, 8, 8, 1, nullptr, a->grad_mu);
+    } else {
+      WgradTask& t = wk.task[wk.n_tasks++];
+      t.A = nullptr;
+      t.B = k.mstream;
+      t.out = a->grad_mu;
+      t.n_a = 1;
+      t.n_b = 1;
+      t.ldo = 1;
+      t.pair0 = 0;
+      pair0 = 1;
+      max_rows = 2;
+    }
+    wk.n_pairs = pair0;
+    wk.n_chunks = (int)((L.K0 + WG_KC - 1) / WG_KC);
+    wk.partial = (float*)(ws + L.partial);
+    err = run_wgrad(wk, max_rows, s);
     if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(err));
   }
   return SDE4_OK;

@@ -11,9 +11,12 @@ torch (cuBLAS) on the device with ``torch.autograd``; what is hand-written is th
 noise (``sde4_rng_split_many`` / ``sde4_rng_normal_many``), so that the terms are comparable with the reference for
 the same ``rng``.
 """
+import ctypes as C
+
 import numpy as np
 import torch
 
+from . import _lib as L
 from . import random as _random
 from ._lib import Sde4Error
 
@@ -277,4 +280,155 @@ class GraphedRegulariser:
             n = int(np.prod(shp)) if len(shp) else 1
             grads.setdefault(mod, {})[k] = res[o:o + n].reshape(shp).copy()
             o += n
+        return float(res[0]), info, grads
+
+
+def regulariser_weights(loss_params, dl):
+    """(w_grad, w_scvex, w_mu): the weights of gradDensity, densitySCVEX and lossMuCoeff in ``total_sum``
+    (nsde.py:1223-1250), ``pen_scvex_mult`` folded in; a term whose penalty is not positive is left out."""
+    mult = float(loss_params.get("pen_scvex_mult", 1.0))
+    w_g = w_s = w_m = 0.0
+    if loss_params.get("pen_grad_density", 0) > 0:
+        p_mu = dl["mu_coeff"]
+        w_g = loss_params["pen_grad_density"] * p_mu * dl.get("grad_scaler", 1.0 / p_mu) * mult
+    if loss_params.get("pen_density_scvex", 0) > 0:
+        w_s = loss_params["pen_density_scvex"] * mult
+    if loss_params.get("pen_mu_coeff", 0) > 0:
+        w_m = loss_params["pen_mu_coeff"] * mult
+    return float(w_g), float(w_s), float(w_m)
+
+
+class NativeRegulariser:
+    """The regulariser's value, logged scalars and parameter gradient from the library's own kernels
+    (``sde4_density_reg``, csrc/reg_kernels.cuh): centres -> ball samples -> scalars -> second-order columns -> the
+    weight-gradient reduction; no library GEMM, no autograd graph.  One pinned H2D copy of the mu parameters (the
+    density network travels in the engine's packed block), one D2H copy of [5 scalars | gradient blocks].
+
+    Covers what the reference's configurations use: ``learn_mucoeff`` of type constant / global / dnn with
+    hidden_layers [8, 8] and tanh; no ``quad_approx``; the terms at every data point (``density_on_partial`` keeps the
+    torch path)."""
+
+    def __init__(self, model, engine, loss_params, dl, num_particles):
+        self.model, self.engine, self.lp, self.dl, self.N = model, engine, loss_params, dl, num_particles
+        lm = dl["learn_mucoeff"]
+        self.mu_type = {"constant": L.MU_CONSTANT, "global": L.MU_GLOBAL}.get(lm["type"], L.MU_DNN)
+        self.dim = engine.desc.density.n_in
+        self.mu_desc = L.NetDesc()
+        self.mu_size = 0
+        if self.mu_type == L.MU_DNN:
+            hl = list(lm["hidden_layers"])
+            act = {"tanh": L.ACT_TANH, "swish": L.ACT_SWISH}.get(lm["activation_fn"], -1)
+            if len(hl) != 2:
+                raise Sde4Error("mu_coeff network: two hidden layers expected")
+            self.mu_desc.n_in, self.mu_desc.h1, self.mu_desc.h2, self.mu_desc.n_out, self.mu_desc.act = self.dim, hl[0], hl[1], 1, act
+            up4 = lambda n: (n + 3) & ~3
+            self.mu_size = self.dim * up4(hl[0]) + up4(hl[0]) + hl[0] * up4(hl[1]) + up4(hl[1]) + up4(hl[1]) + 4
+        elif self.mu_type == L.MU_GLOBAL:
+            self.mu_size = 1
+        self._st = {}
+
+    def supported(self, B=1, Hd=1):
+        """Whether the library has regulariser kernels for this model and mu network."""
+        if self.dl["learn_mucoeff"].get("quad_approx", False) or self.dim <= 0 or self.dim > L.REG_MAXD:
+            return False
+        if self.mu_type == L.MU_DNN and (self.mu_desc.h1, self.mu_desc.h2, self.mu_desc.act) != (8, 8, L.ACT_TANH):
+            return False
+        if int(self.dl["ball_nsamples"]) > 160:
+            return False
+        return L.load().sde4_density_reg_workspace_bytes(C.byref(self.engine.desc), B, self.N, Hd, int(self.dl["ball_nsamples"])) > 0
+
+    def _state(self, B, Hd, dev):
+        sig = (B, Hd, str(dev))
+        st = self._st.get(sig)
+        if st is None:
+            ns = int(self.dl["ball_nsamples"])
+            nb = L.load().sde4_density_reg_workspace_bytes(C.byref(self.engine.desc), B, self.N, Hd, ns)
+            if nb == 0:
+                raise Sde4Error("no regulariser kernels compiled for this architecture")
+            self._st.clear()  # one batch shape at a time: the workspace holds the streams (MBs)
+            nout = 5 + self.engine.param_total + self.mu_size
+            st = self._st[sig] = {
+                "ws": torch.empty(nb, dtype=torch.uint8, device=dev),
+                "out": torch.zeros(nout, dtype=torch.float32, device=dev),
+                "out_host": torch.zeros(nout, dtype=torch.float32).pin_memory(),
+                "mu": torch.zeros(max(self.mu_size, 1), dtype=torch.float32, device=dev),
+                "mu_host": torch.zeros(max(self.mu_size, 1), dtype=torch.float32).pin_memory()}
+        return st
+
+    def _pack_mu(self, nn_params, out):
+        m = self.model.module_name
+        if self.mu_type == L.MU_GLOBAL:
+            out[0] = float(np.asarray(nn_params[m]["mu_coeff"]))
+        elif self.mu_type == L.MU_DNN:
+            self.model._pack_net(out, 0, nn_params, "%s/~mu_coeff_nn/mu_coeff/~" % m, self.mu_desc)
+
+    def _unpack_mu(self, g):
+        m = self.model.module_name
+        if self.mu_type == L.MU_GLOBAL:
+            return {m: {"mu_coeff": np.float32(g[0])}}
+        if self.mu_type != L.MU_DNN:
+            return {}
+        up4 = lambda n: (n + 3) & ~3
+        d = [self.dim, self.mu_desc.h1, self.mu_desc.h2, 1]
+        pre = "%s/~mu_coeff_nn/mu_coeff/~" % m
+        tree, o = {}, 0
+        for k in range(3):
+            if k < 2:
+                outp = up4(d[k + 1])
+                w = g[o:o + d[k] * outp].reshape(d[k], outp)[:, :d[k + 1]].copy()
+                o += d[k] * outp
+            else:
+                inp = up4(d[k])
+                w = g[o:o + d[k + 1] * inp].reshape(d[k + 1], inp)[:, :d[k]].T.copy()
+                o += d[k + 1] * inp
+            b = g[o:o + d[k + 1]].copy()
+            o += up4(d[k + 1])
+            tree["%s/linear_%d" % (pre, k)] = {"w": w, "b": b}
+        return tree
+
+    def __call__(self, nn_params, y, u, key):
+        """-> (total, {logged scalars}, {mod: {leaf: numpy gradient}}) for device tensors y[B, Hd+1, n_y], u[B, Hd, n_u]
+        and a device key int32[2]."""
+        eng = self.engine
+        y, u = y.contiguous(), u.contiguous()
+        B, Hd = y.shape[0], y.shape[1] - 1
+        assert tuple(y.shape) == (B, Hd + 1, eng.n_x) and tuple(u.shape) == (B, Hd, eng.n_u)
+        st = self._state(B, Hd, y.device)
+        pk = eng.packed(nn_params)
+        if self.mu_size:
+            self._pack_mu(nn_params, st["mu_host"].numpy())
+            st["mu"].copy_(st["mu_host"], non_blocking=True)
+        a = L.DensityRegArgs()
+        a.struct_size = C.sizeof(L.DensityRegArgs)
+        a.B, a.N, a.Hd = B, self.N, Hd
+        a.params, a.y, a.u, a.key = pk.dev.data_ptr(), y.data_ptr(), u.data_ptr(), key.data_ptr()
+        a.rng_mode = _random.rng_mode()
+        a.ball_nsamples = int(self.dl["ball_nsamples"])
+        rad = np.broadcast_to(np.asarray(self.dl["ball_radius"], np.float32), (self.dim,))
+        for i in range(self.dim):
+            a.ball_radius[i] = float(rad[i])
+        a.mu_type, a.mu_net = self.mu_type, self.mu_desc
+        a.mu_params = st["mu"].data_ptr() if self.mu_size else None
+        a.mu_coeff = float(self.dl["mu_coeff"])
+        a.w_grad, a.w_scvex, a.w_mu = regulariser_weights(self.lp, self.dl)
+        kind = self.lp.get("pen_mu_type", "quad_inv")
+        if kind not in L.PEN_MU:
+            raise ValueError("Unknown pen_mu_type: {}. Choose from quad_inv, lin_inv, exp_inv".format(kind))
+        a.pen_mu_type = L.PEN_MU[kind]
+        a.pen_mu_temp = float(self.lp.get("pen_mu_temp", 0.0))
+        out = st["out"]
+        a.out = out.data_ptr()
+        a.grad_params = out[5:].data_ptr()
+        a.grad_mu = out[5 + eng.param_total:].data_ptr() if self.mu_size else None
+        a.workspace, a.workspace_bytes = st["ws"].data_ptr(), st["ws"].numel()
+        stream = torch.cuda.current_stream(y.device)
+        L.check(L.load().sde4_density_reg(C.byref(eng.desc), C.byref(a), C.c_void_p(stream.cuda_stream)))
+        st["out_host"].copy_(out, non_blocking=True)
+        stream.synchronize()
+        res = st["out_host"].numpy()
+        info = {k: float(res[1 + i]) for i, k in enumerate(_INFO_KEYS)}
+        gtree = self.model.unpack_grads(res[5:5 + eng.param_total], eng.desc)
+        pre = "%s/~construct_diffusion_density_nn/density/~" % self.model.module_name
+        grads = {mod: leaves for mod, leaves in gtree.items() if mod.startswith(pre)}
+        grads.update(self._unpack_mu(res[5 + eng.param_total:]))
         return float(res[0]), info, grads

@@ -189,7 +189,7 @@ class Engine:
 
     # ---- K1 --------------------------------------------------------------
     def rollout(self, nn_params, y0, u, dt, key=None, N=1, noise=None, noise_mode=None, x_rows=None,
-                block_threads=0, out=None, particle_offset=0, particle_total=0, lanes=0, solver=None):
+                block_threads=0, out=None, particle_offset=0, particle_total=0, lanes=0, solver=None, sim=None):
         """y0[P,n_x], u[P,H,n_u] (or [H,n_u], shared), key [2] or [P,2].  Returns the native
         buffer ``xevol[H+1, x_rows, P*N]`` (sample-minor)."""
         pk = self.packed(nn_params)
@@ -210,7 +210,7 @@ class Engine:
             raise AssertionError("Dimension mismatch on the input of the sde solver")
         G = P * N
         x_rows = self.n_x if x_rows is None else x_rows
-        if out is None:
+        if out is None and sim is None:
             out = torch.empty((H + 1, x_rows, G), dtype=torch.float32, device=y0.device)
         if noise_mode is None:
             noise_mode = L.NOISE_GIVEN if noise is not None else (L.NOISE_THREEFRY if self.noisy else L.NOISE_NONE)
@@ -239,8 +239,41 @@ class Engine:
         if name not in L.SOLVERS:
             raise Sde4Error("unknown sde_solver '%s' (known: %s)" % (name, ", ".join(L.SOLVERS)))
         a.solver = L.SOLVERS[name]
+        if sim is not None:  # _lib.SimOut: simulator summary (last state, particle mean / std, rewards); `out` may be None
+            L.check(L.load().sde4_sim_rollout(C.byref(self.desc), C.byref(a), C.byref(sim), _stream()))
+            return out
         L.check(L.load().sde4_rollout(C.byref(self.desc), C.byref(a), _stream()))
         return out
+
+    def sim_rollout(self, nn_params, y0, u, dt, key, N=1, reward=None, want_std=False, want_step=False, want_traj=False,
+                    lanes=0):
+        """The nSDE as a simulator: P start states x N particles x H steps, WITHOUT writing the trajectories
+        (``sde4_sim_rollout``).  Returns a dict: ``mean[P, n_x]`` (particle mean of the last state), ``std`` (population
+        std, with ``want_std``), ``last[n_x, P*N]``; with ``reward='cartpole_swingup'`` also ``reward_mean[P]`` (per-particle
+        reward summed over the steps up to termination, averaged over particles) and, with ``want_step``,
+        ``reward_of_mean[P]`` / ``done_of_mean[P]`` of the mean next state (mbrl ModelEnv.step)."""
+        y0 = as_f32(y0).reshape(-1, self.n_x).contiguous()
+        P, dev = y0.shape[0], y0.device
+        G = P * N
+        kind = {None: L.REWARD_NONE, "cartpole_swingup": L.REWARD_CARTPOLE_SWINGUP}[reward]
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        res = {"last": f(self.n_x, G), "mean": f(P, self.n_x)}
+        so = L.SimOut()
+        so.reward_kind = kind
+        so.last, so.mean = res["last"].data_ptr(), res["mean"].data_ptr()
+        if want_std:
+            res["std"] = f(P, self.n_x)
+            so.std = res["std"].data_ptr()
+        if kind:
+            res["racc"], res["reward_mean"] = f(G), f(P)
+            so.racc, so.reward_mean = res["racc"].data_ptr(), res["reward_mean"].data_ptr()
+            if want_step:
+                res["reward_of_mean"] = f(P)
+                res["done_of_mean"] = torch.empty(P, dtype=torch.int32, device=dev)
+                so.reward_of_mean, so.done_of_mean = res["reward_of_mean"].data_ptr(), res["done_of_mean"].data_ptr()
+        out = torch.empty((np.asarray(dt).shape[0] + 1, self.n_x, G), dtype=torch.float32, device=dev) if want_traj else None
+        res["xevol"] = self.rollout(nn_params, y0, u, dt, key=key, N=N, out=out, lanes=lanes, sim=so)
+        return res
 
     # ---- K2 + K3 ----------------------------------------------------------
     def cost_grad(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, noise=None,

@@ -35,9 +35,8 @@ class SDESimulator:
         (population std, as ``jnp.std``)."""
         u = as_f32(u).reshape(self.H, -1)
         self.engine.rng_mode = R.rng_mode()
-        xbuf = self.engine.rollout(self.pk, as_f32(x).reshape(1, -1), u, self.ts, key=as_key(rng), N=self.N)
-        last = xbuf[self.H]  # [n_x, N]
-        return last.mean(dim=1), last.std(dim=1, unbiased=False)
+        r = self.engine.sim_rollout(self.pk, as_f32(x).reshape(1, -1), u, self.ts, as_key(rng), N=self.N, want_std=True)
+        return r["mean"][0], r["std"][0]  # reduced on the device by k_sim_reduce; no trajectory is written
 
     def predict(self, obs, act, rng, return_particles=False):
         """P start states ``obs[P, n_x]``, controls ``act[P, H, n_u]`` (or ``[P, n_u]`` for H = 1),
@@ -52,11 +51,32 @@ class SDESimulator:
         if keys.dim() == 1:
             keys = R.split(keys, P)
         self.engine.rng_mode = R.rng_mode()
-        xbuf = self.engine.rollout(self.pk, obs, act, self.ts, key=keys, N=self.N)
         n_x = self.engine.n_x
         if return_particles:
+            xbuf = self.engine.rollout(self.pk, obs, act, self.ts, key=keys, N=self.N)
             return xbuf.view(self.H + 1, n_x, P, self.N).permute(2, 3, 0, 1)
-        return xbuf[self.H].view(n_x, P, self.N).mean(dim=2).t()
+        # fused path: only the last states leave the kernel ([n_x, P*N] instead of [H+1, n_x, P*N]), the particle mean
+        # is taken by the reduction kernel
+        return self.engine.sim_rollout(self.pk, obs, act, self.ts, keys, N=self.N)["mean"]
+
+    def step_summary(self, obs, act, rng, reward=None):
+        """One fused call for mbrl's ``ModelEnv.step``: next states (particle mean) and, for a reward the kernels know
+        (``'cartpole_swingup'``), reward and termination of the mean next state."""
+        obs = as_f32(obs)
+        P = obs.shape[0]
+        act = as_f32(act)
+        if act.dim() == 2:
+            act = act.reshape(P, 1, -1)
+        keys = as_key(rng)
+        if keys.dim() == 1:
+            keys = R.split(keys, P)
+        self.engine.rng_mode = R.rng_mode()
+        return self.engine.sim_rollout(self.pk, obs, act, self.ts, keys, N=self.N, reward=reward, want_step=reward is not None)
+
+    def sequence_rewards(self, obs, act, rng, reward):
+        """Per start state / control sequence: the per-particle reward summed over the steps up to termination, averaged
+        over the particles, accumulated INSIDE the rollout kernel (mbrl ``evaluate_action_sequences``)."""
+        return self.step_summary(obs, act, rng, reward=reward)["reward_mean"]
 
 
 # ---------------------------------------------------------------------------------------------
@@ -91,6 +111,9 @@ class SDEModelEnv:
         self.termination_fn, self.reward_fn = termination_fn, reward_fn
         self.obs_fn = obs_fn if obs_fn is not None else (lambda s: s)
         self._rng = R.PRNGKey(seed)
+        # the reward / termination pair the rollout kernel evaluates itself (cartpole swing-up on cartpole_obs)
+        self._fused_kind = "cartpole_swingup" if (reward_fn is cartpole_swingup_reward and termination_fn is cartpole_swingup_termination
+                                                  and obs_fn is cartpole_obs and simulator.engine.n_x == 4) else None
 
     def _next_key(self):
         ks = R.split(self._rng)
@@ -103,6 +126,10 @@ class SDEModelEnv:
     def step(self, actions, model_state):
         """One simulator step for every state of the batch (mean over the particles, as ``_my_pred_fn``)."""
         actions = as_f32(actions).reshape(model_state["state"].shape[0], -1)
+        if self._fused_kind is not None:  # reward / termination of the mean next state come out of the same launches
+            r = self.sim.step_summary(model_state["state"], actions, self._next_key(), reward=self._fused_kind)
+            nxt = r["mean"]
+            return self.obs_fn(nxt), r["reward_of_mean"].view(-1, 1), r["done_of_mean"].bool().view(-1, 1), {"state": nxt}
         nxt = self.sim.predict(model_state["state"], actions, self._next_key())
         obs = self.obs_fn(nxt)
         rewards = self.reward_fn(actions, obs)
@@ -121,6 +148,8 @@ class SDEModelEnv:
                                horizon=Hs)
             self._seq_sim = sim
         x0 = as_f32(initial_state).reshape(1, -1).expand(B, -1)
+        if self._fused_kind is not None:  # rewards accumulated in the kernel: nothing of the trajectories is written
+            return sim.sequence_rewards(x0, seqs, self._next_key(), self._fused_kind)
         traj = sim.predict(x0, seqs, self._next_key(), return_particles=True)  # [B, N, H+1, n_x]
         obs = self.obs_fn(traj[:, :, 1:, :]).reshape(B * num_particles * Hs, -1)
         act = seqs[:, None, :, :].expand(B, num_particles, Hs, seqs.shape[-1]).reshape(B * num_particles * Hs, -1)

@@ -346,3 +346,57 @@ def test_controls_as_a_function_of_the_observation(cuda, kind):
     want = torch.stack(xs, dim=1).numpy()
     assert hp.rel_err(xevol.cpu().numpy(), want) < 5e-5
     np.testing.assert_allclose(uevol.cpu().numpy()[:, 0], np.clip(want[:, 0] @ K + c, -1, 1), rtol=1e-5, atol=1e-6)
+
+
+def test_fused_simulator_outputs(cuda):
+    """sde4_sim_rollout (no trajectory write-out; particle mean / population std, per-step reward with termination and the
+    reward / done of the mean state computed on the device) against the same quantities formed from the full
+    trajectories of sde4_rollout -- incl. samples that terminate in the middle of the sequence."""
+    import os
+    from sde4mbrl_b200 import io, random as R
+    from sde4mbrl_b200.simulator import (SDEModelEnv, SDESimulator, cartpole_obs, cartpole_swingup_reward,
+                                         cartpole_swingup_termination)
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    nn, nominal = io.load_npz_fixture(os.path.join(gold, "ref_weights_cartpole_bb_learned_si.npz"))
+    P, N, H = 37, 6, 15
+    sim = SDESimulator(sde_models.CartPoleSDE, nominal, nn, num_particles=N, tau=0.02, horizon=H)
+    rng = np.random.default_rng(5)
+    obs = rng.uniform(-1, 1, (P, 4)).astype(np.float32) * np.array([2, 3, np.pi, 6], np.float32)
+    obs[:8, 0] = 119.0 + 0.1 * np.arange(8)    # these cross |x| = 120 after a few steps (0.12 per step) ...
+    obs[:8, 1] = 6.0
+    obs[8, 0] = 500.0                          # ... this one is terminated from the first step on
+    act = rng.uniform(-1, 1, (P, H, 1)).astype(np.float32)
+    key = R.PRNGKey(9)
+    traj = sim.predict(obs, act, key, return_particles=True)              # [P, N, H+1, 4] through sde4_rollout
+    r = sim.step_summary(obs, act, key, reward="cartpole_swingup")
+    last = traj[:, :, -1, :]
+    np.testing.assert_allclose(r["mean"].cpu().numpy(), last.mean(1).cpu().numpy(), rtol=1e-6, atol=1e-6)
+    r2 = sim.engine.sim_rollout(sim.pk, obs, act, sim.ts, R.split(key, P), N=N, want_std=True)
+    np.testing.assert_allclose(r2["std"].cpu().numpy(), last.std(1, unbiased=False).cpu().numpy(), rtol=2e-4, atol=1e-6)
+    assert r2["xevol"] is None  # nothing of the trajectory was written
+    # per-particle reward summed up to (and including) the terminal step, averaged over the particles
+    o = cartpole_obs(traj[:, :, 1:, :]).reshape(P * N * H, -1)
+    a = torch.as_tensor(act, device="cuda")[:, None].expand(P, N, H, 1).reshape(P * N * H, 1)
+    rew = cartpole_swingup_reward(a, o).view(P, N, H)
+    done = cartpole_swingup_termination(a, o).view(P, N, H)
+    alive = (torch.cumsum(done.int(), dim=2) - done.int()) == 0
+    want = (rew * alive).sum(2).mean(1)
+    np.testing.assert_allclose(r["reward_mean"].cpu().numpy(), want.cpu().numpy(), rtol=2e-5, atol=1e-5)
+    assert bool(done[:8].any()) and not bool(done[:8, :, 0].all()) and bool(done[8].all())
+    # reward / termination of the MEAN next state (ModelEnv.step)
+    om = cartpole_obs(last.mean(1))
+    np.testing.assert_allclose(r["reward_of_mean"].cpu().numpy(), cartpole_swingup_reward(a[:P], om).view(-1).cpu().numpy(),
+                               rtol=2e-5, atol=1e-5)
+    assert torch.equal(r["done_of_mean"].bool().view(-1, 1), cartpole_swingup_termination(a[:P], om))
+    # the ModelEnv wrapper picks the fused path for this reward / termination / observation triple and an unfused one else
+    env = SDEModelEnv(sim, cartpole_swingup_termination, cartpole_swingup_reward, obs_fn=cartpole_obs, seed=3)
+    env_u = SDEModelEnv(sim, lambda a_, o_: cartpole_swingup_termination(a_, o_), cartpole_swingup_reward, obs_fn=cartpole_obs, seed=3)
+    assert env._fused_kind == "cartpole_swingup" and env_u._fused_kind is None
+    sim1 = SDESimulator(sde_models.CartPoleSDE, nominal, nn, num_particles=N, tau=0.02, horizon=1)
+    e1 = SDEModelEnv(sim1, cartpole_swingup_termination, cartpole_swingup_reward, obs_fn=cartpole_obs, seed=3)
+    e2 = SDEModelEnv(sim1, lambda a_, o_: cartpole_swingup_termination(a_, o_), cartpole_swingup_reward, obs_fn=cartpole_obs, seed=3)
+    o1, rw1, d1, _ = e1.step(act[:, 0], e1.reset(obs))
+    o2, rw2, d2, _ = e2.step(act[:, 0], e2.reset(obs))
+    np.testing.assert_allclose(o1.cpu().numpy(), o2.cpu().numpy(), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(rw1.cpu().numpy(), rw2.cpu().numpy(), rtol=2e-5, atol=1e-5)
+    assert torch.equal(d1, d2)
