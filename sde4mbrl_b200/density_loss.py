@@ -365,7 +365,7 @@ class NativeRegulariser:
     def _unpack_mu(self, g):
         m = self.model.module_name
         if self.mu_type == L.MU_GLOBAL:
-            return {m: {"mu_coeff": np.float32(g[0])}}
+            return {m: {"mu_coeff": np.array(g[0], np.float32)}}
         if self.mu_type != L.MU_DNN:
             return {}
         up4 = lambda n: (n + 3) & ~3

@@ -610,9 +610,18 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
                     grads.setdefault(mod, {})[name] = (2.0 * coeff * pen_w * dlt).astype(np.float32)
         return tot, grads
 
-    # loss_params["graph_regulariser"] = False keeps the regulariser on the eager torch path
-    graphed = _density.GraphedRegulariser(model, loss_params, dl, num_sample) \
-        if (dl is not None and loss_params.get("graph_regulariser", True)) else None
+    # The distance-aware regulariser runs on the library's own kernels (density_loss.NativeRegulariser ->
+    # sde4_density_reg) whenever they cover the configuration.  loss_params["regulariser"] = "graph" / "eager" (or the
+    # older "graph_regulariser": False) select the torch restatements instead: one CUDA-graph replay, or plain autograd.
+    reg_mode = loss_params.get("regulariser", "native" if loss_params.get("graph_regulariser", True) else "eager")
+    if reg_mode not in ("native", "graph", "eager"):
+        raise Sde4Error("loss_params['regulariser'] must be 'native', 'graph' or 'eager'")
+    native = None
+    if dl is not None and reg_mode == "native":
+        native = _density.NativeRegulariser(model, engine, loss_params, dl, num_sample)
+        if not native.supported():
+            native, reg_mode = None, "graph"
+    graphed = _density.GraphedRegulariser(model, loss_params, dl, num_sample) if (dl is not None and reg_mode == "graph") else None
 
     def _prepare(y, u):
         y, u = as_f32(y), as_f32(u)
@@ -673,9 +682,10 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
             total += loss_data * loss_params["pen_data"]
         dinfo, dgrads = {}, {}
         on_partial = step_weight is not None and params_model.get("density_on_partial", False)
-        if dl is not None and graphed is not None and not on_partial:
-            # distance-aware regulariser at the data points as one CUDA-graph replay (density_loss.GraphedRegulariser)
-            dval, dinfo, dgrads_np = graphed(_nn_params, as_f32(y), as_f32(u), key)
+        if dl is not None and (native is not None or graphed is not None) and not on_partial:
+            # distance-aware regulariser at the data points: the library's kernels, or one CUDA-graph replay of the
+            # torch restatement (density_loss.GraphedRegulariser)
+            dval, dinfo, dgrads_np = (native or graphed)(_nn_params, as_f32(y), as_f32(u), key)
             total += dval
             if want_grad:
                 dgrads = {mod: {k: torch.from_numpy(v) for k, v in leaves.items()} for mod, leaves in dgrads_np.items()}
@@ -724,6 +734,7 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
     loss_fn.value_and_grad = value_and_grad
     loss_fn.engine = engine
     loss_fn.weight_penalty = _penalty  # (unweighted sum, pen_weights-scaled gradients)
+    loss_fn.regulariser = "native" if native is not None else (reg_mode if dl is not None else None)
 
     nonneg = set(params_model.get("noneg_params", []))
     nonzero = loss_params.get("nonneg_nonzero", {})

@@ -104,6 +104,7 @@ def test_density_regulariser_terms_and_grads(cuda, mu_type, N, partial, cdn):
     rng = np.random.default_rng(0)
     y = (rng.normal(0, 0.5, (B, H + 1, 4)) + np.array([0, 0, 3.0, 0])).astype(np.float32)
     u = rng.uniform(-1, 1, (B, H, 1)).astype(np.float32)
+    assert loss_fn.regulariser == "native"  # (density_on_partial: the call below falls to the torch path by itself)
     total, info, grads = loss_fn.value_and_grad(nn, y, u, R.PRNGKey(3))
     tree = _tree64(nn)
     om = orc.make_model("cart_pole_sde", pm, tree, torch.float64)
@@ -401,12 +402,14 @@ def test_graphed_regulariser_replays_match_the_eager_path(cuda):
               "density_loss": {"learn_mucoeff": {"type": "dnn", "init_value": 0.3, "activation_fn": "tanh", "hidden_layers": [8, 8]},
                                "mu_coeff": 10.0, "ball_radius": [0.1, 0.1, 0.4], "ball_nsamples": 6},
               "pen_grad_density": 1.0, "pen_density_scvex": 1.0, "pen_mu_type": "lin_inv", "pen_mu_coeff": 1000.0,
-              "pen_scvex_mult": 0.01, "graph_regulariser": graph}
+              "pen_scvex_mult": 0.01, "regulariser": graph}
         nn0, loss_fn, _, _ = nsde.create_model_loss_fn(pm, lp, sde_constr=sde_models.CartPoleSDE, verbose=False)
         return pm, nn0, loss_fn
 
-    pm, nn0, f_graph = make(True)
-    _, _, f_eager = make(False)
+    pm, nn0, f_graph = make("graph")
+    _, _, f_eager = make("eager")
+    _, _, f_native = make("native")
+    assert (f_graph.regulariser, f_eager.regulariser, f_native.regulariser) == ("graph", "eager", "native")
     rng = np.random.default_rng(0)
     for rep in range(3):
         nn = configs.random_params(sde_models.CartPoleSDE(pm), seed=4 + rep)
@@ -425,3 +428,13 @@ def test_graphed_regulariser_replays_match_the_eager_path(cuda):
             for k in ge[m]:
                 assert np.max(np.abs(gg[m][k] - ge[m][k])) <= 1e-4 * np.max(np.abs(ge[m][k])) + 1e-9, (m, k)
         assert ig["densitySCVEX"] > 0
+        # the library's own kernels (sde4_density_reg) on the same inputs; float32 with MUFU activations against
+        # torch's float32 library kernels
+        tn, inn, gn_ = f_native.value_and_grad(nn, y, u, R.PRNGKey(20 + rep))
+        assert abs(tn - te) <= 5e-5 * abs(te)
+        for k in ie:
+            assert abs(inn[k] - ie[k]) <= 3e-4 * abs(ie[k]) + 1e-12, k
+        gmax = max(float(np.max(np.abs(v))) for d in ge.values() for v in d.values())
+        for m in ge:
+            for k in ge[m]:
+                assert np.max(np.abs(gn_[m][k] - ge[m][k])) <= 3e-3 * np.max(np.abs(ge[m][k])) + 1e-5 * gmax, (m, k)
