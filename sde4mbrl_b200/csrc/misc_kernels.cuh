@@ -322,6 +322,10 @@ struct WgradTask {
   const float* B;
   float* out;
   int n_a, n_b, ldo, pair0;  // pair0: first (a, b) pair of this task in the partial buffer
+  // has_e: the LAST of the n_a rows is not A's but the row E (nullptr: ones) -- the bias sums ride along with the
+  // weight task (the packed layouts keep b right behind w), so the B rows are read once for both
+  const float* E;
+  int has_e;
 };
 struct WgradK {
   WgradTask task[24];
@@ -331,50 +335,112 @@ struct WgradK {
   float* partial;  // [n_chunks][n_pairs]
 };
 
+// Register tiling: a thread owns a 4 x 4 tile of (a, b) pairs over one quarter of the slab's columns (8 LDS feed 16
+// FMA; rows of one tile are 4 apart, so the 32 tiles of a warp read distinct banks); the four column quarters are
+// summed through shared memory in a fixed order.
+constexpr int WG_ROWS_MAX = 72;  // up4(n_a) + up4(n_b), n_a, n_b <= 33
 __global__ void __launch_bounds__(256) k_wgrad_partial(const __grid_constant__ WgradK a) {
-  extern __shared__ float slab[];  // [n_a + n_b][WG_KC + 1]
+  extern __shared__ float slab[];  // [up4(n_a) + up4(n_b)][WG_KC + 1]
   const WgradTask& t = a.task[blockIdx.y];
   const unsigned long long k0 = (unsigned long long)blockIdx.x * WG_KC;
   const int kn = (int)min((unsigned long long)WG_KC, a.K - k0);
   constexpr int LD = WG_KC + 1;
-  const int rows = t.n_a + t.n_b;
-  for (int idx = threadIdx.x; idx < rows * WG_KC; idx += blockDim.x) {
-    const int r = idx / WG_KC, c = idx - r * WG_KC;
-    float v = 0.0f;
-    if (c < kn) {
-      if (r < t.n_a) v = t.A ? t.A[(size_t)r * a.K + k0 + c] : 1.0f;
-      else v = t.B[(size_t)(r - t.n_a) * a.K + k0 + c];
+  const int na4 = (t.n_a + 3) & ~3, nb4 = (t.n_b + 3) & ~3;
+  const int rows = na4 + nb4;
+  {  // thread = column of the slab (blockDim.x == WG_KC); 8 independent row loads in flight per thread
+    const int c = threadIdx.x;
+    const bool in_k = c < kn;
+    const size_t col = (size_t)k0 + c;
+    const int n_own = t.has_e ? t.n_a - 1 : t.n_a;  // rows that come from A
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int r = r0 + q;
+        float x = 0.0f;
+        if (in_k && r < rows) {
+          if (r < na4) {
+            if (r < n_own) x = t.A ? t.A[(size_t)r * a.K + col] : 1.0f;
+            else if (r < t.n_a) x = t.E ? t.E[col] : 1.0f;
+          } else if (r - na4 < t.n_b) {
+            x = t.B[(size_t)(r - na4) * a.K + col];
+          }
+        }
+        v[q] = x;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (r0 + q < rows) slab[(r0 + q) * LD + c] = v[q];
     }
-    slab[r * LD + c] = v;
   }
   __syncthreads();
-  const int pairs = t.n_a * t.n_b;
-  for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
-    const int ia = p / t.n_b, ib = p - ia * t.n_b;
-    const float* sa = slab + ia * LD;
-    const float* sb = slab + (t.n_a + ib) * LD;
-    float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+  const int tiles_b = nb4 >> 2, n_tiles = (na4 >> 2) * tiles_b;
+  const int kq = threadIdx.x >> 6, c0 = kq * (WG_KC / 4);
+  float acc[2][16];  // n_tiles <= 81: at most two tiles per thread
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int tile = (threadIdx.x & 63) + 64 * m;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) acc[m][q] = 0.0f;
+    if (tile < n_tiles) {
+      const int ta = tile / tiles_b, tb = tile - ta * tiles_b;
+      const float* sa = slab + (4 * ta) * LD + c0;
+      const float* sb = slab + (na4 + 4 * tb) * LD + c0;
 #pragma unroll 4
-    for (int c = 0; c < WG_KC; c += 4) {  // the slab is zero-padded beyond kn
-      s0 = fmaf(sa[c], sb[c], s0);
-      s1 = fmaf(sa[c + 1], sb[c + 1], s1);
-      s2 = fmaf(sa[c + 2], sb[c + 2], s2);
-      s3 = fmaf(sa[c + 3], sb[c + 3], s3);
+      for (int c = 0; c < WG_KC / 4; ++c) {  // the slab is zero-padded beyond kn and beyond n_a / n_b
+        float va[4], vb[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          va[q] = sa[q * LD + c];
+          vb[q] = sb[q * LD + c];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) acc[m][i * 4 + jj] = fmaf(va[i], vb[jj], acc[m][i * 4 + jj]);
+      }
     }
-    a.partial[(size_t)blockIdx.x * a.n_pairs + t.pair0 + p] = (s0 + s1) + (s2 + s3);
   }
+  __syncthreads();  // every thread is done with the slab: reuse it as red[4][pairs]
+  const int pairs = t.n_a * t.n_b;
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int tile = (threadIdx.x & 63) + 64 * m;
+    if (tile < n_tiles) {
+      const int ta = tile / tiles_b, tb = tile - ta * tiles_b;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int ia = 4 * ta + i, ib = 4 * tb + jj;
+          if (ia < t.n_a && ib < t.n_b) slab[kq * pairs + ia * t.n_b + ib] = acc[m][i * 4 + jj];
+        }
+    }
+  }
+  __syncthreads();
+  for (int p = threadIdx.x; p < pairs; p += blockDim.x)
+    a.partial[(size_t)blockIdx.x * a.n_pairs + t.pair0 + p] = (slab[p] + slab[pairs + p]) + (slab[2 * pairs + p] + slab[3 * pairs + p]);
 }
 
-__global__ void k_wgrad_final(const __grid_constant__ WgradK a) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= a.n_pairs) return;
+// Stage 2: a CTA sums 32 adjacent pairs over all chunks: 8 chunk lanes per pair (coalesced 128-byte rows of the partial
+// buffer), combined in a fixed order.
+__global__ void __launch_bounds__(256) k_wgrad_final(const __grid_constant__ WgradK a) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, cl = threadIdx.x >> 5;
+  const int q = blockIdx.x * 32 + lane;
+  float s = 0.0f;
+  if (q < a.n_pairs)
+    for (int c = cl; c < a.n_chunks; c += 8) s += a.partial[(size_t)c * a.n_pairs + q];
+  red[cl][lane] = s;
+  __syncthreads();
+  if (cl != 0 || q >= a.n_pairs) return;
+#pragma unroll
+  for (int w = 1; w < 8; ++w) s += red[w][lane];
   int ti = 0;
   while (ti + 1 < a.n_tasks && q >= a.task[ti + 1].pair0) ++ti;
   const WgradTask& t = a.task[ti];
   const int p = q - t.pair0;
   const int ia = p / t.n_b, ib = p - ia * t.n_b;
-  float s = 0.0f;
-  for (int c = 0; c < a.n_chunks; ++c) s += a.partial[(size_t)c * a.n_pairs + q];
   t.out[(size_t)ia * t.ldo + ib] = s * a.scale;
 }
 

@@ -229,21 +229,26 @@ __global__ void __launch_bounds__(160) k_reg_ball(const __grid_constant__ sde4_m
 
 // ---- R3: scalars -- one CTA: the three means, the logged terms, total, and d total / d mu_i ----------------------
 template <int D>
-__global__ void __launch_bounds__(256) k_reg_scalars(const __grid_constant__ RegK a) {
-  __shared__ float sh[3][256];
+__global__ void __launch_bounds__(1024) k_reg_scalars(const __grid_constant__ RegK a) {
+  __shared__ float sh[3][1024];
   const int K0 = a.B * a.Hd;
   const long long KQ = (long long)K0 * a.N;
   float smu = 0.0f, sgn = 0.0f, ssc = 0.0f;
-  for (int i = threadIdx.x; i < K0; i += 256) {
-    smu += a.cen[(size_t)(2 * D + 1) * K0 + i];
-    sgn += a.cen[(size_t)(2 * D + 2) * K0 + i];
+  const float* pmu = a.cen + (size_t)(2 * D + 1) * K0;
+  const float* pgn = a.cen + (size_t)(2 * D + 2) * K0;
+  const float* psc = a.part + (size_t)(D + 2) * KQ;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < K0; i += 1024) {
+    smu += pmu[i];
+    sgn += pgn[i];
   }
-  for (long long q = threadIdx.x; q < KQ; q += 256) ssc += a.part[(size_t)(D + 2) * KQ + q];
+#pragma unroll 4
+  for (long long q = threadIdx.x; q < KQ; q += 1024) ssc += psc[q];
   sh[0][threadIdx.x] = smu;
   sh[1][threadIdx.x] = sgn;
   sh[2][threadIdx.x] = ssc;
   __syncthreads();
-  for (int w = 128; w > 0; w >>= 1) {
+  for (int w = 512; w > 0; w >>= 1) {
     if ((int)threadIdx.x < w) {
       sh[0][threadIdx.x] += sh[0][threadIdx.x + w];
       sh[1][threadIdx.x] += sh[1][threadIdx.x + w];

@@ -260,7 +260,7 @@ cudaError_t launch_reg_t(const sde4_model_desc& d, const RegK& a, cudaStream_t s
   k_reg_centre<M, MuNet><<<(K0 + 127) / 128, 128, sm1, s>>>(d, a);
   const int gpc = bs2 / a.ns;
   k_reg_ball<M, MuNet><<<(unsigned)((KQ + gpc - 1) / gpc), bs2, sm2, s>>>(d, a);
-  k_reg_scalars<C::D><<<1, 256, 0, s>>>(a);
+  k_reg_scalars<C::D><<<1, 1024, 0, s>>>(a);
   k_reg_second<M, MuNet><<<(K0 + 63) / 64, 64, sm4, s>>>(d, a);
   return cudaGetLastError();
 }

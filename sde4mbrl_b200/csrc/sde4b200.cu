@@ -628,7 +628,7 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     wk.K = Kcols;
     wk.scale = 1.0f / (float)((double)a->P * k.n_tot);
     int pair0 = 0, max_rows = 0;
-    auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo) {
+    auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo, bool ones_row = false) {
       WgradTask& t = wk.task[wk.n_tasks++];
       t.A = A;
       t.B = B;
@@ -637,6 +637,8 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
       t.n_b = n_b;
       t.ldo = ldo;
       t.pair0 = pair0;
+      t.E = nullptr;
+      t.has_e = ones_row ? 1 : 0;
       pair0 += n_a * n_b;
       if (n_a + n_b > max_rows) max_rows = n_a + n_b;
     };
@@ -660,10 +662,11 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
       float* b1 = w1 + H1 * h2p;
       float* w2 = b1 + h2p;  // transposed: [OUT][h2p]
       float* b2 = w2 + OUT * h2p;
-      add(r_in, IN, r_c1, H1, w0, h1p);
-      add(nullptr, 1, r_c1, H1, b0, h1p);
-      add(r_h1, H1, r_g2, H2, w1, h2p);
-      add(nullptr, 1, r_g2, H2, b1, h2p);
+      // (b0 sits right behind w0 and b1 behind w1 in the packed layout: the bias sums are the extra all-ones A row)
+      (void)b0;
+      (void)b1;
+      add(r_in, IN + 1, r_c1, H1, w0, h1p, true);
+      add(r_h1, H1 + 1, r_g2, H2, w1, h2p, true);
       add(r_go, OUT, r_h2, H2, w2, h2p);
       add(nullptr, 1, r_go, OUT, b2, 4);
       if (s2 == 0 && e->n_scaler) add(nullptr, 1, r_go + (size_t)OUT * Kcols, e->n_scaler, lo.grad_params + e->off_scaler, e->n_scaler);
@@ -673,15 +676,15 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
     wk.n_chunks = (int)((Kcols + WG_KC - 1) / WG_KC);
     wk.partial = (float*)(ws + L.total + ((dump_bytes + 255) & ~(size_t)255));
     if (pair0 != loss_wgrad_pairs(*e)) return fail(SDE4_ERR_INVALID, "internal: wgrad pair count");
-    const size_t slab = (size_t)max_rows * (WG_KC + 1) * sizeof(float);
+    const size_t slab = (size_t)(max_rows + 6) * (WG_KC + 1) * sizeof(float);  // rows padded to multiples of 4 per operand
     static DevOnce wg_attr;
     const int wg_dev = current_device();
     if (wg_attr.need(wg_dev)) {
-      cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(66 * (WG_KC + 1) * sizeof(float)));
+      cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WG_ROWS_MAX * (WG_KC + 1) * sizeof(float)));
       wg_attr.mark(wg_dev);
     }
     k_wgrad_partial<<<dim3(wk.n_chunks, wk.n_tasks), 256, slab, s>>>(wk);
-    k_wgrad_final<<<(wk.n_pairs + 255) / 256, 256, 0, s>>>(wk);
+    k_wgrad_final<<<(wk.n_pairs + 31) / 32, 256, 0, s>>>(wk);
     err = cudaGetLastError();
     if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(err));
   }
@@ -734,15 +737,15 @@ size_t sde4_density_reg_workspace_bytes(const sde4_model_desc* model, int32_t B,
 }
 
 static cudaError_t run_wgrad(WgradK& wk, int max_rows, cudaStream_t s) {
-  const size_t slab = (size_t)max_rows * (WG_KC + 1) * sizeof(float);
+  const size_t slab = (size_t)(max_rows + 6) * (WG_KC + 1) * sizeof(float);  // rows padded to multiples of 4 per operand
   static DevOnce wg_attr;
   const int wg_dev = current_device();
   if (wg_attr.need(wg_dev)) {
-    cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(66 * (WG_KC + 1) * sizeof(float)));
+    cudaFuncSetAttribute(k_wgrad_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(WG_ROWS_MAX * (WG_KC + 1) * sizeof(float)));
     wg_attr.mark(wg_dev);
   }
   k_wgrad_partial<<<dim3(wk.n_chunks, wk.n_tasks), 256, slab, s>>>(wk);
-  k_wgrad_final<<<(wk.n_pairs + 255) / 256, 256, 0, s>>>(wk);
+  k_wgrad_final<<<(wk.n_pairs + 31) / 32, 256, 0, s>>>(wk);
   return cudaGetLastError();
 }
 
@@ -750,7 +753,7 @@ static cudaError_t run_wgrad(WgradK& wk, int max_rows, cudaStream_t s) {
 // `one` (may be null: all columns count) weights the bias sums
 static void add_net_tasks(WgradK& wk, int& pair0, int& max_rows, const float* base, size_t K, int IN, int H1, int H2,
                           int OUT, const float* one, float* gp) {
-  auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo) {
+  auto add = [&](const float* A, int n_a, const float* B, int n_b, float* out, int ldo, bool extra) {
     WgradTask& t = wk.task[wk.n_tasks++];
     t.A = A;
     t.B = B;
@@ -759,6 +762,8 @@ static void add_net_tasks(WgradK& wk, int& pair0, int& max_rows, const float* ba
     t.n_b = n_b;
     t.ldo = ldo;
     t.pair0 = pair0;
+    t.E = one;
+    t.has_e = extra ? 1 : 0;
     pair0 += n_a * n_b;
     if (n_a + n_b > max_rows) max_rows = n_a + n_b;
   };
@@ -770,18 +775,14 @@ static void add_net_tasks(WgradK& wk, int& pair0, int& max_rows, const float* ba
   const float* r_g2 = base + (size_t)(IN + 2 * H1 + H2) * K;
   const float* r_go = base + (size_t)(IN + 2 * H1 + 2 * H2) * K;
   const int h1p = up4l(H1), h2p = up4l(H2);
-  float* w0 = gp;
-  float* b0 = w0 + IN * h1p;
-  float* w1 = b0 + h1p;
-  float* b1 = w1 + H1 * h2p;
-  float* w2 = b1 + h2p;  // transposed: [OUT][h2p]
+  float* w0 = gp;                    // w0[IN][h1p] b0[h1p]: the bias row rides behind the weight rows
+  float* w1 = w0 + IN * h1p + h1p;   // w1[H1][h2p] b1[h2p]
+  float* w2 = w1 + H1 * h2p + h2p;   // transposed: [OUT][h2p]
   float* b2 = w2 + OUT * h2p;
-  add(r_in, IN, r_c1, H1, w0, h1p);
-  add(one, 1, r_c1, H1, b0, h1p);
-  add(r_h1, H1, r_g2, H2, w1, h2p);
-  add(one, 1, r_g2, H2, b1, h2p);
-  add(r_go, OUT, r_h2, H2, w2, h2p);
-  add(one, 1, r_go, OUT, b2, 4);
+  add(r_in, IN + 1, r_c1, H1, w0, h1p, true);
+  add(r_h1, H1 + 1, r_g2, H2, w1, h2p, true);
+  add(r_go, OUT, r_h2, H2, w2, h2p, false);
+  add(one, 1, r_go, OUT, b2, 4, false);  // (A = the `one` row itself; nullptr: every column counts)
 }
 
 int sde4_density_reg(const sde4_model_desc* model, const sde4_density_reg_args* a, void* stream) {
@@ -880,6 +881,8 @@ int sde4_density_reg(const sde4_model_desc* model, const sde4_density_reg_args* 
       t.n_b = 1;
       t.ldo = 1;
       t.pair0 = 0;
+      t.E = nullptr;
+      t.has_e = 0;
       pair0 = 1;
       max_rows = 2;
     }

@@ -389,12 +389,19 @@ class NativeRegulariser:
     def __call__(self, nn_params, y, u, key):
         """-> (total, {logged scalars}, {mod: {leaf: numpy gradient}}) for device tensors y[B, Hd+1, n_y], u[B, Hd, n_u]
         and a device key int32[2]."""
+        st = self.launch(nn_params, y, u, key)
+        torch.cuda.current_stream(y.device).synchronize()
+        return self.finish(st)
+
+    def launch(self, nn_params, y, u, key, pk=None):
+        """Queue the kernels and the read-back on the current stream; ``finish`` parses the result after the caller has
+        synchronised the stream."""
         eng = self.engine
         y, u = y.contiguous(), u.contiguous()
         B, Hd = y.shape[0], y.shape[1] - 1
         assert tuple(y.shape) == (B, Hd + 1, eng.n_x) and tuple(u.shape) == (B, Hd, eng.n_u)
         st = self._state(B, Hd, y.device)
-        pk = eng.packed(nn_params)
+        pk = eng.packed(nn_params) if pk is None else pk
         if self.mu_size:
             self._pack_mu(nn_params, st["mu_host"].numpy())
             st["mu"].copy_(st["mu_host"], non_blocking=True)
@@ -424,11 +431,24 @@ class NativeRegulariser:
         stream = torch.cuda.current_stream(y.device)
         L.check(L.load().sde4_density_reg(C.byref(eng.desc), C.byref(a), C.c_void_p(stream.cuda_stream)))
         st["out_host"].copy_(out, non_blocking=True)
-        stream.synchronize()
+        st["keep"] = (y, u, key, pk)  # inputs stay alive until the stream has run
+        return st
+
+    def packed_grad(self, st):
+        """The regulariser's gradient w.r.t. the packed model block (valid after the stream has been synchronised)."""
+        return st["out_host"].numpy()[5:5 + self.engine.param_total]
+
+    def finish(self, st, mu_only=False):
+        """-> (total, logged scalars, gradient tree); ``mu_only``: the tree holds the mu parameters only (the caller adds
+        ``packed_grad`` to its own packed block before unpacking)."""
+        eng = self.engine
+        st.pop("keep", None)
         res = st["out_host"].numpy()
         info = {k: float(res[1 + i]) for i, k in enumerate(_INFO_KEYS)}
-        gtree = self.model.unpack_grads(res[5:5 + eng.param_total], eng.desc)
-        pre = "%s/~construct_diffusion_density_nn/density/~" % self.model.module_name
-        grads = {mod: leaves for mod, leaves in gtree.items() if mod.startswith(pre)}
+        grads = {}
+        if not mu_only:
+            gtree = self.model.unpack_grads(res[5:5 + eng.param_total], eng.desc)
+            pre = "%s/~construct_diffusion_density_nn/density/~" % self.model.module_name
+            grads = {mod: leaves for mod, leaves in gtree.items() if mod.startswith(pre)}
         grads.update(self._unpack_mu(res[5 + eng.param_total:]))
         return float(res[0]), info, grads

@@ -587,27 +587,45 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
                 out[mod][name] = lh[-1] if lh else (default if default is not None else current[mod][name])
         return out
 
+    _pen_cache = {}
+
     def _penalty(_nn_params, want_grad):
         """pen_weights * sum_leaves coeff * ||p - nominal||^2 (nsde.py:1155-1168, 1216-1219): coefficients from
         ``special_parameters_pen`` / ``default_weights``; nominal values = ``default_parameters_val`` everywhere, then
         ``nominal_parameters_val`` ({module: {leaf: value}}, update_same_struct_dict), then ``special_parameters_val``
         matched like the coefficients."""
-        coeffs = _matched(_nn_params, special, default_w)
-        nom = {mod: {name: default_val for name in leaves} for mod, leaves in _nn_params.items()}
-        for mod, sub in nominal_val.items():
-            if mod in nom and isinstance(sub, dict):
-                for name, v in sub.items():
-                    nom[mod][name] = v
-        nom = _matched(_nn_params, special_val, None, nom)
-        tot, grads = 0.0, {}
-        for mod, leaves in _nn_params.items():
-            for name, arr in leaves.items():
-                coeff = coeffs[mod][name]
-                a = np.asarray(arr, np.float64)
-                dlt = a - np.asarray(nom[mod][name], np.float64)
-                tot += float(np.sum(dlt ** 2) * coeff)
-                if want_grad:
-                    grads.setdefault(mod, {})[name] = (2.0 * coeff * pen_w * dlt).astype(np.float32)
+        sig = tuple((mod, tuple(leaves)) for mod, leaves in _nn_params.items())
+        if _pen_cache.get("sig") != sig:  # the two trees depend on the NAMES only
+            coeffs = _matched(_nn_params, special, default_w)
+            nom = {mod: {name: default_val for name in leaves} for mod, leaves in _nn_params.items()}
+            for mod, sub in nominal_val.items():
+                if mod in nom and isinstance(sub, dict):
+                    for name, v in sub.items():
+                        nom[mod][name] = v
+            nom = _matched(_nn_params, special_val, None, nom)
+            _pen_cache.update(sig=sig)
+            # flat float64 views in tree order: one vector operation per call instead of a handful per leaf
+            index, cf, nf, o = [], [], [], 0
+            for mod, leaves in _nn_params.items():
+                for name, arr in leaves.items():
+                    shp = np.shape(arr)
+                    n = int(np.prod(shp)) if len(shp) else 1
+                    index.append((mod, name, shp, o, n))
+                    cf.append(np.full(n, coeffs[mod][name], np.float64))
+                    nf.append(np.broadcast_to(np.asarray(nom[mod][name], np.float64), shp).reshape(-1))
+                    o += n
+            _pen_cache.update(index=index, cf=np.concatenate(cf) if cf else np.zeros(0), nf=np.concatenate(nf) if nf else np.zeros(0))
+        index, cf, nf = _pen_cache["index"], _pen_cache["cf"], _pen_cache["nf"]
+        flat = np.empty(cf.shape[0], np.float64)
+        for mod, name, shp, o, n in index:
+            flat[o:o + n] = np.asarray(_nn_params[mod][name]).reshape(-1)
+        flat -= nf
+        tot = float(np.dot(cf, flat * flat))
+        grads = {}
+        if want_grad:
+            gflat = (2.0 * pen_w * cf * flat).astype(np.float32)
+            for mod, name, shp, o, n in index:
+                grads.setdefault(mod, {})[name] = gflat[o:o + n].reshape(shp)
         return tot, grads
 
     # The distance-aware regulariser runs on the library's own kernels (density_loss.NativeRegulariser ->
@@ -646,6 +664,8 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         src = uu if idx.dim() == 2 else uu[:, None].expand(uu.shape[0], idx.shape[1], *uu.shape[1:])
         return torch.gather(src, idx.dim(), ii).squeeze(idx.dim()).contiguous()
 
+    _stage = {}  # pinned read-back buffer [loss_b | packed gradient]
+
     def value_and_grad(_nn_params, y, u, rng, extra_args=None, want_grad=True):
         if extra_args is not None:
             raise Sde4Error("extra_args must be None")
@@ -662,6 +682,18 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
             k_s2c = _random.split_many(k_bn, 3)[:, :, 1].reshape(-1, 2)  # rng_sample2consider (nsde.py:709)
         if n_consider < horizon:  # nsde.py:753-760: every (b, n) keeps its own random subset of the time indexes
             step_weight = _random.choice_mask_many(k_s2c, horizon, n_consider)
+        on_partial = step_weight is not None and params_model.get("density_on_partial", False)
+        pend = None
+        if dl is not None and native is not None and not on_partial:
+            # distance-aware regulariser at the data points on the library's kernels, on a side stream: the data term's
+            # launches (a few thousand threads) run beside it; both are read back behind ONE synchronisation
+            if "side" not in _stage:
+                _stage["side"] = torch.cuda.Stream(device=y_values.device)
+            side, cur = _stage["side"], torch.cuda.current_stream(y_values.device)
+            pk = engine.packed(_nn_params)  # (uploaded on the main stream, which the side stream then waits for)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                pend = native.launch(_nn_params, as_f32(y), as_f32(u), key, pk=pk)
         if strategy == "random":  # nsde.py:735: every (b, n) draws its own data sub-step per solver step
             ridx = _random.randint_many(k_s2c, horizon, 0, num_steps2data).reshape(B, num_sample, horizon)
             u_bn = _pick(u_values, ridx)  # [B, N, H, n_u]
@@ -676,16 +708,27 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         else:
             loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample,
                                                step_weight=step_weight)
-        loss_data = float(loss_b.mean())
+        nb, npar = loss_b.numel(), gpacked.numel()
+        if _stage.get("n") != (nb, npar):
+            _stage["n"] = (nb, npar)
+            _stage["host"] = torch.zeros(nb + npar, dtype=torch.float32).pin_memory()
+        main = torch.cuda.current_stream(loss_b.device)
+        _stage["host"][:nb].copy_(loss_b, non_blocking=True)
+        _stage["host"][nb:].copy_(gpacked, non_blocking=True)
+        # host work that needs nothing from the device goes in front of the synchronisation
+        w_loss, wgrads = _penalty(_nn_params, want_grad) if pen_w > 0 else (0.0, {})
+        if pend is not None:
+            main.wait_stream(_stage["side"])
+        main.synchronize()
+        hres = _stage["host"].numpy()
+        loss_data = float(hres[:nb].mean(dtype=np.float64))
         total = 0.0
         if loss_params.get("pen_data", 0) > 0:
             total += loss_data * loss_params["pen_data"]
         dinfo, dgrads = {}, {}
-        on_partial = step_weight is not None and params_model.get("density_on_partial", False)
-        if dl is not None and (native is not None or graphed is not None) and not on_partial:
-            # distance-aware regulariser at the data points: the library's kernels, or one CUDA-graph replay of the
-            # torch restatement (density_loss.GraphedRegulariser)
-            dval, dinfo, dgrads_np = (native or graphed)(_nn_params, as_f32(y), as_f32(u), key)
+        if pend is not None or (dl is not None and graphed is not None and not on_partial):
+            # (graphed: one CUDA-graph replay of the torch restatement, density_loss.GraphedRegulariser)
+            dval, dinfo, dgrads_np = native.finish(pend, mu_only=True) if pend is not None else graphed(_nn_params, as_f32(y), as_f32(u), key)
             total += dval
             if want_grad:
                 dgrads = {mod: {k: torch.from_numpy(v) for k, v in leaves.items()} for mod, leaves in dgrads_np.items()}
@@ -704,7 +747,6 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
                 dgrads = {mod: {k: v.grad for k, v in leaves.items() if v.grad is not None} for mod, leaves in tt.items()}
             total += float(dtot.detach())
             dinfo = {k: float(v.detach()) if isinstance(v, torch.Tensor) else float(v) for k, v in dinfo.items()}
-        w_loss, wgrads = _penalty(_nn_params, want_grad) if pen_w > 0 else (0.0, {})
         if pen_w > 0:
             total += pen_w * w_loss
         info = {"totalLoss": total, "gradDensity": 0.0, "lossMuCoeff": 0.0, "densitySCVEX": 0.0, "weights": w_loss,
@@ -712,16 +754,17 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
         info.update(dinfo)
         if not want_grad:
             return total, info, None
-        gtree = model.unpack_grads(gpacked.cpu().numpy(), engine.desc)
         pd = float(loss_params.get("pen_data", 0)) if loss_params.get("pen_data", 0) > 0 else 0.0
+        gblock = pd * hres[nb:]
+        if pend is not None:  # the regulariser's block has the same packed layout: add before the (single) unpacking
+            gblock = gblock + native.packed_grad(pend)
+        gtree = model.unpack_grads(gblock, engine.desc)
         grads = {}
         for mod, leaves in _nn_params.items():
             for name, arr in leaves.items():
-                g = np.zeros_like(np.asarray(arr, np.float32))
+                g = wgrads[mod][name] if (mod in wgrads and name in wgrads[mod]) else np.zeros(np.shape(arr), np.float32)
                 if mod in gtree and name in gtree[mod]:
-                    g = g + pd * gtree[mod][name]
-                if mod in wgrads and name in wgrads[mod]:
-                    g = g + wgrads[mod][name]
+                    g = g + gtree[mod][name]
                 if mod in dgrads and name in dgrads[mod]:
                     g = g + dgrads[mod][name].cpu().numpy()
                 grads.setdefault(mod, {})[name] = g
