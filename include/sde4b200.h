@@ -35,6 +35,9 @@ extern "C" {
 #define SDE4_MAX_NU 8
 #define SDE4_MAX_NOPT 24
 #define SDE4_LANES_WS 64
+/* sde4_rollout_args.lanes = SDE4_LANES_TC: the tensor-core forward rollout (one thread per sample, the [32, 32] hidden
+ * layers as tcgen05 3xTF32 products); picked automatically for >= 2 tiles of 128 samples per SM */
+#define SDE4_LANES_TC 65
 
 typedef enum sde4_status {
   SDE4_OK = 0,

@@ -18,6 +18,7 @@ ACT_NONE, ACT_TANH, ACT_SWISH = 0, 1, 2
 RNG_ORIGINAL, RNG_PARTITIONABLE = 0, 1
 NOISE_NONE, NOISE_THREEFRY, NOISE_GIVEN = 0, 1, 2
 LANES_WS = 64  # sde4_cost_args.lanes: the warp-specialised value + gradient kernel (SDE4_LANES_WS)
+LANES_TC = 65  # sde4_rollout_args.lanes: the tensor-core forward rollout (SDE4_LANES_TC)
 MSD_CONTROL, MSD_GROUND_TRUTH, MSD_SIDE_INFO = 1, 2, 4
 CART_SIDE_INFO = 1
 ROTOR_AERO_DRAG = 1

@@ -51,6 +51,17 @@ struct WsRegistrar {
   explicit WsRegistrar(const WsEntry& e) { ws_table().push_back(e); }
 };
 
+// tensor-core forward rollout (kernels_tc.cuh): one thread per sample, CTA = one 128-sample tile
+struct TcEntry {
+  const char* name;
+  bool (*matches)(const sde4_model_desc&);
+  cudaError_t (*launch_rollout)(const sde4_model_desc&, const RolloutK&, int dev, cudaStream_t);
+};
+std::vector<TcEntry>& tc_table();
+struct TcRegistrar {
+  explicit TcRegistrar(const TcEntry& e) { tc_table().push_back(e); }
+};
+
 // cudaFuncSetAttribute is per device and per function: remember which devices a function has been configured on
 // (bit mask, relaxed atomics: setting the attribute twice is harmless, skipping it is not)
 struct DevOnce {

@@ -33,6 +33,16 @@ static const ArchEntry* find_arch(const sde4_model_desc& d) {
 }
 // first registered variant of the architecture; SDE4_WS_NPART (environment, tuning experiments only) picks another
 // particles-per-CTA variant when one is compiled
+std::vector<TcEntry>& tc_table() {
+  static std::vector<TcEntry> table;
+  return table;
+}
+static const TcEntry* find_tc(const sde4_model_desc& d) {
+  for (const TcEntry& e : tc_table())
+    if (e.matches(d)) return &e;
+  return nullptr;
+}
+
 static const WsEntry* find_ws(const sde4_model_desc& d) {
   static const int want = [] {
     const char* v = getenv("SDE4_WS_NPART");
@@ -246,12 +256,26 @@ static int rollout_impl(const sde4_model_desc* model, const sde4_rollout_args* a
   k.last = so ? so->last : nullptr;
   k.racc = so ? so->racc : nullptr;
   k.reward_kind = so ? so->reward_kind : SDE4_REWARD_NONE;
-  const int lanes = pick_lanes(*e, a->lanes, G, false);
-  if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
-  const long long nthr = G * lanes;
-  const int threads = pick_threads(a->block_threads, nthr);
-  const int blocks = (int)((nthr + threads - 1) / threads);
-  cudaError_t err = e->launch_rollout[ilog2(lanes)](*model, k, blocks, threads, (cudaStream_t)stream);
+  // tensor-core forward rollout (kernels_tc.cuh): on request, or by itself in the throughput regime (at least two
+  // 128-sample tiles per SM; profiles/r2_tcgen05_experiment.md), Euler-Maruyama only
+  const TcEntry* tce = nullptr;
+  if (a->lanes == SDE4_LANES_TC) {
+    tce = a->solver == SDE4_SOLVER_EULER_MARUYAMA ? find_tc(*model) : nullptr;
+    if (!tce) return fail(SDE4_ERR_UNSUPPORTED, "no tensor-core rollout kernel for this call (%s; needs [32, 32] networks, Euler-Maruyama)", e->name);
+  } else if (a->lanes == 0 && a->solver == SDE4_SOLVER_EULER_MARUYAMA && G >= 2ll * 128 * sm_count()) {
+    tce = find_tc(*model);
+  }
+  cudaError_t err;
+  if (tce) {
+    err = tce->launch_rollout(*model, k, current_device(), (cudaStream_t)stream);
+  } else {
+    const int lanes = pick_lanes(*e, a->lanes, G, false);
+    if (lanes < 0) return fail(SDE4_ERR_UNSUPPORTED, "requested lane count has no compiled kernel for %s", e->name);
+    const long long nthr = G * lanes;
+    const int threads = pick_threads(a->block_threads, nthr);
+    const int blocks = (int)((nthr + threads - 1) / threads);
+    err = e->launch_rollout[ilog2(lanes)](*model, k, blocks, threads, (cudaStream_t)stream);
+  }
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "rollout launch (%s): %s", e->name, cudaGetErrorString(err));
   if (so && (so->mean || so->std || so->reward_mean || so->reward_of_mean || so->done_of_mean)) {
     SimReduceK r;
