@@ -47,13 +47,14 @@ SDE4_DEV void mma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t accum
       : "memory");
 }
 SDE4_DEV float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+
 }  // namespace tc
 
 // evaluator context: the FP32 scratch columns plus the tile state of this CTA
 struct ScratchTC : Scratch {
   unsigned char* a_row;  // this thread's 16-byte slot in chunk 0 of A_hi (A_lo: + A_TILE; chunk c: + c * A_LBO)
   uint64_t da_hi, da_lo;  // descriptors of the A tiles
-  uint64_t db0;           // descriptor of B_hi of network slot 0 (slot s: + s * 2 tiles; B_lo: + 1 tile)
+  uint64_t db[3];         // descriptor of B_hi of network slot s (B_lo: + 1 tile); slots without a [32, 32] network: unused
   uint32_t mbar, tmem, phase;
 };
 
@@ -81,6 +82,8 @@ SDE4_DEV void mlp_fwd_tc(const float* W, ScratchTC& sc, const float (&in)[N::IN]
       lo.y = h1 - hi.y;
       lo.z = h2 - hi.z;
       lo.w = h3 - hi.w;
+      if (c == 0) __syncthreads();  // the A tiles double as the FP32 scratch columns of the other networks: every
+                                    // thread is past its last column access before the first row is stored
       *reinterpret_cast<float4*>(sc.a_row + c * A_LBO) = hi;
       *reinterpret_cast<float4*>(sc.a_row + A_TILE + c * A_LBO) = lo;
     }
@@ -90,7 +93,7 @@ SDE4_DEV void mlp_fwd_tc(const float* W, ScratchTC& sc, const float (&in)[N::IN]
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint64_t dbh = sc.db0 + (uint64_t)((slot * 2 * B_TILE) >> 4), dbl = dbh + (uint64_t)(B_TILE >> 4);
+    const uint64_t dbh = sc.db[slot], dbl = dbh + (uint64_t)(B_TILE >> 4);
 #pragma unroll
     for (int ks = 0; ks < TK / 8; ++ks) {  // the start address advances by two K chunks per step
       const uint64_t sa = (uint64_t)((2 * ks * A_LBO) >> 4), sb = (uint64_t)((2 * ks * B_LBO) >> 4);
@@ -162,10 +165,15 @@ struct Ev1TC {
 };
 
 template <class A>
+constexpr int tc_nets() {
+  return (tc_net<typename A::DNet>() ? 1 : 0) + (tc_net<typename A::NetA>() ? 1 : 0) + (tc_net<typename A::NetB>() ? 1 : 0);
+}
+template <class A>
 constexpr int tc_smem_bytes() {
-  // parameter image | FP32 scratch columns (forward: 2 slots) | A_hi, A_lo | B tiles of the three slots | mbarrier, tmem slot
-  return (int)(sizeof(float) * ((size_t)A::smem_floats(1) + Scratch::NSLOTS_FWD * MAXW * tc::TM)) + 128 + 2 * (int)tc::A_TILE +
-         6 * (int)tc::B_TILE + 32;
+  // parameter image | A_hi, A_lo (= the two FP32 scratch slots of the forward evaluator, MAXW x 128 floats each; the
+  // uses never overlap in time, see mlp_fwd_tc) | B_hi, B_lo of every [32, 32] network
+  static_assert(Scratch::NSLOTS_FWD * MAXW * tc::TM * sizeof(float) == 2 * tc::A_TILE, "scratch columns = the two A tiles");
+  return (int)(sizeof(float) * (size_t)A::smem_floats(1)) + 128 + 2 * (int)tc::A_TILE + tc_nets<A>() * 2 * (int)tc::B_TILE;
 }
 
 // weight tiles of one network slot: B[n][k] = w1[k][n] (haiku stores [in][out]), split into TF32 high / low parts
@@ -197,14 +205,14 @@ __global__ void __launch_bounds__(tc::TM) k_rollout_tc(const __grid_constant__ s
   __shared__ uint32_t tmem_slot;
   stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar_params);
   Diffusion<M>::derive(W);
-  unsigned char* tiles = reinterpret_cast<unsigned char*>(
-      ((uintptr_t)(W + A::smem_floats(1) + Scratch::NSLOTS_FWD * MAXW * tc::TM) + 127) & ~(uintptr_t)127);
+  unsigned char* tiles = reinterpret_cast<unsigned char*>(((uintptr_t)(W + A::smem_floats(1)) + 127) & ~(uintptr_t)127);
   unsigned char* a_hi = tiles;
   unsigned char* b0 = tiles + 2 * tc::A_TILE;
   __syncthreads();  // the parameter image is complete
+  constexpr int BS1 = tc_net<typename A::DNet>() ? 1 : 0, BS2 = BS1 + (tc_net<typename A::NetA>() ? 1 : 0);  // compact slots
   tc_build_b<typename A::DNet>(W + A::OFF_DENSITY, b0);
-  tc_build_b<typename A::NetA>(W + A::OFF_NET_A, b0 + 2 * tc::B_TILE);
-  tc_build_b<typename A::NetB>(W + A::OFF_NET_B, b0 + 4 * tc::B_TILE);
+  tc_build_b<typename A::NetA>(W + A::OFF_NET_A, b0 + BS1 * 2 * tc::B_TILE);
+  tc_build_b<typename A::NetB>(W + A::OFF_NET_B, b0 + BS2 * 2 * tc::B_TILE);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(&mbar_mma)));
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -219,12 +227,14 @@ __global__ void __launch_bounds__(tc::TM) k_rollout_tc(const __grid_constant__ s
   asm volatile("tcgen05.fence::after_thread_sync;");
   Tctx<M> tcx;
   tcx.l = 0;
-  tcx.ev.base = W + A::smem_floats(1) + threadIdx.x;
+  tcx.ev.base = reinterpret_cast<float*>(a_hi) + threadIdx.x;  // scratch columns alias the A tiles
   tcx.ev.bs = (int)blockDim.x;
   tcx.ev.a_row = a_hi + (threadIdx.x >> 3) * tc::A_SBO + (threadIdx.x & 7) * 16;
   tcx.ev.da_hi = tc::umma_desc(tc::smem_u32(a_hi), tc::A_LBO, tc::A_SBO);
   tcx.ev.da_lo = tc::umma_desc(tc::smem_u32(a_hi + tc::A_TILE), tc::A_LBO, tc::A_SBO);
-  tcx.ev.db0 = tc::umma_desc(tc::smem_u32(b0), tc::B_LBO, tc::B_SBO);
+  tcx.ev.db[0] = tc::umma_desc(tc::smem_u32(b0), tc::B_LBO, tc::B_SBO);
+  tcx.ev.db[1] = tc::umma_desc(tc::smem_u32(b0 + BS1 * 2 * tc::B_TILE), tc::B_LBO, tc::B_SBO);
+  tcx.ev.db[2] = tc::umma_desc(tc::smem_u32(b0 + BS2 * 2 * tc::B_TILE), tc::B_LBO, tc::B_SBO);
   tcx.ev.mbar = tc::smem_u32(&mbar_mma);
   tcx.ev.tmem = tmem_slot;
   tcx.ev.phase = 0;
