@@ -1,5 +1,7 @@
 """Host-side mirror of the reference interface (no GPU needed): time steps, constraint set-up,
 cost descriptors, parameter packing, argument errors."""
+import os
+
 import numpy as np
 import pytest
 
@@ -163,3 +165,30 @@ def test_weight_penalty_matching_follows_get_penalty_parameters():
             want += coeff * float(np.sum((a - nom) ** 2))
             np.testing.assert_allclose(grads[mod][name], 2.0 * coeff * (a - nom), rtol=1e-6, atol=1e-7)
     assert abs(tot - want) <= 1e-9 * max(1.0, abs(want))
+
+
+def test_gen_inst_emits_a_registration_for_an_edited_yaml(tmp_path):
+    """tools/gen_inst.py: a configuration with edited hidden_layers becomes an Arch<...> alias + registration line of
+    csrc/inst_user.cu (compiled by the Makefile when present); widths above the compiled range are refused."""
+    import subprocess
+    import sys
+    import yaml
+    from sde4mbrl_b200 import configs
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pm = configs.cartpole_model(horizon=10, num_particles=4)
+    pm["diffusion_density_nn"]["density_nn"]["hidden_layers"] = [16, 24]
+    cfg = tmp_path / "cart.yaml"
+    cfg.write_text(yaml.safe_dump({"model": pm}))
+    out = tmp_path / "inst_user.cu"
+    tool = os.path.join(root, "tools", "gen_inst.py")
+    subprocess.run([sys.executable, tool, "cartpole", str(cfg), "--name", "cart_a", "--train", "--out", str(out)], check=True, capture_output=True)
+    subprocess.run([sys.executable, tool, "cartpole", str(cfg), "--name", "cart_b", "--lanes", "8", "--out", str(out)], check=True, capture_output=True)
+    subprocess.run([sys.executable, tool, "cartpole", str(cfg), "--name", "cart_a", "--out", str(out)], check=True, capture_output=True)  # replaces
+    text = out.read_text()
+    assert text.count("// >>> cart_a") == 1 and text.count("// >>> cart_b") == 1
+    assert "Net<3, 16, 24, 1, SWISH>" in text and "SDE4_REGISTER(cart_a, CartpoleModel<User_cart_a>)" in text
+    assert "SDE4_REGISTER_LS(cart_b, CartpoleModel, User_cart_b, 8)" in text
+    pm["diffusion_density_nn"]["density_nn"]["hidden_layers"] = [64, 64]
+    cfg.write_text(yaml.safe_dump({"model": pm}))
+    r = subprocess.run([sys.executable, tool, "cartpole", str(cfg), "--out", str(out)], capture_output=True, text=True)
+    assert r.returncode != 0 and "outside the compiled range" in (r.stderr + r.stdout)
