@@ -54,7 +54,7 @@ SDE4_DEV float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0x
 struct ScratchTC : Scratch {
   unsigned char* a_row;  // this thread's 16-byte slot in chunk 0 of A_hi (A_lo: + A_TILE; chunk c: + c * A_LBO)
   uint64_t da_hi, da_lo;  // descriptors of the A tiles
-  uint64_t db[3];         // descriptor of B_hi of network slot s (B_lo: + 1 tile); slots without a [32, 32] network: unused
+  uint64_t db[3], dbl[3];  // descriptors of B_hi / B_lo of network slot s; slots without a [32, 32] network: unused
   uint32_t mbar, tmem, phase;
 };
 
@@ -93,7 +93,7 @@ SDE4_DEV void mlp_fwd_tc(const float* W, ScratchTC& sc, const float (&in)[N::IN]
   __syncthreads();
   if (threadIdx.x == 0) {
     asm volatile("tcgen05.fence::after_thread_sync;");
-    const uint64_t dbh = sc.db[slot], dbl = dbh + (uint64_t)(B_TILE >> 4);
+    const uint64_t dbh = sc.db[slot], dbl = sc.dbl[slot];
 #pragma unroll
     for (int ks = 0; ks < TK / 8; ++ks) {  // the start address advances by two K chunks per step
       const uint64_t sa = (uint64_t)((2 * ks * A_LBO) >> 4), sb = (uint64_t)((2 * ks * B_LBO) >> 4);
@@ -170,24 +170,33 @@ constexpr int tc_nets() {
 }
 template <class A>
 constexpr int tc_smem_bytes() {
-  // parameter image | A_hi, A_lo (= the two FP32 scratch slots of the forward evaluator, MAXW x 128 floats each; the
-  // uses never overlap in time, see mlp_fwd_tc) | B_hi, B_lo of every [32, 32] network
+  // parameter image (the w1 blocks of the [32, 32] networks hold B_lo) | A_hi, A_lo (= the two FP32 scratch slots of the
+  // forward evaluator, MAXW x 128 floats each; the uses never overlap in time, see mlp_fwd_tc) | B_hi of every [32, 32] network
   static_assert(Scratch::NSLOTS_FWD * MAXW * tc::TM * sizeof(float) == 2 * tc::A_TILE, "scratch columns = the two A tiles");
-  return (int)(sizeof(float) * (size_t)A::smem_floats(1)) + 128 + 2 * (int)tc::A_TILE + tc_nets<A>() * 2 * (int)tc::B_TILE;
+  return (int)(sizeof(float) * (size_t)A::smem_floats(1)) + 128 + 2 * (int)tc::A_TILE + tc_nets<A>() * (int)tc::B_TILE;
 }
 
-// weight tiles of one network slot: B[n][k] = w1[k][n] (haiku stores [in][out]), split into TF32 high / low parts
+// weight tiles of one network slot: B[n][k] = w1[k][n] (haiku stores [in][out]), split into TF32 high / low parts.  B_hi
+// goes to its own tile; B_lo REPLACES w1 in the parameter image (same 4 KB, the FP32 copy is dead in this kernel) -- the
+// 4 KB saved per network are what lets a fifth tile be resident per SM.
 template <class N>
-SDE4_DEV void tc_build_b(const float* Wnet, unsigned char* b_slot) {
+SDE4_DEV void tc_build_b(float* Wnet, unsigned char* b_hi) {
   using namespace tc;
   if constexpr (tc_net<N>()) {
-    for (int i = threadIdx.x; i < TK * TN; i += blockDim.x) {
-      const int k = i / TN, n = i - k * TN;
-      const float v = Wnet[N::OFF_W1 + k * N::H2P + n];
-      const float hi = tf32_hi(v);
+    static_assert(N::H2P == TN && (N::OFF_W1 % 4) == 0, "w1 is a dense, 16-byte aligned 32 x 32 block");
+    constexpr int PER = TK * TN / TM;
+    float v[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) v[q] = Wnet[N::OFF_W1 + threadIdx.x + q * TM];
+    __syncthreads();  // every w1 value is in a register before the block is overwritten
+    unsigned char* b_lo = reinterpret_cast<unsigned char*>(Wnet + N::OFF_W1);
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = threadIdx.x + q * TM, k = i / TN, n = i - k * TN;
+      const float hi = tf32_hi(v[q]);
       const uint32_t off = (uint32_t)(k >> 2) * B_LBO + (uint32_t)(n >> 3) * B_SBO + (uint32_t)(n & 7) * 16 + (uint32_t)(k & 3) * 4;
-      *reinterpret_cast<float*>(b_slot + off) = hi;
-      *reinterpret_cast<float*>(b_slot + B_TILE + off) = v - hi;
+      *reinterpret_cast<float*>(b_hi + off) = hi;
+      *reinterpret_cast<float*>(b_lo + off) = v[q] - hi;
     }
   }
 }
@@ -211,8 +220,8 @@ __global__ void __launch_bounds__(tc::TM) k_rollout_tc(const __grid_constant__ s
   __syncthreads();  // the parameter image is complete
   constexpr int BS1 = tc_net<typename A::DNet>() ? 1 : 0, BS2 = BS1 + (tc_net<typename A::NetA>() ? 1 : 0);  // compact slots
   tc_build_b<typename A::DNet>(W + A::OFF_DENSITY, b0);
-  tc_build_b<typename A::NetA>(W + A::OFF_NET_A, b0 + BS1 * 2 * tc::B_TILE);
-  tc_build_b<typename A::NetB>(W + A::OFF_NET_B, b0 + BS2 * 2 * tc::B_TILE);
+  tc_build_b<typename A::NetA>(W + A::OFF_NET_A, b0 + BS1 * tc::B_TILE);
+  tc_build_b<typename A::NetB>(W + A::OFF_NET_B, b0 + BS2 * tc::B_TILE);
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(tc::smem_u32(&mbar_mma)));
     asm volatile("fence.mbarrier_init.release.cluster;");
@@ -233,8 +242,11 @@ __global__ void __launch_bounds__(tc::TM) k_rollout_tc(const __grid_constant__ s
   tcx.ev.da_hi = tc::umma_desc(tc::smem_u32(a_hi), tc::A_LBO, tc::A_SBO);
   tcx.ev.da_lo = tc::umma_desc(tc::smem_u32(a_hi + tc::A_TILE), tc::A_LBO, tc::A_SBO);
   tcx.ev.db[0] = tc::umma_desc(tc::smem_u32(b0), tc::B_LBO, tc::B_SBO);
-  tcx.ev.db[1] = tc::umma_desc(tc::smem_u32(b0 + BS1 * 2 * tc::B_TILE), tc::B_LBO, tc::B_SBO);
-  tcx.ev.db[2] = tc::umma_desc(tc::smem_u32(b0 + BS2 * 2 * tc::B_TILE), tc::B_LBO, tc::B_SBO);
+  tcx.ev.db[1] = tc::umma_desc(tc::smem_u32(b0 + BS1 * tc::B_TILE), tc::B_LBO, tc::B_SBO);
+  tcx.ev.db[2] = tc::umma_desc(tc::smem_u32(b0 + BS2 * tc::B_TILE), tc::B_LBO, tc::B_SBO);
+  tcx.ev.dbl[0] = tc::umma_desc(tc::smem_u32(W + A::OFF_DENSITY + A::DNet::OFF_W1), tc::B_LBO, tc::B_SBO);
+  tcx.ev.dbl[1] = tc::umma_desc(tc::smem_u32(W + A::OFF_NET_A + A::NetA::OFF_W1), tc::B_LBO, tc::B_SBO);
+  tcx.ev.dbl[2] = tc::umma_desc(tc::smem_u32(W + A::OFF_NET_B + A::NetB::OFF_W1), tc::B_LBO, tc::B_SBO);
   tcx.ev.mbar = tc::smem_u32(&mbar_mma);
   tcx.ev.tmem = tmem_slot;
   tcx.ev.phase = 0;

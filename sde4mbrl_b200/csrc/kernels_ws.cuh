@@ -525,8 +525,10 @@ struct WsCfg {
   // exchange buffer, [value][NPART]
   static constexpr int X_IN6 = 0, X_Z = 6, X_FN = X_Z + NZ, X_MN = X_FN + 3, X_ETA = X_MN + 3, X_DW = X_ETA + NO,
                        FWD_VALS = X_DW + 3 * NX;  // three dw slots in rotation
+  // (density value + input gradient: two slots in alternation, B_DENS + (t & 1) * B_DSLOT -- the DENS role writes the item
+  //  of step t any time before B4(t) while PHY still reads the item of step t + 1, so it stays out of B3)
   static constexpr int B_GF = 0, B_GM = 3, B_GIA = 6, B_GIB = B_GIA + NIA, B_FN = B_GIB + NIB, B_DENS = B_FN + 3,
-                       B_J = B_DENS + 1, B_GU = B_J + NZ, BWD_VALS = B_GU + NU;
+                       B_J = B_DENS + 1, B_DSLOT = 1 + NZ, B_GU = B_DENS + 2 * B_DSLOT, BWD_VALS = B_GU + NU;
   static constexpr int VALS = FWD_VALS > BWD_VALS ? FWD_VALS : BWD_VALS;
   static constexpr int N_MISC = 32;  // noise prior [16] | list of the states that carry noise [16]
   static constexpr int OFF_TILES = A::SMEM_FLOATS;                 // float4-aligned (SMEM_FLOATS is a multiple of 4)
@@ -568,6 +570,9 @@ SDE4_DEV void ws_sync() {
 // B1 / B3 (PHY -> networks hand-over) involve the first three warps only: the AUX role never reads what PHY publishes
 // there, and keeping it out lets it generate noise during BOTH halves of a step.
 SDE4_DEV void ws_sync3() { ws_bar<2, 96>(); }
+// B3 of the backward sweep: PHY and RES only -- the DENS role works one step ahead through two output slots and meets the
+// others at B4 alone, which takes its value + gradient pass (the longest item of a backward step) off the PHY -> RES path.
+SDE4_DEV void ws_sync_pr() { ws_bar<3, 64>(); }
 
 // ---- PHY role: one lane per particle ---------------------------------------------------------------------------------
 template <class Cfg, bool PLAINC>
@@ -689,7 +694,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
       xch[(Cfg::B_GF + k) * NPART + pl] = at.gFb[k];
       xch[(Cfg::B_GM + k) * NPART + pl] = at.gM[k];
     }
-    ws_sync3();  // B3: the network backward passes may start
+    ws_sync_pr();  // B3: the network backward passes may start
     // meanwhile: what does not need them -- features of x_t and the stage cost with its gradient
     Quat t1;
     float vb[3], in6[6];
@@ -712,9 +717,10 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
 #pragma unroll
     for (int k = 0; k < 3; ++k) Fn[k] = xch[(Cfg::B_FN + k) * NPART + pl];
     typename Diffusion<M8>::Tape dtp;
-    dtp.dens = xch[Cfg::B_DENS * NPART + pl];
+    const int so = (t & 1) * Cfg::B_DSLOT;
+    dtp.dens = xch[(Cfg::B_DENS + so) * NPART + pl];
 #pragma unroll
-    for (int k = 0; k < NZ; ++k) dtp.J[k] = xch[(Cfg::B_J + k) * NPART + pl];
+    for (int k = 0; k < NZ; ++k) dtp.J[k] = xch[(Cfg::B_J + so + k) * NPART + pl];
     RS::vjp_post(S, d, x, u, vf, t1, vb, Fn, at, giA, giB, gx, gu);
     Diffusion<M8>::apply(W, d, x, lam, [&](int i) { return nzv[i]; }, dtp, gx, gu);
     // row t of the gradient.  When the CTA's particles share a problem the row is summed over them by the RES role
@@ -908,12 +914,12 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
     float out[4], J[4];
     MD::template value_grad<SDE4_WS_FAST_DENSB>(tD, wD, lane, az, out, J);
     load_inputs(ts > 0 ? ts - 1 : 0);
-    ws_sync3();  // B3 (PHY has read the previous item by now)
+    const int so = (ts & 1) * Cfg::B_DSLOT;  // PHY read this slot's previous item (step ts + 2) before B4(ts + 1)
     if (t == 0) {
-      xch[Cfg::B_DENS * NPART + g] = out[0];
-      xch[Cfg::B_DENS * NPART + g + 8] = out[2];
+      xch[(Cfg::B_DENS + so) * NPART + g] = out[0];
+      xch[(Cfg::B_DENS + so) * NPART + g + 8] = out[2];
     }
-    tile_to_xch<NPART>(xch, Cfg::B_J, NZ, lane, J);
+    tile_to_xch<NPART>(xch, Cfg::B_J + so, NZ, lane, J);
     ws_sync<Cfg::THREADS>();  // B4
   }
   ws_sync<Cfg::THREADS>();  // (PHY's last gradient row for the RES role)
@@ -973,7 +979,7 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
     MA::template fwd<true, SDE4_WS_FAST_RESB>(tA, wA, lane, aA, Fn, dA1, dA2);  // cotangent independent: ahead of the barrier
     MB::template fwd<true, SDE4_WS_FAST_RESB>(tB, wB, lane, aB, Mn_unused, dB1, dB2);
     load_inputs(ts > 0 ? ts - 1 : 0);  // requested one step ahead
-    ws_sync3();  // B3: cotangents of the network outputs are there
+    ws_sync_pr();  // B3: cotangents of the network outputs are there
     float agF[4], agM[4], giA[4], giB[4];
     a_from_xch<NPART>(xch, Cfg::B_GF, 3, lane, [](int k) { return k; }, agF);
     a_from_xch<NPART>(xch, Cfg::B_GM, 3, lane, [](int k) { return k; }, agM);
