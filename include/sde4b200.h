@@ -475,6 +475,7 @@ int sde4_version(void);
  * (lets a foreign-language binding verify its struct layout at load time). */
 void sde4_struct_sizes(int32_t out[4]);
 void sde4_apg_struct_sizes(int32_t out[2]); /* sizeof sde4_apg_params, sde4_apg_state */
+void sde4_aux_struct_sizes(int32_t out[3]); /* sizeof sde4_sim_out, sde4_xgpu_reduce, sde4_density_reg_args */
 
 /* ---- FP32 FMA micro-benchmark (roofline denominator) ---------------
  * Runs `iters` dependent-chain-free FFMA (variant 0) / packed fma.rn.f32x2

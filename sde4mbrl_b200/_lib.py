@@ -143,7 +143,7 @@ EXPORTED_SYMBOLS = (
     "sde4_last_error", "sde4_version", "sde4_struct_sizes", "sde4_apg_struct_sizes", "sde4_fma_peak",
     "sde4_apg_init", "sde4_apg_candidates", "sde4_apg_select", "sde4_apg_pick", "sde4_apg_update",
     "sde4_apg_scratch_floats", "sde4_cost_grad_host", "sde4_cost_grad_host_staging_bytes",
-    "sde4_sim_rollout", "sde4_density_reg", "sde4_density_reg_workspace_bytes", "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_rng_randint_many", "sde4_apg_ls_step", "sde4_apg_spec_points", "sde4_apg_spec_gather",
+    "sde4_sim_rollout", "sde4_aux_struct_sizes", "sde4_density_reg", "sde4_density_reg_workspace_bytes", "sde4_rng_split_many", "sde4_rng_normal_many", "sde4_rng_choice_mask", "sde4_rng_randint_many", "sde4_apg_ls_step", "sde4_apg_spec_points", "sde4_apg_spec_gather",
 )
 
 _lib = None

@@ -174,6 +174,11 @@ void sde4_apg_struct_sizes(int32_t out[2]) {
   out[0] = (int32_t)sizeof(sde4_apg_params);
   out[1] = (int32_t)sizeof(sde4_apg_state);
 }
+void sde4_aux_struct_sizes(int32_t out[3]) {
+  out[0] = (int32_t)sizeof(sde4_sim_out);
+  out[1] = (int32_t)sizeof(sde4_xgpu_reduce);
+  out[2] = (int32_t)sizeof(sde4_density_reg_args);
+}
 const char* sde4_last_error(void) { return g_err; }
 
 const char* sde4_supported_archs(void) {

@@ -30,6 +30,9 @@ def test_struct_sizes_match():
     sizes = (C.c_int32 * 4)()
     lib.sde4_struct_sizes(sizes)
     assert list(sizes) == [C.sizeof(L.ModelDesc), C.sizeof(L.CostDesc), C.sizeof(L.RolloutArgs), C.sizeof(L.CostArgs)]
+    aux = (C.c_int32 * 3)()
+    lib.sde4_aux_struct_sizes(aux)
+    assert list(aux) == [C.sizeof(L.SimOut), C.sizeof(L.XgpuReduce), C.sizeof(L.DensityRegArgs)]
 
 
 def test_supported_archs_and_layout_query():
