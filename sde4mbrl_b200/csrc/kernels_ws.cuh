@@ -114,6 +114,61 @@ struct RotorSplit {
     f[9] = 0.5f * qd.z;
   }
 
+  // The same drift in two parts for the PHY role: drift_post_a is everything that needs no network output (motor thrust and
+  // moments, gyroscopic term, quaternion kinematics) and runs while the networks are evaluated; drift_post_b adds the
+  // residual force / moment after the hand-over barrier.
+  struct DriftPart {
+    float T, Ma[3];  // total thrust; (motor moments - w x (I w)) per axis
+    Quat qd;
+  };
+  SDE4_DEV static void drift_post_a(const float* __restrict__ S, const float (&x)[NX], const float (&u)[NU], DriftPart& p) {
+    const Quat q{x[6], x[7], x[8], x[9]};
+    float T = 0.0f, Mm[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int i = 0; i < NU; ++i) {  // motor_models.py:74-95
+      const float th = thrust(S, u[i]);
+      T = fmaf(Mixer<NU>::m(3, i), th, T);
+      Mm[0] = fmaf(Mixer<NU>::m(0, i) * S[4], th, Mm[0]);
+      Mm[1] = fmaf(Mixer<NU>::m(1, i) * S[5], th, Mm[1]);
+      Mm[2] = fmaf(Mixer<NU>::m(2, i) * S[6], th, Mm[2]);
+    }
+    const float w0 = x[10], w1 = x[11], w2 = x[12];
+    const float Iw0 = S[1] * w0, Iw1 = S[2] * w1, Iw2 = S[3] * w2;
+    p.T = T;
+    p.Ma[0] = Mm[0] - (w1 * Iw2 - w2 * Iw1);
+    p.Ma[1] = Mm[1] - (w2 * Iw0 - w0 * Iw2);
+    p.Ma[2] = Mm[2] - (w0 * Iw1 - w1 * Iw0);
+    p.qd = qmul_qv(q, w0, w1, w2);
+  }
+  SDE4_DEV static void drift_post_b(const float* __restrict__ S, const sde4_model_desc& d, const float (&x)[NX],
+                                    const float (&vb)[3], const float (&Fn)[3], const float (&Mn)[3], const DriftPart& p,
+                                    float (&f)[NX]) {
+    const Quat q{x[6], x[7], x[8], x[9]};
+    float Fb[3] = {Fn[0], Fn[1], Fn[2]};
+    if constexpr (DRAG) {  // :264-277
+      Fb[0] += -S[11] * vb[0];
+      Fb[1] += -S[12] * vb[1];
+      Fb[2] += -S[13] * vb[2] + S[14] * (vb[0] * vb[0] + vb[1] * vb[1]);
+    }
+    Fb[2] += p.T;
+    const Quat t2 = qmul_qv(q, Fb[0], Fb[1], Fb[2]);
+    const Quat r2 = qmul(t2, qconj(q));
+    const float inv_m = fast_rcp(S[0]), g = d.cfloat[0];
+    f[0] = x[3];
+    f[1] = x[4];
+    f[2] = x[5];
+    f[3] = r2.x * inv_m;
+    f[4] = r2.y * inv_m;
+    f[5] = fmaf(r2.z, inv_m, -g);
+    f[10] = (p.Ma[0] + Mn[0]) * fast_rcp(S[1]);
+    f[11] = (p.Ma[1] + Mn[1]) * fast_rcp(S[2]);
+    f[12] = (p.Ma[2] + Mn[2]) * fast_rcp(S[3]);
+    f[6] = 0.5f * p.qd.w;
+    f[7] = 0.5f * p.qd.x;
+    f[8] = 0.5f * p.qd.y;
+    f[9] = 0.5f * p.qd.z;
+  }
+
   // Adjoint, first half: the cotangents of the two network outputs (vf = lambda * dt is the cotangent of f)
   struct AdjTmp {
     Quat t2bar;
@@ -134,11 +189,16 @@ struct RotorSplit {
     a.gFb[1] = gFq.y;
     a.gFb[2] = gFq.z;
   }
-  // second half: everything else, given the input cotangents giA / giB the networks returned for gFb / gM
-  SDE4_DEV static void vjp_post(const float* __restrict__ S, const sde4_model_desc& d, const float (&x)[NX],
-                                const float (&u)[NU], const Scaled<NX>& vf, const Quat& t1, const float (&vb)[3],
-                                const float (&Fn)[3], const AdjTmp& a, const float (&giA)[NIA], const float (&giB)[NIB],
-                                float (&gx)[NX], float (&gu)[NU]) {
+  // second half, in two parts.  vjp_post_a: what needs NO network result (rigid-body terms, quaternion kinematics, the
+  // motor polynomial) -- the PHY role runs it while the residual networks' backward passes are in flight, so that only
+  // vjp_post_b (everything fed by the networks' input cotangents giA / giB and the residual force Fn) is left on the
+  // serial path after the hand-over barrier.
+  struct PostPart {
+    Quat gq;
+    float gw[3];
+  };
+  SDE4_DEV static void vjp_post_a(const float* __restrict__ S, const float (&x)[NX], const float (&u)[NU],
+                                  const Scaled<NX>& vf, const AdjTmp& a, PostPart& pp, float (&gx)[NX], float (&gu)[NU]) {
     const Quat q{x[6], x[7], x[8], x[9]};
     const Quat qc = qconj(q);
     const float I0 = S[1], I1 = S[2], I2 = S[3];
@@ -167,6 +227,30 @@ struct RotorSplit {
       gw[1] += gOm.y;
       gw[2] += gOm.z;
     }
+    {  // motors
+      const float gT = a.gFb[2];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        float gth = Mixer<NU>::m(3, i) * gT;
+        gth = fmaf(Mixer<NU>::m(0, i) * S[4], a.gM[0], gth);
+        gth = fmaf(Mixer<NU>::m(1, i) * S[5], a.gM[1], gth);
+        gth = fmaf(Mixer<NU>::m(2, i) * S[6], a.gM[2], gth);
+        gu[i] = fmaf(gth, thrust_du(S, u[i]), gu[i]);
+      }
+    }
+    pp.gq = gq;
+    pp.gw[0] = gw[0];
+    pp.gw[1] = gw[1];
+    pp.gw[2] = gw[2];
+  }
+  SDE4_DEV static void vjp_post_b(const float* __restrict__ S, const sde4_model_desc& d, const float (&x)[NX],
+                                  const float (&u)[NU], const Quat& t1, const float (&vb)[3], const float (&Fn)[3],
+                                  const AdjTmp& a, const float (&giA)[NIA], const float (&giB)[NIB], const PostPart& pp,
+                                  float (&gx)[NX]) {
+    const Quat q{x[6], x[7], x[8], x[9]};
+    const Quat qc = qconj(q);
+    Quat gq = pp.gq;
+    float gw[3] = {pp.gw[0], pp.gw[1], pp.gw[2]};
     float gvb[3] = {0.0f, 0.0f, 0.0f};
     float gin6[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
     if constexpr (HAS_F) {
@@ -184,17 +268,6 @@ struct RotorSplit {
       const Quat t2 = qmul_qv(q, Fb[0], Fb[1], Fb[2]);
       qacc(gq, qconj(qmul_qv(qconj(t2), a.R2[0], a.R2[1], a.R2[2])));  // qcbar = conj(t2) (x) R2
       qacc(gq, qmul_qv(a.t2bar, -Fb[0], -Fb[1], -Fb[2]));               // qbar += t2bar (x) conj(Fq)
-    }
-    {  // motors
-      const float gT = a.gFb[2];
-#pragma unroll
-      for (int i = 0; i < NU; ++i) {
-        float gth = Mixer<NU>::m(3, i) * gT;
-        gth = fmaf(Mixer<NU>::m(0, i) * S[4], a.gM[0], gth);
-        gth = fmaf(Mixer<NU>::m(1, i) * S[5], a.gM[1], gth);
-        gth = fmaf(Mixer<NU>::m(2, i) * S[6], a.gM[2], gth);
-        gu[i] = fmaf(gth, thrust_du(S, u[i]), gu[i]);
-      }
     }
     if constexpr (HAS_M) {
 #pragma unroll
@@ -613,6 +686,8 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
 #pragma unroll
       for (int k = 0; k < 6; ++k) ft[(size_t)k * G] = in6[k];
     }
+    typename RS::DriftPart dp;
+    RS::drift_post_a(S, x, u, dp);  // the network-independent part of the drift, while the networks run
     ws_sync<Cfg::THREADS>();  // B2: network outputs, eta and dw_t are there
     float Fn[3], Mn[3], f[NX];
 #pragma unroll
@@ -620,7 +695,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
       Fn[k] = xch[(Cfg::X_FN + k) * NPART + pl];
       Mn[k] = xch[(Cfg::X_MN + k) * NPART + pl];
     }
-    RS::drift_post(S, d, x, u, vb, Fn, Mn, f);
+    RS::drift_post_b(S, d, x, vb, Fn, Mn, dp, f);
     // sigma o dw: sigma_i = prior_i * eta_k(i), eta = 1 outside the noise-output mask (nsde.py:363,449)
     const float* dwb = xch + (Cfg::X_DW + (t % 3) * NX) * NPART + pl;
 #pragma unroll
@@ -708,6 +783,8 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
       cost = fmaf(wt, ct, cost);
       if (a.write_stage_cost && active) a.xbuf[((size_t)t * a.x_rows + NX) * G + g] = ct;
     }
+    typename RS::PostPart pp;
+    RS::vjp_post_a(S, x, u, vf, at, pp, gx, gu);  // the network-independent half of the drift adjoint
     ws_sync<Cfg::THREADS>();  // B4: input cotangents, residual force, density value + gradient are there
     float giA[Cfg::NIA], giB[Cfg::NIB], Fn[3];
 #pragma unroll
@@ -721,7 +798,7 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
     dtp.dens = xch[(Cfg::B_DENS + so) * NPART + pl];
 #pragma unroll
     for (int k = 0; k < NZ; ++k) dtp.J[k] = xch[(Cfg::B_J + so + k) * NPART + pl];
-    RS::vjp_post(S, d, x, u, vf, t1, vb, Fn, at, giA, giB, gx, gu);
+    RS::vjp_post_b(S, d, x, u, t1, vb, Fn, at, giA, giB, pp, gx);
     Diffusion<M8>::apply(W, d, x, lam, [&](int i) { return nzv[i]; }, dtp, gx, gu);
     // row t of the gradient.  When the CTA's particles share a problem the row is summed over them by the RES role
     // (30 dependent shuffle / add pairs here were half of this role's backward sweep); otherwise one partial per
