@@ -25,19 +25,29 @@ for _ in range(3):
     lib.sde4_debug_ws_trace(out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
 print("events per role", cnt)
 names = ["PHY", "DENS", "RES", "AUX"]
-nb = int(cnt[:3].min())
-ev = out.reshape(4, 512, 2)[:3, :nb]
-arr, dep = ev[:, :, 0], ev[:, :, 1]
-rel = dep.max(axis=0)  # release time of each barrier (B1 / B3: three warps; B2 / B4: all four)
-gaps = np.diff(rel)
-fw = gaps[:2 * H - 1]; bw = gaps[2 * H:2 * H + 2 * H - 1]
-print("forward: mean cycles B1->B2 %.0f, B2->B1 %.0f ; total fwd %.0f" % (fw[0::2].mean(), fw[1::2].mean(), rel[2 * H - 1] - rel[0]))
-print("backward: mean cycles B3->B4 %.0f, B4->B3 %.0f ; total bwd %.0f" % (bw[0::2].mean(), bw[1::2].mean(), rel[4 * H - 1] - rel[2 * H]))
-last = arr.argmax(axis=0)
-for name, sl in (("fwd B1", slice(0, 2 * H, 2)), ("fwd B2", slice(1, 2 * H, 2)), ("bwd B3", slice(2 * H, 4 * H, 2)), ("bwd B4", slice(2 * H + 1, 4 * H, 2))):
-    l = last[sl]
-    wait = (rel[sl][None, :] - arr[:, sl]).mean(axis=1)
-    print(name, "last arriver", {names[r]: int((l == r).sum()) for r in range(3)}, "mean wait", {names[r]: int(wait[r]) for r in range(3)})
-# AUX: barriers B2 (H of them) then B4 (H) + final
-aux = out.reshape(4, 512, 2)[3, :cnt[3]]
-print("AUX mean wait at its barriers: fwd %.0f bwd %.0f" % ((aux[:H, 1] - aux[:H, 0]).mean(), (aux[H:2 * H, 1] - aux[H:2 * H, 0]).mean()))
+ev = out.reshape(4, 512, 2)
+# PHY and RES meet at every barrier (B1, B2 per forward step; B3, B4 per backward step); DENS joins B1, B2 and, in the
+# backward sweep, B4 only (it works one step ahead through two output slots); AUX joins B2 / B4
+pr = ev[[0, 2], :4 * H]
+arr, dep = pr[:, :, 0], pr[:, :, 1]
+dens_f = ev[1, :2 * H]
+dens_b = ev[1, 2 * H:3 * H]           # its k-th backward event is B4 of backward step k
+rel = dep.max(axis=0)
+relf = np.maximum(rel[:2 * H], dens_f[:, 1])
+gaps = np.diff(relf)
+print("forward: mean cycles B1->B2 %.0f, B2->B1 %.0f ; total fwd %.0f" % (gaps[0::2].mean(), gaps[1::2].mean(), relf[-1] - relf[0]))
+relb = rel[2 * H:].copy()
+relb[1::2] = np.maximum(relb[1::2], dens_b[:, 1])
+gb = np.diff(relb)
+print("backward: mean cycles B3->B4 %.0f, B4->B3 %.0f ; total bwd %.0f" % (gb[0::2].mean(), gb[1::2].mean(), relb[-1] - relb[0]))
+for name, sl in (("fwd B1", slice(0, 2 * H, 2)), ("fwd B2", slice(1, 2 * H, 2))):
+    a3 = np.stack([arr[0, sl], dens_f[sl, 0], arr[1, sl]])
+    last = a3.argmax(axis=0)
+    wait = (relf[sl][None, :] - a3).mean(axis=1)
+    print(name, "last arriver", {n: int((last == r).sum()) for r, n in enumerate(["PHY", "DENS", "RES"])}, "mean wait", {n: int(wait[r]) for r, n in enumerate(["PHY", "DENS", "RES"])})
+b3 = arr[:, 2 * H::2]
+print("bwd B3 (PHY, RES)", "last arriver", {n: int((b3.argmax(axis=0) == r).sum()) for r, n in enumerate(["PHY", "RES"])},
+      "mean wait", {n: int((relb[0::2][None, :] - b3).mean(axis=1)[r]) for r, n in enumerate(["PHY", "RES"])})
+a4 = np.stack([arr[0, 2 * H + 1::2], dens_b[:, 0], arr[1, 2 * H + 1::2]])
+print("bwd B4", "last arriver", {n: int((a4.argmax(axis=0) == r).sum()) for r, n in enumerate(["PHY", "DENS", "RES"])},
+      "mean wait", {n: int((relb[1::2][None, :] - a4).mean(axis=1)[r]) for r, n in enumerate(["PHY", "DENS", "RES"])})
