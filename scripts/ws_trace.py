@@ -51,3 +51,6 @@ print("bwd B3 (PHY, RES)", "last arriver", {n: int((b3.argmax(axis=0) == r).sum(
 a4 = np.stack([arr[0, 2 * H + 1::2], dens_b[:, 0], arr[1, 2 * H + 1::2]])
 print("bwd B4", "last arriver", {n: int((a4.argmax(axis=0) == r).sum()) for r, n in enumerate(["PHY", "DENS", "RES"])},
       "mean wait", {n: int((relb[1::2][None, :] - a4).mean(axis=1)[r]) for r, n in enumerate(["PHY", "DENS", "RES"])})
+aux_f = ev[3, :H]                      # AUX: B2 of every forward step
+print("fwd B2 AUX mean wait %d (its noise generation for the next step takes the rest of the %d-cycle step)"
+      % (int((relf[1::2] - aux_f[:, 0]).mean()), int(np.diff(relf[1::2]).mean())))

@@ -647,13 +647,47 @@ SDE4_DEV void ws_sync3() { ws_bar<2, 96>(); }
 // others at B4 alone, which takes its value + gradient pass (the longest item of a backward step) off the PHY -> RES path.
 SDE4_DEV void ws_sync_pr() { ws_bar<3, 64>(); }
 
+// A operand of a network input read from the exchange buffer: value (row p, k) at xch[(base + idx(k)) * NPART + p]
+template <int NPART, class IdxFn>
+SDE4_DEV void a_from_xch(const float* xch, int base, int nk, int lane, IdxFn idx, float (&a)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  a[0] = t < nk ? xch[(base + idx(t)) * NPART + g] : 0.0f;
+  a[1] = t < nk ? xch[(base + idx(t)) * NPART + g + 8] : 0.0f;
+  a[2] = t + 4 < nk ? xch[(base + idx(t + 4)) * NPART + g] : 0.0f;
+  a[3] = t + 4 < nk ? xch[(base + idx(t + 4)) * NPART + g + 8] : 0.0f;
+}
+// k-th set bit of a compile-time mask for a run-time k (k < popc(MASK) <= 8)
+template <uint32_t MASK>
+SDE4_DEV int nth_bit_rt(int k) {
+  int r = 0;
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    if (q < popc(MASK) && k == q) r = nth_bit(MASK, q < popc(MASK) ? q : 0);
+  return r;
+}
+// publish columns 2t, 2t+1 (< n) of rows g, g+8 of an output tile
+template <int NPART>
+SDE4_DEV void tile_to_xch(float* xch, int base, int n, int lane, const float (&c)[4]) {
+  const int g = lane >> 2, t = lane & 3;
+  if (2 * t < n) {
+    xch[(base + 2 * t) * NPART + g] = c[0];
+    xch[(base + 2 * t) * NPART + g + 8] = c[2];
+  }
+  if (2 * t + 1 < n) {
+    xch[(base + 2 * t + 1) * NPART + g] = c[1];
+    xch[(base + 2 * t + 1) * NPART + g + 8] = c[3];
+  }
+}
+
 // ---- PHY role: one lane per particle ---------------------------------------------------------------------------------
 template <class Cfg, bool PLAINC>
-SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, const sde4_cost_desc& cd,
+SDE4_DEV void ws_role_phy(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const sde4_cost_desc& cd,
                           const sde4_cost_desc& td, const CostK& a, float* ftape, int pl, int g, int p, int pd, bool active) {
   using A = typename Cfg::A;
   using RS = typename Cfg::RS;
   using M8 = typename Cfg::M8;
+  using MB = typename Cfg::MB;
+  using NetB = typename A::NetB;
   constexpr int NX = Cfg::NX, NU = Cfg::NU, NPART = Cfg::NPART, NZ = Cfg::NZ;
   const float* __restrict__ S = W + A::OFF_SCALARS;
   const unsigned G = (unsigned)a.G;
@@ -688,6 +722,16 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
     }
     typename RS::DriftPart dp;
     RS::drift_post_a(S, x, u, dp);  // the network-independent part of the drift, while the networks run
+    if constexpr (NetB::PRESENT) {
+      // forward sweep only: this warp would idle ~1 500 cycles here while the RES role evaluates its two networks back to
+      // back (the longest item of a forward step) -- it evaluates the residual-moment network itself, all 32 lanes
+      const int lane = threadIdx.x & 31;
+      float aB[4], Mn4[4];
+      float dB1[MB::NT1][4], dB2[MB::NT2][4];
+      a_from_xch<NPART>(xch, Cfg::X_IN6, NetB::IN, lane, [](int k) { return nth_bit_rt<A::B_MASK>(k); }, aB);
+      MB::template fwd<false, SDE4_WS_FAST_FWD>(tiles + Cfg::TILE_B * 32, W + A::OFF_NET_B, lane, aB, Mn4, dB1, dB2);
+      tile_to_xch<NPART>(xch, Cfg::X_MN, 3, lane, Mn4);
+    }
     ws_sync<Cfg::THREADS>();  // B2: network outputs, eta and dw_t are there
     float Fn[3], Mn[3], f[NX];
 #pragma unroll
@@ -825,38 +869,6 @@ SDE4_DEV void ws_role_phy(const float* W, float* xch, const sde4_model_desc& d, 
     float cv = active ? cost : 0.0f;
     if (a.warp_reduce) cv = warp_sum(cv);
     if (writer) a.cpart[pw] = cv;
-  }
-}
-
-// A operand of a network input read from the exchange buffer: value (row p, k) at xch[(base + idx(k)) * NPART + p]
-template <int NPART, class IdxFn>
-SDE4_DEV void a_from_xch(const float* xch, int base, int nk, int lane, IdxFn idx, float (&a)[4]) {
-  const int g = lane >> 2, t = lane & 3;
-  a[0] = t < nk ? xch[(base + idx(t)) * NPART + g] : 0.0f;
-  a[1] = t < nk ? xch[(base + idx(t)) * NPART + g + 8] : 0.0f;
-  a[2] = t + 4 < nk ? xch[(base + idx(t + 4)) * NPART + g] : 0.0f;
-  a[3] = t + 4 < nk ? xch[(base + idx(t + 4)) * NPART + g + 8] : 0.0f;
-}
-// k-th set bit of a compile-time mask for a run-time k (k < popc(MASK) <= 8)
-template <uint32_t MASK>
-SDE4_DEV int nth_bit_rt(int k) {
-  int r = 0;
-#pragma unroll
-  for (int q = 0; q < 8; ++q)
-    if (q < popc(MASK) && k == q) r = nth_bit(MASK, q < popc(MASK) ? q : 0);
-  return r;
-}
-// publish columns 2t, 2t+1 (< n) of rows g, g+8 of an output tile
-template <int NPART>
-SDE4_DEV void tile_to_xch(float* xch, int base, int n, int lane, const float (&c)[4]) {
-  const int g = lane >> 2, t = lane & 3;
-  if (2 * t < n) {
-    xch[(base + 2 * t) * NPART + g] = c[0];
-    xch[(base + 2 * t) * NPART + g + 8] = c[2];
-  }
-  if (2 * t + 1 < n) {
-    xch[(base + 2 * t + 1) * NPART + g] = c[1];
-    xch[(base + 2 * t + 1) * NPART + g + 8] = c[3];
   }
 }
 
@@ -1024,14 +1036,11 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
   // ---------------- forward sweep ----------------
   for (int ts = 0; ts < H; ++ts) {
     ws_sync3();  // B1
-    float aA[4], aB[4], Fn[4], Mn[4];
+    float aA[4], Fn[4];  // (the residual-moment network of the forward sweep runs on the PHY warp, see ws_role_phy)
     a_from_xch<NPART>(xch, Cfg::X_IN6, NetA::IN, lane, idxA, aA);
-    a_from_xch<NPART>(xch, Cfg::X_IN6, NetB::IN, lane, idxB, aB);
-    float dA1[MA::NT1][4], dA2[MA::NT2][4], dB1[MB::NT1][4], dB2[MB::NT2][4];
-    MA::template fwd<false, SDE4_WS_FAST_FWD>(tA, wA, lane, aA, Fn, dA1, dA2);
-    MB::template fwd<false, SDE4_WS_FAST_FWD>(tB, wB, lane, aB, Mn, dB1, dB2);
+    float dA1f[MA::NT1][4], dA2f[MA::NT2][4];
+    MA::template fwd<false, SDE4_WS_FAST_FWD>(tA, wA, lane, aA, Fn, dA1f, dA2f);
     tile_to_xch<NPART>(xch, Cfg::X_FN, 3, lane, Fn);
-    tile_to_xch<NPART>(xch, Cfg::X_MN, 3, lane, Mn);
     ws_sync<Cfg::THREADS>();  // B2
   }
   // ---------------- backward sweep ----------------
@@ -1150,7 +1159,7 @@ __global__ void __launch_bounds__(128, 3) k_cost_ws(const __grid_constant__ sde4
     const int on = __ldg(a.mask + p) != 0;
     if (!__syncthreads_or(on)) return;
   }
-  if (warp == 0) ws_role_phy<Cfg, PLAINC>(W, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
+  if (warp == 0) ws_role_phy<Cfg, PLAINC>(W, tiles, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
   else if (warp == 1) ws_role_dens<Cfg>(W, tiles, xch, d, a, g0, a.G - 1);
   else if (warp == 2) ws_role_res<Cfg>(W, tiles, xch, d, a, ftape, g0, a.G - 1);
   else ws_role_aux<Cfg>(xch, d, a, g0, in_range, n, pd);
