@@ -703,6 +703,7 @@ SDE4_DEV void ws_role_phy(const float* W, const float4* tiles, float* xch, const
     for (int i = 0; i < NX; ++i) a.xbuf[(size_t)i * G + g] = x[i];
   }
   // ---------------- forward sweep ----------------
+  ws_sync<Cfg::THREADS>();  // B0: dw_0 is there
   for (int t = 0; t < H; ++t) {
     const float dt = __ldg(a.dt + t);
 #pragma unroll
@@ -732,6 +733,29 @@ SDE4_DEV void ws_role_phy(const float* W, const float4* tiles, float* xch, const
       MB::template fwd<false, SDE4_WS_FAST_FWD>(tiles + Cfg::TILE_B * 32, W + A::OFF_NET_B, lane, aB, Mn4, dB1, dB2);
       tile_to_xch<NPART>(xch, Cfg::X_MN, 3, lane, Mn4);
     }
+    // Positions and quaternion: their drift (v, 0.5 q (x) [0, w]) needs no network output and, unless the noise-output
+    // mask says otherwise, no eta; dw_t was generated a step ahead.  Their Euler-Maruyama update, the projection and
+    // their checkpoint rows are done here, in front of the hand-over barrier (same operations, same order: bitwise equal).
+    constexpr uint32_t KIN_MASK = 0x3C7u;  // states 0-2, 6-9
+    constexpr bool EARLY = (A::NOUT_MASK & KIN_MASK) == 0;
+    const float* dwb = xch + (Cfg::X_DW + (t % 3) * NX) * NPART + pl;
+    float xe[NX], aux = 0.0f;
+    float* ckp = a.xbuf + (size_t)(t + 1) * a.x_rows * G + g;
+    if constexpr (EARLY) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xe[k] = fmaf(x[3 + k], dt, x[k]) + d.noise_prior[k] * dwb[k * NPART];
+      xe[6] = fmaf(0.5f * dp.qd.w, dt, x[6]) + d.noise_prior[6] * dwb[6 * NPART];
+      xe[7] = fmaf(0.5f * dp.qd.x, dt, x[7]) + d.noise_prior[7] * dwb[7 * NPART];
+      xe[8] = fmaf(0.5f * dp.qd.y, dt, x[8]) + d.noise_prior[8] * dwb[8 * NPART];
+      xe[9] = fmaf(0.5f * dp.qd.z, dt, x[9]) + d.noise_prior[9] * dwb[9 * NPART];
+      M8::project(xe, aux);  // touches the quaternion only
+      if (active) {
+        a.auxbuf[(size_t)t * G + g] = aux;
+#pragma unroll
+        for (int i = 0; i < NX; ++i)
+          if ((KIN_MASK >> i) & 1u) ckp[(size_t)i * G] = xe[i];
+      }
+    }
     ws_sync<Cfg::THREADS>();  // B2: network outputs, eta and dw_t are there
     float Fn[3], Mn[3], f[NX];
 #pragma unroll
@@ -741,20 +765,22 @@ SDE4_DEV void ws_role_phy(const float* W, const float4* tiles, float* xch, const
     }
     RS::drift_post_b(S, d, x, vb, Fn, Mn, dp, f);
     // sigma o dw: sigma_i = prior_i * eta_k(i), eta = 1 outside the noise-output mask (nsde.py:363,449)
-    const float* dwb = xch + (Cfg::X_DW + (t % 3) * NX) * NPART + pl;
 #pragma unroll
     for (int i = 0; i < NX; ++i) {
-      float s = d.noise_prior[i];
-      if ((A::NOUT_MASK >> i) & 1u) s *= xch[(Cfg::X_ETA + popc(A::NOUT_MASK & ((1u << i) - 1u))) * NPART + pl];
-      x[i] = fmaf(f[i], dt, x[i]) + s * dwb[i * NPART];
+      if (EARLY && ((KIN_MASK >> i) & 1u)) {
+        x[i] = xe[i];
+      } else {
+        float s = d.noise_prior[i];
+        if ((A::NOUT_MASK >> i) & 1u) s *= xch[(Cfg::X_ETA + popc(A::NOUT_MASK & ((1u << i) - 1u))) * NPART + pl];
+        x[i] = fmaf(f[i], dt, x[i]) + s * dwb[i * NPART];
+      }
     }
-    float aux;
-    M8::project(x, aux);
+    if constexpr (!EARLY) M8::project(x, aux);
     if (active) {
-      a.auxbuf[(size_t)t * G + g] = aux;
-      float* out = a.xbuf + (size_t)(t + 1) * a.x_rows * G + g;
+      if (!EARLY) a.auxbuf[(size_t)t * G + g] = aux;
 #pragma unroll
-      for (int i = 0; i < NX; ++i) out[(size_t)i * G] = x[i];
+      for (int i = 0; i < NX; ++i)
+        if (!(EARLY && ((KIN_MASK >> i) & 1u))) ckp[(size_t)i * G] = x[i];
     }
   }
 
@@ -963,6 +989,7 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
   const float4* tD = tiles + Cfg::TILE_D * 32;
   auto ident = [](int k) { return k; };
   // ---------------- forward sweep ----------------
+  ws_sync<Cfg::THREADS>();  // B0
   for (int ts = 0; ts < H; ++ts) {
     ws_sync3();  // B1
     float az[4], out[4];
@@ -1034,6 +1061,7 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
   auto idxA = [](int k) { return nth_bit_rt<A::A_MASK>(k); };
   auto idxB = [](int k) { return nth_bit_rt<A::B_MASK>(k); };
   // ---------------- forward sweep ----------------
+  ws_sync<Cfg::THREADS>();  // B0
   for (int ts = 0; ts < H; ++ts) {
     ws_sync3();  // B1
     float aA[4], Fn[4];  // (the residual-moment network of the forward sweep runs on the PHY warp, see ws_role_phy)
@@ -1088,6 +1116,7 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
   const int lane = threadIdx.x & 31;
   WsNoise<Cfg, 2> noise(xch, d, a, g0, lane_active, n, pd);
   noise.gen(0);
+  ws_sync<Cfg::THREADS>();  // B0: dw_0 is there (PHY reads dw_t in front of B2 of step t)
   for (int ts = 0; ts < H; ++ts) {
     if (ts + 1 < H) noise.gen(ts + 1);  // slot (ts + 1) % 3: PHY reads it after B2 of the next step
     ws_sync<Cfg::THREADS>();  // B2
