@@ -1158,6 +1158,7 @@ __global__ void __launch_bounds__(128, 3) k_cost_ws(const __grid_constant__ sde4
   constexpr int NPART = Cfg::NPART;
   extern __shared__ __align__(16) float W[];
   __shared__ __align__(8) uint64_t mbar;
+  asm volatile("griddepcontrol.launch_dependents;");  // the reduction kernel behind this launch may take its place now
   stage_params_bulk(W, a.params, A::PARAM_TOTAL * sizeof(float), &mbar);
   Diffusion<typename Cfg::M8>::derive(W);
   float4* tiles = reinterpret_cast<float4*>(W + Cfg::OFF_TILES);

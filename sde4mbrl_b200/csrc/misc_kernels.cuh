@@ -80,6 +80,10 @@ SDE4_DEV void xgpu_ticket(const XgpuK& x) {
 }
 
 __global__ void k_reduce(const __grid_constant__ ReduceK a) {
+  // programmatic dependent launch: when launched with the serialization attribute behind a kernel that calls
+  // griddepcontrol.launch_dependents (k_cost_ws), this grid is already resident when the cost kernel's last CTA retires
+  // and only waits here for its memory to be visible; a no-op for ordinary launches
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   k_reduce_body(a);
   xgpu_ticket(a.x);
 }

@@ -645,7 +645,24 @@ static int cost_grad_impl(const sde4_model_desc* model, const sde4_cost_args* a,
   const long long items = (long long)(r.grad ? a->H * r.n_opt + 1 : 1) * a->P;
   r.lpi = (r.NP >= 16 && items * 32 <= (1ll << 24)) ? 32 : 1;  // few problems, many partials: a warp per item
   const int rthreads = 128;
-  k_reduce<<<(int)((items * r.lpi + rthreads - 1) / rthreads), rthreads, 0, s>>>(r);
+  {
+    // behind the warp-specialised cost kernel (which releases its dependents at its start) K3 is launched as a
+    // programmatic dependent: its CTAs are in place before K2 retires (not while the stream is being captured)
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    const bool pdl = wse != nullptr && cudaStreamIsCapturing(s, &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((items * r.lpi + rthreads - 1) / rthreads));
+    cfg.blockDim = dim3(rthreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    err = cudaLaunchKernelEx(&cfg, k_reduce, r);
+    if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(err));
+  }
   err = cudaGetLastError();
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "reduce launch: %s", cudaGetErrorString(err));
   if (lo.enabled) {
