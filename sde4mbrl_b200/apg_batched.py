@@ -69,7 +69,9 @@ class BatchedAPG:
         self.cand, self.svals, self.cand_cost = f(H, n, K * P), f(K, P), f(K * P)
         self.xv, self.xv_cost = f(H, n, 2 * P), f(2 * P)
         if self.merge_xv_grad is None:
-            self.merge_xv_grad = 2 * P * self.N <= 8192  # scripts/apg_modes.py: better up to 8 k samples, worse from 32 k
+            # scripts/apg_modes.py / apg_modes2.py: better up to 4 k samples (3.9 vs 4.7 ms at 2048 x 1), worse from 8 k
+            # (6.4 vs 5.9 ms at 4096 x 1) and clearly worse from 32 k
+            self.merge_xv_grad = 2 * P * self.N < 8192
         if self.progressive_ls is None:
             # worth it when the launches are throughput bound and every warp belongs to one problem
             # (scripts/apg_modes.py: better from 16 k samples per candidate on)

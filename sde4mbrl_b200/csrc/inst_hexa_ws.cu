@@ -16,14 +16,24 @@ cudaError_t launch_cost_ws_t(const sde4_model_desc& d, const sde4_cost_desc& cd,
   const size_t sm = Cfg::smem_bytes();
   static DevOnce once;
   if (once.need(dev)) {
-    cudaFuncSetAttribute(k_cost_ws<A, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    cudaFuncSetAttribute(k_cost_ws<A, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     once.mark(dev);
   }
   const int blocks = (a.G + Cfg::NPART - 1) / Cfg::NPART;
   const bool plain = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
-  if (plain) k_cost_ws<A, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
-  else k_cost_ws<A, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+  int sms = 148;
+  if (dev < 0 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const bool phymb = blocks <= 2 * sms;  // latency regime (see k_cost_ws)
+  if (plain) {
+    if (phymb) k_cost_ws<A, true, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+    else k_cost_ws<A, true, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+  } else {
+    if (phymb) k_cost_ws<A, false, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+    else k_cost_ws<A, false, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+  }
   return cudaGetLastError();
 }
 

@@ -680,7 +680,7 @@ SDE4_DEV void tile_to_xch(float* xch, int base, int n, int lane, const float (&c
 }
 
 // ---- PHY role: one lane per particle ---------------------------------------------------------------------------------
-template <class Cfg, bool PLAINC>
+template <class Cfg, bool PLAINC, bool PHYMB>
 SDE4_DEV void ws_role_phy(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const sde4_cost_desc& cd,
                           const sde4_cost_desc& td, const CostK& a, float* ftape, int pl, int g, int p, int pd, bool active) {
   using A = typename Cfg::A;
@@ -723,8 +723,8 @@ SDE4_DEV void ws_role_phy(const float* W, const float4* tiles, float* xch, const
     }
     typename RS::DriftPart dp;
     RS::drift_post_a(S, x, u, dp);  // the network-independent part of the drift, while the networks run
-    if constexpr (NetB::PRESENT) {
-      // forward sweep only: this warp would idle ~1 500 cycles here while the RES role evaluates its two networks back to
+    if constexpr (NetB::PRESENT && PHYMB) {
+      // forward sweep only, latency regime only (PHYMB, see k_cost_ws): this warp would idle ~1 500 cycles here while the RES role evaluates its two networks back to
       // back (the longest item of a forward step) -- it evaluates the residual-moment network itself, all 32 lanes
       const int lane = threadIdx.x & 31;
       float aB[4], Mn4[4];
@@ -1042,7 +1042,7 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
 }
 
 // ---- RES role: one warp, 16 particles; residual force / moment networks on the tensor cores, in-kernel noise ----------
-template <class Cfg>
+template <class Cfg, bool PHYMB>
 SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const CostK& a,
                           const float* ftape, int g0, int gmax) {
   using A = typename Cfg::A;
@@ -1064,11 +1064,18 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
   ws_sync<Cfg::THREADS>();  // B0
   for (int ts = 0; ts < H; ++ts) {
     ws_sync3();  // B1
-    float aA[4], Fn[4];  // (the residual-moment network of the forward sweep runs on the PHY warp, see ws_role_phy)
+    float aA[4], Fn[4];
     a_from_xch<NPART>(xch, Cfg::X_IN6, NetA::IN, lane, idxA, aA);
     float dA1f[MA::NT1][4], dA2f[MA::NT2][4];
     MA::template fwd<false, SDE4_WS_FAST_FWD>(tA, wA, lane, aA, Fn, dA1f, dA2f);
     tile_to_xch<NPART>(xch, Cfg::X_FN, 3, lane, Fn);
+    if constexpr (!PHYMB) {  // (PHYMB: the residual-moment network of the forward sweep runs on the PHY warp)
+      float aB[4], Mn[4];
+      float dB1f[MB::NT1][4], dB2f[MB::NT2][4];
+      a_from_xch<NPART>(xch, Cfg::X_IN6, NetB::IN, lane, idxB, aB);
+      MB::template fwd<false, SDE4_WS_FAST_FWD>(tB, wB, lane, aB, Mn, dB1f, dB2f);
+      tile_to_xch<NPART>(xch, Cfg::X_MN, 3, lane, Mn);
+    }
     ws_sync<Cfg::THREADS>();  // B2
   }
   // ---------------- backward sweep ----------------
@@ -1149,7 +1156,11 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
 // One CTA = 16 particles, four warps: PHY, DENS, RES, AUX -- warp k of every CTA lands on scheduler k of its SM, so each
 // scheduler (and its L0 instruction cache) runs the code of ONE role.
 // Requirements checked by the launcher: value + gradient, in-kernel threefry noise, no state constraints.
-template <class A, bool PLAINC>
+// PHYMB: where the residual-moment network of the FORWARD sweep runs.  With at most ~2 CTAs per SM the launch is bound by
+// the dependent chain of a step and the PHY warp, idle while the networks run, takes it (true); with many CTAs per SM
+// every scheduler holds the same role of several CTAs, the launch is bound by the busiest ROLE, which is PHY, and the
+// network stays with the RES role (false).
+template <class A, bool PLAINC, bool PHYMB>
 __global__ void __launch_bounds__(128, 3) k_cost_ws(const __grid_constant__ sde4_model_desc d,
                                                     const __grid_constant__ sde4_cost_desc cd,
                                                     const __grid_constant__ sde4_cost_desc td,
@@ -1189,9 +1200,9 @@ __global__ void __launch_bounds__(128, 3) k_cost_ws(const __grid_constant__ sde4
     const int on = __ldg(a.mask + p) != 0;
     if (!__syncthreads_or(on)) return;
   }
-  if (warp == 0) ws_role_phy<Cfg, PLAINC>(W, tiles, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
+  if (warp == 0) ws_role_phy<Cfg, PLAINC, PHYMB>(W, tiles, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
   else if (warp == 1) ws_role_dens<Cfg>(W, tiles, xch, d, a, g0, a.G - 1);
-  else if (warp == 2) ws_role_res<Cfg>(W, tiles, xch, d, a, ftape, g0, a.G - 1);
+  else if (warp == 2) ws_role_res<Cfg, PHYMB>(W, tiles, xch, d, a, ftape, g0, a.G - 1);
   else ws_role_aux<Cfg>(xch, d, a, g0, in_range, n, pd);
 }
 
