@@ -25,7 +25,7 @@ for _ in range(3):
     lib.sde4_debug_ws_trace(out.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
 print("events per role", cnt)
 names = ["PHY", "DENS", "RES", "AUX"]
-ev = out.reshape(4, 512, 2)
+ev = out.reshape(4, 512, 2)[:, 1:]  # (event 0 of every role is B0, the start barrier for the first noise slot)
 # PHY and RES meet at every barrier (B1, B2 per forward step; B3, B4 per backward step); DENS joins B1, B2 and, in the
 # backward sweep, B4 only (it works one step ahead through two output slots); AUX joins B2 / B4
 pr = ev[[0, 2], :4 * H]
