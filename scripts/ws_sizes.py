@@ -16,12 +16,12 @@ cp = configs.hexa_mpc()["cost_params"]
 stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
 ts = compute_timesteps(pm)
 xd = torch.tensor(np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32), device="cuda")
-for P, N in ((256, 16), (512, 32), (2048, 32), (4096, 32)):
+for P, N in ((256, 16), (512, 32), (1024, 32), (2048, 32), (4096, 32)):
     y0 = torch.tensor(np.tile(configs.hover_state(), (P, 1)), device="cuda")
     u = torch.tensor(rng.uniform(0.30, 0.36, (P, H, 6)).astype(np.float32), device="cuda")
     keys = tf.split(tf.PRNGKey(1), P)
     row = []
-    for lanes in (1, 4, 8, L.LANES_WS):
+    for lanes in ((L.LANES_WS,) if os.environ.get("WS_ONLY") else (1, 4, 8, L.LANES_WS)):
         try:
             for _ in range(3):
                 eng.cost_grad(nn, y0, u, ts, xd, stage.desc, N=N, key=keys, lanes=lanes)
@@ -33,4 +33,4 @@ for P, N in ((256, 16), (512, 32), (2048, 32), (4096, 32)):
             row.append("%7.1f" % (e0.elapsed_time(e1) * 100))
         except Exception as ex:
             row.append("   n/a ")
-    print("P=%5d N=%4d G=%6d  us per launch: lanes1 %s lanes4 %s lanes8 %s ws %s" % (P, N, P * N, *row))
+    print("P=%5d N=%4d G=%6d  us per launch (lanes 1 / 4 / 8 / ws, or ws only):" % (P, N, P * N), " ".join(row))

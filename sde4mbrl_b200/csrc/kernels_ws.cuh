@@ -1155,6 +1155,9 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
 // and costs everywhere else: C3 0.358 -> 0.377 ms, 131 k samples 2.03 -> 2.24 ms.)
 // One CTA = 16 particles, four warps: PHY, DENS, RES, AUX -- warp k of every CTA lands on scheduler k of its SM, so each
 // scheduler (and its L0 instruction cache) runs the code of ONE role.
+// (That locality is worth a factor of two: rotating the roles per CTA, so that every scheduler holds a mix of roles and no
+// scheduler is left with the busiest role of every resident CTA, ran 1.2x (16 k samples) to 1.75x (131 k samples) SLOWER --
+// 299 -> 354 us and 2.18 -> 3.80 ms, H = 20, scripts/ws_sizes.py -- three roles' loop bodies do not fit one L0 cache.)
 // Requirements checked by the launcher: value + gradient, in-kernel threefry noise, no state constraints.
 // PHYMB: where the residual-moment network of the FORWARD sweep runs.  With at most ~2 CTAs per SM the launch is bound by
 // the dependent chain of a step and the PHY warp, idle while the networks run, takes it (true); with many CTAs per SM
