@@ -651,7 +651,20 @@ def main():
                                 proximal_fn=prox_h)
                 if rep:
                     tms.append((time.perf_counter() - t0) * 1e3)
+            # the same reference-facing calls with the cost function made by multi_sampling.bind(...) instead of a lambda:
+            # apg.apg hands the solve to the device-side solver
+            cost_b = mcost.bind(nnc, y0c, keyc, stagec, extra_cost_args=xrefc)
+            prox_b = lambda x, stepsize=None: vprox(x)
+            prox_b.box = vprox
+            tmb = []
+            for rep in range(4):
+                t0 = time.perf_counter()
+                st_b = _apg.apg(_apg.init_apg(torch.as_tensor(x0c), cost_b, mpcc["apg_mpc"]), cost_b, mpcc["apg_mpc"],
+                                proximal_fn=prox_b)
+                if rep:
+                    tmb.append((time.perf_counter() - t0) * 1e3)
             c2_extra = {"problem": "cartpole swing-up, 1 problem, %d particles, horizon %d, 20 APG iterations" % (NC, HC),
+                        "apg_api_bound_cost_ms_per_solve": float(np.mean(tmb)), "apg_api_bound_cost_opt_cost": float(st_b.opt_cost),
                         "device_apg_ms_per_solve": dev_ms, "device_apg_opt_cost": dev_cost,
                         "host_apg_api_ms_per_solve": float(np.mean(tms)), "host_apg_opt_cost": float(st_h.opt_cost),
                         "host_apg_iterations": int(st_h.num_steps) - 1}

@@ -175,9 +175,15 @@ class BatchedAPG:
         self._cost(self.y, self.y_cost, grad_buf=self.y_grad)
         ls = self.op["linesearch"]
         lib = L.load()
+        # (both tensors stay referenced until the launch is enqueued: as temporaries inside the call expression the first
+        #  one was freed before the second was made, the caching allocator handed out the same block again, and the
+        #  kernel read the step size as the momentum)
+        mom_t = None if momentum is None else as_f32(momentum).reshape(-1).contiguous()
+        step_t = None if stepsize is None else as_f32(stepsize).reshape(-1).contiguous()
+        for t_ in (mom_t, step_t):
+            assert t_ is None or t_.numel() == P, "momentum / stepsize: one value per problem"
         L.check(lib.sde4_apg_init(C.byref(self.prm), C.byref(self.st), _ptr(self.y), _ptr(self.y_cost), _ptr(self.y_grad),
-                                  _ptr(None if momentum is None else as_f32(momentum).contiguous()),
-                                  _ptr(None if stepsize is None else as_f32(stepsize).contiguous()),
+                                  _ptr(mom_t), _ptr(step_t),
                                   C.c_float(ls["init_stepsize"]), C.c_float(self.op.get("beta_init", 0.25)),
                                   _ptr(self.cand), _stream()))
         return self

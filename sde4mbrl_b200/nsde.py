@@ -436,6 +436,74 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
     multi_sampling.engine = engine
     multi_sampling.time_steps = time_steps
 
+    def device_solver(_nn_params, stage, term, optimizer_params, box=None):
+        """The device-side APG solver (``apg_batched.BatchedAPG``) of this cost for a final stage cost / terminal cost /
+        ``apg_mpc`` options / box, cached on everything that shapes it; the parameter VALUES are refreshed on every call
+        (a tree whose leaves were updated in place, or a new tree of the same architecture, reuses the solver and its
+        CUDA graph)."""
+        from .apg_batched import BatchedAPG
+        import json
+        bkey = None if box is None else (box.first, box.lb_np.tobytes(), box.ub_np.tobytes())
+        key = (bytes(stage.desc), None if term is None else bytes(term.desc),
+               json.dumps(optimizer_params, sort_keys=True, default=float), bkey)
+        cache = multi_sampling.__dict__.setdefault("_device_solvers", {})
+        solver = cache.get(key)
+        if solver is not None:
+            return solver.set_params(_nn_params)
+        lb = ub = None
+        if box is not None:
+            lb, ub = np.full(opt_params_size, -np.inf, np.float32), np.full(opt_params_size, np.inf, np.float32)
+            lb[box.first:], ub[box.first:] = box.lb_np, box.ub_np
+        if len(cache) > 8:
+            cache.clear()
+        solver = cache[key] = BatchedAPG(engine, _nn_params, stage, optimizer_params, time_steps, num_sample, lb=lb, ub=ub,
+                                         terminal=term)
+        return solver
+
+    multi_sampling.device_solver = device_solver
+
+    class _BoundCost:
+        """``lambda opt: multi_sampling(nn_params, y, opt, rng, cost_fn, ...)[0]`` -- the closure ``apg.py`` is handed as
+        ``cost_fn`` (sde_mpc_design.py:207-219) -- as an object that still knows its arguments.  Called, it is that
+        closure; ``apg.init_apg`` / ``apg.one_step_apg`` take value and gradient from its ONE fused launch
+        (``value_and_grad``) instead of an autograd graph; and ``apg.apg`` hands a fresh line-search solve (with no or a
+        box ``proximal_fn``) to the device-side solver, one CUDA-graph replay per iteration instead of 5-8 host-driven
+        cost calls -- same iterates, same ``APGState``."""
+
+        def __init__(self, _nn_params, y, rng, _cost_fn, _terminal_cost=None, extra_cost_args=None):
+            self.nn, self.y, self.rng, self.cost, self.term, self.xref = _nn_params, y, rng, _cost_fn, _terminal_cost, extra_cost_args
+
+        def __call__(self, opt):
+            return multi_sampling(self.nn, self.y, opt, self.rng, self.cost, self.term, extra_cost_args=self.xref)[0]
+
+        def value_and_grad(self, opt):
+            (c, _), g = value_and_grad(self.nn, self.y, opt, self.rng, self.cost, self.term, extra_cost_args=self.xref)
+            return c, g
+
+        def solve_on_device(self, st, optimizer_params, proximal_fn, check_every=4):
+            """``apg.apg`` for a state as ``init_apg`` returns it; None when the device solver does not cover the call
+            (no line search, a proximal operator that is not a box, a state in the middle of a solve, several problems)."""
+            box = proximal_fn if isinstance(proximal_fn, _Box) else getattr(proximal_fn, "box", None)
+            if "linesearch" not in optimizer_params or (proximal_fn is not None and not isinstance(box, _Box)):
+                return None
+            if multi_sampling.particle_reducer is not None or not isinstance(st.xk, torch.Tensor) or st.xk.dim() != 2:
+                return None
+            fresh = (st.num_steps == 1 and st.num_iter_no_improv == 0 and st.not_done and st.opt_cost == st.curr_cost
+                     and st.curr_cost == st.init_cost and st.avg_momentum == st.momentum and st.avg_stepsize == st.stepsize
+                     and (st.xk is st.yk or torch.equal(st.xk, st.yk)) and (st.xk is st.x_opt or torch.equal(st.xk, st.x_opt)))
+            if not fresh:
+                return None
+            solver = device_solver(self.nn, multi_sampling.final_stage(self.cost), self.term, optimizer_params, box)
+            solver.init(st.xk, self.y, self.xref, self.rng, momentum=np.float32(st.momentum), stepsize=np.float32(st.stepsize))
+            solver.run(check_every=check_every)
+            out = solver.state_of(0)
+            vec = {k: getattr(out, k).clone() for k in ("x_opt", "xk", "yk", "grad_yk")}
+            if not st.xk.is_cuda:
+                vec = {k: v.cpu() for k, v in vec.items()}
+            return out._replace(**vec)
+
+    multi_sampling.bind = _BoundCost
+
     def _construct_opt_params(u=None, x=None):
         """``nsde.py:1532-1573`` (including the doubled ``+1e-4`` of the 1-D ``u`` path)."""
         num_var = H

@@ -222,28 +222,8 @@ _POLL_EVERY = 4
 
 
 def _device_solver(multi_cost_sampling, cfg_dict, _sde_learned, stage, term, box):
-    from .apg_batched import BatchedAPG
-    import json
-    op = cfg_dict["apg_mpc"]
-    # keyed on everything that shapes the solver; the parameter VALUES are refreshed below on every call (a tree whose
-    # leaves were updated in place, or a new tree of the same architecture, reuses the solver and its CUDA graph)
-    key = (bytes(stage.desc), None if term is None else bytes(term.desc), json.dumps(op, sort_keys=True, default=float))
-    cache = multi_cost_sampling.__dict__.setdefault("_device_solvers", {})
-    solver = cache.get(key)
-    if solver is not None:
-        solver.set_params(_sde_learned)
-    if solver is None:
-        lb = ub = None
-        if box is not None:
-            n = multi_cost_sampling.n_opt
-            lb, ub = np.full(n, -np.inf, np.float32), np.full(n, np.inf, np.float32)
-            lb[box.first:], ub[box.first:] = box.lb_np, box.ub_np
-        if len(cache) > 8:
-            cache.clear()
-        solver = BatchedAPG(multi_cost_sampling.engine, _sde_learned, stage, op, multi_cost_sampling.time_steps,
-                            multi_cost_sampling.num_particles, lb=lb, ub=ub, terminal=term)
-        cache[key] = solver
-    return solver
+    """The cached ``apg_batched.BatchedAPG`` of this cost (``nsde`` ``multi_sampling.device_solver``)."""
+    return multi_cost_sampling.device_solver(_sde_learned, stage, term, cfg_dict["apg_mpc"], box)
 
 
 def apg_mpc(xt, rng, past_solution, target_x, multi_cost_sampling, proximal_fn, cfg_dict, _sde_learned,

@@ -191,6 +191,49 @@ def test_apg_with_host_tensors_matches_device_tensors(cuda):
     assert hp.rel_err(s_host.x_opt.numpy(), s_dev.x_opt.cpu().numpy()) < 1e-4
 
 
+@pytest.mark.parametrize("with_prox,host_args", [(True, False), (False, False), (True, True)])
+def test_apg_with_bound_cost_runs_on_the_device_solver(cuda, with_prox, host_args):
+    """apg.apg handed ``multi_cost.bind(...)`` instead of a lambda: the fresh line-search solve runs on the device-side
+    solver (apg_batched.BatchedAPG) and must return the APGState the host loop returns for the same closure; a state in
+    the middle of a solve falls back to the host loop, with value + gradient from the fused launch."""
+    from sde4mbrl_b200 import apg, random as R
+    N, H, iters = 8, 20, 6
+    pm, mpc, nn, (_, multi_cost, vprox, _, construct_opt) = _mpc_setup(N, H, iters)
+    cp, op = mpc["cost_params"], mpc["apg_mpc"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    y0 = hp.start_state("hexa", np.random.default_rng(2))
+    xref = np.tile(configs.hover_state(), (H + 1, 1)).astype(np.float32)
+    xref[:, :3] = [0.0, 0.5, 1.4]
+    key = tf.PRNGKey(21) if host_args else R.PRNGKey(21)
+    prox = (lambda x, stepsize=None: vprox(x)) if with_prox else None
+    if with_prox:
+        prox.box = vprox  # (what rotor_mpc.load_mpc_from_cfgfile attaches; vprox itself is accepted too)
+    x0 = construct_opt(u=np.full(6, 0.33, np.float32))
+    if host_args:
+        x0 = x0.cpu()
+    cost_l = lambda o: multi_cost(nn, y0, o, key, stage, extra_cost_args=xref)[0]
+    s_host = apg.apg(apg.init_apg(x0, cost_l, op), cost_l, op, proximal_fn=(lambda x, stepsize=None: vprox(x)) if with_prox else None)
+    cost_b = multi_cost.bind(nn, y0, key, stage, extra_cost_args=xref)
+    assert abs(float(cost_b(x0)) - float(cost_l(x0))) <= 1e-6 * abs(float(cost_l(x0)))
+    st0 = apg.init_apg(x0, cost_b, op)
+    assert abs(float(st0.grad_sqr) - float(apg.init_apg(x0, cost_l, op).grad_sqr)) <= 1e-5 * float(st0.grad_sqr)
+    s_dev = apg.apg(st0, cost_b, op, proximal_fn=prox)
+    assert getattr(multi_cost, "_device_solvers", None), "the solve did not reach the device-side solver"
+    assert s_dev.x_opt.is_cuda == (not host_args)
+    assert int(s_dev.num_steps) == int(s_host.num_steps) == iters + 1
+    for f in ("opt_cost", "curr_cost", "init_cost", "stepsize", "avg_stepsize", "momentum", "avg_momentum", "avg_linesearch", "grad_sqr"):
+        np.testing.assert_allclose(float(getattr(s_dev, f)), float(getattr(s_host, f)), rtol=2e-4, err_msg=f)
+    assert bool(s_dev.not_done) == bool(s_host.not_done)
+    for f in ("x_opt", "xk", "yk", "grad_yk"):
+        assert hp.rel_err(getattr(s_dev, f).cpu().numpy(), getattr(s_host, f).cpu().numpy()) < 2e-3, f
+    # a state in the middle of a solve: host loop (fused value + gradient), same continuation as the lambda
+    op2 = dict(op, max_iter=2)
+    mid_b = apg.apg(s_dev._replace(not_done=True), cost_b, op2, proximal_fn=prox)
+    mid_l = apg.apg(s_dev._replace(not_done=True), cost_l, op2, proximal_fn=prox)
+    assert int(mid_b.num_steps) == int(mid_l.num_steps) == iters + 3
+    np.testing.assert_allclose(float(mid_b.opt_cost), float(mid_l.opt_cost), rtol=1e-5)
+
+
 def test_rejects_python_cost_callables(cuda):
     from sde4mbrl_b200 import random as R
     from sde4mbrl_b200._lib import Sde4Error
