@@ -411,6 +411,16 @@ int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* a, v
   float* outp = hp_dev ? hp_dev : dp;
   d.cost = outp + h.cost;
   d.grad = a->grad ? outp + h.grad : nullptr;
+  // particles of the problem sharded over GPUs (sde4_xgpu_reduce): K3's last CTA sums the world's partials; its output
+  // -- the contiguous [cost | grad] vector of x.n floats -- goes straight into the staging buffer as well
+  sde4_xgpu_reduce xg;
+  size_t goff = h.grad;
+  if (a->xgpu) {
+    xg = *a->xgpu;
+    xg.out = outp + h.cost;
+    d.xgpu = &xg;
+    goff = h.cost + (size_t)P;
+  }
   if (int rc = cost_grad_impl(model, &d, stream, LossOpts())) return rc;
   const size_t out_floats = a->grad ? h.total - h.cost : (size_t)P;
   err = cudaSuccess;
@@ -418,7 +428,7 @@ int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* a, v
   if (err == cudaSuccess) err = cudaStreamSynchronize(s);
   if (err != cudaSuccess) return fail(SDE4_ERR_CUDA, "D2H: %s", cudaGetErrorString(err));
   std::memcpy(a->cost, hp + h.cost, (size_t)P * 4);
-  if (a->grad) std::memcpy(a->grad, hp + h.grad, (size_t)P * H * n_opt * 4);
+  if (a->grad) std::memcpy(a->grad, hp + goff, (size_t)P * H * n_opt * 4);
   return SDE4_OK;
 }
 

@@ -375,11 +375,13 @@ class Engine:
 
     # ---- K2 + K3 with HOST buffers (one packed copy each way) ----------------
     def cost_grad_host(self, nn_params, y0, opt, dt, xref, stage, terminal=None, key=None, N=1, want_grad=True,
-                       want_xtraj=False, block_threads=0, lanes=0):
+                       want_xtraj=False, block_threads=0, lanes=0, particle_offset=0, particle_total=0, xgpu=None):
         """Same evaluation as ``cost_grad`` for arguments that live in HOST memory (numpy arrays / CPU
         tensors): ``sde4_cost_grad_host`` packs them into a pinned staging buffer, does one H2D copy,
         the launches, one D2H copy of [cost | grad] and a stream synchronise.  Returns numpy
-        ``cost[P]``, ``grad`` (shape of ``opt``) or None, and the device ``xtraj`` or None."""
+        ``cost[P]``, ``grad`` (shape of ``opt``) or None, and the device ``xtraj`` or None.
+        ``particle_offset`` / ``particle_total`` / ``xgpu`` (``dist.CostGradReducer.launch_kwargs``): this rank's
+        particles of a problem sharded over GPUs; K3 sums the world's partials and the TOTAL comes back."""
         self._em_only()
         pk = self.packed(nn_params)
         y0 = host_f32(y0).reshape(-1, self.n_x)
@@ -442,6 +444,8 @@ class Engine:
         a.cost, a.grad = cost.ctypes.data, (grad.ctypes.data if want_grad else None)
         a.xtraj = xtraj.data_ptr() if want_xtraj else None
         a.workspace, a.workspace_bytes = ws.data_ptr(), ws.numel()
+        a.particle_offset, a.particle_total = particle_offset, particle_total
+        a.xgpu = C.addressof(xgpu) if xgpu is not None else None
         L.check(lib.sde4_cost_grad_host(C.byref(self.desc), C.byref(a), _ptr(self._stage[0]), _ptr(self._stage[1]),
                                         sbytes, _stream()))
         if squeeze and grad is not None:

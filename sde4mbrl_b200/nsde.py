@@ -392,6 +392,21 @@ def create_online_cost_sampling_fn(params_model, params_mpc, sde_constr=Controll
             raise Sde4Error("particle_reducer must hold H*n_opt + 1 = %d floats" % (n_o + 1))
         host = is_host(y) and is_host(opt_params) and is_host(rng) and is_host(extra_cost_args)
         dev = red.device
+        if host and getattr(red, "_xg", None) is not None:
+            # fused transport: the host-buffer entry point itself (sde4_cost_grad_host with sde4_xgpu_reduce) -- one packed
+            # pinned H2D copy, K2, K3 with the cross-GPU sum in its last CTA writing the TOTAL [cost | grad] straight into
+            # the mapped staging buffer, one stream synchronise
+            o_h = opt_params.detach().numpy() if isinstance(opt_params, torch.Tensor) else opt_params
+            o_h = host_f32(o_h)
+            assert o_h.ndim == 2 and o_h.shape[-1] == opt_params_size, "one problem: opt_params must be [H, n_opt]"
+            kw = red.launch_kwargs(1)
+            cost, grad, xbuf = engine.cost_grad_host(_nn_params, host_f32(y).reshape(1, n_x), o_h, time_steps,
+                                                     host_f32(extra_cost_args), stage.desc, terminal=term, key=rng,
+                                                     N=num_sample, want_grad=True, want_xtraj=True,
+                                                     particle_offset=rank * num_sample, particle_total=world * num_sample,
+                                                     xgpu=kw["xgpu"])
+            xtraj = xbuf.view(H + 1, n_x + 1, 1, num_sample).permute(2, 3, 0, 1)[0]
+            return (torch.from_numpy(cost)[0], xtraj), torch.from_numpy(grad)
         if host:
             st = _stg.get(dev)
             if st is None:
