@@ -825,8 +825,10 @@ def main():
                            "(sde4_cost_grad_host: pinned staging, one H2D + one D2H copy, stream sync inside)"
                            if world == 1 else
                            "nsde.create_online_cost_sampling_fn(...).multi_sampling.value_and_grad on HOST numpy arrays with "
-                           "multi_sampling.particle_reducer = dist.CostGradReducer (one packed pinned H2D copy, K2 + K3 into the "
-                           "symmetric-memory buffer, one-shot all-reduce over NVLink, one D2H copy, stream sync inside)"},
+                           "multi_sampling.particle_reducer = dist.CostGradReducer, transport '%s' (fused: sde4_cost_grad_host with "
+                           "sde4_xgpu_reduce -- one packed pinned H2D copy, K2, K3 whose last CTA sums the peers' partials over "
+                           "NVLink and writes the total into the mapped staging buffer, stream sync; other transports: K3 + "
+                           "library all-reduce + D2H copy)" % args.transport},
             "gpu_launches": 2 * args.steps,
             "wall_s_timed_region": t_wall,
         }

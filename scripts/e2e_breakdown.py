@@ -22,15 +22,19 @@ def step_autograd():
     (g,) = torch.autograd.grad(c, opt_leaf)
 def raw():
     return eng.cost_grad_host(pk, w["y0"], w["opt"], multi_cost.time_steps, w["xref"], w["stage"].desc, key=key_np, N=4096)
+def raw_xtraj():
+    return eng.cost_grad_host(pk, w["y0"], w["opt"], multi_cost.time_steps, w["xref"], w["stage"].desc, key=key_np, N=4096, want_xtraj=True)
+def dev_only_xtraj():
+    eng.cost_grad(pk, y0_d, opt_d, multi_cost.time_steps, xref_d, w["stage"].desc, key=key_d, N=4096, want_xtraj=True); torch.cuda.synchronize()
 def dev_only():
     eng.cost_grad(pk, y0_d, opt_d, multi_cost.time_steps, xref_d, w["stage"].desc, key=key_d, N=4096); torch.cuda.synchronize()
 y0_d = torch.as_tensor(w["y0"], device="cuda")[None]; opt_d = torch.as_tensor(w["opt"], device="cuda")
 xref_d = torch.as_tensor(w["xref"], device="cuda"); key_d = torch.as_tensor(key_np.view(np.int32), device="cuda")
-for fn, name in ((step, "value_and_grad (host arrays)"), (step_autograd, "multi_cost + autograd.grad (host arrays)"), (raw, "Engine.cost_grad_host"), (dev_only, "Engine.cost_grad on device tensors + sync")):
+for fn, name in ((step, "value_and_grad (host arrays)"), (step_autograd, "multi_cost + autograd.grad (host arrays)"), (raw, "Engine.cost_grad_host"), (raw_xtraj, "Engine.cost_grad_host + xtraj"), (dev_only, "Engine.cost_grad on device tensors + sync"), (dev_only_xtraj, "Engine.cost_grad on device tensors + xtraj + sync")):
     for _ in range(5): fn()
     t0 = time.perf_counter()
-    for _ in range(100): fn()
-    print(name, "ms/step", (time.perf_counter() - t0) / 100 * 1e3)
+    for _ in range(300): fn()
+    print(name, "ms/step", (time.perf_counter() - t0) / 300 * 1e3)
 pr = cProfile.Profile(); pr.enable()
 for _ in range(100): step()
 pr.disable()
