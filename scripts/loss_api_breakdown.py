@@ -1,7 +1,8 @@
 """Where the time of the full training loss (data term + distance-aware regulariser + weight penalty) goes when it is
 called through create_model_loss_fn(...).loss_fn.value_and_grad (bench extra `ms_full_loss_value_and_grad_api`).
 cProfile of 20 calls at the cartpole_sde.yaml shape (B = 512, H = 30, 20 ball samples)."""
-import cProfile, pstats, io, contextlib, time
+import cProfile, pstats, io, contextlib, time, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from sde4mbrl_b200 import configs, nsde, sde_models, random as R
@@ -35,5 +36,5 @@ for rep in range(20):
 torch.cuda.synchronize()
 pr.disable()
 s = io.StringIO()
-pstats.Stats(pr, stream=s).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(32)
 print(s.getvalue()[:6000])

@@ -1,5 +1,6 @@
 // inst_hexa_ws.cu -- warp-specialised cost + gradient kernels (kernels_ws.cuh) of the multirotor SDE architectures
 // whose single-problem launches are bound by the serial instruction chain (BASELINE configs[2]).
+#include <cstdlib>
 #include "kernels_ws.cuh"
 #include "registry.cuh"
 namespace sde4 {
@@ -20,6 +21,8 @@ cudaError_t launch_cost_ws_t(const sde4_model_desc& d, const sde4_cost_desc& cd,
     cudaFuncSetAttribute(k_cost_ws<A, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     cudaFuncSetAttribute(k_cost_ws<A, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     cudaFuncSetAttribute(k_cost_ws<A, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    cudaFuncSetAttribute(k_cost_ws<A, false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     once.mark(dev);
   }
   const int blocks = (a.G + Cfg::NPART - 1) / Cfg::NPART;
@@ -27,11 +30,20 @@ cudaError_t launch_cost_ws_t(const sde4_model_desc& d, const sde4_cost_desc& cd,
   int sms = 148;
   if (dev < 0 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
   const bool phymb = blocks <= 2 * sms;  // latency regime (see k_cost_ws)
+  // four CTAs per SM where that saves a wave of CTAs (up to two waves; beyond, three per SM have the higher throughput)
+  static const int force_minb = [] {
+    const char* e = std::getenv("SDE4_WS_MINB");  // tuning aid: 3 / 4 forces the instantiation
+    return e ? std::atoi(e) : 0;
+  }();
+  const int w3 = (blocks + 3 * sms - 1) / (3 * sms), w4 = (blocks + 4 * sms - 1) / (4 * sms);
+  const bool four = !phymb && (force_minb ? force_minb == 4 : (w4 < w3 && w4 <= 2));
   if (plain) {
     if (phymb) k_cost_ws<A, true, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+    else if (four) k_cost_ws<A, true, false, 4><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
     else k_cost_ws<A, true, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
   } else {
     if (phymb) k_cost_ws<A, false, true><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
+    else if (four) k_cost_ws<A, false, false, 4><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
     else k_cost_ws<A, false, false><<<blocks, Cfg::THREADS, sm, s>>>(d, cd, td, a, ftape);
   }
   return cudaGetLastError();

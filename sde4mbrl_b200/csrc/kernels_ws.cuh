@@ -1163,8 +1163,10 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
 // the dependent chain of a step and the PHY warp, idle while the networks run, takes it (true); with many CTAs per SM
 // every scheduler holds the same role of several CTAs, the launch is bound by the busiest ROLE, which is PHY, and the
 // network stays with the RES role (false).
-template <class A, bool PLAINC, bool PHYMB>
-__global__ void __launch_bounds__(128, 3) k_cost_ws(const __grid_constant__ sde4_model_desc d,
+// MINB = 4 (128 registers, a few spills): only where a fourth resident CTA per SM saves a whole wave of CTAs -- 7 168
+// samples (448 CTAs: one wave instead of 444 + 4) and 16 384 samples (two waves instead of three); the launcher decides.
+template <class A, bool PLAINC, bool PHYMB, int MINB = 3>
+__global__ void __launch_bounds__(128, MINB) k_cost_ws(const __grid_constant__ sde4_model_desc d,
                                                     const __grid_constant__ sde4_cost_desc cd,
                                                     const __grid_constant__ sde4_cost_desc td,
                                                     const __grid_constant__ CostK a, float* ftape) {
