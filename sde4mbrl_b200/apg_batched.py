@@ -29,8 +29,8 @@ from .engine import as_f32, as_key, _ptr, _stream
 
 # speculative iterations while (points per problem) * P * N stays at or below this many samples (scripts/apg_spec.py;
 # refitted with scripts/apg_modes2.py on the warp-specialised kernel: 14 points x 384 problems = 5 376 samples 2.81 ms
-# against 3.18 ms merged, 7 168 samples 3.11 vs 3.14 ms, 8 960 samples 3.45 vs 3.33 ms)
-SPECULATIVE_MAX_SAMPLES = 6144
+# against 3.18 ms merged, 6 720 samples 2.93 vs 3.21 ms, 7 168 samples 3.11 vs 3.14 ms, 8 960 samples 3.45 vs 3.33 ms)
+SPECULATIVE_MAX_SAMPLES = 7168
 
 
 class BatchedAPG:

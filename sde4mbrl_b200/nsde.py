@@ -797,13 +797,14 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
             step_weight = _random.choice_mask_many(k_s2c, horizon, n_consider)
         on_partial = step_weight is not None and params_model.get("density_on_partial", False)
         pend = None
+        pk_all = engine.packed(_nn_params)  # ONE fingerprint + upload per call: the data term and the regulariser share it
         if dl is not None and native is not None and not on_partial:
             # distance-aware regulariser at the data points on the library's kernels, on a side stream: the data term's
             # launches (a few thousand threads) run beside it; both are read back behind ONE synchronisation
             if "side" not in _stage:
                 _stage["side"] = torch.cuda.Stream(device=y_values.device)
             side, cur = _stage["side"], torch.cuda.current_stream(y_values.device)
-            pk = engine.packed(_nn_params)  # (uploaded on the main stream, which the side stream then waits for)
+            pk = pk_all  # (uploaded on the main stream, which the side stream then waits for)
             side.wait_stream(cur)
             with torch.cuda.stream(side):
                 pend = native.launch(_nn_params, as_f32(y), as_f32(u), key, pk=pk)
@@ -813,13 +814,13 @@ def create_model_loss_fn(model_params, loss_params, sde_constr=ControlledSDE, ve
             loss_b, gpacked = None, None
             for n in range(num_sample):  # one launch per particle index: particle n of every element, its own controls
                 sw = None if step_weight is None else step_weight[:, n::num_sample].contiguous()
-                lb, gp = engine.loss_grad(_nn_params, y_values, u_bn[:, n].contiguous(), time_steps, data_cost.desc, keys, N=1,
+                lb, gp = engine.loss_grad(pk_all, y_values, u_bn[:, n].contiguous(), time_steps, data_cost.desc, keys, N=1,
                                           step_weight=sw, particle_offset=n, particle_total=num_sample)
                 loss_b = lb.clone() if loss_b is None else loss_b + lb
                 gpacked = gp.clone() if gpacked is None else gpacked + gp
             u_values = u_bn[:, 0]
         else:
-            loss_b, gpacked = engine.loss_grad(_nn_params, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample,
+            loss_b, gpacked = engine.loss_grad(pk_all, y_values, u_values, time_steps, data_cost.desc, keys, N=num_sample,
                                                step_weight=step_weight)
         nb, npar = loss_b.numel(), gpacked.numel()
         if _stage.get("n") != (nb, npar):
