@@ -120,6 +120,7 @@ def test_host_buffer_path_matches_device_path(cuda):
     (c3, xt3), g3 = multi_cost.value_and_grad(nn, y0, opt_np, key_np, stage, extra_cost_args=xref)
     assert float(c3) == float(c_dev) and tuple(xt3.shape) == (N, H + 1, 14)
     np.testing.assert_array_equal(g3.numpy(), g_dev.cpu().numpy())
+    np.testing.assert_array_equal(xt3.cpu().numpy(), xt_dev.cpu().numpy())  # (the lean host route builds its own view)
     (c4, _), g4 = multi_cost.value_and_grad(nn, y0, o_dev.detach(), R.PRNGKey(9), stage, extra_cost_args=xref)
     assert c4.is_cuda and float(c4) == float(c_dev) and torch.equal(g4, g_dev)
     # value only, numpy in (no autograd)
@@ -135,6 +136,15 @@ def test_host_buffer_path_matches_device_path(cuda):
     cd_, gd_, _ = eng.cost_grad(nn, y0b, optb, multi_cost.time_steps, xref, stage.desc, key=keyb, N=N)
     np.testing.assert_array_equal(ch, cd_.cpu().numpy())
     np.testing.assert_array_equal(gh, gd_.cpu().numpy())
+    # the same batch through value_and_grad: host arrays (lean route) against device tensors (generic route)
+    (cb_h, xtb_h), gb_h = multi_cost.value_and_grad(nn, y0b, optb, keyb, stage, extra_cost_args=xref)
+    (cb_d, xtb_d), gb_d = multi_cost.value_and_grad(nn, torch.as_tensor(y0b, device="cuda"), torch.as_tensor(optb, device="cuda"),
+                                                    torch.as_tensor(keyb.view(np.int32), device="cuda"), stage,
+                                                    extra_cost_args=torch.as_tensor(xref, device="cuda"))
+    assert tuple(xtb_h.shape) == tuple(xtb_d.shape) == (P, N, H + 1, 14) and not cb_h.is_cuda
+    np.testing.assert_array_equal(cb_h.numpy(), cb_d.cpu().numpy())
+    np.testing.assert_array_equal(gb_h.numpy(), gb_d.cpu().numpy())
+    np.testing.assert_array_equal(xtb_h.cpu().numpy(), xtb_d.cpu().numpy())
 
 
 def test_apg_mpc_trace_matches_oracle(cuda):
