@@ -556,13 +556,16 @@ struct MmaNet {
     bwd_from_g2<FAST>(tiles, lane, g2, d1, gin);
   }
   // scalar-output network: value (column 0 of `out`, threads with t == 0) and the input gradient d out / d in
-  template <bool FAST>
+  // `mid()` runs between the forward pass and the gradient pass (the two density producers of the backward sweep join a
+  // CTA barrier there: an item is made over two steps)
+  template <bool FAST, class Mid>
   SDE4_DEV static void value_grad(const float4* tiles, const float* w, int lane, const float (&ain)[4], float (&out)[4],
-                                  float (&gin)[4]) {
+                                  float (&gin)[4], Mid&& mid) {
     static_assert(N::OUT == 1, "scalar-output network expected");
     const int t = lane & 3;
     float d1[NT1][4], d2[NT2][4];
     fwd<true, FAST>(tiles, w, lane, ain, out, d1, d2);
+    mid();
 #pragma unroll
     for (int n = 0; n < NT2; ++n) {
       const float2 v = *reinterpret_cast<const float2*>(w + N::OFF_W2 + 8 * n + 2 * t);
@@ -975,14 +978,15 @@ struct WsNoise {
 };
 
 // ---- DENS role: one warp, 16 particles; density network on the tensor cores, eta, half of the noise ----------------------------------------
-template <class Cfg>
+// OWN_BWD: the role's own backward sweep follows (every item in one piece, one step ahead; many CTAs per SM) -- otherwise
+// the caller continues with ws_densaux_bwd.
+template <class Cfg, bool OWN_BWD>
 SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const CostK& a,
                            int g0, int gmax) {
   using A = typename Cfg::A;
   using MD = typename Cfg::MD;
   using DNet = typename A::DNet;
   constexpr int NPART = Cfg::NPART, NZ = Cfg::NZ, NO = Cfg::NO;
-  const unsigned G = (unsigned)a.G;
   const int H = a.H;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const float* wD = W + A::OFF_DENSITY;
@@ -1013,6 +1017,8 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
     }
     ws_sync<Cfg::THREADS>();  // B2
   }
+  if constexpr (!OWN_BWD) return;
+  const unsigned G = (unsigned)a.G;
   // ---------------- backward sweep: density value + input gradient of step t, one step ahead of its use ----------------
   // rows of the A operand: particles g0 + g, g0 + g + 8 (clamped to the last valid sample)
   const unsigned ga = min(g0 + g, gmax), gb = min(g0 + g + 8, gmax);
@@ -1028,7 +1034,7 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
   load_inputs(H - 1);  // the forward sweep's last B2 ordered PHY's checkpoint stores before these loads
   for (int ts = H - 1; ts >= 0; --ts) {
     float out[4], J[4];
-    MD::template value_grad<SDE4_WS_FAST_DENSB>(tD, wD, lane, az, out, J);
+    MD::template value_grad<SDE4_WS_FAST_DENSB>(tD, wD, lane, az, out, J, []() {});
     load_inputs(ts > 0 ? ts - 1 : 0);
     const int so = (ts & 1) * Cfg::B_DSLOT;  // PHY read this slot's previous item (step ts + 2) before B4(ts + 1)
     if (t == 0) {
@@ -1039,6 +1045,84 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
     ws_sync<Cfg::THREADS>();  // B4
   }
   ws_sync<Cfg::THREADS>();  // (PHY's last gradient row for the RES role)
+}
+
+// ---- backward sweep of the DENS and AUX warps: the density value + input gradient of every step ---------------------------
+// The item of step t depends on the checkpoint x_t only, not on the cotangent, but it is the longest single piece of a
+// backward step (a value + gradient pass of the 32 x 32 network: the DENS warp alone was the last arriver at B4 in 72 % of
+// the steps, PHY and RES waiting ~480 cycles for it).  The AUX warp has next to nothing to do in this sweep, so the two
+// warps share the items by step parity -- par = 0 (DENS): steps H-1, H-3, ...; par = 1 (AUX): steps H-2, H-4, ... -- and
+// each makes its item over TWO steps: forward pass, B4 of the step in between (the other warp's item), gradient pass,
+// publish, B4 of its own step.  Both warps run this ONE copy of the code (the instruction cache is what binds the kernel
+// otherwise); item t goes to slot t & 1, which PHY finished reading (item t + 2) before B4(t + 1).  The AUX warp keeps
+// its own duty, the fixed-order sum of the control-gradient row PHY left in front of each B4.
+// Latency regime only (PHYMB).  With many CTAs per SM the busiest scheduler binds and the kernel sits on an instruction-cache
+// cliff: two producers cost 65 k samples 1.02 -> 1.33 ms, and so did this shared loop run with ONE producer (stride 1) --
+// the extra 3 KB of code alone -- so those instantiations keep the roles' own backward sweeps (OWN_BWD above).
+template <class Cfg>
+SDE4_DEV void ws_densaux_bwd(const float* W, const float4* tiles, float* xch, const sde4_model_desc& d, const CostK& a,
+                             int g0, int gmax, int par) {
+  using A = typename Cfg::A;
+  using MD = typename Cfg::MD;
+  constexpr int NPART = Cfg::NPART, NZ = Cfg::NZ, NU = Cfg::NU;
+  const unsigned G = (unsigned)a.G;
+  const int H = a.H;
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const float* wD = W + A::OFF_DENSITY;
+  const float4* tD = tiles + Cfg::TILE_D * 32;
+  // Gradient row of step ts: fixed-order sum over the CTA's particles of what PHY left in the exchange buffer:
+  // thread = (control j, quarter of the particles); serial over the quarter, two butterfly rounds.
+  constexpr int QP = NPART / 4;
+  const int rj = lane >> 2, rq = lane & 3;
+  auto sum_row = [&](int ts) {
+    if (!a.warp_reduce) return;
+    float v = 0.0f;
+    if (rj < NU) {
+#pragma unroll
+      for (int k = 0; k < QP; ++k) v += xch[(Cfg::B_GU + rj) * NPART + rq * QP + k];
+    }
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (rj < NU && rq == 0) a.gpart[((size_t)ts * NU + rj) * a.PW + g0 / NPART] = v;
+  };
+  int nb = 0;  // B4 barriers joined so far; barrier number k is B4 of step H - 1 - k
+  auto join = [&]() {
+    ws_sync<Cfg::THREADS>();  // B4: PHY stored gradient row H - nb in front of it and rewrites the slot only after it
+    if (par == 1 && nb >= 1) sum_row(H - nb);
+    ++nb;
+  };
+  // rows of the A operand: particles g0 + g, g0 + g + 8 (clamped to the last valid sample)
+  const unsigned ga = min(g0 + g, gmax), gb = min(g0 + g + 8, gmax);
+  float az[4];
+  auto load_inputs = [&](int ts) {
+    const float* xin = a.xbuf + (size_t)ts * a.x_rows * G;
+    const int k0 = nth_bit_rt<A::NIN_MASK>(t), k1 = nth_bit_rt<A::NIN_MASK>(t + 4 < NZ ? t + 4 : 0);
+    az[0] = t < NZ ? xin[(size_t)k0 * G + ga] * d.inv_red_scale : 0.0f;
+    az[1] = t < NZ ? xin[(size_t)k0 * G + gb] * d.inv_red_scale : 0.0f;
+    az[2] = t + 4 < NZ ? xin[(size_t)k1 * G + ga] * d.inv_red_scale : 0.0f;
+    az[3] = t + 4 < NZ ? xin[(size_t)k1 * G + gb] * d.inv_red_scale : 0.0f;
+  };
+  int ts = H - 1 - par;
+  bool whole = par == 0;  // the item of step H - 1 is due at the first barrier: made in one piece
+  if (ts >= 0) load_inputs(ts);  // the forward sweep's last B2 ordered PHY's checkpoint stores before these loads
+  for (; ts >= 0; ts -= 2) {
+    float out[4], J[4];
+    MD::template value_grad<SDE4_WS_FAST_DENSB>(tD, wD, lane, az, out, J, [&]() {
+      if (!whole) join();
+      whole = false;
+    });
+    load_inputs(ts > 1 ? ts - 2 : 0);
+    const int so = (ts & 1) * Cfg::B_DSLOT;
+    if (t == 0) {
+      xch[(Cfg::B_DENS + so) * NPART + g] = out[0];
+      xch[(Cfg::B_DENS + so) * NPART + g + 8] = out[2];
+    }
+    tile_to_xch<NPART>(xch, Cfg::B_J + so, NZ, lane, J);
+    join();
+  }
+  while (nb < H) join();       // (the last item belongs to the other warp)
+  ws_sync<Cfg::THREADS>();     // PHY's last gradient row is there
+  if (par == 1) sum_row(0);
 }
 
 // ---- RES role: one warp, 16 particles; residual force / moment networks on the tensor cores, in-kernel noise ----------
@@ -1116,11 +1200,9 @@ SDE4_DEV void ws_role_res(const float* W, const float4* tiles, float* xch, const
 
 // ---- AUX role: one warp; in-kernel threefry noise one step ahead (forward sweep), fixed-order sum of the control-gradient
 //      rows over the CTA's particles (backward sweep) ------------------------------------------------------------------
-template <class Cfg>
+template <class Cfg, bool OWN_BWD>
 SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, int g0, bool lane_active, int n, int pd) {
-  constexpr int NPART = Cfg::NPART, NU = Cfg::NU;
   const int H = a.H;
-  const int lane = threadIdx.x & 31;
   WsNoise<Cfg, 2> noise(xch, d, a, g0, lane_active, n, pd);
   noise.gen(0);
   ws_sync<Cfg::THREADS>();  // B0: dw_0 is there (PHY reads dw_t in front of B2 of step t)
@@ -1128,6 +1210,9 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
     if (ts + 1 < H) noise.gen(ts + 1);  // slot (ts + 1) % 3: PHY reads it after B2 of the next step
     ws_sync<Cfg::THREADS>();  // B2
   }
+  if constexpr (!OWN_BWD) return;
+  constexpr int NPART = Cfg::NPART, NU = Cfg::NU;
+  const int lane = threadIdx.x & 31;
   // Gradient row of step ts: fixed-order sum over the CTA's particles of what PHY left in the exchange buffer:
   // thread = (control j, quarter of the particles); serial over the quarter, two butterfly rounds.
   constexpr int QP = NPART / 4;
@@ -1206,9 +1291,12 @@ __global__ void __launch_bounds__(128, MINB) k_cost_ws(const __grid_constant__ s
     if (!__syncthreads_or(on)) return;
   }
   if (warp == 0) ws_role_phy<Cfg, PLAINC, PHYMB>(W, tiles, xch, d, cd, td, a, ftape, pl, g, p, pd, active);
-  else if (warp == 1) ws_role_dens<Cfg>(W, tiles, xch, d, a, g0, a.G - 1);
   else if (warp == 2) ws_role_res<Cfg, PHYMB>(W, tiles, xch, d, a, ftape, g0, a.G - 1);
-  else ws_role_aux<Cfg>(xch, d, a, g0, in_range, n, pd);
+  else {  // forward sweep: their own roles; backward sweep (latency regime): the two density producers, one copy of the code
+    if (warp == 1) ws_role_dens<Cfg, !PHYMB>(W, tiles, xch, d, a, g0, a.G - 1);
+    else ws_role_aux<Cfg, !PHYMB>(xch, d, a, g0, in_range, n, pd);
+    if constexpr (PHYMB) ws_densaux_bwd<Cfg>(W, tiles, xch, d, a, g0, a.G - 1, warp == 3 ? 1 : 0);
+  }
 }
 
 }  // namespace sde4
