@@ -494,7 +494,30 @@ struct MmaNet {
         else c2[n][r] = act_fwd<N::ACT>(c2[n][r]);
       }
     }
-    {
+    if constexpr (N::OUT == 1) {
+      // scalar output (the density network): an FP32 dot product over the thread's own columns and two butterfly rounds
+      // over the quad instead of NT2 k-steps of three dependent MMAs for one useful column in eight -- ~100 instead of
+      // ~500 cycles on the chain of the forward sweep, where this network is the last arriver of every step.
+      // Every thread of the quad ends up with the value of rows g (out[0]) and g + 8 (out[2]).
+      float s0a = 0.0f, s0b = 0.0f, s1a = 0.0f, s1b = 0.0f;
+#pragma unroll
+      for (int n = 0; n < NT2; ++n) {
+        const float2 v = *reinterpret_cast<const float2*>(w + N::OFF_W2 + 8 * n + 2 * t);
+        s0a = fmaf(c2[n][0], v.x, s0a);
+        s0b = fmaf(c2[n][1], v.y, s0b);
+        s1a = fmaf(c2[n][2], v.x, s1a);
+        s1b = fmaf(c2[n][3], v.y, s1b);
+      }
+      float s0 = s0a + s0b, s1 = s1a + s1b;
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+      const float b2 = w[N::OFF_B2];
+      out[0] = s0 + b2;
+      out[2] = s1 + b2;
+      out[1] = out[3] = 0.0f;
+    } else {
       AccT<FAST> acc;
       acc.init(2 * t < N::OUT ? w[N::OFF_B2 + 2 * t] : 0.0f, 2 * t + 1 < N::OUT ? w[N::OFF_B2 + 2 * t + 1] : 0.0f);
 #pragma unroll
@@ -1000,8 +1023,8 @@ SDE4_DEV void ws_role_dens(const float* W, const float4* tiles, float* xch, cons
     a_from_xch<NPART>(xch, Cfg::X_Z, NZ, lane, ident, az);
     float d1[MD::NT1][4], d2[MD::NT2][4];
     MD::template fwd<false, SDE4_WS_FAST_FWD>(tD, wD, lane, az, out, d1, d2);
-    // density of rows g, g+8 sits in column 0 (threads with t == 0): hand it to the quad, thread t forms eta_t, eta_{t+4}
-    const float dg = __shfl_sync(0xffffffffu, out[0], lane & ~3), dg8 = __shfl_sync(0xffffffffu, out[2], lane & ~3);
+    // density of rows g, g+8: thread t of the quad forms eta_t, eta_{t+4}
+    const float dg = out[0], dg8 = out[2];  // (the scalar-output layer leaves the value with every thread of the quad)
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int k = t + 4 * q;
