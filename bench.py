@@ -778,7 +778,7 @@ def main():
             pass
         roof = {"bound": "fp32", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "hbm_view": hbm_view,
-                "traffic": 2756864, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_cost_ws launch, profiles/r2_f_ws_final_ncu.txt (checkpoints stay in L2)", "peak_source": "measured in this run by sde4_fma_peak (FFMA / fma.rn.f32x2 loop)",
+                "traffic": 3342080, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_cost_ws launch, profiles/r2_h_ws_final_ncu.txt (checkpoints stay in L2)", "peak_source": "measured in this run by sde4_fma_peak (FFMA / fma.rn.f32x2 loop)",
                 "peaks_tflops": peaks, "kernel_ms": k_ms,
                 "algorithmic_flop_per_launch": flop,
                 "note": "path is FP32-FMA bound (SURVEY 8d), not HBM/tensor; HBM write-out of this launch = %.1f MB"
