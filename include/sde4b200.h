@@ -293,7 +293,9 @@ int sde4_cost_grad(const sde4_model_desc* model, const sde4_cost_args* args, voi
  * `staging_device`, evaluated, and [cost | grad] comes back with ONE copy (or, when the pinned buffer is mapped
  * into the device's address space -- unified addressing -- stored straight into it by the reduce kernel); the call returns after the
  * stream has been synchronised.  Both staging buffers are caller-owned and at least
- * sde4_cost_grad_host_staging_bytes() long. */
+ * sde4_cost_grad_host_staging_bytes() long.
+ * With `args->xgpu` (particles of the problem sharded over GPUs, see sde4_xgpu_reduce) `xgpu->out` is ignored: the last
+ * CTA of the reduce kernel writes the cross-GPU TOTAL into the staging buffer and `cost` / `grad` receive that total. */
 size_t sde4_cost_grad_host_staging_bytes(const sde4_model_desc* model, int32_t P, int32_t H, int32_t n_slack);
 int sde4_cost_grad_host(const sde4_model_desc* model, const sde4_cost_args* args, void* staging_pinned,
                         void* staging_device, size_t staging_bytes, void* stream);
