@@ -192,3 +192,31 @@ def test_gen_inst_emits_a_registration_for_an_edited_yaml(tmp_path):
     cfg.write_text(yaml.safe_dump({"model": pm}))
     r = subprocess.run([sys.executable, tool, "cartpole", str(cfg), "--out", str(out)], capture_output=True, text=True)
     assert r.returncode != 0 and "outside the compiled range" in (r.stderr + r.stdout)
+
+
+def test_bound_cost_declines_what_the_device_solver_does_not_cover():
+    """``multi_sampling.bind(...)`` (the closure apg.py is handed, as an object): ``solve_on_device`` must return None --
+    i.e. leave the solve to the host loop of apg.py -- for a configuration without line search, a proximal operator that
+    is not the box, and a state that is not a fresh ``init_apg`` state.  None of these reaches the GPU."""
+    import contextlib, io
+    import torch
+    from sde4mbrl_b200 import apg
+    H = 5
+    pm = configs.hexa_model(horizon=H, num_particles=2, stepsize=0.05)
+    mpc = configs.hexa_mpc(horizon=H, dt=0.05, num_particles=2, max_iter=3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        _, multi_cost, vprox, _, _ = nsde.create_online_cost_sampling_fn(pm, mpc, sde_constr=sde_models.SDERotorModel)
+    cp = mpc["cost_params"]
+    stage = costs.with_slew(costs.one_step_cost_f(cp, 6), cp, 6)
+    xref = np.zeros((H + 1, 13), np.float32)
+    cost_b = multi_cost.bind({}, np.zeros(13, np.float32), np.array([0, 1], np.uint32), stage, extra_cost_args=xref)
+    assert callable(cost_b) and hasattr(cost_b, "value_and_grad")
+    op = mpc["apg_mpc"]
+    x0 = torch.full((H, 6), 0.3)
+    st = apg.init_opt_state(x0, op)  # a fresh state (no cost evaluation)
+    no_ls = {k: v for k, v in op.items() if k != "linesearch"}
+    no_ls["stepsize"] = 0.01
+    assert cost_b.solve_on_device(st, no_ls, None) is None                       # no line search
+    assert cost_b.solve_on_device(st, op, lambda x, stepsize=None: x) is None    # a proximal operator that is not the box
+    assert cost_b.solve_on_device(st._replace(num_steps=4), op, vprox) is None   # in the middle of a solve
+    assert cost_b.solve_on_device(st._replace(xk=x0 + 1.0), op, vprox) is None   # xk != yk
