@@ -29,7 +29,14 @@ cudaError_t launch_cost_ws_t(const sde4_model_desc& d, const sde4_cost_desc& cd,
   const bool plain = cd.kind == SDE4_COST_ROTOR_TRACK && cd.sig_mask == 0 && !cd.use_res_sig;
   int sms = 148;
   if (dev < 0 || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-  const bool phymb = blocks <= 2 * sms;  // latency regime (see k_cost_ws)
+  static const int phymb_max = [] {
+    // CTAs per SM up to which the latency-regime kernel runs: one wave of up to three CTAs per SM is still bound by the chain of
+    // a step (speculative APG launches of 5-7 k samples: 2.80 -> 2.69 ms and 2.88 -> 2.76 ms per 20 iterations against the
+    // many-CTAs instantiation); from the second wave on the busiest role binds.  SDE4_WS_PHYMB_MAX overrides (tuning aid).
+    const char* e = std::getenv("SDE4_WS_PHYMB_MAX");
+    return e ? std::atoi(e) : 3;
+  }();
+  const bool phymb = blocks <= phymb_max * sms;  // latency regime (see k_cost_ws)
   // four CTAs per SM where that saves a wave of CTAs (up to two waves; beyond, three per SM have the higher throughput)
   static const int force_minb = [] {
     const char* e = std::getenv("SDE4_WS_MINB");  // tuning aid: 3 / 4 forces the instantiation

@@ -1267,7 +1267,7 @@ SDE4_DEV void ws_role_aux(float* xch, const sde4_model_desc& d, const CostK& a, 
 // scheduler is left with the busiest role of every resident CTA, ran 1.2x (16 k samples) to 1.75x (131 k samples) SLOWER --
 // 299 -> 354 us and 2.18 -> 3.80 ms, H = 20, scripts/ws_sizes.py -- three roles' loop bodies do not fit one L0 cache.)
 // Requirements checked by the launcher: value + gradient, in-kernel threefry noise, no state constraints.
-// PHYMB: where the residual-moment network of the FORWARD sweep runs.  With at most ~2 CTAs per SM the launch is bound by
+// PHYMB: where the residual-moment network of the FORWARD sweep runs.  With one wave of at most 3 CTAs per SM the launch is bound by
 // the dependent chain of a step and the PHY warp, idle while the networks run, takes it (true); with many CTAs per SM
 // every scheduler holds the same role of several CTAs, the launch is bound by the busiest ROLE, which is PHY, and the
 // network stays with the RES role (false).
